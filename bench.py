@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dynamic-embedding table hot path.
+
+Metric (BASELINE.json): embedding lookup+insert M keys/s at dim 64 on 1/2/4/8 B200, with the fraction of the
+HBM roofline.  Workload at N=1 = BASELINE.json configs[1]: an HKV-style table with 100M resident int64 keys,
+dim-64 fp32 rows, Zipf(alpha=1.05) id stream, 1,048,576 unique keys per step.
+
+One STEP = one pass of the hot path over one batch: Find (lookup) of the batch + Insert (upsert, the
+optimizer write-back) of the batch.  `value` = keys per second, every key looked up AND upserted once per step,
+inputs resident in HBM.  `e2e` = the same step through the host-buffer entry points of the plugin API
+(pinned HOST keys/values in, HOST rows out, PCIe copies inside the timed region).
+
+N>1 (launched by torchrun, one rank per GPU): the table is key-hash sharded (owner = (key & 0x7fffffff) % N,
+the reference's default_partition_fn); every rank keeps a 100M-key shard (weak scaling) and drives batches of
+keys owned by ANY rank: partition -> NCCL all-to-all of keys -> local find -> all-to-all of rows back, and
+keys+rows to their owners -> local insert.
+
+--impl reference : the reference's own CPU cuckoo path (oracle/_ref = its vendored libcuckoo compiled from
+/root/reference, else the C port) on the host cores, same metric, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 64
+ALPHA = 1.05
+KEY_SALT = 0x9E3779B97F4A7C15
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--resident", type=int, default=100_000_000, help="resident keys per GPU")
+  ap.add_argument("--batch", type=int, default=1 << 20, help="unique keys per step per GPU")
+  ap.add_argument("--dim", type=int, default=DIM)
+  ap.add_argument("--cpu-resident", type=int, default=1 << 24, help="resident keys of the CPU-baseline sample")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--e2e-steps", type=int, default=5)
+  return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic Criteo-shaped id stream: rank ~ Zipf(1.05) over the vocabulary, key = fmix64(rank+salt)
+# ------------------------------------------------------------------------------------------------
+def fmix64_np(x):
+  x = x.astype(np.uint64)
+  x ^= x >> np.uint64(33)
+  x *= np.uint64(0xff51afd7ed558ccd)
+  x ^= x >> np.uint64(33)
+  x *= np.uint64(0xc4ceb9fe1a85ec53)
+  x ^= x >> np.uint64(33)
+  return x
+
+
+def rank_to_key_np(rank):
+  with np.errstate(over="ignore"):
+    k = fmix64_np(rank.astype(np.uint64) + np.uint64(KEY_SALT)) & np.uint64(0x7fffffffffffffff)
+  return k.astype(np.int64)
+
+
+def zipf_cdf_np(vocab):
+  w = np.arange(1, vocab + 1, dtype=np.float64) ** (-ALPHA)
+  c = np.cumsum(w)
+  return c / c[-1]
+
+
+def zipf_unique_batch_np(cdf, batch, rng):
+  """`batch` distinct ranks drawn Zipf(alpha) (duplicates of a draw are dropped, as tf.unique does before the
+  table is touched), in random order."""
+  got = np.zeros(0, dtype=np.int64)
+  while got.shape[0] < batch:
+    r = np.searchsorted(cdf, rng.random(2 * batch), side="left").astype(np.int64)
+    got = np.unique(np.concatenate([got, r]))
+  rng.shuffle(got)
+  return got[:batch]
+
+
+def torch_fmix64(x):
+  import torch
+  m1 = torch.tensor(-49064778989728563, dtype=torch.int64, device=x.device)
+  m2 = torch.tensor(-4265267296055464877, dtype=torch.int64, device=x.device)
+  s = lambda v: (v >> 33) & 0x7fffffff
+  x = x ^ s(x)
+  x = x * m1
+  x = x ^ s(x)
+  x = x * m2
+  x = x ^ s(x)
+  return x
+
+
+def rank_to_key_torch(rank):
+  import torch
+  salt = torch.tensor(KEY_SALT - (1 << 64), dtype=torch.int64, device=rank.device)
+  return torch_fmix64(rank + salt) & 0x7fffffffffffffff
+
+
+def zipf_cdf_torch(vocab, device):
+  import torch
+  c = torch.empty(vocab, dtype=torch.float64, device=device)
+  chunk = 1 << 26
+  carry = 0.0
+  for b in range(0, vocab, chunk):
+    e = min(vocab, b + chunk)
+    w = torch.arange(b + 1, e + 1, dtype=torch.float64, device=device).pow_(-ALPHA)
+    torch.cumsum(w, 0, out=c[b:e])
+    c[b:e] += carry
+    carry = float(c[e - 1])
+  c /= carry
+  return c
+
+
+def zipf_unique_batch_torch(cdf, batch, gen):
+  import torch
+  got = torch.zeros(0, dtype=torch.int64, device=cdf.device)
+  while got.numel() < batch:
+    u = torch.rand(2 * batch, dtype=torch.float64, device=cdf.device, generator=gen)
+    r = torch.searchsorted(cdf, u).clamp_(max=cdf.numel() - 1)
+    got = torch.unique(torch.cat([got, r]))
+  perm = torch.randperm(got.numel(), device=cdf.device, generator=gen)
+  return got[perm[:batch]]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own cuckoo path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(dim, resident, batch, steps, warmup):
+  from oracle import oracle as O
+  O.build()
+  threads = os.cpu_count() or 1
+  if O.have_ref():
+    table, kind = O.RefTable(dim, resident * 2, threads=threads), "reference"
+  else:
+    table, kind, threads = O.PortTable(dim, resident * 2), "port", 1
+  rng = np.random.default_rng(42)
+  cdf = zipf_cdf_np(resident)
+  fill = 1 << 20
+  fill_vals = rng.normal(0, 0.01, (fill, dim)).astype(np.float32)  # row content is irrelevant to the timing
+  for b in range(0, resident, fill):
+    r = np.arange(b, min(resident, b + fill), dtype=np.int64)
+    table.insert(rank_to_key_np(r), fill_vals[:r.shape[0]])
+  default = np.zeros(dim, np.float32)
+  vals = rng.normal(0, 0.01, (batch, dim)).astype(np.float32)
+  out = np.zeros((batch, dim), np.float32)  # reused output buffer (TF's allocator pools outputs as well)
+  times_find, times_ins = [], []
+  for it in range(warmup + steps):
+    keys = rank_to_key_np(zipf_unique_batch_np(cdf, batch, rng))
+    t0 = time.perf_counter()
+    table.find(keys, default, out=out)
+    t1 = time.perf_counter()
+    table.insert(keys, vals)
+    t2 = time.perf_counter()
+    if it >= warmup:
+      times_find.append(t1 - t0)
+      times_ins.append(t2 - t1)
+  tf, ti = float(np.mean(times_find)), float(np.mean(times_ins))
+  table.close()
+  return {
+      "value": batch / (tf + ti) / 1e6, "unit": "M keys/s", "cores": threads, "kind": kind,
+      "sample": "resident %d keys (of the GPU arm's %s), dim %d, batch %d unique Zipf(%.2f) keys, %d timed steps "
+                "of find+insert; find %.1f M keys/s, insert %.1f M keys/s" %
+                (resident, "100M", dim, batch, ALPHA, steps, batch / tf / 1e6, batch / ti / 1e6),
+      "ms_per_step": (tf + ti) * 1e3,
+  }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.idx = gpu_index
+    self.samples = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True)
+      self.th = threading.Thread(target=self._read, daemon=True)
+      self.th.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.samples.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.25)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in self.samples:
+      f = [x.strip() for x in s.split(",")]
+      if len(f) < 8:
+        continue
+      try:
+        sm.append(float(f[1]))
+        mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for nme, v in zip(names, f[4:8]):
+        if v.lower().startswith("active"):
+          reasons.add(nme)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  try:
+    with open(p) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  except Exception:
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+  import torch
+  import torch.distributed as dist
+  from recommenders_addons_b200 import dynamic_embedding as de
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  dim, B, resident = args.dim, args.batch, args.resident
+  free = torch.cuda.mem_get_info()[0]
+  while 2 * resident * (8 + dim * 4) * 1.1 + (12 << 30) > free and resident > (1 << 20):
+    resident //= 2  # smaller GPU than a B200: shrink and say so in config
+  vocab = resident * world
+
+  gen = torch.Generator(device=dev).manual_seed(42 + rank)
+  gen_v = torch.Generator(device=dev).manual_seed(43 + rank)
+  var = de.Variable(dim=dim, init_size=2 * resident, initializer=0.0, name="bench_table",
+                    kv_creator=de.HkvHashTableCreator(de.HkvHashTableConfig(init_capacity=2 * resident,
+                                                                             max_capacity=2 * resident)))
+  table = var.tables[0]
+  # ---- prefill this rank's shard: all ranks r of the vocabulary with owner(key(r)) == rank --------------
+  chunk = 1 << 20
+  for b in range(0, vocab, chunk):
+    r = torch.arange(b, min(vocab, b + chunk), dtype=torch.int64, device=dev)
+    k = rank_to_key_torch(r)
+    if world > 1:
+      k = k[de.default_partition_fn(k, world, True) == rank]
+    if k.numel():
+      table.insert(k, torch.randn(k.numel(), dim, device=dev, generator=gen_v) * 0.01)
+  local_size = int(table.size())
+  cdf = zipf_cdf_torch(vocab, dev)
+  n_batches = args.steps + args.warmup
+  key_batches = [rank_to_key_torch(zipf_unique_batch_torch(cdf, B, gen)) for _ in range(n_batches)]
+  del cdf
+  new_vals = torch.randn(B, dim, device=dev, generator=gen_v) * 0.01
+  default = torch.zeros(dim, device=dev)
+  out = torch.empty(B, dim, device=dev)
+  sharded = de.ShardedVariable(var) if world > 1 else None
+
+  def step(i, ev=None):
+    k = key_batches[i]
+    if sharded is None:
+      if ev:
+        ev[0].record()
+      rows = table.lookup(k, dynamic_default_values=default)
+      if ev:
+        ev[1].record()
+      table.insert(k, new_vals)
+      if ev:
+        ev[2].record()
+      return rows
+    if ev:
+      ev[0].record()
+    rows = sharded.lookup(k)
+    if ev:
+      ev[1].record()
+    sharded.upsert(k, new_vals)
+    if ev:
+      ev[2].record()
+    return rows
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for i in range(args.warmup):
+    step(i)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+  t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  t_start.record()
+  for s in range(args.steps):
+    step(args.warmup + s, evs[s])
+  t_end.record()
+  barrier()
+  clocks = sampler.stop() if rank == 0 else None
+  total_ms = t_start.elapsed_time(t_end)
+  find_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+  ins_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+  tt = torch.tensor([total_ms, find_ms, ins_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  total_ms, find_ms_max, ins_ms_max = [float(x) for x in tt.tolist()]
+  ms_per_step = total_ms / args.steps
+  value = world * B / (ms_per_step * 1e-3) / 1e6
+
+  # ---- e2e through the host-buffer plugin API (N=1: table ops on pinned host tensors) -------------------
+  e2e = None
+  if not args.no_e2e:
+    n_e2e = max(1, min(args.e2e_steps, args.steps))
+    hk = [key_batches[args.warmup + i].cpu().pin_memory() for i in range(n_e2e)]
+    hv = new_vals.cpu().pin_memory()
+    hd = default.cpu().pin_memory()
+    ho = torch.empty(B, dim).pin_memory()
+    if sharded is None:
+      def e2e_step(i):
+        table.lookup_host(hk[i], hd, ho)
+        table.insert_host(hk[i], hv)
+    else:
+      def e2e_step(i):
+        k = hk[i].to(dev, non_blocking=True)
+        v = hv.to(dev, non_blocking=True)
+        rows = sharded.lookup(k)
+        ho.copy_(rows, non_blocking=True)
+        sharded.upsert(k, v)
+        torch.cuda.synchronize()
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+      e2e_step(i)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * B * n_e2e / float(dt.item()) / 1e6, "unit": "M keys/s",
+           "h2d_bytes_per_step": int(B * (8 + 8 + dim * 4) + dim * 4), "d2h_bytes_per_step": int(B * dim * 4),
+           "steps": n_e2e,
+           "api": "CuckooHashTable.lookup_host + insert_host (det_find_host / det_insert_host), pinned host buffers"
+                  if sharded is None else "ShardedVariable.lookup/upsert with pinned H2D/D2H copies"}
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+  peak, peak_src = measured_peak_gbs()
+  find_ms_1 = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+  algo_bytes = B * dim * 4  # north_star roofline: keys x dim x 4 B per lookup launch
+  achieved = algo_bytes / (find_ms_1 * 1e-3) / 1e9
+  honest_bytes = B * (8 + 64 + 2 * dim * 4)  # key in + one 64 B bucket + row read + row written out
+  line = {
+      "metric": "embedding lookup+insert M keys/s at dim64", "value": value, "unit": "M keys/s", "n_gpus": world,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "int64 keys / f32 rows (copy; no arithmetic)",
+      "data": "synthetic",
+      "config": {
+          "workload": "BASELINE configs[1]: HKV-style table, %d resident keys/GPU, dim %d fp32, Zipf(%.2f) ids, "
+                      "%d unique keys/step/GPU; step = Find(batch) + Insert(batch)" % (resident, dim, ALPHA, B),
+          "resident_keys_per_gpu": local_size, "capacity_slots": table.capacity(), "batch": B, "dim": dim,
+          "l2": "inputs larger than L2: every step touches a different batch (%.0f MB of rows + %.0f MB out + %.0f MB "
+                "in) of a %.1f GB table; the Zipf head is hot by design" %
+                (B * dim * 4 / 1e6, B * dim * 4 / 1e6, B * dim * 4 / 1e6, table.stats()["hbm_bytes"] / 1e9),
+          "parallelism": "key-hash sharded x%d, NCCL all-to-all of keys and rows" % world if world > 1 else "single GPU",
+      },
+      "find_ms": find_ms_max, "insert_ms": ins_ms_max,
+      "find_Mkeys_s": world * B / (find_ms_max * 1e-3) / 1e6, "insert_Mkeys_s": world * B / (ins_ms_max * 1e-3) / 1e6,
+      "gpu_launches": (2 if world == 1 else 10) * args.steps,
+      "clocks": clocks,
+      "roofline": {
+          "bound": "hbm", "kernel": "det::find_kernel<16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+          "algorithmic_bytes_per_launch": algo_bytes,
+          "note": "algorithmic = keys x dim x 4 B (north_star definition); the kernel necessarily also moves the "
+                  "gathered rows out (+%d B/key) and one 64 B bucket + 8 B key per probe: honest-traffic rate %.0f GB/s "
+                  "(%.2f of peak)" % (dim * 4, honest_bytes / (find_ms_1 * 1e-3) / 1e9,
+                                      honest_bytes / (find_ms_1 * 1e-3) / 1e9 / peak),
+      },
+  }
+  if e2e:
+    line["e2e"] = e2e
+  if world == 1 and not args.no_cpu_baseline:
+    try:
+      cb = cpu_arm(dim, args.cpu_resident, B, steps=3, warmup=1)
+      cb.pop("ms_per_step", None)
+      line["cpu_baseline"] = cb
+    except Exception as ex:  # the checker is optional for the bench line; never hide the GPU number
+      line["cpu_baseline"] = {"value": None, "unit": "M keys/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def reference_arm(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  steps = max(1, min(args.steps, 5))
+  warm = max(1, min(args.warmup, 2))
+  cb = cpu_arm(args.dim, args.cpu_resident, args.batch, steps=steps, warmup=warm)
+  ms = cb.pop("ms_per_step")
+  line = {
+      "impl": "reference", "metric": "embedding lookup+insert M keys/s at dim64", "value": cb["value"],
+      "unit": "M keys/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "int64 keys / f32 rows (copy; no arithmetic)", "data": "synthetic",
+      "config": {"workload": "BASELINE configs[1] on the reference's CPU cuckoo path (TableWrapperOptimized over "
+                             "libcuckoo), bounded sample: " + cb["sample"], "batch": args.batch, "dim": args.dim},
+      "cpu_baseline": cb,
+      "e2e": {"value": cb["value"], "unit": "M keys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+if __name__ == "__main__":
+  a = parse_args()
+  if a.impl == "reference":
+    reference_arm(a)
+  else:
+    gpu_arm(a)

@@ -1,0 +1,212 @@
+/* include/detable.h -- C ABI of the B200-native dynamic-embedding table engine.
+ *
+ * This is the drop-in boundary for the ONE hot path this repo accelerates: the
+ * `tfra.dynamic_embedding` table path of tensorflow/recommenders-addons.  Each entry point
+ * replaces one method of the reference's table objects, i.e. what the TF custom-op kernels
+ * `TFRA>CuckooHashTable*` / `TFRA>HkvHashTable*` call after unpacking their tensors.
+ * Reference paths below are relative to
+ *   /root/reference/tensorflow_recommenders_addons/dynamic_embedding/core/
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / TF types.  `det_stream_t` is a `cudaStream_t`.
+ *   - unless a parameter says HOST, every data pointer is a DEVICE pointer on the table's GPU.
+ *   - every call is asynchronous on the caller's stream and never synchronises, except:
+ *       det_size / det_export (return a count to the host), the *_host entry points, and a
+ *       mutating call that has to GROW the table (rare; see DESIGN.md "capacity").
+ *   - return value: DET_OK or an error code; det_last_error() gives the message of the last
+ *     failing call on the calling thread (mirrors OP_REQUIRES_OK(ctx, Status),
+ *     kernels/cuckoo_hashtable_op.cc:601-604; HKV exceptions -> Status(kInternal),
+ *     kernels/lookup_impl/lookup_table_op_hkv.h:54-60).
+ *   - keys are int64 (the only key type the reference registers on GPU,
+ *     kernels/hkv_hashtable_op_gpu.cu.cc:1133-1138); ALL 2^64 key values are legal.
+ *   - rows are `dim` elements of `value_dtype`, contiguous, row-major [n, dim].
+ *   - keys inside ONE mutating call must be unique (same contract as the reference's GPU
+ *     table, python/ops/dynamic_embedding_variable.py:1377-1378).  Duplicates are memory-safe:
+ *     the key is stored once; insert keeps one of the rows per 16-byte chunk, accum adds all.
+ */
+#ifndef DETABLE_H_
+#define DETABLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct det_table det_table;
+typedef void* det_stream_t; /* cudaStream_t */
+typedef int det_status;
+
+enum {
+  DET_OK = 0,
+  DET_INVALID_ARGUMENT = 1, /* errors::InvalidArgument */
+  DET_OUT_OF_MEMORY = 2,    /* "...adjust param 'max_hbm' smaller", lookup_table_op_hkv.h:364-368 */
+  DET_CUDA_ERROR = 3,       /* CUDA_CHECK */
+  DET_TABLE_FULL = 4,       /* max_capacity reached */
+  DET_UNIMPLEMENTED = 5,
+  DET_INTERNAL = 6,
+  DET_IO_ERROR = 7
+};
+
+/* value dtypes the reference registers for its GPU table (hkv_hashtable_op_gpu.cu.cc:1133-1138) */
+enum {
+  DET_FLOAT32 = 0,
+  DET_FLOAT16 = 1,
+  DET_BFLOAT16 = 2,
+  DET_INT32 = 3,
+  DET_INT64 = 4,
+  DET_INT8 = 5,
+  DET_FLOAT64 = 6
+};
+
+/* combiner of embedding_lookup_sparse (python/ops/dynamic_embedding_ops.py:205-206) */
+enum { DET_COMBINER_SUM = 0, DET_COMBINER_MEAN = 1, DET_COMBINER_SQRTN = 2 };
+
+/* Attributes of the table-creating ops:
+ *   CuckooHashTableOfTensors: key_dtype, value_dtype, value_shape, init_size  (ops/cuckoo_hashtable_ops.cc:293-309)
+ *   HkvHashTableOfTensors:    + init_capacity, max_capacity, ...              (ops/hkv_hashtable_ops.cc:318-331) */
+typedef struct det_config {
+  int32_t value_dtype;      /* DET_FLOAT32 ... */
+  int32_t dim;              /* value_shape[0] */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t num_slot_planes;  /* 0..3 optimizer slot planes co-indexed with the value rows (fp32 only) */
+  uint64_t init_capacity;   /* keys; 0 -> 8192 (TF_HASHTABLE_INIT_SIZE default, cuckoo_hashtable_op.cc:199-205) */
+  uint64_t max_capacity;    /* keys; 0 -> grow without bound (cuckoo semantics); else DET_TABLE_FULL beyond it */
+  float max_load_factor;    /* 0 -> 0.75 */
+  uint32_t flags;           /* reserved, 0 */
+} det_config;
+
+/* ---- lifetime: HashTableOp::Compute / LookupOrCreate, kernels/cuckoo_hashtable_op.h:59-110 ---- */
+det_status det_table_create(det_table** out, const det_config* cfg);
+det_status det_table_destroy(det_table* t);
+const char* det_last_error(void);
+/* library/ABI probe used by the loaders */
+int det_abi_version(void);
+const char* det_build_info(void);
+
+/* ---- LookupInterface surface (kernels/cuckoo_hashtable_op.cc:211-308; GPU twin
+ *      kernels/hkv_hashtable_op_gpu.cu.cc:181-470) ---- */
+
+/* Find / FindWithExists (cuckoo_hashtable_op.cc:215-233; TableWrapperOptimized::find,
+ * kernels/lookup_impl/lookup_table_op_cpu.h:188-217).  A missing key yields the default row:
+ * defaults[i,:] if full_size_default else defaults[0,:] (is_full_default rule, :48-50).
+ * `exists` may be NULL.  Lookup never inserts. */
+det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* defaults,
+                    int full_size_default, void* values_out, uint8_t* exists, det_stream_t stream);
+
+/* Insert = insert_or_assign per key (cuckoo_hashtable_op.cc:235-266; lookup_table_op_cpu.h:165-171). */
+det_status det_insert(det_table* t, const int64_t* keys, const void* values, size_t n,
+                      det_stream_t stream);
+
+/* Accum = insert_or_accum (cuckoo_hashtable_op.cc:248-286; lib/cuckoo/cuckoohash_map.hh:620-633):
+ *   found & exists[i] -> row += values_or_deltas[i];  !found & !exists[i] -> insert row;  else no-op. */
+det_status det_accum(det_table* t, const int64_t* keys, const void* values_or_deltas,
+                     const uint8_t* exists, size_t n, det_stream_t stream);
+
+/* Remove (cuckoo_hashtable_op.cc:268-276): absent keys are ignored. */
+det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t stream);
+
+/* Clear (cuckoo_hashtable_op.cc:278-281). */
+det_status det_clear(det_table* t, det_stream_t stream);
+
+/* size() (cuckoo_hashtable_op.cc:213).  HOST out; synchronises `stream`. */
+det_status det_size(det_table* t, int64_t* size_out_host, det_stream_t stream);
+
+/* capacity in keys at the current allocation (lookup_table_op_hkv.h:750). No sync. */
+det_status det_capacity(det_table* t, uint64_t* capacity_out_host);
+
+/* Make room for `total_keys` keys without further growth (cuckoohash_map::reserve). May sync. */
+det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream);
+
+/* ExportValues (cuckoo_hashtable_op.cc:293-308): writes up to max_n (key,row) pairs in table order,
+ * *n_out_host = number written (HOST).  plane = 0 value rows, 1..num_slot_planes an optimizer slot
+ * plane (the reference keeps each slot in its own table `<var>/<opt>/<slot>`,
+ * python/ops/dynamic_embedding_optimizer.py:870-958).  Synchronises `stream`. */
+det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
+                      int64_t* n_out_host, det_stream_t stream);
+
+/* ImportValues = clear + insert (cuckoo_hashtable_op.cc:288-291). */
+det_status det_import(det_table* t, const int64_t* keys, const void* values, size_t n,
+                      det_stream_t stream);
+
+/* ---- fused entry points (replace chains of reference ops) ---- */
+
+/* tf.unique as used by embedding_lookup_sparse / embedding_lookup_unique
+ * (python/ops/dynamic_embedding_ops.py:224, :95): unique_out in first-occurrence order,
+ * idx_out[i] = position of ids[i] in unique_out, *n_unique_dev (DEVICE int64).
+ * workspace: det_unique_workspace_bytes(n) bytes of device scratch. */
+size_t det_unique_workspace_bytes(size_t n);
+det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t* idx_out,
+                      int64_t* n_unique_dev, void* workspace, size_t workspace_bytes,
+                      det_stream_t stream);
+
+/* embedding_lookup_sparse forward in ONE kernel (python/ops/dynamic_embedding_ops.py:219-291):
+ * out[b,:] = combine_{i in segment b} w_i * row(ids[i]); missing ids use `default_row` [dim]
+ * (broadcast default).  segment_ids are sorted ascending (canonical SparseTensor order);
+ * weights may be NULL (all 1).  Rows of `out` without ids are zero.  fp32 tables only. */
+det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* segment_ids,
+                             const float* weights, size_t nnz, size_t batch, int combiner,
+                             const float* default_row, float* out, det_stream_t stream);
+
+/* One DynamicEmbeddingOptimizer step on unique keys, fused (find param + find slot(s) -> dense
+ * rule -> upsert param + upsert slot(s); python/ops/dynamic_embedding_optimizer.py:161-204,
+ * python/ops/embedding_weights.py:434-444).  Missing keys start from init_param[dim]
+ * (or [n,dim] if full_size_init) and the slot initial value, then get inserted.
+ * Adagrad: a += g*g; p -= lr*g/(sqrt(a)+eps)   (eps = 0: TF1 AdagradOptimizer; 1e-7: Keras)
+ *   slot plane 1 = accumulator.
+ * Adam   : m += (g-m)(1-b1); v += (g*g-v)(1-b2); p -= m*alpha/(sqrt(v)+eps),
+ *   alpha = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller;  plane 1 = m, plane 2 = v. */
+det_status det_apply_adagrad(det_table* t, const int64_t* keys, const float* grads, size_t n,
+                             float lr, float epsilon, const float* init_param, int full_size_init,
+                             float init_accum, det_stream_t stream);
+det_status det_apply_adam(det_table* t, const int64_t* keys, const float* grads, size_t n,
+                          float alpha, float beta1, float beta2, float epsilon,
+                          const float* init_param, int full_size_init, det_stream_t stream);
+
+/* ---- HOST-buffer entry points (the op placed on host tensors; used for end-to-end timing):
+ * pinned or pageable HOST pointers; chunked H2D -> kernel -> D2H pipeline on internal streams;
+ * synchronous on return. ---- */
+det_status det_find_host(det_table* t, const int64_t* keys_host, size_t n, const void* defaults_host,
+                         int full_size_default, void* values_out_host, uint8_t* exists_host);
+det_status det_insert_host(det_table* t, const int64_t* keys_host, const void* values_host, size_t n);
+
+/* ---- key-hash sharding across GPUs (python/ops/dynamic_embedding_variable.py:165-197 default_partition_fn,
+ * python/ops/shadow_embedding_ops.py:397-447 alltoall exchange) ----
+ * Partition n keys into num_shards contiguous groups by owner = (key & 0x7fffffff) % S (gpu_mode)
+ * or floor-mod(key, S):  keys_out = keys grouped by owner (stable within a group),
+ * perm_out[j] = original position of keys_out[j], counts_out[s] = keys owned by shard s (DEVICE int64[S]).
+ * workspace: det_partition_workspace_bytes(n, S). */
+size_t det_partition_workspace_bytes(size_t n, int num_shards);
+det_status det_partition(const int64_t* keys, size_t n, int num_shards, int gpu_mode,
+                         int64_t* keys_out, int32_t* perm_out, int64_t* counts_out, void* workspace,
+                         size_t workspace_bytes, det_stream_t stream);
+/* rows_out[perm[j],:] = rows_in[j,:]  (dynamic_stitch of the returned rows) and its inverse
+ * rows_out[j,:] = rows_in[perm[j],:] (gather before sending values/grads to their owners). */
+det_status det_scatter_rows(const void* rows_in, const int32_t* perm, size_t n, size_t row_bytes,
+                            void* rows_out, det_stream_t stream);
+det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, size_t row_bytes,
+                           void* rows_out, det_stream_t stream);
+
+/* ---- file-system format of SaveToFileSystem / LoadFromFileSystem
+ * (cuckoo_hashtable_op.cc:310-504): raw little-endian `<prefix>-keys` (int64[n]) and
+ * `<prefix>-values` (V[n*dim]).  HOST paths; synchronous. ---- */
+det_status det_save(det_table* t, const char* prefix, size_t buffer_keys);
+det_status det_load(det_table* t, const char* prefix, size_t buffer_keys);
+
+/* introspection for tests / benches (HOST outs; synchronises) */
+typedef struct det_stats {
+  int64_t size;        /* live keys */
+  int64_t used_slots;  /* non-empty slots (live + tombstones) */
+  uint64_t capacity;   /* slots */
+  uint64_t buckets;
+  uint64_t hbm_bytes;  /* device bytes held by the table */
+  uint32_t error_flags;
+  uint32_t rehash_count;
+} det_stats;
+det_status det_get_stats(det_table* t, det_stats* out_host, det_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DETABLE_H_ */

@@ -71,7 +71,8 @@ class _CTable:
     self._h = None
 
   # -- op semantics of cuckoo_hashtable_op.cc:211-308 ------------------------------------
-  def find(self, keys, default, return_exists=False):
+  def find(self, keys, default, return_exists=False, out=None):
+    """`out` (optional, [n, dim] float32) is reused as the output buffer, like TF's pooled allocator."""
     keys = np.ascontiguousarray(keys, dtype=np.int64).reshape(-1)
     n = keys.shape[0]
     default = np.ascontiguousarray(default, dtype=np.float32)
@@ -79,7 +80,9 @@ class _CTable:
     full = int(default.size == n * self.dim)
     if not full:
       assert default.size >= self.dim, "default must hold at least one row"
-    out = np.empty((n, self.dim), dtype=np.float32)
+    if out is None:
+      out = np.empty((n, self.dim), dtype=np.float32)
+    assert out.dtype == np.float32 and out.size == n * self.dim and out.flags.c_contiguous
     exists = np.zeros(n, dtype=np.uint8)
     self._fn("find")(self._h, _ptr(keys, _c_i64p), n, _ptr(default, _c_f32p), full,
                      _ptr(out, _c_f32p), _ptr(exists, _c_u8p))

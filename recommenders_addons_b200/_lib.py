@@ -1,0 +1,93 @@
+"""ctypes binding of include/detable.h (the drop-in C ABI).  No torch types cross this boundary:
+only raw device/host pointers, sizes and a cudaStream_t."""
+import ctypes
+import os
+
+from . import build as _build
+
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_i = ctypes.c_int
+
+DET_OK = 0
+DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
+COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
+
+
+class DetConfig(ctypes.Structure):
+  _fields_ = [("value_dtype", ctypes.c_int32), ("dim", ctypes.c_int32), ("device", ctypes.c_int32),
+              ("num_slot_planes", ctypes.c_int32), ("init_capacity", ctypes.c_uint64),
+              ("max_capacity", ctypes.c_uint64), ("max_load_factor", ctypes.c_float),
+              ("flags", ctypes.c_uint32)]
+
+
+class DetStats(ctypes.Structure):
+  _fields_ = [("size", ctypes.c_int64), ("used_slots", ctypes.c_int64), ("capacity", ctypes.c_uint64),
+              ("buckets", ctypes.c_uint64), ("hbm_bytes", ctypes.c_uint64), ("error_flags", ctypes.c_uint32),
+              ("rehash_count", ctypes.c_uint32)]
+
+
+# name -> (restype, argtypes); must list EVERY function include/detable.h declares
+SIGNATURES = {
+    "det_table_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(DetConfig)]),
+    "det_table_destroy": (_i, [_vp]),
+    "det_last_error": (ctypes.c_char_p, []),
+    "det_abi_version": (_i, []),
+    "det_build_info": (ctypes.c_char_p, []),
+    "det_find": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
+    "det_insert": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "det_accum": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "det_remove": (_i, [_vp, _vp, _sz, _vp]),
+    "det_clear": (_i, [_vp, _vp]),
+    "det_size": (_i, [_vp, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "det_capacity": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    "det_reserve": (_i, [_vp, ctypes.c_uint64, _vp]),
+    "det_export": (_i, [_vp, _i, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "det_import": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "det_unique_workspace_bytes": (_sz, [_sz]),
+    "det_unique": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "det_lookup_sparse": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
+    "det_apply_adagrad": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, _vp, _i, ctypes.c_float, _vp]),
+    "det_apply_adam": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                            _vp, _i, _vp]),
+    "det_find_host": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "det_insert_host": (_i, [_vp, _vp, _vp, _sz]),
+    "det_partition_workspace_bytes": (_sz, [_sz, _i]),
+    "det_partition": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "det_scatter_rows": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "det_gather_rows": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "det_save": (_i, [_vp, ctypes.c_char_p, _sz]),
+    "det_load": (_i, [_vp, ctypes.c_char_p, _sz]),
+    "det_get_stats": (_i, [_vp, ctypes.POINTER(DetStats), _vp]),
+}
+
+_LIB = None
+
+
+class DetError(RuntimeError):
+  """Raised for a non-OK det_status (mirrors tf.errors.* raised through OP_REQUIRES_OK)."""
+
+  def __init__(self, code, msg):
+    super().__init__("detable status %d: %s" % (code, msg))
+    self.code = code
+
+
+def lib():
+  """Load libdetable.so (building it when sources are newer).  Fails loudly: there is no fallback."""
+  global _LIB
+  if _LIB is None:
+    path = _build.build()
+    if not os.path.exists(path):
+      raise RuntimeError("libdetable.so missing: the CUDA extension is required (no CPU fallback)")
+    l = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+      fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+      fn.restype = res
+      fn.argtypes = args
+    _LIB = l
+  return _LIB
+
+
+def check(status):
+  if status != DET_OK:
+    raise DetError(status, lib().det_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,61 @@
+"""Build the C-ABI CUDA library in-tree: recommenders_addons_b200/lib/libdetable.so (sm_100a only).
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box with
+the gpurun snapshot.  `python -m recommenders_addons_b200.build [--force]`.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIB_DIR, "libdetable.so")
+SOURCES = ["table.cu", "fused.cu", "host_api.cu"]
+HEADERS = ["common.cuh", "host.h", os.path.join("..", "..", "include", "detable.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",            # every fp32 mul/add rounds separately: bit-parity with the NumPy oracle
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def _nvcc():
+  for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+    if cand and os.path.exists(cand):
+      return cand
+  return None
+
+
+def needs_build():
+  if not os.path.exists(LIB):
+    return True
+  t = os.path.getmtime(LIB)
+  deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, h) for h in HEADERS]
+  return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+  if not force and not needs_build():
+    return LIB
+  nvcc = _nvcc()
+  if nvcc is None:
+    if os.path.exists(LIB):
+      return LIB  # GPU box without sources newer than the shipped library
+    raise RuntimeError("nvcc not found and no prebuilt libdetable.so")
+  os.makedirs(LIB_DIR, exist_ok=True)
+  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+      [os.path.join(CSRC, s) for s in SOURCES]
+  out = subprocess.run(cmd, capture_output=True, text=True)
+  if out.returncode != 0:
+    raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
+  if verbose:
+    print(out.stderr)
+  return LIB
+
+
+if __name__ == "__main__":
+  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,370 @@
+// common.cuh -- table layout in HBM and the warp-cooperative probe / row-move primitives shared by
+// every kernel of the engine (sm_100a).
+//
+// Layout (DESIGN.md "data layout"): struct-of-arrays, all planes co-indexed by SLOT:
+//   keys   : int64 [nb*8]            8-slot buckets = 64 B = two 32 B sectors, one DRAM burst
+//   values : V     [(nb*8+2)][dim]   row s belongs to slot s; 2 trailing rows serve the two key
+//                                    values that double as in-table sentinels (EMPTY/TOMB)
+//   slots_k: float [(nb*8+2)][dim]   optional optimizer planes (accumulator / m / v)
+// Probing: bucket b0 = mulhi64(fmix64(key), nb), linear over buckets.  A 4-lane subgroup owns one
+// key: each lane loads 16 B (2 keys) of the 64 B bucket, matches are found with __ballot_sync.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace det {
+
+constexpr int kBucket = 8;
+constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;  // INT64_MIN
+constexpr long long kTombKey = kEmptyKey + 1;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxPlanes = 4;  // plane 0 = values, 1..3 = optimizer slots
+
+enum : unsigned { kErrTableFull = 1u, kErrBadSegment = 2u };
+
+struct DevState {
+  unsigned long long size;       // live keys (including the two special keys)
+  unsigned long long used;       // non-EMPTY slots in the key plane (live + tombstones)
+  unsigned int special[2];       // presence of kEmptyKey / kTombKey as USER keys
+  unsigned int error;            // sticky error bits
+  unsigned int pad;
+  unsigned long long scratch[4]; // export cursor etc.
+};
+
+struct TableView {
+  long long* keys;
+  unsigned char* planes[kMaxPlanes];
+  unsigned long long nb;  // buckets
+  unsigned int row_bytes; // bytes per row in plane 0
+  unsigned int dim;
+  DevState* st;
+  __host__ __device__ unsigned long long capacity() const { return nb * kBucket; }
+};
+
+__host__ __device__ __forceinline__ unsigned long long fmix64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return k;
+}
+
+__device__ __forceinline__ unsigned long long bucket_of(long long key, unsigned long long nb) {
+  return __umul64hi(fmix64((unsigned long long)key), nb);
+}
+
+__device__ __forceinline__ bool is_special(long long key) { return key == kEmptyKey || key == kTombKey; }
+
+// ---- memory access flavours -----------------------------------------------------------------
+// L2-coherent 16 B load of two keys (mutating kernels: L1 may hold lines older than a peer's CAS)
+__device__ __forceinline__ longlong2 ld_keys_cg(const long long* p) {
+  longlong2 r;
+  asm volatile("ld.global.cg.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+// read-only path for kernels that do not mutate the key plane
+__device__ __forceinline__ longlong2 ld_keys_nc(const long long* p) {
+  longlong2 r;
+  asm volatile("ld.global.nc.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<16> { using type = int4; };
+template <> struct VecT<8> { using type = int2; };
+template <> struct VecT<4> { using type = int; };
+template <> struct VecT<2> { using type = short; };
+template <> struct VecT<1> { using type = char; };
+
+// streaming (no L1 allocation) row loads/stores
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type ld_row(const unsigned char* p) {
+  return *reinterpret_cast<const typename VecT<VEC>::type*>(p);
+}
+template <>
+__device__ __forceinline__ int4 ld_row<16>(const unsigned char* p) {
+  int4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+template <>
+__device__ __forceinline__ int2 ld_row<8>(const unsigned char* p) {
+  int2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_row(unsigned char* p, typename VecT<VEC>::type v) {
+  *reinterpret_cast<typename VecT<VEC>::type*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st_row<16>(unsigned char* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void st_row<8>(unsigned char* p, int2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y)
+               : "memory");
+}
+
+// ---- subgroup helpers -------------------------------------------------------------------------
+// Interleave the 4 ballot bits of my subgroup for "first key of the lane" (b0) and "second key"
+// (b1) into an 8-bit mask indexed by slot-in-bucket (lane l holds slots 2l and 2l+1).
+__device__ __forceinline__ unsigned mask8(unsigned b0, unsigned b1, int sg) {
+  unsigned a = (b0 >> (sg * 4)) & 0xFu, b = (b1 >> (sg * 4)) & 0xFu;
+  a = (a | (a << 2)) & 0x33u;
+  a = (a | (a << 1)) & 0x55u;
+  b = (b | (b << 2)) & 0x33u;
+  b = (b | (b << 1)) & 0x55u;
+  return a | (b << 1);
+}
+
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+  return __shfl_sync(kFull, v, src);
+}
+
+// Read-only probe of 32 keys (one per lane) by 8 four-lane subgroups, 4 rounds.
+// Returns, in lane j, the slot of key j or -1.  COHERENT selects L2-coherent key loads.
+template <bool COHERENT>
+__device__ __forceinline__ long long warp_find_slots(const TableView& t, long long mykey, bool valid,
+                                                     int lane) {
+  const int sg = lane >> 2, sl = lane & 3;
+  const unsigned long long nb = t.nb;
+  const bool special = is_special(mykey);
+  const unsigned long long myb = bucket_of(mykey, nb);
+  const bool probe_me = valid && !special;
+
+  long long keyr[4];
+  unsigned long long br[4];
+  bool actr[4];
+  longlong2 first[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int src = r * 8 + sg;
+    keyr[r] = shfl_ll(mykey, src);
+    br[r] = (unsigned long long)shfl_ll((long long)myb, src);
+    actr[r] = __shfl_sync(kFull, (int)probe_me, src) != 0;
+    first[r] = make_longlong2(kEmptyKey, kEmptyKey);
+    if (actr[r]) {
+      const long long* p = t.keys + br[r] * kBucket + sl * 2;
+      first[r] = COHERENT ? ld_keys_cg(p) : ld_keys_nc(p);
+    }
+  }
+  long long result = -1;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long key = keyr[r];
+    unsigned long long b = br[r];
+    bool active = actr[r];
+    long long found = -1;
+    unsigned long long probes = 0;
+    longlong2 kk = first[r];
+    while (__any_sync(kFull, active)) {
+      const unsigned bh0 = __ballot_sync(kFull, active && kk.x == key);
+      const unsigned bh1 = __ballot_sync(kFull, active && kk.y == key);
+      const unsigned be = __ballot_sync(kFull, active && (kk.x == kEmptyKey || kk.y == kEmptyKey));
+      if (active) {
+        const unsigned H = mask8(bh0, bh1, sg);
+        if (H) {
+          found = (long long)(b * kBucket) + (__ffs(H) - 1);
+          active = false;
+        } else if (((be >> (sg * 4)) & 0xFu) || ++probes >= nb) {
+          active = false;  // chain ends in a bucket that still has an EMPTY slot: key absent
+        } else {
+          b = (b + 1 == nb) ? 0 : b + 1;
+          const long long* p = t.keys + b * kBucket + sl * 2;
+          kk = COHERENT ? ld_keys_cg(p) : ld_keys_nc(p);
+        }
+      }
+    }
+    const long long v = shfl_ll(found, (lane & 7) * 4);
+    if ((lane >> 3) == r) result = v;
+  }
+  if (valid && special) {
+    const int idx = (mykey == kTombKey) ? 1 : 0;
+    const unsigned present = *((volatile unsigned*)&t.st->special[idx]);
+    result = present ? (long long)(nb * kBucket + idx) : -1;
+  }
+  return result;
+}
+
+// Find-or-claim probe used by every mutating kernel.  Lane j passes its key; `claim` says whether
+// an absent key may be inserted.  Returns the slot (or -1: absent and not claimed / table full) and
+// sets is_new when this call created the key.  new_from_empty counts claims that consumed an EMPTY
+// slot (as opposed to recycling a tombstone) for the `used` counter.
+__device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long long mykey, bool valid,
+                                                        bool claim, int lane, bool& is_new,
+                                                        bool& from_empty) {
+  const int sg = lane >> 2, sl = lane & 3;
+  const unsigned long long nb = t.nb;
+  const bool special = is_special(mykey);
+  const unsigned long long myb = bucket_of(mykey, nb);
+  const bool probe_me = valid && !special;
+
+  long long result = -1;
+  bool res_new = false, res_empty = false;
+#pragma unroll 1
+  for (int r = 0; r < 4; ++r) {
+    const int src = r * 8 + sg;
+    const long long key = shfl_ll(mykey, src);
+    const unsigned long long b0 = (unsigned long long)shfl_ll((long long)myb, src);
+    bool active = __shfl_sync(kFull, (int)probe_me, src) != 0;
+    const bool may_claim = __shfl_sync(kFull, (int)claim, src) != 0;
+    unsigned long long b = b0;
+    long long found = -1, first_free = -1;
+    bool ff_tomb = false, fnew = false, fempty = false;
+    unsigned long long probes = 0;
+    unsigned restarts = 0;
+    while (__any_sync(kFull, active)) {
+      longlong2 kk = make_longlong2(0, 0);
+      if (active) kk = ld_keys_cg(t.keys + b * kBucket + sl * 2);
+      const unsigned bh0 = __ballot_sync(kFull, active && kk.x == key);
+      const unsigned bh1 = __ballot_sync(kFull, active && kk.y == key);
+      const unsigned be0 = __ballot_sync(kFull, active && kk.x == kEmptyKey);
+      const unsigned be1 = __ballot_sync(kFull, active && kk.y == kEmptyKey);
+      const unsigned bt0 = __ballot_sync(kFull, active && kk.x == kTombKey);
+      const unsigned bt1 = __ballot_sync(kFull, active && kk.y == kTombKey);
+      bool want_cas = false;
+      if (active) {
+        const unsigned H = mask8(bh0, bh1, sg);
+        const unsigned E = mask8(be0, be1, sg);
+        const unsigned T = mask8(bt0, bt1, sg);
+        if (H) {
+          found = (long long)(b * kBucket) + (__ffs(H) - 1);
+          active = false;
+        } else {
+          const unsigned F = E | T;
+          if (first_free < 0 && F) {
+            const int f = __ffs(F) - 1;
+            first_free = (long long)(b * kBucket) + f;
+            ff_tomb = ((T >> f) & 1u) != 0;
+          }
+          ++probes;
+          if (E || probes >= nb) {
+            // end of the probe chain: the key is absent
+            if (!may_claim) {
+              active = false;
+            } else if (first_free < 0) {
+              atomicOr(&t.st->error, kErrTableFull);
+              active = false;
+            } else {
+              want_cas = true;
+            }
+          } else {
+            b = (b + 1 == nb) ? 0 : b + 1;
+          }
+        }
+      }
+      long long old = 0;
+      const long long expect = ff_tomb ? kTombKey : kEmptyKey;
+      if (want_cas && sl == 0) {
+        old = (long long)atomicCAS((unsigned long long*)(t.keys + first_free), (unsigned long long)expect,
+                                   (unsigned long long)key);
+      }
+      old = shfl_ll(old, sg * 4);
+      if (want_cas) {
+        if (old == expect) {
+          found = first_free;
+          fnew = true;
+          fempty = !ff_tomb;
+          active = false;
+        } else if (old == key) {
+          found = first_free;  // a duplicate of this key in the same batch won the race
+          active = false;
+        } else {
+          // slot taken by another key meanwhile: rescan the chain from its start
+          b = b0;
+          first_free = -1;
+          ff_tomb = false;
+          probes = 0;
+          if (++restarts > 1024u) {
+            atomicOr(&t.st->error, kErrTableFull);
+            active = false;
+          }
+        }
+      }
+    }
+    const long long v = shfl_ll(found, (lane & 7) * 4);
+    const int vn = __shfl_sync(kFull, (int)fnew | ((int)fempty << 1), (lane & 7) * 4);
+    if ((lane >> 3) == r) {
+      result = v;
+      res_new = (vn & 1) != 0;
+      res_empty = (vn & 2) != 0;
+    }
+  }
+  if (valid && special) {
+    const int idx = (mykey == kTombKey) ? 1 : 0;
+    const long long s = (long long)(nb * kBucket + idx);
+    if (claim) {
+      const unsigned old = atomicExch(&t.st->special[idx], 1u);
+      result = s;
+      res_new = (old == 0);
+      res_empty = false;
+    } else {
+      const unsigned present = *((volatile unsigned*)&t.st->special[idx]);
+      result = present ? s : -1;
+    }
+  }
+  is_new = res_new;
+  from_empty = res_empty;
+  return result;
+}
+
+// ---- warp-cooperative row movement ---------------------------------------------------------------
+// Geometry of a row in VEC-byte vectors: vpr vectors per row, lpr = lanes per row (power of two,
+// <= 32), so a warp moves 32/lpr rows per step.
+struct RowGeom {
+  unsigned row_bytes;
+  unsigned vpr;        // vectors per row
+  unsigned lpr;        // lanes per row (pow2)
+  unsigned lpr_shift;  // log2(lpr)
+};
+
+// For each of the warp's 32 items (item j held by lane j): copy one row from src_j to dst_j.
+// Lane j provides its row's src/dst pointers (nullptr src or dst = skip).
+template <int VEC>
+__device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned char* my_src,
+                                               unsigned char* my_dst, int lane) {
+  using V = typename VecT<VEC>::type;
+  const unsigned rows_per_step = 32u >> g.lpr_shift;
+  const unsigned sub = (unsigned)lane >> g.lpr_shift;        // which row of the step
+  const unsigned c0 = (unsigned)lane & (g.lpr - 1u);          // first vector of the lane
+  if (g.vpr == g.lpr) {
+    // fast path: exactly one vector per lane per row; 4 rows in flight per lane
+    for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step * 4u) {
+      const unsigned char* s[4];
+      unsigned char* d[4];
+      V v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned j = j0 + u * rows_per_step + sub;
+        const unsigned jj = j & 31u;
+        s[u] = (const unsigned char*)shfl_ll((long long)my_src, jj);
+        d[u] = (unsigned char*)shfl_ll((long long)my_dst, jj);
+        if (j >= 32u) s[u] = nullptr;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (s[u] && d[u]) v[u] = ld_row<VEC>(s[u] + c0 * VEC);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (s[u] && d[u]) st_row<VEC>(d[u] + c0 * VEC, v[u]);
+    }
+  } else {
+    for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step) {
+      const unsigned j = j0 + sub;
+      const unsigned char* s = (const unsigned char*)shfl_ll((long long)my_src, j & 31u);
+      unsigned char* d = (unsigned char*)shfl_ll((long long)my_dst, j & 31u);
+      if (s && d) {
+        for (unsigned c = c0; c < g.vpr; c += g.lpr) st_row<VEC>(d + c * VEC, ld_row<VEC>(s + c * VEC));
+      }
+    }
+  }
+}
+
+}  // namespace det

@@ -1,0 +1,711 @@
+// fused.cu -- kernels that replace CHAINS of reference ops on the hot path:
+//   K6  det_lookup_sparse   unique -> find -> gather*weights -> segment_sum -> normalise
+//                           (python/ops/dynamic_embedding_ops.py:219-291)
+//   K7  det_apply_adagrad / det_apply_adam
+//                           find(param)+find(slots) -> dense rule -> upsert(param)+upsert(slots)
+//                           (python/ops/dynamic_embedding_optimizer.py:161-204)
+//   K8  det_partition / det_gather_rows / det_scatter_rows
+//                           default_partition_fn + dynamic_partition / dynamic_stitch
+//                           (python/ops/dynamic_embedding_variable.py:131-197)
+//       det_unique          tf.unique, first-occurrence order
+// Compiled with --fmad=false: every fp32 multiply and add rounds separately, so results are
+// bit-identical to the NumPy restatement in oracle/oracle.py.
+#include "host.h"
+
+namespace det {
+
+constexpr int kThreadsF = 256;
+
+// ------------------------------------------------------------------------------------------------
+// generic exclusive scan of uint32 flags (n up to 2^32) : block sums -> single-block scan -> apply
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 1024;
+
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s_warp, unsigned& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(kFull, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned ws = s_warp[lane];
+    unsigned xs = ws;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(kFull, xs, o);
+      if (lane >= o) xs += y;
+    }
+    s_warp[lane] = xs - ws;
+    if (lane == 31) s_warp[32] = xs;
+  }
+  __syncthreads();
+  const unsigned excl = s_warp[w] + x - v;
+  total = s_warp[32];
+  __syncthreads();
+  return excl;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+scan_block_sums_kernel(const unsigned* __restrict__ flags, size_t n, unsigned* __restrict__ block_sums) {
+  __shared__ unsigned s_warp[33];
+  const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
+  unsigned total;
+  block_exclusive_scan(i < n ? flags[i] : 0u, s_warp, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of block sums (64-bit carry), total -> *total_out
+__global__ void __launch_bounds__(kScanBlock)
+scan_sums_kernel(unsigned* __restrict__ block_sums, size_t nblocks, long long* __restrict__ total_out) {
+  __shared__ unsigned s_warp[33];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < nblocks; base += kScanBlock) {
+    const size_t i = base + threadIdx.x;
+    const unsigned v = i < nblocks ? block_sums[i] : 0u;
+    unsigned total;
+    const unsigned excl = block_exclusive_scan(v, s_warp, total);
+    const unsigned long long carry = s_carry;
+    if (i < nblocks) block_sums[i] = (unsigned)(carry + excl);
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = (long long)s_carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// det_unique
+// ------------------------------------------------------------------------------------------------
+struct UniqueWs {
+  long long* hkeys;     // [hcap]
+  unsigned* hmin;       // [hcap] min position of the key, later its rank
+  unsigned* myslot;     // [n]
+  unsigned* flags;      // [n]
+  unsigned* block_sums; // [nblocks]
+  unsigned* special;    // [2]: min position / rank of the key equal to the scratch sentinel
+  size_t hcap;          // power of two
+};
+
+static size_t unique_hcap(size_t n) {
+  size_t c = 64;
+  while (c < 2 * n) c <<= 1;
+  return c;
+}
+
+__global__ void unique_init_kernel(UniqueWs w) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < w.hcap; i += (size_t)gridDim.x * blockDim.x) {
+    w.hkeys[i] = kEmptyKey;
+    w.hmin[i] = 0xffffffffu;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 2) w.special[threadIdx.x] = 0xffffffffu;
+}
+
+__global__ void unique_insert_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long key = ids[i];
+  if (key == kEmptyKey) {
+    atomicMin(&w.special[0], (unsigned)i);
+    w.myslot[i] = 0xffffffffu;
+    return;
+  }
+  size_t s = fmix64((unsigned long long)key) & (w.hcap - 1);
+  while (true) {
+    const long long old = (long long)atomicCAS((unsigned long long*)(w.hkeys + s), (unsigned long long)kEmptyKey,
+                                               (unsigned long long)key);
+    if (old == kEmptyKey || old == key) {
+      atomicMin(&w.hmin[s], (unsigned)i);
+      w.myslot[i] = (unsigned)s;
+      return;
+    }
+    s = (s + 1) & (w.hcap - 1);
+  }
+}
+
+__global__ void unique_flag_kernel(UniqueWs w, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned s = w.myslot[i];
+  const unsigned first = (s == 0xffffffffu) ? w.special[0] : w.hmin[s];
+  w.flags[i] = (first == (unsigned)i) ? 1u : 0u;
+}
+
+// first occurrences: rank = exclusive scan; write unique_out[rank], remember rank in the hash slot
+__global__ void __launch_bounds__(kScanBlock)
+unique_rank_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n, long long* __restrict__ unique_out) {
+  __shared__ unsigned s_warp[33];
+  const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const unsigned f = i < n ? w.flags[i] : 0u;
+  unsigned total;
+  const unsigned excl = block_exclusive_scan(f, s_warp, total);
+  if (i < n && f) {
+    const unsigned rank = w.block_sums[blockIdx.x] + excl;
+    unique_out[rank] = ids[i];
+    const unsigned s = w.myslot[i];
+    if (s == 0xffffffffu) w.special[1] = rank; else w.hmin[s] = rank;
+  }
+}
+
+__global__ void unique_idx_kernel(UniqueWs w, size_t n, int* __restrict__ idx_out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned s = w.myslot[i];
+  idx_out[i] = (int)((s == 0xffffffffu) ? w.special[1] : w.hmin[s]);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t unique_ws_layout(size_t n, unsigned char* base, UniqueWs* w) {
+  const size_t hcap = unique_hcap(n);
+  const size_t nblocks = (n + kScanBlock - 1) / kScanBlock;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  long long* hkeys = (long long*)take(hcap * 8);
+  unsigned* hmin = (unsigned*)take(hcap * 4);
+  unsigned* myslot = (unsigned*)take(n * 4);
+  unsigned* flags = (unsigned*)take(n * 4);
+  unsigned* bs = (unsigned*)take((nblocks + 1) * 4);
+  unsigned* sp = (unsigned*)take(16);
+  if (w) {
+    w->hkeys = hkeys; w->hmin = hmin; w->myslot = myslot; w->flags = flags;
+    w->block_sums = bs; w->special = sp; w->hcap = hcap;
+  }
+  return off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: fused embedding_lookup_sparse
+// ------------------------------------------------------------------------------------------------
+// seg_start[b] = first position i with segment_ids[i] >= b ; seg_start[batch] = nnz
+__global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, size_t batch,
+                                       long long* __restrict__ seg_start, DevState* st) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nnz) return;
+  const long long cur = i < nnz ? (long long)seg[i] : (long long)batch;
+  const long long prev = i > 0 ? (long long)seg[i - 1] : -1;
+  if (cur < prev || cur < 0 || cur > (long long)batch || (i < nnz && cur >= (long long)batch)) {
+    atomicOr(&st->error, kErrBadSegment);
+    return;
+  }
+  for (long long b = prev + 1; b <= cur; ++b) seg_start[b] = (long long)i;
+}
+
+// probe by the first 4 lanes of a lane-group (group size >= 4, aligned); every lane of the group
+// gets the slot
+__device__ __forceinline__ long long group_find_slot(const TableView& t, long long key, bool act, int gbase,
+                                                     int gl) {
+  const bool special = is_special(key);
+  bool active = act && !special;
+  const unsigned long long nb = t.nb;
+  unsigned long long b = bucket_of(key, nb);
+  long long found = -1;
+  unsigned long long probes = 0;
+  const int sg = gbase >> 2;
+  while (__any_sync(kFull, active)) {
+    const bool ld = active && gl < 4;
+    longlong2 kk = make_longlong2(0, 0);
+    if (ld) kk = ld_keys_nc(t.keys + b * kBucket + gl * 2);
+    const unsigned bh0 = __ballot_sync(kFull, ld && kk.x == key);
+    const unsigned bh1 = __ballot_sync(kFull, ld && kk.y == key);
+    const unsigned be = __ballot_sync(kFull, ld && (kk.x == kEmptyKey || kk.y == kEmptyKey));
+    if (active) {
+      const unsigned H = mask8(bh0, bh1, sg);
+      if (H) {
+        found = (long long)(b * kBucket) + (__ffs(H) - 1);
+        active = false;
+      } else if (((be >> (sg * 4)) & 0xFu) || ++probes >= nb) {
+        active = false;
+      } else {
+        b = (b + 1 == nb) ? 0 : b + 1;
+      }
+    }
+  }
+  if (act && special) {
+    const int idx = (key == kTombKey) ? 1 : 0;
+    const unsigned present = *((volatile unsigned*)&t.st->special[idx]);
+    found = present ? (long long)(nb * kBucket + idx) : -1;
+  }
+  return found;
+}
+
+template <int VF> struct FVec;
+template <> struct FVec<4> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void fill(float x) { v = make_float4(x, x, x, x); }
+  template <typename F> __device__ __forceinline__ void apply(F f) { f(v.x); f(v.y); f(v.z); f(v.w); }
+  template <typename F> __device__ __forceinline__ void zip(const FVec& o, F f) { f(v.x, o.v.x); f(v.y, o.v.y); f(v.z, o.v.z); f(v.w, o.v.w); }
+};
+template <> struct FVec<1> {
+  float v;
+  __device__ __forceinline__ void load(const float* p) { v = *p; }
+  __device__ __forceinline__ void store(float* p) const { *p = v; }
+  __device__ __forceinline__ void zero() { v = 0.f; }
+  __device__ __forceinline__ void fill(float x) { v = x; }
+  template <typename F> __device__ __forceinline__ void apply(F f) { f(v); }
+  template <typename F> __device__ __forceinline__ void zip(const FVec& o, F f) { f(v, o.v); }
+};
+
+constexpr int kMaxVecPerLane = 8;
+
+template <int VF>
+__global__ void __launch_bounds__(kThreadsF)
+lookup_sparse_kernel(TableView t, const long long* __restrict__ ids, const long long* __restrict__ seg_start,
+                     const float* __restrict__ weights, size_t batch, int combiner,
+                     const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
+                     unsigned lpr_shift) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (int)(lpr - 1), gbase = lane & ~(int)(lpr - 1);
+  const unsigned gpw = 32u >> lpr_shift;
+  const unsigned gidx = (unsigned)lane >> lpr_shift;
+  const unsigned dim = t.dim;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
+  const float* table = (const float*)t.planes[0];
+  for (size_t sb = warp0 * gpw; sb < batch; sb += nwarps * gpw) {
+    const size_t b = sb + gidx;
+    const bool act_seg = b < batch;
+    const long long start = act_seg ? seg_start[b] : 0;
+    const long long end = act_seg ? seg_start[b + 1] : 0;
+    FVec<VF> acc[kMaxVecPerLane];
+#pragma unroll
+    for (int v = 0; v < kMaxVecPerLane; ++v) acc[v].zero();
+    float wsum = 0.f, wsq = 0.f;
+    for (long long k = 0; __any_sync(kFull, start + k < end); ++k) {
+      const long long i = start + k;
+      const bool act = i < end;
+      const long long key = act ? __ldg(ids + i) : 0;
+      const float w = act ? (weights ? __ldg(weights + i) : 1.f) : 0.f;
+      const long long slot = group_find_slot(t, key, act, gbase, gl);
+      if (act) {
+        const float* src = slot >= 0 ? table + (size_t)slot * dim : default_row;
+#pragma unroll
+        for (int v = 0; v < kMaxVecPerLane; ++v) {
+          const unsigned c = (unsigned)gl + (unsigned)v * lpr;
+          if (c < vpr) {
+            FVec<VF> x;
+            x.load(src + (size_t)c * VF);
+            acc[v].zip(x, [w](float& a, float xv) { a = a + xv * w; });
+          }
+        }
+        wsum = wsum + w;
+        wsq = wsq + w * w;
+      }
+    }
+    if (act_seg) {
+      float div = 1.f;
+      bool do_div = false;
+      if (end > start) {
+        if (combiner == DET_COMBINER_MEAN) { div = wsum; do_div = true; }
+        else if (combiner == DET_COMBINER_SQRTN) { div = sqrtf(wsq); do_div = true; }
+      }
+      float* dst = out + b * dim;
+#pragma unroll
+      for (int v = 0; v < kMaxVecPerLane; ++v) {
+        const unsigned c = (unsigned)gl + (unsigned)v * lpr;
+        if (c < vpr) {
+          if (do_div) acc[v].apply([div](float& a) { a = a / div; });
+          acc[v].store(dst + (size_t)c * VF);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: fused find-or-insert + optimizer update
+// ------------------------------------------------------------------------------------------------
+struct OptHyper {
+  float lr;       // adagrad lr | adam alpha
+  float eps;
+  float beta1, beta2;
+  float init_slot;  // adagrad initial accumulator
+};
+
+template <int VF, int OPT>
+__global__ void __launch_bounds__(kThreadsF)
+apply_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ grads, size_t n,
+             OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
+             unsigned lpr_shift) {
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    s_new = 0;
+    s_used = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned dim = t.dim;
+  const unsigned rows_per_step = 32u >> lpr_shift;
+  const unsigned sub = (unsigned)lane >> lpr_shift;
+  const unsigned c0 = (unsigned)lane & (lpr - 1u);
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
+  float* P = (float*)t.planes[0];
+  float* S1 = (float*)t.planes[1];
+  float* S2 = (float*)t.planes[2];
+  const float omb1 = 1.f - h.beta1, omb2 = 1.f - h.beta2;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
+    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+    if (lane == 0 && bn) {
+      atomicAdd(&s_new, __popc(bn));
+      atomicAdd(&s_used, __popc(bu));
+    }
+    for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step) {
+      const unsigned j = j0 + sub;
+      const long long s = shfl_ll(slot, (int)j);
+      const bool nw = (bn >> j) & 1u;
+      if (base + j >= n || s < 0) continue;
+      const size_t ro = (size_t)s * dim;
+      const float* g_row = grads + (base + j) * dim;
+      const float* i_row = full_init ? init_param + (base + j) * dim : init_param;
+      for (unsigned c = c0; c < vpr; c += lpr) {
+        const size_t o = (size_t)c * VF;
+        FVec<VF> g, p, a;
+        g.load(g_row + o);
+        if (nw) p.load(i_row + o); else p.load(P + ro + o);
+        if (OPT == 0) {
+          if (nw) a.fill(h.init_slot); else a.load(S1 + ro + o);
+          // accum += g*g ; var -= lr*g / (sqrt(accum) + eps)
+          a.zip(g, [](float& av, float gv) { av = av + gv * gv; });
+          FVec<VF> upd = g;
+          upd.zip(a, [&h](float& u, float av) { u = (h.lr * u) / (sqrtf(av) + h.eps); });
+          p.zip(upd, [](float& pv, float u) { pv = pv - u; });
+          a.store(S1 + ro + o);
+          p.store(P + ro + o);
+        } else {
+          FVec<VF> m, v;
+          if (nw) { m.zero(); v.zero(); } else { m.load(S1 + ro + o); v.load(S2 + ro + o); }
+          // m += (g-m)(1-b1) ; v += (g*g-v)(1-b2) ; var -= (m*alpha)/(sqrt(v)+eps)
+          m.zip(g, [omb1](float& mv, float gv) { mv = mv + (gv - mv) * omb1; });
+          v.zip(g, [omb2](float& vv, float gv) { vv = vv + (gv * gv - vv) * omb2; });
+          FVec<VF> upd = m;
+          upd.zip(v, [&h](float& u, float vv) { u = (u * h.lr) / (sqrtf(vv) + h.eps); });
+          p.zip(upd, [](float& pv, float u) { pv = pv - u; });
+          m.store(S1 + ro + o);
+          v.store(S2 + ro + o);
+          p.store(P + ro + o);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: key-hash partition (stable) + row gather/scatter
+// ------------------------------------------------------------------------------------------------
+constexpr int kPartBlock = 1024;
+constexpr int kMaxShards = 64;
+
+__device__ __forceinline__ int owner_of(long long key, int S, int gpu_mode) {
+  if (gpu_mode) {
+    const int k32 = (int)(key & 0x7fffffffLL);
+    return k32 % S;
+  }
+  long long m = key % (long long)S;  // floor-mod like tf.math.mod
+  if (m < 0) m += S;
+  return (int)m;
+}
+
+__global__ void __launch_bounds__(kPartBlock)
+partition_hist_kernel(const long long* __restrict__ keys, size_t n, int S, int gpu_mode,
+                      unsigned* __restrict__ hist /*[S][nblocks]*/, size_t nblocks) {
+  __shared__ unsigned s_h[kMaxShards];
+  if (threadIdx.x < kMaxShards) s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * kPartBlock + threadIdx.x;
+  if (i < n) atomicAdd(&s_h[owner_of(keys[i], S, gpu_mode)], 1u);
+  __syncthreads();
+  if ((int)threadIdx.x < S) hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// one block: for shard-major flattened hist [S*nblocks], exclusive scan -> global start of each
+// (shard, block) run; counts per shard
+__global__ void __launch_bounds__(kScanBlock)
+partition_scan_kernel(unsigned* __restrict__ hist, size_t nblocks, int S, long long* __restrict__ counts_out) {
+  __shared__ unsigned s_warp[33];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const size_t total_n = (size_t)S * nblocks;
+  for (size_t base = 0; base < total_n; base += kScanBlock) {
+    const size_t i = base + threadIdx.x;
+    const unsigned v = i < total_n ? hist[i] : 0u;
+    unsigned total;
+    const unsigned excl = block_exclusive_scan(v, s_warp, total);
+    const unsigned long long carry = s_carry;
+    if (i < total_n) hist[i] = (unsigned)(carry + excl);
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  // counts: start of next shard - start of this shard
+  const unsigned long long n_all = s_carry;
+  if ((int)threadIdx.x < S) {
+    const unsigned long long a = hist[(size_t)threadIdx.x * nblocks];
+    const unsigned long long b = ((int)threadIdx.x + 1 < S) ? hist[(size_t)(threadIdx.x + 1) * nblocks] : n_all;
+    counts_out[threadIdx.x] = (long long)(b - a);
+  }
+}
+
+__global__ void __launch_bounds__(kPartBlock)
+partition_write_kernel(const long long* __restrict__ keys, size_t n, int S, int gpu_mode,
+                       const unsigned* __restrict__ hist, size_t nblocks, long long* __restrict__ keys_out,
+                       int* __restrict__ perm_out) {
+  __shared__ unsigned s_cnt[kPartBlock / 32][kMaxShards];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < (kPartBlock / 32) * kMaxShards; q += kPartBlock) (&s_cnt[0][0])[q] = 0;
+  __syncthreads();
+  const size_t i = (size_t)blockIdx.x * kPartBlock + threadIdx.x;
+  const bool valid = i < n;
+  const long long key = valid ? keys[i] : 0;
+  const int own = valid ? owner_of(key, S, gpu_mode) : -1;
+  const unsigned peers = __match_any_sync(kFull, own);
+  const unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+  if (valid && rank_in_warp == 0) s_cnt[w][own] = __popc(peers);
+  __syncthreads();
+  // exclusive prefix over warps, per shard (S columns, 32 rows): thread s handles shard s
+  if ((int)threadIdx.x < S) {
+    unsigned run = 0;
+    for (int ww = 0; ww < kPartBlock / 32; ++ww) {
+      const unsigned c = s_cnt[ww][threadIdx.x];
+      s_cnt[ww][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  if (valid) {
+    const size_t dest = (size_t)hist[(size_t)own * nblocks + blockIdx.x] + s_cnt[w][own] + rank_in_warp;
+    keys_out[dest] = key;
+    perm_out[dest] = (int)i;
+  }
+}
+
+template <int VEC, bool SCATTER>
+__global__ void __launch_bounds__(kThreadsF)
+permute_rows_kernel(const unsigned char* __restrict__ in, const int* __restrict__ perm, size_t n,
+                    unsigned char* __restrict__ out, RowGeom g) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t j = base + lane;
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (j < n) {
+      const size_t p = (size_t)perm[j];
+      src = in + (SCATTER ? j : p) * g.row_bytes;
+      dst = out + (SCATTER ? p : j) * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+  }
+}
+
+static void fgeom(unsigned dim, bool vec4, unsigned min_lpr, unsigned* vpr, unsigned* lpr, unsigned* sh) {
+  *vpr = vec4 ? dim / 4 : dim;
+  unsigned l = 1, s = 0;
+  while ((l < *vpr || l < min_lpr) && l < 32u) {
+    l <<= 1;
+    ++s;
+  }
+  *lpr = l;
+  *sh = s;
+}
+
+}  // namespace det
+
+using namespace det;
+
+extern "C" {
+
+size_t det_unique_workspace_bytes(size_t n) { return unique_ws_layout(n ? n : 1, nullptr, nullptr); }
+
+det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t* idx_out, int64_t* n_unique_dev,
+                      void* workspace, size_t workspace_bytes, det_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!n_unique_dev) return fail(DET_INVALID_ARGUMENT, "det_unique: null n_unique");
+  if (n == 0) {
+    CUDA_TRY(cudaMemsetAsync(n_unique_dev, 0, sizeof(int64_t), s));
+    return DET_OK;
+  }
+  if (n >= 0xfffffff0ull) return fail(DET_INVALID_ARGUMENT, "det_unique: n too large");
+  if (!ids || !unique_out || !idx_out || !workspace) return fail(DET_INVALID_ARGUMENT, "det_unique: null argument");
+  if (workspace_bytes < det_unique_workspace_bytes(n)) return fail(DET_INVALID_ARGUMENT, "det_unique: workspace too small");
+  UniqueWs w;
+  unique_ws_layout(n, (unsigned char*)workspace, &w);
+  const size_t nblocks = (n + kScanBlock - 1) / kScanBlock;
+  const int g256 = (int)((n + 255) / 256);
+  unique_init_kernel<<<(int)((w.hcap + 1023) / 1024 < 4096 ? (w.hcap + 1023) / 1024 : 4096), 1024, 0, s>>>(w);
+  unique_insert_kernel<<<g256, 256, 0, s>>>(w, (const long long*)ids, n);
+  unique_flag_kernel<<<g256, 256, 0, s>>>(w, n);
+  scan_block_sums_kernel<<<(int)nblocks, kScanBlock, 0, s>>>(w.flags, n, w.block_sums);
+  scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.block_sums, nblocks, (long long*)n_unique_dev);
+  unique_rank_kernel<<<(int)nblocks, kScanBlock, 0, s>>>(w, (const long long*)ids, n, (long long*)unique_out);
+  unique_idx_kernel<<<g256, 256, 0, s>>>(w, n, idx_out);
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* segment_ids, const float* weights,
+                             size_t nnz, size_t batch, int combiner, const float* default_row, float* out,
+                             det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_lookup_sparse: null table");
+  if (t->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_lookup_sparse: float32 tables only");
+  if (combiner < DET_COMBINER_SUM || combiner > DET_COMBINER_SQRTN)
+    return fail(DET_INVALID_ARGUMENT, "combiner must be one of 'mean', 'sqrtn' or 'sum'");
+  if (batch == 0) return DET_OK;
+  if (!out || !default_row || (nnz && (!ids || !segment_ids))) return fail(DET_INVALID_ARGUMENT, "det_lookup_sparse: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  long long* seg_start = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&seg_start, (batch + 1) * sizeof(long long), s));
+  segment_offsets_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, s>>>(segment_ids, nnz, batch, seg_start, t->view.st);
+  const unsigned dim = (unsigned)t->cfg.dim;
+  const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out) & 15u) == 0);
+  unsigned vpr, lpr, sh;
+  fgeom(dim, vec4, 4, &vpr, &lpr, &sh);
+  if ((vpr + lpr - 1) / lpr > (unsigned)kMaxVecPerLane) {
+    cudaFreeAsync(seg_start, s);
+    return fail(DET_UNIMPLEMENTED, "det_lookup_sparse: dim too large for the fused kernel");
+  }
+  const unsigned gpw = 32u >> sh;
+  const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
+  if (vec4)
+    lookup_sparse_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, (const long long*)ids, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+  else
+    lookup_sparse_kernel<1><<<grid, kThreadsF, 0, s>>>(t->view, (const long long*)ids, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(seg_start, s));
+  return DET_OK;
+}
+
+static det_status apply_common(det_table* t, const int64_t* keys, const float* grads, size_t n, OptHyper h,
+                               const float* init_param, int full_init, int opt, cudaStream_t s) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_apply: null table");
+  if (t->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_apply: float32 tables only");
+  if (t->cfg.num_slot_planes < (opt == 0 ? 1 : 2))
+    return fail(DET_INVALID_ARGUMENT, "det_apply: table was created with too few optimizer slot planes");
+  if (n == 0) return DET_OK;
+  if (!keys || !grads || !init_param) return fail(DET_INVALID_ARGUMENT, "det_apply: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det_status st = ensure_room(t, n, s);
+  if (st != DET_OK) return st;
+  const unsigned dim = (unsigned)t->cfg.dim;
+  const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)grads | (uintptr_t)init_param) & 15u) == 0);
+  unsigned vpr, lpr, sh;
+  fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
+  const int grid = grid_for(n, kThreadsF, t->sm_count, 8);
+  const TableView v = t->view;
+  const long long* k = (const long long*)keys;
+  if (opt == 0) {
+    if (vec4) apply_kernel<4, 0><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
+    else apply_kernel<1, 0><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
+  } else {
+    if (vec4) apply_kernel<4, 1><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
+    else apply_kernel<1, 1><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_apply_adagrad(det_table* t, const int64_t* keys, const float* grads, size_t n, float lr, float epsilon,
+                             const float* init_param, int full_size_init, float init_accum, det_stream_t stream) {
+  OptHyper h;
+  h.lr = lr; h.eps = epsilon; h.beta1 = 0.f; h.beta2 = 0.f; h.init_slot = init_accum;
+  if (t) t->slot_init[1] = init_accum;
+  return apply_common(t, keys, grads, n, h, init_param, full_size_init, 0, (cudaStream_t)stream);
+}
+
+det_status det_apply_adam(det_table* t, const int64_t* keys, const float* grads, size_t n, float alpha, float beta1,
+                          float beta2, float epsilon, const float* init_param, int full_size_init,
+                          det_stream_t stream) {
+  OptHyper h;
+  h.lr = alpha; h.eps = epsilon; h.beta1 = beta1; h.beta2 = beta2; h.init_slot = 0.f;
+  return apply_common(t, keys, grads, n, h, init_param, full_size_init, 1, (cudaStream_t)stream);
+}
+
+size_t det_partition_workspace_bytes(size_t n, int num_shards) {
+  const size_t nblocks = (n + kPartBlock - 1) / kPartBlock;
+  return align256((size_t)(num_shards > 0 ? num_shards : 1) * (nblocks ? nblocks : 1) * sizeof(unsigned)) + 256;
+}
+
+det_status det_partition(const int64_t* keys, size_t n, int num_shards, int gpu_mode, int64_t* keys_out,
+                         int32_t* perm_out, int64_t* counts_out, void* workspace, size_t workspace_bytes,
+                         det_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_shards < 1 || num_shards > kMaxShards) return fail(DET_INVALID_ARGUMENT, "det_partition: num_shards must be in [1,64]");
+  if (!counts_out) return fail(DET_INVALID_ARGUMENT, "det_partition: null counts");
+  if (n == 0) {
+    CUDA_TRY(cudaMemsetAsync(counts_out, 0, sizeof(int64_t) * num_shards, s));
+    return DET_OK;
+  }
+  if (n >= 0x7fffffffull) return fail(DET_INVALID_ARGUMENT, "det_partition: n too large");
+  if (!keys || !keys_out || !perm_out || !workspace) return fail(DET_INVALID_ARGUMENT, "det_partition: null argument");
+  if (workspace_bytes < det_partition_workspace_bytes(n, num_shards)) return fail(DET_INVALID_ARGUMENT, "det_partition: workspace too small");
+  const size_t nblocks = (n + kPartBlock - 1) / kPartBlock;
+  unsigned* hist = (unsigned*)workspace;
+  partition_hist_kernel<<<(int)nblocks, kPartBlock, 0, s>>>((const long long*)keys, n, num_shards, gpu_mode, hist, nblocks);
+  partition_scan_kernel<<<1, kScanBlock, 0, s>>>(hist, nblocks, num_shards, (long long*)counts_out);
+  partition_write_kernel<<<(int)nblocks, kPartBlock, 0, s>>>((const long long*)keys, n, num_shards, gpu_mode, hist, nblocks,
+                                                            (long long*)keys_out, perm_out);
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+static det_status permute_rows(const void* in, const int32_t* perm, size_t n, size_t row_bytes, void* out, bool scatter,
+                               cudaStream_t s) {
+  if (n == 0) return DET_OK;
+  if (!in || !perm || !out || row_bytes == 0) return fail(DET_INVALID_ARGUMENT, "det_*_rows: null argument");
+  const int vec = pick_vec(row_bytes, in, out, nullptr);
+  const RowGeom g = make_geom((unsigned)row_bytes, vec);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = grid_for(n, kThreadsF, sms, 8);
+  const unsigned char* i = (const unsigned char*)in;
+  unsigned char* o = (unsigned char*)out;
+#define LAUNCH(V)                                                                              \
+  if (scatter) permute_rows_kernel<V, true><<<grid, kThreadsF, 0, s>>>(i, perm, n, o, g);      \
+  else permute_rows_kernel<V, false><<<grid, kThreadsF, 0, s>>>(i, perm, n, o, g);
+  switch (vec) {
+    case 16: LAUNCH(16) break;
+    case 8: LAUNCH(8) break;
+    case 4: LAUNCH(4) break;
+    case 2: LAUNCH(2) break;
+    default: LAUNCH(1) break;
+  }
+#undef LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_scatter_rows(const void* rows_in, const int32_t* perm, size_t n, size_t row_bytes, void* rows_out,
+                            det_stream_t stream) {
+  return permute_rows(rows_in, perm, n, row_bytes, rows_out, true, (cudaStream_t)stream);
+}
+
+det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, size_t row_bytes, void* rows_out,
+                           det_stream_t stream) {
+  return permute_rows(rows_in, perm, n, row_bytes, rows_out, false, (cudaStream_t)stream);
+}
+
+}  // extern "C"

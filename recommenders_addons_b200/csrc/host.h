@@ -1,0 +1,58 @@
+// host.h -- host-side table object and shared declarations for the .cu translation units.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <type_traits>
+
+#include "../../include/detable.h"
+#include "common.cuh"
+
+namespace det {
+
+extern thread_local std::string g_last_error;
+det_status fail(det_status code, const std::string& msg);
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      cudaGetLastError();                                                                           \
+      return ::det::fail(_e == cudaErrorMemoryAllocation ? DET_OUT_OF_MEMORY : DET_CUDA_ERROR,      \
+                         std::string("CUDA error at " __FILE__ ":") + std::to_string(__LINE__) +    \
+                             ": " + cudaGetErrorString(_e));                                        \
+    }                                                                                               \
+  } while (0)
+
+struct HostPipe;  // chunked H2D -> kernel -> D2H pipeline state (host_api.cu)
+
+size_t dtype_size(int dt);
+RowGeom make_geom(unsigned row_bytes, int vec);
+int pick_vec(size_t row_bytes, const void* a, const void* b, const void* c);
+int grid_for(size_t n_items, int items_per_block, int sm_count, int blocks_per_sm);
+
+}  // namespace det
+
+struct det_table {
+  det_config cfg;
+  size_t row_bytes = 0;
+  float max_lf = 0.75f;
+  int sm_count = 148;
+  det::TableView view{};
+  void* raw[1 + det::kMaxPlanes];
+  det::DevState* h_state = nullptr;  // pinned host mirror
+  uint64_t used_ub = 0;              // host upper bound of non-EMPTY slots (no sync needed)
+  uint32_t rehash_count = 0;
+  float slot_init[det::kMaxPlanes];  // value given to slot-plane rows of keys created by insert/accum
+  det::HostPipe* pipe = nullptr;
+};
+
+namespace det {
+struct SlotInit;
+det_status ensure_room(det_table* t, size_t n, cudaStream_t s);
+det_status table_clear_async(det_table* t, cudaStream_t s);
+void host_pipe_free(det_table* t);
+}  // namespace det

@@ -1,0 +1,280 @@
+// host_api.cu -- entry points that take HOST buffers:
+//   det_find_host / det_insert_host : the table op placed on host tensors.  Work is cut into chunks
+//     that flow H2D -> kernel -> D2H on three internal streams, so the PCIe copies in both directions
+//     overlap each other and the kernels.  Pageable buffers are staged through pinned bounce buffers.
+//   det_save / det_load : the reference's SaveToFileSystem / LoadFromFileSystem raw file format
+//     (kernels/cuckoo_hashtable_op.cc:310-504): <prefix>-keys = int64[n], <prefix>-values = V[n*dim].
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "host.h"
+
+namespace det {
+
+constexpr int kPipeStreams = 3;
+constexpr size_t kPipeChunkBytes = 8u << 20;  // value bytes per chunk
+
+struct HostPipe {
+  cudaStream_t streams[kPipeStreams];
+  cudaEvent_t done[kPipeStreams];
+  size_t chunk_keys = 0;
+  // per stream device scratch
+  long long* d_keys[kPipeStreams];
+  unsigned char* d_vals[kPipeStreams];
+  unsigned char* d_defs[kPipeStreams];
+  unsigned char* d_exists[kPipeStreams];
+  // per stream pinned bounce buffers (only used for pageable user memory)
+  long long* h_keys[kPipeStreams];
+  unsigned char* h_vals[kPipeStreams];
+  unsigned char* h_exists[kPipeStreams];
+};
+
+static det_status pipe_get(det_table* t, HostPipe** out) {
+  if (t->pipe) {
+    *out = t->pipe;
+    return DET_OK;
+  }
+  HostPipe* p = new HostPipe();
+  memset(p, 0, sizeof(*p));
+  size_t ck = kPipeChunkBytes / t->row_bytes;
+  if (ck < 1024) ck = 1024;
+  ck = (ck + 31) & ~(size_t)31;
+  p->chunk_keys = ck;
+  for (int i = 0; i < kPipeStreams; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc((void**)&p->d_keys[i], ck * 8));
+    CUDA_TRY(cudaMalloc((void**)&p->d_vals[i], ck * t->row_bytes));
+    CUDA_TRY(cudaMalloc((void**)&p->d_defs[i], ck * t->row_bytes));
+    CUDA_TRY(cudaMalloc((void**)&p->d_exists[i], ck));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_keys[i], ck * 8));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_vals[i], ck * t->row_bytes));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_exists[i], ck));
+  }
+  t->pipe = p;
+  *out = p;
+  return DET_OK;
+}
+
+void host_pipe_free(det_table* t) {
+  HostPipe* p = t->pipe;
+  if (!p) return;
+  for (int i = 0; i < kPipeStreams; ++i) {
+    if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+    if (p->done[i]) cudaEventDestroy(p->done[i]);
+    cudaFree(p->d_keys[i]);
+    cudaFree(p->d_vals[i]);
+    cudaFree(p->d_defs[i]);
+    cudaFree(p->d_exists[i]);
+    cudaFreeHost(p->h_keys[i]);
+    cudaFreeHost(p->h_vals[i]);
+    cudaFreeHost(p->h_exists[i]);
+  }
+  delete p;
+  t->pipe = nullptr;
+}
+
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace det
+
+using namespace det;
+
+extern "C" {
+
+det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void* defaults, int full_default,
+                         void* values_out, uint8_t* exists) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_find_host: null table");
+  if (n == 0) return DET_OK;
+  if (!keys || !defaults || !values_out) return fail(DET_INVALID_ARGUMENT, "det_find_host: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  HostPipe* p;
+  det_status st = pipe_get(t, &p);
+  if (st != DET_OK) return st;
+  const size_t rb = t->row_bytes, ck = p->chunk_keys;
+  const bool pin_k = is_pinned(keys), pin_v = is_pinned(values_out), pin_e = is_pinned(exists),
+             pin_d = is_pinned(defaults);
+  const unsigned char* defs = (const unsigned char*)defaults;
+  unsigned char* vout = (unsigned char*)values_out;
+  // broadcast default row: upload once per stream
+  if (!full_default)
+    for (int i = 0; i < kPipeStreams; ++i)
+      CUDA_TRY(cudaMemcpyAsync(p->d_defs[i], defs, rb, cudaMemcpyHostToDevice, p->streams[i]));
+  size_t c = 0;
+  for (size_t off = 0; off < n; off += ck, ++c) {
+    const int i = (int)(c % kPipeStreams);
+    const size_t m = (n - off < ck) ? n - off : ck;
+    cudaStream_t s = p->streams[i];
+    if (c >= (size_t)kPipeStreams) {
+      // the bounce buffers of this stream are free again once its previous chunk has drained
+      CUDA_TRY(cudaEventSynchronize(p->done[i]));
+      if (!pin_v || !pin_e) {
+        const size_t poff = off - ck * kPipeStreams;
+        if (!pin_v) memcpy(vout + poff * rb, p->h_vals[i], ck * rb);
+        if (!pin_e && exists) memcpy(exists + poff, p->h_exists[i], ck);
+      }
+    }
+    const long long* hk = (const long long*)keys + off;
+    if (!pin_k) {
+      memcpy(p->h_keys[i], hk, m * 8);
+      hk = p->h_keys[i];
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_keys[i], hk, m * 8, cudaMemcpyHostToDevice, s));
+    if (full_default) {
+      // full-size defaults travel with the keys (pageable sources are staged by the driver)
+      CUDA_TRY(cudaMemcpyAsync(p->d_defs[i], defs + off * rb, m * rb, cudaMemcpyHostToDevice, s));
+      (void)pin_d;
+    }
+    st = det_find(t, (const int64_t*)p->d_keys[i], m, p->d_defs[i], full_default, p->d_vals[i],
+                  exists ? p->d_exists[i] : nullptr, (det_stream_t)s);
+    if (st != DET_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(pin_v ? (void*)(vout + off * rb) : (void*)p->h_vals[i], p->d_vals[i], m * rb,
+                             cudaMemcpyDeviceToHost, s));
+    if (exists)
+      CUDA_TRY(cudaMemcpyAsync(pin_e ? (void*)(exists + off) : (void*)p->h_exists[i], p->d_exists[i], m,
+                               cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(p->done[i], s));
+  }
+  // drain: last up-to-3 chunks
+  const size_t nchunks = c;
+  for (size_t q = (nchunks > (size_t)kPipeStreams ? nchunks - kPipeStreams : 0); q < nchunks; ++q) {
+    const int i = (int)(q % kPipeStreams);
+    CUDA_TRY(cudaEventSynchronize(p->done[i]));
+    const size_t off = q * ck;
+    const size_t m = (n - off < ck) ? n - off : ck;
+    if (!pin_v) memcpy(vout + off * rb, p->h_vals[i], m * rb);
+    if (!pin_e && exists) memcpy(exists + off, p->h_exists[i], m);
+  }
+  return DET_OK;
+}
+
+det_status det_insert_host(det_table* t, const int64_t* keys, const void* values, size_t n) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert_host: null table");
+  if (n == 0) return DET_OK;
+  if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert_host: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  HostPipe* p;
+  det_status st = pipe_get(t, &p);
+  if (st != DET_OK) return st;
+  const size_t rb = t->row_bytes, ck = p->chunk_keys;
+  const bool pin_k = is_pinned(keys), pin_v = is_pinned(values);
+  // growth (if any) must happen before the chunks are in flight on several streams
+  st = ensure_room(t, n, p->streams[0]);
+  if (st != DET_OK) return st;
+  t->used_ub -= n;  // the per-chunk det_insert calls account for their keys again
+  size_t c = 0;
+  for (size_t off = 0; off < n; off += ck, ++c) {
+    const int i = (int)(c % kPipeStreams);
+    const size_t m = (n - off < ck) ? n - off : ck;
+    cudaStream_t s = p->streams[i];
+    if (c >= (size_t)kPipeStreams) CUDA_TRY(cudaEventSynchronize(p->done[i]));
+    const long long* hk = (const long long*)keys + off;
+    const unsigned char* hv = (const unsigned char*)values + off * rb;
+    if (!pin_k) {
+      memcpy(p->h_keys[i], hk, m * 8);
+      hk = p->h_keys[i];
+    }
+    if (!pin_v) {
+      memcpy(p->h_vals[i], hv, m * rb);
+      hv = p->h_vals[i];
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_keys[i], hk, m * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(p->d_vals[i], hv, m * rb, cudaMemcpyHostToDevice, s));
+    st = det_insert(t, (const int64_t*)p->d_keys[i], p->d_vals[i], m, (det_stream_t)s);
+    if (st != DET_OK) return st;
+    CUDA_TRY(cudaEventRecord(p->done[i], s));
+  }
+  for (int i = 0; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+  return DET_OK;
+}
+
+det_status det_save(det_table* t, const char* prefix, size_t buffer_keys) {
+  if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_save: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  int64_t n = 0;
+  det_status st = det_size(t, &n, nullptr);
+  if (st != DET_OK) return st;
+  (void)buffer_keys;
+  const size_t rb = t->row_bytes;
+  long long* dk = nullptr;
+  unsigned char* dv = nullptr;
+  const size_t cnt = n > 0 ? (size_t)n : 1;
+  CUDA_TRY(cudaMalloc((void**)&dk, cnt * 8));
+  cudaError_t e = cudaMalloc((void**)&dv, cnt * rb);
+  if (e != cudaSuccess) {
+    cudaFree(dk);
+    cudaGetLastError();
+    return fail(DET_OUT_OF_MEMORY, "det_save: no HBM for the export buffer");
+  }
+  int64_t got = 0;
+  st = det_export(t, 0, (int64_t*)dk, dv, (size_t)n, &got, nullptr);
+  std::vector<long long> hk((size_t)got);
+  std::vector<unsigned char> hv((size_t)got * rb);
+  if (st == DET_OK && got > 0) {
+    if (cudaMemcpy(hk.data(), dk, (size_t)got * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(hv.data(), dv, (size_t)got * rb, cudaMemcpyDeviceToHost) != cudaSuccess)
+      st = fail(DET_CUDA_ERROR, "det_save: D2H copy failed");
+  }
+  cudaFree(dk);
+  cudaFree(dv);
+  if (st != DET_OK) return st;
+  // tmp + rename like the reference (cuckoo_hashtable_op.cc:310-391)
+  const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
+  const std::string kt = kf + ".tmp", vt = vf + ".tmp";
+  FILE* fk = fopen(kt.c_str(), "wb");
+  FILE* fv = fopen(vt.c_str(), "wb");
+  bool ok = fk && fv;
+  if (ok && got > 0) {
+    ok = fwrite(hk.data(), 8, (size_t)got, fk) == (size_t)got &&
+         fwrite(hv.data(), rb, (size_t)got, fv) == (size_t)got;
+  }
+  if (fk) ok = (fclose(fk) == 0) && ok;
+  if (fv) ok = (fclose(fv) == 0) && ok;
+  if (ok) ok = rename(kt.c_str(), kf.c_str()) == 0 && rename(vt.c_str(), vf.c_str()) == 0;
+  if (!ok) return fail(DET_IO_ERROR, "det_save: cannot write " + kf + " / " + vf);
+  return DET_OK;
+}
+
+det_status det_load(det_table* t, const char* prefix, size_t buffer_keys) {
+  if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_load: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
+  FILE* fk = fopen(kf.c_str(), "rb");
+  FILE* fv = fopen(vf.c_str(), "rb");
+  if (!fk || !fv) {
+    if (fk) fclose(fk);
+    if (fv) fclose(fv);
+    return fail(DET_IO_ERROR, "det_load: cannot open " + kf + " / " + vf);
+  }
+  const size_t rb = t->row_bytes;
+  if (buffer_keys == 0) buffer_keys = 1u << 20;
+  std::vector<long long> hk(buffer_keys);
+  std::vector<unsigned char> hv(buffer_keys * rb);
+  det_status st = DET_OK;
+  // LoadFromFileSystem without load_entire_dir = clear + insert all (cuckoo_hashtable_op.cc:393-465)
+  st = det_clear(t, nullptr);
+  while (st == DET_OK) {
+    const size_t m = fread(hk.data(), 8, buffer_keys, fk);
+    if (m == 0) break;
+    if (fread(hv.data(), rb, m, fv) != m) {
+      st = fail(DET_IO_ERROR, "det_load: " + vf + " is shorter than " + kf);
+      break;
+    }
+    st = det_insert_host(t, (const int64_t*)hk.data(), hv.data(), m);
+  }
+  fclose(fk);
+  fclose(fv);
+  return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,836 @@
+// table.cu -- the table object behind include/detable.h and kernels K1..K5 (find / insert / accum /
+// remove / clear / size / export / rehash).  sm_100a only.  See DESIGN.md for layout and rooflines.
+#include "host.h"
+
+namespace det {
+
+thread_local std::string g_last_error;
+
+det_status fail(det_status code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+size_t dtype_size(int dt) {
+  switch (dt) {
+    case DET_FLOAT32: return 4;
+    case DET_FLOAT16: return 2;
+    case DET_BFLOAT16: return 2;
+    case DET_INT32: return 4;
+    case DET_INT64: return 8;
+    case DET_INT8: return 1;
+    case DET_FLOAT64: return 8;
+    default: return 0;
+  }
+}
+
+RowGeom make_geom(unsigned row_bytes, int vec) {
+  RowGeom g;
+  g.row_bytes = row_bytes;
+  g.vpr = row_bytes / (unsigned)vec;
+  unsigned lpr = 1, sh = 0;
+  while (lpr < g.vpr && lpr < 32u) {
+    lpr <<= 1;
+    ++sh;
+  }
+  g.lpr = lpr;
+  g.lpr_shift = sh;
+  return g;
+}
+
+int pick_vec(size_t row_bytes, const void* a, const void* b, const void* c) {
+  uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c;
+  if ((bits & 15u) == 0) return 16;
+  if ((bits & 7u) == 0) return 8;
+  if ((bits & 3u) == 0) return 4;
+  if ((bits & 1u) == 0) return 2;
+  return 1;
+}
+
+int grid_for(size_t n_items, int items_per_block, int sm_count, int blocks_per_sm) {
+  size_t need = (n_items + (size_t)items_per_block - 1) / (size_t)items_per_block;
+  size_t cap = (size_t)sm_count * (size_t)blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ================================================================================================
+// Kernels
+// ================================================================================================
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = kThreads / 32;
+
+// K1: Find / FindWithExists with the default-row fill folded in (replaces HKV find +
+// gpu_fill_default_values, lookup_table_op_hkv.h:317-327, 719-732).
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+find_kernel(TableView t, const long long* __restrict__ keys, size_t n,
+            const unsigned char* __restrict__ defaults, int full_default,
+            unsigned char* __restrict__ out, unsigned char* __restrict__ exists, RowGeom g) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const long long slot = warp_find_slots<false>(t, key, valid, lane);
+    if (exists != nullptr && valid) exists[i] = slot >= 0 ? 1 : 0;
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid) {
+      src = slot >= 0 ? t.planes[0] + (size_t)slot * g.row_bytes
+                      : (full_default ? defaults + i * g.row_bytes : defaults);
+      dst = out + i * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+  }
+}
+
+// fill `rows` consecutive fp32 rows of a slot plane with a constant (used for new keys)
+__device__ __forceinline__ void warp_fill_rows_f32(unsigned char* my_dst, unsigned dim, float value,
+                                                   int lane) {
+  for (int j = 0; j < 32; ++j) {
+    float* d = (float*)shfl_ll((long long)my_dst, j);
+    if (d) {
+      for (unsigned c = lane; c < dim; c += 32) d[c] = value;
+    }
+  }
+}
+
+struct SlotInit {
+  float v[kMaxPlanes];
+  int n_planes;  // number of slot planes (excluding values)
+};
+
+// K2: Insert (insert_or_assign).  New keys also get their optimizer slot rows initialised.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
+              size_t n, RowGeom g, SlotInit si) {
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    s_new = 0;
+    s_used = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
+    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+    if (lane == 0 && bn) {
+      atomicAdd(&s_new, __popc(bn));
+      atomicAdd(&s_used, __popc(bu));
+    }
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid && slot >= 0) {
+      src = values + i * g.row_bytes;
+      dst = t.planes[0] + (size_t)slot * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+    if (si.n_planes > 0 && bn) {
+      for (int p = 1; p <= si.n_planes; ++p) {
+        unsigned char* d = (is_new && slot >= 0) ? t.planes[p] + (size_t)slot * t.dim * 4u : nullptr;
+        warp_fill_rows_f32(d, t.dim, si.v[p], lane);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+}
+
+template <typename T> struct AccT { using type = T; };
+__device__ __forceinline__ float acc_add(float a, float b) { return a + b; }
+__device__ __forceinline__ double acc_add(double a, double b) { return a + b; }
+__device__ __forceinline__ int acc_add(int a, int b) { return a + b; }
+__device__ __forceinline__ long long acc_add(long long a, long long b) { return a + b; }
+__device__ __forceinline__ signed char acc_add(signed char a, signed char b) { return (signed char)(a + b); }
+__device__ __forceinline__ __half acc_add(__half a, __half b) { return __hadd(a, b); }
+__device__ __forceinline__ __nv_bfloat16 acc_add(__nv_bfloat16 a, __nv_bfloat16 b) { return __hadd(a, b); }
+
+// K3: Accum (insert_or_accum, cuckoohash_map.hh:620-633): found&exist -> row += delta (element by
+// element, one rounding each, like ValueArray::operator+=); !found&!exist -> insert; else no-op.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+accum_kernel(TableView t, const long long* __restrict__ keys, const T* __restrict__ vod,
+             const unsigned char* __restrict__ exists, size_t n, SlotInit si) {
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    s_new = 0;
+    s_used = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned dim = t.dim;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const bool ex = valid ? (exists[i] != 0) : false;
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim(t, key, valid, valid && !ex, lane, is_new, from_empty);
+    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+    if (lane == 0 && bn) {
+      atomicAdd(&s_new, __popc(bn));
+      atomicAdd(&s_used, __popc(bu));
+    }
+    // mode: 0 skip, 1 assign (new key), 2 add (found & exist)
+    int mode = 0;
+    if (valid && slot >= 0) mode = is_new ? 1 : (ex ? 2 : 0);
+    for (int j = 0; j < 32; ++j) {
+      const int m = __shfl_sync(kFull, mode, j);
+      if (m == 0) continue;
+      const long long s = shfl_ll(slot, j);
+      T* row = (T*)t.planes[0] + (size_t)s * dim;
+      const T* in = vod + (base + j) * dim;
+      if (m == 1) {
+        for (unsigned c = lane; c < dim; c += 32) row[c] = in[c];
+      } else {
+        for (unsigned c = lane; c < dim; c += 32) row[c] = acc_add(row[c], in[c]);
+      }
+    }
+    if (si.n_planes > 0 && bn) {
+      for (int p = 1; p <= si.n_planes; ++p) {
+        unsigned char* d = (is_new && slot >= 0) ? t.planes[p] + (size_t)slot * dim * 4u : nullptr;
+        warp_fill_rows_f32(d, dim, si.v[p], lane);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+}
+
+// K4: Remove.  A slot whose bucket still has an EMPTY slot goes straight back to EMPTY (no probe
+// chain can run through such a bucket); otherwise it becomes a tombstone.
+__global__ void __launch_bounds__(kThreads)
+remove_kernel(TableView t, const long long* __restrict__ keys, size_t n) {
+  __shared__ unsigned s_removed, s_freed;
+  if (threadIdx.x == 0) {
+    s_removed = 0;
+    s_freed = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  const long long cap = (long long)t.capacity();
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const long long slot = warp_find_slots<true>(t, key, valid, lane);
+    bool removed = false, freed = false;
+    if (valid && slot >= 0) {
+      if (slot >= cap) {
+        removed = atomicExch(&t.st->special[slot - cap], 0u) != 0u;
+      } else {
+        const long long* bp = t.keys + (slot & ~(long long)(kBucket - 1));
+        bool has_empty = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const longlong2 kk = ld_keys_cg(bp + q * 2);
+          has_empty |= (kk.x == kEmptyKey) | (kk.y == kEmptyKey);
+        }
+        const long long nv = has_empty ? kEmptyKey : kTombKey;
+        const long long old = (long long)atomicCAS((unsigned long long*)(t.keys + slot),
+                                                   (unsigned long long)key, (unsigned long long)nv);
+        removed = (old == key);
+        freed = removed && has_empty;
+      }
+    }
+    const unsigned br = __ballot_sync(kFull, removed), bf = __ballot_sync(kFull, freed);
+    if (lane == 0 && br) {
+      atomicAdd(&s_removed, __popc(br));
+      atomicAdd(&s_freed, __popc(bf));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_removed) {
+    atomicAdd(&t.st->size, (unsigned long long)(-(long long)s_removed));
+    atomicAdd(&t.st->used, (unsigned long long)(-(long long)s_freed));
+  }
+}
+
+// K5a: Clear
+__global__ void fill_keys_kernel(long long* keys, size_t n, long long v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    keys[i] = v;
+}
+__global__ void reset_state_kernel(DevState* st) {
+  st->size = 0;
+  st->used = 0;
+  st->special[0] = 0;
+  st->special[1] = 0;
+  st->scratch[0] = st->scratch[1] = st->scratch[2] = st->scratch[3] = 0;
+}
+
+// K5b: Export, deterministic table order: (1) live count per 2048-slot tile, (2) exclusive scan of
+// the tile counts, (3) per-tile compaction of keys + rows.
+constexpr int kExportTile = 2048;
+
+__device__ __forceinline__ bool live_key(long long k) { return k != kEmptyKey && k != kTombKey; }
+
+__global__ void __launch_bounds__(kThreads)
+export_count_kernel(TableView t, unsigned* __restrict__ tile_counts, size_t n_tiles) {
+  __shared__ unsigned s_cnt;
+  const size_t cap = t.capacity();
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    unsigned c = 0;
+    for (int q = 0; q < kExportTile / kThreads; ++q) {
+      const size_t s = tile * kExportTile + (size_t)q * kThreads + threadIdx.x;
+      if (s < cap && live_key(t.keys[s])) ++c;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_counts[tile] = s_cnt;
+    __syncthreads();
+  }
+}
+
+// single-block exclusive scan of n_tiles counters -> 64-bit offsets; total (plus special keys) to st
+__global__ void __launch_bounds__(1024)
+export_scan_kernel(const unsigned* __restrict__ tile_counts, unsigned long long* __restrict__ tile_offsets,
+                   size_t n_tiles, DevState* st) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (size_t base = 0; base < n_tiles; base += 1024) {
+    const size_t i = base + threadIdx.x;
+    const unsigned long long v = i < n_tiles ? tile_counts[i] : 0;
+    unsigned long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      unsigned long long ws = s_warp[lane], xs = ws;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(kFull, xs, o);
+        if (lane >= o) xs += y;
+      }
+      s_warp[lane] = xs - ws;  // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    const unsigned long long carry = s_carry;
+    const unsigned long long incl = carry + s_warp[w] + x;
+    if (i < n_tiles) tile_offsets[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st->scratch[0] = s_carry;  // live non-special keys
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+export_write_kernel(TableView t, int plane, unsigned plane_row_bytes,
+                    const unsigned long long* __restrict__ tile_offsets, size_t n_tiles,
+                    long long* __restrict__ keys_out, unsigned char* __restrict__ vals_out, size_t max_n,
+                    RowGeom g) {
+  __shared__ unsigned s_warp_cnt[kWarpsPerBlock];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t cap = t.capacity();
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // each warp owns a contiguous 256-slot strip of the tile -> output order = slot order
+    const size_t strip = tile * kExportTile + (size_t)w * (kExportTile / kWarpsPerBlock);
+    long long k[kExportTile / kThreads];
+    unsigned cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kExportTile / kThreads; ++q) {
+      const size_t s = strip + (size_t)q * 32 + lane;
+      k[q] = s < cap ? t.keys[s] : kEmptyKey;
+      cnt += __popc(__ballot_sync(kFull, live_key(k[q])));
+    }
+    if (lane == 0) s_warp_cnt[w] = cnt;
+    __syncthreads();
+    unsigned long long off = tile_offsets[tile];
+    for (int ww = 0; ww < w; ++ww) off += s_warp_cnt[ww];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kExportTile / kThreads; ++q) {
+      const size_t s = strip + (size_t)q * 32 + lane;
+      const bool lv = live_key(k[q]);
+      const unsigned b = __ballot_sync(kFull, lv);
+      const unsigned long long o = off + __popc(b & ((1u << lane) - 1u));
+      const unsigned char* src = nullptr;
+      unsigned char* dst = nullptr;
+      if (lv && o < max_n) {
+        if (keys_out) keys_out[o] = k[q];
+        if (vals_out) {
+          src = t.planes[plane] + s * plane_row_bytes;
+          dst = vals_out + o * plane_row_bytes;
+        }
+      }
+      if (b && vals_out) warp_move_rows<VEC>(g, src, dst, lane);
+      off += __popc(b);
+    }
+  }
+}
+
+// the two special keys are appended after the regular ones
+__global__ void export_special_kernel(TableView t, int plane, unsigned plane_row_bytes,
+                                      long long* keys_out, unsigned char* vals_out, size_t max_n) {
+  unsigned long long o = t.st->scratch[0];
+  const size_t cap = t.capacity();
+  for (int idx = 0; idx < 2; ++idx) {
+    if (t.st->special[idx]) {
+      if (o < max_n) {
+        if (threadIdx.x == 0 && keys_out) keys_out[o] = idx ? kTombKey : kEmptyKey;
+        if (vals_out) {
+          const unsigned char* src = t.planes[plane] + (cap + idx) * plane_row_bytes;
+          for (unsigned c = threadIdx.x; c < plane_row_bytes; c += blockDim.x)
+            vals_out[o * plane_row_bytes + c] = src[c];
+        }
+      }
+      ++o;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) t.st->scratch[1] = o < max_n ? o : max_n;  // rows written
+}
+
+// Rehash: move every live slot of `src` into `dst` (fresh, all EMPTY).
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+rehash_kernel(TableView src, TableView dst, RowGeom g, RowGeom gslot, int n_planes) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  const size_t cap = src.capacity();
+  for (size_t base = warp0 * 32; base < cap; base += nwarps * 32) {
+    const size_t s = base + lane;
+    const long long key = s < cap ? src.keys[s] : kEmptyKey;
+    const bool valid = live_key(key);
+    if (!__any_sync(kFull, valid)) continue;
+    bool is_new, from_empty;
+    const long long ns = warp_find_or_claim(dst, key, valid, valid, lane, is_new, from_empty);
+    const bool ok = valid && ns >= 0;
+    warp_move_rows<VEC>(g, ok ? src.planes[0] + s * g.row_bytes : nullptr,
+                        ok ? dst.planes[0] + (size_t)ns * g.row_bytes : nullptr, lane);
+    for (int p = 1; p <= n_planes; ++p)
+      warp_move_rows<4>(gslot, ok ? src.planes[p] + s * gslot.row_bytes : nullptr,
+                        ok ? dst.planes[p] + (size_t)ns * gslot.row_bytes : nullptr, lane);
+  }
+}
+__global__ void rehash_fix_state_kernel(DevState* st) {
+  st->used = st->size - st->special[0] - st->special[1];
+}
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+static det_status alloc_planes(det_table* t, uint64_t nb, TableView* v, void** raw) {
+  const size_t cap = nb * kBucket;
+  const size_t key_bytes = cap * sizeof(long long);
+  const size_t val_bytes = (cap + 2) * t->row_bytes;
+  const size_t slot_bytes = (cap + 2) * (size_t)t->cfg.dim * 4u;
+  for (int i = 0; i < 1 + kMaxPlanes; ++i) raw[i] = nullptr;
+  cudaError_t e = cudaMalloc(&raw[0], key_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&raw[1], val_bytes);
+  for (int p = 1; p <= t->cfg.num_slot_planes && e == cudaSuccess; ++p) e = cudaMalloc(&raw[1 + p], slot_bytes);
+  if (e != cudaSuccess) {
+    for (int i = 0; i < 1 + kMaxPlanes; ++i)
+      if (raw[i]) cudaFree(raw[i]);
+    cudaGetLastError();
+    return fail(DET_OUT_OF_MEMORY,
+                "detable: cannot allocate " +
+                    std::to_string((key_bytes + val_bytes + slot_bytes * t->cfg.num_slot_planes) >> 20) +
+                    " MiB of HBM for the table; choose a smaller init/max capacity");
+  }
+  v->keys = (long long*)raw[0];
+  for (int p = 0; p < kMaxPlanes; ++p) v->planes[p] = (unsigned char*)raw[1 + p];
+  v->nb = nb;
+  v->row_bytes = (unsigned)t->row_bytes;
+  v->dim = (unsigned)t->cfg.dim;
+  v->st = t->view.st;
+  return DET_OK;
+}
+
+static size_t planes_bytes(const det_table* t, uint64_t nb) {
+  const size_t cap = nb * kBucket;
+  return cap * 8 + (cap + 2) * t->row_bytes + (size_t)t->cfg.num_slot_planes * (cap + 2) * t->cfg.dim * 4u;
+}
+
+det_status table_clear_async(det_table* t, cudaStream_t s) {
+  const size_t cap = t->view.capacity();
+  fill_keys_kernel<<<grid_for(cap, 1024 * 4, t->sm_count, 8), 1024, 0, s>>>(t->view.keys, cap, kEmptyKey);
+  reset_state_kernel<<<1, 1, 0, s>>>(t->view.st);
+  CUDA_TRY(cudaGetLastError());
+  t->used_ub = 0;
+  return DET_OK;
+}
+
+template <typename F>
+static det_status dispatch_vec(int vec, F&& f) {
+  switch (vec) {
+    case 16: return f(std::integral_constant<int, 16>());
+    case 8: return f(std::integral_constant<int, 8>());
+    case 4: return f(std::integral_constant<int, 4>());
+    case 2: return f(std::integral_constant<int, 2>());
+    default: return f(std::integral_constant<int, 1>());
+  }
+}
+
+static det_status read_state(det_table* t, cudaStream_t s, DevState* out) {
+  CUDA_TRY(cudaMemcpyAsync(t->h_state, t->view.st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *out = *t->h_state;
+  return DET_OK;
+}
+
+static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
+  TableView nv;
+  void* raw[1 + kMaxPlanes];
+  det_status st = alloc_planes(t, new_nb, &nv, raw);
+  if (st != DET_OK) return st;
+  const size_t ncap = new_nb * kBucket;
+  fill_keys_kernel<<<grid_for(ncap, 4096, t->sm_count, 8), 1024, 0, s>>>(nv.keys, ncap, kEmptyKey);
+  const TableView ov = t->view;
+  const int vec = pick_vec(t->row_bytes, nullptr, nullptr, nullptr);
+  const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
+  const RowGeom gs = make_geom((unsigned)t->cfg.dim * 4u, 4);
+  const int np = t->cfg.num_slot_planes;
+  const int grid = grid_for(ov.capacity(), kThreads, t->sm_count, 8);
+  dispatch_vec(vec, [&](auto V) -> det_status {
+    rehash_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(ov, nv, g, gs, np);
+    return DET_OK;
+  });
+  // special rows
+  for (int p = 0; p <= np; ++p) {
+    const size_t rb = p == 0 ? t->row_bytes : (size_t)t->cfg.dim * 4u;
+    CUDA_TRY(cudaMemcpyAsync(nv.planes[p] + ncap * rb, ov.planes[p] + ov.capacity() * rb, 2 * rb,
+                             cudaMemcpyDeviceToDevice, s));
+  }
+  rehash_fix_state_kernel<<<1, 1, 0, s>>>(t->view.st);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < 1 + kMaxPlanes; ++i)
+    if (t->raw[i]) cudaFree(t->raw[i]);
+  for (int i = 0; i < 1 + kMaxPlanes; ++i) t->raw[i] = raw[i];
+  t->view = nv;
+  t->rehash_count++;
+  return DET_OK;
+}
+
+// Make sure `n` more keys fit under the load-factor limit.  Steady state: pure host arithmetic on an
+// upper bound, no sync.  Near the limit: one sync to read the true counters, then grow if needed.
+det_status ensure_room(det_table* t, size_t n, cudaStream_t s) {
+  const double cap = (double)t->view.capacity();
+  const uint64_t limit = (uint64_t)(cap * t->max_lf);
+  if (t->used_ub + n <= limit) {
+    t->used_ub += n;
+    return DET_OK;
+  }
+  DevState ds;
+  det_status st = read_state(t, s, &ds);
+  if (st != DET_OK) return st;
+  const uint64_t special = ds.special[0] + ds.special[1];
+  const uint64_t live = ds.size - special;
+  t->used_ub = ds.used;
+  if (ds.used + n <= limit) {
+    t->used_ub += n;
+    return DET_OK;
+  }
+  // grow (or purge tombstones at the same size when the live set is small)
+  uint64_t nb = t->view.nb;
+  const uint64_t need = live + n;
+  if ((double)need > (double)limit * 0.5) {
+    uint64_t want = (uint64_t)((double)need / t->max_lf / kBucket) + 1;
+    nb = nb * 2 > want ? nb * 2 : want;
+  }
+  if (t->cfg.max_capacity) {
+    const uint64_t max_nb = (t->cfg.max_capacity + kBucket - 1) / kBucket;
+    if (nb > max_nb) nb = max_nb;
+    if ((double)need > (double)(nb * kBucket) * t->max_lf)
+      return fail(DET_TABLE_FULL, "detable: max_capacity reached (" + std::to_string(t->cfg.max_capacity) +
+                                      " slots); " + std::to_string(need) + " keys do not fit");
+  }
+  st = rehash_to(t, nb, s);
+  if (st != DET_OK) return st;
+  t->used_ub = live + n;
+  return DET_OK;
+}
+
+SlotInit slot_init_of(const det_table* t) {
+  SlotInit si;
+  si.n_planes = t->cfg.num_slot_planes;
+  for (int p = 0; p < kMaxPlanes; ++p) si.v[p] = t->slot_init[p];
+  return si;
+}
+
+}  // namespace det
+
+using namespace det;
+
+extern "C" {
+
+int det_abi_version(void) { return 1; }
+
+const char* det_build_info(void) {
+  return "detable sm_100a; nvcc " __DATE__ " " __TIME__ "; 8-slot buckets; 4-lane subgroup probing";
+}
+
+const char* det_last_error(void) { return g_last_error.c_str(); }
+
+det_status det_table_create(det_table** out, const det_config* cfg) {
+  if (!out || !cfg) return fail(DET_INVALID_ARGUMENT, "det_table_create: null argument");
+  const size_t es = dtype_size(cfg->value_dtype);
+  if (es == 0) return fail(DET_INVALID_ARGUMENT, "det_table_create: unsupported value_dtype");
+  if (cfg->dim <= 0) return fail(DET_INVALID_ARGUMENT, "det_table_create: dim must be positive (value_shape must be a vector)");
+  if (cfg->num_slot_planes < 0 || cfg->num_slot_planes >= kMaxPlanes)
+    return fail(DET_INVALID_ARGUMENT, "det_table_create: num_slot_planes must be in [0,3]");
+  if (cfg->num_slot_planes > 0 && cfg->value_dtype != DET_FLOAT32)
+    return fail(DET_INVALID_ARGUMENT, "det_table_create: optimizer slot planes need float32 values");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(DET_INVALID_ARGUMENT, "det_table_create: bad device ordinal");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  det_table* t = new det_table();
+  t->cfg = *cfg;
+  t->row_bytes = es * (size_t)cfg->dim;
+  t->max_lf = cfg->max_load_factor > 0.f ? cfg->max_load_factor : 0.75f;
+  if (t->max_lf > 0.9f) t->max_lf = 0.9f;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  t->sm_count = prop.multiProcessorCount;
+  uint64_t init = cfg->init_capacity ? cfg->init_capacity : 8192;
+  if (cfg->max_capacity && init > cfg->max_capacity) init = cfg->max_capacity;
+  const uint64_t nb = (init + kBucket - 1) / kBucket;
+  for (int i = 0; i < 1 + kMaxPlanes; ++i) t->raw[i] = nullptr;
+  for (int p = 0; p < kMaxPlanes; ++p) t->slot_init[p] = 0.f;
+  cudaError_t e = cudaMalloc((void**)&t->view.st, sizeof(DevState));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&t->h_state, sizeof(DevState));
+  if (e != cudaSuccess) {
+    delete t;
+    return fail(DET_OUT_OF_MEMORY, std::string("det_table_create: ") + cudaGetErrorString(e));
+  }
+  det_status st = alloc_planes(t, nb, &t->view, t->raw);
+  if (st != DET_OK) {
+    cudaFree(t->view.st);
+    cudaFreeHost(t->h_state);
+    delete t;
+    return st;
+  }
+  st = table_clear_async(t, 0);
+  if (st == DET_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_table_create: init failed");
+  if (st != DET_OK) {
+    det_table_destroy(t);
+    return st;
+  }
+  *out = t;
+  return DET_OK;
+}
+
+det_status det_table_destroy(det_table* t) {
+  if (!t) return DET_OK;
+  cudaSetDevice(t->cfg.device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 1 + kMaxPlanes; ++i)
+    if (t->raw[i]) cudaFree(t->raw[i]);
+  if (t->view.st) cudaFree(t->view.st);
+  if (t->h_state) cudaFreeHost(t->h_state);
+  host_pipe_free(t);
+  delete t;
+  return DET_OK;
+}
+
+det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* defaults, int full_size_default,
+                    void* values_out, uint8_t* exists, det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_find: null table");
+  if (n == 0) return DET_OK;
+  if (!keys || !values_out || !defaults) return fail(DET_INVALID_ARGUMENT, "det_find: null keys/values/default_value");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const int vec = pick_vec(t->row_bytes, defaults, values_out, nullptr);
+  const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
+  const int grid = grid_for(n, kThreads, t->sm_count, 8);
+  const TableView v = t->view;
+  return dispatch_vec(vec, [&](auto V) -> det_status {
+    find_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, n,
+                                                              (const unsigned char*)defaults, full_size_default,
+                                                              (unsigned char*)values_out, exists, g);
+    CUDA_TRY(cudaGetLastError());
+    return DET_OK;
+  });
+}
+
+det_status det_insert(det_table* t, const int64_t* keys, const void* values, size_t n, det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert: null table");
+  if (n == 0) return DET_OK;
+  if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert: null keys/values");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det_status st = ensure_room(t, n, s);
+  if (st != DET_OK) return st;
+  const int vec = pick_vec(t->row_bytes, values, nullptr, nullptr);
+  const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
+  const int grid = grid_for(n, kThreads, t->sm_count, 8);
+  const TableView v = t->view;
+  const SlotInit si = slot_init_of(t);
+  return dispatch_vec(vec, [&](auto V) -> det_status {
+    insert_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(v, (const long long*)keys,
+                                                                (const unsigned char*)values, n, g, si);
+    CUDA_TRY(cudaGetLastError());
+    return DET_OK;
+  });
+}
+
+det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists, size_t n,
+                     det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_accum: null table");
+  if (n == 0) return DET_OK;
+  if (!keys || !vod || !exists) return fail(DET_INVALID_ARGUMENT, "det_accum: null keys/values_or_deltas/exists");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det_status st = ensure_room(t, n, s);
+  if (st != DET_OK) return st;
+  const int grid = grid_for(n, kThreads, t->sm_count, 8);
+  const TableView v = t->view;
+  const SlotInit si = slot_init_of(t);
+  const long long* k = (const long long*)keys;
+  switch (t->cfg.value_dtype) {
+    case DET_FLOAT32: accum_kernel<float><<<grid, kThreads, 0, s>>>(v, k, (const float*)vod, exists, n, si); break;
+    case DET_FLOAT64: accum_kernel<double><<<grid, kThreads, 0, s>>>(v, k, (const double*)vod, exists, n, si); break;
+    case DET_INT32: accum_kernel<int><<<grid, kThreads, 0, s>>>(v, k, (const int*)vod, exists, n, si); break;
+    case DET_INT64: accum_kernel<long long><<<grid, kThreads, 0, s>>>(v, k, (const long long*)vod, exists, n, si); break;
+    case DET_INT8: accum_kernel<signed char><<<grid, kThreads, 0, s>>>(v, k, (const signed char*)vod, exists, n, si); break;
+    case DET_FLOAT16: accum_kernel<__half><<<grid, kThreads, 0, s>>>(v, k, (const __half*)vod, exists, n, si); break;
+    case DET_BFLOAT16: accum_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(v, k, (const __nv_bfloat16*)vod, exists, n, si); break;
+    default: return fail(DET_UNIMPLEMENTED, "det_accum: dtype");
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_remove: null table");
+  if (n == 0) return DET_OK;
+  if (!keys) return fail(DET_INVALID_ARGUMENT, "det_remove: null keys");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  remove_kernel<<<grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s>>>(t->view, (const long long*)keys, n);
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_clear(det_table* t, det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_clear: null table");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  return table_clear_async(t, (cudaStream_t)stream);
+}
+
+det_status det_size(det_table* t, int64_t* size_out_host, det_stream_t stream) {
+  if (!t || !size_out_host) return fail(DET_INVALID_ARGUMENT, "det_size: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  DevState ds;
+  det_status st = read_state(t, (cudaStream_t)stream, &ds);
+  if (st != DET_OK) return st;
+  *size_out_host = (int64_t)ds.size;
+  if (ds.error & kErrTableFull) return fail(DET_INTERNAL, "detable: a probe ran out of free slots (table full)");
+  return DET_OK;
+}
+
+det_status det_capacity(det_table* t, uint64_t* out) {
+  if (!t || !out) return fail(DET_INVALID_ARGUMENT, "det_capacity: null argument");
+  *out = t->view.capacity();
+  return DET_OK;
+}
+
+det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_reserve: null table");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const uint64_t limit = (uint64_t)((double)t->view.capacity() * t->max_lf);
+  if (total_keys <= limit) return DET_OK;
+  uint64_t nb = (uint64_t)((double)total_keys / t->max_lf / kBucket) + 1;
+  if (t->cfg.max_capacity && nb * kBucket > t->cfg.max_capacity)
+    return fail(DET_TABLE_FULL, "det_reserve: beyond max_capacity");
+  cudaStream_t s = (cudaStream_t)stream;
+  DevState ds;
+  det_status st = read_state(t, s, &ds);
+  if (st != DET_OK) return st;
+  st = rehash_to(t, nb, s);
+  if (st != DET_OK) return st;
+  t->used_ub = ds.size;
+  return DET_OK;
+}
+
+det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
+                      int64_t* n_out_host, det_stream_t stream) {
+  if (!t || !n_out_host) return fail(DET_INVALID_ARGUMENT, "det_export: null argument");
+  if (plane < 0 || plane > t->cfg.num_slot_planes) return fail(DET_INVALID_ARGUMENT, "det_export: bad plane");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  const TableView v = t->view;
+  const size_t cap = v.capacity();
+  const size_t n_tiles = (cap + kExportTile - 1) / kExportTile;
+  unsigned* counts = nullptr;
+  unsigned long long* offs = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&counts, n_tiles * sizeof(unsigned), s));
+  CUDA_TRY(cudaMallocAsync((void**)&offs, n_tiles * sizeof(unsigned long long), s));
+  const int grid = grid_for(n_tiles, 1, t->sm_count, 8);
+  export_count_kernel<<<grid, kThreads, 0, s>>>(v, counts, n_tiles);
+  export_scan_kernel<<<1, 1024, 0, s>>>(counts, offs, n_tiles, v.st);
+  const unsigned prb = plane == 0 ? (unsigned)t->row_bytes : (unsigned)t->cfg.dim * 4u;
+  const int vec = pick_vec(prb, values_out, nullptr, nullptr);
+  const RowGeom g = make_geom(prb, vec);
+  dispatch_vec(vec, [&](auto V) -> det_status {
+    export_write_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(
+        v, plane, prb, offs, n_tiles, (long long*)keys_out, (unsigned char*)values_out, max_n, g);
+    return DET_OK;
+  });
+  export_special_kernel<<<1, 128, 0, s>>>(v, plane, prb, (long long*)keys_out, (unsigned char*)values_out, max_n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(counts, s));
+  CUDA_TRY(cudaFreeAsync(offs, s));
+  DevState ds;
+  det_status st = read_state(t, s, &ds);
+  if (st != DET_OK) return st;
+  *n_out_host = (int64_t)ds.scratch[1];
+  return DET_OK;
+}
+
+det_status det_import(det_table* t, const int64_t* keys, const void* values, size_t n, det_stream_t stream) {
+  det_status st = det_clear(t, stream);
+  if (st != DET_OK) return st;
+  return det_insert(t, keys, values, n, stream);
+}
+
+det_status det_get_stats(det_table* t, det_stats* out, det_stream_t stream) {
+  if (!t || !out) return fail(DET_INVALID_ARGUMENT, "det_get_stats: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  DevState ds;
+  det_status st = read_state(t, (cudaStream_t)stream, &ds);
+  if (st != DET_OK) return st;
+  out->size = (int64_t)ds.size;
+  out->used_slots = (int64_t)ds.used;
+  out->capacity = t->view.capacity();
+  out->buckets = t->view.nb;
+  out->hbm_bytes = planes_bytes(t, t->view.nb);
+  out->error_flags = ds.error;
+  out->rehash_count = t->rehash_count;
+  return DET_OK;
+}
+
+}  // extern "C"

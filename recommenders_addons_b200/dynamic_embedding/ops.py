@@ -1,0 +1,138 @@
+"""`de.embedding_lookup_sparse` / `de.safe_embedding_lookup_sparse`
+(reference: python/ops/dynamic_embedding_ops.py:120-438)."""
+import ctypes
+
+import torch
+
+from .. import _lib
+from .table import _ptr, _stream_ptr
+from .variable import TrainableWrapper, Variable, embedding_lookup, unique
+
+
+class SparseIds(object):
+  """Minimal stand-in for tf.SparseTensor: `indices` [nnz, rank] int64 in canonical row-major order,
+  `values` [nnz], `dense_shape` (tuple)."""
+
+  def __init__(self, indices, values, dense_shape):
+    self.indices = indices
+    self.values = values
+    self.dense_shape = tuple(int(d) for d in dense_shape)
+
+
+def _fused_ok(params, default_rows):
+  return (params.shard_num == 1 and params.value_dtype == torch.float32 and default_rows.numel() == params.dim)
+
+
+def lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner, default_row=None):
+  """K6: one kernel does find -> *weight -> per-segment sum -> normalise (det_lookup_sparse)."""
+  table = params.tables[0]
+  dev = table.device
+  ids = ids.reshape(-1).to(dev).contiguous()
+  seg = segment_ids.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+  w = None if weights is None else weights.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+  if default_row is None:
+    default_row = table._default_value
+  default_row = default_row.to(device=dev, dtype=torch.float32).contiguous()
+  out = torch.empty((batch, params.dim), dtype=torch.float32, device=dev)
+  _lib.check(_lib.lib().det_lookup_sparse(table.handle, _ptr(ids), _ptr(seg), _ptr(w), ids.numel(), batch,
+                                          _lib.COMBINERS[combiner], _ptr(default_row), _ptr(out),
+                                          _stream_ptr(dev)))
+  return out
+
+
+def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None, name="embedding_lookup_sparse",
+                            combiner="mean", max_norm=None, return_trainable=False):
+  """Dynamic version of tf.nn.embedding_lookup_sparse (dynamic_embedding_ops.py:120-293): for every row of
+  the dense matrix represented by sp_ids, combine (sum / mean / sqrtn) the weighted embeddings of its ids.
+  Result: [dense_shape[0], dim] float32.
+
+  Forward-only calls on a single-shard fp32 variable with a constant default row run the fused kernel;
+  `return_trainable=True`, `max_norm`, sharded variables and random initializers take the composed
+  path (unique -> lookup -> gather*weights -> segment sum), exactly the reference's op sequence."""
+  if combiner not in ("mean", "sqrtn", "sum"):
+    raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
+  if not isinstance(sp_ids, SparseIds):
+    raise TypeError("sp_ids must be SparseTensor")
+  ignore_weights = sp_weights is None
+  if not ignore_weights and not isinstance(sp_weights, SparseIds):
+    raise TypeError("sp_weights must be either None or SparseTensor")
+  if not isinstance(params, Variable):
+    raise TypeError("params should be a Variable instance.")
+  segment_ids = sp_ids.indices[:, 0].to(torch.int32)
+  ids = sp_ids.values
+  batch = sp_ids.dense_shape[0]
+  weights = None if ignore_weights else sp_weights.values
+  static_default = params.initializer is None or not callable(params.initializer)
+  if not return_trainable and max_norm is None and static_default and _fused_ok(params, params.tables[0]._default_value):
+    return lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner)
+
+  uniq, idx = unique(ids)
+  r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)
+  emb_u, tw = r if return_trainable else (r, None)
+  emb = emb_u.to(torch.float32)[idx.long()]
+  seg64 = segment_ids.long().to(emb.device)
+  w = torch.ones(ids.numel(), dtype=torch.float32, device=emb.device) if ignore_weights else \
+      weights.to(device=emb.device, dtype=torch.float32)
+  out = torch.zeros((batch, params.dim), dtype=torch.float32, device=emb.device).index_add(0, seg64, emb * w[:, None])
+  if combiner != "sum":
+    den = torch.zeros(batch, dtype=torch.float32, device=emb.device).index_add(
+        0, seg64, w if combiner == "mean" else w * w)
+    if combiner == "sqrtn":
+      den = den.sqrt()
+    touched = torch.zeros(batch, dtype=torch.bool, device=emb.device)
+    touched[seg64] = True
+    out = torch.where(touched[:, None], out / den[:, None], out)
+  return (out, tw) if return_trainable else out
+
+
+def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=None, combiner="mean",
+                                 default_id=None, name="safe_embedding_lookup_sparse", partition_strategy=None,
+                                 max_norm=None, return_trainable=False):
+  """dynamic_embedding_ops.py:296-438: flatten leading dims, prune weights <= 0 (unless combiner is "sum"),
+  give empty rows `default_id` (or a zero vector when default_id is None), then embedding_lookup_sparse."""
+  shape = sparse_ids.dense_shape
+  rank = len(shape)
+  lead = 1
+  for d in shape[:-1]:
+    lead *= d
+  idx = sparse_ids.indices
+  strides = []
+  s = 1
+  for d in reversed(shape[:-1]):
+    strides.append(s)
+    s *= d
+  strides = list(reversed(strides))
+  row = torch.zeros(idx.shape[0], dtype=torch.int64, device=idx.device)
+  for k in range(rank - 1):
+    row = row + idx[:, k] * strides[k]
+  ids = sparse_ids.values
+  w = None if sparse_weights is None else sparse_weights.values
+  col = idx[:, rank - 1]
+  if combiner != "sum" and w is not None:
+    keep = w > 0
+    row, col, ids, w = row[keep], col[keep], ids[keep], w[keep]
+  # sparse_fill_empty_rows
+  present = torch.zeros(lead, dtype=torch.bool, device=idx.device)
+  present[row] = True
+  empty_rows = torch.nonzero(~present).reshape(-1)
+  if empty_rows.numel():
+    row = torch.cat([row, empty_rows])
+    col = torch.cat([col, torch.zeros_like(empty_rows)])
+    ids = torch.cat([ids, torch.full_like(empty_rows, default_id or 0)])
+    if w is not None:
+      w = torch.cat([w, torch.ones(empty_rows.numel(), dtype=w.dtype, device=w.device)])
+    order = torch.sort(row * (shape[-1] + 1) + col, stable=True).indices
+    row, col, ids = row[order], col[order], ids[order]
+    if w is not None:
+      w = w[order]
+  ind2 = torch.stack([row, col], 1)
+  sp2 = SparseIds(ind2, ids, (lead, shape[-1]))
+  sw2 = None if w is None else SparseIds(ind2, w, (lead, shape[-1]))
+  r = embedding_lookup_sparse(embedding_weights, sp2, sw2, combiner=combiner, max_norm=max_norm,
+                              return_trainable=return_trainable)
+  result, tw = r if return_trainable else (r, None)
+  if default_id is None and empty_rows.numel():
+    result = result.clone()
+    result[empty_rows] = 0
+  final = result.reshape(tuple(shape[:-1]) + (result.shape[-1],))
+  return (final, tw) if return_trainable else final

@@ -1,0 +1,303 @@
+"""Table objects: the Python `LookupInterface` of the reference
+(python/ops/cuckoo_hashtable_ops.py:44-575, python/ops/hkv_hashtable_ops.py) over the C ABI.
+
+Tensors are torch CUDA tensors; only their data pointers and the current CUDA stream cross into
+libdetable.so.  Method names, argument meaning and error behaviour follow the reference:
+TypeError on dtype mismatch ("Signature mismatch. Keys must be dtype ..."), DetError for engine
+failures (the reference raises tf.errors.* through OP_REQUIRES_OK).
+"""
+import ctypes
+import os
+
+import torch
+
+from .. import _lib
+
+_TORCH_TO_NAME = {
+    torch.float32: "float32", torch.float16: "float16", torch.bfloat16: "bfloat16", torch.int32: "int32",
+    torch.int64: "int64", torch.int8: "int8", torch.float64: "float64",
+}
+# the (key, value) dtype pairs the reference registers for its GPU table
+# (python/ops/dynamic_embedding_variable.py:637-645) + float64
+VALID_VALUE_DTYPES = tuple(_TORCH_TO_NAME.keys())
+
+
+def _stream_ptr(device):
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+  return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class KVCreator(object):
+  """python/ops/dynamic_embedding_creator.py:34-78"""
+
+  def __init__(self, config=None, saver=None):
+    self.config = config
+    self.saver = saver
+
+  def create(self, key_dtype=None, value_dtype=None, default_value=None, name=None, checkpoint=None,
+             init_size=None, config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
+    raise NotImplementedError("create function must be implemented")
+
+
+class CuckooHashTableConfig(object):
+  """python/ops/dynamic_embedding_creator.py:80-87"""
+
+  def __init__(self):
+    pass
+
+
+class HkvHashTableConfig(object):
+  """python/ops/dynamic_embedding_creator.py:140-170 (capacity attributes of the HKV ops)."""
+
+  def __init__(self, init_capacity=1024 * 1024, max_capacity=1024 * 1024, max_hbm_for_values=1024 * 1024 * 1024,
+               evict_strategy=None, step_per_epoch=0, gen_scores_fn=None, reserved_key_start_bit=0):
+    self.init_capacity = init_capacity
+    self.max_capacity = max_capacity
+    self.max_hbm_for_values = max_hbm_for_values
+    self.evict_strategy = evict_strategy
+    self.step_per_epoch = step_per_epoch
+    self.gen_scores_fn = gen_scores_fn
+    self.reserved_key_start_bit = reserved_key_start_bit
+
+
+class CuckooHashTable(object):
+  """A generic mutable hash table on one GPU (reference: cuckoo_hashtable_ops.py:44; placed on a GPU the
+  reference dispatches to the HKV ops, :153-165 -- here both names run the same sm_100a engine)."""
+
+  def __init__(self, key_dtype, value_dtype, default_value, name="CuckooHashTable", checkpoint=True, init_size=0,
+               config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0, max_capacity=0,
+               max_load_factor=0.0):
+    if key_dtype != torch.int64:
+      raise TypeError("key dtype %s is not supported on GPU: keys must be int64" % (key_dtype,))
+    if value_dtype not in _TORCH_TO_NAME:
+      raise TypeError("value dtype %s is not supported" % (value_dtype,))
+    if device is None:
+      device = torch.device("cuda", torch.cuda.current_device())
+    self._device = torch.device(device)
+    if self._device.type != "cuda":
+      raise RuntimeError("recommenders_addons_b200 tables live in GPU HBM; device=%s is not a CUDA device "
+                         "(there is no CPU fallback)" % (device,))
+    if self._device.index is None:
+      self._device = torch.device("cuda", torch.cuda.current_device())
+    self._key_dtype = key_dtype
+    self._value_dtype = value_dtype
+    self._default_value = torch.as_tensor(default_value, dtype=value_dtype).reshape(-1).to(self._device)
+    self._dim = int(self._default_value.numel())  # value_shape = default_value.shape (must be a vector)
+    self._name = name
+    self._checkpoint = checkpoint
+    self._init_size = int(init_size)
+    self._config = config
+    self._num_slot_planes = int(num_slot_planes)
+    cfg = _lib.DetConfig()
+    cfg.value_dtype = _lib.DTYPE_CODES[_TORCH_TO_NAME[value_dtype]]
+    cfg.dim = self._dim
+    cfg.device = self._device.index
+    cfg.num_slot_planes = self._num_slot_planes
+    cfg.init_capacity = self._init_size
+    cfg.max_capacity = int(max_capacity)
+    cfg.max_load_factor = float(max_load_factor)
+    cfg.flags = 0
+    self._lib = _lib.lib()
+    h = ctypes.c_void_p()
+    _lib.check(self._lib.det_table_create(ctypes.byref(h), ctypes.byref(cfg)))
+    self._h = h
+
+  # -- properties of LookupInterface ---------------------------------------------------------
+  @property
+  def name(self):
+    return self._name
+
+  @property
+  def key_dtype(self):
+    return self._key_dtype
+
+  @property
+  def value_dtype(self):
+    return self._value_dtype
+
+  @property
+  def dim(self):
+    return self._dim
+
+  @property
+  def device(self):
+    return self._device
+
+  @property
+  def handle(self):
+    return self._h
+
+  def _check_keys(self, keys):
+    if not torch.is_tensor(keys):
+      keys = torch.as_tensor(keys, dtype=self._key_dtype)
+    if keys.dtype != self._key_dtype:
+      raise TypeError("Signature mismatch. Keys must be dtype %s, got %s." % (self._key_dtype, keys.dtype))
+    return keys.to(self._device).contiguous()
+
+  def _check_values(self, values, n, what="Values"):
+    if not torch.is_tensor(values):
+      values = torch.as_tensor(values, dtype=self._value_dtype)
+    if values.dtype != self._value_dtype:
+      raise TypeError("Signature mismatch. %s must be dtype %s, got %s." % (what, self._value_dtype, values.dtype))
+    values = values.to(self._device).contiguous()
+    if values.numel() != n * self._dim:
+      # CheckKeyAndValueTensorsForInsert (cuckoo_hashtable_op.cc:671)
+      raise ValueError("Expected shape %s for value, got %s" % ([n, self._dim], list(values.shape)))
+    return values
+
+  # -- ops ------------------------------------------------------------------------------------
+  def size(self, name=None):
+    """Number of elements (0-d int64 tensor, like the reference's Size op)."""
+    out = ctypes.c_int64(0)
+    _lib.check(self._lib.det_size(self._h, ctypes.byref(out), _stream_ptr(self._device)))
+    return torch.tensor(out.value, dtype=torch.int64)
+
+  def capacity(self):
+    out = ctypes.c_uint64(0)
+    _lib.check(self._lib.det_capacity(self._h, ctypes.byref(out)))
+    return int(out.value)
+
+  def reserve(self, total_keys):
+    _lib.check(self._lib.det_reserve(self._h, int(total_keys), _stream_ptr(self._device)))
+
+  def stats(self):
+    st = _lib.DetStats()
+    _lib.check(self._lib.det_get_stats(self._h, ctypes.byref(st), _stream_ptr(self._device)))
+    return {f: getattr(st, f) for f, _ in _lib.DetStats._fields_}
+
+  def remove(self, keys, name=None):
+    keys = self._check_keys(keys).reshape(-1)
+    _lib.check(self._lib.det_remove(self._h, _ptr(keys), keys.numel(), _stream_ptr(self._device)))
+
+  def clear(self, name=None):
+    _lib.check(self._lib.det_clear(self._h, _stream_ptr(self._device)))
+
+  def lookup(self, keys, dynamic_default_values=None, return_exists=False, name=None):
+    """Find / FindWithExists.  Values have shape keys.shape + [dim]; a missing key gets the default
+    row: dynamic_default_values[i] if it is full-size, else its first row, else the static default."""
+    keys = self._check_keys(keys)
+    shape = tuple(keys.shape)
+    flat = keys.reshape(-1)
+    n = flat.numel()
+    default = self._default_value if dynamic_default_values is None else dynamic_default_values
+    if not torch.is_tensor(default):
+      default = torch.as_tensor(default, dtype=self._value_dtype)
+    if default.dtype != self._value_dtype:
+      raise TypeError("Signature mismatch. default_value must be dtype %s, got %s." % (self._value_dtype, default.dtype))
+    default = default.to(self._device).contiguous()
+    full = 1 if (n > 0 and default.numel() == n * self._dim) else 0
+    if not full and default.numel() < self._dim:
+      raise ValueError("default_value must hold at least one row of %d elements" % self._dim)
+    values = torch.empty(shape + (self._dim,), dtype=self._value_dtype, device=self._device)
+    exists = torch.empty(shape, dtype=torch.bool, device=self._device) if return_exists else None
+    _lib.check(self._lib.det_find(self._h, _ptr(flat), n, _ptr(default), full, _ptr(values), _ptr(exists),
+                                  _stream_ptr(self._device)))
+    return (values, exists) if return_exists else values
+
+  def insert(self, keys, values, name=None):
+    keys = self._check_keys(keys).reshape(-1)
+    values = self._check_values(values, keys.numel())
+    _lib.check(self._lib.det_insert(self._h, _ptr(keys), _ptr(values), keys.numel(), _stream_ptr(self._device)))
+
+  def accum(self, keys, values_or_deltas, exists, name=None):
+    keys = self._check_keys(keys).reshape(-1)
+    vod = self._check_values(values_or_deltas, keys.numel(), "values_or_deltas")
+    if not torch.is_tensor(exists):
+      exists = torch.as_tensor(exists, dtype=torch.bool)
+    if exists.dtype != torch.bool:
+      raise TypeError("Signature mismatch. exists must be dtype bool, got %s." % (exists.dtype,))
+    exists = exists.to(self._device).contiguous().reshape(-1)
+    if exists.numel() != keys.numel():
+      raise ValueError("exists must have the same shape as keys")
+    _lib.check(self._lib.det_accum(self._h, _ptr(keys), _ptr(vod), _ptr(exists), keys.numel(),
+                                   _stream_ptr(self._device)))
+
+  def export(self, name=None, plane=0):
+    """(keys, values) of everything in the table, in table order (undefined, as in the reference)."""
+    n = int(self.size())
+    vdtype = self._value_dtype if plane == 0 else torch.float32
+    keys = torch.empty(n, dtype=torch.int64, device=self._device)
+    values = torch.empty((n, self._dim), dtype=vdtype, device=self._device)
+    got = ctypes.c_int64(0)
+    _lib.check(self._lib.det_export(self._h, int(plane), _ptr(keys), _ptr(values), n, ctypes.byref(got),
+                                    _stream_ptr(self._device)))
+    return keys[:got.value], values[:got.value]
+
+  def import_(self, keys, values):
+    """ImportValues = clear + insert (cuckoo_hashtable_op.cc:288-291)."""
+    keys = self._check_keys(keys).reshape(-1)
+    values = self._check_values(values, keys.numel())
+    _lib.check(self._lib.det_import(self._h, _ptr(keys), _ptr(values), keys.numel(), _stream_ptr(self._device)))
+
+  # host-tensor flavour of lookup / insert (ops placed on host tensors; used by bench e2e)
+  def lookup_host(self, keys_host, default_host, values_out_host, exists_out_host=None):
+    n = keys_host.numel()
+    full = 1 if default_host.numel() == n * self._dim and n > 0 else 0
+    torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_find_host(self._h, _ptr(keys_host), n, _ptr(default_host), full,
+                                       _ptr(values_out_host), _ptr(exists_out_host)))
+
+  def insert_host(self, keys_host, values_host):
+    torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_insert_host(self._h, _ptr(keys_host), _ptr(values_host), keys_host.numel()))
+
+  # file-system format (cuckoo_hashtable_ops.py:425-523)
+  def save_to_file_system(self, dirpath, file_name=None, dirpath_env="TFRA_SAVED_KV", append_to_file=False,
+                          buffer_size=4194304, name=None):
+    dirpath = os.environ.get(dirpath_env) or dirpath
+    os.makedirs(dirpath, exist_ok=True)
+    prefix = os.path.join(dirpath, file_name if file_name else self._name)
+    torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_save(self._h, prefix.encode(), int(buffer_size)))
+
+  def load_from_file_system(self, dirpath, file_name=None, dirpath_env="TFRA_SAVED_KV", load_entire_dir=False,
+                            buffer_size=4194304, name=None):
+    dirpath = os.environ.get(dirpath_env) or dirpath
+    prefix = os.path.join(dirpath, file_name if file_name else self._name)
+    torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_load(self._h, prefix.encode(), int(buffer_size)))
+
+  def close(self):
+    if getattr(self, "_h", None) is not None and self._h:
+      self._lib.det_table_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+class HkvHashTable(CuckooHashTable):
+  """python/ops/hkv_hashtable_ops.py: same LookupInterface, capacity taken from HkvHashTableConfig."""
+
+  def __init__(self, key_dtype, value_dtype, default_value, name="HkvHashTable", checkpoint=True, init_size=0,
+               config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
+    cfg = config if config is not None else HkvHashTableConfig()
+    super().__init__(key_dtype, value_dtype, default_value, name=name, checkpoint=checkpoint,
+                     init_size=cfg.init_capacity if cfg.init_capacity else init_size, config=cfg, device=device,
+                     num_slot_planes=num_slot_planes, max_capacity=0, max_load_factor=0.0)
+
+
+class CuckooHashTableCreator(KVCreator):
+  """python/ops/dynamic_embedding_creator.py:89-138"""
+
+  def create(self, key_dtype=None, value_dtype=None, default_value=None, name=None, checkpoint=None,
+             init_size=None, config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
+    return CuckooHashTable(key_dtype=key_dtype, value_dtype=value_dtype, default_value=default_value, name=name,
+                           checkpoint=checkpoint, init_size=init_size or 0, config=config or self.config,
+                           device=device, num_slot_planes=num_slot_planes)
+
+
+class HkvHashTableCreator(KVCreator):
+  """python/ops/dynamic_embedding_creator.py:172-240"""
+
+  def create(self, key_dtype=None, value_dtype=None, default_value=None, name=None, checkpoint=None,
+             init_size=None, config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
+    return HkvHashTable(key_dtype=key_dtype, value_dtype=value_dtype, default_value=default_value, name=name,
+                        checkpoint=checkpoint, init_size=init_size or 0, config=config or self.config,
+                        device=device, num_slot_planes=num_slot_planes)

@@ -1,0 +1,308 @@
+"""`de.Variable`, `de.get_variable`, `de.embedding_lookup`, `de.embedding_lookup_unique`
+(reference: python/ops/dynamic_embedding_variable.py:165-197, 478-1007, 1265-1530;
+python/ops/dynamic_embedding_ops.py:64-117) on torch CUDA tensors over the C ABI."""
+import ctypes
+
+import torch
+
+from .. import _lib
+from .table import CuckooHashTableCreator, KVCreator, _ptr, _stream_ptr
+
+_VARIABLES = {}
+
+
+def default_partition_fn(keys, shard_num, gpu_mode=True):
+  """The default partition function ("mod" strategy), dynamic_embedding_variable.py:165-197:
+  (key & 0x7fffffff) % shard_num on GPU builds (int32 arithmetic), floor-mod(key, shard_num) otherwise."""
+  if shard_num <= 1:
+    return torch.zeros(keys.shape, dtype=torch.int32, device=keys.device)
+  if gpu_mode:
+    k32 = (keys & 0x7fffffff).to(torch.int32)
+    return torch.remainder(k32, shard_num).to(torch.int32)
+  return torch.remainder(keys, shard_num).to(torch.int32)
+
+
+def unique(ids):
+  """tf.unique on the GPU: (unique values in first-occurrence order, int32 index of each id)."""
+  flat = ids.reshape(-1).contiguous()
+  n = flat.numel()
+  dev = flat.device
+  lib = _lib.lib()
+  uniq = torch.empty(n, dtype=torch.int64, device=dev)
+  idx = torch.empty(n, dtype=torch.int32, device=dev)
+  cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+  ws_bytes = lib.det_unique_workspace_bytes(n)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  _lib.check(lib.det_unique(_ptr(flat), n, _ptr(uniq), _ptr(idx), _ptr(cnt), _ptr(ws), ws_bytes, _stream_ptr(dev)))
+  return uniq[:int(cnt.item())], idx
+
+
+def partition(keys, shard_num, gpu_mode=True):
+  """default_partition_fn + dynamic_partition in one pass: keys grouped by owner (stable), the original
+  position of every grouped key, and the per-shard counts (host list)."""
+  flat = keys.reshape(-1).contiguous()
+  n = flat.numel()
+  dev = flat.device
+  lib = _lib.lib()
+  keys_out = torch.empty_like(flat)
+  perm = torch.empty(n, dtype=torch.int32, device=dev)
+  counts = torch.zeros(shard_num, dtype=torch.int64, device=dev)
+  ws_bytes = lib.det_partition_workspace_bytes(n, shard_num)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  _lib.check(lib.det_partition(_ptr(flat), n, shard_num, 1 if gpu_mode else 0, _ptr(keys_out), _ptr(perm),
+                               _ptr(counts), _ptr(ws), ws_bytes, _stream_ptr(dev)))
+  return keys_out, perm, counts
+
+
+def gather_rows(rows, perm):
+  """rows_out[j] = rows[perm[j]]"""
+  rows = rows.contiguous()
+  n = perm.numel()
+  out = torch.empty((n,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+  rb = rows[0].numel() * rows.element_size() if n else 0
+  _lib.check(_lib.lib().det_gather_rows(_ptr(rows), _ptr(perm), n, rb, _ptr(out), _stream_ptr(rows.device)))
+  return out
+
+
+def scatter_rows(rows, perm):
+  """rows_out[perm[j]] = rows[j]  (dynamic_stitch)"""
+  rows = rows.contiguous()
+  n = perm.numel()
+  out = torch.empty_like(rows)
+  rb = rows[0].numel() * rows.element_size() if n else 0
+  _lib.check(_lib.lib().det_scatter_rows(_ptr(rows), _ptr(perm), n, rb, _ptr(out), _stream_ptr(rows.device)))
+  return out
+
+
+class Variable(object):
+  """A distributed dynamic-embedding variable: a set of hash tables, one per entry of `devices`
+  (dynamic_embedding_variable.py:478-693).  It is not a tensor: rows appear when they are first written."""
+
+  def __init__(self, key_dtype=torch.int64, value_dtype=torch.float32, dim=1, devices=None,
+               partitioner=default_partition_fn, shared_name=None, name="DynamicEmbedding_Variable",
+               initializer=None, trainable=True, checkpoint=True, init_size=0, kv_creator=None,
+               restrict_policy=None, bp_v2=False, num_slot_planes=0):
+    self.key_dtype = key_dtype
+    self.value_dtype = value_dtype
+    self.dim = int(dim)
+    self.bp_v2 = bp_v2
+    self.name = name
+    self.trainable = trainable
+    self.checkpoint = checkpoint
+    self.partition_fn = partitioner
+    self.initializer = initializer
+    if devices is None:
+      devices = ["cuda:%d" % torch.cuda.current_device()]
+    self.devices = [torch.device(d) for d in (devices if isinstance(devices, (list, tuple)) else [devices])]
+    self.shard_num = len(self.devices)
+    self.init_size = int(init_size)
+    self.kv_creator = kv_creator if kv_creator else CuckooHashTableCreator()
+    if not isinstance(self.kv_creator, KVCreator):
+      raise TypeError("config should be instance of 'config', but got %s" % type(self.kv_creator))
+    if restrict_policy is not None:
+      raise NotImplementedError("restrict policies are out of scope of the hot path (SURVEY.md 2, #20)")
+    if key_dtype != torch.int64:
+      raise TypeError("key-value dtype (%s-%s) is not support! keys must be int64 on GPU" % (key_dtype, value_dtype))
+    static_default = self._convert_anything_to_init(initializer, self.dim)
+    self._tables = []
+    for idx, dev in enumerate(self.devices):
+      self._tables.append(
+          self.kv_creator.create(key_dtype=key_dtype, value_dtype=value_dtype, default_value=static_default,
+                                 name=self._make_name(idx), checkpoint=checkpoint,
+                                 init_size=int(self.init_size / self.shard_num), device=dev,
+                                 num_slot_planes=num_slot_planes))
+
+  # dynamic_embedding_variable.py:712-766: any initializer -> one static default row [dim]
+  def _convert_anything_to_init(self, raw_init, dim):
+    init = raw_init
+    if init is None:
+      return torch.zeros(dim, dtype=self.value_dtype)
+    if callable(init):
+      try:
+        init = init([dim])
+      except Exception:
+        init = init([1])
+    init = torch.as_tensor(init)
+    if init.numel() == dim:
+      return init.reshape(dim).to(self.value_dtype)
+    first = init.reshape(-1)[0] if init.numel() > 0 else torch.zeros((), dtype=self.value_dtype)
+    return torch.full((dim,), first.item()).to(self.value_dtype)
+
+  def _make_name(self, table_idx):
+    return "{}_mht_{}of{}".format(self.name.replace("/", "_"), table_idx + 1, self.shard_num)
+
+  @property
+  def tables(self):
+    return self._tables
+
+  def _partition(self, keys):
+    """-> (grouped keys, perm or None, list of (begin, end) per shard)"""
+    flat = keys.reshape(-1)
+    if self.shard_num <= 1:
+      return flat, None, [(0, flat.numel())]
+    if self.partition_fn is default_partition_fn:
+      grouped, perm, counts = partition(flat.to(self.devices[0]), self.shard_num, True)
+    else:
+      owner = self.partition_fn(flat, self.shard_num).to(torch.int64)
+      perm64 = torch.sort(owner, stable=True).indices
+      grouped, perm = flat[perm64], perm64.to(torch.int32)
+      counts = torch.bincount(owner, minlength=self.shard_num)
+    bounds, b = [], 0
+    for c in counts.tolist():
+      bounds.append((b, b + int(c)))
+      b += int(c)
+    return grouped, perm, bounds
+
+  def upsert(self, keys, values, name=None):
+    """Insert or update `keys` with `values` (:772-804)."""
+    values = values.reshape(-1, self.dim)
+    grouped, perm, bounds = self._partition(keys)
+    vals = values if perm is None else gather_rows(values, perm)
+    for idx, (b, e) in enumerate(bounds):
+      if e > b:
+        self._tables[idx].insert(grouped[b:e], vals[b:e])
+
+  def accum(self, keys, old_values, new_values, exists, name=None):
+    """Insert `keys` if absent, else accumulate new - old (:806-855):
+    values_or_deltas = where(exists, new_values - old_values, new_values)."""
+    old_values = old_values.reshape(-1, self.dim)
+    new_values = new_values.reshape(-1, self.dim)
+    exists = torch.as_tensor(exists, dtype=torch.bool, device=new_values.device).reshape(-1)
+    vod = torch.where(exists.reshape(-1, 1), new_values - old_values, new_values)
+    grouped, perm, bounds = self._partition(keys)
+    if perm is not None:
+      vod = gather_rows(vod, perm)
+      exists = exists[perm.long()]
+    for idx, (b, e) in enumerate(bounds):
+      if e > b:
+        self._tables[idx].accum(grouped[b:e], vod[b:e], exists[b:e])
+
+  def remove(self, keys, name=None):
+    grouped, _, bounds = self._partition(keys)
+    for idx, (b, e) in enumerate(bounds):
+      if e > b:
+        self._tables[idx].remove(grouped[b:e])
+
+  def clear(self, name=None):
+    for t in self._tables:
+      t.clear()
+
+  def _create_default_values_by_initializer(self, n, device):
+    """:919-931: a callable initializer yields one default row per looked-up key ([n, dim])."""
+    if self.initializer is None or not callable(self.initializer):
+      return None
+    try:
+      return torch.as_tensor(self.initializer([n, self.dim])).to(device=device, dtype=self.value_dtype)
+    except Exception:
+      return torch.as_tensor(self.initializer([self.dim])).to(device=device, dtype=self.value_dtype)
+
+  def lookup(self, keys, return_exists=False, name=None):
+    """Values for `keys` (shape keys.shape + [dim]); absent keys give the initializer/default row and are
+    NOT inserted (:933-986)."""
+    shape = tuple(keys.shape)
+    grouped, perm, bounds = self._partition(keys)
+    vals, exs = [], []
+    for idx, (b, e) in enumerate(bounds):
+      part = grouped[b:e]
+      dyn = self._create_default_values_by_initializer(e - b, self._tables[idx].device) if e > b else None
+      r = self._tables[idx].lookup(part, dynamic_default_values=dyn, return_exists=return_exists)
+      if return_exists:
+        vals.append(r[0])
+        exs.append(r[1])
+      else:
+        vals.append(r)
+    values = vals[0] if len(vals) == 1 else torch.cat(vals, 0)
+    if perm is not None:
+      values = scatter_rows(values, perm)
+    values = values.reshape(shape + (self.dim,))
+    if return_exists:
+      ex = exs[0] if len(exs) == 1 else torch.cat(exs, 0)
+      if perm is not None:
+        out = torch.empty_like(ex)
+        out[perm.long()] = ex
+        ex = out
+      return values, ex.reshape(shape)
+    return values
+
+  def export(self, name=None):
+    ks, vs = zip(*[t.export() for t in self._tables])
+    return torch.cat(ks, 0), torch.cat(vs, 0)
+
+  def size(self, index=None, name=None):
+    if index is not None:
+      return self._tables[index].size()
+    return torch.stack([t.size() for t in self._tables]).sum()
+
+  def embedding_lookup(self, ids, name=None, max_norm=None, return_trainable=False):
+    return embedding_lookup(self, ids, name=name, max_norm=max_norm, return_trainable=return_trainable)
+
+
+class TrainableWrapper(object):
+  """Dense scratch view of the rows of `params` selected by `ids` (python/ops/embedding_weights.py:123-170):
+  filled from the table before each read; the optimizer writes the update back to the table."""
+
+  def __init__(self, params, ids, values, exists=None):
+    self.params = params
+    self.ids = ids
+    self.values = values  # [n, dim] leaf tensor, requires_grad for trainable params
+    self.exists = exists
+
+
+def _clip(values, max_norm):
+  """embedding_weights.py:497-521 (tf.clip_by_norm over the last axis)."""
+  if max_norm is None:
+    return values
+  norm = values.norm(dim=-1, keepdim=True)
+  return values * (max_norm / torch.maximum(norm, torch.as_tensor(max_norm, dtype=values.dtype,
+                                                                    device=values.device)))
+
+
+def embedding_lookup(params, ids, partition_strategy=None, name=None, validate_indices=None, max_norm=None,
+                     return_trainable=False):
+  """de.embedding_lookup (:1362-1530).  `ids` may have any shape; the result is ids.shape + [dim]."""
+  if not isinstance(params, Variable):
+    raise TypeError("params should be a Variable instance.")
+  if params.key_dtype != ids.dtype:
+    raise TypeError("params.key_dtype should be same with ids.dtype: {} vs. {}".format(params.key_dtype, ids.dtype))
+  flat = ids.reshape(-1)
+  if params.bp_v2:
+    vals, exists = params.lookup(flat, return_exists=True)
+  else:
+    vals, exists = params.lookup(flat), None
+  vals = vals.reshape(-1, params.dim)
+  tw = None
+  if return_trainable:
+    vals = vals.detach().requires_grad_(params.trainable and vals.dtype.is_floating_point)
+    tw = TrainableWrapper(params, flat, vals, exists)
+  out = _clip(vals, max_norm).reshape(tuple(ids.shape) + (params.dim,))
+  return (out, tw) if return_trainable else out
+
+
+def embedding_lookup_unique(params, ids, partition_strategy=None, name=None, validate_indices=None, max_norm=None,
+                            return_trainable=False):
+  """de.embedding_lookup_unique (dynamic_embedding_ops.py:64-117): unique -> lookup -> gather."""
+  flat = ids.reshape(-1)
+  uniq, idx = unique(flat)
+  r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)
+  emb, tw = r if return_trainable else (r, None)
+  out = emb[idx.long()].reshape(tuple(ids.shape) + (params.dim,))
+  return (out, tw) if return_trainable else out
+
+
+def get_variable(name, key_dtype=torch.int64, value_dtype=torch.float32, dim=1, devices=None,
+                 partitioner=default_partition_fn, shared_name="get_variable", initializer=None, trainable=True,
+                 checkpoint=True, init_size=0, kv_creator=None, restrict_policy=None, bp_v2=False,
+                 num_slot_planes=0):
+  """de.get_variable (:1265-1359): one Variable per name."""
+  if name in _VARIABLES:
+    raise ValueError("Variable %s has already existed." % name)
+  var = Variable(key_dtype=key_dtype, value_dtype=value_dtype, dim=dim, devices=devices, partitioner=partitioner,
+                 shared_name=shared_name, name=name, initializer=initializer, trainable=trainable,
+                 checkpoint=checkpoint, init_size=init_size, kv_creator=kv_creator,
+                 restrict_policy=restrict_policy, bp_v2=bp_v2, num_slot_planes=num_slot_planes)
+  _VARIABLES[name] = var
+  return var
+
+
+def _reset_variables():
+  _VARIABLES.clear()

@@ -1,0 +1,117 @@
+"""Host-side logic that needs no GPU: partition function parity, import surface, and the multi-rank key
+exchange (world_size 2, gloo) with an in-memory stand-in for the local shard."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle as O
+
+
+def test_import_surface():
+  from recommenders_addons_b200 import dynamic_embedding as de
+  for name in ("get_variable", "Variable", "embedding_lookup", "embedding_lookup_unique", "embedding_lookup_sparse",
+               "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "CuckooHashTable", "HkvHashTable",
+               "CuckooHashTableCreator", "HkvHashTableCreator", "default_partition_fn"):
+    assert hasattr(de, name), name
+
+
+def test_default_partition_fn_matches_oracle():
+  from recommenders_addons_b200 import dynamic_embedding as de
+  rng = np.random.default_rng(0)
+  k = rng.integers(-2**63, 2**63 - 1, size=4096, dtype=np.int64)
+  for s in (1, 2, 3, 8):
+    for gpu_mode in (True, False):
+      got = de.default_partition_fn(torch.from_numpy(k), s, gpu_mode).numpy()
+      np.testing.assert_array_equal(got, O.default_partition_fn(k, s, gpu_mode))
+
+
+def test_table_requires_cuda_and_fails_loudly():
+  from recommenders_addons_b200 import dynamic_embedding as de
+  if torch.cuda.is_available():
+    pytest.skip("GPU present")
+  with pytest.raises(Exception):
+    de.CuckooHashTable(torch.int64, torch.float32, [0.0] * 4, device="cpu")
+  with pytest.raises(Exception):
+    de.get_variable("no_gpu_var", dim=4)
+
+
+def test_dtype_checks():
+  from recommenders_addons_b200 import dynamic_embedding as de
+  with pytest.raises(TypeError):
+    de.CuckooHashTable(torch.int32, torch.float32, [0.0], device="cuda:0")
+
+
+class _DictShard(object):
+  """CPU stand-in with Variable's lookup/upsert surface, for exchange-logic tests only."""
+
+  def __init__(self, dim):
+    self.dim = dim
+    self.d = {}
+
+  def lookup(self, keys):
+    out = torch.zeros((keys.numel(), self.dim))
+    for i, k in enumerate(keys.tolist()):
+      if k in self.d:
+        out[i] = self.d[k]
+    return out
+
+  def upsert(self, keys, values):
+    for k, v in zip(keys.tolist(), values):
+      self.d[k] = v.clone()
+
+
+def _cpu_partition(world):
+  def f(keys):
+    owner = torch.from_numpy(O.default_partition_fn(keys.numpy(), world, True)).long()
+    perm = torch.sort(owner, stable=True).indices
+    return keys[perm], perm.to(torch.int32), torch.bincount(owner, minlength=world)
+  return f
+
+
+def _worker(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from recommenders_addons_b200.dynamic_embedding.sharded import ShardedVariable
+  dim = 4
+  sv = ShardedVariable(_DictShard(dim), partition_impl=_cpu_partition(world),
+                       gather_impl=lambda rows, perm: rows[perm.long()],
+                       scatter_impl=lambda rows, perm: torch.empty_like(rows).index_copy_(0, perm.long(), rows))
+  g = torch.Generator().manual_seed(100 + rank)
+  keys = torch.unique(torch.randint(0, 10000, (500,), generator=g))
+  vals = keys.float().reshape(-1, 1).repeat(1, dim) + 0.5 * rank  # value encodes (key, writer)
+  sv.upsert(keys, vals)
+  dist.barrier()
+  # every key this rank owns must satisfy the partition rule
+  own = torch.tensor(sorted(sv.local.d.keys()))
+  assert bool((torch.from_numpy(O.default_partition_fn(own.numpy(), world, True)) == rank).all())
+  # lookups of keys written by BOTH ranks come back in request order, from whichever rank owns them
+  other = torch.unique(torch.randint(0, 10000, (500,), generator=torch.Generator().manual_seed(100 + (1 - rank))))
+  q_keys = torch.cat([keys[:50], other[:50], torch.tensor([20001, 20002])])
+  rows = sv.lookup(q_keys)
+  base = rows[:, 0] - q_keys.float()
+  ok = bool(((base == 0.0) | (base == 0.5) | (rows[:, 0] == 0)).all()) and bool((rows[-2:] == 0).all())
+  ok = ok and bool((rows[:50, 0] - keys[:50].float()).abs().max() <= 0.5)
+  q.put((rank, ok, len(sv.local.d)))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_sharded_exchange_world2_gloo():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29500 + (os.getpid() % 500)
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in range(2)]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert all(ok for _, ok, _ in res), res
+  assert sum(n for _, _, n in res) > 0
