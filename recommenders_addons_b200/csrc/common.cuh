@@ -19,6 +19,9 @@ constexpr long long kEmptyKey = (long long)0x8000000000000000ULL;  // INT64_MIN
 constexpr long long kTombKey = kEmptyKey + 1;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxPlanes = 4;  // plane 0 = values, 1..3 = optimizer slots
+// first word of an optimizer-slot row whose key was created by insert/accum and never stepped (a quiet NaN
+// payload no optimizer produces): the fused optimizer treats such a row as "slot absent -> initializer"
+constexpr unsigned kSlotUninit = 0x7fc0de7au;
 
 enum : unsigned { kErrTableFull = 1u, kErrBadSegment = 2u };
 

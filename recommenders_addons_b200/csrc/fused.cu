@@ -369,8 +369,14 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
       const unsigned j = j0 + sub;
       const long long s = shfl_ll(slot, (int)j);
       const bool nw = (bn >> j) & 1u;
-      if (base + j >= n || s < 0) continue;
-      const size_t ro = (size_t)s * dim;
+      const bool row_ok = (base + j < n) && s >= 0;
+      const size_t ro = row_ok ? (size_t)s * dim : 0;
+      // slot state absent: key created in this launch, or created by insert/accum and never stepped.
+      // Every lane reads the marker word BEFORE any lane of the row's group overwrites it.
+      const unsigned mark = row_ok ? __float_as_uint(S1[ro]) : 0u;
+      __syncwarp();
+      if (!row_ok) continue;
+      const bool fresh = nw || (mark == kSlotUninit);
       const float* g_row = grads + (base + j) * dim;
       const float* i_row = full_init ? init_param + (base + j) * dim : init_param;
       for (unsigned c = c0; c < vpr; c += lpr) {
@@ -379,7 +385,7 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
         g.load(g_row + o);
         if (nw) p.load(i_row + o); else p.load(P + ro + o);
         if (OPT == 0) {
-          if (nw) a.fill(h.init_slot); else a.load(S1 + ro + o);
+          if (fresh) a.fill(h.init_slot); else a.load(S1 + ro + o);
           // accum += g*g ; var -= lr*g / (sqrt(accum) + eps)
           a.zip(g, [](float& av, float gv) { av = av + gv * gv; });
           FVec<VF> upd = g;
@@ -389,7 +395,7 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
           p.store(P + ro + o);
         } else {
           FVec<VF> m, v;
-          if (nw) { m.zero(); v.zero(); } else { m.load(S1 + ro + o); v.load(S2 + ro + o); }
+          if (fresh) { m.zero(); v.zero(); } else { m.load(S1 + ro + o); v.load(S2 + ro + o); }
           // m += (g-m)(1-b1) ; v += (g*g-v)(1-b2) ; var -= (m*alpha)/(sqrt(v)+eps)
           m.zip(g, [omb1](float& mv, float gv) { mv = mv + (gv - mv) * omb1; });
           v.zip(g, [omb2](float& vv, float gv) { vv = vv + (gv * gv - vv) * omb2; });

@@ -87,17 +87,6 @@ find_kernel(TableView t, const long long* __restrict__ keys, size_t n,
   }
 }
 
-// fill `rows` consecutive fp32 rows of a slot plane with a constant (used for new keys)
-__device__ __forceinline__ void warp_fill_rows_f32(unsigned char* my_dst, unsigned dim, float value,
-                                                   int lane) {
-  for (int j = 0; j < 32; ++j) {
-    float* d = (float*)shfl_ll((long long)my_dst, j);
-    if (d) {
-      for (unsigned c = lane; c < dim; c += 32) d[c] = value;
-    }
-  }
-}
-
 struct SlotInit {
   float v[kMaxPlanes];
   int n_planes;  // number of slot planes (excluding values)
@@ -135,12 +124,12 @@ insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned ch
       dst = t.planes[0] + (size_t)slot * g.row_bytes;
     }
     warp_move_rows<VEC>(g, src, dst, lane);
-    if (si.n_planes > 0 && bn) {
-      for (int p = 1; p <= si.n_planes; ++p) {
-        unsigned char* d = (is_new && slot >= 0) ? t.planes[p] + (size_t)slot * t.dim * 4u : nullptr;
-        warp_fill_rows_f32(d, t.dim, si.v[p], lane);
-      }
-    }
+    // a key created outside the optimizer has no slot state yet: mark its slot rows "uninitialised" (the
+    // reference keeps slots in separate tables, where such a key is simply absent and reads the slot
+    // initializer at the next optimizer step)
+    if (is_new && slot >= 0)
+      for (int p = 1; p <= si.n_planes; ++p)
+        *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * t.dim * 4u) = kSlotUninit;
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_new) {
@@ -201,12 +190,9 @@ accum_kernel(TableView t, const long long* __restrict__ keys, const T* __restric
         for (unsigned c = lane; c < dim; c += 32) row[c] = acc_add(row[c], in[c]);
       }
     }
-    if (si.n_planes > 0 && bn) {
-      for (int p = 1; p <= si.n_planes; ++p) {
-        unsigned char* d = (is_new && slot >= 0) ? t.planes[p] + (size_t)slot * dim * 4u : nullptr;
-        warp_fill_rows_f32(d, dim, si.v[p], lane);
-      }
-    }
+    if (is_new && slot >= 0)
+      for (int p = 1; p <= si.n_planes; ++p)
+        *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * dim * 4u) = kSlotUninit;
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_new) {
@@ -409,6 +395,23 @@ __global__ void export_special_kernel(TableView t, int plane, unsigned plane_row
   }
   __syncthreads();
   if (threadIdx.x == 0) t.st->scratch[1] = o < max_n ? o : max_n;  // rows written
+}
+
+// exported optimizer-slot rows that were never initialised read as the slot initializer value
+__global__ void export_fix_slot_rows_kernel(float* __restrict__ vals, const unsigned long long* __restrict__ n_rows,
+                                            unsigned dim, float init) {
+  const size_t n = (size_t)*n_rows;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (size_t r = warp0; r < n; r += nwarps) {
+    float* row = vals + r * dim;
+    const bool un = __float_as_uint(row[0]) == kSlotUninit;
+    __syncwarp();
+    if (un)
+      for (unsigned c = lane; c < dim; c += 32) row[c] = init;
+    __syncwarp();
+  }
 }
 
 // Rehash: move every live slot of `src` into `dst` (fresh, all EMPTY).
@@ -801,6 +804,9 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
     return DET_OK;
   });
   export_special_kernel<<<1, 128, 0, s>>>(v, plane, prb, (long long*)keys_out, (unsigned char*)values_out, max_n);
+  if (plane > 0 && values_out)
+    export_fix_slot_rows_kernel<<<grid_for(max_n, 8, t->sm_count, 8), kThreads, 0, s>>>(
+        (float*)values_out, &v.st->scratch[1], (unsigned)t->cfg.dim, t->slot_init[plane]);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaFreeAsync(counts, s));
   CUDA_TRY(cudaFreeAsync(offs, s));

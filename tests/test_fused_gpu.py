@@ -234,3 +234,40 @@ def test_train_step_forward_backward_matches_dense_twin():
     W[touched] = W[touched] - 0.1 * g / A[touched].sqrt()
   got = var.lookup(torch.arange(vocab, device=dev))
   torch.testing.assert_close(got, W, rtol=1e-5, atol=1e-6)
+
+
+def test_slot_state_of_keys_created_by_insert():
+  """A key written by insert/accum has NO optimizer slot yet (the reference keeps slots in separate tables,
+  dynamic_embedding_optimizer.py:870-958): its first optimizer step must start from the slot initializer,
+  and an export of the slot plane shows the initializer for never-stepped keys."""
+  torch = _torch()
+  from recommenders_addons_b200 import dynamic_embedding as de
+  dim = 16
+  rng = np.random.default_rng(9)
+  var = de.Variable(dim=dim, initializer=0.0, num_slot_planes=1, name="slot-lazy")
+  dev = var.tables[0].device
+  keys = np.arange(4000, dtype=np.int64)
+  vals = rng.normal(0, 0.01, (4000, dim)).astype(np.float32)
+  var.upsert(torch.from_numpy(keys).to(dev), torch.from_numpy(vals).to(dev))
+  p, a = O.PortTable(dim), O.PortTable(dim)
+  p.insert(keys, vals)
+  opt = de.FusedAdagrad(0.1, initial_accumulator_value=0.1)
+  step_keys = np.concatenate([keys[::3], np.arange(5000, 5500)]).astype(np.int64)  # stepped existing + brand new
+  for _ in range(2):
+    g = rng.normal(0, 1e-2, (step_keys.shape[0], dim)).astype(np.float32)
+    O.sparse_adagrad_step(p, a, step_keys, g, 0.1, np.zeros(dim, np.float32), np.full(dim, 0.1, np.float32))
+    opt.apply_gradients([(torch.from_numpy(g).to(dev), (var, torch.from_numpy(step_keys).to(dev)))])
+  k, v = var.tables[0].export(plane=0)
+  o = torch.argsort(k)
+  ek, ev = sorted_export(p)
+  np.testing.assert_array_equal(k[o].cpu().numpy(), ek)
+  np.testing.assert_array_equal(v[o].cpu().numpy(), ev)
+  k1, a1 = var.tables[0].export(plane=1)
+  o1 = torch.argsort(k1)
+  k1, a1 = k1[o1].cpu().numpy(), a1[o1].cpu().numpy()
+  np.testing.assert_array_equal(k1, ek)
+  stepped = np.isin(k1, step_keys)
+  ak, av = sorted_export(a)
+  np.testing.assert_array_equal(k1[stepped], ak)
+  np.testing.assert_array_equal(a1[stepped], av)
+  assert (a1[~stepped] == np.float32(0.1)).all()
