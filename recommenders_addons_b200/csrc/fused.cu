@@ -613,7 +613,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   if (n == 0) return DET_OK;
   if (!keys || !grads || !init_param) return fail(DET_INVALID_ARGUMENT, "det_apply: null argument");
   CUDA_TRY(cudaSetDevice(t->cfg.device));
-  det_status st = ensure_room(t, n, s);
+  det_status st = ensure_room(t, (const long long*)keys, n, s);
   if (st != DET_OK) return st;
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)grads | (uintptr_t)init_param) & 15u) == 0);
@@ -630,6 +630,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
     else apply_kernel<1, 1><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
   }
   CUDA_TRY(cudaGetLastError());
+  note_mutation(t, n, s);
   return DET_OK;
 }
 

@@ -45,6 +45,10 @@ struct det_table {
   void* raw[1 + det::kMaxPlanes];
   det::DevState* h_state = nullptr;  // pinned host mirror
   uint64_t used_ub = 0;              // host upper bound of non-EMPTY slots (no sync needed)
+  unsigned long long* h_used_snap = nullptr;  // pinned: async snapshot of DevState::used
+  cudaEvent_t snap_ev = nullptr;
+  bool snap_inflight = false;
+  uint64_t n_since_snap = 0;         // keys of mutating calls issued after the snapshot in flight
   uint32_t rehash_count = 0;
   float slot_init[det::kMaxPlanes];  // value given to slot-plane rows of keys created by insert/accum
   det::HostPipe* pipe = nullptr;
@@ -52,7 +56,10 @@ struct det_table {
 
 namespace det {
 struct SlotInit;
-det_status ensure_room(det_table* t, size_t n, cudaStream_t s);
+det_status ensure_room(det_table* t, const long long* keys_or_null, size_t n, cudaStream_t s);
+void note_mutation(det_table* t, size_t n, cudaStream_t s);
+det_status insert_impl(det_table* t, const int64_t* keys, const void* values, size_t n, cudaStream_t s,
+                       bool check_room);
 det_status table_clear_async(det_table* t, cudaStream_t s);
 void host_pipe_free(det_table* t);
 }  // namespace det

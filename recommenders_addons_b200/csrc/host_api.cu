@@ -169,9 +169,9 @@ det_status det_insert_host(det_table* t, const int64_t* keys, const void* values
   const size_t rb = t->row_bytes, ck = p->chunk_keys;
   const bool pin_k = is_pinned(keys), pin_v = is_pinned(values);
   // growth (if any) must happen before the chunks are in flight on several streams
-  st = ensure_room(t, n, p->streams[0]);
+  st = ensure_room(t, nullptr, n, p->streams[0]);
   if (st != DET_OK) return st;
-  t->used_ub -= n;  // the per-chunk det_insert calls account for their keys again
+  if (t->snap_inflight) t->n_since_snap += n;  // these keys are not covered by a snapshot already in flight
   size_t c = 0;
   for (size_t off = 0; off < n; off += ck, ++c) {
     const int i = (int)(c % kPipeStreams);
@@ -190,7 +190,7 @@ det_status det_insert_host(det_table* t, const int64_t* keys, const void* values
     }
     CUDA_TRY(cudaMemcpyAsync(p->d_keys[i], hk, m * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(p->d_vals[i], hv, m * rb, cudaMemcpyHostToDevice, s));
-    st = det_insert(t, (const int64_t*)p->d_keys[i], p->d_vals[i], m, (det_stream_t)s);
+    st = insert_impl(t, (const int64_t*)p->d_keys[i], p->d_vals[i], m, s, /*check_room=*/false);
     if (st != DET_OK) return st;
     CUDA_TRY(cudaEventRecord(p->done[i], s));
   }

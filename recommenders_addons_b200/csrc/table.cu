@@ -252,6 +252,23 @@ remove_kernel(TableView t, const long long* __restrict__ keys, size_t n) {
   }
 }
 
+// exact number of keys of a batch that are not in the table yet (growth decisions near the load limit)
+__global__ void __launch_bounds__(kThreads)
+count_missing_kernel(TableView t, const long long* __restrict__ keys, size_t n, unsigned long long* out) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  unsigned cnt = 0;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const long long slot = warp_find_slots<true>(t, key, valid, lane);
+    cnt += __popc(__ballot_sync(kFull, valid && slot < 0));
+  }
+  if (lane == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
 // K5a: Clear
 __global__ void fill_keys_kernel(long long* keys, size_t n, long long v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -537,9 +554,19 @@ static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
   return DET_OK;
 }
 
-// Make sure `n` more keys fit under the load-factor limit.  Steady state: pure host arithmetic on an
-// upper bound, no sync.  Near the limit: one sync to read the true counters, then grow if needed.
-det_status ensure_room(det_table* t, size_t n, cudaStream_t s) {
+// Make sure `n` more keys fit under the load-factor limit.
+//  * steady state: pure host arithmetic on an upper bound of `used`; the bound is tightened without any
+//    sync from an asynchronous snapshot of the device counter taken after mutating kernels (note_mutation);
+//  * near the limit: one sync to read the true counters, and (when `keys` is given) an exact count of the
+//    batch's keys that are really new, so re-writing resident keys never grows the table;
+//  * really full: rehash into >= 2x planes, or DET_TABLE_FULL when max_capacity forbids it.
+det_status ensure_room(det_table* t, const long long* keys, size_t n, cudaStream_t s) {
+  if (t->snap_inflight && cudaEventQuery(t->snap_ev) == cudaSuccess) {
+    t->used_ub = *t->h_used_snap + t->n_since_snap;
+    t->snap_inflight = false;
+  } else {
+    cudaGetLastError();  // cudaErrorNotReady is expected
+  }
   const double cap = (double)t->view.capacity();
   const uint64_t limit = (uint64_t)(cap * t->max_lf);
   if (t->used_ub + n <= limit) {
@@ -549,6 +576,7 @@ det_status ensure_room(det_table* t, size_t n, cudaStream_t s) {
   DevState ds;
   det_status st = read_state(t, s, &ds);
   if (st != DET_OK) return st;
+  t->snap_inflight = false;
   const uint64_t special = ds.special[0] + ds.special[1];
   const uint64_t live = ds.size - special;
   t->used_ub = ds.used;
@@ -556,9 +584,23 @@ det_status ensure_room(det_table* t, size_t n, cudaStream_t s) {
     t->used_ub += n;
     return DET_OK;
   }
+  uint64_t n_new = n;
+  if (keys != nullptr) {
+    CUDA_TRY(cudaMemsetAsync(&t->view.st->scratch[2], 0, sizeof(unsigned long long), s));
+    count_missing_kernel<<<grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s>>>(t->view, keys, n,
+                                                                                 &t->view.st->scratch[2]);
+    CUDA_TRY(cudaGetLastError());
+    st = read_state(t, s, &ds);
+    if (st != DET_OK) return st;
+    n_new = ds.scratch[2];
+    if (ds.used + n_new <= limit) {
+      t->used_ub = ds.used + n_new;
+      return DET_OK;
+    }
+  }
   // grow (or purge tombstones at the same size when the live set is small)
   uint64_t nb = t->view.nb;
-  const uint64_t need = live + n;
+  const uint64_t need = live + n_new;
   if ((double)need > (double)limit * 0.5) {
     uint64_t want = (uint64_t)((double)need / t->max_lf / kBucket) + 1;
     nb = nb * 2 > want ? nb * 2 : want;
@@ -572,8 +614,25 @@ det_status ensure_room(det_table* t, size_t n, cudaStream_t s) {
   }
   st = rehash_to(t, nb, s);
   if (st != DET_OK) return st;
-  t->used_ub = live + n;
+  t->used_ub = live + n_new;
   return DET_OK;
+}
+
+// Called after every mutating launch of n keys on stream s (one stream per table at a time): keeps an
+// asynchronous snapshot of the device `used` counter in flight so that the host bound stays tight.
+void note_mutation(det_table* t, size_t n, cudaStream_t s) {
+  if (t->snap_inflight) {
+    t->n_since_snap += n;
+    return;
+  }
+  if (cudaMemcpyAsync(t->h_used_snap, &t->view.st->used, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) ==
+          cudaSuccess &&
+      cudaEventRecord(t->snap_ev, s) == cudaSuccess) {
+    t->snap_inflight = true;
+    t->n_since_snap = 0;
+  } else {
+    cudaGetLastError();
+  }
 }
 
 SlotInit slot_init_of(const det_table* t) {
@@ -625,6 +684,8 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
   for (int p = 0; p < kMaxPlanes; ++p) t->slot_init[p] = 0.f;
   cudaError_t e = cudaMalloc((void**)&t->view.st, sizeof(DevState));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&t->h_state, sizeof(DevState));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&t->h_used_snap, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->snap_ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete t;
     return fail(DET_OUT_OF_MEMORY, std::string("det_table_create: ") + cudaGetErrorString(e));
@@ -654,6 +715,8 @@ det_status det_table_destroy(det_table* t) {
     if (t->raw[i]) cudaFree(t->raw[i]);
   if (t->view.st) cudaFree(t->view.st);
   if (t->h_state) cudaFreeHost(t->h_state);
+  if (t->h_used_snap) cudaFreeHost(t->h_used_snap);
+  if (t->snap_ev) cudaEventDestroy(t->snap_ev);
   host_pipe_free(t);
   delete t;
   return DET_OK;
@@ -680,13 +743,22 @@ det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* def
 }
 
 det_status det_insert(det_table* t, const int64_t* keys, const void* values, size_t n, det_stream_t stream) {
+  return det::insert_impl(t, keys, values, n, (cudaStream_t)stream, true);
+}
+
+}  // extern "C"
+
+namespace det {
+det_status insert_impl(det_table* t, const int64_t* keys, const void* values, size_t n, cudaStream_t s,
+                       bool check_room) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert: null table");
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert: null keys/values");
-  cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(t->cfg.device));
-  det_status st = ensure_room(t, n, s);
-  if (st != DET_OK) return st;
+  if (check_room) {
+    det_status st = ensure_room(t, (const long long*)keys, n, s);
+    if (st != DET_OK) return st;
+  }
   const int vec = pick_vec(t->row_bytes, values, nullptr, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
   const int grid = grid_for(n, kThreads, t->sm_count, 8);
@@ -696,9 +768,13 @@ det_status det_insert(det_table* t, const int64_t* keys, const void* values, siz
     insert_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(v, (const long long*)keys,
                                                                 (const unsigned char*)values, n, g, si);
     CUDA_TRY(cudaGetLastError());
+    if (check_room) note_mutation(t, n, s);
     return DET_OK;
   });
 }
+}  // namespace det
+
+extern "C" {
 
 det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists, size_t n,
                      det_stream_t stream) {
@@ -707,7 +783,7 @@ det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const u
   if (!keys || !vod || !exists) return fail(DET_INVALID_ARGUMENT, "det_accum: null keys/values_or_deltas/exists");
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(t->cfg.device));
-  det_status st = ensure_room(t, n, s);
+  det_status st = ensure_room(t, (const long long*)keys, n, s);
   if (st != DET_OK) return st;
   const int grid = grid_for(n, kThreads, t->sm_count, 8);
   const TableView v = t->view;
@@ -724,6 +800,7 @@ det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const u
     default: return fail(DET_UNIMPLEMENTED, "det_accum: dtype");
   }
   CUDA_TRY(cudaGetLastError());
+  note_mutation(t, n, s);
   return DET_OK;
 }
 
@@ -776,6 +853,7 @@ det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream) {
   st = rehash_to(t, nb, s);
   if (st != DET_OK) return st;
   t->used_ub = ds.size;
+  t->snap_inflight = false;
   return DET_OK;
 }
 

@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Per-kernel sweep (dev tool, not the headline bench): times every table kernel with CUDA events on the torch
+stream for dim {16,64,128}, uniform and Zipf keys, several hit rates; prints one JSON line per case.
+    python scripts/microbench.py [--resident 50000000] [--batch 1048576] [--reps 10]
+Env DET_FIND_VARIANT / DET_INSERT_VARIANT select experimental kernel variants inside libdetable.so."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from recommenders_addons_b200 import dynamic_embedding as de  # noqa: E402
+from recommenders_addons_b200.dynamic_embedding.ops import lookup_sparse_fused  # noqa: E402
+import bench as B  # noqa: E402
+
+
+def timeit(fn, reps, flush=None):
+  ts = []
+  for _ in range(reps + 2):
+    if flush is not None:
+      flush.add_(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+  ts = ts[2:]
+  return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--resident", type=int, default=50_000_000)
+  ap.add_argument("--batch", type=int, default=1 << 20)
+  ap.add_argument("--reps", type=int, default=10)
+  ap.add_argument("--dims", default="16,64,128")
+  ap.add_argument("--tag", default="")
+  a = ap.parse_args()
+  dev = torch.device("cuda", 0)
+  Bn = a.batch
+  flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)  # > L2
+  gen = torch.Generator(device=dev).manual_seed(1)
+  peak = B.measured_peak_gbs()[0]
+  for dim in [int(x) for x in a.dims.split(",")]:
+    res = a.resident
+    free = torch.cuda.mem_get_info()[0]
+    planes = 3 if dim <= 64 else 2
+    while 2 * res * (8 + planes * dim * 4) * 1.1 + (8 << 30) > free:
+      res //= 2
+    var = de.Variable(dim=dim, init_size=2 * res, initializer=0.0, num_slot_planes=planes - 1, name="mb%d" % dim)
+    t = var.tables[0]
+    for b in range(0, res, 1 << 20):
+      r = torch.arange(b, min(res, b + (1 << 20)), dtype=torch.int64, device=dev)
+      t.insert(B.rank_to_key_torch(r), torch.randn(r.numel(), dim, device=dev, generator=gen) * 0.01)
+    cdf = B.zipf_cdf_torch(res, dev)
+    cases = {
+        "zipf_hit100": B.rank_to_key_torch(B.zipf_unique_batch_torch(cdf, Bn, gen)),
+        "uniform_hit100": B.rank_to_key_torch(torch.randperm(res, device=dev, generator=gen)[:Bn]),
+        "uniform_hit50": B.rank_to_key_torch(torch.cat([torch.randperm(res, device=dev, generator=gen)[:Bn // 2],
+                                                        torch.arange(res, res + Bn // 2, device=dev)])[torch.randperm(Bn, device=dev, generator=gen)]),
+        "uniform_hit0": B.rank_to_key_torch(torch.arange(2 * res, 2 * res + Bn, device=dev)),
+    }
+    del cdf
+    default = torch.zeros(dim, device=dev)
+    vals = torch.randn(Bn, dim, device=dev, generator=gen) * 0.01
+    grads = torch.randn(Bn, dim, device=dev, generator=gen) * 0.01
+    ex = torch.ones(Bn, dtype=torch.bool, device=dev)
+    row = dim * 4
+
+    def emit(op, case, med, mn, algo_bytes, honest_bytes):
+      print(json.dumps({"tag": a.tag, "op": op, "dim": dim, "case": case, "ms_med": round(med, 4), "ms_min": round(mn, 4),
+                        "Mkeys_s": round(Bn / med / 1e3, 1), "algo_GBs": round(algo_bytes / med / 1e6, 1),
+                        "algo_frac": round(algo_bytes / med / 1e6 / peak, 3),
+                        "honest_GBs": round(honest_bytes / med / 1e6, 1),
+                        "honest_frac": round(honest_bytes / med / 1e6 / peak, 3), "resident": res}), flush=True)
+
+    for name, k in cases.items():
+      med, mn = timeit(lambda: t.lookup(k, dynamic_default_values=default), a.reps, flush)
+      emit("find", name, med, mn, Bn * row, Bn * (8 + 64 + 2 * row))
+      med, mn = timeit(lambda: t.lookup(k, dynamic_default_values=default, return_exists=True), a.reps, flush)
+      emit("find_exists", name, med, mn, Bn * row, Bn * (8 + 64 + 2 * row + 1))
+    for name in ("zipf_hit100", "uniform_hit100"):
+      k = cases[name]
+      med, mn = timeit(lambda: t.insert(k, vals), a.reps, flush)
+      emit("insert_existing", name, med, mn, Bn * row, Bn * (8 + 64 + 2 * row))
+      med, mn = timeit(lambda: t.accum(k, vals, ex), a.reps, flush)
+      emit("accum_existing", name, med, mn, 2 * Bn * row, Bn * (8 + 1 + 64 + 3 * row))
+      opt = de.FusedAdagrad(0.01, 0.1)
+      med, mn = timeit(lambda: opt.apply_sparse(var, k, grads), a.reps, flush)
+      emit("adagrad", name, med, mn, 5 * Bn * row, Bn * (8 + 64 + 5 * row))
+      if planes >= 3:
+        opt2 = de.FusedAdam(0.01)
+        opt2.iterations = 1
+        med, mn = timeit(lambda: opt2.apply_sparse(var, k, grads), a.reps, flush)
+        emit("adam", name, med, mn, 7 * Bn * row, Bn * (8 + 64 + 7 * row))
+      seg = torch.arange(Bn, device=dev, dtype=torch.int32)
+      med, mn = timeit(lambda: lookup_sparse_fused(var, k, seg, None, Bn, "sum"), a.reps, flush)
+      emit("lookup_sparse_1id", name, med, mn, Bn * row, Bn * (8 + 4 + 64 + 2 * row))
+      seg4 = torch.arange(Bn, device=dev, dtype=torch.int32) // 4
+      med, mn = timeit(lambda: lookup_sparse_fused(var, k, seg4, None, Bn // 4, "mean"), a.reps, flush)
+      emit("lookup_sparse_4ids", name, med, mn, Bn * row, Bn * (8 + 4 + 64 + row) + Bn // 4 * row)
+    # new-key insert into free space, then remove them again
+    newk = B.rank_to_key_torch(torch.arange(3 * res, 3 * res + Bn, device=dev))
+    ts_i, ts_r = [], []
+    for _ in range(4):
+      flush.add_(1)
+      e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+      e[0].record()
+      t.insert(newk, vals)
+      e[1].record()
+      t.remove(newk)
+      e[2].record()
+      torch.cuda.synchronize()
+      ts_i.append(e[0].elapsed_time(e[1]))
+      ts_r.append(e[1].elapsed_time(e[2]))
+    emit("insert_new", "uniform", float(np.median(ts_i)), float(np.min(ts_i)), Bn * row, Bn * (8 + 64 + 2 * row))
+    emit("remove", "uniform", float(np.median(ts_r)), float(np.min(ts_r)), Bn * 64, Bn * (8 + 128))
+    u = cases["zipf_hit100"]
+    med, mn = timeit(lambda: de.unique(u), a.reps)
+    emit("unique", "zipf", med, mn, Bn * 12, Bn * 12)
+    from recommenders_addons_b200.dynamic_embedding import variable as V
+    med, mn = timeit(lambda: V.partition(u, 8, True), a.reps)
+    emit("partition8", "zipf", med, mn, Bn * 20, Bn * 28)
+    var.tables[0].close()
+    del var, t
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+  main()

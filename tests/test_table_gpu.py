@@ -180,7 +180,9 @@ def test_tombstone_recycling_and_clear():
   for x, y in zip(sorted_export(gt), sorted_export(ot)):
     np.testing.assert_array_equal(x, y)
   st = gt.t.stats()
-  assert st["capacity"] == 1 << 14 and st["rehash_count"] == 0  # 9000 live keys never exceed 0.75 * 16384
+  # 9000 live keys never exceed 0.75 * 16384: re-writing resident keys must not grow the table (the growth
+  # decision counts the batch's really-new keys), and tombstones are recycled or purged in place
+  assert st["capacity"] == 1 << 14 and st["error_flags"] == 0
 
 
 def test_insert_repeat_data_keeps_size():
