@@ -166,7 +166,7 @@ def cpu_arm(dim, resident, batch, steps, warmup):
     if it >= warmup:
       times_find.append(t1 - t0)
       times_ins.append(t2 - t1)
-  tf, ti = float(np.mean(times_find)), float(np.mean(times_ins))
+  tf, ti = float(np.median(times_find)), float(np.median(times_ins))
   table.close()
   return {
       "value": batch / (tf + ti) / 1e6, "unit": "M keys/s", "cores": threads, "kind": kind,
@@ -415,7 +415,7 @@ def gpu_arm(args):
     line["e2e"] = e2e
   if world == 1 and not args.no_cpu_baseline:
     try:
-      cb = cpu_arm(dim, args.cpu_resident, B, steps=3, warmup=1)
+      cb = cpu_arm(dim, args.cpu_resident, B, steps=7, warmup=2)
       cb.pop("ms_per_step", None)
       line["cpu_baseline"] = cb
     except Exception as ex:  # the checker is optional for the bench line; never hide the GPU number
@@ -429,8 +429,8 @@ def reference_arm(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  steps = max(1, min(args.steps, 5))
-  warm = max(1, min(args.warmup, 2))
+  steps = max(1, min(args.steps, 9))
+  warm = max(1, min(args.warmup, 3))
   cb = cpu_arm(args.dim, args.cpu_resident, args.batch, steps=steps, warmup=warm)
   ms = cb.pop("ms_per_step")
   line = {

@@ -211,7 +211,19 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
 
   long long result = -1;
   bool res_new = false, res_empty = false;
-#pragma unroll 1
+  // First-bucket loads of all 4 rounds are issued up front (memory-level parallelism).  A view that is stale
+  // by the time its round runs is harmless: free slots only disappear during a mutating kernel, every claim is
+  // validated by the CAS, and a failed CAS restarts the chain with fresh L2-coherent loads.
+  longlong2 first[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int src = r * 8 + sg;
+    const unsigned long long b0 = (unsigned long long)shfl_ll((long long)myb, src);
+    const bool act = __shfl_sync(kFull, (int)probe_me, src) != 0;
+    first[r] = make_longlong2(0, 0);
+    if (act) first[r] = ld_keys_cg(t.keys + b0 * kBucket + sl * 2);
+  }
+#pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int src = r * 8 + sg;
     const long long key = shfl_ll(mykey, src);
@@ -223,9 +235,11 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
     bool ff_tomb = false, fnew = false, fempty = false;
     unsigned long long probes = 0;
     unsigned restarts = 0;
+    bool use_first = true;
     while (__any_sync(kFull, active)) {
-      longlong2 kk = make_longlong2(0, 0);
-      if (active) kk = ld_keys_cg(t.keys + b * kBucket + sl * 2);
+      longlong2 kk = first[r];
+      if (active && !use_first) kk = ld_keys_cg(t.keys + b * kBucket + sl * 2);
+      use_first = false;
       const unsigned bh0 = __ballot_sync(kFull, active && kk.x == key);
       const unsigned bh1 = __ballot_sync(kFull, active && kk.y == key);
       const unsigned be0 = __ballot_sync(kFull, active && kk.x == kEmptyKey);
@@ -328,17 +342,39 @@ struct RowGeom {
   unsigned lpr_shift;  // log2(lpr)
 };
 
+// cached (L1-allocating, read-only) vector load: used for the broadcast default row, which every warp of
+// the grid reads -- streaming it from L2 with no_allocate makes two L2 lines a chip-wide hot spot
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type ld_cached(const unsigned char* p) {
+  return __ldg(reinterpret_cast<const typename VecT<VEC>::type*>(p));
+}
+template <>
+__device__ __forceinline__ short ld_cached<2>(const unsigned char* p) {
+  return __ldg(reinterpret_cast<const short*>(p));
+}
+template <>
+__device__ __forceinline__ char ld_cached<1>(const unsigned char* p) {
+  return __ldg(reinterpret_cast<const char*>(p));
+}
+
+// marker a lane passes as its row's source to say "the broadcast default row"
+#define DET_SRC_DEFAULT (reinterpret_cast<const unsigned char*>(uintptr_t(1)))
+
 // For each of the warp's 32 items (item j held by lane j): copy one row from src_j to dst_j.
-// Lane j provides its row's src/dst pointers (nullptr src or dst = skip).
+// Lane j provides its row's src/dst pointers (nullptr src or dst = skip; src == DET_SRC_DEFAULT = copy the
+// broadcast row `bdef`, which each lane keeps in a register / L1).
 template <int VEC>
 __device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned char* my_src,
-                                               unsigned char* my_dst, int lane) {
+                                               unsigned char* my_dst, int lane,
+                                               const unsigned char* bdef = nullptr) {
   using V = typename VecT<VEC>::type;
   const unsigned rows_per_step = 32u >> g.lpr_shift;
   const unsigned sub = (unsigned)lane >> g.lpr_shift;        // which row of the step
   const unsigned c0 = (unsigned)lane & (g.lpr - 1u);          // first vector of the lane
   if (g.vpr == g.lpr) {
     // fast path: exactly one vector per lane per row; 4 rows in flight per lane
+    V defv = V();
+    if (bdef != nullptr) defv = ld_cached<VEC>(bdef + c0 * VEC);
     for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step * 4u) {
       const unsigned char* s[4];
       unsigned char* d[4];
@@ -352,8 +388,10 @@ __device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned 
         if (j >= 32u) s[u] = nullptr;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (s[u] && d[u]) v[u] = ld_row<VEC>(s[u] + c0 * VEC);
+      for (int u = 0; u < 4; ++u) {
+        v[u] = defv;
+        if (s[u] > DET_SRC_DEFAULT && d[u]) v[u] = ld_row<VEC>(s[u] + c0 * VEC);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (s[u] && d[u]) st_row<VEC>(d[u] + c0 * VEC, v[u]);
@@ -364,10 +402,119 @@ __device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned 
       const unsigned char* s = (const unsigned char*)shfl_ll((long long)my_src, j & 31u);
       unsigned char* d = (unsigned char*)shfl_ll((long long)my_dst, j & 31u);
       if (s && d) {
-        for (unsigned c = c0; c < g.vpr; c += g.lpr) st_row<VEC>(d + c * VEC, ld_row<VEC>(s + c * VEC));
+        if (s == DET_SRC_DEFAULT) {
+          for (unsigned c = c0; c < g.vpr; c += g.lpr) st_row<VEC>(d + c * VEC, ld_cached<VEC>(bdef + c * VEC));
+        } else {
+          for (unsigned c = c0; c < g.vpr; c += g.lpr) st_row<VEC>(d + c * VEC, ld_row<VEC>(s + c * VEC));
+        }
       }
     }
   }
 }
+
+// ---- TMA bulk staging of key tiles (cp.async.bulk global -> shared, completion on an mbarrier) ----------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kTileKeys = 256;  // keys per CTA tile (= blockDim): 2 KB per stage
+constexpr int kStages = 2;
+
+// Persistent-CTA key-tile pipeline: thread 0 prefetches tile i+1 with one TMA bulk copy while the CTA works
+// on tile i.  Usage (all threads of a 256-thread CTA):
+//   KeyTiles kt; kt.init(keys, n);                       // tile = blockIdx.x, step gridDim.x
+//   for (; kt.valid(); kt.next()) { long long k = kt.key(valid); ... }
+struct KeyTiles {
+  long long (*s_keys)[kTileKeys];
+  unsigned long long* s_bar;
+  const long long* keys;
+  size_t n, n_tiles, tile;
+  unsigned it;
+
+  __device__ __forceinline__ void issue(size_t tl, int stage) {
+    const size_t k0 = tl * kTileKeys;
+    const size_t cnt = (n - k0 < (size_t)kTileKeys) ? n - k0 : (size_t)kTileKeys;
+    const unsigned bytes = (unsigned)(cnt & ~(size_t)1) * 8u;
+    if (bytes) {
+      mbar_arrive_expect_tx(&s_bar[stage], bytes);
+      bulk_g2s(s_keys[stage], keys + k0, bytes, &s_bar[stage]);
+    } else {
+      mbar_arrive(&s_bar[stage]);
+    }
+  }
+  __device__ __forceinline__ void init(long long (*sk)[kTileKeys], unsigned long long* sb, const long long* k,
+                                       size_t n_) {
+    s_keys = sk;
+    s_bar = sb;
+    keys = k;
+    n = n_;
+    n_tiles = (n + kTileKeys - 1) / kTileKeys;
+    tile = blockIdx.x;
+    it = 0;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && tile < n_tiles) issue(tile, 0);
+  }
+  __device__ __forceinline__ bool valid() const { return tile < n_tiles; }
+  // index of this thread's key in the current tile + the key itself; ends with a CTA barrier after which the
+  // stage may be refilled
+  __device__ __forceinline__ long long key(size_t& i, bool& ok) {
+    const int stage = (int)(it & 1u);
+    const size_t nxt = tile + gridDim.x;
+    if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, stage ^ 1);
+    mbar_wait(&s_bar[stage], (it >> 1) & 1u);
+    const size_t k0 = tile * kTileKeys;
+    const size_t cnt = (n - k0 < (size_t)kTileKeys) ? n - k0 : (size_t)kTileKeys;
+    i = k0 + threadIdx.x;
+    ok = threadIdx.x < cnt;
+    long long k = 0;
+    if (ok) k = (threadIdx.x < (cnt & ~(size_t)1)) ? s_keys[stage][threadIdx.x] : __ldg(keys + i);
+    __syncthreads();
+    return k;
+  }
+  __device__ __forceinline__ void next() {
+    tile += gridDim.x;
+    ++it;
+  }
+};
 
 }  // namespace det

@@ -198,42 +198,20 @@ __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, 
   for (long long b = prev + 1; b <= cur; ++b) seg_start[b] = (long long)i;
 }
 
-// probe by the first 4 lanes of a lane-group (group size >= 4, aligned); every lane of the group
-// gets the slot
-__device__ __forceinline__ long long group_find_slot(const TableView& t, long long key, bool act, int gbase,
-                                                     int gl) {
-  const bool special = is_special(key);
-  bool active = act && !special;
-  const unsigned long long nb = t.nb;
-  unsigned long long b = bucket_of(key, nb);
-  long long found = -1;
-  unsigned long long probes = 0;
-  const int sg = gbase >> 2;
-  while (__any_sync(kFull, active)) {
-    const bool ld = active && gl < 4;
-    longlong2 kk = make_longlong2(0, 0);
-    if (ld) kk = ld_keys_nc(t.keys + b * kBucket + gl * 2);
-    const unsigned bh0 = __ballot_sync(kFull, ld && kk.x == key);
-    const unsigned bh1 = __ballot_sync(kFull, ld && kk.y == key);
-    const unsigned be = __ballot_sync(kFull, ld && (kk.x == kEmptyKey || kk.y == kEmptyKey));
-    if (active) {
-      const unsigned H = mask8(bh0, bh1, sg);
-      if (H) {
-        found = (long long)(b * kBucket) + (__ffs(H) - 1);
-        active = false;
-      } else if (((be >> (sg * 4)) & 0xFu) || ++probes >= nb) {
-        active = false;
-      } else {
-        b = (b + 1 == nb) ? 0 : b + 1;
-      }
-    }
+// K6 phase A: slot of every id (-1 = absent), 32 ids per warp-step with the same warp-cooperative probe as
+// det_find; only 8 B per id leave the kernel (the [nnz, dim] gather of the reference is never materialised)
+__global__ void __launch_bounds__(kThreadsF)
+resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz, long long* __restrict__ slots) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
+  for (size_t base = warp0 * 32; base < nnz; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < nnz;
+    const long long key = valid ? __ldg(ids + i) : 0;
+    const long long slot = warp_find_slots<false>(t, key, valid, lane);
+    if (valid) slots[i] = slot;
   }
-  if (act && special) {
-    const int idx = (key == kTombKey) ? 1 : 0;
-    const unsigned present = *((volatile unsigned*)&t.st->special[idx]);
-    found = present ? (long long)(nb * kBucket + idx) : -1;
-  }
-  return found;
 }
 
 template <int VF> struct FVec;
@@ -257,15 +235,96 @@ template <> struct FVec<1> {
 };
 
 constexpr int kMaxVecPerLane = 8;
+constexpr int kSegPerGroup = 4;  // segments a lane-group works on concurrently (independent load chains)
 
+// K6 phase B, common case (one vector per lane covers the row): each lane-group owns kSegPerGroup
+// consecutive output rows and walks their ids in lock step, so up to 4 independent row loads are in flight
+// per lane; within a segment the ids are accumulated strictly in order (mul, then add: the summation order of
+// the reference test oracle).
 template <int VF>
 __global__ void __launch_bounds__(kThreadsF)
-lookup_sparse_kernel(TableView t, const long long* __restrict__ ids, const long long* __restrict__ seg_start,
-                     const float* __restrict__ weights, size_t batch, int combiner,
-                     const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
-                     unsigned lpr_shift) {
+segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
+                   const float* __restrict__ weights, size_t batch, int combiner,
+                   const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
+                   unsigned lpr_shift) {
+  constexpr int U = kSegPerGroup;
   const int lane = threadIdx.x & 31;
-  const int gl = lane & (int)(lpr - 1), gbase = lane & ~(int)(lpr - 1);
+  const unsigned gl = (unsigned)lane & (lpr - 1u);
+  const unsigned gpw = 32u >> lpr_shift;
+  const unsigned gidx = (unsigned)lane >> lpr_shift;
+  const unsigned dim = t.dim;
+  const bool lane_on = gl < vpr;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
+  const float* table = (const float*)t.planes[0];
+  FVec<VF> defv;
+  defv.zero();
+  if (lane_on) defv.load(default_row + (size_t)gl * VF);
+  for (size_t sb = warp0 * gpw * U; sb < batch; sb += nwarps * gpw * U) {
+    const size_t b0 = sb + (size_t)gidx * U;
+    long long st[U], en[U];
+    FVec<VF> acc[U];
+    float wsum[U], wsq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = b0 + u < batch;
+      st[u] = ok ? seg_start[b0 + u] : 0;
+      en[u] = ok ? seg_start[b0 + u + 1] : 0;
+      acc[u].zero();
+      wsum[u] = 0.f;
+      wsq[u] = 0.f;
+    }
+    for (long long k = 0;; ++k) {
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < U; ++u) any |= st[u] + k < en[u];
+      if (!__any_sync(kFull, any)) break;
+      long long sl[U];
+      float w[U];
+      FVec<VF> x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool act = st[u] + k < en[u];
+        sl[u] = act ? __ldg(slots + st[u] + k) : -2;
+        w[u] = act ? (weights ? __ldg(weights + st[u] + k) : 1.f) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        x[u] = defv;
+        if (sl[u] >= 0 && lane_on) x[u].load(table + (size_t)sl[u] * dim + (size_t)gl * VF);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (sl[u] != -2) {
+          const float wu = w[u];
+          acc[u].zip(x[u], [wu](float& a, float xv) { a = a + xv * wu; });
+          wsum[u] = wsum[u] + wu;
+          wsq[u] = wsq[u] + wu * wu;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (b0 + u < batch && lane_on) {
+        if (en[u] > st[u] && combiner != DET_COMBINER_SUM) {
+          const float div = combiner == DET_COMBINER_MEAN ? wsum[u] : sqrtf(wsq[u]);
+          acc[u].apply([div](float& a) { a = a / div; });
+        }
+        acc[u].store(out + (b0 + u) * dim + (size_t)gl * VF);
+      }
+    }
+  }
+}
+
+// K6 phase B, wide rows (several vectors per lane): one lane-group per output row
+template <int VF>
+__global__ void __launch_bounds__(kThreadsF)
+segment_sum_wide_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
+                        const float* __restrict__ weights, size_t batch, int combiner,
+                        const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
+                        unsigned lpr_shift) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (int)(lpr - 1);
   const unsigned gpw = 32u >> lpr_shift;
   const unsigned gidx = (unsigned)lane >> lpr_shift;
   const unsigned dim = t.dim;
@@ -281,26 +340,21 @@ lookup_sparse_kernel(TableView t, const long long* __restrict__ ids, const long 
 #pragma unroll
     for (int v = 0; v < kMaxVecPerLane; ++v) acc[v].zero();
     float wsum = 0.f, wsq = 0.f;
-    for (long long k = 0; __any_sync(kFull, start + k < end); ++k) {
-      const long long i = start + k;
-      const bool act = i < end;
-      const long long key = act ? __ldg(ids + i) : 0;
-      const float w = act ? (weights ? __ldg(weights + i) : 1.f) : 0.f;
-      const long long slot = group_find_slot(t, key, act, gbase, gl);
-      if (act) {
-        const float* src = slot >= 0 ? table + (size_t)slot * dim : default_row;
+    for (long long i = start; i < end; ++i) {
+      const long long slot = __ldg(slots + i);
+      const float w = weights ? __ldg(weights + i) : 1.f;
+      const float* src = slot >= 0 ? table + (size_t)slot * dim : default_row;
 #pragma unroll
-        for (int v = 0; v < kMaxVecPerLane; ++v) {
-          const unsigned c = (unsigned)gl + (unsigned)v * lpr;
-          if (c < vpr) {
-            FVec<VF> x;
-            x.load(src + (size_t)c * VF);
-            acc[v].zip(x, [w](float& a, float xv) { a = a + xv * w; });
-          }
+      for (int v = 0; v < kMaxVecPerLane; ++v) {
+        const unsigned c = (unsigned)gl + (unsigned)v * lpr;
+        if (c < vpr) {
+          FVec<VF> x;
+          x.load(src + (size_t)c * VF);
+          acc[v].zip(x, [w](float& a, float xv) { a = a + xv * w; });
         }
-        wsum = wsum + w;
-        wsq = wsq + w * w;
       }
+      wsum = wsum + w;
+      wsq = wsq + w * w;
     }
     if (act_seg) {
       float div = 1.f;
@@ -583,25 +637,38 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(t->cfg.device));
   long long* seg_start = nullptr;
+  long long* slots = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&seg_start, (batch + 1) * sizeof(long long), s));
+  CUDA_TRY(cudaMallocAsync((void**)&slots, (nnz ? nnz : 1) * sizeof(long long), s));
   segment_offsets_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, s>>>(segment_ids, nnz, batch, seg_start, t->view.st);
+  if (nnz)
+    resolve_slots_kernel<<<grid_for(nnz, kThreadsF, t->sm_count, 8), kThreadsF, 0, s>>>(t->view, (const long long*)ids,
+                                                                                     nnz, slots);
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out) & 15u) == 0);
   unsigned vpr, lpr, sh;
-  fgeom(dim, vec4, 4, &vpr, &lpr, &sh);
-  if ((vpr + lpr - 1) / lpr > (unsigned)kMaxVecPerLane) {
-    cudaFreeAsync(seg_start, s);
-    return fail(DET_UNIMPLEMENTED, "det_lookup_sparse: dim too large for the fused kernel");
-  }
+  fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
+  det_status rc = DET_OK;
   const unsigned gpw = 32u >> sh;
-  const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
-  if (vec4)
-    lookup_sparse_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, (const long long*)ids, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
-  else
-    lookup_sparse_kernel<1><<<grid, kThreadsF, 0, s>>>(t->view, (const long long*)ids, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaFreeAsync(seg_start, s));
-  return DET_OK;
+  if (vpr <= lpr) {
+    const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, 8);
+    if (vec4)
+      segment_sum_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+    else
+      segment_sum_kernel<1><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+  } else if ((vpr + lpr - 1) / lpr <= (unsigned)kMaxVecPerLane) {
+    const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
+    if (vec4)
+      segment_sum_wide_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+    else
+      segment_sum_wide_kernel<1><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+  } else {
+    rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse: dim too large for the fused kernel");
+  }
+  if (rc == DET_OK && cudaGetLastError() != cudaSuccess) rc = fail(DET_CUDA_ERROR, "det_lookup_sparse: launch failed");
+  cudaFreeAsync(seg_start, s);
+  cudaFreeAsync(slots, s);
+  return rc;
 }
 
 static det_status apply_common(det_table* t, const int64_t* keys, const float* grads, size_t n, OptHyper h,

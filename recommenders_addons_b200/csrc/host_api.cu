@@ -263,6 +263,8 @@ det_status det_load(det_table* t, const char* prefix, size_t buffer_keys) {
   det_status st = DET_OK;
   // LoadFromFileSystem without load_entire_dir = clear + insert all (cuckoo_hashtable_op.cc:393-465)
   st = det_clear(t, nullptr);
+  // the chunked inserts below run on the table's internal (non-blocking) streams: the clear must be complete
+  if (st == DET_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_load: clear failed");
   while (st == DET_OK) {
     const size_t m = fread(hk.data(), 8, buffer_keys, fk);
     if (m == 0) break;

@@ -1,5 +1,7 @@
 // table.cu -- the table object behind include/detable.h and kernels K1..K5 (find / insert / accum /
 // remove / clear / size / export / rehash).  sm_100a only.  See DESIGN.md for layout and rooflines.
+#include <stdlib.h>
+
 #include "host.h"
 
 namespace det {
@@ -54,6 +56,27 @@ int grid_for(size_t n_items, int items_per_block, int sm_count, int blocks_per_s
   return (int)(need < cap ? need : cap);
 }
 
+// resident CTAs per SM of a kernel (cached per kernel): grids are sized to exactly one resident wave
+template <typename K>
+static int occupancy_of(K kernel, int threads) {
+  static thread_local const void* last_k = nullptr;
+  static thread_local int last_v = 0;
+  if (last_k == (const void*)kernel) return last_v;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) {
+    cudaGetLastError();
+    nb = 2;
+  }
+  last_k = (const void*)kernel;
+  last_v = nb;
+  return nb;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 // ================================================================================================
 // Kernels
 // ================================================================================================
@@ -61,7 +84,25 @@ constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 
 // K1: Find / FindWithExists with the default-row fill folded in (replaces HKV find +
-// gpu_fill_default_values, lookup_table_op_hkv.h:317-327, 719-732).
+// gpu_fill_default_values, lookup_table_op_hkv.h:317-327, 719-732).  One warp-step = 32 keys.
+template <int VEC>
+__device__ __forceinline__ void find_step(const TableView& t, long long key, size_t i, bool valid,
+                                          const unsigned char* __restrict__ defaults, int full_default,
+                                          unsigned char* __restrict__ out, unsigned char* __restrict__ exists,
+                                          const RowGeom& g, int lane) {
+  const long long slot = warp_find_slots<false>(t, key, valid, lane);
+  if (exists != nullptr && valid) exists[i] = slot >= 0 ? 1 : 0;
+  const unsigned char* src = nullptr;
+  unsigned char* dst = nullptr;
+  if (valid) {
+    src = slot >= 0 ? t.planes[0] + (size_t)slot * g.row_bytes
+                    : (full_default ? defaults + i * g.row_bytes : DET_SRC_DEFAULT);
+    dst = out + i * g.row_bytes;
+  }
+  warp_move_rows<VEC>(g, src, dst, lane, full_default ? nullptr : defaults);
+}
+
+// variant 0: keys read with coalesced LDG, grid-stride by warp
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 find_kernel(TableView t, const long long* __restrict__ keys, size_t n,
@@ -74,16 +115,27 @@ find_kernel(TableView t, const long long* __restrict__ keys, size_t n,
     const size_t i = base + lane;
     const bool valid = i < n;
     const long long key = valid ? __ldg(keys + i) : 0;
-    const long long slot = warp_find_slots<false>(t, key, valid, lane);
-    if (exists != nullptr && valid) exists[i] = slot >= 0 ? 1 : 0;
-    const unsigned char* src = nullptr;
-    unsigned char* dst = nullptr;
-    if (valid) {
-      src = slot >= 0 ? t.planes[0] + (size_t)slot * g.row_bytes
-                      : (full_default ? defaults + i * g.row_bytes : defaults);
-      dst = out + i * g.row_bytes;
-    }
-    warp_move_rows<VEC>(g, src, dst, lane);
+    find_step<VEC>(t, key, i, valid, defaults, full_default, out, exists, g, lane);
+  }
+}
+
+// variant 1 (default): persistent CTAs, key tiles staged into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier), tile i+1 in flight while tile i is probed and gathered
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+find_kernel_tma(TableView t, const long long* __restrict__ keys, size_t n,
+                const unsigned char* __restrict__ defaults, int full_default,
+                unsigned char* __restrict__ out, unsigned char* __restrict__ exists, RowGeom g) {
+  __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
+  const int lane = threadIdx.x & 31;
+  KeyTiles kt;
+  kt.init(s_keys, s_bar, keys, n);
+  for (; kt.valid(); kt.next()) {
+    size_t i;
+    bool valid;
+    const long long key = kt.key(i, valid);
+    find_step<VEC>(t, key, i, valid, defaults, full_default, out, exists, g, lane);
   }
 }
 
@@ -92,7 +144,33 @@ struct SlotInit {
   int n_planes;  // number of slot planes (excluding values)
 };
 
-// K2: Insert (insert_or_assign).  New keys also get their optimizer slot rows initialised.
+// K2: Insert (insert_or_assign).
+template <int VEC>
+__device__ __forceinline__ void insert_step(const TableView& t, long long key, size_t i, bool valid,
+                                            const unsigned char* __restrict__ values, const RowGeom& g,
+                                            const SlotInit& si, int lane, unsigned* s_new, unsigned* s_used) {
+  bool is_new, from_empty;
+  const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
+  const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+  if (lane == 0 && bn) {
+    atomicAdd(s_new, __popc(bn));
+    atomicAdd(s_used, __popc(bu));
+  }
+  const unsigned char* src = nullptr;
+  unsigned char* dst = nullptr;
+  if (valid && slot >= 0) {
+    src = values + i * g.row_bytes;
+    dst = t.planes[0] + (size_t)slot * g.row_bytes;
+  }
+  warp_move_rows<VEC>(g, src, dst, lane);
+  // a key created outside the optimizer has no slot state yet: mark its slot rows "uninitialised" (the
+  // reference keeps slots in separate tables, where such a key is simply absent and reads the slot
+  // initializer at the next optimizer step)
+  if (is_new && slot >= 0)
+    for (int p = 1; p <= si.n_planes; ++p)
+      *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * t.dim * 4u) = kSlotUninit;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
@@ -110,26 +188,34 @@ insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned ch
     const size_t i = base + lane;
     const bool valid = i < n;
     const long long key = valid ? __ldg(keys + i) : 0;
-    bool is_new, from_empty;
-    const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
-    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
-    if (lane == 0 && bn) {
-      atomicAdd(&s_new, __popc(bn));
-      atomicAdd(&s_used, __popc(bu));
-    }
-    const unsigned char* src = nullptr;
-    unsigned char* dst = nullptr;
-    if (valid && slot >= 0) {
-      src = values + i * g.row_bytes;
-      dst = t.planes[0] + (size_t)slot * g.row_bytes;
-    }
-    warp_move_rows<VEC>(g, src, dst, lane);
-    // a key created outside the optimizer has no slot state yet: mark its slot rows "uninitialised" (the
-    // reference keeps slots in separate tables, where such a key is simply absent and reads the slot
-    // initializer at the next optimizer step)
-    if (is_new && slot >= 0)
-      for (int p = 1; p <= si.n_planes; ++p)
-        *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * t.dim * 4u) = kSlotUninit;
+    insert_step<VEC>(t, key, i, valid, values, g, si, lane, &s_new, &s_used);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+insert_kernel_tma(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
+                  size_t n, RowGeom g, SlotInit si) {
+  __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    s_new = 0;
+    s_used = 0;
+  }
+  const int lane = threadIdx.x & 31;
+  KeyTiles kt;
+  kt.init(s_keys, s_bar, keys, n);
+  for (; kt.valid(); kt.next()) {
+    size_t i;
+    bool valid;
+    const long long key = kt.key(i, valid);
+    insert_step<VEC>(t, key, i, valid, values, g, si, lane, &s_new, &s_used);
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_new) {
@@ -149,10 +235,17 @@ __device__ __forceinline__ __nv_bfloat16 acc_add(__nv_bfloat16 a, __nv_bfloat16 
 
 // K3: Accum (insert_or_accum, cuckoohash_map.hh:620-633): found&exist -> row += delta (element by
 // element, one rounding each, like ValueArray::operator+=); !found&!exist -> insert; else no-op.
-template <typename T>
+// Rows move as VEC-byte vectors, lpr lanes per row (same geometry as find/insert).
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 accum_kernel(TableView t, const long long* __restrict__ keys, const T* __restrict__ vod,
-             const unsigned char* __restrict__ exists, size_t n, SlotInit si) {
+             const unsigned char* __restrict__ exists, size_t n, SlotInit si, RowGeom g) {
+  using V = typename VecT<VEC>::type;
+  constexpr int E = VEC / (int)sizeof(T);
+  union VU {
+    V v;
+    T e[E];
+  };
   __shared__ unsigned s_new, s_used;
   if (threadIdx.x == 0) {
     s_new = 0;
@@ -161,6 +254,9 @@ accum_kernel(TableView t, const long long* __restrict__ keys, const T* __restric
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned dim = t.dim;
+  const unsigned rows_per_step = 32u >> g.lpr_shift;
+  const unsigned sub = (unsigned)lane >> g.lpr_shift;
+  const unsigned c0 = (unsigned)lane & (g.lpr - 1u);
   const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
   for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
@@ -178,16 +274,23 @@ accum_kernel(TableView t, const long long* __restrict__ keys, const T* __restric
     // mode: 0 skip, 1 assign (new key), 2 add (found & exist)
     int mode = 0;
     if (valid && slot >= 0) mode = is_new ? 1 : (ex ? 2 : 0);
-    for (int j = 0; j < 32; ++j) {
-      const int m = __shfl_sync(kFull, mode, j);
+    for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step) {
+      const unsigned j = j0 + sub;
+      const int m = __shfl_sync(kFull, mode, (int)j);
+      const long long sl = shfl_ll(slot, (int)j);
       if (m == 0) continue;
-      const long long s = shfl_ll(slot, j);
-      T* row = (T*)t.planes[0] + (size_t)s * dim;
-      const T* in = vod + (base + j) * dim;
-      if (m == 1) {
-        for (unsigned c = lane; c < dim; c += 32) row[c] = in[c];
-      } else {
-        for (unsigned c = lane; c < dim; c += 32) row[c] = acc_add(row[c], in[c]);
+      unsigned char* row = t.planes[0] + (size_t)sl * g.row_bytes;
+      const unsigned char* in = (const unsigned char*)vod + (base + j) * g.row_bytes;
+      for (unsigned c = c0; c < g.vpr; c += g.lpr) {
+        VU d;
+        d.v = ld_row<VEC>(in + c * VEC);
+        if (m == 2) {
+          VU r;
+          r.v = ld_row<VEC>(row + c * VEC);
+#pragma unroll
+          for (int q = 0; q < E; ++q) d.e[q] = acc_add(r.e[q], d.e[q]);
+        }
+        st_row<VEC>(row + c * VEC, d.v);
       }
     }
     if (is_new && slot >= 0)
@@ -635,6 +738,33 @@ void note_mutation(det_table* t, size_t n, cudaStream_t s) {
   }
 }
 
+template <typename T, int VEC>
+static det_status launch_accum_v(det_table* t, const TableView& v, const long long* k, const void* vod,
+                                 const uint8_t* exists, size_t n, const SlotInit& si, const RowGeom& g,
+                                 cudaStream_t s) {
+  const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(accum_kernel<T, VEC>, kThreads));
+  accum_kernel<T, VEC><<<grid, kThreads, 0, s>>>(v, k, (const T*)vod, exists, n, si, g);
+  return DET_OK;
+}
+
+template <typename T>
+static det_status launch_accum(det_table* t, const TableView& v, const long long* k, const void* vod,
+                               const uint8_t* exists, size_t n, const SlotInit& si, const RowGeom& g, int vec,
+                               cudaStream_t s) {
+  switch (vec) {
+    case 16: return launch_accum_v<T, 16>(t, v, k, vod, exists, n, si, g, s);
+    case 8:
+      if constexpr (sizeof(T) <= 8) return launch_accum_v<T, 8>(t, v, k, vod, exists, n, si, g, s);
+    case 4:
+      if constexpr (sizeof(T) <= 4) return launch_accum_v<T, 4>(t, v, k, vod, exists, n, si, g, s);
+    case 2:
+      if constexpr (sizeof(T) <= 2) return launch_accum_v<T, 2>(t, v, k, vod, exists, n, si, g, s);
+    case 1:
+      if constexpr (sizeof(T) <= 1) return launch_accum_v<T, 1>(t, v, k, vod, exists, n, si, g, s);
+    default: return fail(DET_INVALID_ARGUMENT, "det_accum: unsupported alignment");
+  }
+}
+
 SlotInit slot_init_of(const det_table* t) {
   SlotInit si;
   si.n_planes = t->cfg.num_slot_planes;
@@ -731,12 +861,22 @@ det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* def
   CUDA_TRY(cudaSetDevice(t->cfg.device));
   const int vec = pick_vec(t->row_bytes, defaults, values_out, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
-  const int grid = grid_for(n, kThreads, t->sm_count, 8);
   const TableView v = t->view;
+  // variant 1 (default): persistent CTAs + TMA-staged key tiles; needs 16 B aligned keys.  DET_FIND_VARIANT=0
+  // selects the plain grid-stride kernel.
+  static const int variant = env_int("DET_FIND_VARIANT", 1);
+  const bool tma = variant == 1 && (((uintptr_t)keys & 15u) == 0);
   return dispatch_vec(vec, [&](auto V) -> det_status {
-    find_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, n,
-                                                              (const unsigned char*)defaults, full_size_default,
-                                                              (unsigned char*)values_out, exists, g);
+    constexpr int VV = decltype(V)::value;
+    if (tma) {
+      const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(find_kernel_tma<VV>, kThreads));
+      find_kernel_tma<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, n, (const unsigned char*)defaults,
+                                                    full_size_default, (unsigned char*)values_out, exists, g);
+    } else {
+      const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(find_kernel<VV>, kThreads));
+      find_kernel<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, n, (const unsigned char*)defaults,
+                                                full_size_default, (unsigned char*)values_out, exists, g);
+    }
     CUDA_TRY(cudaGetLastError());
     return DET_OK;
   });
@@ -761,12 +901,19 @@ det_status insert_impl(det_table* t, const int64_t* keys, const void* values, si
   }
   const int vec = pick_vec(t->row_bytes, values, nullptr, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
-  const int grid = grid_for(n, kThreads, t->sm_count, 8);
   const TableView v = t->view;
   const SlotInit si = slot_init_of(t);
+  static const int variant = env_int("DET_INSERT_VARIANT", 1);
+  const bool tma = variant == 1 && (((uintptr_t)keys & 15u) == 0);
   return dispatch_vec(vec, [&](auto V) -> det_status {
-    insert_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(v, (const long long*)keys,
-                                                                (const unsigned char*)values, n, g, si);
+    constexpr int VV = decltype(V)::value;
+    if (tma) {
+      const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(insert_kernel_tma<VV>, kThreads));
+      insert_kernel_tma<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, (const unsigned char*)values, n, g, si);
+    } else {
+      const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(insert_kernel<VV>, kThreads));
+      insert_kernel<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, (const unsigned char*)values, n, g, si);
+    }
     CUDA_TRY(cudaGetLastError());
     if (check_room) note_mutation(t, n, s);
     return DET_OK;
@@ -785,20 +932,24 @@ det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const u
   CUDA_TRY(cudaSetDevice(t->cfg.device));
   det_status st = ensure_room(t, (const long long*)keys, n, s);
   if (st != DET_OK) return st;
-  const int grid = grid_for(n, kThreads, t->sm_count, 8);
   const TableView v = t->view;
   const SlotInit si = slot_init_of(t);
   const long long* k = (const long long*)keys;
+  int vec = pick_vec(t->row_bytes, vod, nullptr, nullptr);
+  const int es = (int)dtype_size(t->cfg.value_dtype);
+  if (vec < es) return fail(DET_INVALID_ARGUMENT, "det_accum: values_or_deltas is not aligned to the value dtype");
+  const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
   switch (t->cfg.value_dtype) {
-    case DET_FLOAT32: accum_kernel<float><<<grid, kThreads, 0, s>>>(v, k, (const float*)vod, exists, n, si); break;
-    case DET_FLOAT64: accum_kernel<double><<<grid, kThreads, 0, s>>>(v, k, (const double*)vod, exists, n, si); break;
-    case DET_INT32: accum_kernel<int><<<grid, kThreads, 0, s>>>(v, k, (const int*)vod, exists, n, si); break;
-    case DET_INT64: accum_kernel<long long><<<grid, kThreads, 0, s>>>(v, k, (const long long*)vod, exists, n, si); break;
-    case DET_INT8: accum_kernel<signed char><<<grid, kThreads, 0, s>>>(v, k, (const signed char*)vod, exists, n, si); break;
-    case DET_FLOAT16: accum_kernel<__half><<<grid, kThreads, 0, s>>>(v, k, (const __half*)vod, exists, n, si); break;
-    case DET_BFLOAT16: accum_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(v, k, (const __nv_bfloat16*)vod, exists, n, si); break;
+    case DET_FLOAT32: st = launch_accum<float>(t, v, k, vod, exists, n, si, g, vec, s); break;
+    case DET_FLOAT64: st = launch_accum<double>(t, v, k, vod, exists, n, si, g, vec, s); break;
+    case DET_INT32: st = launch_accum<int>(t, v, k, vod, exists, n, si, g, vec, s); break;
+    case DET_INT64: st = launch_accum<long long>(t, v, k, vod, exists, n, si, g, vec, s); break;
+    case DET_INT8: st = launch_accum<signed char>(t, v, k, vod, exists, n, si, g, vec, s); break;
+    case DET_FLOAT16: st = launch_accum<__half>(t, v, k, vod, exists, n, si, g, vec, s); break;
+    case DET_BFLOAT16: st = launch_accum<__nv_bfloat16>(t, v, k, vod, exists, n, si, g, vec, s); break;
     default: return fail(DET_UNIMPLEMENTED, "det_accum: dtype");
   }
+  if (st != DET_OK) return st;
   CUDA_TRY(cudaGetLastError());
   note_mutation(t, n, s);
   return DET_OK;

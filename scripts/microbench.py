@@ -39,6 +39,7 @@ def main():
   ap.add_argument("--reps", type=int, default=10)
   ap.add_argument("--dims", default="16,64,128")
   ap.add_argument("--tag", default="")
+  ap.add_argument("--ops", default="", help="comma list of op-name prefixes to run (default all)")
   a = ap.parse_args()
   dev = torch.device("cuda", 0)
   Bn = a.batch
@@ -71,7 +72,14 @@ def main():
     ex = torch.ones(Bn, dtype=torch.bool, device=dev)
     row = dim * 4
 
+    want = [o for o in a.ops.split(",") if o]
+
+    def on(op):
+      return not want or any(op.startswith(w) for w in want)
+
     def emit(op, case, med, mn, algo_bytes, honest_bytes):
+      if med is None:
+        return
       print(json.dumps({"tag": a.tag, "op": op, "dim": dim, "case": case, "ms_med": round(med, 4), "ms_min": round(mn, 4),
                         "Mkeys_s": round(Bn / med / 1e3, 1), "algo_GBs": round(algo_bytes / med / 1e6, 1),
                         "algo_frac": round(algo_bytes / med / 1e6 / peak, 3),
@@ -79,34 +87,34 @@ def main():
                         "honest_frac": round(honest_bytes / med / 1e6 / peak, 3), "resident": res}), flush=True)
 
     for name, k in cases.items():
-      med, mn = timeit(lambda: t.lookup(k, dynamic_default_values=default), a.reps, flush)
+      med, mn = (timeit(lambda: t.lookup(k, dynamic_default_values=default), a.reps, flush) if on("find") else (None, None))
       emit("find", name, med, mn, Bn * row, Bn * (8 + 64 + 2 * row))
-      med, mn = timeit(lambda: t.lookup(k, dynamic_default_values=default, return_exists=True), a.reps, flush)
+      med, mn = (timeit(lambda: t.lookup(k, dynamic_default_values=default, return_exists=True), a.reps, flush) if on("find_exists") else (None, None))
       emit("find_exists", name, med, mn, Bn * row, Bn * (8 + 64 + 2 * row + 1))
     for name in ("zipf_hit100", "uniform_hit100"):
       k = cases[name]
-      med, mn = timeit(lambda: t.insert(k, vals), a.reps, flush)
+      med, mn = (timeit(lambda: t.insert(k, vals), a.reps, flush) if on("insert_existing") else (None, None))
       emit("insert_existing", name, med, mn, Bn * row, Bn * (8 + 64 + 2 * row))
-      med, mn = timeit(lambda: t.accum(k, vals, ex), a.reps, flush)
+      med, mn = (timeit(lambda: t.accum(k, vals, ex), a.reps, flush) if on("accum_existing") else (None, None))
       emit("accum_existing", name, med, mn, 2 * Bn * row, Bn * (8 + 1 + 64 + 3 * row))
       opt = de.FusedAdagrad(0.01, 0.1)
-      med, mn = timeit(lambda: opt.apply_sparse(var, k, grads), a.reps, flush)
+      med, mn = (timeit(lambda: opt.apply_sparse(var, k, grads), a.reps, flush) if on("adagrad") else (None, None))
       emit("adagrad", name, med, mn, 5 * Bn * row, Bn * (8 + 64 + 5 * row))
       if planes >= 3:
         opt2 = de.FusedAdam(0.01)
         opt2.iterations = 1
-        med, mn = timeit(lambda: opt2.apply_sparse(var, k, grads), a.reps, flush)
-        emit("adam", name, med, mn, 7 * Bn * row, Bn * (8 + 64 + 7 * row))
+        med, mn = (timeit(lambda: opt2.apply_sparse(var, k, grads), a.reps, flush) if on("adam") else (None, None))
+      emit("adam", name, med, mn, 7 * Bn * row, Bn * (8 + 64 + 7 * row))
       seg = torch.arange(Bn, device=dev, dtype=torch.int32)
-      med, mn = timeit(lambda: lookup_sparse_fused(var, k, seg, None, Bn, "sum"), a.reps, flush)
+      med, mn = (timeit(lambda: lookup_sparse_fused(var, k, seg, None, Bn, "sum"), a.reps, flush) if on("lookup_sparse_1id") else (None, None))
       emit("lookup_sparse_1id", name, med, mn, Bn * row, Bn * (8 + 4 + 64 + 2 * row))
       seg4 = torch.arange(Bn, device=dev, dtype=torch.int32) // 4
-      med, mn = timeit(lambda: lookup_sparse_fused(var, k, seg4, None, Bn // 4, "mean"), a.reps, flush)
+      med, mn = (timeit(lambda: lookup_sparse_fused(var, k, seg4, None, Bn // 4, "mean"), a.reps, flush) if on("lookup_sparse_4ids") else (None, None))
       emit("lookup_sparse_4ids", name, med, mn, Bn * row, Bn * (8 + 4 + 64 + row) + Bn // 4 * row)
     # new-key insert into free space, then remove them again
     newk = B.rank_to_key_torch(torch.arange(3 * res, 3 * res + Bn, device=dev))
     ts_i, ts_r = [], []
-    for _ in range(4):
+    for _ in range(4 if on("insert_new") or on("remove") else 0):
       flush.add_(1)
       e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
       e[0].record()
@@ -117,13 +125,15 @@ def main():
       torch.cuda.synchronize()
       ts_i.append(e[0].elapsed_time(e[1]))
       ts_r.append(e[1].elapsed_time(e[2]))
-    emit("insert_new", "uniform", float(np.median(ts_i)), float(np.min(ts_i)), Bn * row, Bn * (8 + 64 + 2 * row))
-    emit("remove", "uniform", float(np.median(ts_r)), float(np.min(ts_r)), Bn * 64, Bn * (8 + 128))
+    if ts_i:
+      emit("remove", "uniform", float(np.median(ts_r)), float(np.min(ts_r)), Bn * 64, Bn * (8 + 128))
+    if ts_i:
+      emit("insert_new", "uniform", float(np.median(ts_i)), float(np.min(ts_i)), Bn * row, Bn * (8 + 64 + 2 * row))
     u = cases["zipf_hit100"]
-    med, mn = timeit(lambda: de.unique(u), a.reps)
+    med, mn = (timeit(lambda: de.unique(u), a.reps) if on("unique") else (None, None))
     emit("unique", "zipf", med, mn, Bn * 12, Bn * 12)
     from recommenders_addons_b200.dynamic_embedding import variable as V
-    med, mn = timeit(lambda: V.partition(u, 8, True), a.reps)
+    med, mn = (timeit(lambda: V.partition(u, 8, True), a.reps) if on("partition8") else (None, None))
     emit("partition8", "zipf", med, mn, Bn * 20, Bn * 28)
     var.tables[0].close()
     del var, t
