@@ -49,6 +49,8 @@ def parse_args():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=5)
+  ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                  help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
   ap.add_argument("--distinct-batches", type=int, default=64, help="distinct key batches cycled through")
   return ap.parse_args()
 
@@ -285,7 +287,18 @@ def gpu_arm(args):
   new_vals = torch.randn(B, dim, device=dev, generator=gen_v) * 0.01
   default = torch.zeros(dim, device=dev)
   out = torch.empty(B, dim, device=dev)
-  sharded = de.ShardedVariable(var) if world > 1 else None
+  sharded, exchange = None, "none"
+  if world > 1:
+    exchange = args.exchange
+    if exchange == "peer":
+      try:
+        sharded = de.PeerShardedVariable(var)
+      except Exception as ex:  # CUDA IPC not available in this sandbox: fall back to the NCCL exchange, say so
+        print("peer-memory group failed (%r): falling back to NCCL all-to-all" % (ex,), file=sys.stderr)
+        exchange = "nccl"
+    if exchange == "nccl":
+      sharded = de.ShardedVariable(var)
+  is_peer = exchange == "peer"
 
   def step(i, ev=None):
     k = key_batches[i % n_batches]
@@ -302,9 +315,13 @@ def gpu_arm(args):
     if ev:
       ev[0].record()
     rows = sharded.lookup(k)
+    if is_peer:
+      sharded.phase_barrier()  # every rank has finished reading before any rank writes
     if ev:
       ev[1].record()
     sharded.upsert(k, new_vals)
+    if is_peer:
+      sharded.phase_barrier()  # every rank has finished writing before the next step reads
     if ev:
       ev[2].record()
     return rows
@@ -356,8 +373,12 @@ def gpu_arm(args):
         k = hk[i].to(dev, non_blocking=True)
         v = hv.to(dev, non_blocking=True)
         rows = sharded.lookup(k)
+        if is_peer:
+          sharded.phase_barrier()
         ho.copy_(rows, non_blocking=True)
         sharded.upsert(k, v)
+        if is_peer:
+          sharded.phase_barrier()
         torch.cuda.synchronize()
     e2e_step(0)
     barrier()
@@ -372,7 +393,7 @@ def gpu_arm(args):
            "h2d_bytes_per_step": int(B * (8 + 8 + dim * 4) + dim * 4), "d2h_bytes_per_step": int(B * dim * 4),
            "steps": n_e2e,
            "api": "CuckooHashTable.lookup_host + insert_host (det_find_host / det_insert_host), pinned host buffers"
-                  if sharded is None else "ShardedVariable.lookup/upsert with pinned H2D/D2H copies"}
+                  if sharded is None else ("PeerShardedVariable" if is_peer else "ShardedVariable") + ".lookup/upsert with pinned H2D/D2H copies"}
 
   if rank != 0:
     if world > 1:
@@ -395,20 +416,24 @@ def gpu_arm(args):
           "l2": "inputs larger than L2: %d distinct batches are cycled, every step touches %.0f MB of rows + %.0f MB out + "
                 "%.0f MB in of a %.1f GB table (no L2 flush; the Zipf head is hot by design)" %
                 (n_batches, B * dim * 4 / 1e6, B * dim * 4 / 1e6, B * dim * 4 / 1e6, table.stats()["hbm_bytes"] / 1e9),
-          "parallelism": "key-hash sharded x%d, NCCL all-to-all of keys and rows" % world if world > 1 else "single GPU",
+          "parallelism": ("key-hash sharded x%d, %s" % (world, "one-sided NVLink peer-memory kernels (det_peer_find/insert), no collective"
+                                                       if is_peer else "NCCL all-to-all of keys and rows")) if world > 1 else "single GPU",
       },
       "find_ms": find_ms_max, "insert_ms": ins_ms_max,
       "find_Mkeys_s": world * B / (find_ms_max * 1e-3) / 1e6, "insert_Mkeys_s": world * B / (ins_ms_max * 1e-3) / 1e6,
-      "gpu_launches": (2 if world == 1 else 10) * args.steps,
+      "gpu_launches": (2 if world == 1 else (4 if is_peer else 10)) * args.steps,
       "clocks": clocks,
       "roofline": {
-          "bound": "hbm", "kernel": "det::find_kernel<16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+          "bound": "hbm", "kernel": ("det::find_kernel_tma<16>" if world == 1 else ("det::peer_find_kernel<16> (+peer barrier)" if is_peer else "partition+all_to_all+find_kernel+all_to_all+scatter")), "achieved": achieved, "peak": peak, "unit": "GB/s",
           "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
           "algorithmic_bytes_per_launch": algo_bytes,
           "note": "algorithmic = keys x dim x 4 B (north_star definition); the kernel necessarily also moves the "
                   "gathered rows out (+%d B/key) and one 64 B bucket + 8 B key per probe: honest-traffic rate %.0f GB/s "
                   "(%.2f of peak)" % (dim * 4, honest_bytes / (find_ms_1 * 1e-3) / 1e9,
-                                      honest_bytes / (find_ms_1 * 1e-3) / 1e9 / peak),
+                                      honest_bytes / (find_ms_1 * 1e-3) / 1e9 / peak) +
+                  ("" if world == 1 else "; at N>1 (N-1)/N of the buckets and rows cross NVLink (measured peer copy 770 GB/s "
+                   "per direction per GPU): NVLink-side rate of this rank %.0f GB/s" %
+                   ((world - 1) / world * B * (64 + dim * 4) / (find_ms_1 * 1e-3) / 1e9)),
       },
   }
   if e2e:

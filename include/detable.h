@@ -188,6 +188,27 @@ det_status det_scatter_rows(const void* rows_in, const int32_t* perm, size_t n, 
 det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, size_t row_bytes,
                            void* rows_out, det_stream_t stream);
 
+/* ---- one table sharded over the GPUs of an NVSwitch box, accessed ONE-SIDED over NVLink peer memory
+ * (replaces HvdVariable.__alltoall_embedding_lookup__, python/ops/shadow_embedding_ops.py:397-447: partition ->
+ * alltoall(ids) -> local lookup -> alltoall(rows) -> scatter).  Every rank owns the shard owner(key) == rank,
+ * exports CUDA-IPC handles of its planes (det_peer_export), gathers all ranks' handles (any transport) and
+ * builds a group; det_peer_find / det_peer_insert then take keys owned by ANY rank: one kernel probes the owner's
+ * key plane and moves the row over NVLink, no collective.  A published table cannot grow.
+ * tables[p] non-NULL = shard p lives in this process (its own rank, or several shards faked on one GPU like the
+ * reference's tests, kernel_tests/dynamic_embedding_ops_test.py:329); NULL = map it from handles[p].
+ * det_peer_barrier: flag barrier over peer memory separating the "all ranks read" / "all ranks write" phases. */
+typedef struct det_peer_group det_peer_group;
+size_t det_peer_handle_bytes(void);
+det_status det_peer_export(det_table* t, void* handle_out_host);
+det_status det_peer_group_create(det_peer_group** out, det_table* const* tables, const void* handles_host,
+                                 int world, int rank, int gpu_mode);
+det_status det_peer_group_destroy(det_peer_group* g);
+det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
+                         int full_size_default, void* values_out, uint8_t* exists, det_stream_t stream);
+det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
+                           det_stream_t stream);
+det_status det_peer_barrier(det_peer_group* g, det_stream_t stream);
+
 /* ---- file-system format of SaveToFileSystem / LoadFromFileSystem
  * (cuckoo_hashtable_op.cc:310-504): raw little-endian `<prefix>-keys` (int64[n]) and
  * `<prefix>-values` (V[n*dim]).  HOST paths; synchronous. ---- */

@@ -56,6 +56,13 @@ SIGNATURES = {
     "det_partition": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "det_scatter_rows": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     "det_gather_rows": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "det_peer_handle_bytes": (_sz, []),
+    "det_peer_export": (_i, [_vp, _vp]),
+    "det_peer_group_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _i, _i, _i]),
+    "det_peer_group_destroy": (_i, [_vp]),
+    "det_peer_find": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
+    "det_peer_insert": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "det_peer_barrier": (_i, [_vp, _vp]),
     "det_save": (_i, [_vp, ctypes.c_char_p, _sz]),
     "det_load": (_i, [_vp, ctypes.c_char_p, _sz]),
     "det_get_stats": (_i, [_vp, ctypes.POINTER(DetStats), _vp]),

@@ -131,19 +131,28 @@ __device__ __forceinline__ long long shfl_ll(long long v, int src) {
   return __shfl_sync(kFull, v, src);
 }
 
+// The table a lane's key lives in.  Single-GPU kernels use one table for the whole warp (MULTI = false);
+// the sharded kernels (sharded.cu) give every lane the table of its key's OWNER GPU, mapped over NVLink
+// (MULTI = true: key plane pointer and bucket count travel with the key through the subgroup shuffles, and
+// claims use system-scope atomics).
+struct TabRef {
+  long long* keys;
+  unsigned long long nb;
+  DevState* st;
+};
+
 // Read-only probe of 32 keys (one per lane) by 8 four-lane subgroups, 4 rounds.
 // Returns, in lane j, the slot of key j or -1.  COHERENT selects L2-coherent key loads.
-template <bool COHERENT>
-__device__ __forceinline__ long long warp_find_slots(const TableView& t, long long mykey, bool valid,
-                                                     int lane) {
+template <bool COHERENT, bool MULTI>
+__device__ __forceinline__ long long warp_find_slots_t(const TabRef& my, long long mykey, bool valid, int lane) {
   const int sg = lane >> 2, sl = lane & 3;
-  const unsigned long long nb = t.nb;
   const bool special = is_special(mykey);
-  const unsigned long long myb = bucket_of(mykey, nb);
+  const unsigned long long myb = bucket_of(mykey, my.nb);
   const bool probe_me = valid && !special;
 
   long long keyr[4];
-  unsigned long long br[4];
+  unsigned long long br[4], nbr[4];
+  const long long* kbr[4];
   bool actr[4];
   longlong2 first[4];
 #pragma unroll
@@ -152,9 +161,16 @@ __device__ __forceinline__ long long warp_find_slots(const TableView& t, long lo
     keyr[r] = shfl_ll(mykey, src);
     br[r] = (unsigned long long)shfl_ll((long long)myb, src);
     actr[r] = __shfl_sync(kFull, (int)probe_me, src) != 0;
+    if (MULTI) {
+      kbr[r] = (const long long*)shfl_ll((long long)my.keys, src);
+      nbr[r] = (unsigned long long)shfl_ll((long long)my.nb, src);
+    } else {
+      kbr[r] = my.keys;
+      nbr[r] = my.nb;
+    }
     first[r] = make_longlong2(kEmptyKey, kEmptyKey);
     if (actr[r]) {
-      const long long* p = t.keys + br[r] * kBucket + sl * 2;
+      const long long* p = kbr[r] + br[r] * kBucket + sl * 2;
       first[r] = COHERENT ? ld_keys_cg(p) : ld_keys_nc(p);
     }
   }
@@ -162,6 +178,8 @@ __device__ __forceinline__ long long warp_find_slots(const TableView& t, long lo
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const long long key = keyr[r];
+    const unsigned long long nb = nbr[r];
+    const long long* kb = kbr[r];
     unsigned long long b = br[r];
     bool active = actr[r];
     long long found = -1;
@@ -180,7 +198,7 @@ __device__ __forceinline__ long long warp_find_slots(const TableView& t, long lo
           active = false;  // chain ends in a bucket that still has an EMPTY slot: key absent
         } else {
           b = (b + 1 == nb) ? 0 : b + 1;
-          const long long* p = t.keys + b * kBucket + sl * 2;
+          const long long* p = kb + b * kBucket + sl * 2;
           kk = COHERENT ? ld_keys_cg(p) : ld_keys_nc(p);
         }
       }
@@ -190,23 +208,30 @@ __device__ __forceinline__ long long warp_find_slots(const TableView& t, long lo
   }
   if (valid && special) {
     const int idx = (mykey == kTombKey) ? 1 : 0;
-    const unsigned present = *((volatile unsigned*)&t.st->special[idx]);
-    result = present ? (long long)(nb * kBucket + idx) : -1;
+    const unsigned present = *((volatile unsigned*)&my.st->special[idx]);
+    result = present ? (long long)(my.nb * kBucket + idx) : -1;
   }
   return result;
 }
 
+template <bool COHERENT>
+__device__ __forceinline__ long long warp_find_slots(const TableView& t, long long mykey, bool valid,
+                                                     int lane) {
+  const TabRef my = {t.keys, t.nb, t.st};
+  return warp_find_slots_t<COHERENT, false>(my, mykey, valid, lane);
+}
+
 // Find-or-claim probe used by every mutating kernel.  Lane j passes its key; `claim` says whether
 // an absent key may be inserted.  Returns the slot (or -1: absent and not claimed / table full) and
-// sets is_new when this call created the key.  new_from_empty counts claims that consumed an EMPTY
-// slot (as opposed to recycling a tombstone) for the `used` counter.
-__device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long long mykey, bool valid,
-                                                        bool claim, int lane, bool& is_new,
-                                                        bool& from_empty) {
+// sets is_new when this call created the key.  from_empty tells whether the claim consumed an EMPTY slot
+// (as opposed to recycling a tombstone) for the `used` counter.
+template <bool MULTI>
+__device__ __forceinline__ long long warp_find_or_claim_t(const TabRef& my, long long mykey, bool valid,
+                                                          bool claim, int lane, bool& is_new,
+                                                          bool& from_empty) {
   const int sg = lane >> 2, sl = lane & 3;
-  const unsigned long long nb = t.nb;
   const bool special = is_special(mykey);
-  const unsigned long long myb = bucket_of(mykey, nb);
+  const unsigned long long myb = bucket_of(mykey, my.nb);
   const bool probe_me = valid && !special;
 
   long long result = -1;
@@ -215,13 +240,22 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
   // by the time its round runs is harmless: free slots only disappear during a mutating kernel, every claim is
   // validated by the CAS, and a failed CAS restarts the chain with fresh L2-coherent loads.
   longlong2 first[4];
+  long long* kbr[4];
+  unsigned long long nbr[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int src = r * 8 + sg;
     const unsigned long long b0 = (unsigned long long)shfl_ll((long long)myb, src);
     const bool act = __shfl_sync(kFull, (int)probe_me, src) != 0;
+    if (MULTI) {
+      kbr[r] = (long long*)shfl_ll((long long)my.keys, src);
+      nbr[r] = (unsigned long long)shfl_ll((long long)my.nb, src);
+    } else {
+      kbr[r] = my.keys;
+      nbr[r] = my.nb;
+    }
     first[r] = make_longlong2(0, 0);
-    if (act) first[r] = ld_keys_cg(t.keys + b0 * kBucket + sl * 2);
+    if (act) first[r] = ld_keys_cg(kbr[r] + b0 * kBucket + sl * 2);
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -230,6 +264,8 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
     const unsigned long long b0 = (unsigned long long)shfl_ll((long long)myb, src);
     bool active = __shfl_sync(kFull, (int)probe_me, src) != 0;
     const bool may_claim = __shfl_sync(kFull, (int)claim, src) != 0;
+    long long* const kb = kbr[r];
+    const unsigned long long nb = nbr[r];
     unsigned long long b = b0;
     long long found = -1, first_free = -1;
     bool ff_tomb = false, fnew = false, fempty = false;
@@ -238,7 +274,7 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
     bool use_first = true;
     while (__any_sync(kFull, active)) {
       longlong2 kk = first[r];
-      if (active && !use_first) kk = ld_keys_cg(t.keys + b * kBucket + sl * 2);
+      if (active && !use_first) kk = ld_keys_cg(kb + b * kBucket + sl * 2);
       use_first = false;
       const unsigned bh0 = __ballot_sync(kFull, active && kk.x == key);
       const unsigned bh1 = __ballot_sync(kFull, active && kk.y == key);
@@ -267,7 +303,7 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
             if (!may_claim) {
               active = false;
             } else if (first_free < 0) {
-              atomicOr(&t.st->error, kErrTableFull);
+              if (MULTI) atomicOr_system(&my.st->error, kErrTableFull); else atomicOr(&my.st->error, kErrTableFull);
               active = false;
             } else {
               want_cas = true;
@@ -280,8 +316,9 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
       long long old = 0;
       const long long expect = ff_tomb ? kTombKey : kEmptyKey;
       if (want_cas && sl == 0) {
-        old = (long long)atomicCAS((unsigned long long*)(t.keys + first_free), (unsigned long long)expect,
-                                   (unsigned long long)key);
+        unsigned long long* addr = (unsigned long long*)(kb + first_free);
+        old = MULTI ? (long long)atomicCAS_system(addr, (unsigned long long)expect, (unsigned long long)key)
+                    : (long long)atomicCAS(addr, (unsigned long long)expect, (unsigned long long)key);
       }
       old = shfl_ll(old, sg * 4);
       if (want_cas) {
@@ -300,7 +337,7 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
           ff_tomb = false;
           probes = 0;
           if (++restarts > 1024u) {
-            atomicOr(&t.st->error, kErrTableFull);
+            if (MULTI) atomicOr_system(&my.st->error, kErrTableFull); else atomicOr(&my.st->error, kErrTableFull);
             active = false;
           }
         }
@@ -316,20 +353,27 @@ __device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long
   }
   if (valid && special) {
     const int idx = (mykey == kTombKey) ? 1 : 0;
-    const long long s = (long long)(nb * kBucket + idx);
+    const long long s = (long long)(my.nb * kBucket + idx);
     if (claim) {
-      const unsigned old = atomicExch(&t.st->special[idx], 1u);
+      const unsigned old = MULTI ? atomicExch_system(&my.st->special[idx], 1u) : atomicExch(&my.st->special[idx], 1u);
       result = s;
       res_new = (old == 0);
       res_empty = false;
     } else {
-      const unsigned present = *((volatile unsigned*)&t.st->special[idx]);
+      const unsigned present = *((volatile unsigned*)&my.st->special[idx]);
       result = present ? s : -1;
     }
   }
   is_new = res_new;
   from_empty = res_empty;
   return result;
+}
+
+__device__ __forceinline__ long long warp_find_or_claim(const TableView& t, long long mykey, bool valid,
+                                                        bool claim, int lane, bool& is_new,
+                                                        bool& from_empty) {
+  const TabRef my = {t.keys, t.nb, t.st};
+  return warp_find_or_claim_t<false>(my, mykey, valid, claim, lane, is_new, from_empty);
 }
 
 // ---- warp-cooperative row movement ---------------------------------------------------------------

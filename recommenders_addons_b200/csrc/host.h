@@ -52,6 +52,7 @@ struct det_table {
   uint32_t rehash_count = 0;
   float slot_init[det::kMaxPlanes];  // value given to slot-plane rows of keys created by insert/accum
   det::HostPipe* pipe = nullptr;
+  unsigned long long* peer_bar = nullptr;  // arrival flags of the NVLink peer barrier (sharded.cu)
 };
 
 namespace det {

@@ -1,0 +1,350 @@
+// sharded.cu -- ONE table key-hash sharded over the GPUs of an NVSwitch box, accessed ONE-SIDED over NVLink.
+//
+// Reference shape (python/ops/shadow_embedding_ops.py:397-447, HvdVariable.__alltoall_embedding_lookup__):
+//   partition ids by owner -> alltoall(ids) -> local lookup -> alltoall(rows) -> scatter back     (5 ops + 2 collectives)
+// Here every rank maps its peers' key/value planes (CUDA IPC over NVLink peer memory) and ONE kernel per rank does
+// the whole exchange: each 4-lane subgroup probes its key's OWNER table directly (remote 64 B bucket load), the row
+// is then loaded from (find) or stored to (insert) the owner's HBM over NVLink with 128-bit accesses; slot claims
+// and the size counters use system-scope atomics on the owner's memory.  No partition, pack, collective or
+// unpack kernels, and no host round trip for split sizes.  owner(key) = (key & 0x7fffffff) % S, the reference's
+// default_partition_fn for GPU builds (python/ops/dynamic_embedding_variable.py:165-197).
+//
+// Phases (all ranks reading / all ranks writing) are separated by det_peer_barrier, a flag barrier over the same
+// peer memory, which gives the ordering the reference gets from its collectives.
+#include <string.h>
+
+#include "host.h"
+
+namespace det {
+
+constexpr int kMaxPeers = 8;
+constexpr unsigned long long kPeerMagic = 0x44455450454552ULL;  // "DETPEER"
+constexpr unsigned kErrBarrierTimeout = 4u;
+
+struct PeerViews {
+  TableView v[kMaxPeers];
+  int world;
+  int rank;
+  int gpu_mode;
+};
+
+struct PeerBlob {
+  unsigned long long magic;
+  cudaIpcMemHandle_t keys;
+  cudaIpcMemHandle_t planes[kMaxPlanes];
+  cudaIpcMemHandle_t state;
+  cudaIpcMemHandle_t bar;
+  unsigned long long nb;
+  unsigned int row_bytes;
+  unsigned int dim;
+  int n_planes;  // 1 + slot planes
+  int device;
+  int value_dtype;
+  int pad;
+};
+
+__device__ __forceinline__ int peer_owner(long long key, int S, int gpu_mode) {
+  if (gpu_mode) return (int)(key & 0x7fffffffLL) % S;
+  long long m = key % (long long)S;
+  if (m < 0) m += S;
+  return (int)m;
+}
+
+constexpr int kThreadsP = 256;
+
+// K8a: sharded Find -- probe the owner's key plane and gather the row over NVLink, default fill folded in
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+peer_find_kernel(PeerViews pv, const long long* __restrict__ keys, size_t n,
+                 const unsigned char* __restrict__ defaults, int full_default, unsigned char* __restrict__ out,
+                 unsigned char* __restrict__ exists, RowGeom g) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsP + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsP) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const int own = valid ? peer_owner(key, pv.world, pv.gpu_mode) : pv.rank;
+    const TableView& tv = pv.v[own];
+    const TabRef my = {tv.keys, tv.nb, tv.st};
+    const long long slot = warp_find_slots_t<true, true>(my, key, valid, lane);
+    if (exists != nullptr && valid) exists[i] = slot >= 0 ? 1 : 0;
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid) {
+      src = slot >= 0 ? tv.planes[0] + (size_t)slot * g.row_bytes
+                      : (full_default ? defaults + i * g.row_bytes : DET_SRC_DEFAULT);
+      dst = out + i * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane, full_default ? nullptr : defaults);
+  }
+}
+
+// K8b: sharded Insert -- find-or-claim in the owner's key plane (system-scope CAS), row stored to the owner's HBM
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+peer_insert_kernel(PeerViews pv, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
+                   size_t n, RowGeom g, int n_slot_planes) {
+  __shared__ unsigned s_new[kMaxPeers], s_used[kMaxPeers];
+  if (threadIdx.x < kMaxPeers) {
+    s_new[threadIdx.x] = 0;
+    s_used[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsP + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsP) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const int own = valid ? peer_owner(key, pv.world, pv.gpu_mode) : pv.rank;
+    const TableView& tv = pv.v[own];
+    const TabRef my = {tv.keys, tv.nb, tv.st};
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim_t<true>(my, key, valid, valid, lane, is_new, from_empty);
+    if (__any_sync(kFull, is_new)) {
+      for (int o = 0; o < pv.world; ++o) {
+        const unsigned bn = __ballot_sync(kFull, is_new && own == o);
+        const unsigned bu = __ballot_sync(kFull, from_empty && own == o);
+        if (lane == 0 && bn) {
+          atomicAdd(&s_new[o], __popc(bn));
+          atomicAdd(&s_used[o], __popc(bu));
+        }
+      }
+    }
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid && slot >= 0) {
+      src = values + i * g.row_bytes;
+      dst = tv.planes[0] + (size_t)slot * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+    if (is_new && slot >= 0)
+      for (int p = 1; p <= n_slot_planes; ++p)
+        *reinterpret_cast<unsigned*>(tv.planes[p] + (size_t)slot * tv.dim * 4u) = kSlotUninit;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < pv.world && s_new[threadIdx.x]) {
+    atomicAdd_system(&pv.v[threadIdx.x].st->size, (unsigned long long)s_new[threadIdx.x]);
+    atomicAdd_system(&pv.v[threadIdx.x].st->used, (unsigned long long)s_used[threadIdx.x]);
+  }
+}
+
+struct BarPtrs {
+  unsigned long long* peer[kMaxPeers];  // peer[p] = rank p's arrival array (mapped), peer[rank] = local
+};
+
+// flag barrier over peer memory: publish epoch in every peer's array, wait until every peer published here
+__global__ void peer_barrier_kernel(BarPtrs bp, int rank, int world, unsigned long long epoch, DevState* st,
+                                    long long timeout_cycles) {
+  const int p = threadIdx.x;
+  if (p < world) {
+    __threadfence_system();
+    unsigned long long* dst = bp.peer[p] + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    const unsigned long long* src = bp.peer[rank] + p;
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > timeout_cycles) {
+        atomicOr(&st->error, kErrBarrierTimeout);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+}  // namespace det
+
+using namespace det;
+
+struct det_peer_group {
+  PeerViews pv;
+  BarPtrs bar;
+  det_table* local = nullptr;
+  unsigned long long* bar_local = nullptr;  // owned
+  void* opened[kMaxPeers][3 + kMaxPlanes];  // IPC mappings to close
+  int n_slot_planes = 0;
+  size_t row_bytes = 0;
+  unsigned long long epoch = 0;
+  int sm_count = 148;
+  int device = 0;
+};
+
+extern "C" {
+
+size_t det_peer_handle_bytes(void) { return sizeof(PeerBlob); }
+
+det_status det_peer_export(det_table* t, void* blob_out) {
+  if (!t || !blob_out) return fail(DET_INVALID_ARGUMENT, "det_peer_export: null argument");
+  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  PeerBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = kPeerMagic;
+  CUDA_TRY(cudaIpcGetMemHandle(&b.keys, t->view.keys));
+  b.n_planes = 1 + t->cfg.num_slot_planes;
+  for (int p = 0; p < b.n_planes; ++p) CUDA_TRY(cudaIpcGetMemHandle(&b.planes[p], t->view.planes[p]));
+  CUDA_TRY(cudaIpcGetMemHandle(&b.state, t->view.st));
+  if (!t->peer_bar) {
+    CUDA_TRY(cudaMalloc((void**)&t->peer_bar, kMaxPeers * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(t->peer_bar, 0, kMaxPeers * sizeof(unsigned long long)));
+  }
+  CUDA_TRY(cudaIpcGetMemHandle(&b.bar, t->peer_bar));
+  b.nb = t->view.nb;
+  b.row_bytes = (unsigned)t->row_bytes;
+  b.dim = (unsigned)t->cfg.dim;
+  b.device = t->cfg.device;
+  b.value_dtype = t->cfg.value_dtype;
+  // a published table must keep its planes: growth would invalidate the peers' mappings
+  t->cfg.max_capacity = t->view.capacity();
+  memcpy(blob_out, &b, sizeof(b));
+  return DET_OK;
+}
+
+det_status det_peer_group_destroy(det_peer_group* g) {
+  if (!g) return DET_OK;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < kMaxPeers; ++p)
+    for (int q = 0; q < 3 + kMaxPlanes; ++q)
+      if (g->opened[p][q]) cudaIpcCloseMemHandle(g->opened[p][q]);
+  delete g;
+  return DET_OK;
+}
+
+det_status det_peer_group_create(det_peer_group** out, det_table* const* tables, const void* blobs, int world,
+                                 int rank, int gpu_mode) {
+  if (!out || !tables) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: null argument");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: world must be in [1,8] and rank in [0,world)");
+  det_table* local = tables[rank];
+  if (!local) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: tables[rank] must be the local shard");
+  CUDA_TRY(cudaSetDevice(local->cfg.device));
+  det_peer_group* g = new det_peer_group();
+  memset(g->opened, 0, sizeof(g->opened));
+  g->local = local;
+  g->device = local->cfg.device;
+  g->sm_count = local->sm_count;
+  g->n_slot_planes = local->cfg.num_slot_planes;
+  g->row_bytes = local->row_bytes;
+  g->pv.world = world;
+  g->pv.rank = rank;
+  g->pv.gpu_mode = gpu_mode;
+  const PeerBlob* bl = (const PeerBlob*)blobs;
+  for (int p = 0; p < world; ++p) {
+    if (tables[p]) {
+      det_table* t = tables[p];
+      if (t->row_bytes != local->row_bytes || t->cfg.num_slot_planes != local->cfg.num_slot_planes) {
+        det_peer_group_destroy(g);
+        return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: shards differ in row size / slot planes");
+      }
+      if (!t->peer_bar) {
+        CUDA_TRY(cudaMalloc((void**)&t->peer_bar, kMaxPeers * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(t->peer_bar, 0, kMaxPeers * sizeof(unsigned long long)));
+      }
+      t->cfg.max_capacity = t->view.capacity();
+      g->pv.v[p] = t->view;
+      g->bar.peer[p] = t->peer_bar;
+      continue;
+    }
+    if (!bl) {
+      det_peer_group_destroy(g);
+      return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: remote shard without a handle blob");
+    }
+    const PeerBlob& b = bl[p];
+    if (b.magic != kPeerMagic || b.row_bytes != local->row_bytes || b.n_planes != 1 + local->cfg.num_slot_planes) {
+      det_peer_group_destroy(g);
+      return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: bad or mismatching peer handle blob");
+    }
+    void* ptr[3 + kMaxPlanes] = {nullptr};
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr[0], b.keys, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&ptr[1], b.state, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&ptr[2], b.bar, cudaIpcMemLazyEnablePeerAccess);
+    for (int q = 0; q < b.n_planes && e == cudaSuccess; ++q)
+      e = cudaIpcOpenMemHandle(&ptr[3 + q], b.planes[q], cudaIpcMemLazyEnablePeerAccess);
+    for (int q = 0; q < 3 + kMaxPlanes; ++q) g->opened[p][q] = ptr[q];
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      const std::string msg = std::string("det_peer_group_create: cannot map shard ") + std::to_string(p) +
+                              " over CUDA IPC: " + cudaGetErrorString(e);
+      det_peer_group_destroy(g);
+      return fail(DET_CUDA_ERROR, msg);
+    }
+    TableView& v = g->pv.v[p];
+    v.keys = (long long*)ptr[0];
+    v.st = (DevState*)ptr[1];
+    for (int q = 0; q < kMaxPlanes; ++q) v.planes[q] = (unsigned char*)ptr[3 + q];
+    v.nb = b.nb;
+    v.row_bytes = b.row_bytes;
+    v.dim = b.dim;
+    g->bar.peer[p] = (unsigned long long*)ptr[2];
+  }
+  *out = g;
+  return DET_OK;
+}
+
+det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
+                         int full_size_default, void* values_out, uint8_t* exists, det_stream_t stream) {
+  if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_find: null group");
+  if (n == 0) return DET_OK;
+  if (!keys || !values_out || !defaults) return fail(DET_INVALID_ARGUMENT, "det_peer_find: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(g->device));
+  const int vec = pick_vec(g->row_bytes, defaults, values_out, nullptr);
+  const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
+  const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+  const unsigned char* d = (const unsigned char*)defaults;
+  unsigned char* o = (unsigned char*)values_out;
+  const long long* k = (const long long*)keys;
+  switch (vec) {
+    case 16: peer_find_kernel<16><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 8: peer_find_kernel<8><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 4: peer_find_kernel<4><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 2: peer_find_kernel<2><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    default: peer_find_kernel<1><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
+                           det_stream_t stream) {
+  if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_insert: null group");
+  if (n == 0) return DET_OK;
+  if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_peer_insert: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(g->device));
+  const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
+  const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
+  const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+  const unsigned char* v = (const unsigned char*)values;
+  const long long* k = (const long long*)keys;
+  const int np = g->n_slot_planes;
+  switch (vec) {
+    case 16: peer_insert_kernel<16><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
+    case 8: peer_insert_kernel<8><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
+    case 4: peer_insert_kernel<4><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
+    case 2: peer_insert_kernel<2><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
+    default: peer_insert_kernel<1><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+det_status det_peer_barrier(det_peer_group* g, det_stream_t stream) {
+  if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_barrier: null group");
+  CUDA_TRY(cudaSetDevice(g->device));
+  g->epoch += 1;
+  // ~4 s at 2 GHz: a peer that never arrives must not hang the GPU
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->bar, g->pv.rank, g->pv.world, g->epoch, g->local->view.st,
+                                                         8000000000LL);
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+}  // extern "C"

@@ -382,6 +382,8 @@ __global__ void reset_state_kernel(DevState* st) {
   st->used = 0;
   st->special[0] = 0;
   st->special[1] = 0;
+  st->error = 0;  // cudaMalloc memory is not zeroed: every field must be initialised here
+  st->pad = 0;
   st->scratch[0] = st->scratch[1] = st->scratch[2] = st->scratch[3] = 0;
 }
 
@@ -847,6 +849,7 @@ det_status det_table_destroy(det_table* t) {
   if (t->h_state) cudaFreeHost(t->h_state);
   if (t->h_used_snap) cudaFreeHost(t->h_used_snap);
   if (t->snap_ev) cudaEventDestroy(t->snap_ev);
+  if (t->peer_bar) cudaFree(t->peer_bar);
   host_pipe_free(t);
   delete t;
   return DET_OK;

@@ -85,3 +85,98 @@ class ShardedVariable(object):
     t = s.clone().to(next(iter(self.local.tables)).device) if hasattr(self.local, "tables") else s.clone()
     dist.all_reduce(t, group=self.group)
     return t
+
+
+class PeerShardedVariable(object):
+  """The B200-native sharded table: every rank maps its peers' shards over NVLink (CUDA IPC) and ONE kernel per
+  call probes the owner's key plane and moves the row over NVLink -- no partition / all-to-all / stitch
+  (det_peer_find / det_peer_insert).  `local_variable` must be single-shard, pre-sized (a published table cannot
+  grow) and created identically on every rank.  With `fake_shards` (a list of Variables on ONE GPU, the way the
+  reference's tests fake devices) no process group is needed.
+
+  lookup()/upsert() are stream-ordered on the current stream; phase_barrier() separates a phase in which ranks
+  read from a phase in which ranks write (the ordering the reference gets from its collectives)."""
+
+  def __init__(self, local_variable=None, group=None, fake_shards=None, gpu_mode=True):
+    import ctypes
+    from .. import _lib
+    self._lib = _lib.lib()
+    self._libmod = _lib
+    if fake_shards is not None:
+      self.world, self.rank = len(fake_shards), 0
+      tables = [v.tables[0] for v in fake_shards]
+      self.local = fake_shards[0]
+      blobs = None
+    else:
+      self.local = local_variable
+      self.world = dist.get_world_size(group)
+      self.rank = dist.get_rank(group)
+      t = local_variable.tables[0]
+      nbytes = self._lib.det_peer_handle_bytes()
+      mine = (ctypes.c_ubyte * nbytes)()
+      _lib.check(self._lib.det_peer_export(t.handle, ctypes.cast(mine, ctypes.c_void_p)))
+      send = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=t.device)
+      gathered = [torch.empty_like(send) for _ in range(self.world)]
+      dist.all_gather(gathered, send, group=group)
+      blobs = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+      tables = [None] * self.world
+      tables[self.rank] = t
+    self._tables = tables
+    self.dim = self.local.dim
+    self.device = self.local.tables[0].device
+    self.value_dtype = self.local.value_dtype
+    arr = (ctypes.c_void_p * self.world)(*[(tb.handle if tb is not None else None) for tb in tables])
+    self._blob_buf = ctypes.create_string_buffer(blobs, len(blobs)) if blobs is not None else None
+    g = ctypes.c_void_p()
+    _lib.check(self._lib.det_peer_group_create(ctypes.byref(g), arr,
+                                               ctypes.cast(self._blob_buf, ctypes.c_void_p) if blobs else None,
+                                               self.world, self.rank, 1 if gpu_mode else 0))
+    self._g = g
+    self._group = group
+    self._default = self.local.tables[0]._default_value
+
+  def _sp(self):
+    import ctypes
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  def lookup(self, keys, return_exists=False, default=None):
+    import ctypes
+    flat = keys.reshape(-1).contiguous()
+    n = flat.numel()
+    d = self._default if default is None else default.contiguous()
+    full = 1 if (n > 0 and d.numel() == n * self.dim) else 0
+    out = torch.empty((n, self.dim), dtype=self.value_dtype, device=self.device)
+    ex = torch.empty(n, dtype=torch.bool, device=self.device) if return_exists else None
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    self._libmod.check(self._lib.det_peer_find(self._g, p(flat), n, p(d), full, p(out), p(ex), self._sp()))
+    out = out.reshape(tuple(keys.shape) + (self.dim,))
+    return (out, ex.reshape(keys.shape)) if return_exists else out
+
+  def upsert(self, keys, values):
+    import ctypes
+    flat = keys.reshape(-1).contiguous()
+    vals = values.reshape(-1, self.dim).contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    self._libmod.check(self._lib.det_peer_insert(self._g, p(flat), p(vals), flat.numel(), self._sp()))
+
+  def phase_barrier(self):
+    self._libmod.check(self._lib.det_peer_barrier(self._g, self._sp()))
+
+  def size(self):
+    if self._group is None and self.world > 1 and all(t is not None for t in self._tables):
+      return sum(int(t.size()) for t in self._tables)
+    s = self.local.size().to(self.device)
+    if self.world > 1:
+      dist.all_reduce(s, group=self._group)
+    return int(s)
+
+  def close(self):
+    if getattr(self, "_g", None):
+      self._lib.det_peer_group_destroy(self._g)
+      self._g = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass

@@ -1,0 +1,69 @@
+"""One-sided sharded table (det_peer_*): ONE kernel probes the owner shard and moves rows directly.
+Single-GPU coverage fakes the shards on one device (as the reference's tests do,
+dynamic_embedding_ops_test.py:329); the real NVLink path is covered by tests/test_multigpu_gpu.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("dim", [4, 64])
+def test_peer_fake_shards_vs_oracle(world, dim):
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  dev = torch.device("cuda", 0)
+  shards = [de.Variable(dim=dim, init_size=1 << 16, initializer=-1.0, name="peer-%d-%d-%d" % (world, dim, i))
+            for i in range(world)]
+  pv = de.PeerShardedVariable(fake_shards=shards)
+  rng = np.random.default_rng(world * 10 + dim)
+  lo = np.iinfo(np.int64).min
+  keys = rng.choice(np.arange(-40000, 40000), 20000, replace=False).astype(np.int64)
+  keys[:3] = [lo, lo + 1, np.iinfo(np.int64).max]
+  vals = rng.normal(0, 0.01, (keys.shape[0], dim)).astype(np.float32)
+  ot = O.PortTable(dim)
+  tk = lambda a: torch.from_numpy(a).to(dev)
+  pv.upsert(tk(keys), tk(vals))
+  ot.insert(keys, vals)
+  # every key landed in the shard the reference's partition function names, sizes are exact
+  owner = O.default_partition_fn(keys, world, True)
+  assert [int(s.size()) for s in shards] == [int((owner == i).sum()) for i in range(world)]
+  assert pv.size() == ot.size()
+  for i, s in enumerate(shards):
+    k, _ = s.export()
+    assert bool((torch.from_numpy(O.default_partition_fn(k.cpu().numpy(), world, True)) == i).all())
+  # lookups of present + absent keys, broadcast and full-size defaults
+  q = np.concatenate([keys[::2], rng.integers(50000, 90000, 5000)]).astype(np.int64)
+  rng.shuffle(q)
+  got, ex = pv.lookup(tk(q), return_exists=True)
+  exp, eex = ot.find(q, np.full(dim, -1, np.float32), True)
+  np.testing.assert_array_equal(ex.cpu().numpy(), eex)
+  np.testing.assert_array_equal(got.cpu().numpy(), exp)
+  d = rng.normal(size=(q.shape[0], dim)).astype(np.float32)
+  np.testing.assert_array_equal(pv.lookup(tk(q), default=tk(d)).cpu().numpy(), ot.find(q, d))
+  # overwrite + new keys through the one-sided path; then the per-shard tables agree with plain lookups
+  k2 = np.concatenate([keys[:5000], rng.integers(100000, 200000, 3000)]).astype(np.int64)
+  k2 = np.unique(k2)
+  v2 = rng.normal(0, 0.01, (k2.shape[0], dim)).astype(np.float32)
+  pv.upsert(tk(k2), tk(v2))
+  pv.phase_barrier()
+  ot.insert(k2, v2)
+  assert pv.size() == ot.size()
+  allk = np.concatenate([keys, k2])
+  np.testing.assert_array_equal(pv.lookup(tk(allk)).cpu().numpy(), ot.find(allk, np.full(dim, -1, np.float32)))
+  for s in shards:
+    assert s.tables[0].stats()["error_flags"] == 0
+  pv.close()
+
+
+def test_published_table_cannot_grow():
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  from recommenders_addons_b200._lib import DetError
+  shards = [de.Variable(dim=4, init_size=1024, name="peer-fixed-%d" % i) for i in range(2)]
+  pv = de.PeerShardedVariable(fake_shards=shards)
+  with pytest.raises(DetError, match="max_capacity"):
+    shards[0].upsert(torch.arange(0, 4000, 2, device="cuda"), torch.zeros(2000, 4, device="cuda"))
+  pv.close()
