@@ -242,7 +242,7 @@ constexpr int kSegPerGroup = 4;  // segments a lane-group works on concurrently 
 // per lane; within a segment the ids are accumulated strictly in order (mul, then add: the summation order of
 // the reference test oracle).
 template <int VF>
-__global__ void __launch_bounds__(kThreadsF)
+__global__ void __launch_bounds__(kThreadsF, 3)
 segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
                    const float* __restrict__ weights, size_t batch, int combiner,
                    const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
@@ -642,8 +642,8 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   CUDA_TRY(cudaMallocAsync((void**)&slots, (nnz ? nnz : 1) * sizeof(long long), s));
   segment_offsets_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, s>>>(segment_ids, nnz, batch, seg_start, t->view.st);
   if (nnz)
-    resolve_slots_kernel<<<grid_for(nnz, kThreadsF, t->sm_count, 8), kThreadsF, 0, s>>>(t->view, (const long long*)ids,
-                                                                                     nnz, slots);
+    resolve_slots_kernel<<<grid_for(nnz, kThreadsF, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF,
+                           0, s>>>(t->view, (const long long*)ids, nnz, slots);
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out) & 15u) == 0);
   unsigned vpr, lpr, sh;
@@ -651,7 +651,8 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   det_status rc = DET_OK;
   const unsigned gpw = 32u >> sh;
   if (vpr <= lpr) {
-    const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, 8);
+    const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
+    const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
       segment_sum_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
     else
@@ -686,7 +687,10 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)grads | (uintptr_t)init_param) & 15u) == 0);
   unsigned vpr, lpr, sh;
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
-  const int grid = grid_for(n, kThreadsF, t->sm_count, 8);
+  int occ;
+  if (opt == 0) occ = vec4 ? occupancy_of(apply_kernel<4, 0>, kThreadsF) : occupancy_of(apply_kernel<1, 0>, kThreadsF);
+  else occ = vec4 ? occupancy_of(apply_kernel<4, 1>, kThreadsF) : occupancy_of(apply_kernel<1, 1>, kThreadsF);
+  const int grid = grid_for(n, kThreadsF, t->sm_count, occ);
   const TableView v = t->view;
   const long long* k = (const long long*)keys;
   if (opt == 0) {

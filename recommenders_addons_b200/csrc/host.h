@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 #include <type_traits>
@@ -26,6 +27,27 @@ det_status fail(det_status code, const std::string& msg);
                              ": " + cudaGetErrorString(_e));                                        \
     }                                                                                               \
   } while (0)
+
+// resident CTAs per SM of a kernel (cached per kernel): grids are sized to exactly one resident wave
+template <typename K>
+inline int occupancy_of(K kernel, int threads) {
+  static thread_local const void* last_k = nullptr;
+  static thread_local int last_v = 0;
+  if (last_k == (const void*)kernel) return last_v;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) {
+    cudaGetLastError();
+    nb = 2;
+  }
+  last_k = (const void*)kernel;
+  last_v = nb;
+  return nb;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 
 struct HostPipe;  // chunked H2D -> kernel -> D2H pipeline state (host_api.cu)
 

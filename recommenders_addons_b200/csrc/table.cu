@@ -56,27 +56,6 @@ int grid_for(size_t n_items, int items_per_block, int sm_count, int blocks_per_s
   return (int)(need < cap ? need : cap);
 }
 
-// resident CTAs per SM of a kernel (cached per kernel): grids are sized to exactly one resident wave
-template <typename K>
-static int occupancy_of(K kernel, int threads) {
-  static thread_local const void* last_k = nullptr;
-  static thread_local int last_v = 0;
-  if (last_k == (const void*)kernel) return last_v;
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) {
-    cudaGetLastError();
-    nb = 2;
-  }
-  last_k = (const void*)kernel;
-  last_v = nb;
-  return nb;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 // ================================================================================================
 // Kernels
 // ================================================================================================
@@ -808,6 +787,12 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
   if (t->max_lf > 0.9f) t->max_lf = 0.9f;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  // Probes read one 64 B bucket and nothing near it: ask L2 not to fetch 128 B per miss (ncu: dram read was
+  // keys + rows + 128 B per probe with the default granularity).  DET_L2_FETCH=0 leaves the device default.
+  {
+    const int fetch = env_int("DET_L2_FETCH", 64);
+    if (fetch > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
+  }
   t->sm_count = prop.multiProcessorCount;
   uint64_t init = cfg->init_capacity ? cfg->init_capacity : 8192;
   if (cfg->max_capacity && init > cfg->max_capacity) init = cfg->max_capacity;
