@@ -419,46 +419,65 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
       atomicAdd(&s_new, __popc(bn));
       atomicAdd(&s_used, __popc(bu));
     }
-    for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step) {
-      const unsigned j = j0 + sub;
-      const long long s = shfl_ll(slot, (int)j);
-      const bool nw = (bn >> j) & 1u;
-      const bool row_ok = (base + j < n) && s >= 0;
-      const size_t ro = row_ok ? (size_t)s * dim : 0;
-      // slot state absent: key created in this launch, or created by insert/accum and never stepped.
-      // Every lane reads the marker word BEFORE any lane of the row's group overwrites it.
-      const unsigned mark = row_ok ? __float_as_uint(S1[ro]) : 0u;
+    // two row-steps per iteration: all loads of both rows are issued before the first update/store
+    constexpr int RU = 2;
+    for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step * RU) {
+      bool ok[RU], nwv[RU], fresh[RU];
+      size_t ro[RU], gi[RU];
+      unsigned mark[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const unsigned j = j0 + (unsigned)u * rows_per_step + sub;
+        const unsigned jj = j & 31u;
+        const long long s = shfl_ll(slot, (int)jj);
+        nwv[u] = (bn >> jj) & 1u;
+        gi[u] = base + jj;
+        ok[u] = (j < 32u) && (gi[u] < n) && s >= 0;
+        ro[u] = ok[u] ? (size_t)s * dim : 0;
+        // slot state absent: key created in this launch, or created by insert/accum and never stepped.
+        // Every lane reads the marker word BEFORE any lane of the row's group overwrites it.
+        mark[u] = ok[u] ? __float_as_uint(S1[ro[u]]) : 0u;
+      }
       __syncwarp();
-      if (!row_ok) continue;
-      const bool fresh = nw || (mark == kSlotUninit);
-      const float* g_row = grads + (base + j) * dim;
-      const float* i_row = full_init ? init_param + (base + j) * dim : init_param;
+#pragma unroll
+      for (int u = 0; u < RU; ++u) fresh[u] = nwv[u] || (mark[u] == kSlotUninit);
       for (unsigned c = c0; c < vpr; c += lpr) {
         const size_t o = (size_t)c * VF;
-        FVec<VF> g, p, a;
-        g.load(g_row + o);
-        if (nw) p.load(i_row + o); else p.load(P + ro + o);
-        if (OPT == 0) {
-          if (fresh) a.fill(h.init_slot); else a.load(S1 + ro + o);
-          // accum += g*g ; var -= lr*g / (sqrt(accum) + eps)
-          a.zip(g, [](float& av, float gv) { av = av + gv * gv; });
-          FVec<VF> upd = g;
-          upd.zip(a, [&h](float& u, float av) { u = (h.lr * u) / (sqrtf(av) + h.eps); });
-          p.zip(upd, [](float& pv, float u) { pv = pv - u; });
-          a.store(S1 + ro + o);
-          p.store(P + ro + o);
-        } else {
-          FVec<VF> m, v;
-          if (fresh) { m.zero(); v.zero(); } else { m.load(S1 + ro + o); v.load(S2 + ro + o); }
-          // m += (g-m)(1-b1) ; v += (g*g-v)(1-b2) ; var -= (m*alpha)/(sqrt(v)+eps)
-          m.zip(g, [omb1](float& mv, float gv) { mv = mv + (gv - mv) * omb1; });
-          v.zip(g, [omb2](float& vv, float gv) { vv = vv + (gv * gv - vv) * omb2; });
-          FVec<VF> upd = m;
-          upd.zip(v, [&h](float& u, float vv) { u = (u * h.lr) / (sqrtf(vv) + h.eps); });
-          p.zip(upd, [](float& pv, float u) { pv = pv - u; });
-          m.store(S1 + ro + o);
-          v.store(S2 + ro + o);
-          p.store(P + ro + o);
+        FVec<VF> g[RU], p[RU], a[RU], b[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          if (!ok[u]) continue;
+          g[u].load(grads + gi[u] * dim + o);
+          if (nwv[u]) p[u].load((full_init ? init_param + gi[u] * dim : init_param) + o);
+          else p[u].load(P + ro[u] + o);
+          if (OPT == 0) {
+            if (fresh[u]) a[u].fill(h.init_slot); else a[u].load(S1 + ro[u] + o);
+          } else {
+            if (fresh[u]) { a[u].zero(); b[u].zero(); } else { a[u].load(S1 + ro[u] + o); b[u].load(S2 + ro[u] + o); }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+          if (!ok[u]) continue;
+          if (OPT == 0) {
+            // accum += g*g ; var -= lr*g / (sqrt(accum) + eps)
+            a[u].zip(g[u], [](float& av, float gv) { av = av + gv * gv; });
+            FVec<VF> upd = g[u];
+            upd.zip(a[u], [&h](float& x, float av) { x = (h.lr * x) / (sqrtf(av) + h.eps); });
+            p[u].zip(upd, [](float& pv, float x) { pv = pv - x; });
+            a[u].store(S1 + ro[u] + o);
+            p[u].store(P + ro[u] + o);
+          } else {
+            // m += (g-m)(1-b1) ; v += (g*g-v)(1-b2) ; var -= (m*alpha)/(sqrt(v)+eps)
+            a[u].zip(g[u], [omb1](float& mv, float gv) { mv = mv + (gv - mv) * omb1; });
+            b[u].zip(g[u], [omb2](float& vv, float gv) { vv = vv + (gv * gv - vv) * omb2; });
+            FVec<VF> upd = a[u];
+            upd.zip(b[u], [&h](float& x, float vv) { x = (x * h.lr) / (sqrtf(vv) + h.eps); });
+            p[u].zip(upd, [](float& pv, float x) { pv = pv - x; });
+            a[u].store(S1 + ro[u] + o);
+            b[u].store(S2 + ro[u] + o);
+            p[u].store(P + ro[u] + o);
+          }
         }
       }
     }
@@ -638,8 +657,14 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   CUDA_TRY(cudaSetDevice(t->cfg.device));
   long long* seg_start = nullptr;
   long long* slots = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&seg_start, (batch + 1) * sizeof(long long), s));
-  CUDA_TRY(cudaMallocAsync((void**)&slots, (nnz ? nnz : 1) * sizeof(long long), s));
+  {
+    void* sc = nullptr;
+    const size_t seg_bytes = ((batch + 1) * sizeof(long long) + 255) & ~(size_t)255;
+    det_status sst = table_scratch(t, seg_bytes + (nnz ? nnz : 1) * sizeof(long long), &sc);
+    if (sst != DET_OK) return sst;
+    seg_start = (long long*)sc;
+    slots = (long long*)((unsigned char*)sc + seg_bytes);
+  }
   segment_offsets_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, s>>>(segment_ids, nnz, batch, seg_start, t->view.st);
   if (nnz)
     resolve_slots_kernel<<<grid_for(nnz, kThreadsF, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF,
@@ -667,8 +692,6 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
     rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse: dim too large for the fused kernel");
   }
   if (rc == DET_OK && cudaGetLastError() != cudaSuccess) rc = fail(DET_CUDA_ERROR, "det_lookup_sparse: launch failed");
-  cudaFreeAsync(seg_start, s);
-  cudaFreeAsync(slots, s);
   return rc;
 }
 

@@ -74,6 +74,8 @@ struct det_table {
   uint32_t rehash_count = 0;
   float slot_init[det::kMaxPlanes];  // value given to slot-plane rows of keys created by insert/accum
   det::HostPipe* pipe = nullptr;
+  void* scratch = nullptr;           // per-table device scratch reused by det_lookup_sparse / det_export
+  size_t scratch_bytes = 0;
   unsigned long long* peer_bar = nullptr;  // arrival flags of the NVLink peer barrier (sharded.cu)
 };
 
@@ -84,5 +86,7 @@ void note_mutation(det_table* t, size_t n, cudaStream_t s);
 det_status insert_impl(det_table* t, const int64_t* keys, const void* values, size_t n, cudaStream_t s,
                        bool check_room);
 det_status table_clear_async(det_table* t, cudaStream_t s);
+// stream-ordered users only (one stream per table at a time); grows with a sync, never shrinks
+det_status table_scratch(det_table* t, size_t bytes, void** out);
 void host_pipe_free(det_table* t);
 }  // namespace det

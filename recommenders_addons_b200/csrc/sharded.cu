@@ -174,6 +174,7 @@ struct det_peer_group {
   unsigned long long epoch = 0;
   int sm_count = 148;
   int device = 0;
+  int n_remote = 0;  // shards mapped from other processes
 };
 
 extern "C" {
@@ -257,6 +258,7 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
       return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: remote shard without a handle blob");
     }
     const PeerBlob& b = bl[p];
+    g->n_remote++;
     if (b.magic != kPeerMagic || b.row_bytes != local->row_bytes || b.n_planes != 1 + local->cfg.num_slot_planes) {
       det_peer_group_destroy(g);
       return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: bad or mismatching peer handle blob");
@@ -338,11 +340,12 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
 
 det_status det_peer_barrier(det_peer_group* g, det_stream_t stream) {
   if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_barrier: null group");
+  if (g->n_remote == 0) return DET_OK;  // every shard lives in this process: stream order is the barrier
   CUDA_TRY(cudaSetDevice(g->device));
   g->epoch += 1;
-  // ~4 s at 2 GHz: a peer that never arrives must not hang the GPU
+  // ~20 s at 2 GHz: a peer that never arrives must not hang the GPU
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->bar, g->pv.rank, g->pv.world, g->epoch, g->local->view.st,
-                                                         8000000000LL);
+                                                         40000000000LL);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
 }

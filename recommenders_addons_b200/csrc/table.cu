@@ -746,6 +746,22 @@ static det_status launch_accum(det_table* t, const TableView& v, const long long
   }
 }
 
+det_status table_scratch(det_table* t, size_t bytes, void** out) {
+  if (bytes > t->scratch_bytes) {
+    if (t->scratch) {
+      CUDA_TRY(cudaDeviceSynchronize());
+      cudaFree(t->scratch);
+      t->scratch = nullptr;
+      t->scratch_bytes = 0;
+    }
+    const size_t want = bytes + (bytes >> 2) + 4096;
+    CUDA_TRY(cudaMalloc(&t->scratch, want));
+    t->scratch_bytes = want;
+  }
+  *out = t->scratch;
+  return DET_OK;
+}
+
 SlotInit slot_init_of(const det_table* t) {
   SlotInit si;
   si.n_planes = t->cfg.num_slot_planes;
@@ -835,6 +851,7 @@ det_status det_table_destroy(det_table* t) {
   if (t->h_used_snap) cudaFreeHost(t->h_used_snap);
   if (t->snap_ev) cudaEventDestroy(t->snap_ev);
   if (t->peer_bar) cudaFree(t->peer_bar);
+  if (t->scratch) cudaFree(t->scratch);
   host_pipe_free(t);
   delete t;
   return DET_OK;
@@ -1007,8 +1024,14 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
   const size_t n_tiles = (cap + kExportTile - 1) / kExportTile;
   unsigned* counts = nullptr;
   unsigned long long* offs = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&counts, n_tiles * sizeof(unsigned), s));
-  CUDA_TRY(cudaMallocAsync((void**)&offs, n_tiles * sizeof(unsigned long long), s));
+  {
+    void* sc = nullptr;
+    const size_t off_bytes = (n_tiles * sizeof(unsigned) + 255) & ~(size_t)255;
+    det_status sst = table_scratch(t, off_bytes + n_tiles * sizeof(unsigned long long), &sc);
+    if (sst != DET_OK) return sst;
+    counts = (unsigned*)sc;
+    offs = (unsigned long long*)((unsigned char*)sc + off_bytes);
+  }
   const int grid = grid_for(n_tiles, 1, t->sm_count, 8);
   export_count_kernel<<<grid, kThreads, 0, s>>>(v, counts, n_tiles);
   export_scan_kernel<<<1, 1024, 0, s>>>(counts, offs, n_tiles, v.st);
@@ -1025,8 +1048,6 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
     export_fix_slot_rows_kernel<<<grid_for(max_n, 8, t->sm_count, 8), kThreads, 0, s>>>(
         (float*)values_out, &v.st->scratch[1], (unsigned)t->cfg.dim, t->slot_init[plane]);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaFreeAsync(counts, s));
-  CUDA_TRY(cudaFreeAsync(offs, s));
   DevState ds;
   det_status st = read_state(t, s, &ds);
   if (st != DET_OK) return st;

@@ -6,6 +6,9 @@ mkdir -p gpurun_out
 rm -f gpurun_out/summary_multi$N.txt
 nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
 if [ "$N" = "2" ]; then
+  timeout 600 python -m pytest tests/test_peer_gpu.py tests/test_fused_gpu.py tests/test_table_gpu.py -x -q -m gpu -p no:cacheprovider --timeout 500 > gpurun_out/test_single_on_multi.log 2>&1
+  echo "single-gpu tests exit $?" | tee -a gpurun_out/summary_multi$N.txt
+  tail -n 5 gpurun_out/test_single_on_multi.log
   timeout 600 python -m pytest tests/test_multigpu_gpu.py -x -q -m gpu -p no:cacheprovider --timeout 500 > gpurun_out/test_multigpu.log 2>&1
   echo "multigpu test exit $?" | tee -a gpurun_out/summary_multi$N.txt
   tail -n 15 gpurun_out/test_multigpu.log
