@@ -51,6 +51,8 @@ def parse_args():
   ap.add_argument("--e2e-steps", type=int, default=5)
   ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                   help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
+  ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                  help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2])")
   ap.add_argument("--distinct-batches", type=int, default=64, help="distinct key batches cycled through")
   return ap.parse_args()
 
@@ -472,9 +474,73 @@ def reference_arm(args):
   print(json.dumps(line))
 
 
+def c3_arm(args):
+  """Secondary workload, BASELINE configs[2]: fused embedding_lookup_sparse + Adagrad, 26 Criteo-shaped sparse
+  features x batch 65536 (nnz = 1,703,936 ids/step, one id per (sample, feature)), dim 64, single GPU.
+  Step = forward (det_lookup_sparse: ids -> [nnz, dim] rows, combiner sum) + tf.unique of the ids + per-unique
+  gradient sum + fused find-or-insert Adagrad (det_apply_adagrad).  Not the headline metric."""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  from recommenders_addons_b200.dynamic_embedding.ops import lookup_sparse_fused
+  dev = torch.device("cuda", 0)
+  torch.cuda.set_device(0)
+  dim, nfeat, batch = args.dim, 26, 65536
+  rng = np.random.default_rng(45)
+  vocab = np.exp(rng.uniform(np.log(1e3), np.log(4e7), nfeat))
+  vocab = np.maximum(1000, (vocab / vocab.sum() * 1e8)).astype(np.int64)  # ~1e8 rows in total
+  gen = torch.Generator(device=dev).manual_seed(42)
+  total = int(vocab.sum())
+  var = de.Variable(dim=dim, init_size=2 * total, initializer=0.0, num_slot_planes=1, name="c3_table")
+  table = var.tables[0]
+  offs = np.concatenate([[0], np.cumsum(vocab)])[:-1]
+  for b in range(0, total, 1 << 20):  # resident: every (feature, rank) key
+    r = torch.arange(b, min(total, b + (1 << 20)), dtype=torch.int64, device=dev)
+    table.insert(rank_to_key_torch(r), torch.randn(r.numel(), dim, device=dev, generator=gen) * 0.01)
+  cdfs = [zipf_cdf_torch(int(v), dev) for v in vocab]
+  nb = max(1, min(args.steps + args.warmup, 16))
+  batches = []
+  for _ in range(nb):
+    cols = [torch.searchsorted(c, torch.rand(batch, dtype=torch.float64, device=dev, generator=gen)).clamp_(max=c.numel() - 1) + int(o)
+            for c, o in zip(cdfs, offs)]
+    batches.append(rank_to_key_torch(torch.stack(cols, 1).reshape(-1)))  # row-major (sample, feature)
+  del cdfs
+  nnz = batch * nfeat
+  seg = torch.arange(nnz, device=dev, dtype=torch.int32)
+  gout = torch.randn(nnz, dim, device=dev, generator=gen) * 0.01  # upstream gradient of every (sample, feature) row
+  opt = de.FusedAdagrad(0.01, 0.1)
+
+  def step(i):
+    ids = batches[i % nb]
+    out = lookup_sparse_fused(var, ids, seg, None, nnz, "sum")
+    uniq, idx = de.unique(ids)
+    g = torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
+    opt.iterations += 1
+    opt.apply_sparse(var, uniq, g)
+    return out
+
+  for i in range(args.warmup):
+    step(i)
+  torch.cuda.synchronize()
+  t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t0.record()
+  for i in range(args.steps):
+    step(args.warmup + i)
+  t1.record()
+  torch.cuda.synchronize()
+  ms = t0.elapsed_time(t1) / args.steps
+  print(json.dumps({"metric": "fused embedding_lookup_sparse + Adagrad step, M ids/s (BASELINE configs[2])",
+                    "value": nnz / ms / 1e3, "unit": "M ids/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
+                    "config": {"workload": "26 features x batch 65536, dim %d, %d resident rows, Zipf(1.05) per feature; "
+                                           "includes tf.unique + torch index_add for the per-unique gradient sum" % (dim, total),
+                               "nnz": nnz, "unique_per_step": int(de.unique(batches[0])[0].numel())}}))
+
+
 if __name__ == "__main__":
   a = parse_args()
   if a.impl == "reference":
     reference_arm(a)
+  elif a.workload == "c3":
+    c3_arm(a)
   else:
     gpu_arm(a)

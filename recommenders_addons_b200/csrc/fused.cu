@@ -386,7 +386,7 @@ struct OptHyper {
   float init_slot;  // adagrad initial accumulator
 };
 
-template <int VF, int OPT>
+template <int VF, int OPT, int RU>
 __global__ void __launch_bounds__(kThreadsF)
 apply_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ grads, size_t n,
              OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
@@ -420,7 +420,6 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
       atomicAdd(&s_used, __popc(bu));
     }
     // two row-steps per iteration: all loads of both rows are issued before the first update/store
-    constexpr int RU = 2;
     for (unsigned j0 = 0; j0 < 32u; j0 += rows_per_step * RU) {
       bool ok[RU], nwv[RU], fresh[RU];
       size_t ro[RU], gi[RU];
@@ -710,19 +709,22 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)grads | (uintptr_t)init_param) & 15u) == 0);
   unsigned vpr, lpr, sh;
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
-  int occ;
-  if (opt == 0) occ = vec4 ? occupancy_of(apply_kernel<4, 0>, kThreadsF) : occupancy_of(apply_kernel<1, 0>, kThreadsF);
-  else occ = vec4 ? occupancy_of(apply_kernel<4, 1>, kThreadsF) : occupancy_of(apply_kernel<1, 1>, kThreadsF);
-  const int grid = grid_for(n, kThreadsF, t->sm_count, occ);
+  static const int ru = env_int("DET_APPLY_RU", 2);
   const TableView v = t->view;
   const long long* k = (const long long*)keys;
-  if (opt == 0) {
-    if (vec4) apply_kernel<4, 0><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
-    else apply_kernel<1, 0><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
-  } else {
-    if (vec4) apply_kernel<4, 1><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
-    else apply_kernel<1, 1><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh);
+#define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
+  {                                                                                                           \
+    const int grid = grid_for(n, kThreadsF, t->sm_count, occupancy_of(apply_kernel<VF_, OPT_, RU_>, kThreadsF)); \
+    apply_kernel<VF_, OPT_, RU_><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh); \
   }
+  if (opt == 0) {
+    if (vec4) { if (ru == 2) DET_LAUNCH_APPLY(4, 0, 2) else DET_LAUNCH_APPLY(4, 0, 1) }
+    else DET_LAUNCH_APPLY(1, 0, 1)
+  } else {
+    if (vec4) { if (ru == 2) DET_LAUNCH_APPLY(4, 1, 2) else DET_LAUNCH_APPLY(4, 1, 1) }
+    else DET_LAUNCH_APPLY(1, 1, 1)
+  }
+#undef DET_LAUNCH_APPLY
   CUDA_TRY(cudaGetLastError());
   note_mutation(t, n, s);
   return DET_OK;

@@ -251,6 +251,17 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
       t->cfg.max_capacity = t->view.capacity();
       g->pv.v[p] = t->view;
       g->bar.peer[p] = t->peer_bar;
+      if (t->cfg.device != local->cfg.device) {
+        // a shard on another GPU of the same process: plain peer access instead of CUDA IPC
+        CUDA_TRY(cudaSetDevice(local->cfg.device));
+        cudaError_t pe = cudaDeviceEnablePeerAccess(t->cfg.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+          det_peer_group_destroy(g);
+          return fail(DET_CUDA_ERROR, std::string("det_peer_group_create: no peer access to device ") +
+                                          std::to_string(t->cfg.device) + ": " + cudaGetErrorString(pe));
+        }
+        cudaGetLastError();
+      }
       continue;
     }
     if (!bl) {
