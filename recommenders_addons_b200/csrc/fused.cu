@@ -653,7 +653,7 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   if (batch == 0) return DET_OK;
   if (!out || !default_row || (nnz && (!ids || !segment_ids))) return fail(DET_INVALID_ARGUMENT, "det_lookup_sparse: null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   long long* seg_start = nullptr;
   long long* slots = nullptr;
   {
@@ -702,7 +702,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
     return fail(DET_INVALID_ARGUMENT, "det_apply: table was created with too few optimizer slot planes");
   if (n == 0) return DET_OK;
   if (!keys || !grads || !init_param) return fail(DET_INVALID_ARGUMENT, "det_apply: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   det_status st = ensure_room(t, (const long long*)keys, n, s);
   if (st != DET_OK) return st;
   const unsigned dim = (unsigned)t->cfg.dim;

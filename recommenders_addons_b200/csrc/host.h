@@ -49,6 +49,28 @@ inline int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Every entry point runs on its table's device and puts the caller's current device back on return: the
+// caller's framework (torch, TF) must never find its current CUDA context changed by a table call.
+struct DevGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    if (prev != dev) {
+      cudaSetDevice(dev);
+      changed = true;
+    }
+  }
+  ~DevGuard() {
+    if (changed && prev >= 0) cudaSetDevice(prev);
+  }
+  DevGuard(const DevGuard&) = delete;
+  DevGuard& operator=(const DevGuard&) = delete;
+};
+
 struct HostPipe;  // chunked H2D -> kernel -> D2H pipeline state (host_api.cu)
 
 size_t dtype_size(int dt);

@@ -97,7 +97,7 @@ det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_find_host: null table");
   if (n == 0) return DET_OK;
   if (!keys || !defaults || !values_out) return fail(DET_INVALID_ARGUMENT, "det_find_host: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   HostPipe* p;
   det_status st = pipe_get(t, &p);
   if (st != DET_OK) return st;
@@ -162,7 +162,7 @@ det_status det_insert_host(det_table* t, const int64_t* keys, const void* values
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert_host: null table");
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert_host: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   HostPipe* p;
   det_status st = pipe_get(t, &p);
   if (st != DET_OK) return st;
@@ -200,7 +200,7 @@ det_status det_insert_host(det_table* t, const int64_t* keys, const void* values
 
 det_status det_save(det_table* t, const char* prefix, size_t buffer_keys) {
   if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_save: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   int64_t n = 0;
   det_status st = det_size(t, &n, nullptr);
   if (st != DET_OK) return st;
@@ -247,7 +247,7 @@ det_status det_save(det_table* t, const char* prefix, size_t buffer_keys) {
 
 det_status det_load(det_table* t, const char* prefix, size_t buffer_keys) {
   if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_load: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
   FILE* fk = fopen(kf.c_str(), "rb");
   FILE* fv = fopen(vf.c_str(), "rb");

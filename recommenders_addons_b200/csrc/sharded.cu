@@ -183,7 +183,7 @@ size_t det_peer_handle_bytes(void) { return sizeof(PeerBlob); }
 
 det_status det_peer_export(det_table* t, void* blob_out) {
   if (!t || !blob_out) return fail(DET_INVALID_ARGUMENT, "det_peer_export: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   PeerBlob b;
   memset(&b, 0, sizeof(b));
   b.magic = kPeerMagic;
@@ -209,7 +209,7 @@ det_status det_peer_export(det_table* t, void* blob_out) {
 
 det_status det_peer_group_destroy(det_peer_group* g) {
   if (!g) return DET_OK;
-  cudaSetDevice(g->device);
+  det::DevGuard _dg(g->device);
   cudaDeviceSynchronize();
   for (int p = 0; p < kMaxPeers; ++p)
     for (int q = 0; q < 3 + kMaxPlanes; ++q)
@@ -225,7 +225,7 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
     return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: world must be in [1,8] and rank in [0,world)");
   det_table* local = tables[rank];
   if (!local) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: tables[rank] must be the local shard");
-  CUDA_TRY(cudaSetDevice(local->cfg.device));
+  det::DevGuard _dg(local->cfg.device);
   det_peer_group* g = new det_peer_group();
   memset(g->opened, 0, sizeof(g->opened));
   g->local = local;
@@ -245,6 +245,7 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
         return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: shards differ in row size / slot planes");
       }
       if (!t->peer_bar) {
+        det::DevGuard _d2(t->cfg.device);
         CUDA_TRY(cudaMalloc((void**)&t->peer_bar, kMaxPeers * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(t->peer_bar, 0, kMaxPeers * sizeof(unsigned long long)));
       }
@@ -253,7 +254,7 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
       g->bar.peer[p] = t->peer_bar;
       if (t->cfg.device != local->cfg.device) {
         // a shard on another GPU of the same process: plain peer access instead of CUDA IPC
-        CUDA_TRY(cudaSetDevice(local->cfg.device));
+        det::DevGuard _dg(local->cfg.device);
         cudaError_t pe = cudaDeviceEnablePeerAccess(t->cfg.device, 0);
         if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
           det_peer_group_destroy(g);
@@ -307,7 +308,7 @@ det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const
   if (n == 0) return DET_OK;
   if (!keys || !values_out || !defaults) return fail(DET_INVALID_ARGUMENT, "det_peer_find: null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(g->device));
+  det::DevGuard _dg(g->device);
   const int vec = pick_vec(g->row_bytes, defaults, values_out, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
   const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
@@ -331,7 +332,7 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_peer_insert: null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(g->device));
+  det::DevGuard _dg(g->device);
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
   const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
@@ -352,7 +353,7 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
 det_status det_peer_barrier(det_peer_group* g, det_stream_t stream) {
   if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_barrier: null group");
   if (g->n_remote == 0) return DET_OK;  // every shard lives in this process: stream order is the barrier
-  CUDA_TRY(cudaSetDevice(g->device));
+  det::DevGuard _dg(g->device);
   g->epoch += 1;
   // ~20 s at 2 GHz: a peer that never arrives must not hang the GPU
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->bar, g->pv.rank, g->pv.world, g->epoch, g->local->view.st,

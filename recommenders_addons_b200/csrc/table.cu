@@ -795,7 +795,7 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(DET_INVALID_ARGUMENT, "det_table_create: bad device ordinal");
-  CUDA_TRY(cudaSetDevice(cfg->device));
+  det::DevGuard _dg(cfg->device);
   det_table* t = new det_table();
   t->cfg = *cfg;
   t->row_bytes = es * (size_t)cfg->dim;
@@ -842,7 +842,7 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
 
 det_status det_table_destroy(det_table* t) {
   if (!t) return DET_OK;
-  cudaSetDevice(t->cfg.device);
+  det::DevGuard _dg(t->cfg.device);
   cudaDeviceSynchronize();
   for (int i = 0; i < 1 + kMaxPlanes; ++i)
     if (t->raw[i]) cudaFree(t->raw[i]);
@@ -863,7 +863,7 @@ det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* def
   if (n == 0) return DET_OK;
   if (!keys || !values_out || !defaults) return fail(DET_INVALID_ARGUMENT, "det_find: null keys/values/default_value");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   const int vec = pick_vec(t->row_bytes, defaults, values_out, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
   const TableView v = t->view;
@@ -899,7 +899,7 @@ det_status insert_impl(det_table* t, const int64_t* keys, const void* values, si
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert: null table");
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert: null keys/values");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   if (check_room) {
     det_status st = ensure_room(t, (const long long*)keys, n, s);
     if (st != DET_OK) return st;
@@ -934,7 +934,7 @@ det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const u
   if (n == 0) return DET_OK;
   if (!keys || !vod || !exists) return fail(DET_INVALID_ARGUMENT, "det_accum: null keys/values_or_deltas/exists");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   det_status st = ensure_room(t, (const long long*)keys, n, s);
   if (st != DET_OK) return st;
   const TableView v = t->view;
@@ -965,7 +965,7 @@ det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t 
   if (n == 0) return DET_OK;
   if (!keys) return fail(DET_INVALID_ARGUMENT, "det_remove: null keys");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   remove_kernel<<<grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s>>>(t->view, (const long long*)keys, n);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
@@ -973,13 +973,13 @@ det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t 
 
 det_status det_clear(det_table* t, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_clear: null table");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   return table_clear_async(t, (cudaStream_t)stream);
 }
 
 det_status det_size(det_table* t, int64_t* size_out_host, det_stream_t stream) {
   if (!t || !size_out_host) return fail(DET_INVALID_ARGUMENT, "det_size: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   DevState ds;
   det_status st = read_state(t, (cudaStream_t)stream, &ds);
   if (st != DET_OK) return st;
@@ -996,7 +996,7 @@ det_status det_capacity(det_table* t, uint64_t* out) {
 
 det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_reserve: null table");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   const uint64_t limit = (uint64_t)((double)t->view.capacity() * t->max_lf);
   if (total_keys <= limit) return DET_OK;
   uint64_t nb = (uint64_t)((double)total_keys / t->max_lf / kBucket) + 1;
@@ -1018,7 +1018,7 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
   if (!t || !n_out_host) return fail(DET_INVALID_ARGUMENT, "det_export: null argument");
   if (plane < 0 || plane > t->cfg.num_slot_planes) return fail(DET_INVALID_ARGUMENT, "det_export: bad plane");
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   const TableView v = t->view;
   const size_t cap = v.capacity();
   const size_t n_tiles = (cap + kExportTile - 1) / kExportTile;
@@ -1063,7 +1063,7 @@ det_status det_import(det_table* t, const int64_t* keys, const void* values, siz
 
 det_status det_get_stats(det_table* t, det_stats* out, det_stream_t stream) {
   if (!t || !out) return fail(DET_INVALID_ARGUMENT, "det_get_stats: null argument");
-  CUDA_TRY(cudaSetDevice(t->cfg.device));
+  det::DevGuard _dg(t->cfg.device);
   DevState ds;
   det_status st = read_state(t, (cudaStream_t)stream, &ds);
   if (st != DET_OK) return st;
