@@ -268,9 +268,25 @@ def gpu_arm(args):
 
   gen = torch.Generator(device=dev).manual_seed(42 + rank)
   gen_v = torch.Generator(device=dev).manual_seed(43 + rank)
-  var = de.Variable(dim=dim, init_size=2 * resident, initializer=0.0, name="bench_table",
-                    kv_creator=de.HkvHashTableCreator(de.HkvHashTableConfig(init_capacity=2 * resident,
-                                                                             max_capacity=2 * resident)))
+  sharded, exchange = None, "none"
+  if world > 1:
+    exchange = args.exchange
+    if exchange == "peer":
+      try:
+        # the shard lives in a symmetric-memory region that every rank maps (CUDA VMM, 2 MB pages)
+        sharded = de.PeerShardedVariable.create(dim, 2 * resident, initializer=0.0, name="bench_table")
+      except Exception as ex:  # no symmetric memory in this sandbox: NCCL exchange instead, and say so
+        print("symmetric-memory peer group failed (%r): falling back to NCCL all-to-all" % (ex,), file=sys.stderr)
+        exchange = "nccl"
+  if sharded is not None:
+    var = sharded.local
+  else:
+    var = de.Variable(dim=dim, init_size=2 * resident, initializer=0.0, name="bench_table",
+                      kv_creator=de.HkvHashTableCreator(de.HkvHashTableConfig(init_capacity=2 * resident,
+                                                                               max_capacity=2 * resident)))
+  if world > 1 and exchange == "nccl":
+    sharded = de.ShardedVariable(var)
+  is_peer = exchange == "peer"
   table = var.tables[0]
   # ---- prefill this rank's shard: all ranks r of the vocabulary with owner(key(r)) == rank --------------
   chunk = 1 << 20
@@ -289,19 +305,6 @@ def gpu_arm(args):
   new_vals = torch.randn(B, dim, device=dev, generator=gen_v) * 0.01
   default = torch.zeros(dim, device=dev)
   out = torch.empty(B, dim, device=dev)
-  sharded, exchange = None, "none"
-  if world > 1:
-    exchange = args.exchange
-    if exchange == "peer":
-      try:
-        sharded = de.PeerShardedVariable(var)
-      except Exception as ex:  # CUDA IPC not available in this sandbox: fall back to the NCCL exchange, say so
-        print("peer-memory group failed (%r): falling back to NCCL all-to-all" % (ex,), file=sys.stderr)
-        exchange = "nccl"
-    if exchange == "nccl":
-      sharded = de.ShardedVariable(var)
-  is_peer = exchange == "peer"
-
   def step(i, ev=None):
     k = key_batches[i % n_batches]
     if sharded is None:

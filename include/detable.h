@@ -80,6 +80,10 @@ typedef struct det_config {
 /* ---- lifetime: HashTableOp::Compute / LookupOrCreate, kernels/cuckoo_hashtable_op.h:59-110 ---- */
 det_status det_table_create(det_table** out, const det_config* cfg);
 det_status det_table_destroy(det_table* t);
+/* A table inside caller-provided device memory (fixed capacity = cfg->init_capacity slots, never grows, memory not
+ * freed by destroy): lets the planes live in memory that peers map, see det_peer_group_create_regions. */
+size_t det_table_region_bytes(const det_config* cfg);
+det_status det_table_create_in_region(det_table** out, const det_config* cfg, void* region, size_t region_bytes);
 const char* det_last_error(void);
 /* library/ABI probe used by the loaders */
 int det_abi_version(void);
@@ -203,6 +207,11 @@ det_status det_peer_export(det_table* t, void* handle_out_host);
 det_status det_peer_group_create(det_peer_group** out, det_table* const* tables, const void* handles_host,
                                  int world, int rank, int gpu_mode);
 det_status det_peer_group_destroy(det_peer_group* g);
+/* Same group over SYMMETRIC-MEMORY regions (preferred: CUDA VMM mappings keep 2 MB pages; legacy CUDA-IPC imports
+ * make random access over a 50 GB shard TLB-bound).  Every rank builds its shard with det_table_create_in_region
+ * in a region all peers have mapped; region_ptrs[p] = where THIS process sees rank p's region. */
+det_status det_peer_group_create_regions(det_peer_group** out, det_table* local, const void* const* region_ptrs,
+                                         int world, int rank, int gpu_mode);
 det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
                          int full_size_default, void* values_out, uint8_t* exists, det_stream_t stream);
 det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,

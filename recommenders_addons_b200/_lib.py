@@ -60,6 +60,9 @@ SIGNATURES = {
     "det_peer_export": (_i, [_vp, _vp]),
     "det_peer_group_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _i, _i, _i]),
     "det_peer_group_destroy": (_i, [_vp]),
+    "det_peer_group_create_regions": (_i, [ctypes.POINTER(_vp), _vp, ctypes.POINTER(_vp), _i, _i, _i]),
+    "det_table_region_bytes": (_sz, [ctypes.POINTER(DetConfig)]),
+    "det_table_create_in_region": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(DetConfig), _vp, _sz]),
     "det_peer_find": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "det_peer_insert": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_peer_barrier": (_i, [_vp, _vp]),

@@ -98,10 +98,16 @@ struct det_table {
   det::HostPipe* pipe = nullptr;
   void* scratch = nullptr;           // per-table device scratch reused by det_lookup_sparse / det_export
   size_t scratch_bytes = 0;
+  bool external = false;             // planes live in a caller-provided region (not owned, fixed capacity)
   unsigned long long* peer_bar = nullptr;  // arrival flags of the NVLink peer barrier (sharded.cu)
 };
 
 namespace det {
+struct RegionLayout {
+  uint64_t nb;
+  size_t off_state, off_bar, off_keys, off_plane[kMaxPlanes], bytes;
+};
+void region_layout(const det_config& cfg, RegionLayout* L);
 struct SlotInit;
 det_status ensure_room(det_table* t, const long long* keys_or_null, size_t n, cudaStream_t s);
 void note_mutation(det_table* t, size_t n, cudaStream_t s);

@@ -302,6 +302,51 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
   return DET_OK;
 }
 
+// Group over symmetric-memory regions: every rank created its shard with det_table_create_in_region inside a
+// region that all peers have mapped (e.g. torch.distributed._symmetric_memory: CUDA VMM, 2 MB pages -- unlike
+// legacy CUDA-IPC imports, whose small-page mappings make random access over a 50 GB table TLB-bound).
+// region_ptrs[p] = address at which THIS process sees rank p's region; all shards share `cfg` (same layout).
+det_status det_peer_group_create_regions(det_peer_group** out, det_table* local, const void* const* region_ptrs,
+                                         int world, int rank, int gpu_mode) {
+  if (!out || !local || !region_ptrs) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: null argument");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: world must be in [1,8] and rank in [0,world)");
+  if (!local->external) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: the local shard must live in a region");
+  det::DevGuard _dg(local->cfg.device);
+  det_peer_group* g = new det_peer_group();
+  memset(g->opened, 0, sizeof(g->opened));
+  g->local = local;
+  g->device = local->cfg.device;
+  g->sm_count = local->sm_count;
+  g->n_slot_planes = local->cfg.num_slot_planes;
+  g->row_bytes = local->row_bytes;
+  g->pv.world = world;
+  g->pv.rank = rank;
+  g->pv.gpu_mode = gpu_mode;
+  g->n_remote = world - 1;
+  det_config c = local->cfg;
+  c.init_capacity = local->view.capacity();
+  RegionLayout L;
+  region_layout(c, &L);
+  for (int p = 0; p < world; ++p) {
+    unsigned char* base = (unsigned char*)region_ptrs[p];
+    if (!base) {
+      delete g;
+      return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: null region pointer");
+    }
+    TableView& v = g->pv.v[p];
+    v.st = (DevState*)(base + L.off_state);
+    v.keys = (long long*)(base + L.off_keys);
+    for (int q = 0; q < kMaxPlanes; ++q) v.planes[q] = base + L.off_plane[q];
+    v.nb = L.nb;
+    v.row_bytes = (unsigned)local->row_bytes;
+    v.dim = (unsigned)local->cfg.dim;
+    g->bar.peer[p] = (unsigned long long*)(base + L.off_bar);
+  }
+  *out = g;
+  return DET_OK;
+}
+
 det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
                          int full_size_default, void* values_out, uint8_t* exists, det_stream_t stream) {
   if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_find: null group");
@@ -311,7 +356,7 @@ det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const
   det::DevGuard _dg(g->device);
   const int vec = pick_vec(g->row_bytes, defaults, values_out, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
-  const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+  const int grid = grid_for(n, kThreadsP, g->sm_count, occupancy_of(peer_find_kernel<16>, kThreadsP));
   const unsigned char* d = (const unsigned char*)defaults;
   unsigned char* o = (unsigned char*)values_out;
   const long long* k = (const long long*)keys;
@@ -335,7 +380,7 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
   det::DevGuard _dg(g->device);
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
-  const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+  const int grid = grid_for(n, kThreadsP, g->sm_count, occupancy_of(peer_insert_kernel<16>, kThreadsP));
   const unsigned char* v = (const unsigned char*)values;
   const long long* k = (const long long*)keys;
   const int np = g->n_slot_planes;

@@ -605,6 +605,7 @@ static det_status read_state(det_table* t, cudaStream_t s, DevState* out) {
 }
 
 static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
+  if (t->external) return fail(DET_TABLE_FULL, "detable: a table living in a caller-provided region cannot grow");
   TableView nv;
   void* raw[1 + kMaxPlanes];
   det_status st = alloc_planes(t, new_nb, &nv, raw);
@@ -783,7 +784,37 @@ const char* det_build_info(void) {
 
 const char* det_last_error(void) { return g_last_error.c_str(); }
 
-det_status det_table_create(det_table** out, const det_config* cfg) {
+}  // extern "C"
+
+namespace det {
+
+static size_t align256u(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Fixed layout of a table inside ONE caller-provided region (every peer of a sharded group uses the same
+// layout, so a peer's planes are found at the same offsets from its region base):
+//   [DevState 256 B][peer barrier flags 256 B][keys][values (+2 rows)][slot planes ...], each 256 B aligned
+void region_layout(const det_config& cfg, RegionLayout* L) {
+  const size_t es = dtype_size(cfg.value_dtype);
+  const uint64_t init = cfg.init_capacity ? cfg.init_capacity : 8192;
+  L->nb = (init + kBucket - 1) / kBucket;
+  const size_t cap = L->nb * kBucket;
+  size_t off = 0;
+  L->off_state = off;
+  off += 256;
+  L->off_bar = off;
+  off += 256;
+  L->off_keys = off;
+  off += align256u(cap * sizeof(long long));
+  L->off_plane[0] = off;
+  off += align256u((cap + 2) * es * (size_t)cfg.dim);
+  for (int p = 1; p < kMaxPlanes; ++p) {
+    L->off_plane[p] = off;
+    if (p <= cfg.num_slot_planes) off += align256u((cap + 2) * (size_t)cfg.dim * 4u);
+  }
+  L->bytes = off;
+}
+
+static det_status create_common(det_table** out, const det_config* cfg, void* region, size_t region_bytes) {
   if (!out || !cfg) return fail(DET_INVALID_ARGUMENT, "det_table_create: null argument");
   const size_t es = dtype_size(cfg->value_dtype);
   if (es == 0) return fail(DET_INVALID_ARGUMENT, "det_table_create: unsupported value_dtype");
@@ -803,8 +834,8 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
   if (t->max_lf > 0.9f) t->max_lf = 0.9f;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
-  // Probes read one 64 B bucket and nothing near it: ask L2 not to fetch 128 B per miss (ncu: dram read was
-  // keys + rows + 128 B per probe with the default granularity).  DET_L2_FETCH=0 leaves the device default.
+  // Probes read one 64 B bucket and nothing near it: ask L2 not to fetch more than that per miss.
+  // DET_L2_FETCH=0 leaves the device default (measured effect on B200: ~1 %).
   {
     const int fetch = env_int("DET_L2_FETCH", 64);
     if (fetch > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
@@ -815,22 +846,47 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
   const uint64_t nb = (init + kBucket - 1) / kBucket;
   for (int i = 0; i < 1 + kMaxPlanes; ++i) t->raw[i] = nullptr;
   for (int p = 0; p < kMaxPlanes; ++p) t->slot_init[p] = 0.f;
-  cudaError_t e = cudaMalloc((void**)&t->view.st, sizeof(DevState));
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&t->h_state, sizeof(DevState));
+  cudaError_t e = cudaMallocHost((void**)&t->h_state, sizeof(DevState));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&t->h_used_snap, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->snap_ev, cudaEventDisableTiming);
+  if (e == cudaSuccess && region == nullptr) e = cudaMalloc((void**)&t->view.st, sizeof(DevState));
   if (e != cudaSuccess) {
     delete t;
     return fail(DET_OUT_OF_MEMORY, std::string("det_table_create: ") + cudaGetErrorString(e));
   }
-  det_status st = alloc_planes(t, nb, &t->view, t->raw);
-  if (st != DET_OK) {
-    cudaFree(t->view.st);
-    cudaFreeHost(t->h_state);
-    delete t;
-    return st;
+  det_status st = DET_OK;
+  if (region == nullptr) {
+    st = alloc_planes(t, nb, &t->view, t->raw);
+    if (st != DET_OK) {
+      cudaFree(t->view.st);
+      cudaFreeHost(t->h_state);
+      delete t;
+      return st;
+    }
+  } else {
+    RegionLayout L;
+    det_config c2 = *cfg;
+    c2.init_capacity = init;
+    region_layout(c2, &L);
+    if (((uintptr_t)region & 255u) != 0 || region_bytes < L.bytes) {
+      cudaFreeHost(t->h_state);
+      delete t;
+      return fail(DET_INVALID_ARGUMENT, "det_table_create_in_region: region must be 256 B aligned and hold " +
+                                            std::to_string(L.bytes) + " bytes");
+    }
+    unsigned char* base = (unsigned char*)region;
+    t->external = true;
+    t->cfg.max_capacity = L.nb * kBucket;  // planes owned by the caller: the table cannot grow
+    t->view.st = (DevState*)(base + L.off_state);
+    t->peer_bar = (unsigned long long*)(base + L.off_bar);
+    t->view.keys = (long long*)(base + L.off_keys);
+    for (int p = 0; p < kMaxPlanes; ++p) t->view.planes[p] = base + L.off_plane[p];
+    t->view.nb = L.nb;
+    t->view.row_bytes = (unsigned)t->row_bytes;
+    t->view.dim = (unsigned)cfg->dim;
+    if (cudaMemset(base + L.off_bar, 0, 256) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_table_create_in_region: memset failed");
   }
-  st = table_clear_async(t, 0);
+  if (st == DET_OK) st = table_clear_async(t, 0);
   if (st == DET_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_table_create: init failed");
   if (st != DET_OK) {
     det_table_destroy(t);
@@ -840,17 +896,37 @@ det_status det_table_create(det_table** out, const det_config* cfg) {
   return DET_OK;
 }
 
+}  // namespace det
+
+extern "C" {
+
+det_status det_table_create(det_table** out, const det_config* cfg) { return det::create_common(out, cfg, nullptr, 0); }
+
+size_t det_table_region_bytes(const det_config* cfg) {
+  if (!cfg || dtype_size(cfg->value_dtype) == 0 || cfg->dim <= 0) return 0;
+  RegionLayout L;
+  region_layout(*cfg, &L);
+  return L.bytes;
+}
+
+det_status det_table_create_in_region(det_table** out, const det_config* cfg, void* region, size_t region_bytes) {
+  if (!region) return fail(DET_INVALID_ARGUMENT, "det_table_create_in_region: null region");
+  return det::create_common(out, cfg, region, region_bytes);
+}
+
 det_status det_table_destroy(det_table* t) {
   if (!t) return DET_OK;
   det::DevGuard _dg(t->cfg.device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 1 + kMaxPlanes; ++i)
-    if (t->raw[i]) cudaFree(t->raw[i]);
-  if (t->view.st) cudaFree(t->view.st);
+  if (!t->external) {
+    for (int i = 0; i < 1 + kMaxPlanes; ++i)
+      if (t->raw[i]) cudaFree(t->raw[i]);
+    if (t->view.st) cudaFree(t->view.st);
+    if (t->peer_bar) cudaFree(t->peer_bar);
+  }
   if (t->h_state) cudaFreeHost(t->h_state);
   if (t->h_used_snap) cudaFreeHost(t->h_used_snap);
   if (t->snap_ev) cudaEventDestroy(t->snap_ev);
-  if (t->peer_bar) cudaFree(t->peer_bar);
   if (t->scratch) cudaFree(t->scratch);
   host_pipe_free(t);
   delete t;

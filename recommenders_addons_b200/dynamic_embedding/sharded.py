@@ -97,11 +97,66 @@ class PeerShardedVariable(object):
   lookup()/upsert() are stream-ordered on the current stream; phase_barrier() separates a phase in which ranks
   read from a phase in which ranks write (the ordering the reference gets from its collectives)."""
 
+  @classmethod
+  def create(cls, dim, capacity, group=None, value_dtype=torch.float32, initializer=None, num_slot_planes=0,
+             name="PeerShardedVariable", gpu_mode=True):
+    """Preferred constructor: the local shard (fixed `capacity` slots) is built inside a torch symmetric-memory
+    region (CUDA VMM, mapped by every rank with 2 MB pages); peers are addressed through the rendezvous
+    handle's buffer pointers.  Collective over `group`."""
+    import torch.distributed._symmetric_memory as symm_mem
+    from .table import CuckooHashTable
+    from .variable import Variable
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nbytes = CuckooHashTable.region_bytes(value_dtype, dim, capacity, num_slot_planes, dev.index)
+    region = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+    hdl = symm_mem.rendezvous(region, group if group is not None else dist.group.WORLD)
+
+    from .table import KVCreator
+
+    class _RegionCreator(KVCreator):
+      """builds the (single) shard table inside the symmetric region"""
+
+      def create(self, key_dtype=None, value_dtype=None, default_value=None, name=None, checkpoint=None,
+                 init_size=None, config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
+        return CuckooHashTable(key_dtype, value_dtype, default_value, name=name, init_size=capacity, device=device,
+                               num_slot_planes=num_slot_planes, region=region)
+
+    creator = _RegionCreator()
+    var = Variable(dim=dim, value_dtype=value_dtype, init_size=capacity, initializer=initializer, name=name,
+                   kv_creator=creator, num_slot_planes=num_slot_planes, devices=[dev])
+    self = cls.__new__(cls)
+    self._init_common(var, group, gpu_mode)
+    import ctypes
+    ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+    g = ctypes.c_void_p()
+    self._libmod.check(self._lib.det_peer_group_create_regions(ctypes.byref(g), var.tables[0].handle, ptrs, self.world,
+                                                               self.rank, 1 if gpu_mode else 0))
+    self._g = g
+    self._symm = (region, hdl)
+    self._tables = [None] * self.world
+    self._tables[self.rank] = var.tables[0]
+    self.backing = "symmetric-memory"
+    return self
+
+  def _init_common(self, local_variable, group, gpu_mode):
+    from .. import _lib
+    self._lib = _lib.lib()
+    self._libmod = _lib
+    self.local = local_variable
+    self.world = dist.get_world_size(group)
+    self.rank = dist.get_rank(group)
+    self.dim = local_variable.dim
+    self.device = local_variable.tables[0].device
+    self.value_dtype = local_variable.value_dtype
+    self._group = group
+    self._default = local_variable.tables[0]._default_value
+
   def __init__(self, local_variable=None, group=None, fake_shards=None, gpu_mode=True):
     import ctypes
     from .. import _lib
     self._lib = _lib.lib()
     self._libmod = _lib
+    self.backing = "cuda-ipc" if fake_shards is None else "same-process"
     if fake_shards is not None:
       self.world, self.rank = len(fake_shards), 0
       tables = [v.tables[0] for v in fake_shards]

@@ -69,7 +69,7 @@ class CuckooHashTable(object):
 
   def __init__(self, key_dtype, value_dtype, default_value, name="CuckooHashTable", checkpoint=True, init_size=0,
                config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0, max_capacity=0,
-               max_load_factor=0.0):
+               max_load_factor=0.0, region=None):
     if key_dtype != torch.int64:
       raise TypeError("key dtype %s is not supported on GPU: keys must be int64" % (key_dtype,))
     if value_dtype not in _TORCH_TO_NAME:
@@ -102,8 +102,21 @@ class CuckooHashTable(object):
     cfg.flags = 0
     self._lib = _lib.lib()
     h = ctypes.c_void_p()
-    _lib.check(self._lib.det_table_create(ctypes.byref(h), ctypes.byref(cfg)))
+    self._region = region  # keeps the caller-provided memory alive (e.g. a symmetric-memory tensor)
+    if region is None:
+      _lib.check(self._lib.det_table_create(ctypes.byref(h), ctypes.byref(cfg)))
+    else:
+      _lib.check(self._lib.det_table_create_in_region(ctypes.byref(h), ctypes.byref(cfg),
+                                                      ctypes.c_void_p(region.data_ptr()), region.numel()))
     self._h = h
+
+  @staticmethod
+  def region_bytes(value_dtype, dim, capacity, num_slot_planes=0, device_index=0):
+    """Bytes of device memory a fixed-capacity table of `capacity` slots needs (det_table_region_bytes)."""
+    cfg = _lib.DetConfig()
+    cfg.value_dtype = _lib.DTYPE_CODES[_TORCH_TO_NAME[value_dtype]]
+    cfg.dim, cfg.device, cfg.num_slot_planes, cfg.init_capacity = int(dim), int(device_index), int(num_slot_planes), int(capacity)
+    return int(_lib.lib().det_table_region_bytes(ctypes.byref(cfg)))
 
   # -- properties of LookupInterface ---------------------------------------------------------
   @property

@@ -23,16 +23,20 @@ def _worker(rank, world, port, q):
   ok = True
   msg = ""
   try:
-    for mode in ("nccl", "peer"):
-      var = de.Variable(dim=dim, init_size=1 << 18, initializer=-1.0, name="mg-%s-%d" % (mode, rank))
-      sv = de.ShardedVariable(var) if mode == "nccl" else de.PeerShardedVariable(var)
+    for mode in ("nccl", "peer", "symm"):
+      if mode == "symm":  # shard inside a torch symmetric-memory region (CUDA VMM): the production path
+        sv = de.PeerShardedVariable.create(dim, 1 << 18, initializer=-1.0, name="mg-symm-%d" % rank)
+        var = sv.local
+      else:
+        var = de.Variable(dim=dim, init_size=1 << 18, initializer=-1.0, name="mg-%s-%d" % (mode, rank))
+        sv = de.ShardedVariable(var) if mode == "nccl" else de.PeerShardedVariable(var)
       # every rank writes its own disjoint key set (owned by arbitrary ranks) ...
       rng = np.random.default_rng(1234)
       allkeys = rng.choice(np.arange(-10**6, 10**6), 60000, replace=False).astype(np.int64)
       allvals = rng.normal(0, 0.01, (allkeys.shape[0], dim)).astype(np.float32)
       mine = slice(rank, None, world)
       sv.upsert(torch.from_numpy(allkeys[mine]).to(dev), torch.from_numpy(allvals[mine]).to(dev))
-      if mode == "peer":
+      if mode != "nccl":
         sv.phase_barrier()
       torch.cuda.synchronize()
       dist.barrier()
@@ -49,7 +53,7 @@ def _worker(rank, world, port, q):
       owner = O.default_partition_fn(allkeys, world, True)
       if own != int((owner == rank).sum()):
         ok, msg = False, "shard size %d != %d in mode %s" % (own, int((owner == rank).sum()), mode)
-      if mode == "peer":
+      if mode != "nccl":
         sv.phase_barrier()
         torch.cuda.synchronize()
       dist.barrier()
