@@ -67,3 +67,28 @@ def test_published_table_cannot_grow():
   with pytest.raises(DetError, match="max_capacity"):
     shards[0].upsert(torch.arange(0, 4000, 2, device="cuda"), torch.zeros(2000, 4, device="cuda"))
   pv.close()
+
+
+def test_table_in_caller_provided_region():
+  """det_table_create_in_region: the planes live in memory the caller owns (the symmetric-memory region of the
+  multi-GPU path); behaviour is identical to an owned table but the capacity is fixed."""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  from recommenders_addons_b200._lib import DetError
+  from tests.helpers import golden_files, replay_golden, GpuTableNp
+  g = np.load([p for p in golden_files() if p.endswith("dim16.npz")][0])
+  dim, cap = 16, 1 << 14
+  nbytes = de.CuckooHashTable.region_bytes(torch.float32, dim, cap, 1, 0)
+  assert nbytes >= cap * (8 + 2 * dim * 4)
+  region = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+  t = GpuTableNp.__new__(GpuTableNp)
+  t.torch, t.dim, t.dtype = torch, dim, torch.float32
+  t.t = de.CuckooHashTable(torch.int64, torch.float32, [0.0] * dim, init_size=cap, num_slot_planes=1, region=region)
+  t.dev = t.t.device
+  replay_golden(t, g)
+  assert t.t.capacity() == cap
+  with pytest.raises(DetError, match="max_capacity|cannot grow"):
+    t.t.insert(torch.arange(10**6, 10**6 + 20000), torch.zeros(20000, dim))
+  with pytest.raises(DetError, match="region"):
+    de.CuckooHashTable(torch.int64, torch.float32, [0.0] * dim, init_size=cap, region=region[: nbytes // 2])
+  t.t.close()
