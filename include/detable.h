@@ -174,6 +174,13 @@ det_status det_apply_adam(det_table* t, const int64_t* keys, const float* grads,
 det_status det_find_host(det_table* t, const int64_t* keys_host, size_t n, const void* defaults_host,
                          int full_size_default, void* values_out_host, uint8_t* exists_host);
 det_status det_insert_host(det_table* t, const int64_t* keys_host, const void* values_host, size_t n);
+/* Asynchronous flavours (PINNED host buffers only): return once everything is enqueued on the table's internal
+ * streams; det_host_sync() waits.  Find and insert use separate streams, so a lookup of batch i+1 (D2H-heavy)
+ * overlaps the write-back of batch i (H2D-heavy) on a full-duplex PCIe link -- input prefetch as tf.data does. */
+det_status det_find_host_async(det_table* t, const int64_t* keys_host, size_t n, const void* defaults_host,
+                               int full_size_default, void* values_out_host, uint8_t* exists_host);
+det_status det_insert_host_async(det_table* t, const int64_t* keys_host, const void* values_host, size_t n);
+det_status det_host_sync(det_table* t);
 
 /* ---- key-hash sharding across GPUs (python/ops/dynamic_embedding_variable.py:165-197 default_partition_fn,
  * python/ops/shadow_embedding_ops.py:397-447 alltoall exchange) ----

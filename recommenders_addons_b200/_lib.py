@@ -52,6 +52,9 @@ SIGNATURES = {
                             _vp, _i, _vp]),
     "det_find_host": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "det_insert_host": (_i, [_vp, _vp, _vp, _sz]),
+    "det_find_host_async": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "det_insert_host_async": (_i, [_vp, _vp, _vp, _sz]),
+    "det_host_sync": (_i, [_vp]),
     "det_partition_workspace_bytes": (_sz, [_sz, _i]),
     "det_partition": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "det_scatter_rows": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),

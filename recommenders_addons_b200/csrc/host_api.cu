@@ -31,9 +31,10 @@ struct HostPipe {
   unsigned char* h_exists[kPipeStreams];
 };
 
-static det_status pipe_get(det_table* t, HostPipe** out) {
-  if (t->pipe) {
-    *out = t->pipe;
+static det_status pipe_get(det_table* t, int which, HostPipe** out) {
+  HostPipe*& slot = which == 0 ? t->pipe : t->pipe2;
+  if (slot) {
+    *out = slot;
     return DET_OK;
   }
   HostPipe* p = new HostPipe();
@@ -53,13 +54,12 @@ static det_status pipe_get(det_table* t, HostPipe** out) {
     CUDA_TRY(cudaMallocHost((void**)&p->h_vals[i], ck * t->row_bytes));
     CUDA_TRY(cudaMallocHost((void**)&p->h_exists[i], ck));
   }
-  t->pipe = p;
+  slot = p;
   *out = p;
   return DET_OK;
 }
 
-void host_pipe_free(det_table* t) {
-  HostPipe* p = t->pipe;
+static void host_pipe_free_one(HostPipe* p) {
   if (!p) return;
   for (int i = 0; i < kPipeStreams; ++i) {
     if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
@@ -73,7 +73,13 @@ void host_pipe_free(det_table* t) {
     cudaFreeHost(p->h_exists[i]);
   }
   delete p;
+}
+
+void host_pipe_free(det_table* t) {
+  host_pipe_free_one(t->pipe);
+  host_pipe_free_one(t->pipe2);
   t->pipe = nullptr;
+  t->pipe2 = nullptr;
 }
 
 static bool is_pinned(const void* p) {
@@ -92,18 +98,21 @@ using namespace det;
 
 extern "C" {
 
-det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void* defaults, int full_default,
-                         void* values_out, uint8_t* exists) {
+static det_status find_host_impl(det_table* t, const int64_t* keys, size_t n, const void* defaults, int full_default,
+                                 void* values_out, uint8_t* exists, bool wait) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_find_host: null table");
   if (n == 0) return DET_OK;
   if (!keys || !defaults || !values_out) return fail(DET_INVALID_ARGUMENT, "det_find_host: null argument");
   det::DevGuard _dg(t->cfg.device);
   HostPipe* p;
-  det_status st = pipe_get(t, &p);
+  det_status st = pipe_get(t, 0, &p);
   if (st != DET_OK) return st;
   const size_t rb = t->row_bytes, ck = p->chunk_keys;
   const bool pin_k = is_pinned(keys), pin_v = is_pinned(values_out), pin_e = is_pinned(exists),
              pin_d = is_pinned(defaults);
+  const bool all_pinned = pin_k && pin_v && pin_e && pin_d;
+  if (!wait && !all_pinned)
+    return fail(DET_INVALID_ARGUMENT, "det_find_host_async: all host buffers must be pinned (page-locked)");
   const unsigned char* defs = (const unsigned char*)defaults;
   unsigned char* vout = (unsigned char*)values_out;
   // broadcast default row: upload once per stream
@@ -115,8 +124,9 @@ det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void
     const int i = (int)(c % kPipeStreams);
     const size_t m = (n - off < ck) ? n - off : ck;
     cudaStream_t s = p->streams[i];
-    if (c >= (size_t)kPipeStreams) {
+    if (c >= (size_t)kPipeStreams && !all_pinned) {
       // the bounce buffers of this stream are free again once its previous chunk has drained
+      // (with pinned user buffers nothing is bounced and stream order alone protects the device scratch)
       CUDA_TRY(cudaEventSynchronize(p->done[i]));
       if (!pin_v || !pin_e) {
         const size_t poff = off - ck * kPipeStreams;
@@ -145,6 +155,7 @@ det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void
                                cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaEventRecord(p->done[i], s));
   }
+  if (!wait) return DET_OK;  // det_host_sync() drains
   // drain: last up-to-3 chunks
   const size_t nchunks = c;
   for (size_t q = (nchunks > (size_t)kPipeStreams ? nchunks - kPipeStreams : 0); q < nchunks; ++q) {
@@ -158,16 +169,28 @@ det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void
   return DET_OK;
 }
 
-det_status det_insert_host(det_table* t, const int64_t* keys, const void* values, size_t n) {
+det_status det_find_host(det_table* t, const int64_t* keys, size_t n, const void* defaults, int full_default,
+                         void* values_out, uint8_t* exists) {
+  return find_host_impl(t, keys, n, defaults, full_default, values_out, exists, true);
+}
+
+det_status det_find_host_async(det_table* t, const int64_t* keys, size_t n, const void* defaults, int full_default,
+                               void* values_out, uint8_t* exists) {
+  return find_host_impl(t, keys, n, defaults, full_default, values_out, exists, false);
+}
+
+static det_status insert_host_impl(det_table* t, const int64_t* keys, const void* values, size_t n, bool wait) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert_host: null table");
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert_host: null argument");
   det::DevGuard _dg(t->cfg.device);
   HostPipe* p;
-  det_status st = pipe_get(t, &p);
+  det_status st = pipe_get(t, 1, &p);
   if (st != DET_OK) return st;
   const size_t rb = t->row_bytes, ck = p->chunk_keys;
   const bool pin_k = is_pinned(keys), pin_v = is_pinned(values);
+  if (!wait && !(pin_k && pin_v))
+    return fail(DET_INVALID_ARGUMENT, "det_insert_host_async: all host buffers must be pinned (page-locked)");
   // growth (if any) must happen before the chunks are in flight on several streams
   st = ensure_room(t, nullptr, n, p->streams[0]);
   if (st != DET_OK) return st;
@@ -177,7 +200,7 @@ det_status det_insert_host(det_table* t, const int64_t* keys, const void* values
     const int i = (int)(c % kPipeStreams);
     const size_t m = (n - off < ck) ? n - off : ck;
     cudaStream_t s = p->streams[i];
-    if (c >= (size_t)kPipeStreams) CUDA_TRY(cudaEventSynchronize(p->done[i]));
+    if (c >= (size_t)kPipeStreams && !(pin_k && pin_v)) CUDA_TRY(cudaEventSynchronize(p->done[i]));
     const long long* hk = (const long long*)keys + off;
     const unsigned char* hv = (const unsigned char*)values + off * rb;
     if (!pin_k) {
@@ -194,7 +217,25 @@ det_status det_insert_host(det_table* t, const int64_t* keys, const void* values
     if (st != DET_OK) return st;
     CUDA_TRY(cudaEventRecord(p->done[i], s));
   }
+  if (!wait) return DET_OK;
   for (int i = 0; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+  return DET_OK;
+}
+
+det_status det_insert_host(det_table* t, const int64_t* keys, const void* values, size_t n) {
+  return insert_host_impl(t, keys, values, n, true);
+}
+
+det_status det_insert_host_async(det_table* t, const int64_t* keys, const void* values, size_t n) {
+  return insert_host_impl(t, keys, values, n, false);
+}
+
+det_status det_host_sync(det_table* t) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_host_sync: null table");
+  det::DevGuard _dg(t->cfg.device);
+  for (HostPipe* p : {t->pipe, t->pipe2})
+    if (p)
+      for (int i = 0; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
   return DET_OK;
 }
 

@@ -630,7 +630,8 @@ static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
   }
   rehash_fix_state_kernel<<<1, 1, 0, s>>>(t->view.st);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s));
+  // the old planes are freed below: nothing on ANY stream may still be reading them (async host pipelines)
+  CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 1 + kMaxPlanes; ++i)
     if (t->raw[i]) cudaFree(t->raw[i]);
   for (int i = 0; i < 1 + kMaxPlanes; ++i) t->raw[i] = raw[i];

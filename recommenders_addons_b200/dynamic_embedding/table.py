@@ -257,6 +257,19 @@ class CuckooHashTable(object):
     torch.cuda.current_stream(self._device).synchronize()
     _lib.check(self._lib.det_insert_host(self._h, _ptr(keys_host), _ptr(values_host), keys_host.numel()))
 
+  def lookup_host_async(self, keys_host, default_host, values_out_host, exists_out_host=None):
+    """enqueue only (pinned tensors); host_sync() waits.  The caller orders it against its own stream work."""
+    n = keys_host.numel()
+    full = 1 if default_host.numel() == n * self._dim and n > 0 else 0
+    _lib.check(self._lib.det_find_host_async(self._h, _ptr(keys_host), n, _ptr(default_host), full,
+                                             _ptr(values_out_host), _ptr(exists_out_host)))
+
+  def insert_host_async(self, keys_host, values_host):
+    _lib.check(self._lib.det_insert_host_async(self._h, _ptr(keys_host), _ptr(values_host), keys_host.numel()))
+
+  def host_sync(self):
+    _lib.check(self._lib.det_host_sync(self._h))
+
   # file-system format (cuckoo_hashtable_ops.py:425-523)
   def save_to_file_system(self, dirpath, file_name=None, dirpath_env="TFRA_SAVED_KV", append_to_file=False,
                           buffer_size=4194304, name=None):

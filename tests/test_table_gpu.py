@@ -378,3 +378,32 @@ def test_config_c1_flow_1m_keys_dim16():
   kb, vb = sorted_export(ot)
   np.testing.assert_array_equal(ka, kb)
   np.testing.assert_array_equal(va, vb)
+
+
+def test_async_host_entry_points_overlap_semantics():
+  """det_find_host_async / det_insert_host_async (pinned buffers only): enqueue-and-return; lookups of one batch
+  may be issued together with the write-back of another; det_host_sync drains both pipelines."""
+  torch = _torch()
+  from recommenders_addons_b200 import dynamic_embedding as de
+  from recommenders_addons_b200._lib import DetError
+  dim, n = 64, 200000
+  t = de.CuckooHashTable(torch.int64, torch.float32, [0.0] * dim, init_size=1 << 21)
+  g = torch.Generator().manual_seed(3)
+  ka = torch.randperm(1 << 22, generator=g)[:n].pin_memory()
+  kb = (torch.randperm(1 << 22, generator=g)[:n] + (1 << 23)).pin_memory()  # disjoint from ka
+  va, vb = torch.randn(n, dim, generator=g).pin_memory(), torch.randn(n, dim, generator=g).pin_memory()
+  d = torch.full((dim,), -2.0).pin_memory()
+  out = torch.empty(n, dim).pin_memory()
+  ex = torch.empty(n, dtype=torch.bool).pin_memory()
+  t.insert_host_async(ka, va)
+  t.host_sync()
+  t.insert_host_async(kb, vb)                 # write-back of batch b ...
+  t.lookup_host_async(ka, d, out, ex)         # ... overlapped with the lookup of batch a
+  t.host_sync()
+  assert int(t.size()) == 2 * n
+  assert bool(ex.all()) and torch.equal(out, va)
+  t.lookup_host_async(kb, d, out, ex)
+  t.host_sync()
+  assert bool(ex.all()) and torch.equal(out, vb)
+  with pytest.raises(DetError, match="pinned"):
+    t.insert_host_async(torch.arange(10), torch.zeros(10, dim))
