@@ -233,6 +233,62 @@ class Variable(object):
       return self._tables[index].size()
     return torch.stack([t.size() for t in self._tables]).sum()
 
+  # ---- file-system checkpoints (dynamic_embedding_variable.py:1009-1131, 200-450) -------------------------
+  def _saved_file_name(self, idx, proc_size, proc_rank):
+    import re
+    return re.sub(r"_mht_([^/]*)of([^/]*)", "_mht_%dof%d_rank%d_size%d" % (idx + 1, self.shard_num, proc_rank, proc_size),
+                  self._tables[idx]._name)
+
+  def save_to_file_system(self, dirpath, proc_size=1, proc_rank=0, file_name_list=None, dirpath_env="TFRA_SAVED_KV",
+                          append_to_file=False, buffer_size=4194304, name=None):
+    """One raw `<name>_mht_<i>of<N>_rank<r>_size<s>-keys` / `-values` pair per shard (the reference's naming)."""
+    for idx, t in enumerate(self._tables):
+      fn = file_name_list[idx] if file_name_list is not None else self._saved_file_name(idx, proc_size, proc_rank)
+      t.save_to_file_system(dirpath, file_name=fn, dirpath_env=dirpath_env, append_to_file=append_to_file,
+                            buffer_size=buffer_size)
+
+  def load_from_file_system(self, dirpath, proc_size=1, proc_rank=0, file_name_list=None, dirpath_env="TFRA_SAVED_KV",
+                            load_entire_dir=False, buffer_size=4194304, name=None):
+    """Loads shard i from the file written for (shard i of N, rank, size): same topology as the save."""
+    for idx, t in enumerate(self._tables):
+      fn = file_name_list[idx] if file_name_list is not None else self._saved_file_name(idx, proc_size, proc_rank)
+      t.load_from_file_system(dirpath, file_name=fn, dirpath_env=dirpath_env, load_entire_dir=load_entire_dir,
+                              buffer_size=buffer_size)
+
+  def load_from_file_system_with_restore_function(self, dirpath, proc_size=1, proc_rank=0, buffer_size=4194304):
+    """Reshard-on-load (load_de_variable_from_file_system, :200-450): reads EVERY saved shard of this variable,
+    whatever (shards x ranks) topology wrote it, keeps the keys this rank owns under the CURRENT partitioning and
+    routes them to the current local shards."""
+    import glob
+    import os
+    import re
+    import numpy as np
+    dirpath = os.environ.get("TFRA_SAVED_KV") or dirpath
+    base = self.name.replace("/", "_")
+    pat = re.compile(re.escape(base) + r"_mht_(\d+)of(\d+)_rank(\d+)_size(\d+)-keys$")
+    files = sorted(f for f in glob.glob(os.path.join(dirpath, base + "_mht_*-keys")) if pat.search(os.path.basename(f)))
+    if not files:
+      raise FileNotFoundError("no saved shards of variable %s under %s" % (self.name, dirpath))
+    self.clear()
+    np_dtype = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64,
+                torch.int8: np.int8, torch.float16: np.float16}.get(self.value_dtype)
+    if np_dtype is None:
+      raise TypeError("reshard-on-load is not implemented for %s rows" % (self.value_dtype,))
+    dev = self._tables[0].device
+    for kf in files:
+      keys = np.fromfile(kf, dtype=np.int64)
+      vals = np.fromfile(kf[:-len("-keys")] + "-values", dtype=np_dtype).reshape(-1, self.dim)
+      if keys.shape[0] != vals.shape[0]:
+        raise IOError("%s: keys and values files disagree" % kf)
+      for b in range(0, keys.shape[0], int(buffer_size)):
+        k = torch.from_numpy(keys[b:b + int(buffer_size)]).to(dev)
+        v = torch.from_numpy(vals[b:b + int(buffer_size)]).to(dev)
+        if proc_size > 1:
+          mine = self.partition_fn(k, proc_size) == proc_rank
+          k, v = k[mine], v[mine]
+        if k.numel():
+          self.upsert(k, v)
+
   def embedding_lookup(self, ids, name=None, max_norm=None, return_trainable=False):
     return embedding_lookup(self, ids, name=name, max_norm=max_norm, return_trainable=return_trainable)
 

@@ -407,3 +407,34 @@ def test_async_host_entry_points_overlap_semantics():
   assert bool(ex.all()) and torch.equal(out, vb)
   with pytest.raises(DetError, match="pinned"):
     t.insert_host_async(torch.arange(10), torch.zeros(10, dim))
+
+
+def test_variable_file_system_naming_and_reshard_on_load(tmp_path):
+  """Variable.save_to_file_system writes the reference's `<name>_mht_<i>of<N>_rank<r>_size<s>-keys/-values`
+  files (dynamic_embedding_variable.py:1041-1044); a variable with a DIFFERENT shard count restores them with
+  load_from_file_system_with_restore_function (reshard-on-load, :360-450)."""
+  import os
+  torch = _torch()
+  from recommenders_addons_b200 import dynamic_embedding as de
+  dim = 8
+  rng = np.random.default_rng(11)
+  k = rng.choice(np.arange(-10**6, 10**6), 30000, replace=False).astype(np.int64)
+  v = rng.normal(size=(30000, dim)).astype(np.float32)
+  a = de.Variable(dim=dim, devices=["cuda:0"] * 3, name="emb/ckpt_var")
+  dev = a.tables[0].device
+  a.upsert(torch.from_numpy(k).to(dev), torch.from_numpy(v).to(dev))
+  a.save_to_file_system(str(tmp_path), proc_size=1, proc_rank=0, dirpath_env="__unset__")
+  names = sorted(os.listdir(str(tmp_path)))
+  assert names == sorted("emb_ckpt_var_mht_%dof3_rank0_size1-%s" % (i, s) for i in (1, 2, 3) for s in ("keys", "values"))
+  # same topology: plain load
+  a2 = de.Variable(dim=dim, devices=["cuda:0"] * 3, name="emb/ckpt_var")
+  a2.load_from_file_system(str(tmp_path), dirpath_env="__unset__")
+  assert [int(a2.size(i)) for i in range(3)] == [int(a.size(i)) for i in range(3)]
+  # different topology: 2 shards read the 3 saved shards
+  b = de.Variable(dim=dim, devices=["cuda:0"] * 2, name="emb/ckpt_var")
+  b.load_from_file_system_with_restore_function(str(tmp_path))
+  assert int(b.size()) == 30000
+  owner = O.default_partition_fn(k, 2, True)
+  assert [int(b.size(i)) for i in range(2)] == [int((owner == i).sum()) for i in range(2)]
+  got = b.lookup(torch.from_numpy(k).to(dev))
+  np.testing.assert_array_equal(got.cpu().numpy(), v)
