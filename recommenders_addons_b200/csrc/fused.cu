@@ -709,7 +709,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)grads | (uintptr_t)init_param) & 15u) == 0);
   unsigned vpr, lpr, sh;
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
-  static const int ru = env_int("DET_APPLY_RU", 2);
+  static const int ru = env_int("DET_APPLY_RU", 1);  // measured on B200: one row-step per iteration wins (more resident CTAs)
   const TableView v = t->view;
   const long long* k = (const long long*)keys;
 #define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
