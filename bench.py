@@ -475,7 +475,11 @@ def gpu_arm(args):
       "clocks": clocks,
       "roofline": {
           "bound": "hbm", "kernel": ("det::find_kernel_tma<16>" if world == 1 else ("det::peer_find_kernel<16> (+peer barrier)" if is_peer else "partition+all_to_all+find_kernel+all_to_all+scatter")), "achieved": achieved, "peak": peak, "unit": "GB/s",
-          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+          "frac": achieved / peak,
+          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the
+          # ncu --set full capture summarised in profiles/r01_find_kernel_tma_dim64.csv (408.5 MB + 213.2 MB)
+          "traffic": 621701120 if (world == 1 and B == (1 << 20) and dim == 64) else None, "traffic_unit": "bytes per launch",
+          "peak_source": peak_src,
           "algorithmic_bytes_per_launch": algo_bytes,
           "note": "algorithmic = keys x dim x 4 B (north_star definition); the kernel necessarily also moves the "
                   "gathered rows out (+%d B/key) and one 64 B bucket + 8 B key per probe: honest-traffic rate %.0f GB/s "
