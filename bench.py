@@ -48,7 +48,7 @@ def parse_args():
   ap.add_argument("--cpu-resident", type=int, default=1 << 24, help="resident keys of the CPU-baseline sample")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
-  ap.add_argument("--e2e-steps", type=int, default=5)
+  ap.add_argument("--e2e-steps", type=int, default=10)
   ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                   help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
   ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
@@ -235,6 +235,20 @@ class ClockSampler(object):
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(gpu_index):
+  """Run the calling thread on the CPUs nearest to the GPU (so pinned staging buffers are first-touched on the
+  GPU's NUMA node).  Returns the previous affinity mask, or None when nothing was changed."""
+  try:
+    import pynvml
+    prev = os.sched_getaffinity(0)
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+    pynvml.nvmlDeviceSetCpuAffinity(h)
+    return prev
+  except Exception:
+    return None
+
+
 def measured_peak_gbs():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   try:
@@ -390,6 +404,7 @@ def gpu_arm(args):
   # ---- e2e through the host-buffer plugin API (N=1: table ops on pinned host tensors) -------------------
   e2e = None
   if not args.no_e2e:
+    prev_aff = bind_to_gpu_numa(local_rank)
     n_e2e = max(1, min(args.e2e_steps, args.steps))
     hk = [key_batches[(args.warmup + i) % n_batches].cpu().pin_memory() for i in range(n_e2e)]
     hv = new_vals.cpu().pin_memory()
@@ -445,6 +460,8 @@ def gpu_arm(args):
                     "(det_insert_host_async / det_find_host_async, pinned host buffers, both PCIe directions busy); "
                     "sequential_value = lookup_host then insert_host of the same batch, back to back")
 
+  if not args.no_e2e and prev_aff is not None:
+    os.sched_setaffinity(0, prev_aff)  # the CPU baseline below must see every host core again
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()

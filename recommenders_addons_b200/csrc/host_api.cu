@@ -17,18 +17,18 @@ constexpr int kPipeStreams = 3;
 constexpr size_t kPipeChunkBytes = 8u << 20;  // value bytes per chunk
 
 struct HostPipe {
-  cudaStream_t streams[kPipeStreams];
-  cudaEvent_t done[kPipeStreams];
+  cudaStream_t streams[kPipeStreams] = {};
+  cudaEvent_t done[kPipeStreams] = {};
   size_t chunk_keys = 0;
   // per stream device scratch
-  long long* d_keys[kPipeStreams];
-  unsigned char* d_vals[kPipeStreams];
-  unsigned char* d_defs[kPipeStreams];
-  unsigned char* d_exists[kPipeStreams];
+  long long* d_keys[kPipeStreams] = {};
+  unsigned char* d_vals[kPipeStreams] = {};
+  unsigned char* d_defs[kPipeStreams] = {};
+  unsigned char* d_exists[kPipeStreams] = {};
   // per stream pinned bounce buffers (only used for pageable user memory)
-  long long* h_keys[kPipeStreams];
-  unsigned char* h_vals[kPipeStreams];
-  unsigned char* h_exists[kPipeStreams];
+  long long* h_keys[kPipeStreams] = {};
+  unsigned char* h_vals[kPipeStreams] = {};
+  unsigned char* h_exists[kPipeStreams] = {};
 };
 
 static det_status pipe_get(det_table* t, int which, HostPipe** out) {
@@ -38,7 +38,6 @@ static det_status pipe_get(det_table* t, int which, HostPipe** out) {
     return DET_OK;
   }
   HostPipe* p = new HostPipe();
-  memset(p, 0, sizeof(*p));
   size_t ck = kPipeChunkBytes / t->row_bytes;
   if (ck < 1024) ck = 1024;
   ck = (ck + 31) & ~(size_t)31;
