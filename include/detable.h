@@ -224,6 +224,19 @@ det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const
 det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
                            det_stream_t stream);
 det_status det_peer_barrier(det_peer_group* g, det_stream_t stream);
+/* One-sided all-to-all-v of (key, row) pairs -- hvd.alltoall(ids, splits) + hvd.alltoall(rows, splits)
+ * (python/ops/shadow_embedding_ops.py:420-441) as ONE kernel: det_peer_route partitions the batch by owner and writes
+ * every pair into its segment of the owner's peer-mapped INBOX with posted NVLink stores, then publishes the counts.
+ * After det_peer_barrier the owner reads how much every source sent (det_peer_inbox_counts, HOST out, syncs) and
+ * concatenates the segments (det_peer_inbox_gather).  Backward path: row gradients travel to the owner, which
+ * combines duplicates and runs the fused optimizer locally (half-sync, dynamic_embedding_optimizer.py:580-595).
+ * inbox_ptrs[p] = where THIS process sees rank p's inbox (det_peer_inbox_bytes each, zeroed by its owner). */
+size_t det_peer_inbox_bytes(int world, size_t max_items, size_t row_bytes);
+det_status det_peer_inbox_attach(det_peer_group* g, const void* const* inbox_ptrs, size_t max_items, size_t row_bytes);
+det_status det_peer_route(det_peer_group* g, const int64_t* keys, const void* rows, size_t n, det_stream_t stream);
+det_status det_peer_inbox_counts(det_peer_group* g, int shard, int64_t* counts_host, det_stream_t stream);
+det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* counts_host, int64_t* keys_out,
+                                 void* rows_out, det_stream_t stream);
 
 /* ---- file-system format of SaveToFileSystem / LoadFromFileSystem
  * (cuckoo_hashtable_op.cc:310-504): raw little-endian `<prefix>-keys` (int64[n]) and

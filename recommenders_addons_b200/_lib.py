@@ -69,6 +69,11 @@ SIGNATURES = {
     "det_peer_find": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "det_peer_insert": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_peer_barrier": (_i, [_vp, _vp]),
+    "det_peer_inbox_bytes": (_sz, [_i, _sz, _sz]),
+    "det_peer_inbox_attach": (_i, [_vp, ctypes.POINTER(_vp), _sz, _sz]),
+    "det_peer_route": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "det_peer_inbox_counts": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "det_peer_inbox_gather": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp]),
     "det_save": (_i, [_vp, ctypes.c_char_p, _sz]),
     "det_load": (_i, [_vp, ctypes.c_char_p, _sz]),
     "det_get_stats": (_i, [_vp, ctypes.POINTER(DetStats), _vp]),

@@ -132,6 +132,69 @@ peer_insert_kernel(PeerViews pv, const long long* __restrict__ keys, const unsig
   }
 }
 
+// ---- one-sided all-to-all-v ("route"): the reference's hvd.alltoall(ids / rows, splits) as ONE kernel ------
+// Every rank owns an INBOX that all peers map: for each source rank a segment of `cap` (key, row) pairs plus a
+// count.  peer_route_kernel partitions this rank's batch by owner and writes every (key, row) pair straight into
+// its segment of the owner's inbox with posted NVLink stores; positions come from block-aggregated atomics on a
+// LOCAL cursor (only this rank writes its segment, so no remote atomics).  peer_publish_counts_kernel then
+// stores the per-owner totals into the owners' count words.  After det_peer_barrier the owner consumes its inbox
+// locally (det_peer_inbox_counts / det_peer_inbox_gather).  Used for the backward path: row gradients travel to
+// the owner, which combines duplicates and runs the fused optimizer (half-sync: never all-reduced).
+struct InboxView {
+  unsigned char* base[kMaxPeers];  // where THIS process sees rank p's inbox
+  size_t off_keys, off_rows;       // offsets of MY (source) segment inside any owner's inbox
+  size_t cap;                      // items per segment
+  unsigned row_bytes;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+peer_route_kernel(InboxView ib, int world, int gpu_mode, const long long* __restrict__ keys,
+                  const unsigned char* __restrict__ rows, size_t n, RowGeom g, unsigned long long* cursor,
+                  DevState* st) {
+  __shared__ unsigned s_cnt[kMaxPeers];
+  __shared__ unsigned long long s_base[kMaxPeers];
+  const int lane = threadIdx.x & 31;
+  const size_t n_tiles = (n + kThreadsP - 1) / kThreadsP;
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x < kMaxPeers) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t i = tile * kThreadsP + threadIdx.x;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const int own = valid ? peer_owner(key, world, gpu_mode) : 0;
+    unsigned pos = 0;
+    if (valid) pos = atomicAdd(&s_cnt[own], 1u);
+    __syncthreads();
+    if ((int)threadIdx.x < world) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+    const unsigned long long dest = s_base[own] + pos;
+    const bool ok = valid && dest < ib.cap;
+    if (valid && !ok) atomicOr(&st->error, kErrTableFull);
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (ok) {
+      reinterpret_cast<long long*>(ib.base[own] + ib.off_keys)[dest] = key;
+      src = rows + i * g.row_bytes;
+      dst = ib.base[own] + ib.off_rows + dest * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+    __syncthreads();
+  }
+}
+
+__global__ void peer_publish_counts_kernel(InboxView ib, int world, int rank, unsigned long long* cursor) {
+  const int o = threadIdx.x;
+  if (o < world) {
+    __threadfence_system();
+    unsigned long long c = cursor[o];
+    if (c > ib.cap) c = ib.cap;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(ib.base[o]) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(c) : "memory");
+    cursor[o] = 0;
+  }
+}
+
 struct BarPtrs {
   unsigned long long* peer[kMaxPeers];  // peer[p] = rank p's arrival array (mapped), peer[rank] = local
 };
@@ -175,6 +238,11 @@ struct det_peer_group {
   int sm_count = 148;
   int device = 0;
   int n_remote = 0;  // shards mapped from other processes
+  // inbox of the one-sided all-to-all-v
+  unsigned char* inbox[kMaxPeers] = {};
+  size_t inbox_cap = 0, inbox_row_bytes = 0, inbox_seg_keys = 0, inbox_seg_rows = 0;
+  unsigned long long* cursor = nullptr;      // owned, [kMaxPeers]
+  unsigned long long* h_counts = nullptr;    // pinned, [kMaxPeers]
 };
 
 extern "C" {
@@ -214,6 +282,8 @@ det_status det_peer_group_destroy(det_peer_group* g) {
   for (int p = 0; p < kMaxPeers; ++p)
     for (int q = 0; q < 3 + kMaxPlanes; ++q)
       if (g->opened[p][q]) cudaIpcCloseMemHandle(g->opened[p][q]);
+  if (g->cursor) cudaFree(g->cursor);
+  if (g->h_counts) cudaFreeHost(g->h_counts);
   delete g;
   return DET_OK;
 }
@@ -344,6 +414,103 @@ det_status det_peer_group_create_regions(det_peer_group** out, det_table* local,
     g->bar.peer[p] = (unsigned long long*)(base + L.off_bar);
   }
   *out = g;
+  return DET_OK;
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t det_peer_inbox_bytes(int world, size_t max_items, size_t row_bytes) {
+  if (world < 1 || world > kMaxPeers) return 0;
+  return 256 + (size_t)world * (al256(max_items * 8) + al256(max_items * row_bytes));
+}
+
+// inbox_ptrs[p] = where THIS process sees rank p's inbox (det_peer_inbox_bytes each, zero-initialised by the owner)
+det_status det_peer_inbox_attach(det_peer_group* g, const void* const* inbox_ptrs, size_t max_items, size_t row_bytes) {
+  if (!g || !inbox_ptrs || max_items == 0 || row_bytes == 0) return fail(DET_INVALID_ARGUMENT, "det_peer_inbox_attach: bad argument");
+  det::DevGuard _dg(g->device);
+  for (int p = 0; p < g->pv.world; ++p) {
+    if (!inbox_ptrs[p] || ((uintptr_t)inbox_ptrs[p] & 255u)) return fail(DET_INVALID_ARGUMENT, "det_peer_inbox_attach: inbox pointers must be non-null and 256 B aligned");
+    g->inbox[p] = (unsigned char*)inbox_ptrs[p];
+  }
+  g->inbox_cap = max_items;
+  g->inbox_row_bytes = row_bytes;
+  g->inbox_seg_keys = al256(max_items * 8);
+  g->inbox_seg_rows = al256(max_items * row_bytes);
+  if (!g->cursor) {
+    CUDA_TRY(cudaMalloc((void**)&g->cursor, kMaxPeers * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(g->cursor, 0, kMaxPeers * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost((void**)&g->h_counts, kMaxPeers * sizeof(unsigned long long)));
+  }
+  return DET_OK;
+}
+
+static InboxView inbox_view(const det_peer_group* g, int source) {
+  InboxView ib;
+  for (int p = 0; p < kMaxPeers; ++p) ib.base[p] = g->inbox[p];
+  ib.off_keys = 256 + (size_t)source * g->inbox_seg_keys;
+  ib.off_rows = 256 + (size_t)g->pv.world * g->inbox_seg_keys + (size_t)source * g->inbox_seg_rows;
+  ib.cap = g->inbox_cap;
+  ib.row_bytes = (unsigned)g->inbox_row_bytes;
+  return ib;
+}
+
+// partition by owner + pack + send, one kernel; then publish the per-owner counts.  Follow with det_peer_barrier.
+det_status det_peer_route(det_peer_group* g, const int64_t* keys, const void* rows, size_t n, det_stream_t stream) {
+  if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_route: null group");
+  if (!g->cursor) return fail(DET_INVALID_ARGUMENT, "det_peer_route: no inbox attached");
+  if (n > g->inbox_cap) return fail(DET_INVALID_ARGUMENT, "det_peer_route: batch larger than the inbox segments");
+  if (n && (!keys || !rows)) return fail(DET_INVALID_ARGUMENT, "det_peer_route: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  det::DevGuard _dg(g->device);
+  const InboxView ib = inbox_view(g, g->pv.rank);
+  if (n) {
+    const int vec = pick_vec(g->inbox_row_bytes, rows, nullptr, nullptr);
+    const RowGeom geo = make_geom((unsigned)g->inbox_row_bytes, vec);
+    const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+    const long long* k = (const long long*)keys;
+    const unsigned char* r = (const unsigned char*)rows;
+    DevState* st = g->local->view.st;
+    switch (vec) {
+      case 16: peer_route_kernel<16><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 8: peer_route_kernel<8><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 4: peer_route_kernel<4><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 2: peer_route_kernel<2><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      default: peer_route_kernel<1><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+    }
+  }
+  peer_publish_counts_kernel<<<1, 32, 0, s>>>(ib, g->pv.world, g->pv.rank, g->cursor);
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
+// counts_host[s] = items rank s routed to shard `shard` (which must live in this process).  Synchronises.
+det_status det_peer_inbox_counts(det_peer_group* g, int shard, int64_t* counts_host, det_stream_t stream) {
+  if (!g || !counts_host || shard < 0 || shard >= g->pv.world || !g->cursor) return fail(DET_INVALID_ARGUMENT, "det_peer_inbox_counts: bad argument");
+  det::DevGuard _dg(g->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(g->h_counts, g->inbox[shard], g->pv.world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int p = 0; p < g->pv.world; ++p) counts_host[p] = (int64_t)g->h_counts[p];
+  return DET_OK;
+}
+
+// keys_out / rows_out = concatenation of the inbox segments of shard `shard` in source-rank order
+det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* counts_host, int64_t* keys_out,
+                                 void* rows_out, det_stream_t stream) {
+  if (!g || !counts_host || shard < 0 || shard >= g->pv.world || !g->cursor) return fail(DET_INVALID_ARGUMENT, "det_peer_inbox_gather: bad argument");
+  det::DevGuard _dg(g->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t off = 0;
+  for (int p = 0; p < g->pv.world; ++p) {
+    const size_t c = (size_t)counts_host[p];
+    if (c == 0) continue;
+    if (c > g->inbox_cap || !keys_out || !rows_out) return fail(DET_INVALID_ARGUMENT, "det_peer_inbox_gather: bad count / null output");
+    const unsigned char* kb = g->inbox[shard] + 256 + (size_t)p * g->inbox_seg_keys;
+    const unsigned char* rb = g->inbox[shard] + 256 + (size_t)g->pv.world * g->inbox_seg_keys + (size_t)p * g->inbox_seg_rows;
+    CUDA_TRY(cudaMemcpyAsync(keys_out + off, kb, c * 8, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync((unsigned char*)rows_out + off * g->inbox_row_bytes, rb, c * g->inbox_row_bytes, cudaMemcpyDeviceToDevice, s));
+    off += c;
+  }
   return DET_OK;
 }
 

@@ -217,6 +217,71 @@ class PeerShardedVariable(object):
   def phase_barrier(self):
     self._libmod.check(self._lib.det_peer_barrier(self._g, self._sp()))
 
+  # ---- one-sided all-to-all-v: (key, row) pairs travel to the owner's inbox (backward path) ---------------
+  def attach_inbox(self, max_items):
+    """Collective.  Gives every rank an inbox of `max_items` (key, row) pairs per source rank that all peers map."""
+    import ctypes
+    rb = self.dim * torch.empty(0, dtype=self.value_dtype).element_size()
+    nbytes = int(self._lib.det_peer_inbox_bytes(self.world, int(max_items), rb))
+    if self.backing == "symmetric-memory":
+      import torch.distributed._symmetric_memory as symm_mem
+      box = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+      box.zero_()
+      hdl = symm_mem.rendezvous(box, self._group if self._group is not None else dist.group.WORLD)
+      ptrs = [int(p) for p in hdl.buffer_ptrs]
+      self._inbox = (box, hdl)
+    elif self.backing == "same-process":
+      boxes = [torch.zeros(nbytes, dtype=torch.uint8, device=t.device) for t in self._tables]
+      ptrs = [b.data_ptr() for b in boxes]
+      self._inbox = boxes
+    else:
+      raise RuntimeError("the inbox needs the symmetric-memory backing (PeerShardedVariable.create)")
+    torch.cuda.synchronize(self.device)
+    arr = (ctypes.c_void_p * self.world)(*ptrs)
+    self._libmod.check(self._lib.det_peer_inbox_attach(self._g, arr, int(max_items), rb))
+    self._inbox_items = int(max_items)
+    if self._group is not None or self.backing == "symmetric-memory":
+      dist.barrier(group=self._group)
+
+  def route(self, keys, rows):
+    """partition by owner + pack + send in one kernel; follow with phase_barrier() before inbox_take()."""
+    import ctypes
+    flat = keys.reshape(-1).contiguous()
+    r = rows.reshape(-1, self.dim).contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    self._libmod.check(self._lib.det_peer_route(self._g, p(flat), p(r), flat.numel(), self._sp()))
+
+  def inbox_take(self, shard=None):
+    """(keys, rows) every source routed to this rank's shard (concatenated in source-rank order)."""
+    import ctypes
+    shard = self.rank if shard is None else int(shard)
+    counts = (ctypes.c_int64 * self.world)()
+    self._libmod.check(self._lib.det_peer_inbox_counts(self._g, shard, counts, self._sp()))
+    total = int(sum(counts))
+    dev = self.device if self._tables[shard] is None else self._tables[shard].device
+    keys = torch.empty(total, dtype=torch.int64, device=dev)
+    rows = torch.empty((total, self.dim), dtype=self.value_dtype, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
+    self._libmod.check(self._lib.det_peer_inbox_gather(self._g, shard, counts, p(keys), p(rows), self._sp()))
+    return keys, rows, [int(c) for c in counts]
+
+  def apply_gradients(self, optimizer, keys, grads):
+    """Backward of the sharded lookup: route the row-gradients to their owners over NVLink, combine the gradients
+    that several ranks sent for the same key, then run the fused optimizer on the local shard (half-sync: sparse
+    rows are never all-reduced, dynamic_embedding_optimizer.py:580-595)."""
+    from .variable import unique
+    self.route(keys, grads)
+    self.phase_barrier()
+    rk, rg, _ = self.inbox_take()
+    self.phase_barrier()  # every owner has emptied its inbox: the next route may overwrite it
+    if rk.numel():
+      uniq, idx = unique(rk)
+      gsum = torch.zeros((uniq.numel(), self.dim), dtype=rg.dtype, device=rg.device).index_add_(0, idx.long(), rg)
+      optimizer.iterations += 1
+      optimizer.apply_sparse(self.local, uniq, gsum)
+    else:
+      optimizer.iterations += 1
+
   def size(self):
     if self._group is None and self.world > 1 and all(t is not None for t in self._tables):
       return sum(int(t.size()) for t in self._tables)

@@ -57,6 +57,25 @@ def _worker(rank, world, port, q):
         sv.phase_barrier()
         torch.cuda.synchronize()
       dist.barrier()
+      if mode == "symm":
+        # backward path: every rank routes row-gradients for keys of ALL owners; owners combine and step
+        var2 = de.PeerShardedVariable.create(dim, 1 << 18, initializer=0.0, num_slot_planes=1, name="mg-opt-%d" % rank)
+        var2.attach_inbox(1 << 16)
+        opt = de.FusedAdagrad(0.1, 0.1)
+        gk = allkeys[:20000]                                   # the SAME keys from both ranks -> summed on the owner
+        gg = np.full((gk.shape[0], dim), 0.01 * (rank + 1), np.float32)
+        var2.apply_gradients(opt, torch.from_numpy(gk).to(dev), torch.from_numpy(gg).to(dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+        gsum = np.float32(0.01 * sum(range(1, world + 1)))
+        acc = np.float32(0.1) + gsum * gsum
+        expect = np.float32(0) - (np.float32(0.1) * gsum) / np.sqrt(acc)
+        got2 = var2.lookup(torch.from_numpy(gk).to(dev)).cpu().numpy()
+        if not np.allclose(got2, expect, rtol=1e-6, atol=1e-8):
+          ok, msg = False, "sharded adagrad mismatch: %r vs %r" % (got2[0, 0], expect)
+        var2.phase_barrier()
+        torch.cuda.synchronize()
+        dist.barrier()
       if var.tables[0].stats()["error_flags"] != 0:
         ok, msg = False, "error flags in mode %s" % mode
   except Exception as e:  # noqa: BLE001

@@ -92,3 +92,63 @@ def test_table_in_caller_provided_region():
   with pytest.raises(DetError, match="region"):
     de.CuckooHashTable(torch.int64, torch.float32, [0.0] * dim, init_size=cap, region=region[: nbytes // 2])
   t.t.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_route_inbox(world):
+  """det_peer_route = partition + pack + send in one kernel: every (key, row) pair lands in the inbox of the shard
+  the reference's partition function names, in its source's segment, with exact counts (fake shards on one GPU)."""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  dim = 16
+  dev = torch.device("cuda", 0)
+  shards = [de.Variable(dim=dim, init_size=4096, name="route-%d-%d" % (world, i)) for i in range(world)]
+  pv = de.PeerShardedVariable(fake_shards=shards)
+  pv.attach_inbox(50000)
+  rng = np.random.default_rng(world)
+  for n in (1, 255, 40000):
+    keys = rng.integers(-2**62, 2**62, n).astype(np.int64)
+    rows = rng.normal(size=(n, dim)).astype(np.float32)
+    pv.route(torch.from_numpy(keys).to(dev), torch.from_numpy(rows).to(dev))
+    pv.phase_barrier()
+    owner = O.default_partition_fn(keys, world, True)
+    for sh in range(world):
+      k, r, counts = pv.inbox_take(sh)
+      assert counts[0] == int((owner == sh).sum()) and sum(counts[1:]) == 0   # this process routes as rank 0
+      got = dict(zip(k.cpu().numpy().tolist(), map(tuple, r.cpu().numpy())))
+      exp = dict(zip(keys[owner == sh].tolist(), map(tuple, rows[owner == sh])))
+      assert got == exp
+  for s in shards:
+    assert s.tables[0].stats()["error_flags"] == 0
+  pv.close()
+
+
+def test_peer_apply_gradients_single_process():
+  """route -> combine duplicate keys -> fused Adagrad on the owner shard == oracle tables stepped with the summed
+  gradient (twin-model idea of dynamic_embedding_optimizer_test.py:349-440)."""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  dim, world = 8, 1
+  dev = torch.device("cuda", 0)
+  shards = [de.Variable(dim=dim, init_size=1 << 15, initializer=0.0, num_slot_planes=1, name="route-opt")]
+  pv = de.PeerShardedVariable(fake_shards=shards)
+  pv.attach_inbox(20000)
+  opt = de.FusedAdagrad(0.1, 0.1)
+  p, a = O.PortTable(dim), O.PortTable(dim)
+  rng = np.random.default_rng(0)
+  for step in range(4):
+    keys = rng.integers(0, 3000, 8000).astype(np.int64)          # duplicates: several "ranks" touch the same row
+    g = rng.normal(0, 1e-2, (8000, dim)).astype(np.float32)
+    pv.apply_gradients(opt, torch.from_numpy(keys).to(dev), torch.from_numpy(g).to(dev))
+    # oracle: gradients of a key are summed in arrival order (route keeps no order -> compare with tolerance)
+    uk, inv = np.unique(keys, return_inverse=True)
+    gs = np.zeros((uk.shape[0], dim), np.float64)
+    np.add.at(gs, inv, g.astype(np.float64))
+    O.sparse_adagrad_step(p, a, uk, gs.astype(np.float32), 0.1, np.zeros(dim, np.float32), np.full(dim, 0.1, np.float32))
+  k, v = shards[0].export()
+  o = torch.argsort(k)
+  ek, ev = p.export()
+  eo = np.argsort(ek)
+  np.testing.assert_array_equal(k[o].cpu().numpy(), ek[eo])
+  np.testing.assert_allclose(v[o].cpu().numpy(), ev[eo], rtol=1e-5, atol=1e-7)
+  pv.close()
