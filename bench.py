@@ -51,7 +51,7 @@ def parse_args():
   ap.add_argument("--e2e-steps", type=int, default=10)
   ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                   help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
-  ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+  ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
                   help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2])")
   ap.add_argument("--distinct-batches", type=int, default=64, help="distinct key batches cycled through")
   return ap.parse_args()
@@ -607,11 +607,87 @@ def c3_arm(args):
                                "nnz": nnz, "unique_per_step": int(de.unique(batches[0])[0].numel())}}))
 
 
+def c5_arm(args):
+  """Secondary workload, BASELINE configs[4] (torchrun, N GPUs): DLRM-style forward + backward over ONE key-hash
+  sharded table (26 features share it through salted keys), dim 128, global batch 131072, half-sync sparse update.
+  Per step and rank: tf.unique of the rank's ids -> one-sided sharded lookup (det_peer_find) -> dense tower stubbed
+  by an all-reduce of a fixed 50 MB buffer -> per-unique row gradients routed to their owners over NVLink
+  (det_peer_route), duplicates combined, fused Adagrad on the owner (det_apply_adagrad).  Not the headline."""
+  import torch
+  import torch.distributed as dist
+  from recommenders_addons_b200 import dynamic_embedding as de
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  dist.init_process_group("nccl", device_id=dev)
+  dim, nfeat, gbatch = 128, 26, 131072
+  resident = min(args.resident, 60_000_000)          # rows per GPU actually resident (of the 2B-row key space)
+  vocab = resident * world
+  sv = de.PeerShardedVariable.create(dim, 2 * resident, initializer=0.0, num_slot_planes=1, name="c5_table")
+  table = sv.local.tables[0]
+  gen = torch.Generator(device=dev).manual_seed(42 + rank)
+  for b in range(0, vocab, 1 << 20):
+    r = torch.arange(b, min(vocab, b + (1 << 20)), dtype=torch.int64, device=dev)
+    k = rank_to_key_torch(r)
+    k = k[de.default_partition_fn(k, world, True) == rank]
+    if k.numel():
+      table.insert(k, torch.randn(k.numel(), dim, device=dev, generator=gen) * 0.01)
+  cdf = zipf_cdf_torch(vocab, dev)
+  ids_per_rank = gbatch // world * nfeat
+  sv.attach_inbox(ids_per_rank)
+  nb = max(1, min(args.steps + args.warmup, 16))
+  batches = [rank_to_key_torch(torch.searchsorted(cdf, torch.rand(ids_per_rank, dtype=torch.float64, device=dev, generator=gen))
+                               .clamp_(max=vocab - 1)) for _ in range(nb)]
+  del cdf
+  dense = torch.zeros(50 * 1024 * 1024 // 4, device=dev)
+  opt = de.FusedAdagrad(0.01, 0.1)
+
+  def step(i):
+    ids = batches[i % nb]
+    uniq, idx = de.unique(ids)
+    rows = sv.lookup(uniq)                          # forward: one-sided sharded lookup of the unique ids
+    sv.phase_barrier()
+    emb = rows[idx.long()]                          # [ids, dim] activations handed to the dense tower
+    dist.all_reduce(dense)                          # half-sync: only the dense tower is all-reduced
+    gout = emb * 1e-3                               # stand-in for the tower's gradient w.r.t. the activations
+    g = torch.zeros_like(rows).index_add_(0, idx.long(), gout)
+    sv.apply_gradients(opt, uniq, g)                # backward: route -> combine -> fused Adagrad on the owner
+
+  for i in range(args.warmup):
+    step(i)
+  torch.cuda.synchronize()
+  dist.barrier()
+  t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t0.record()
+  for i in range(args.steps):
+    step(args.warmup + i)
+  t1.record()
+  torch.cuda.synchronize()
+  dist.barrier()
+  ms = torch.tensor([t0.elapsed_time(t1) / args.steps], dtype=torch.float64, device=dev)
+  dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  if rank == 0:
+    print(json.dumps({"metric": "DLRM-style sharded forward+backward step, M ids/s (BASELINE configs[4])",
+                      "value": gbatch * nfeat / float(ms.item()) / 1e3, "unit": "M ids/s", "n_gpus": world,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()),
+                      "higher_is_better": True, "scaling": "strong", "data": "synthetic",
+                      "config": {"workload": "26 features x global batch %d, dim %d, %d resident rows/GPU (2B-row key space), "
+                                             "Zipf(1.05); unique -> det_peer_find -> 50 MB dense all-reduce -> det_peer_route -> "
+                                             "combine -> det_apply_adagrad" % (gbatch, dim, resident),
+                                 "ids_per_rank": ids_per_rank, "unique_per_rank": int(de.unique(batches[0])[0].numel())}}))
+  dist.destroy_process_group()
+
+
 if __name__ == "__main__":
   a = parse_args()
   if a.impl == "reference":
     reference_arm(a)
   elif a.workload == "c3":
     c3_arm(a)
+  elif a.workload == "c5":
+    c5_arm(a)
   else:
     gpu_arm(a)
