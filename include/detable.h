@@ -145,10 +145,13 @@ det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t
                       int64_t* n_unique_dev, void* workspace, size_t workspace_bytes,
                       det_stream_t stream);
 
-/* embedding_lookup_sparse forward in ONE kernel (python/ops/dynamic_embedding_ops.py:219-291):
+/* embedding_lookup_sparse forward, fused (python/ops/dynamic_embedding_ops.py:219-291): a slot-resolve pass
+ * (8 B per id) + ONE gather/weight/segment-sum/normalise pass -- the reference's [nnz, dim] gather, its weighted
+ * copy and the segment_sum input are never materialised:
  * out[b,:] = combine_{i in segment b} w_i * row(ids[i]); missing ids use `default_row` [dim]
  * (broadcast default).  segment_ids are sorted ascending (canonical SparseTensor order);
- * weights may be NULL (all 1).  Rows of `out` without ids are zero.  fp32 tables only. */
+ * weights may be NULL (all 1).  Rows of `out` without ids are zero.  fp32 tables only.
+ * Uses the table's scratch buffer: one stream per table at a time. */
 det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* segment_ids,
                              const float* weights, size_t nnz, size_t batch, int combiner,
                              const float* default_row, float* out, det_stream_t stream);

@@ -510,6 +510,7 @@ struct KeyTiles {
   const long long* keys;
   size_t n, n_tiles, tile;
   unsigned it;
+  bool tma;  // false: keys not 16 B aligned -> plain coalesced loads, same tile schedule
 
   __device__ __forceinline__ void issue(size_t tl, int stage) {
     const size_t k0 = tl * kTileKeys;
@@ -523,7 +524,7 @@ struct KeyTiles {
     }
   }
   __device__ __forceinline__ void init(long long (*sk)[kTileKeys], unsigned long long* sb, const long long* k,
-                                       size_t n_) {
+                                       size_t n_, bool use_tma = true) {
     s_keys = sk;
     s_bar = sb;
     keys = k;
@@ -531,17 +532,25 @@ struct KeyTiles {
     n_tiles = (n + kTileKeys - 1) / kTileKeys;
     tile = blockIdx.x;
     it = 0;
-    if (threadIdx.x == 0) {
-      for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
-      mbar_fence_init();
+    tma = use_tma;
+    if (tma) {
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
+        mbar_fence_init();
+      }
+      __syncthreads();
+      if (threadIdx.x == 0 && tile < n_tiles) issue(tile, 0);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && tile < n_tiles) issue(tile, 0);
   }
   __device__ __forceinline__ bool valid() const { return tile < n_tiles; }
   // index of this thread's key in the current tile + the key itself; ends with a CTA barrier after which the
   // stage may be refilled
   __device__ __forceinline__ long long key(size_t& i, bool& ok) {
+    if (!tma) {
+      i = tile * kTileKeys + threadIdx.x;
+      ok = i < n;
+      return ok ? __ldg(keys + i) : 0;
+    }
     const int stage = (int)(it & 1u);
     const size_t nxt = tile + gridDim.x;
     if (threadIdx.x == 0 && nxt < n_tiles) issue(nxt, stage ^ 1);

@@ -201,14 +201,17 @@ __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, 
 // K6 phase A: slot of every id (-1 = absent), 32 ids per warp-step with the same warp-cooperative probe as
 // det_find; only 8 B per id leave the kernel (the [nnz, dim] gather of the reference is never materialised)
 __global__ void __launch_bounds__(kThreadsF)
-resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz, long long* __restrict__ slots) {
+resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz, long long* __restrict__ slots,
+                     int use_tma) {
+  __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
   const int lane = threadIdx.x & 31;
-  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
-  for (size_t base = warp0 * 32; base < nnz; base += nwarps * 32) {
-    const size_t i = base + lane;
-    const bool valid = i < nnz;
-    const long long key = valid ? __ldg(ids + i) : 0;
+  KeyTiles kt;
+  kt.init(s_keys, s_bar, ids, nnz, use_tma != 0);
+  for (; kt.valid(); kt.next()) {
+    size_t i;
+    bool valid;
+    const long long key = kt.key(i, valid);
     const long long slot = warp_find_slots<false>(t, key, valid, lane);
     if (valid) slots[i] = slot;
   }
@@ -390,7 +393,9 @@ template <int VF, int OPT, int RU>
 __global__ void __launch_bounds__(kThreadsF)
 apply_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ grads, size_t n,
              OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
-             unsigned lpr_shift) {
+             unsigned lpr_shift, int use_tma) {
+  __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
   __shared__ unsigned s_new, s_used;
   if (threadIdx.x == 0) {
     s_new = 0;
@@ -402,16 +407,17 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
   const unsigned rows_per_step = 32u >> lpr_shift;
   const unsigned sub = (unsigned)lane >> lpr_shift;
   const unsigned c0 = (unsigned)lane & (lpr - 1u);
-  const size_t warp0 = ((size_t)blockIdx.x * kThreadsF + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
   float* P = (float*)t.planes[0];
   float* S1 = (float*)t.planes[1];
   float* S2 = (float*)t.planes[2];
   const float omb1 = 1.f - h.beta1, omb2 = 1.f - h.beta2;
-  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
-    const size_t i = base + lane;
-    const bool valid = i < n;
-    const long long key = valid ? __ldg(keys + i) : 0;
+  KeyTiles kt;
+  kt.init(s_keys, s_bar, keys, n, use_tma != 0);
+  for (; kt.valid(); kt.next()) {
+    size_t i;
+    bool valid;
+    const long long key = kt.key(i, valid);
+    const size_t base = i - (size_t)lane;
     bool is_new, from_empty;
     const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
     const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
@@ -647,6 +653,7 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
                              size_t nnz, size_t batch, int combiner, const float* default_row, float* out,
                              det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_lookup_sparse: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   if (t->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_lookup_sparse: float32 tables only");
   if (combiner < DET_COMBINER_SUM || combiner > DET_COMBINER_SQRTN)
     return fail(DET_INVALID_ARGUMENT, "combiner must be one of 'mean', 'sqrtn' or 'sum'");
@@ -666,8 +673,8 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   }
   segment_offsets_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, s>>>(segment_ids, nnz, batch, seg_start, t->view.st);
   if (nnz)
-    resolve_slots_kernel<<<grid_for(nnz, kThreadsF, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF,
-                           0, s>>>(t->view, (const long long*)ids, nnz, slots);
+    resolve_slots_kernel<<<grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF,
+                           0, s>>>(t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0);
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out) & 15u) == 0);
   unsigned vpr, lpr, sh;
@@ -697,6 +704,7 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
 static det_status apply_common(det_table* t, const int64_t* keys, const float* grads, size_t n, OptHyper h,
                                const float* init_param, int full_init, int opt, cudaStream_t s) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_apply: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   if (t->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_apply: float32 tables only");
   if (t->cfg.num_slot_planes < (opt == 0 ? 1 : 2))
     return fail(DET_INVALID_ARGUMENT, "det_apply: table was created with too few optimizer slot planes");
@@ -714,8 +722,9 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   const long long* k = (const long long*)keys;
 #define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
   {                                                                                                           \
-    const int grid = grid_for(n, kThreadsF, t->sm_count, occupancy_of(apply_kernel<VF_, OPT_, RU_>, kThreadsF)); \
-    apply_kernel<VF_, OPT_, RU_><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh); \
+    const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(apply_kernel<VF_, OPT_, RU_>, kThreadsF)); \
+    apply_kernel<VF_, OPT_, RU_><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, \
+                                                            (((uintptr_t)keys & 15u) == 0) ? 1 : 0);                 \
   }
   if (opt == 0) {
     if (vec4) { if (ru == 2) DET_LAUNCH_APPLY(4, 0, 2) else DET_LAUNCH_APPLY(4, 0, 1) }

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <string>
 #include <type_traits>
 
@@ -81,6 +82,9 @@ int grid_for(size_t n_items, int items_per_block, int sm_count, int blocks_per_s
 }  // namespace det
 
 struct det_table {
+  // host-side bookkeeping of mutating / scratch-using entry points (the reference takes a mutex for mutators and a
+  // shared lock for readers, hkv_hashtable_op_gpu.cu.cc:201-364; det_find needs no host lock)
+  std::mutex mu;
   det_config cfg;
   size_t row_bytes = 0;
   float max_lf = 0.75f;

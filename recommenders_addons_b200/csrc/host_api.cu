@@ -191,9 +191,12 @@ static det_status insert_host_impl(det_table* t, const int64_t* keys, const void
   if (!wait && !(pin_k && pin_v))
     return fail(DET_INVALID_ARGUMENT, "det_insert_host_async: all host buffers must be pinned (page-locked)");
   // growth (if any) must happen before the chunks are in flight on several streams
-  st = ensure_room(t, nullptr, n, p->streams[0]);
-  if (st != DET_OK) return st;
-  if (t->snap_inflight) t->n_since_snap += n;  // these keys are not covered by a snapshot already in flight
+  {
+    std::lock_guard<std::mutex> _lk(t->mu);
+    st = ensure_room(t, nullptr, n, p->streams[0]);
+    if (st != DET_OK) return st;
+    if (t->snap_inflight) t->n_since_snap += n;  // these keys are not covered by a snapshot already in flight
+  }
   size_t c = 0;
   for (size_t off = 0; off < n; off += ck, ++c) {
     const int i = (int)(c % kPipeStreams);

@@ -203,7 +203,6 @@ insert_kernel_tma(TableView t, const long long* __restrict__ keys, const unsigne
   }
 }
 
-template <typename T> struct AccT { using type = T; };
 __device__ __forceinline__ float acc_add(float a, float b) { return a + b; }
 __device__ __forceinline__ double acc_add(double a, double b) { return a + b; }
 __device__ __forceinline__ int acc_add(int a, int b) { return a + b; }
@@ -974,6 +973,7 @@ namespace det {
 det_status insert_impl(det_table* t, const int64_t* keys, const void* values, size_t n, cudaStream_t s,
                        bool check_room) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_insert: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_insert: null keys/values");
   det::DevGuard _dg(t->cfg.device);
@@ -1008,6 +1008,7 @@ extern "C" {
 det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists, size_t n,
                      det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_accum: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   if (n == 0) return DET_OK;
   if (!keys || !vod || !exists) return fail(DET_INVALID_ARGUMENT, "det_accum: null keys/values_or_deltas/exists");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1039,6 +1040,7 @@ det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const u
 
 det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_remove: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   if (n == 0) return DET_OK;
   if (!keys) return fail(DET_INVALID_ARGUMENT, "det_remove: null keys");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1050,6 +1052,7 @@ det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t 
 
 det_status det_clear(det_table* t, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_clear: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   det::DevGuard _dg(t->cfg.device);
   return table_clear_async(t, (cudaStream_t)stream);
 }
@@ -1073,6 +1076,7 @@ det_status det_capacity(det_table* t, uint64_t* out) {
 
 det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_reserve: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
   det::DevGuard _dg(t->cfg.device);
   const uint64_t limit = (uint64_t)((double)t->view.capacity() * t->max_lf);
   if (total_keys <= limit) return DET_OK;
@@ -1093,6 +1097,7 @@ det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream) {
 det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
                       int64_t* n_out_host, det_stream_t stream) {
   if (!t || !n_out_host) return fail(DET_INVALID_ARGUMENT, "det_export: null argument");
+  std::lock_guard<std::mutex> _lk(t->mu);
   if (plane < 0 || plane > t->cfg.num_slot_planes) return fail(DET_INVALID_ARGUMENT, "det_export: bad plane");
   cudaStream_t s = (cudaStream_t)stream;
   det::DevGuard _dg(t->cfg.device);
