@@ -39,6 +39,9 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+  """Returns the path of libdetable.so, (re)building it when a source is newer.  Safe under torchrun: the build
+  is serialised with a file lock, written to a temporary name and renamed, so concurrent ranks never load a
+  half-written library."""
   if not force and not needs_build():
     return LIB
   nvcc = _nvcc()
@@ -47,13 +50,25 @@ def build(force=False, verbose=False):
       return LIB  # GPU box without sources newer than the shipped library
     raise RuntimeError("nvcc not found and no prebuilt libdetable.so")
   os.makedirs(LIB_DIR, exist_ok=True)
-  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-      [os.path.join(CSRC, s) for s in SOURCES]
-  out = subprocess.run(cmd, capture_output=True, text=True)
-  if out.returncode != 0:
-    raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
-  if verbose:
-    print(out.stderr)
+  import fcntl
+  with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+      if not force and not needs_build():
+        return LIB  # another rank built it while we waited
+      tmp = LIB + ".tmp.%d" % os.getpid()
+      cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+      out = subprocess.run(cmd, capture_output=True, text=True)
+      if out.returncode != 0:
+        if os.path.exists(tmp):
+          os.remove(tmp)
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
+      os.replace(tmp, LIB)
+      if verbose:
+        print(out.stderr)
+    finally:
+      fcntl.flock(lock, fcntl.LOCK_UN)
   return LIB
 
 
