@@ -494,6 +494,148 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
   }
 }
 
+// K7 variant: rows staged through shared memory with cp.async (LDGSTS), two batches in flight per warp.
+// The plain kernel is latency-bound (ncu: DRAM 45 %, issue 35 %, nothing saturated): a lane holds the three
+// (four) 16 B loads of ONE row-step in registers and stalls on them.  Here a lane's loads of the NEXT batch of
+// row-steps are in flight (no registers held) while it updates the current batch.  Requires VF == 4 rows with one
+// vector per lane (vpr <= lpr, dim <= 128).  Same arithmetic, same results.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kStageSteps = 2;  // row-steps per batch
+
+template <int OPT>
+__global__ void __launch_bounds__(kThreadsF)
+apply_staged_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ grads, size_t n,
+                    OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
+                    unsigned lpr_shift, int use_tma) {
+  constexpr int NS = OPT == 0 ? 3 : 4;  // streams per row: grad, param, slot1 (, slot2)
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    s_new = 0;
+    s_used = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned dim = t.dim;
+  const unsigned rows_per_step = 32u >> lpr_shift;
+  const unsigned sub = (unsigned)lane >> lpr_shift;
+  const unsigned c0 = (unsigned)lane & (lpr - 1u);
+  const bool lane_on = c0 < vpr;
+  float* P = (float*)t.planes[0];
+  float* S1 = (float*)t.planes[1];
+  float* S2 = (float*)t.planes[2];
+  const float omb1 = 1.f - h.beta1, omb2 = 1.f - h.beta2;
+  // per warp: 2 stages x kStageSteps steps x NS streams x 32 lanes x 16 B
+  float4* wbuf = reinterpret_cast<float4*>(dyn_smem) + (size_t)warp * (2 * kStageSteps * NS * 32);
+  auto sm = [&](int stage, int step, int stream) -> float4* { return wbuf + ((stage * kStageSteps + step) * NS + stream) * 32 + lane; };
+  // first word of the slot row of MY row-group (lane sub*lpr holds vector 0)
+  auto sm_mark = [&](int stage, int step) -> const float* {
+    return reinterpret_cast<const float*>(wbuf + ((stage * kStageSteps + step) * NS + 2) * 32 + (sub << lpr_shift));
+  };
+  const unsigned steps_total = 32u / rows_per_step;            // row-steps per 32 keys
+  const unsigned n_batches = (steps_total + kStageSteps - 1) / kStageSteps;
+  KeyTiles kt;
+  kt.init(s_keys, s_bar, keys, n, use_tma != 0);
+  for (; kt.valid(); kt.next()) {
+    size_t i;
+    bool valid;
+    const long long key = kt.key(i, valid);
+    const size_t base = i - (size_t)lane;
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
+    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+    if (lane == 0 && bn) {
+      atomicAdd(&s_new, __popc(bn));
+      atomicAdd(&s_used, __popc(bu));
+    }
+    // issue the async loads of one batch of row-steps into `stage`
+    auto issue = [&](unsigned b, int stage) {
+#pragma unroll
+      for (int st = 0; st < kStageSteps; ++st) {
+        const unsigned step = b * kStageSteps + st;
+        const unsigned j = step * rows_per_step + sub;
+        const long long sl = shfl_ll(slot, (int)(j & 31u));
+        const bool nw = (bn >> (j & 31u)) & 1u;
+        const size_t gi = base + (j & 31u);
+        const bool ok = step < steps_total && gi < n && sl >= 0 && lane_on;
+        if (ok) {
+          const size_t ro = (size_t)sl * dim + (size_t)c0 * 4;
+          cp_async16(sm(stage, st, 0), grads + gi * dim + (size_t)c0 * 4);
+          cp_async16(sm(stage, st, 1), nw ? (full_init ? init_param + gi * dim : init_param) + (size_t)c0 * 4 : P + ro);
+          if (!nw) {
+            cp_async16(sm(stage, st, 2), S1 + ro);
+            if (OPT == 1) cp_async16(sm(stage, st, 3), S2 + ro);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    issue(0, 0);
+    for (unsigned b = 0; b < n_batches; ++b) {
+      const int stage = (int)(b & 1u);
+      if (b + 1 < n_batches) {
+        issue(b + 1, stage ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int st = 0; st < kStageSteps; ++st) {
+        const unsigned step = b * kStageSteps + st;
+        const unsigned j = step * rows_per_step + sub;
+        const long long sl = shfl_ll(slot, (int)(j & 31u));
+        const bool nw = (bn >> (j & 31u)) & 1u;
+        const size_t gi = base + (j & 31u);
+        const bool row_ok = step < steps_total && gi < n && sl >= 0;
+        // slot state absent: key created in this launch, or created by insert/accum and never stepped
+        const bool fresh = nw || (row_ok && __float_as_uint(*sm_mark(stage, st)) == kSlotUninit);
+        if (row_ok && lane_on) {
+          const size_t ro = (size_t)sl * dim + (size_t)c0 * 4;
+          FVec<4> g, p, a, b2;
+          g.v = *sm(stage, st, 0);
+          p.v = *sm(stage, st, 1);
+          if (OPT == 0) {
+            if (fresh) a.fill(h.init_slot); else a.v = *sm(stage, st, 2);
+            a.zip(g, [](float& av, float gv) { av = av + gv * gv; });
+            FVec<4> upd = g;
+            upd.zip(a, [&h](float& x, float av) { x = (h.lr * x) / (sqrtf(av) + h.eps); });
+            p.zip(upd, [](float& pv, float x) { pv = pv - x; });
+            a.store(S1 + ro);
+            p.store(P + ro);
+          } else {
+            if (fresh) { a.zero(); b2.zero(); } else { a.v = *sm(stage, st, 2); b2.v = *sm(stage, st, 3); }
+            a.zip(g, [omb1](float& mv, float gv) { mv = mv + (gv - mv) * omb1; });
+            b2.zip(g, [omb2](float& vv, float gv) { vv = vv + (gv * gv - vv) * omb2; });
+            FVec<4> upd = a;
+            upd.zip(b2, [&h](float& x, float vv) { x = (x * h.lr) / (sqrtf(vv) + h.eps); });
+            p.zip(upd, [](float& pv, float x) { pv = pv - x; });
+            a.store(S1 + ro);
+            b2.store(S2 + ro);
+            p.store(P + ro);
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with this stage before the next issue overwrites it
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K8: key-hash partition (stable) + row gather/scatter
 // ------------------------------------------------------------------------------------------------
@@ -718,8 +860,28 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   unsigned vpr, lpr, sh;
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
   static const int ru = env_int("DET_APPLY_RU", 1);  // measured on B200: one row-step per iteration wins (more resident CTAs)
+  static const int staged = env_int("DET_APPLY_STAGED", 0);
   const TableView v = t->view;
   const long long* k = (const long long*)keys;
+  if (staged && vec4 && vpr <= lpr) {
+    // cp.async-staged variant: 2 stages x kStageSteps x streams x 512 B per warp of dynamic shared memory
+    const int ns = opt == 0 ? 3 : 4;
+    const size_t smem = (size_t)(kThreadsF / 32) * 2 * kStageSteps * ns * 32 * 16;
+    const int tma = (((uintptr_t)keys & 15u) == 0) ? 1 : 0;
+    int occ = 1;
+    if (opt == 0) {
+      CUDA_TRY(cudaFuncSetAttribute(apply_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_staged_kernel<0>, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
+      apply_staged_kernel<0><<<grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
+    } else {
+      CUDA_TRY(cudaFuncSetAttribute(apply_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_staged_kernel<1>, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
+      apply_staged_kernel<1><<<grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
+    }
+    CUDA_TRY(cudaGetLastError());
+    note_mutation(t, n, s);
+    return DET_OK;
+  }
 #define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
   {                                                                                                           \
     const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(apply_kernel<VF_, OPT_, RU_>, kThreadsF)); \
