@@ -70,3 +70,45 @@ def test_error_convention_without_gpu():
   cfg.value_dtype, cfg.dim = 0, 0
   assert lib.det_table_create(ctypes.byref(h), ctypes.byref(cfg)) == 1
   assert b"dim" in lib.det_last_error()
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+  """sizeof/offsetof of det_config and det_stats as the C compiler sees them == the ctypes mirrors in _lib.py."""
+  from recommenders_addons_b200 import _lib
+  src = tmp_path / "layout.c"
+  src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "%s"
+int main(void) {
+  printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(det_config), offsetof(det_config, init_capacity),
+         offsetof(det_config, max_load_factor), sizeof(det_stats), offsetof(det_stats, hbm_bytes),
+         offsetof(det_stats, rehash_count));
+  return 0;
+}
+''' % HEADER)
+  exe = tmp_path / "layout"
+  p = subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], capture_output=True, text=True)
+  assert p.returncode == 0, p.stderr
+  out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()
+  got = [int(x) for x in out]
+  exp = [ctypes.sizeof(_lib.DetConfig), _lib.DetConfig.init_capacity.offset, _lib.DetConfig.max_load_factor.offset,
+         ctypes.sizeof(_lib.DetStats), _lib.DetStats.hbm_bytes.offset, _lib.DetStats.rehash_count.offset]
+  assert got == exp, (got, exp)
+
+
+def test_peer_and_region_entry_points_reject_bad_arguments_without_gpu():
+  from recommenders_addons_b200 import _lib
+  lib = _lib.lib()
+  assert lib.det_peer_handle_bytes() > 64 * 3
+  assert lib.det_peer_inbox_bytes(8, 1 << 20, 256) == 256 + 8 * ((1 << 23) + (1 << 28))
+  assert lib.det_peer_inbox_bytes(9, 10, 16) == 0          # at most 8 GPUs in one NVSwitch domain
+  cfg = _lib.DetConfig()
+  cfg.value_dtype, cfg.dim, cfg.init_capacity, cfg.num_slot_planes = 0, 64, 1 << 20, 1
+  n = lib.det_table_region_bytes(ctypes.byref(cfg))
+  assert n >= (1 << 20) * (8 + 2 * 256) and n % 256 == 0
+  h = ctypes.c_void_p()
+  assert lib.det_table_create_in_region(ctypes.byref(h), ctypes.byref(cfg), None, 0) == 1
+  assert lib.det_peer_group_create_regions(ctypes.byref(h), None, None, 2, 0, 1) == 1
+  assert lib.det_peer_route(None, None, None, 0, None) == 1
+  assert lib.det_host_sync(None) == 1
