@@ -7,10 +7,11 @@ from .variable import (Variable, default_partition_fn, embedding_lookup, embeddi
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
 from .optimizer import DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam
 from .sharded import PeerShardedVariable, ShardedVariable
+from . import layers
 
 __all__ = [
     "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvHashTable", "HkvHashTableConfig",
     "HkvHashTableCreator", "KVCreator", "Variable", "default_partition_fn", "embedding_lookup",
     "embedding_lookup_unique", "get_variable", "unique", "SparseIds", "embedding_lookup_sparse",
-    "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable",
+    "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
 ]

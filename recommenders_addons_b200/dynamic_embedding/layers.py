@@ -1,0 +1,93 @@
+"""Callers of the hot path, mirrored as thin torch modules (reference: python/keras/layers/embedding.py:111-595 --
+`Embedding`, `SquashedEmbedding`, `HvdAllToAllEmbedding` are thin wrappers over embedding_lookup_unique on a
+ShadowVariable / HvdVariable).  Training flow, like the reference's TrainableWrapper: forward fills a dense scratch
+of the UNIQUE rows from the table, autograd produces the gradient of that scratch, `apply_gradients(optimizer)`
+writes the update back with the fused find-or-insert + optimizer kernel."""
+import torch
+
+from .optimizer import _FusedBase
+from .sharded import PeerShardedVariable
+from .variable import Variable, default_partition_fn, embedding_lookup_unique, unique
+
+
+class Embedding(torch.nn.Module):
+  """de.keras.layers.Embedding: dynamic embedding space, arbitrary ids shape -> ids.shape + [embedding_size]."""
+
+  def __init__(self, embedding_size, key_dtype=torch.int64, value_dtype=torch.float32, combiner="sum", initializer=None,
+               devices=None, name="DynamicEmbeddingLayer", with_unique=True, trainable=True, bp_v2=False,
+               init_capacity=0, partitioner=default_partition_fn, kv_creator=None, max_norm=None, num_slot_planes=2):
+    super().__init__()
+    if combiner not in ("sum", "mean", "sqrtn"):
+      raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
+    self.embedding_size = int(embedding_size)
+    self.combiner = combiner
+    self.with_unique = with_unique
+    self.max_norm = max_norm
+    self.params = Variable(key_dtype=key_dtype, value_dtype=value_dtype, dim=self.embedding_size, devices=devices,
+                           partitioner=partitioner, name=name, initializer=initializer, trainable=trainable,
+                           init_size=init_capacity, kv_creator=kv_creator, bp_v2=bp_v2,
+                           num_slot_planes=num_slot_planes if value_dtype == torch.float32 else 0)
+    self._wrappers = []
+
+  def forward(self, ids):
+    out, tw = embedding_lookup_unique(self.params, ids, max_norm=self.max_norm, return_trainable=True)
+    if self.training and self.params.trainable:
+      self._wrappers.append(tw)
+    return out
+
+  def apply_gradients(self, optimizer):
+    """optimizer: de.FusedAdagrad / de.FusedAdam (or DynamicEmbeddingOptimizer(torch optimizer))."""
+    if not isinstance(optimizer, _FusedBase):
+      raise TypeError("use de.DynamicEmbeddingOptimizer(...) / de.FusedAdagrad / de.FusedAdam")
+    gv = [(tw.values.grad, tw) for tw in self._wrappers if tw.values.grad is not None]
+    self._wrappers = []
+    if gv:
+      optimizer.apply_gradients(gv)
+
+
+class SquashedEmbedding(Embedding):
+  """embedding.py:337-362: ids [batch, n] -> [batch, embedding_size], reduced over axis 1 with the combiner."""
+
+  def forward(self, ids):
+    emb = super().forward(ids)
+    if self.combiner == "sum":
+      return emb.sum(dim=1)
+    if self.combiner == "mean":
+      return emb.mean(dim=1)
+    return emb.sum(dim=1) / (emb.shape[1] ** 0.5)
+
+
+class AllToAllEmbedding(torch.nn.Module):
+  """HvdAllToAllEmbedding (embedding.py:545-595) over the one-sided sharded table: ids owned by ANY rank.
+  forward: unique -> det_peer_find -> gather; apply_gradients: per-unique gradients routed to their owners
+  (det_peer_route), combined and stepped there."""
+
+  def __init__(self, embedding_size, capacity_per_shard, group=None, initializer=None, name="AllToAllEmbedding",
+               num_slot_planes=2):
+    super().__init__()
+    self.embedding_size = int(embedding_size)
+    self.params = PeerShardedVariable.create(self.embedding_size, capacity_per_shard, group=group,
+                                             initializer=initializer, num_slot_planes=num_slot_planes, name=name)
+    self._pending = []
+    self._inbox_items = 0
+
+  def forward(self, ids):
+    flat = ids.reshape(-1)
+    uniq, idx = unique(flat)
+    rows = self.params.lookup(uniq).reshape(-1, self.embedding_size)
+    self.params.phase_barrier()
+    rows = rows.detach().requires_grad_(self.training)
+    if self.training:
+      self._pending.append((uniq, rows))
+    return rows[idx.long()].reshape(tuple(ids.shape) + (self.embedding_size,))
+
+  def apply_gradients(self, optimizer, max_unique_per_rank=None):
+    for uniq, rows in self._pending:
+      if rows.grad is None:
+        continue
+      need = int(max_unique_per_rank or uniq.numel())
+      if need > self._inbox_items:
+        self.params.attach_inbox(max(need, 2 * self._inbox_items))  # collective
+        self._inbox_items = max(need, 2 * self._inbox_items)
+      self.params.apply_gradients(optimizer, uniq, rows.grad)
+    self._pending = []

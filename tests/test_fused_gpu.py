@@ -271,3 +271,36 @@ def test_slot_state_of_keys_created_by_insert():
   np.testing.assert_array_equal(k1[stepped], ak)
   np.testing.assert_array_equal(a1[stepped], av)
   assert (a1[~stepped] == np.float32(0.1)).all()
+
+
+def test_embedding_layer_twin_training():
+  """A de.layers.SquashedEmbedding trained with the fused Adagrad == a dense torch twin trained with the same rule
+  (the comparison the reference makes between HvdAllToAllEmbedding and tf.keras.layers.Embedding,
+  kernel_tests/horovod_sync_train_test.py:300-336)."""
+  torch = _torch()
+  from recommenders_addons_b200 import dynamic_embedding as de
+  dim, vocab, batch, n = 8, 40, 16, 3
+  torch.manual_seed(1)
+  layer = de.layers.SquashedEmbedding(dim, combiner="sum", initializer=0.0, name="layer-twin", num_slot_planes=1)
+  layer.train()
+  opt = de.FusedAdagrad(0.1, 0.1)
+  dev = layer.params.tables[0].device
+  W = torch.zeros(vocab, dim, device=dev)
+  A = torch.full((vocab, dim), 0.1, device=dev)
+  target = torch.randn(batch, dim, device=dev)
+  for step in range(6):
+    ids = torch.randint(0, vocab, (batch, n), device=dev)
+    out = layer(ids)
+    assert out.shape == (batch, dim)
+    ((out - target) ** 2).sum().backward()
+    layer.apply_gradients(opt)
+    Wd = W.clone().requires_grad_(True)
+    ((Wd[ids].sum(1) - target) ** 2).sum().backward()
+    touched = torch.unique(ids)
+    g = Wd.grad[touched]
+    A[touched] = A[touched] + g * g
+    W[touched] = W[touched] - 0.1 * g / A[touched].sqrt()
+  got = layer.params.lookup(torch.arange(vocab, device=dev))
+  torch.testing.assert_close(got, W, rtol=1e-5, atol=1e-6)
+  plain = de.layers.Embedding(dim, name="layer-plain")
+  assert plain(torch.tensor([[15, 2], [4, 92], [22, 4]], device=dev)).shape == (3, 2, dim)

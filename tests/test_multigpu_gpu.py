@@ -76,6 +76,25 @@ def _worker(rank, world, port, q):
         var2.phase_barrier()
         torch.cuda.synchronize()
         dist.barrier()
+        # the caller layer (HvdAllToAllEmbedding mirror): forward over ids of all owners + routed backward
+        layer = de.layers.AllToAllEmbedding(dim, 1 << 16, initializer=0.0, name="mg-layer-%d" % rank, num_slot_planes=1)
+        layer.train()
+        lids = torch.from_numpy(allkeys[:4096].reshape(64, 64)).to(dev)
+        out = layer(lids)
+        if tuple(out.shape) != (64, 64, dim) or float(out.abs().max()) != 0.0:
+          ok, msg = False, "layer forward"
+        out.sum().backward()                                   # d/d(row) = number of occurrences = 1 per unique id
+        layer.apply_gradients(de.FusedAdagrad(0.1, 0.1), max_unique_per_rank=4096)
+        torch.cuda.synchronize()
+        dist.barrier()
+        gsum = np.float32(world)                                # every rank contributes gradient 1 for the same ids
+        expect = np.float32(0) - (np.float32(0.1) * gsum) / np.sqrt(np.float32(0.1) + gsum * gsum)
+        got3 = layer.params.lookup(lids.reshape(-1)).cpu().numpy()
+        layer.params.phase_barrier()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if not np.allclose(got3, expect, rtol=1e-6, atol=1e-8):
+          ok, msg = False, "layer backward: %r vs %r" % (got3[0, 0], expect)
       if var.tables[0].stats()["error_flags"] != 0:
         ok, msg = False, "error flags in mode %s" % mode
   except Exception as e:  # noqa: BLE001
