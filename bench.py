@@ -450,13 +450,13 @@ def gpu_arm(args):
       torch.cuda.synchronize()
       t0 = time.perf_counter()
       for i in range(n_e2e):
-        table.insert_host_async(hk[i], hv)
-        table.lookup_host_async(hk[(i + 1) % n_e2e], hd, ho2 if i % 2 == 0 else ho)
+        table.lookup_host_async(hk[(i + 1) % n_e2e], hd, ho2 if i % 2 == 0 else ho)  # D2H-heavy: rows of batch i+1
+        table.insert_host_async(hk[i], hv)                                          # H2D-heavy: write-back of batch i
         table.host_sync()
       dtp = time.perf_counter() - t0
       e2e["sequential_value"] = seq_value
       e2e["value"] = B * n_e2e / dtp / 1e6
-      e2e["api"] = ("CuckooHashTable.insert_host_async(batch i) + lookup_host_async(batch i+1) + host_sync per step "
+      e2e["api"] = ("CuckooHashTable.lookup_host_async(batch i+1) + insert_host_async(batch i) + host_sync per step "
                     "(det_insert_host_async / det_find_host_async, pinned host buffers, both PCIe directions busy); "
                     "sequential_value = lookup_host then insert_host of the same batch, back to back")
 

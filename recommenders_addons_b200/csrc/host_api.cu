@@ -26,6 +26,11 @@ struct HostPipe {
   unsigned char* d_defs[kPipeStreams] = {};
   unsigned char* d_exists[kPipeStreams] = {};
   // per stream pinned bounce buffers (only used for pageable user memory)
+  // all keys of one det_find_host call, uploaded in ONE copy before the chunk kernels: the lookups then never
+  // queue behind a concurrent write-back's bulk H2D traffic on the copy engine
+  long long* d_keys_all = nullptr;
+  size_t d_keys_all_cap = 0;
+  cudaEvent_t keys_ready = nullptr;
   long long* h_keys[kPipeStreams] = {};
   unsigned char* h_vals[kPipeStreams] = {};
   unsigned char* h_exists[kPipeStreams] = {};
@@ -71,6 +76,8 @@ static void host_pipe_free_one(HostPipe* p) {
     cudaFreeHost(p->h_vals[i]);
     cudaFreeHost(p->h_exists[i]);
   }
+  if (p->d_keys_all) cudaFree(p->d_keys_all);
+  if (p->keys_ready) cudaEventDestroy(p->keys_ready);
   delete p;
 }
 
@@ -118,6 +125,28 @@ static det_status find_host_impl(det_table* t, const int64_t* keys, size_t n, co
   if (!full_default)
     for (int i = 0; i < kPipeStreams; ++i)
       CUDA_TRY(cudaMemcpyAsync(p->d_defs[i], defs, rb, cudaMemcpyHostToDevice, p->streams[i]));
+  // pinned keys: one upload for the whole call
+  const long long* d_all = nullptr;
+  if (pin_k) {
+    if (p->d_keys_all_cap < n) {
+      if (p->d_keys_all) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(p->d_keys_all);
+        p->d_keys_all = nullptr;
+        p->d_keys_all_cap = 0;
+      }
+      const size_t want = n + (n >> 2) + 1024;
+      CUDA_TRY(cudaMalloc((void**)&p->d_keys_all, want * 8));
+      p->d_keys_all_cap = want;
+    }
+    if (!p->keys_ready) CUDA_TRY(cudaEventCreateWithFlags(&p->keys_ready, cudaEventDisableTiming));
+    // chunk kernels of a previous (asynchronous) call on the other streams may still read the old keys
+    for (int i = 1; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(p->streams[0], p->done[i], 0));
+    CUDA_TRY(cudaMemcpyAsync(p->d_keys_all, keys, n * 8, cudaMemcpyHostToDevice, p->streams[0]));
+    CUDA_TRY(cudaEventRecord(p->keys_ready, p->streams[0]));
+    for (int i = 1; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(p->streams[i], p->keys_ready, 0));
+    d_all = p->d_keys_all;
+  }
   size_t c = 0;
   for (size_t off = 0; off < n; off += ck, ++c) {
     const int i = (int)(c % kPipeStreams);
@@ -133,18 +162,17 @@ static det_status find_host_impl(det_table* t, const int64_t* keys, size_t n, co
         if (!pin_e && exists) memcpy(exists + poff, p->h_exists[i], ck);
       }
     }
-    const long long* hk = (const long long*)keys + off;
-    if (!pin_k) {
-      memcpy(p->h_keys[i], hk, m * 8);
-      hk = p->h_keys[i];
+    const long long* dk = d_all ? d_all + off : p->d_keys[i];
+    if (!d_all) {
+      memcpy(p->h_keys[i], (const long long*)keys + off, m * 8);
+      CUDA_TRY(cudaMemcpyAsync(p->d_keys[i], p->h_keys[i], m * 8, cudaMemcpyHostToDevice, s));
     }
-    CUDA_TRY(cudaMemcpyAsync(p->d_keys[i], hk, m * 8, cudaMemcpyHostToDevice, s));
     if (full_default) {
       // full-size defaults travel with the keys (pageable sources are staged by the driver)
       CUDA_TRY(cudaMemcpyAsync(p->d_defs[i], defs + off * rb, m * rb, cudaMemcpyHostToDevice, s));
       (void)pin_d;
     }
-    st = det_find(t, (const int64_t*)p->d_keys[i], m, p->d_defs[i], full_default, p->d_vals[i],
+    st = det_find(t, (const int64_t*)dk, m, p->d_defs[i], full_default, p->d_vals[i],
                   exists ? p->d_exists[i] : nullptr, (det_stream_t)s);
     if (st != DET_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(pin_v ? (void*)(vout + off * rb) : (void*)p->h_vals[i], p->d_vals[i], m * rb,
