@@ -43,7 +43,8 @@ static det_status pipe_get(det_table* t, int which, HostPipe** out) {
     return DET_OK;
   }
   HostPipe* p = new HostPipe();
-  size_t ck = kPipeChunkBytes / t->row_bytes;
+  static const size_t chunk_bytes = (size_t)env_int("DET_HOST_CHUNK_MB", (int)(kPipeChunkBytes >> 20)) << 20;
+  size_t ck = (chunk_bytes ? chunk_bytes : kPipeChunkBytes) / t->row_bytes;
   if (ck < 1024) ck = 1024;
   ck = (ck + 31) & ~(size_t)31;
   p->chunk_keys = ck;
