@@ -1,12 +1,10 @@
 """`de.embedding_lookup_sparse` / `de.safe_embedding_lookup_sparse`
 (reference: python/ops/dynamic_embedding_ops.py:120-438)."""
-import ctypes
-
 import torch
 
 from .. import _lib
 from .table import _ptr, _stream_ptr
-from .variable import TrainableWrapper, Variable, embedding_lookup, unique
+from .variable import Variable, embedding_lookup, unique
 
 
 class SparseIds(object):

@@ -7,14 +7,12 @@ table passes plus dense passes.  Here ONE kernel per step does find-or-insert + 
 (det_apply_adagrad / det_apply_adam); slots live in planes co-indexed with the value rows instead of in
 separate `<var>/<opt>/<slot>` tables (exportable as such through `Variable.tables[i].export(plane=k)`).
 """
-import math
-
 import numpy as np
 import torch
 
 from .. import _lib
 from .table import _ptr, _stream_ptr
-from .variable import TrainableWrapper, Variable, unique
+from .variable import TrainableWrapper, Variable
 
 
 def _init_rows(params, n, device):

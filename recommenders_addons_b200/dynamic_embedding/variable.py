@@ -1,8 +1,6 @@
 """`de.Variable`, `de.get_variable`, `de.embedding_lookup`, `de.embedding_lookup_unique`
 (reference: python/ops/dynamic_embedding_variable.py:165-197, 478-1007, 1265-1530;
 python/ops/dynamic_embedding_ops.py:64-117) on torch CUDA tensors over the C ABI."""
-import ctypes
-
 import torch
 
 from .. import _lib

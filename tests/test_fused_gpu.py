@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.helpers import GpuTableNp, sorted_export
+from tests.helpers import sorted_export
 
 pytestmark = pytest.mark.gpu
 

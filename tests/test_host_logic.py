@@ -1,7 +1,6 @@
 """Host-side logic that needs no GPU: partition function parity, import surface, and the multi-rank key
 exchange (world_size 2, gloo) with an in-memory stand-in for the local shard."""
 import os
-import sys
 
 import numpy as np
 import pytest
