@@ -83,11 +83,11 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
   return (out, tw) if return_trainable else out
 
 
-def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=None, combiner="mean",
-                                 default_id=None, name="safe_embedding_lookup_sparse", partition_strategy=None,
-                                 max_norm=None, return_trainable=False):
-  """dynamic_embedding_ops.py:296-438: flatten leading dims, prune weights <= 0 (unless combiner is "sum"),
-  give empty rows `default_id` (or a zero vector when default_id is None), then embedding_lookup_sparse."""
+def _safe_preprocess(sparse_ids, sparse_weights, combiner, default_id):
+  """The tensor surgery of safe_embedding_lookup_sparse (dynamic_embedding_ops.py:349-383), device-agnostic:
+  flatten the leading dims to one row axis, prune entries with weight <= 0 (unless combiner is "sum"), give every
+  empty row one (default_id or 0, weight 1) entry, keep canonical row-major order.
+  Returns (SparseIds 2-D, weights SparseIds or None, indices of the originally empty rows, original dense_shape)."""
   shape = sparse_ids.dense_shape
   rank = len(shape)
   lead = 1
@@ -126,6 +126,15 @@ def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=N
   ind2 = torch.stack([row, col], 1)
   sp2 = SparseIds(ind2, ids, (lead, shape[-1]))
   sw2 = None if w is None else SparseIds(ind2, w, (lead, shape[-1]))
+  return sp2, sw2, empty_rows, shape
+
+
+def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=None, combiner="mean",
+                                 default_id=None, name="safe_embedding_lookup_sparse", partition_strategy=None,
+                                 max_norm=None, return_trainable=False):
+  """dynamic_embedding_ops.py:296-438: flatten leading dims, prune weights <= 0 (unless combiner is "sum"),
+  give empty rows `default_id` (or a zero vector when default_id is None), then embedding_lookup_sparse."""
+  sp2, sw2, empty_rows, shape = _safe_preprocess(sparse_ids, sparse_weights, combiner, default_id)
   r = embedding_lookup_sparse(embedding_weights, sp2, sw2, combiner=combiner, max_norm=max_norm,
                               return_trainable=return_trainable)
   result, tw = r if return_trainable else (r, None)

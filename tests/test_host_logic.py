@@ -114,3 +114,59 @@ def test_sharded_exchange_world2_gloo():
     assert p.exitcode == 0
   assert all(ok for _, ok, _ in res), res
   assert sum(n for _, _, n in res) > 0
+
+
+def _fixture(indices, shape):
+  from recommenders_addons_b200 import dynamic_embedding as de
+  ids = torch.tensor([0, 1, -100, -100, 2, 0, 1])
+  weights = torch.tensor([1.0, 2.0, 1.0, 1.0, 3.0, 0.0, -0.5])
+  ind = torch.tensor(indices)
+  return de.SparseIds(ind, ids, shape), de.SparseIds(ind, weights, shape)
+
+
+def test_safe_lookup_preprocessing_2d_fixture():
+  """_ids_and_weights_2d (dynamic_embedding_ops_test.py:187-216): row 0 valid ids + an invalid one, row 1 only an
+  invalid id, row 2 empty, row 3 single id, row 4 only weights <= 0."""
+  from recommenders_addons_b200.dynamic_embedding.ops import _safe_preprocess
+  sp, sw = _fixture([[0, 0], [0, 1], [0, 2], [1, 0], [3, 0], [4, 0], [4, 1]], (5, 4))
+  sp2, sw2, empty, shape = _safe_preprocess(sp, sw, "mean", None)
+  # weights <= 0 pruned (row 4 becomes empty); rows 2 and 4 get one filler entry (id 0, weight 1)
+  assert sp2.dense_shape == (5, 4) and shape == (5, 4)
+  assert sp2.indices[:, 0].tolist() == [0, 0, 0, 1, 2, 3, 4]
+  assert sp2.values.tolist() == [0, 1, -100, -100, 0, 2, 0]
+  assert sw2.values.tolist() == [1.0, 2.0, 1.0, 1.0, 1.0, 3.0, 1.0]
+  assert empty.tolist() == [2, 4]
+  # combiner "sum" keeps non-positive weights; default_id fills the empty row
+  sp3, sw3, empty3, _ = _safe_preprocess(sp, sw, "sum", 3)
+  assert sp3.values.tolist() == [0, 1, -100, -100, 3, 2, 0, 1] and empty3.tolist() == [2]
+  assert sw3.values.tolist() == [1.0, 2.0, 1.0, 1.0, 1.0, 3.0, 0.0, -0.5]
+  # no weights at all: nothing is pruned
+  sp4, sw4, empty4, _ = _safe_preprocess(sp, None, "mean", None)
+  assert sw4 is None and sp4.values.numel() == 8 and empty4.tolist() == [2]
+
+
+def test_safe_lookup_preprocessing_3d_fixture():
+  """_ids_and_weights_3d (dynamic_embedding_ops_test.py:219-250): leading dims [2, 3] flatten to 6 rows."""
+  from recommenders_addons_b200.dynamic_embedding.ops import _safe_preprocess
+  sp, sw = _fixture([[0, 0, 0], [0, 0, 1], [0, 0, 2], [0, 1, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1]], (2, 3, 4))
+  sp2, sw2, empty, shape = _safe_preprocess(sp, sw, "mean", None)
+  assert sp2.dense_shape == (6, 4) and shape == (2, 3, 4)
+  assert sp2.indices[:, 0].tolist() == [0, 0, 0, 1, 2, 3, 4, 5]
+  assert empty.tolist() == [2, 4, 5]
+  assert sp2.values.tolist() == [0, 1, -100, -100, 0, 2, 0, 0]
+
+
+def test_sparse_combiners_cpu_oracle_against_reference_fixture():
+  """SafeEmbeddingLookupSparseTest::test_safe_embedding_lookup_sparse_return_zero_vector semantics
+  (dynamic_embedding_ops_test.py:1007-1040) on the oracle: mean of rows 0,1 weighted 1,2 (invalid id -> default 0)."""
+  from recommenders_addons_b200.dynamic_embedding.ops import _safe_preprocess
+  dim = 4
+  emb = np.arange(3 * dim, dtype=np.float32).reshape(3, dim) + 1
+  t = O.PortTable(dim)
+  t.insert(np.array([0, 1, 2]), emb)
+  sp, sw = _fixture([[0, 0], [0, 1], [0, 2], [1, 0], [3, 0], [4, 0], [4, 1]], (5, 4))
+  sp2, sw2, empty, _ = _safe_preprocess(sp, sw, "mean", None)
+  out = O.embedding_lookup_sparse(t, sp2.values.numpy(), sp2.indices[:, 0].numpy(), sw2.values.numpy(), 5, "mean")
+  out[empty.numpy()] = 0
+  exp = np.stack([(emb[0] * 1 + emb[1] * 2) / 4.0, np.zeros(dim), np.zeros(dim), emb[2], np.zeros(dim)]).astype(np.float32)
+  np.testing.assert_allclose(out, exp, rtol=1e-6, atol=1e-6)
