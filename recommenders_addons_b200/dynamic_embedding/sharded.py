@@ -37,8 +37,10 @@ def exchange_rows(rows, in_splits, out_splits, group=None):
 class ShardedVariable(object):
   """One shard of a key-hash-sharded variable per rank; lookups / updates take keys owned by ANY rank."""
 
-  def __init__(self, local_variable, group=None, partition_impl=None, gather_impl=None, scatter_impl=None):
+  def __init__(self, local_variable, group=None, partition_impl=None, gather_impl=None, scatter_impl=None,
+               unique_impl=None):
     self.local = local_variable
+    self._unique = unique_impl
     self.group = group
     self.world = dist.get_world_size(group)
     self.rank = dist.get_rank(group)
@@ -73,8 +75,10 @@ class ShardedVariable(object):
     g = self._gather(grads.reshape(-1, self.dim), perm)
     recv_keys, rc, sc = exchange_keys(grouped, counts, self.group)
     recv_g = exchange_rows(g, sc, rc, self.group)
-    from .variable import unique
-    uniq, idx = unique(recv_keys)
+    if self._unique is None:
+      from .variable import unique
+      self._unique = unique
+    uniq, idx = self._unique(recv_keys)
     gsum = torch.zeros((uniq.numel(), self.dim), dtype=recv_g.dtype, device=recv_g.device).index_add(
         0, idx.long(), recv_g)
     optimizer.iterations += 1

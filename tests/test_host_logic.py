@@ -170,3 +170,57 @@ def test_sparse_combiners_cpu_oracle_against_reference_fixture():
   out[empty.numpy()] = 0
   exp = np.stack([(emb[0] * 1 + emb[1] * 2) / 4.0, np.zeros(dim), np.zeros(dim), emb[2], np.zeros(dim)]).astype(np.float32)
   np.testing.assert_allclose(out, exp, rtol=1e-6, atol=1e-6)
+
+
+class _SgdStub(object):
+  """optimizer stand-in: plain SGD on the dict shard (exchange-logic test only)."""
+  iterations = 0
+
+  def apply_sparse(self, shard, keys, grads):
+    for k, g in zip(keys.tolist(), grads):
+      shard.d[k] = shard.d.get(k, torch.zeros(shard.dim)) - 0.5 * g
+
+
+def _cpu_unique(keys):
+  u, idx = O.unique_first_occurrence(keys.numpy())
+  return torch.from_numpy(u), torch.from_numpy(idx)
+
+
+def _worker_bwd(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from recommenders_addons_b200.dynamic_embedding.sharded import ShardedVariable
+  dim = 2
+  sv = ShardedVariable(_DictShard(dim), partition_impl=_cpu_partition(world),
+                       gather_impl=lambda rows, perm: rows[perm.long()],
+                       scatter_impl=lambda rows, perm: torch.empty_like(rows).index_copy_(0, perm.long(), rows),
+                       unique_impl=_cpu_unique)
+  keys = torch.arange(0, 40)                      # BOTH ranks send gradients for the same 40 keys
+  grads = torch.full((40, dim), float(rank + 1))
+  sv.apply_gradients(_SgdStub(), keys, grads)
+  dist.barrier()
+  # the owner combined the gradients of both ranks before stepping: -0.5 * (1 + 2)
+  ok = all(abs(float(v[0]) + 1.5) < 1e-6 for v in sv.local.d.values())
+  owned = sorted(sv.local.d.keys())
+  ok = ok and owned == [k for k in range(40) if (k & 0x7fffffff) % world == rank]
+  q.put((rank, ok, len(owned)))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_sharded_backward_routes_and_combines_world2_gloo():
+  """half-sync sparse update over the exchange (dynamic_embedding_optimizer.py:580-595): row gradients travel to
+  the owner, duplicates from several ranks are summed there, sparse rows are never all-reduced."""
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29800 + (os.getpid() % 150)
+  procs = [ctx.Process(target=_worker_bwd, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in range(2)]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert all(ok for _, ok, _ in res), res
+  assert sum(n for _, _, n in res) == 40
