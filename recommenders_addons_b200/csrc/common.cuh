@@ -497,6 +497,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                : "memory");
 }
 
+// Ampere-style asynchronous 16 B copies global -> shared (SASS LDGSTS): data in flight without holding registers
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 constexpr int kTileKeys = 256;  // keys per CTA tile (= blockDim): 2 KB per stage
 constexpr int kStages = 2;
 

@@ -499,15 +499,6 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
 // (four) 16 B loads of ONE row-step in registers and stalls on them.  Here a lane's loads of the NEXT batch of
 // row-steps are in flight (no registers held) while it updates the current batch.  Requires VF == 4 rows with one
 // vector per lane (vpr <= lpr, dim <= 128).  Same arithmetic, same results.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 constexpr int kStageSteps = 2;  // row-steps per batch
 
 template <int OPT>

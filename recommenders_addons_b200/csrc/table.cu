@@ -282,6 +282,100 @@ accum_kernel(TableView t, const long long* __restrict__ keys, const T* __restric
   }
 }
 
+// K3 variant for float32 rows made of one 16 B vector per lane: the delta rows and (for keys that accumulate) the
+// table rows of the NEXT batch of row-steps are in flight through shared memory (cp.async) while the current
+// batch is added and stored -- the same latency-hiding scheme as apply_staged_kernel.
+constexpr int kAccSteps = 2;
+
+__global__ void __launch_bounds__(kThreads)
+accum_staged_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ vod,
+                    const unsigned char* __restrict__ exists, size_t n, SlotInit si, RowGeom g) {
+  __shared__ __align__(16) float4 s_buf[kWarpsPerBlock][2][kAccSteps][2][32];  // [warp][stage][step][delta|row][lane]
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    s_new = 0;
+    s_used = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned dim = t.dim;
+  const unsigned rows_per_step = 32u >> g.lpr_shift;
+  const unsigned sub = (unsigned)lane >> g.lpr_shift;
+  const unsigned c0 = (unsigned)lane & (g.lpr - 1u);
+  const bool lane_on = c0 < g.vpr;
+  const unsigned steps_total = 32u / rows_per_step;
+  const unsigned n_batches = (steps_total + kAccSteps - 1) / kAccSteps;
+  float* P = (float*)t.planes[0];
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const bool ex = valid ? (exists[i] != 0) : false;
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim(t, key, valid, valid && !ex, lane, is_new, from_empty);
+    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+    if (lane == 0 && bn) {
+      atomicAdd(&s_new, __popc(bn));
+      atomicAdd(&s_used, __popc(bu));
+    }
+    // mode: 0 skip, 1 assign (new key), 2 add (found & exist)
+    int mode = 0;
+    if (valid && slot >= 0) mode = is_new ? 1 : (ex ? 2 : 0);
+    auto issue = [&](unsigned b, int stage) {
+#pragma unroll
+      for (int st = 0; st < kAccSteps; ++st) {
+        const unsigned step = b * kAccSteps + st;
+        const unsigned j = (step * rows_per_step + sub) & 31u;
+        const int m = __shfl_sync(kFull, mode, (int)j);
+        const long long sl = shfl_ll(slot, (int)j);
+        if (step < steps_total && m != 0 && lane_on) {
+          cp_async16(&s_buf[warp][stage][st][0][lane], vod + (base + j) * dim + (size_t)c0 * 4);
+          if (m == 2) cp_async16(&s_buf[warp][stage][st][1][lane], P + (size_t)sl * dim + (size_t)c0 * 4);
+        }
+      }
+      cp_async_commit();
+    };
+    issue(0, 0);
+    for (unsigned b = 0; b < n_batches; ++b) {
+      const int stage = (int)(b & 1u);
+      if (b + 1 < n_batches) {
+        issue(b + 1, stage ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+#pragma unroll
+      for (int st = 0; st < kAccSteps; ++st) {
+        const unsigned step = b * kAccSteps + st;
+        const unsigned j = (step * rows_per_step + sub) & 31u;
+        const int m = __shfl_sync(kFull, mode, (int)j);
+        const long long sl = shfl_ll(slot, (int)j);
+        if (step < steps_total && m != 0 && lane_on) {
+          float4 d = s_buf[warp][stage][st][0][lane];   // each lane reads back only what it copied itself
+          if (m == 2) {
+            const float4 r = s_buf[warp][stage][st][1][lane];
+            d.x = r.x + d.x;
+            d.y = r.y + d.y;
+            d.z = r.z + d.z;
+            d.w = r.w + d.w;
+          }
+          *reinterpret_cast<float4*>(P + (size_t)sl * dim + (size_t)c0 * 4) = d;
+        }
+      }
+    }
+    if (is_new && slot >= 0)
+      for (int p = 1; p <= si.n_planes; ++p)
+        *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * dim * 4u) = kSlotUninit;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+}
+
 // K4: Remove.  A slot whose bucket still has an EMPTY slot goes straight back to EMPTY (no probe
 // chain can run through such a bucket); otherwise it becomes a tombstone.
 __global__ void __launch_bounds__(kThreads)
@@ -733,6 +827,14 @@ template <typename T>
 static det_status launch_accum(det_table* t, const TableView& v, const long long* k, const void* vod,
                                const uint8_t* exists, size_t n, const SlotInit& si, const RowGeom& g, int vec,
                                cudaStream_t s) {
+  if constexpr (std::is_same<T, float>::value) {
+    static const int staged = env_int("DET_ACCUM_STAGED", 1);
+    if (staged && vec == 16 && g.vpr <= g.lpr) {
+      const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(accum_staged_kernel, kThreads));
+      accum_staged_kernel<<<grid, kThreads, 0, s>>>(v, k, (const float*)vod, exists, n, si, g);
+      return DET_OK;
+    }
+  }
   switch (vec) {
     case 16: return launch_accum_v<T, 16>(t, v, k, vod, exists, n, si, g, s);
     case 8:
