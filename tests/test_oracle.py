@@ -185,3 +185,52 @@ def test_twin_adagrad_matches_dense():
     dense_p[keys], dense_a[keys] = O.adagrad_dense(dense_p[keys], dense_a[keys], g, 0.1)
   k, v = p.export()
   np.testing.assert_array_equal(v[np.argsort(k)], dense_p[np.sort(k)])
+
+
+# ---- property-based pinning of the C port against the reference's own engine -----------------------------
+try:
+  from hypothesis import given, settings, strategies as st
+  _HAVE_HYP = True
+except Exception:  # pragma: no cover
+  _HAVE_HYP = False
+
+if _HAVE_HYP:
+  _op = st.tuples(st.sampled_from(["insert", "accum", "remove", "find", "clear"]),
+                  st.lists(st.integers(min_value=-40, max_value=40), min_size=0, max_size=60),
+                  st.integers(min_value=0, max_value=2**31 - 1))
+
+  @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+  @settings(max_examples=60, deadline=None)
+  @given(st.sampled_from([1, 3, 16]), st.sampled_from([1, 4, 64]), st.lists(_op, min_size=1, max_size=25))
+  def test_port_vs_reference_engine_property(dim, init_size, ops):
+    """Arbitrary op streams over a tiny key universe and tiny initial tables (init_size 1/4/64 slots: every
+    insert path runs -- last-empty-slot placement, BFS displacement, doubling): the C port and the reference's
+    libcuckoo agree on sizes, find results, exists masks and export ORDER after every op.  Duplicate keys inside a
+    call are allowed here (both engines are single-threaded, so the outcome is deterministic)."""
+    r, p = O.RefTable(dim, init_size, threads=1), O.PortTable(dim, init_size)
+    for name, keys, seed in ops:
+      k = np.array(keys, dtype=np.int64)
+      rng = np.random.default_rng(seed)
+      if name == "insert":
+        v = rng.integers(-5, 5, size=(k.shape[0], dim)).astype(np.float32)
+        r.insert(k, v), p.insert(k, v)
+      elif name == "accum":
+        v = rng.integers(-5, 5, size=(k.shape[0], dim)).astype(np.float32)
+        ex = rng.integers(0, 2, size=k.shape[0]).astype(bool)
+        r.accum(k, v, ex), p.accum(k, v, ex)
+      elif name == "remove":
+        r.remove(k), p.remove(k)
+      elif name == "clear":
+        r.clear(), p.clear()
+      else:
+        d = rng.integers(-9, 9, size=(max(1, k.shape[0]), dim)).astype(np.float32)
+        a, ea = r.find(k, d if k.shape[0] else d[0], True)
+        b, eb = p.find(k, d if k.shape[0] else d[0], True)
+        np.testing.assert_array_equal(ea, eb)
+        np.testing.assert_array_equal(a, b)
+      assert r.size() == p.size()
+      ka, va = r.export()
+      kb, vb = p.export()
+      np.testing.assert_array_equal(ka, kb)
+      np.testing.assert_array_equal(va, vb)
+    r.close(), p.close()
