@@ -32,7 +32,7 @@ class LayoutModel(object):
     self.used = 0
 
   def home(self, key):
-    return (fmix64(key) * self.nb) >> 64
+    return (fmix64(int(key)) * self.nb) >> 64
 
   def _chain(self, key):
     """yields (bucket index, slot range) along the probe chain until (and including) the bucket that ends it"""

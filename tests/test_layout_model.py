@@ -71,3 +71,102 @@ def test_erase_to_empty_shortcut_never_cuts_a_chain():
     assert m.find(k) >= 0
   m.insert(99991 if m.home(99991) == home0 else same[0], -1)   # recycles the tombstone
   m.check_invariants()
+
+
+# ---- the concurrent find-or-claim protocol under arbitrary interleavings -----------------------------------
+class _Agent(object):
+  """One 4-lane subgroup of warp_find_or_claim_t as a step machine: LOAD a bucket view, PROCESS it, CAS."""
+
+  def __init__(self, model, key, prefetched):
+    self.m, self.key = model, key
+    self.b0 = model.home(key)
+    self.b, self.first_free, self.ff_tomb, self.probes = self.b0, -1, False, 0
+    self.view = prefetched          # first-bucket view taken before ANY agent ran (the up-front loads)
+    self.state = "PROCESS" if prefetched is not None else "LOAD"
+    self.result = None              # ("found"|"new", slot)
+
+  def _snapshot(self, b):
+    return list(self.m.keys[b * 8:(b + 1) * 8])
+
+  def step(self):
+    m = self.m
+    if self.state == "LOAD":
+      self.view = self._snapshot(self.b)
+      self.state = "PROCESS"
+    elif self.state == "PROCESS":
+      v = self.view
+      if self.key in v:
+        self.result = ("found", self.b * 8 + v.index(self.key))
+        self.state = "DONE"
+        return
+      free = [i for i, k in enumerate(v) if k in (EMPTY, TOMB)]
+      if self.first_free < 0 and free:
+        self.first_free = self.b * 8 + free[0]
+        self.ff_tomb = v[free[0]] == TOMB
+      self.probes += 1
+      if EMPTY in v or self.probes >= m.nb:
+        assert self.first_free >= 0, "table full"
+        self.state = "CAS"
+      else:
+        self.b = (self.b + 1) % m.nb
+        self.state = "LOAD"
+    elif self.state == "CAS":
+      expect = TOMB if self.ff_tomb else EMPTY
+      old = m.keys[self.first_free]
+      if old == expect:
+        m.keys[self.first_free] = self.key      # atomicCAS succeeded
+        self.result = ("new", self.first_free)
+        self.state = "DONE"
+      elif old == self.key:
+        self.result = ("found", self.first_free)
+        self.state = "DONE"
+      else:                                      # slot taken by another key: rescan with fresh loads
+        self.b, self.first_free, self.ff_tomb, self.probes = self.b0, -1, False, 0
+        self.state = "LOAD"
+
+
+def _interleave(seed, nb, n_resident, batch_keys, stale_prefetch):
+  rng = np.random.default_rng(seed)
+  m = LayoutModel(nb)
+  resident = list(rng.choice(np.arange(1000, 1000 + 4 * nb * 8), size=n_resident, replace=False))
+  for k in resident:
+    m.insert(int(k), 0)
+  for k in resident[::3]:                        # leave tombstones / freed slots behind
+    m.remove(int(k))
+  before = {k for k in m.keys if k not in (EMPTY, TOMB)}
+  agents = []
+  for k in batch_keys:
+    pre = list(m.keys[m.home(k) * 8:(m.home(k) + 1) * 8]) if stale_prefetch else None
+    agents.append(_Agent(m, int(k), pre))
+  live = list(agents)
+  while live:
+    a = live[int(rng.integers(len(live)))]
+    a.step()
+    if a.state == "DONE":
+      live.remove(a)
+  stored = [k for k in m.keys if k not in (EMPTY, TOMB)]
+  assert len(stored) == len(set(stored)), "a key was inserted twice"
+  for k in set(int(x) for x in batch_keys):
+    news = [a for a in agents if a.key == k and a.result[0] == "new"]
+    assert len(news) == (0 if k in before else 1), (k, len(news))
+    slots = {a.result[1] for a in agents if a.key == k}
+    assert len(slots) == 1 and m.keys[next(iter(slots))] == k     # every duplicate resolved to THE slot of k
+  assert set(stored) == before | set(int(x) for x in batch_keys)
+
+
+@pytest.mark.parametrize("stale_prefetch", [False, True])
+def test_find_or_claim_protocol_interleavings(stale_prefetch):
+  """Random schedules of many subgroups claiming slots in few buckets, with duplicate keys in the batch, recycled
+  tombstones and (stale_prefetch) first-bucket views loaded before any claim: never a duplicate slot, exactly one
+  'new' per absent key, and every duplicate of a key ends on the same slot."""
+  for seed in range(120):
+    rng = np.random.default_rng(10_000 + seed)
+    nb = int(rng.integers(2, 5))
+    n_res = int(rng.integers(0, nb * 8 * 0.5))
+    room = int(nb * 8 * 0.75) - n_res
+    n_new = int(rng.integers(1, max(2, room)))
+    fresh = rng.choice(np.arange(0, 900), size=n_new, replace=False)
+    dup = rng.choice(fresh, size=int(rng.integers(0, n_new + 1)))          # duplicates inside the batch
+    batch = np.concatenate([fresh, dup])
+    rng.shuffle(batch)
+    _interleave(seed, nb, n_res, batch, stale_prefetch)
