@@ -170,3 +170,59 @@ def test_find_or_claim_protocol_interleavings(stale_prefetch):
     batch = np.concatenate([fresh, dup])
     rng.shuffle(batch)
     _interleave(seed, nb, n_res, batch, stale_prefetch)
+
+
+class _RemoveAgent(object):
+  """remove_kernel for one key: probe (read-only scan), re-read the key's bucket, CAS key -> EMPTY | TOMB."""
+
+  def __init__(self, model, key):
+    self.m, self.key = model, key
+    self.b, self.probes = model.home(key), 0
+    self.state, self.slot, self.removed = "SCAN", -1, False
+
+  def step(self):
+    m = self.m
+    if self.state == "SCAN":
+      v = list(m.keys[self.b * 8:(self.b + 1) * 8])
+      if self.key in v:
+        self.slot = self.b * 8 + v.index(self.key)
+        self.state = "REREAD"
+      elif EMPTY in v or self.probes + 1 >= m.nb:
+        self.state = "DONE"
+      else:
+        self.probes += 1
+        self.b = (self.b + 1) % m.nb
+    elif self.state == "REREAD":
+      lo = (self.slot // 8) * 8
+      self.has_empty = EMPTY in list(m.keys[lo:lo + 8])
+      self.state = "CAS"
+    elif self.state == "CAS":
+      if m.keys[self.slot] == self.key:
+        m.keys[self.slot] = EMPTY if self.has_empty else TOMB
+        self.removed = True
+      self.state = "DONE"
+
+
+def test_concurrent_removes_keep_every_survivor_reachable():
+  for seed in range(150):
+    rng = np.random.default_rng(seed)
+    nb = int(rng.integers(2, 6))
+    m = LayoutModel(nb)
+    keys = [int(k) for k in rng.choice(np.arange(0, 5000), size=int(nb * 8 * 0.75), replace=False)]
+    for k in keys:
+      m.insert(k, k)
+    victims = [keys[i] for i in rng.choice(len(keys), size=len(keys) // 2, replace=False)]
+    batch = victims + [victims[i] for i in rng.integers(0, len(victims), size=3)] + [7777, 8888]   # dups + absent keys
+    agents = [_RemoveAgent(m, k) for k in batch]
+    live = list(agents)
+    while live:
+      a = live[int(rng.integers(len(live)))]
+      a.step()
+      if a.state == "DONE":
+        live.remove(a)
+    survivors = set(keys) - set(victims)
+    for k in victims:
+      assert sum(a.removed for a in agents if a.key == k) == 1      # exactly one duplicate wins the CAS
+      assert m.find(k) < 0
+    for k in survivors:
+      assert m.find(k) >= 0 and m.keys[m.find(k)] == k              # no chain was cut by an erase-to-EMPTY
