@@ -73,9 +73,26 @@ typedef struct det_config {
   int32_t num_slot_planes;  /* 0..3 optimizer slot planes co-indexed with the value rows (fp32 only) */
   uint64_t init_capacity;   /* keys; 0 -> 8192 (TF_HASHTABLE_INIT_SIZE default, cuckoo_hashtable_op.cc:199-205) */
   uint64_t max_capacity;    /* keys; 0 -> grow without bound (cuckoo semantics); else DET_TABLE_FULL beyond it */
-  float max_load_factor;    /* 0 -> 0.75 */
-  uint32_t flags;           /* reserved, 0 */
+  float max_load_factor;    /* 0 -> 0.75 (0.875 with an eviction strategy) */
+  uint32_t flags;           /* bits 0..3: eviction strategy + 1 (DET_FLAGS_EVICT), 0 = none; other bits reserved, 0 */
 } det_config;
+
+/* Eviction strategies of the HKV table (python/ops/hkv_hashtable_ops.py HkvEvictStrategy; kernels/lookup_impl/
+ * lookup_table_op_hkv.h:454-479).  With a strategy the table keeps a uint64 SCORE per key and, once it holds
+ * max_load_factor * max_capacity keys, evicts the lowest-scored keys to make room instead of failing with
+ * DET_TABLE_FULL (DESIGN.md "capacity management").  Score of a key after insert / assign / accum:
+ *   LRU  device clock (ns)      EPOCHLRU  epoch << 32 | low32(clock >> 20)
+ *   LFU  old + delta            EPOCHLFU  epoch << 32 | min(low32(old) + delta, 2^32 - 1)     (delta: `scores`, default 1)
+ *   CUSTOMIZED  the score the caller provides. */
+enum {
+  DET_EVICT_NONE = -1,
+  DET_EVICT_LRU = 0,
+  DET_EVICT_LFU = 1,
+  DET_EVICT_EPOCHLRU = 2,
+  DET_EVICT_EPOCHLFU = 3,
+  DET_EVICT_CUSTOMIZED = 4
+};
+#define DET_FLAGS_EVICT(strategy) ((uint32_t)((strategy) + 1) & 0xFu)
 
 /* ---- lifetime: HashTableOp::Compute / LookupOrCreate, kernels/cuckoo_hashtable_op.h:59-110 ---- */
 det_status det_table_create(det_table** out, const det_config* cfg);
@@ -133,6 +150,22 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
 /* ImportValues = clear + insert (cuckoo_hashtable_op.cc:288-291). */
 det_status det_import(det_table* t, const int64_t* keys, const void* values, size_t n,
                       det_stream_t stream);
+
+/* ---- tables with an eviction strategy: the `scores` input of the HKV ops (ops/hkv_hashtable_ops.cc:191-219),
+ * ExportWithScores / ExportKeysAndScores (:259-294), set_global_epoch (lookup_table_op_hkv.h:499-507) ----
+ * det_insert / det_accum / det_apply_* on such a table behave as if scores == NULL.
+ * scores: DEVICE uint64[n] or NULL.  A key that is not in the table is refused (not inserted) when the table is at
+ * its limit and the key's score is below every resident score (HKV: below its bucket's minimum). */
+det_status det_insert_scored(det_table* t, const int64_t* keys, const void* values, const uint64_t* scores, size_t n,
+                             det_stream_t stream);
+det_status det_accum_scored(det_table* t, const int64_t* keys, const void* values_or_deltas, const uint8_t* exists,
+                            const uint64_t* scores, size_t n, det_stream_t stream);
+/* scores_out[i] = score of keys[i], 0 when absent (export_with_scores = det_export + det_find_scores of its keys) */
+det_status det_find_scores(det_table* t, const int64_t* keys, size_t n, uint64_t* scores_out, det_stream_t stream);
+det_status det_set_global_epoch(det_table* t, uint64_t epoch);
+/* Evict the n_evict lowest-scored keys now (what the reference's restrict policies do with a side table and a
+ * top-k, python/ops/restrict_policies.py:118-361).  *n_evicted_out_host may be NULL.  Synchronises `stream`. */
+det_status det_evict(det_table* t, uint64_t n_evict, int64_t* n_evicted_out_host, det_stream_t stream);
 
 /* ---- fused entry points (replace chains of reference ops) ---- */
 
@@ -256,6 +289,9 @@ typedef struct det_stats {
   uint64_t hbm_bytes;  /* device bytes held by the table */
   uint32_t error_flags;
   uint32_t rehash_count;
+  uint32_t evict_events;  /* eviction events so far (ABI >= 2) */
+  uint32_t reserved;
+  uint64_t evicted_keys;  /* keys evicted so far */
 } det_stats;
 det_status det_get_stats(det_table* t, det_stats* out_host, det_stream_t stream);
 

@@ -12,6 +12,12 @@ _i = ctypes.c_int
 DET_OK = 0
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
+# HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
+EVICT_STRATEGIES = {"LRU": 0, "LFU": 1, "EPOCHLRU": 2, "EPOCHLFU": 3, "CUSTOMIZED": 4}
+
+
+def flags_evict(strategy):
+  return (int(strategy) + 1) & 0xF
 
 
 class DetConfig(ctypes.Structure):
@@ -24,7 +30,8 @@ class DetConfig(ctypes.Structure):
 class DetStats(ctypes.Structure):
   _fields_ = [("size", ctypes.c_int64), ("used_slots", ctypes.c_int64), ("capacity", ctypes.c_uint64),
               ("buckets", ctypes.c_uint64), ("hbm_bytes", ctypes.c_uint64), ("error_flags", ctypes.c_uint32),
-              ("rehash_count", ctypes.c_uint32)]
+              ("rehash_count", ctypes.c_uint32), ("evict_events", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+              ("evicted_keys", ctypes.c_uint64)]
 
 
 # name -> (restype, argtypes); must list EVERY function include/detable.h declares
@@ -77,6 +84,11 @@ SIGNATURES = {
     "det_save": (_i, [_vp, ctypes.c_char_p, _sz]),
     "det_load": (_i, [_vp, ctypes.c_char_p, _sz]),
     "det_get_stats": (_i, [_vp, ctypes.POINTER(DetStats), _vp]),
+    "det_insert_scored": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "det_accum_scored": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "det_find_scores": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "det_set_global_epoch": (_i, [_vp, ctypes.c_uint64]),
+    "det_evict": (_i, [_vp, ctypes.c_uint64, ctypes.POINTER(ctypes.c_int64), _vp]),
 }
 
 _LIB = None

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libdetable.so")
-SOURCES = ["table.cu", "fused.cu", "host_api.cu", "sharded.cu"]
+SOURCES = ["table.cu", "fused.cu", "host_api.cu", "sharded.cu", "evict.cu"]
 HEADERS = ["common.cuh", "host.h", os.path.join("..", "..", "include", "detable.h")]
 
 NVCC_FLAGS = [

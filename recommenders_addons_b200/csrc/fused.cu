@@ -871,6 +871,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
     }
     CUDA_TRY(cudaGetLastError());
     note_mutation(t, n, s);
+    if (t->ev) return evict_touch(t, k, nullptr, n, s);
     return DET_OK;
   }
 #define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
@@ -889,6 +890,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
 #undef DET_LAUNCH_APPLY
   CUDA_TRY(cudaGetLastError());
   note_mutation(t, n, s);
+  if (t->ev) return evict_touch(t, k, nullptr, n, s);
   return DET_OK;
 }
 

@@ -72,7 +72,8 @@ struct DevGuard {
   DevGuard& operator=(const DevGuard&) = delete;
 };
 
-struct HostPipe;  // chunked H2D -> kernel -> D2H pipeline state (host_api.cu)
+struct HostPipe;    // chunked H2D -> kernel -> D2H pipeline state (host_api.cu)
+struct EvictState;  // score plane + eviction bookkeeping of a table with an eviction strategy (evict.cu)
 
 size_t dtype_size(int dt);
 RowGeom make_geom(unsigned row_bytes, int vec);
@@ -105,6 +106,8 @@ struct det_table {
   size_t scratch_bytes = 0;
   bool external = false;             // planes live in a caller-provided region (not owned, fixed capacity)
   unsigned long long* peer_bar = nullptr;  // arrival flags of the NVLink peer barrier (sharded.cu)
+  det::EvictState* ev = nullptr;     // non-null: the table has an eviction strategy (evict.cu)
+  uint64_t last_used_snap = 0;       // last exact value of DevState::used the host has seen (snapshot or sync read)
 };
 
 namespace det {
@@ -122,4 +125,17 @@ det_status table_clear_async(det_table* t, cudaStream_t s);
 // stream-ordered users only (one stream per table at a time); grows with a sync, never shrinks
 det_status table_scratch(det_table* t, size_t bytes, void** out);
 void host_pipe_free(det_table* t);
+det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s);
+// evict.cu (all called with t->mu held, except evict_insert which takes it)
+det_status evict_attach(det_table* t, int strategy);
+void evict_free(det_table* t);
+bool evict_at_max(const det_table* t);
+det_status evict_room(det_table* t, const long long* keys_or_null, size_t n, cudaStream_t s);
+det_status evict_on_rehash(det_table* t, const TableView& ov, const TableView& nv, cudaStream_t s);
+void evict_on_clear(det_table* t, cudaStream_t s);
+det_status evict_before_remove(det_table* t, const long long* keys, size_t n, cudaStream_t s);
+det_status evict_touch(det_table* t, const long long* keys, const unsigned long long* scores, size_t n, cudaStream_t s);
+det_status evict_insert(det_table* t, const int64_t* keys, const void* values, const uint64_t* scores, size_t n,
+                        cudaStream_t s);
+void evict_stats(const det_table* t, uint32_t* events, uint64_t* evicted);
 }  // namespace det

@@ -219,6 +219,20 @@ static det_status insert_host_impl(det_table* t, const int64_t* keys, const void
   const bool pin_k = is_pinned(keys), pin_v = is_pinned(values);
   if (!wait && !(pin_k && pin_v))
     return fail(DET_INVALID_ARGUMENT, "det_insert_host_async: all host buffers must be pinned (page-locked)");
+  if (t->ev) {
+    // table with an eviction strategy: room is made chunk by chunk (eviction events synchronise), so the chunks go
+    // through the device entry point one after the other on one stream
+    cudaStream_t s = p->streams[0];
+    for (size_t off = 0; off < n; off += ck) {
+      const size_t m = (n - off < ck) ? n - off : ck;
+      CUDA_TRY(cudaMemcpyAsync(p->d_keys[0], (const long long*)keys + off, m * 8, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(p->d_vals[0], (const unsigned char*)values + off * rb, m * rb, cudaMemcpyHostToDevice, s));
+      st = det::evict_insert(t, (const int64_t*)p->d_keys[0], p->d_vals[0], nullptr, m, s);
+      if (st != DET_OK) return st;
+      CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return DET_OK;
+  }
   // growth (if any) must happen before the chunks are in flight on several streams
   {
     std::lock_guard<std::mutex> _lk(t->mu);

@@ -676,6 +676,7 @@ det_status table_clear_async(det_table* t, cudaStream_t s) {
   reset_state_kernel<<<1, 1, 0, s>>>(t->view.st);
   CUDA_TRY(cudaGetLastError());
   t->used_ub = 0;
+  if (t->ev) evict_on_clear(t, s);
   return DET_OK;
 }
 
@@ -697,7 +698,7 @@ static det_status read_state(det_table* t, cudaStream_t s, DevState* out) {
   return DET_OK;
 }
 
-static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
+det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
   if (t->external) return fail(DET_TABLE_FULL, "detable: a table living in a caller-provided region cannot grow");
   TableView nv;
   void* raw[1 + kMaxPlanes];
@@ -723,6 +724,10 @@ static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
   }
   rehash_fix_state_kernel<<<1, 1, 0, s>>>(t->view.st);
   CUDA_TRY(cudaGetLastError());
+  if (t->ev) {  // scores follow their keys into the new planes
+    st = evict_on_rehash(t, ov, nv, s);
+    if (st != DET_OK) return st;
+  }
   // the old planes are freed below: nothing on ANY stream may still be reading them (async host pipelines)
   CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 1 + kMaxPlanes; ++i)
@@ -742,10 +747,13 @@ static det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
 det_status ensure_room(det_table* t, const long long* keys, size_t n, cudaStream_t s) {
   if (t->snap_inflight && cudaEventQuery(t->snap_ev) == cudaSuccess) {
     t->used_ub = *t->h_used_snap + t->n_since_snap;
+    t->last_used_snap = *t->h_used_snap;
     t->snap_inflight = false;
   } else {
     cudaGetLastError();  // cudaErrorNotReady is expected
   }
+  // a table with an eviction strategy that has reached max_capacity makes room by evicting (evict.cu)
+  if (t->ev && evict_at_max(t)) return evict_room(t, keys, n, s);
   const double cap = (double)t->view.capacity();
   const uint64_t limit = (uint64_t)(cap * t->max_lf);
   if (t->used_ub + n <= limit) {
@@ -787,9 +795,19 @@ det_status ensure_room(det_table* t, const long long* keys, size_t n, cudaStream
   if (t->cfg.max_capacity) {
     const uint64_t max_nb = (t->cfg.max_capacity + kBucket - 1) / kBucket;
     if (nb > max_nb) nb = max_nb;
-    if ((double)need > (double)(nb * kBucket) * t->max_lf)
-      return fail(DET_TABLE_FULL, "detable: max_capacity reached (" + std::to_string(t->cfg.max_capacity) +
-                                      " slots); " + std::to_string(need) + " keys do not fit");
+    if ((double)need > (double)(nb * kBucket) * t->max_lf) {
+      if (!t->ev)
+        return fail(DET_TABLE_FULL, "detable: max_capacity reached (" + std::to_string(t->cfg.max_capacity) +
+                                        " slots); " + std::to_string(need) + " keys do not fit");
+      // eviction strategy: grow to the maximum first, then evict the lowest-scored keys
+      if (nb != t->view.nb) {
+        st = rehash_to(t, nb, s);
+        if (st != DET_OK) return st;
+        t->used_ub = live;
+        t->last_used_snap = live;
+      }
+      return evict_room(t, keys, n, s);
+    }
   }
   st = rehash_to(t, nb, s);
   if (st != DET_OK) return st;
@@ -878,7 +896,7 @@ using namespace det;
 
 extern "C" {
 
-int det_abi_version(void) { return 1; }
+int det_abi_version(void) { return 2; }
 
 const char* det_build_info(void) {
   return "detable sm_100a; nvcc " __DATE__ " " __TIME__ "; 8-slot buckets; 4-lane subgroup probing";
@@ -932,7 +950,8 @@ static det_status create_common(det_table** out, const det_config* cfg, void* re
   det_table* t = new det_table();
   t->cfg = *cfg;
   t->row_bytes = es * (size_t)cfg->dim;
-  t->max_lf = cfg->max_load_factor > 0.f ? cfg->max_load_factor : 0.75f;
+  const int evict_strategy = (int)(cfg->flags & 0xFu) - 1;  // DET_FLAGS_EVICT
+  t->max_lf = cfg->max_load_factor > 0.f ? cfg->max_load_factor : (evict_strategy >= 0 ? 0.875f : 0.75f);
   if (t->max_lf > 0.9f) t->max_lf = 0.9f;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -988,6 +1007,7 @@ static det_status create_common(det_table** out, const det_config* cfg, void* re
     t->view.dim = (unsigned)cfg->dim;
     if (cudaMemset(base + L.off_bar, 0, 256) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_table_create_in_region: memset failed");
   }
+  if (st == DET_OK && evict_strategy >= 0) st = evict_attach(t, evict_strategy);
   if (st == DET_OK) st = table_clear_async(t, 0);
   if (st == DET_OK && cudaStreamSynchronize(0) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_table_create: init failed");
   if (st != DET_OK) {
@@ -1031,6 +1051,7 @@ det_status det_table_destroy(det_table* t) {
   if (t->snap_ev) cudaEventDestroy(t->snap_ev);
   if (t->scratch) cudaFree(t->scratch);
   host_pipe_free(t);
+  evict_free(t);
   delete t;
   return DET_OK;
 }
@@ -1066,6 +1087,7 @@ det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* def
 }
 
 det_status det_insert(det_table* t, const int64_t* keys, const void* values, size_t n, det_stream_t stream) {
+  if (t && t->ev) return det::evict_insert(t, keys, values, nullptr, n, (cudaStream_t)stream);
   return det::insert_impl(t, keys, values, n, (cudaStream_t)stream, true);
 }
 
@@ -1107,9 +1129,10 @@ det_status insert_impl(det_table* t, const int64_t* keys, const void* values, si
 
 extern "C" {
 
-det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists, size_t n,
-                     det_stream_t stream) {
+static det_status accum_impl(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists,
+                             const uint64_t* scores, size_t n, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_accum: null table");
+  if (scores && !t->ev) return fail(DET_INVALID_ARGUMENT, "det_accum_scored: the table was created without an eviction strategy");
   std::lock_guard<std::mutex> _lk(t->mu);
   if (n == 0) return DET_OK;
   if (!keys || !vod || !exists) return fail(DET_INVALID_ARGUMENT, "det_accum: null keys/values_or_deltas/exists");
@@ -1137,7 +1160,18 @@ det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const u
   if (st != DET_OK) return st;
   CUDA_TRY(cudaGetLastError());
   note_mutation(t, n, s);
+  if (t->ev) return evict_touch(t, k, (const unsigned long long*)scores, n, s);
   return DET_OK;
+}
+
+det_status det_accum(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists, size_t n,
+                     det_stream_t stream) {
+  return accum_impl(t, keys, vod, exists, nullptr, n, stream);
+}
+
+det_status det_accum_scored(det_table* t, const int64_t* keys, const void* vod, const uint8_t* exists,
+                            const uint64_t* scores, size_t n, det_stream_t stream) {
+  return accum_impl(t, keys, vod, exists, scores, n, stream);
 }
 
 det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t stream) {
@@ -1147,6 +1181,10 @@ det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t 
   if (!keys) return fail(DET_INVALID_ARGUMENT, "det_remove: null keys");
   cudaStream_t s = (cudaStream_t)stream;
   det::DevGuard _dg(t->cfg.device);
+  if (t->ev) {  // a free slot always carries score 0
+    det_status est = evict_before_remove(t, (const long long*)keys, n, s);
+    if (est != DET_OK) return est;
+  }
   remove_kernel<<<grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s>>>(t->view, (const long long*)keys, n);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
@@ -1258,6 +1296,8 @@ det_status det_get_stats(det_table* t, det_stats* out, det_stream_t stream) {
   out->hbm_bytes = planes_bytes(t, t->view.nb);
   out->error_flags = ds.error;
   out->rehash_count = t->rehash_count;
+  out->reserved = 0;
+  evict_stats(t, &out->evict_events, &out->evicted_keys);
   return DET_OK;
 }
 

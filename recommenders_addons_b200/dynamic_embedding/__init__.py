@@ -1,6 +1,6 @@
 """Mirror of the reference's `tfra.dynamic_embedding` export list for the hot path
 (/root/reference/tensorflow_recommenders_addons/dynamic_embedding/__init__.py:17-53)."""
-from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreator, HkvHashTable,
+from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreator, HkvEvictStrategy, HkvHashTable,
                     HkvHashTableConfig, HkvHashTableCreator, KVCreator)
 from .variable import (Variable, default_partition_fn, embedding_lookup, embedding_lookup_unique,
                        get_variable, unique)
@@ -10,7 +10,7 @@ from .sharded import PeerShardedVariable, ShardedVariable
 from . import layers
 
 __all__ = [
-    "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvHashTable", "HkvHashTableConfig",
+    "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvEvictStrategy", "HkvHashTable", "HkvHashTableConfig",
     "HkvHashTableCreator", "KVCreator", "Variable", "default_partition_fn", "embedding_lookup",
     "embedding_lookup_unique", "get_variable", "unique", "SparseIds", "embedding_lookup_sparse",
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",

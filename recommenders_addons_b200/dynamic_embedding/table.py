@@ -7,6 +7,7 @@ TypeError on dtype mismatch ("Signature mismatch. Keys must be dtype ..."), DetE
 failures (the reference raises tf.errors.* through OP_REQUIRES_OK).
 """
 import ctypes
+import enum
 import os
 
 import torch
@@ -49,8 +50,22 @@ class CuckooHashTableConfig(object):
     pass
 
 
+@enum.unique
+class HkvEvictStrategy(enum.IntEnum):
+  """python/ops/dynamic_embedding_creator.py:140-146"""
+  LRU = 0
+  LFU = 1
+  EPOCHLRU = 2
+  EPOCHLFU = 3
+  CUSTOMIZED = 4
+
+
 class HkvHashTableConfig(object):
-  """python/ops/dynamic_embedding_creator.py:140-170 (capacity attributes of the HKV ops)."""
+  """python/ops/dynamic_embedding_creator.py:149-170 (capacity attributes of the HKV ops).
+
+  evict_strategy=None (the default HERE; the reference defaults to LRU): the table grows without bound and never
+  evicts.  With a strategy the table is bounded by max_capacity slots and evicts its lowest-scored keys
+  (csrc/evict.cu)."""
 
   def __init__(self, init_capacity=1024 * 1024, max_capacity=1024 * 1024, max_hbm_for_values=1024 * 1024 * 1024,
                evict_strategy=None, step_per_epoch=0, gen_scores_fn=None, reserved_key_start_bit=0):
@@ -69,7 +84,7 @@ class CuckooHashTable(object):
 
   def __init__(self, key_dtype, value_dtype, default_value, name="CuckooHashTable", checkpoint=True, init_size=0,
                config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0, max_capacity=0,
-               max_load_factor=0.0, region=None):
+               max_load_factor=0.0, region=None, evict_strategy=None):
     if key_dtype != torch.int64:
       raise TypeError("key dtype %s is not supported on GPU: keys must be int64" % (key_dtype,))
     if value_dtype not in _TORCH_TO_NAME:
@@ -99,7 +114,8 @@ class CuckooHashTable(object):
     cfg.init_capacity = self._init_size
     cfg.max_capacity = int(max_capacity)
     cfg.max_load_factor = float(max_load_factor)
-    cfg.flags = 0
+    cfg.flags = 0 if evict_strategy is None else _lib.flags_evict(int(evict_strategy))
+    self._evict_strategy = evict_strategy
     self._lib = _lib.lib()
     h = ctypes.c_void_p()
     self._region = region  # keeps the caller-provided memory alive (e.g. a symmetric-memory tensor)
@@ -299,14 +315,114 @@ class CuckooHashTable(object):
 
 
 class HkvHashTable(CuckooHashTable):
-  """python/ops/hkv_hashtable_ops.py: same LookupInterface, capacity taken from HkvHashTableConfig."""
+  """python/ops/hkv_hashtable_ops.py: same LookupInterface, capacity taken from HkvHashTableConfig.  With
+  config.evict_strategy the table is bounded by max_capacity and keeps a score per key (insert / accum take the
+  scores the reference's `_gen_scores` produces, :209-216; epochs advance like gpu::TableWrapper::upsert,
+  core/kernels/lookup_impl/lookup_table_op_hkv.h:519-535)."""
 
   def __init__(self, key_dtype, value_dtype, default_value, name="HkvHashTable", checkpoint=True, init_size=0,
                config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
     cfg = config if config is not None else HkvHashTableConfig()
-    super().__init__(key_dtype, value_dtype, default_value, name=name, checkpoint=checkpoint,
-                     init_size=cfg.init_capacity if cfg.init_capacity else init_size, config=cfg, device=device,
-                     num_slot_planes=num_slot_planes, max_capacity=0, max_load_factor=0.0)
+    strategy = cfg.evict_strategy
+    if strategy is not None:
+      strategy = HkvEvictStrategy(int(strategy))
+    init = cfg.init_capacity if cfg.init_capacity else init_size
+    if strategy is not None and cfg.max_capacity:
+      init = min(int(init) if init else int(cfg.max_capacity), int(cfg.max_capacity))
+    super().__init__(key_dtype, value_dtype, default_value, name=name, checkpoint=checkpoint, init_size=init, config=cfg,
+                     device=device, num_slot_planes=num_slot_planes,
+                     max_capacity=int(cfg.max_capacity) if strategy is not None else 0, max_load_factor=0.0,
+                     evict_strategy=strategy)
+    self._step_per_epoch = int(cfg.step_per_epoch or 0)
+    self._gen_scores_fn = cfg.gen_scores_fn
+    self._curr_epoch, self._curr_step = 0, 1
+
+  @property
+  def evict_strategy(self):
+    return self._evict_strategy
+
+  def _gen_scores(self, keys):
+    """hkv_hashtable_ops.py:209-216: CUSTOMIZED -> gen_scores_fn(keys); LFU / EPOCHLFU -> ones; else none"""
+    st = self._evict_strategy
+    if st == HkvEvictStrategy.CUSTOMIZED:
+      assert self._gen_scores_fn is not None, "You must set gen_scores_fn when set evict strategy to CUSTOMIZED"
+      sc = self._gen_scores_fn(keys)
+      if not torch.is_tensor(sc):
+        sc = torch.as_tensor(sc)
+      sc = sc.to(device=self._device, dtype=torch.int64).contiguous().reshape(-1)
+      if sc.numel() != keys.numel():
+        raise ValueError("gen_scores_fn must return one score per key")
+      return sc
+    if st in (HkvEvictStrategy.LFU, HkvEvictStrategy.EPOCHLFU):
+      return torch.ones(keys.numel(), dtype=torch.int64, device=self._device)
+    return None
+
+  def _step_epoch(self):
+    if self._evict_strategy in (HkvEvictStrategy.EPOCHLRU, HkvEvictStrategy.EPOCHLFU):
+      self._curr_step += 1
+      if self._curr_step > self._step_per_epoch:
+        self._curr_epoch += 1
+        self._curr_step = 1
+        _lib.check(self._lib.det_set_global_epoch(self._h, self._curr_epoch))
+
+  def insert(self, keys, values, name=None):
+    if self._evict_strategy is None:
+      return super().insert(keys, values, name=name)
+    keys = self._check_keys(keys).reshape(-1)
+    values = self._check_values(values, keys.numel())
+    scores = self._gen_scores(keys)
+    _lib.check(self._lib.det_insert_scored(self._h, _ptr(keys), _ptr(values), _ptr(scores), keys.numel(),
+                                           _stream_ptr(self._device)))
+    self._step_epoch()
+
+  def accum(self, keys, values_or_deltas, exists, name=None):
+    if self._evict_strategy is None:
+      return super().accum(keys, values_or_deltas, exists, name=name)
+    keys = self._check_keys(keys).reshape(-1)
+    vod = self._check_values(values_or_deltas, keys.numel(), "values_or_deltas")
+    if not torch.is_tensor(exists):
+      exists = torch.as_tensor(exists, dtype=torch.bool)
+    if exists.dtype != torch.bool:
+      raise TypeError("Signature mismatch. exists must be dtype bool, got %s." % (exists.dtype,))
+    exists = exists.to(self._device).contiguous().reshape(-1)
+    if exists.numel() != keys.numel():
+      raise ValueError("exists must have the same shape as keys")
+    scores = self._gen_scores(keys)
+    _lib.check(self._lib.det_accum_scored(self._h, _ptr(keys), _ptr(vod), _ptr(exists), _ptr(scores), keys.numel(),
+                                          _stream_ptr(self._device)))
+
+  def _scores_of(self, keys):
+    scores = torch.empty(keys.numel(), dtype=torch.int64, device=self._device)
+    _lib.check(self._lib.det_find_scores(self._h, _ptr(keys), keys.numel(), _ptr(scores), _stream_ptr(self._device)))
+    return scores
+
+  def export_keys_and_scores(self, split_size, name=None):
+    """hkv_hashtable_ops.py:421-434 (split_size only bounds the reference's staging buffer)"""
+    if not (isinstance(split_size, int) and split_size > 0):
+      raise ValueError("split_size must be positive integer.")
+    if self._evict_strategy is None:
+      raise RuntimeError("the table was created without an eviction strategy: it keeps no scores")
+    n = int(self.size())
+    keys = torch.empty(n, dtype=torch.int64, device=self._device)
+    got = ctypes.c_int64(0)
+    _lib.check(self._lib.det_export(self._h, 0, _ptr(keys), None, n, ctypes.byref(got), _stream_ptr(self._device)))
+    keys = keys[:got.value]
+    return keys, self._scores_of(keys)
+
+  def export_with_scores(self, split_size, name=None):
+    """hkv_hashtable_ops.py:436-448"""
+    if not (isinstance(split_size, int) and split_size > 0):
+      raise ValueError("split_size must be positive integer.")
+    if self._evict_strategy is None:
+      raise RuntimeError("the table was created without an eviction strategy: it keeps no scores")
+    keys, values = self.export()
+    return keys, values, self._scores_of(keys)
+
+  def evict(self, n_evict):
+    """remove the n_evict lowest-scored keys now; returns how many went"""
+    got = ctypes.c_int64(0)
+    _lib.check(self._lib.det_evict(self._h, int(n_evict), ctypes.byref(got), _stream_ptr(self._device)))
+    return int(got.value)
 
 
 class CuckooHashTableCreator(KVCreator):

@@ -4,7 +4,7 @@ python/ops/dynamic_embedding_ops.py:64-117) on torch CUDA tensors over the C ABI
 import torch
 
 from .. import _lib
-from .table import CuckooHashTableCreator, KVCreator, _ptr, _stream_ptr
+from .table import CuckooHashTableCreator, HkvHashTableCreator, KVCreator, _ptr, _stream_ptr
 
 _VARIABLES = {}
 
@@ -225,6 +225,19 @@ class Variable(object):
   def export(self, name=None):
     ks, vs = zip(*[t.export() for t in self._tables])
     return torch.cat(ks, 0), torch.cat(vs, 0)
+
+  def export_keys_and_scores(self, split_size, name=None):
+    """dynamic_embedding_variable.py:1099-1112 (HKV tables with an eviction strategy only)"""
+    if not isinstance(self.kv_creator, HkvHashTableCreator):
+      raise TypeError("Only hkv HashTable support export_keys_and_scores")
+    ks, sc = zip(*[t.export_keys_and_scores(split_size=split_size, name=name) for t in self._tables])
+    return torch.cat(ks, 0), torch.cat(sc, 0)
+
+  def export_with_scores(self, split_size, name=None):
+    if not isinstance(self.kv_creator, HkvHashTableCreator):
+      raise TypeError("Only hkv HashTable support export_with_scores")
+    ks, vs, sc = zip(*[t.export_with_scores(split_size=split_size, name=name) for t in self._tables])
+    return torch.cat(ks, 0), torch.cat(vs, 0), torch.cat(sc, 0)
 
   def size(self, index=None, name=None):
     if index is not None:

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
   assert set(names) == set(_lib.SIGNATURES.keys()), set(names) ^ set(_lib.SIGNATURES.keys())
   for n in names:
     assert getattr(lib, n) is not None
-  assert lib.det_abi_version() == 1
+  assert lib.det_abi_version() == 2
   assert b"sm_100a" in lib.det_build_info()
 
 
@@ -112,3 +112,17 @@ def test_peer_and_region_entry_points_reject_bad_arguments_without_gpu():
   assert lib.det_peer_group_create_regions(ctypes.byref(h), None, None, 2, 0, 1) == 1
   assert lib.det_peer_route(None, None, None, 0, None) == 1
   assert lib.det_host_sync(None) == 1
+
+
+def test_scored_entry_points_reject_bad_arguments_without_gpu():
+  """the capacity-management entry points (det_insert_scored ...) validate their arguments before touching CUDA"""
+  from recommenders_addons_b200 import _lib
+  lib = _lib.lib()
+  assert lib.det_insert_scored(None, None, None, None, 0, None) == 1
+  assert lib.det_accum_scored(None, None, None, None, None, 0, None) == 1
+  assert lib.det_find_scores(None, None, 0, None, None) == 1
+  assert lib.det_set_global_epoch(None, 3) == 1
+  assert lib.det_evict(None, 1, None, None) == 1
+  assert b"null table" in lib.det_last_error()
+  assert _lib.flags_evict(_lib.EVICT_STRATEGIES["LRU"]) == 1 and _lib.flags_evict(-1) == 0
+  assert ctypes.sizeof(_lib.DetStats) == 64
