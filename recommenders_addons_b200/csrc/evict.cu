@@ -33,8 +33,8 @@ struct EvictDev {
   unsigned long long smin, smax, n_live;        // pass 1
   unsigned long long prefix, remaining;         // radix select: decided high bits / rank left inside the prefix
   unsigned long long n_new, n_adm;              // classify: keys of the batch not in the table / of those, admitted
-  unsigned long long tie_ticket, n_evicted, n_moved;
-  unsigned long long pad[6];
+  unsigned long long tie_ticket, n_evicted, n_moved, n_erased;
+  unsigned long long pad[5];
   unsigned int hist[kHistBins];
 };
 
@@ -193,6 +193,7 @@ __global__ void evict_reset_kernel(EvictDev* d) {
     d->tie_ticket = 0;
     d->n_evicted = 0;
     d->n_moved = 0;
+    d->n_erased = 0;
   }
 }
 
@@ -339,19 +340,26 @@ evict_apply_kernel(TableView t, unsigned long long* __restrict__ sc, EvictDev* d
   }
 }
 
-// One repair round: a live key is UNREACHABLE when a bucket between its home bucket and the bucket it sits in has an
-// EMPTY slot (a probe for it stops there).  Such a key is re-seated with the ordinary find-or-claim (first free
-// slot of its chain, which lies before its present slot), its rows / optimizer slots / score travel with it and the
-// old slot becomes EMPTY -- which may in turn cut chains further on: the host repeats rounds until nothing moves.
-// Stale views are harmless: a key judged unreachable that has become reachable again is FOUND by the claim probe
-// and left alone; a key that becomes unreachable after its check is caught by the next round.
+// Repair rounds.  A live key is UNREACHABLE when a bucket between its home bucket and the bucket it sits in has an
+// EMPTY slot (a probe for it stops there).  One round = two kernels, each of which changes the set of EMPTY slots in
+// ONE direction only, which is what makes the parallel pass safe without locks:
+//   repair_move_kernel   every unreachable key is COPIED (ordinary find-or-claim: first free slot of its chain,
+//                        which lies before its present slot; rows / optimizer slots / score travel along).  EMPTY
+//                        slots only disappear here, so a key that is reachable stays reachable -- in particular a
+//                        fresh copy is never picked up by another warp while its rows are still being written.
+//                        A key judged unreachable from a stale view is simply FOUND by the claim probe and skipped.
+//   repair_sweep_kernel  a displaced key that has an earlier match along its probe chain is a stale copy: its slot
+//                        goes back to EMPTY (score 0).  EMPTY slots only appear here; a probe cut short by one of
+//                        them reports "no earlier copy" and the stale copy survives until the next round.
+// Freed slots may cut chains further on: the host repeats rounds until one moves nothing and erases nothing.
 template <int VEC>
 __global__ void __launch_bounds__(kThreadsE)
-repair_kernel(TableView t, unsigned long long* __restrict__ sc, RowGeom g, RowGeom gslot, int n_planes, EvictDev* d) {
-  __shared__ unsigned s_moved, s_tomb;
+repair_move_kernel(TableView t, unsigned long long* __restrict__ sc, RowGeom g, RowGeom gslot, int n_planes,
+                   EvictDev* d) {
+  __shared__ unsigned s_moved, s_used;
   if (threadIdx.x == 0) {
     s_moved = 0;
-    s_tomb = 0;
+    s_used = 0;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -361,9 +369,8 @@ repair_kernel(TableView t, unsigned long long* __restrict__ sc, RowGeom g, RowGe
   for (size_t base = warp0 * 32; base < cap; base += nwarps * 32) {
     const size_t s = base + lane;
     const long long key = s < cap ? ld_key_cg(t.keys + s) : kEmptyKey;
-    const bool lv = live_key_e(key);
     bool need = false;
-    if (lv) {
+    if (live_key_e(key)) {
       const unsigned long long bs = s / kBucket;
       unsigned long long b = bucket_of(key, t.nb);
       while (b != bs) {
@@ -390,27 +397,47 @@ repair_kernel(TableView t, unsigned long long* __restrict__ sc, RowGeom g, RowGe
     for (int p = 1; p <= n_planes; ++p)
       warp_move_rows<4>(gslot, ok ? t.planes[p] + s * gslot.row_bytes : nullptr,
                         ok ? t.planes[p] + (size_t)ns * gslot.row_bytes : nullptr, lane);
-    if (ok) {
-      sc[ns] = sc[s];
-      sc[s] = 0ull;
-    }
-    // every lane has issued its row stores (their loads have therefore completed): the old slot may be reused now
-    __syncwarp();
-    if (ok) {
-      __threadfence();
-      st_key_cg(t.keys + s, kEmptyKey);
-    }
-    const unsigned bm = __ballot_sync(kFull, ok), bt = __ballot_sync(kFull, ok && !from_empty);
+    if (ok) sc[ns] = sc[s];
+    const unsigned bm = __ballot_sync(kFull, ok), bu = __ballot_sync(kFull, ok && from_empty);
     if (lane == 0 && bm) {
       atomicAdd(&s_moved, __popc(bm));
-      atomicAdd(&s_tomb, __popc(bt));
+      atomicAdd(&s_used, __popc(bu));
     }
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_moved) {
     atomicAdd(&d->n_moved, (unsigned long long)s_moved);
-    // a move consumes one EMPTY slot and frees one; a recycled tombstone lowers the number of non-EMPTY slots
-    if (s_tomb) atomicAdd(&t.st->used, (unsigned long long)(-(long long)s_tomb));
+    if (s_used) atomicAdd(&t.st->used, (unsigned long long)s_used);  // copies that consumed an EMPTY slot
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsE)
+repair_sweep_kernel(TableView t, unsigned long long* __restrict__ sc, EvictDev* d) {
+  __shared__ unsigned s_erased;
+  if (threadIdx.x == 0) s_erased = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t cap = t.capacity();
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsE + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsE) >> 5;
+  for (size_t base = warp0 * 32; base < cap; base += nwarps * 32) {
+    const size_t s = base + lane;
+    const long long key = s < cap ? ld_key_cg(t.keys + s) : kEmptyKey;
+    const bool displaced = live_key_e(key) && bucket_of(key, t.nb) != s / kBucket;
+    if (!__any_sync(kFull, displaced)) continue;
+    const long long first = warp_find_slots<true>(t, key, displaced, lane);  // first match along the chain
+    const bool stale = displaced && first >= 0 && (size_t)first != s;
+    if (stale) {
+      sc[s] = 0ull;
+      st_key_cg(t.keys + s, kEmptyKey);
+    }
+    const unsigned be = __ballot_sync(kFull, stale);
+    if (lane == 0 && be) atomicAdd(&s_erased, __popc(be));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_erased) {
+    atomicAdd(&d->n_erased, (unsigned long long)s_erased);
+    atomicAdd(&t.st->used, (unsigned long long)(-(long long)s_erased));
   }
 }
 
@@ -575,16 +602,17 @@ det_status evict_lowest(det_table* t, uint64_t k, cudaStream_t s) {
   const RowGeom gs = make_geom((unsigned)t->cfg.dim * 4u, 4);
   const int np = t->cfg.num_slot_planes;
   for (int round = 0; round < 256; ++round) {
-    CUDA_TRY(cudaMemsetAsync(&ev->dev->n_moved, 0, sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(&ev->dev->n_moved, 0, 2 * sizeof(unsigned long long), s));  // n_moved, n_erased
+    const int rgrid = grid_for(cap, kThreadsE, t->sm_count, 8);
     dispatch_vec_e(vec, [&](auto V) -> det_status {
-      repair_kernel<decltype(V)::value><<<grid_for(cap, kThreadsE, t->sm_count, 8), kThreadsE, 0, s>>>(v, ev->scores, g, gs, np,
-                                                                                                  ev->dev);
+      repair_move_kernel<decltype(V)::value><<<rgrid, kThreadsE, 0, s>>>(v, ev->scores, g, gs, np, ev->dev);
       return DET_OK;
     });
+    repair_sweep_kernel<<<rgrid, kThreadsE, 0, s>>>(v, ev->scores, ev->dev);
     CUDA_TRY(cudaGetLastError());
     st = read_dev(t, s);
     if (st != DET_OK) return st;
-    if (ev->h_dev->n_moved == 0) break;
+    if (ev->h_dev->n_moved == 0 && ev->h_dev->n_erased == 0) break;
   }
   ev->n_events++;
   ev->n_evicted += ev->h_dev->n_evicted;

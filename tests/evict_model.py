@@ -105,30 +105,46 @@ class EvictModel(LayoutModel):
     return True
 
   def repair_round(self, order=None):
-    """every live key that is no longer reachable along its probe chain is re-seated in the first free slot of
-    the chain (always closer to its home bucket), its old slot becomes EMPTY.  Returns the number of moves."""
-    moves = 0
-    slots = range(self.nb * BUCKET) if order is None else order
+    """one round = two passes, each changing the set of EMPTY slots in one direction only (the two kernels
+    repair_move_kernel / repair_sweep_kernel):
+      move : every unreachable key is COPIED to the first free slot of its chain (closer to home); EMPTY slots
+             only disappear, so reachable keys -- fresh copies included -- stay reachable during the pass
+      sweep: a displaced key that has an earlier match along its chain is a stale copy -> its slot becomes EMPTY
+    Returns moves + erasures."""
+    moves = erased = 0
+    slots = list(range(self.nb * BUCKET)) if order is None else list(order)
     for s in slots:
       k = self.keys[s]
       if k in (EMPTY, TOMB) or self.reachable(s):
         continue
-      first_free = -1
+      found, first_free = -1, -1
       for _, chain_slots in self._chain(k):
         for q in chain_slots:
-          assert self.keys[q] != k
+          if found < 0 and self.keys[q] == k:
+            found = q
           if first_free < 0 and self.keys[q] in (EMPTY, TOMB):
             first_free = q
+      if found >= 0:
+        continue          # another copy is reachable already
       assert first_free >= 0
-      if self.keys[first_free] == TOMB:
-        self.used -= 1   # a tombstone was recycled and an EMPTY slot appears where the key was
+      if self.keys[first_free] == EMPTY:
+        self.used += 1
       self.keys[first_free] = k
-      self.vals[first_free] = self.vals.pop(s)
+      self.vals[first_free] = self.vals[s]
       self.scores[first_free] = self.scores[s]
-      self.keys[s] = EMPTY
-      self.scores[s] = 0
       moves += 1
-    return moves
+    for s in slots:
+      k = self.keys[s]
+      if k in (EMPTY, TOMB) or self.home(k) == s // BUCKET:
+        continue
+      first = self.find(k)
+      if first >= 0 and first != s:
+        self.keys[s] = EMPTY
+        self.scores[s] = 0
+        self.vals.pop(s, None)
+        self.used -= 1
+        erased += 1
+    return moves + erased
 
   def repair(self):
     rounds = 0

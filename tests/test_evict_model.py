@@ -216,63 +216,103 @@ def test_invariants_under_random_streams(strategy, nb, ops):
 
 
 # ---- (3) the repair pass under random interleavings ------------------------------------------------------------
+def _probe_steps(m, key):
+  """generator: walks the probe chain of `key` one bucket per step (other threads run in between), yields None
+  while walking and finally ('done', first match or -1, first free slot or -1)"""
+  b = m.home(key)
+  found, first_free = -1, -1
+  for _ in range(m.nb):
+    lo = b * BUCKET
+    ks = [m.keys[q] for q in range(lo, lo + BUCKET)]       # one 64 B bucket load
+    for j, k in enumerate(ks):
+      if found < 0 and k == key:
+        found = lo + j
+      if first_free < 0 and k in (EMPTY, TOMB):
+        first_free = lo + j
+    if found >= 0 or EMPTY in ks:
+      break
+    b = (b + 1) % m.nb
+    yield None
+  yield ("done", found, first_free)
+
+
 def _interleaved_repair_round(m, rng):
-  """threads = displaced keys; each runs  check -> claim (CAS on the first free slot of its chain) -> copy -> erase
-  with arbitrary interleaving (the kernel: one lane per slot, claims via warp_find_or_claim)."""
-  threads = []
-  for s in range(m.nb * BUCKET):
-    k = m.keys[s]
-    if k not in (EMPTY, TOMB) and m.home(k) != s // BUCKET:
-      threads.append({"s": s, "k": k, "pc": 0, "dst": -1})
-  moves = 0
+  """the two kernels of a repair round with arbitrary interleaving of their threads (one thread per displaced key;
+  the kernels themselves are separated by a launch boundary).
+  move : check -> probe bucket by bucket -> CAS claim -> copy            (EMPTY slots only disappear)
+  sweep: probe bucket by bucket -> erase when an earlier match exists     (EMPTY slots only appear)"""
+  work = 0
+  threads = [{"s": s, "k": m.keys[s], "pc": 0} for s in range(m.nb * BUCKET)
+             if m.keys[s] not in (EMPTY, TOMB) and m.home(m.keys[s]) != s // BUCKET]
   live = list(range(len(threads)))
   while live:
     i = rng.choice(live)
     t = threads[i]
-    if t["pc"] == 0:     # reachability check (a snapshot that may be stale by the time of the claim)
-      t["pc"] = 1 if not m.reachable(t["s"]) else 9
-    elif t["pc"] == 1:   # find-or-claim along the chain with fresh loads
-      found, first_free = -1, -1
-      for _, chain_slots in m._chain(t["k"]):
-        for q in chain_slots:
-          if m.keys[q] == t["k"]:
-            found = q
-          if first_free < 0 and m.keys[q] in (EMPTY, TOMB):
-            first_free = q
-      if found >= 0:
-        t["pc"] = 9      # reachable again (somebody filled the gap): nothing to do
+    if t["pc"] == 0:
+      if m.reachable(t["s"]):
+        t["pc"] = 9
       else:
-        assert first_free >= 0
-        if m.keys[first_free] == TOMB:
-          m.used -= 1
-        m.keys[first_free] = t["k"]   # CAS succeeded (a failed CAS restarts this step)
-        t["dst"] = first_free
-        t["pc"] = 2
-    elif t["pc"] == 2:   # row + score copy
+        t["gen"] = _probe_steps(m, t["k"])
+        t["pc"] = 1
+    elif t["pc"] == 1:
+      r = next(t["gen"])
+      if r is not None:
+        _, found, first_free = r
+        if found >= 0:
+          t["pc"] = 9                      # reachable again, or a duplicate's mover got there first
+        else:
+          assert first_free >= 0
+          if m.keys[first_free] in (EMPTY, TOMB):   # the CAS
+            if m.keys[first_free] == EMPTY:
+              m.used += 1
+            m.keys[first_free] = t["k"]
+            t["dst"] = first_free
+            t["pc"] = 2
+          else:
+            t["gen"] = _probe_steps(m, t["k"])      # CAS lost: rescan the chain
+    elif t["pc"] == 2:
       m.vals[t["dst"]] = m.vals[t["s"]]
       m.scores[t["dst"]] = m.scores[t["s"]]
-      t["pc"] = 3
-    elif t["pc"] == 3:   # erase the old slot
-      m.keys[t["s"]] = EMPTY
-      m.scores[t["s"]] = 0
-      m.vals.pop(t["s"], None)
-      moves += 1
+      work += 1
       t["pc"] = 9
     if t["pc"] == 9:
       live.remove(i)
-  return moves
+  # ---- launch boundary ----
+  threads = [{"s": s, "k": m.keys[s], "gen": None} for s in range(m.nb * BUCKET)
+             if m.keys[s] not in (EMPTY, TOMB) and m.home(m.keys[s]) != s // BUCKET]
+  live = list(range(len(threads)))
+  while live:
+    i = rng.choice(live)
+    t = threads[i]
+    if t["gen"] is None:
+      t["gen"] = _probe_steps(m, t["k"])
+    r = next(t["gen"])
+    if r is None:
+      continue
+    _, found, _ff = r
+    if found >= 0 and found != t["s"]:
+      m.keys[t["s"]] = EMPTY
+      m.scores[t["s"]] = 0
+      m.vals.pop(t["s"], None)
+      m.used -= 1
+      work += 1
+    live.remove(i)
+  return work
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(24))
 def test_repair_under_random_interleavings(seed):
   rng = random.Random(seed)
-  m = EvictModel(48, CUSTOMIZED, max_lf=0.9)
+  m = EvictModel(rng.choice([8, 16, 48]), CUSTOMIZED, max_lf=rng.choice([0.8, 0.9, 0.95]))
   keys = rng.sample(range(1 << 40), m.limit)
   scores = [rng.randrange(0, 1000) for _ in keys]
   m.insert_scored(keys, [k ^ 5 for k in keys], scores)
+  if seed % 2:                       # user removes leave tombstones in full buckets: movers recycle them
+    for k in rng.sample(keys, len(keys) // 10):
+      m.remove(k)
   m.check_invariants()
   content = m.live()
-  k = len(keys) // 3
+  k = max(1, len(content) // rng.choice([2, 3, 10]))
   tau, quota = m.select_threshold(k)
   ev = m.evict_apply(tau, quota)
   for x in ev:
@@ -283,4 +323,5 @@ def test_repair_under_random_interleavings(seed):
     assert rounds < 64
   m.check_invariants()          # every key reachable again, stored once, free slots carry score 0
   assert m.live() == content    # nothing lost, rows travelled with their keys
-  assert m.used == m.size       # eviction leaves no tombstones behind
+  if not seed % 2:
+    assert m.used == m.size     # eviction leaves no tombstones behind
