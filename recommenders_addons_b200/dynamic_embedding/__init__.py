@@ -6,6 +6,7 @@ from .variable import (Variable, default_partition_fn, embedding_lookup, embeddi
                        get_variable, unique)
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
 from .optimizer import DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam
+from .restrict_policies import FrequencyRestrictPolicy, RestrictPolicy, TimestampRestrictPolicy
 from .sharded import PeerShardedVariable, ShardedVariable
 from . import layers
 
@@ -14,4 +15,5 @@ __all__ = [
     "HkvHashTableCreator", "KVCreator", "Variable", "default_partition_fn", "embedding_lookup",
     "embedding_lookup_unique", "get_variable", "unique", "SparseIds", "embedding_lookup_sparse",
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
+    "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy",
 ]

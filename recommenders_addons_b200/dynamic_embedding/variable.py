@@ -97,8 +97,6 @@ class Variable(object):
     self.kv_creator = kv_creator if kv_creator else CuckooHashTableCreator()
     if not isinstance(self.kv_creator, KVCreator):
       raise TypeError("config should be instance of 'config', but got %s" % type(self.kv_creator))
-    if restrict_policy is not None:
-      raise NotImplementedError("restrict policies are out of scope of the hot path (SURVEY.md 2, #20)")
     if key_dtype != torch.int64:
       raise TypeError("key-value dtype (%s-%s) is not support! keys must be int64 on GPU" % (key_dtype, value_dtype))
     static_default = self._convert_anything_to_init(initializer, self.dim)
@@ -109,6 +107,14 @@ class Variable(object):
                                  name=self._make_name(idx), checkpoint=checkpoint,
                                  init_size=int(self.init_size / self.shard_num), device=dev,
                                  num_slot_planes=num_slot_planes))
+    # dynamic_embedding_variable.py:604-611
+    if restrict_policy is not None:
+      from .restrict_policies import RestrictPolicy
+      if not (isinstance(restrict_policy, type) and issubclass(restrict_policy, RestrictPolicy)):
+        raise TypeError("restrict_policy must be subclass of RestrictPolicy.")
+      self._restrict_policy = restrict_policy(self)
+    else:
+      self._restrict_policy = None
 
   # dynamic_embedding_variable.py:712-766: any initializer -> one static default row [dim]
   def _convert_anything_to_init(self, raw_init, dim):
@@ -132,6 +138,16 @@ class Variable(object):
   @property
   def tables(self):
     return self._tables
+
+  @property
+  def restrict_policy(self):
+    return self._restrict_policy
+
+  def restrict(self, num_reserved, **kwargs):
+    """:857-873: shrink to `num_reserved` keys by the rule of the restrict policy (no-op without one)"""
+    if self._restrict_policy is not None:
+      return self._restrict_policy.apply_restriction(num_reserved, **kwargs)
+    return None
 
   def _partition(self, keys):
     """-> (grouped keys, perm or None, list of (begin, end) per shard)"""
