@@ -80,7 +80,8 @@ typedef struct det_config {
 /* Eviction strategies of the HKV table (python/ops/hkv_hashtable_ops.py HkvEvictStrategy; kernels/lookup_impl/
  * lookup_table_op_hkv.h:454-479).  With a strategy the table keeps a uint64 SCORE per key and, once it holds
  * max_load_factor * max_capacity keys, evicts the lowest-scored keys to make room instead of failing with
- * DET_TABLE_FULL (DESIGN.md "capacity management").  Score of a key after insert / assign / accum:
+ * DET_TABLE_FULL (DESIGN.md "capacity management"); with max_capacity == 0 it keeps the scores, grows without
+ * bound and only det_evict removes keys.  Score of a key after insert / assign / accum:
  *   LRU  device clock (ns)      EPOCHLRU  epoch << 32 | low32(clock >> 20)
  *   LFU  old + delta            EPOCHLFU  epoch << 32 | min(low32(old) + delta, 2^32 - 1)     (delta: `scores`, default 1)
  *   CUSTOMIZED  the score the caller provides. */

@@ -500,8 +500,6 @@ det_status evict_attach(det_table* t, int strategy) {
     return fail(DET_INVALID_ARGUMENT, "det_table_create: unknown eviction strategy in cfg.flags");
   if (t->external)
     return fail(DET_UNIMPLEMENTED, "det_table_create_in_region: eviction strategies are not available for tables in a caller-provided region");
-  if (t->cfg.max_capacity == 0)
-    return fail(DET_INVALID_ARGUMENT, "det_table_create: an eviction strategy needs max_capacity > 0");
   EvictState* ev = new EvictState();
   ev->strategy = strategy;
   const size_t n = t->view.capacity() + 2;
@@ -567,6 +565,7 @@ det_status evict_touch(det_table* t, const long long* keys, const unsigned long 
 }
 
 bool evict_at_max(const det_table* t) {
+  if (t->cfg.max_capacity == 0) return false;  // scores are kept, the table grows without bound: det_evict only
   const uint64_t max_nb = (t->cfg.max_capacity + kBucket - 1) / kBucket;
   return t->view.nb >= max_nb;
 }
@@ -699,8 +698,9 @@ det_status evict_insert(det_table* t, const int64_t* keys, const void* values, c
   if (ev->strategy == DET_EVICT_CUSTOMIZED && scores == nullptr)
     return fail(DET_INVALID_ARGUMENT, "det_insert: the CUSTOMIZED eviction strategy needs scores (det_insert_scored)");
   det::DevGuard _dg(t->cfg.device);
+  // a launch never brings more new keys than a quarter of what the table may hold (room is made per launch)
   const uint64_t max_cap = ((t->cfg.max_capacity + kBucket - 1) / kBucket) * kBucket;
-  uint64_t chunk = (uint64_t)((double)max_cap * t->max_lf) / 4;
+  uint64_t chunk = t->cfg.max_capacity ? (uint64_t)((double)max_cap * t->max_lf) / 4 : (uint64_t)n;
   if (chunk < 1) chunk = 1;
   const int vec = pick_vec(t->row_bytes, values, nullptr, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);

@@ -51,8 +51,9 @@ class _FusedBase(object):
       self._check(params)
       self.apply_sparse(params, ids.reshape(-1), grad.reshape(-1, params.dim))
       # TrainableWrapper.update_op (embedding_weights.py:441-442): the restrict policy sees every updated id
-      if params.restrict_policy is not None:
-        params.restrict_policy.apply_update(ids.reshape(-1))
+      policy = getattr(params, "restrict_policy", None)
+      if policy is not None:
+        policy.apply_update(ids.reshape(-1))
 
   def apply_sparse(self, params, keys, grads):
     """keys must be unique (they are: embedding_lookup_unique / _sparse dedupe before the lookup)."""
