@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libdetable.so")
 SOURCES = ["table.cu", "fused.cu", "host_api.cu", "sharded.cu", "evict.cu"]
-HEADERS = ["common.cuh", "host.h", os.path.join("..", "..", "include", "detable.h")]
+HEADERS = ["common.cuh", "host.h", "evict_kernels.cuh", os.path.join("..", "..", "include", "detable.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

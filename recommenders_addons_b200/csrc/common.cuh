@@ -8,8 +8,13 @@
 //   slots_k: float [(nb*8+2)][dim]   optional optimizer planes (accumulator / m / v)
 // Probing: bucket b0 = mulhi64(fmix64(key), nb), linear over buckets.  A 4-lane subgroup owns one
 // key: each lane loads 16 B (2 keys) of the 64 B bucket, matches are found with __ballot_sync.
+//
+// DET_EMU is defined only by the test suite's SIMT-emulation harness (tests/emu/cuda_emu.h), which compiles this
+// header with g++ to execute the probe primitives without a GPU: the few PTX loads/stores get plain-C bodies there.
 #pragma once
+#ifndef DET_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace det {
@@ -63,13 +68,23 @@ __device__ __forceinline__ bool is_special(long long key) { return key == kEmpty
 // L2-coherent 16 B load of two keys (mutating kernels: L1 may hold lines older than a peer's CAS)
 __device__ __forceinline__ longlong2 ld_keys_cg(const long long* p) {
   longlong2 r;
+#ifdef DET_EMU
+  r.x = __atomic_load_n(p, __ATOMIC_RELAXED);
+  r.y = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
+#else
   asm volatile("ld.global.cg.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+#endif
   return r;
 }
 // read-only path for kernels that do not mutate the key plane
 __device__ __forceinline__ longlong2 ld_keys_nc(const long long* p) {
   longlong2 r;
+#ifdef DET_EMU
+  r.x = p[0];
+  r.y = p[1];
+#else
   asm volatile("ld.global.nc.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+#endif
   return r;
 }
 
@@ -88,15 +103,23 @@ __device__ __forceinline__ typename VecT<VEC>::type ld_row(const unsigned char* 
 template <>
 __device__ __forceinline__ int4 ld_row<16>(const unsigned char* p) {
   int4 r;
+#ifdef DET_EMU
+  r = *reinterpret_cast<const int4*>(p);
+#else
   asm volatile("ld.global.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+#endif
   return r;
 }
 template <>
 __device__ __forceinline__ int2 ld_row<8>(const unsigned char* p) {
   int2 r;
+#ifdef DET_EMU
+  r = *reinterpret_cast<const int2*>(p);
+#else
   asm volatile("ld.global.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+#endif
   return r;
 }
 template <int VEC>
@@ -105,14 +128,22 @@ __device__ __forceinline__ void st_row(unsigned char* p, typename VecT<VEC>::typ
 }
 template <>
 __device__ __forceinline__ void st_row<16>(unsigned char* p, int4 v) {
+#ifdef DET_EMU
+  *reinterpret_cast<int4*>(p) = v;
+#else
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
                : "memory");
+#endif
 }
 template <>
 __device__ __forceinline__ void st_row<8>(unsigned char* p, int2 v) {
+#ifdef DET_EMU
+  *reinterpret_cast<int2*>(p) = v;
+#else
   asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y)
                : "memory");
+#endif
 }
 
 // ---- subgroup helpers -------------------------------------------------------------------------
@@ -456,6 +487,7 @@ __device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned 
   }
 }
 
+#ifndef DET_EMU
 // ---- TMA bulk staging of key tiles (cp.async.bulk global -> shared, completion on an mbarrier) ----------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -579,5 +611,6 @@ struct KeyTiles {
     ++it;
   }
 };
+#endif  // !DET_EMU
 
 }  // namespace det
