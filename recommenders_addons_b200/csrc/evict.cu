@@ -116,7 +116,7 @@ det_status evict_on_rehash(det_table* t, const TableView& ov, const TableView& n
   unsigned long long* ns = nullptr;
   CUDA_TRY(cudaMalloc((void**)&ns, (ncap + 2) * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(ns, 0, (ncap + 2) * sizeof(unsigned long long), s));
-  carry_scores_kernel<<<grid_for(ocap, kThreadsE, t->sm_count, 8), kThreadsE, 0, s>>>(ov, ev->scores, nv, ns);
+  DET_LAUNCH(carry_scores_kernel, grid_for(ocap, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, ov, ev->scores, nv, ns);
   CUDA_TRY(cudaMemcpyAsync(ns + ncap, ev->scores + ocap, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -131,14 +131,14 @@ void evict_on_clear(det_table* t, cudaStream_t s) {
 }
 
 det_status evict_before_remove(det_table* t, const long long* keys, size_t n, cudaStream_t s) {
-  scores_of_keys_kernel<<<grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s>>>(t->view, keys, n, t->ev->scores,
+  DET_LAUNCH(scores_of_keys_kernel, grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, t->view, keys, n, t->ev->scores,
                                                                                   nullptr, 1);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
 }
 
 det_status evict_touch(det_table* t, const long long* keys, const unsigned long long* scores, size_t n, cudaStream_t s) {
-  touch_kernel<<<grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s>>>(t->view, keys, scores, n, t->ev->scores,
+  DET_LAUNCH(touch_kernel, grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, t->view, keys, scores, n, t->ev->scores,
                                                                          rule_of(t));
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
@@ -156,8 +156,8 @@ det_status evict_lowest(det_table* t, uint64_t k, cudaStream_t s) {
   const TableView v = t->view;
   const size_t cap = v.capacity();
   const int grid = grid_for(cap, kThreadsE * 4, t->sm_count, 8);
-  evict_reset_kernel<<<1, 256, 0, s>>>(ev->dev);
-  minmax_kernel<<<grid, kThreadsE, 0, s>>>(v, ev->scores, ev->dev);
+  DET_LAUNCH(evict_reset_kernel, 1, 256, 0, s, ev->dev);
+  DET_LAUNCH(minmax_kernel, grid, kThreadsE, 0, s, v, ev->scores, ev->dev);
   CUDA_TRY(cudaGetLastError());
   det_status st = read_dev(t, s);
   if (st != DET_OK) return st;
@@ -166,14 +166,14 @@ det_status evict_lowest(det_table* t, uint64_t k, cudaStream_t s) {
   if (k > n_live) k = n_live;
   int sig = 0;
   for (unsigned long long diff = smin ^ smax; diff; diff >>= 1) ++sig;   // bits in which the scores differ
-  select_init_kernel<<<1, 1, 0, s>>>(ev->dev, smin & ~lowmask(sig), k);
+  DET_LAUNCH(select_init_kernel, 1, 1, 0, s, ev->dev, smin & ~lowmask(sig), k);
   for (int hi = sig; hi > 0;) {
     const int bits = hi < kHistBits ? hi : kHistBits;
-    hist_kernel<<<grid, kThreadsE, 0, s>>>(v, ev->scores, ev->dev, hi, bits);
-    pick_kernel<<<1, 32, 0, s>>>(ev->dev, hi, bits);
+    DET_LAUNCH(hist_kernel, grid, kThreadsE, 0, s, v, ev->scores, ev->dev, hi, bits);
+    DET_LAUNCH(pick_kernel, 1, 32, 0, s, ev->dev, hi, bits);
     hi -= bits;
   }
-  evict_apply_kernel<<<grid, kThreadsE, 0, s>>>(v, ev->scores, ev->dev);
+  DET_LAUNCH(evict_apply_kernel, grid, kThreadsE, 0, s, v, ev->scores, ev->dev);
   CUDA_TRY(cudaGetLastError());
   // repair rounds
   const int vec = pick_vec(t->row_bytes, nullptr, nullptr, nullptr);
@@ -184,10 +184,10 @@ det_status evict_lowest(det_table* t, uint64_t k, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(&ev->dev->n_moved, 0, 2 * sizeof(unsigned long long), s));  // n_moved, n_erased
     const int rgrid = grid_for(cap, kThreadsE, t->sm_count, 8);
     dispatch_vec_e(vec, [&](auto V) -> det_status {
-      repair_move_kernel<decltype(V)::value><<<rgrid, kThreadsE, 0, s>>>(v, ev->scores, g, gs, np, ev->dev);
+      DET_LAUNCH(repair_move_kernel<decltype(V)::value>, rgrid, kThreadsE, 0, s, v, ev->scores, g, gs, np, ev->dev);
       return DET_OK;
     });
-    repair_sweep_kernel<<<rgrid, kThreadsE, 0, s>>>(v, ev->scores, ev->dev);
+    DET_LAUNCH(repair_sweep_kernel, rgrid, kThreadsE, 0, s, v, ev->scores, ev->dev);
     CUDA_TRY(cudaGetLastError());
     st = read_dev(t, s);
     if (st != DET_OK) return st;
@@ -234,10 +234,10 @@ det_status evict_room(det_table* t, const long long* keys, size_t n, cudaStream_
       if (st != DET_OK) return st;
       mask = (unsigned char*)sc;
     }
-    evict_reset_kernel<<<1, 256, 0, s>>>(ev->dev);
+    DET_LAUNCH(evict_reset_kernel, 1, 256, 0, s, ev->dev);
     if (admission)
-      minmax_kernel<<<grid_for(cap, kThreadsE * 4, t->sm_count, 8), kThreadsE, 0, s>>>(t->view, ev->scores, ev->dev);
-    classify_kernel<<<grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s>>>(t->view, keys, ev->ctx_scores, n, rule_of(t),
+      DET_LAUNCH(minmax_kernel, grid_for(cap, kThreadsE * 4, t->sm_count, 8), kThreadsE, 0, s, t->view, ev->scores, ev->dev);
+    DET_LAUNCH(classify_kernel, grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, t->view, keys, ev->ctx_scores, n, rule_of(t),
                                                                               admission ? 1 : 0, mask, ev->dev);
     CUDA_TRY(cudaGetLastError());
     st = read_dev(t, s);
@@ -304,7 +304,7 @@ det_status evict_insert(det_table* t, const int64_t* keys, const void* values, c
     st = dispatch_vec_e(vec, [&](auto V) -> det_status {
       constexpr int VV = decltype(V)::value;
       const int grid = grid_for(m, kThreadsE, t->sm_count, occupancy_of(insert_scored_kernel<VV>, kThreadsE));
-      insert_scored_kernel<VV><<<grid, kThreadsE, 0, s>>>(v, k, vals, sc_in, mask, m, g, np, ev->scores, rule);
+      DET_LAUNCH(insert_scored_kernel<VV>, grid, kThreadsE, 0, s, v, k, vals, sc_in, mask, m, g, np, ev->scores, rule);
       CUDA_TRY(cudaGetLastError());
       return DET_OK;
     });
@@ -337,7 +337,7 @@ det_status det_find_scores(det_table* t, const int64_t* keys, size_t n, uint64_t
   if (!keys || !scores_out) return fail(DET_INVALID_ARGUMENT, "det_find_scores: null argument");
   det::DevGuard _dg(t->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
-  scores_of_keys_kernel<<<grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s>>>(
+  DET_LAUNCH(scores_of_keys_kernel, grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, 
       t->view, (const long long*)keys, n, t->ev->scores, (unsigned long long*)scores_out, 0);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;

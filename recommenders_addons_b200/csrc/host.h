@@ -13,6 +13,15 @@
 #include "../../include/detable.h"
 #include "common.cuh"
 
+// Kernel launch.  The test suite's SIMT emulator (tests/emu/, -DDET_EMU) compiles these translation units with g++
+// and runs the launch as OS threads; nvcc sees the ordinary <<<>>> launch.
+#ifdef DET_EMU
+#define DET_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::emu::launch((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
+#else
+#define DET_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace det {
 
 extern thread_local std::string g_last_error;

@@ -672,8 +672,8 @@ static size_t planes_bytes(const det_table* t, uint64_t nb) {
 
 det_status table_clear_async(det_table* t, cudaStream_t s) {
   const size_t cap = t->view.capacity();
-  fill_keys_kernel<<<grid_for(cap, 1024 * 4, t->sm_count, 8), 1024, 0, s>>>(t->view.keys, cap, kEmptyKey);
-  reset_state_kernel<<<1, 1, 0, s>>>(t->view.st);
+  DET_LAUNCH(fill_keys_kernel, grid_for(cap, 1024 * 4, t->sm_count, 8), 1024, 0, s, t->view.keys, cap, kEmptyKey);
+  DET_LAUNCH(reset_state_kernel, 1, 1, 0, s, t->view.st);
   CUDA_TRY(cudaGetLastError());
   t->used_ub = 0;
   if (t->ev) evict_on_clear(t, s);
@@ -705,7 +705,7 @@ det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
   det_status st = alloc_planes(t, new_nb, &nv, raw);
   if (st != DET_OK) return st;
   const size_t ncap = new_nb * kBucket;
-  fill_keys_kernel<<<grid_for(ncap, 4096, t->sm_count, 8), 1024, 0, s>>>(nv.keys, ncap, kEmptyKey);
+  DET_LAUNCH(fill_keys_kernel, grid_for(ncap, 4096, t->sm_count, 8), 1024, 0, s, nv.keys, ncap, kEmptyKey);
   const TableView ov = t->view;
   const int vec = pick_vec(t->row_bytes, nullptr, nullptr, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
@@ -713,7 +713,7 @@ det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
   const int np = t->cfg.num_slot_planes;
   const int grid = grid_for(ov.capacity(), kThreads, t->sm_count, 8);
   dispatch_vec(vec, [&](auto V) -> det_status {
-    rehash_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(ov, nv, g, gs, np);
+    DET_LAUNCH(rehash_kernel<decltype(V)::value>, grid, kThreads, 0, s, ov, nv, g, gs, np);
     return DET_OK;
   });
   // special rows
@@ -722,7 +722,7 @@ det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
     CUDA_TRY(cudaMemcpyAsync(nv.planes[p] + ncap * rb, ov.planes[p] + ov.capacity() * rb, 2 * rb,
                              cudaMemcpyDeviceToDevice, s));
   }
-  rehash_fix_state_kernel<<<1, 1, 0, s>>>(t->view.st);
+  DET_LAUNCH(rehash_fix_state_kernel, 1, 1, 0, s, t->view.st);
   CUDA_TRY(cudaGetLastError());
   if (t->ev) {  // scores follow their keys into the new planes
     st = evict_on_rehash(t, ov, nv, s);
@@ -774,7 +774,7 @@ det_status ensure_room(det_table* t, const long long* keys, size_t n, cudaStream
   uint64_t n_new = n;
   if (keys != nullptr) {
     CUDA_TRY(cudaMemsetAsync(&t->view.st->scratch[2], 0, sizeof(unsigned long long), s));
-    count_missing_kernel<<<grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s>>>(t->view, keys, n,
+    DET_LAUNCH(count_missing_kernel, grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s, t->view, keys, n,
                                                                                  &t->view.st->scratch[2]);
     CUDA_TRY(cudaGetLastError());
     st = read_state(t, s, &ds);
@@ -837,7 +837,8 @@ static det_status launch_accum_v(det_table* t, const TableView& v, const long lo
                                  const uint8_t* exists, size_t n, const SlotInit& si, const RowGeom& g,
                                  cudaStream_t s) {
   const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(accum_kernel<T, VEC>, kThreads));
-  accum_kernel<T, VEC><<<grid, kThreads, 0, s>>>(v, k, (const T*)vod, exists, n, si, g);
+  const auto kern = accum_kernel<T, VEC>;
+  DET_LAUNCH(kern, grid, kThreads, 0, s, v, k, (const T*)vod, exists, n, si, g);
   return DET_OK;
 }
 
@@ -849,7 +850,7 @@ static det_status launch_accum(det_table* t, const TableView& v, const long long
     static const int staged = env_int("DET_ACCUM_STAGED", 1);
     if (staged && vec == 16 && g.vpr <= g.lpr) {
       const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(accum_staged_kernel, kThreads));
-      accum_staged_kernel<<<grid, kThreads, 0, s>>>(v, k, (const float*)vod, exists, n, si, g);
+      DET_LAUNCH(accum_staged_kernel, grid, kThreads, 0, s, v, k, (const float*)vod, exists, n, si, g);
       return DET_OK;
     }
   }
@@ -1074,11 +1075,11 @@ det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* def
     constexpr int VV = decltype(V)::value;
     if (tma) {
       const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(find_kernel_tma<VV>, kThreads));
-      find_kernel_tma<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, n, (const unsigned char*)defaults,
+      DET_LAUNCH(find_kernel_tma<VV>, grid, kThreads, 0, s, v, (const long long*)keys, n, (const unsigned char*)defaults,
                                                     full_size_default, (unsigned char*)values_out, exists, g);
     } else {
       const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(find_kernel<VV>, kThreads));
-      find_kernel<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, n, (const unsigned char*)defaults,
+      DET_LAUNCH(find_kernel<VV>, grid, kThreads, 0, s, v, (const long long*)keys, n, (const unsigned char*)defaults,
                                                 full_size_default, (unsigned char*)values_out, exists, g);
     }
     CUDA_TRY(cudaGetLastError());
@@ -1115,10 +1116,10 @@ det_status insert_impl(det_table* t, const int64_t* keys, const void* values, si
     constexpr int VV = decltype(V)::value;
     if (tma) {
       const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(insert_kernel_tma<VV>, kThreads));
-      insert_kernel_tma<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, (const unsigned char*)values, n, g, si);
+      DET_LAUNCH(insert_kernel_tma<VV>, grid, kThreads, 0, s, v, (const long long*)keys, (const unsigned char*)values, n, g, si);
     } else {
       const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(insert_kernel<VV>, kThreads));
-      insert_kernel<VV><<<grid, kThreads, 0, s>>>(v, (const long long*)keys, (const unsigned char*)values, n, g, si);
+      DET_LAUNCH(insert_kernel<VV>, grid, kThreads, 0, s, v, (const long long*)keys, (const unsigned char*)values, n, g, si);
     }
     CUDA_TRY(cudaGetLastError());
     if (check_room) note_mutation(t, n, s);
@@ -1185,7 +1186,7 @@ det_status det_remove(det_table* t, const int64_t* keys, size_t n, det_stream_t 
     det_status est = evict_before_remove(t, (const long long*)keys, n, s);
     if (est != DET_OK) return est;
   }
-  remove_kernel<<<grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s>>>(t->view, (const long long*)keys, n);
+  DET_LAUNCH(remove_kernel, grid_for(n, kThreads, t->sm_count, 8), kThreads, 0, s, t->view, (const long long*)keys, n);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
 }
@@ -1255,19 +1256,19 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
     offs = (unsigned long long*)((unsigned char*)sc + off_bytes);
   }
   const int grid = grid_for(n_tiles, 1, t->sm_count, 8);
-  export_count_kernel<<<grid, kThreads, 0, s>>>(v, counts, n_tiles);
-  export_scan_kernel<<<1, 1024, 0, s>>>(counts, offs, n_tiles, v.st);
+  DET_LAUNCH(export_count_kernel, grid, kThreads, 0, s, v, counts, n_tiles);
+  DET_LAUNCH(export_scan_kernel, 1, 1024, 0, s, counts, offs, n_tiles, v.st);
   const unsigned prb = plane == 0 ? (unsigned)t->row_bytes : (unsigned)t->cfg.dim * 4u;
   const int vec = pick_vec(prb, values_out, nullptr, nullptr);
   const RowGeom g = make_geom(prb, vec);
   dispatch_vec(vec, [&](auto V) -> det_status {
-    export_write_kernel<decltype(V)::value><<<grid, kThreads, 0, s>>>(
+    DET_LAUNCH(export_write_kernel<decltype(V)::value>, grid, kThreads, 0, s, 
         v, plane, prb, offs, n_tiles, (long long*)keys_out, (unsigned char*)values_out, max_n, g);
     return DET_OK;
   });
-  export_special_kernel<<<1, 128, 0, s>>>(v, plane, prb, (long long*)keys_out, (unsigned char*)values_out, max_n);
+  DET_LAUNCH(export_special_kernel, 1, 128, 0, s, v, plane, prb, (long long*)keys_out, (unsigned char*)values_out, max_n);
   if (plane > 0 && values_out)
-    export_fix_slot_rows_kernel<<<grid_for(max_n, 8, t->sm_count, 8), kThreads, 0, s>>>(
+    DET_LAUNCH(export_fix_slot_rows_kernel, grid_for(max_n, 8, t->sm_count, 8), kThreads, 0, s, 
         (float*)values_out, &v.st->scratch[1], (unsigned)t->cfg.dim, t->slot_init[plane]);
   CUDA_TRY(cudaGetLastError());
   DevState ds;
