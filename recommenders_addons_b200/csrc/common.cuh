@@ -487,7 +487,20 @@ __device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned 
   }
 }
 
-#ifndef DET_EMU
+#ifdef DET_EMU
+// The emulator has no TMA / mbarrier unit: KeyTiles runs its plain-load tile schedule (tma = false) and the
+// asynchronous 16 B copies complete immediately.
+static inline void mbar_init(unsigned long long*, unsigned) { abort(); }
+static inline void mbar_fence_init() { abort(); }
+static inline void mbar_arrive_expect_tx(unsigned long long*, unsigned) { abort(); }
+static inline void mbar_arrive(unsigned long long*) { abort(); }
+static inline void mbar_wait(unsigned long long*, unsigned) { abort(); }
+static inline void bulk_g2s(void*, const void*, unsigned, unsigned long long*) { abort(); }
+static inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+static inline void cp_async_commit() {}
+template <int N>
+static inline void cp_async_wait() {}
+#else
 // ---- TMA bulk staging of key tiles (cp.async.bulk global -> shared, completion on an mbarrier) ----------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -539,6 +552,8 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#endif  // DET_EMU
+
 constexpr int kTileKeys = 256;  // keys per CTA tile (= blockDim): 2 KB per stage
 constexpr int kStages = 2;
 
@@ -575,6 +590,9 @@ struct KeyTiles {
     tile = blockIdx.x;
     it = 0;
     tma = use_tma;
+#ifdef DET_EMU
+    tma = false;
+#endif
     if (tma) {
       if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
@@ -611,6 +629,5 @@ struct KeyTiles {
     ++it;
   }
 };
-#endif  // !DET_EMU
 
 }  // namespace det

@@ -1,8 +1,10 @@
 // host.h -- host-side table object and shared declarations for the .cu translation units.
 #pragma once
+#ifndef DET_EMU  // the emulator build gets its own definitions of these (tests/emu/cuda_emu.h, cuda_runtime_emu.h)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 

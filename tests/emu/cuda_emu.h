@@ -1,11 +1,11 @@
 // cuda_emu.h -- a minimal SIMT emulator for TESTING device code without a GPU (test infrastructure only; nothing in
 // the product includes it).  The kernel sources are compiled unchanged by g++ with -DDET_EMU:
-//   * every CUDA thread is an OS thread; a block's threads run concurrently, blocks run one after the other
-//     (so `__shared__` can simply be `static`);
-//   * warp collectives (__shfl_sync, __ballot_sync, __any_sync, __syncwarp) are barriers over the 32 lane threads of
-//     a warp that exchange values through a per-warp mailbox -- divergence needs no special care because each lane
-//     really is its own thread; __syncthreads is a barrier over the block;
-//   * atomics are the GCC __atomic builtins on ordinary host memory, so races between "CUDA threads" are REAL races
+//   * every WARP is an OS thread and every lane a fiber (ucontext) of it; a block's warps run concurrently, blocks
+//     run one after the other (so `__shared__` can simply be `static`);
+//   * warp collectives (__shfl_sync, __ballot_sync, __any_sync, __syncwarp) park the lane until all live lanes of
+//     the warp have arrived and exchange values through a per-warp mailbox -- divergence needs no special care
+//     because each lane has its own stack and program counter; __syncthreads parks it until the block has arrived;
+//   * atomics are the GCC __atomic builtins on ordinary host memory, so races between warps are REAL races
 //     between OS threads: the claim / repair protocols are exercised under genuine concurrency.
 // Only full-mask collectives are supported (all this code base uses).
 #pragma once
@@ -23,6 +23,8 @@
 #include <thread>
 #include <vector>
 
+#include <ucontext.h>
+
 #define __global__
 #define __device__
 #define __host__
@@ -30,12 +32,11 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 
 struct emu_dim3 {
   unsigned x = 0, y = 0, z = 0;
 };
-inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 struct longlong2 {
   long long x, y;
@@ -52,13 +53,66 @@ struct alignas(16) float4 {
 };
 
 namespace emu {
-struct Warp {
-  std::barrier<> bar{32};
-  unsigned long long vals[32] = {};
+// One OS thread per WARP; its 32 lanes are fibers (ucontext) scheduled round-robin by that thread.  A lane that
+// reaches a warp collective parks until all live lanes of the warp have arrived; __syncthreads parks it until all
+// live threads of the block have.  Warps of a block run truly concurrently (atomics, CAS races are real), blocks run
+// one after the other (so `__shared__` can be `static`).
+constexpr size_t kFiberStack = 256 * 1024;
+
+struct Fiber {
+  ucontext_t ctx;
+  emu_dim3 tid;
+  int lane = 0;
+  bool done = false;
+  void* stack = nullptr;
 };
-inline thread_local Warp* warp = nullptr;
-inline thread_local int lane = 0;
-inline thread_local std::barrier<>* block_bar = nullptr;
+
+struct Block {
+  std::atomic<unsigned> arrived{0};
+  std::atomic<unsigned> gen{0};
+  std::atomic<unsigned> alive{0};
+};
+
+struct Warp {
+  Fiber f[32];
+  int n_lanes = 0, alive = 0, cur = 0;
+  ucontext_t sched;
+  unsigned long long vals[32] = {};
+  int arrived = 0;
+  unsigned gen = 0;
+  Block* block = nullptr;
+  const void* fn = nullptr;
+  void (*invoke)(const void*) = nullptr;
+};
+
+inline thread_local Warp* W = nullptr;
+inline thread_local emu_dim3 t_blockIdx, t_blockDim, t_gridDim;
+
+static inline Fiber* self() { return &W->f[W->cur]; }
+static inline void yield_lane() { swapcontext(&W->f[W->cur].ctx, &W->sched); }
+
+// barrier over the live lanes of the warp
+static inline void warp_barrier() {
+  Warp* w = W;
+  const unsigned my = w->gen;
+  if (++w->arrived >= w->alive) {
+    w->arrived = 0;
+    ++w->gen;
+  } else {
+    while (w->gen == my) yield_lane();
+  }
+}
+
+static inline void block_barrier() {
+  Block* b = W->block;
+  const unsigned my = b->gen.load();
+  if (b->arrived.fetch_add(1) + 1 >= b->alive.load()) {
+    b->arrived.store(0);
+    b->gen.fetch_add(1);
+  } else {
+    while (b->gen.load() == my) yield_lane();
+  }
+}
 
 inline unsigned long long now_ns() {
   return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
@@ -73,41 +127,114 @@ inline void require_full(unsigned mask) {
   }
 }
 
-// run `fn` as a grid of `grid` blocks of `block` threads (block % 32 == 0)
+static void fiber_main() {
+  Warp* w = W;
+  Fiber* me = &w->f[w->cur];
+  w->invoke(w->fn);
+  // an exited thread no longer takes part in barriers: release whoever waits for it
+  me->done = true;
+  w->vals[me->lane] = 0;
+  --w->alive;
+  if (w->alive > 0 && w->arrived >= w->alive) {
+    w->arrived = 0;
+    ++w->gen;
+  }
+  Block* b = w->block;
+  const unsigned left = b->alive.fetch_sub(1) - 1;
+  if (left > 0 && b->arrived.load() >= left) {
+    b->arrived.store(0);
+    b->gen.fetch_add(1);
+  }
+  swapcontext(&me->ctx, &w->sched);
+}
+
+static void run_warp(Warp* w, emu_dim3 bi, emu_dim3 bd, emu_dim3 gd) {
+  W = w;
+  t_blockIdx = bi;
+  t_blockDim = bd;
+  t_gridDim = gd;
+  for (int l = 0; l < w->n_lanes; ++l) {
+    Fiber& f = w->f[l];
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kFiberStack;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, (void (*)())fiber_main, 0);
+  }
+  int idle_rounds = 0;
+  while (w->alive > 0) {
+    bool progressed = false;
+    for (int l = 0; l < w->n_lanes; ++l) {
+      if (w->f[l].done) continue;
+      const unsigned g0 = w->gen;
+      const int a0 = w->arrived;
+      w->cur = l;
+      swapcontext(&w->sched, &w->f[l].ctx);
+      if (w->f[l].done || w->gen != g0 || w->arrived != a0) progressed = true;
+    }
+    // every live lane is parked on the block barrier (or on an atomic another warp must release): let others run
+    if (!progressed && ++idle_rounds > 4) {
+      std::this_thread::yield();
+      idle_rounds = 0;
+    }
+  }
+}
+
+// run `fn` as a grid of `grid` blocks of `block` threads (a last partial warp must not use warp collectives that
+// name absent lanes, as on the GPU)
 template <typename F>
 void launch(unsigned grid, unsigned block, F fn) {
-  if (block % 32 != 0) abort();
+  if (block == 0 || grid == 0) abort();
+  const unsigned n_warps = (block + 31) / 32;
+  std::vector<std::unique_ptr<Warp>> warps;
+  for (unsigned w = 0; w < n_warps; ++w) {
+    warps.emplace_back(new Warp());
+    for (int l = 0; l < 32; ++l) warps[w]->f[l].stack = malloc(kFiberStack);
+  }
   for (unsigned b = 0; b < grid; ++b) {
-    std::barrier<> bbar((std::ptrdiff_t)block);
-    std::vector<std::unique_ptr<Warp>> warps;
-    for (unsigned w = 0; w < block / 32; ++w) warps.emplace_back(new Warp());
+    Block blk;
+    blk.alive.store(block);
     std::vector<std::thread> th;
-    th.reserve(block);
-    for (unsigned t = 0; t < block; ++t) {
-      th.emplace_back([&, t, b]() {
-        threadIdx.x = t;
-        blockIdx.x = b;
-        blockDim.x = block;
-        gridDim.x = grid;
-        warp = warps[t / 32].get();
-        lane = (int)(t & 31);
-        block_bar = &bbar;
-        fn();
-        // an exited thread no longer takes part in barriers
-        warp->vals[lane] = 0;
-        warp->bar.arrive_and_drop();
-        bbar.arrive_and_drop();
-      });
+    for (unsigned w = 0; w < n_warps; ++w) {
+      Warp* wp = warps[w].get();
+      wp->n_lanes = (int)(block - w * 32 < 32 ? block - w * 32 : 32);
+      wp->alive = wp->n_lanes;
+      wp->arrived = 0;
+      wp->gen = 0;
+      wp->block = &blk;
+      wp->fn = &fn;
+      wp->invoke = [](const void* p) { (*(const F*)p)(); };
+      for (int l = 0; l < 32; ++l) {
+        wp->f[l].done = l >= wp->n_lanes;
+        wp->f[l].lane = l;
+        wp->f[l].tid.x = w * 32 + (unsigned)l;
+        wp->vals[l] = 0;
+      }
+      emu_dim3 bi, bd, gd;
+      bi.x = b;
+      bd.x = block;
+      gd.x = grid;
+      if (n_warps == 1)
+        run_warp(wp, bi, bd, gd);
+      else
+        th.emplace_back(run_warp, wp, bi, bd, gd);
     }
     for (auto& x : th) x.join();
   }
+  for (auto& w : warps)
+    for (int l = 0; l < 32; ++l) free(w->f[l].stack);
 }
 }  // namespace emu
 
-static inline void __syncthreads() { emu::block_bar->arrive_and_wait(); }
+#define threadIdx (::emu::self()->tid)
+#define blockIdx (::emu::t_blockIdx)
+#define blockDim (::emu::t_blockDim)
+#define gridDim (::emu::t_gridDim)
+
+static inline void __syncthreads() { emu::block_barrier(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) {
   emu::require_full(mask);
-  emu::warp->bar.arrive_and_wait();
+  emu::warp_barrier();
 }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
@@ -128,42 +255,44 @@ static inline T emu_from(unsigned long long b) {
 template <typename T>
 static inline T __shfl_sync(unsigned mask, T v, int src) {
   emu::require_full(mask);
-  emu::Warp& w = *emu::warp;
-  w.vals[emu::lane] = emu_bits(v);
-  w.bar.arrive_and_wait();
+  emu::Warp& w = *emu::W;
+  w.vals[emu::self()->lane] = emu_bits(v);
+  emu::warp_barrier();
   const unsigned long long r = w.vals[src & 31];
-  w.bar.arrive_and_wait();
+  emu::warp_barrier();
   return emu_from<T>(r);
 }
 template <typename T>
 static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
   emu::require_full(mask);
-  emu::Warp& w = *emu::warp;
-  w.vals[emu::lane] = emu_bits(v);
-  w.bar.arrive_and_wait();
-  const unsigned src = (unsigned)emu::lane + delta;
+  emu::Warp& w = *emu::W;
+  const int lane = emu::self()->lane;
+  w.vals[lane] = emu_bits(v);
+  emu::warp_barrier();
+  const unsigned src = (unsigned)lane + delta;
   const unsigned long long r = src < 32 ? w.vals[src] : emu_bits(v);
-  w.bar.arrive_and_wait();
+  emu::warp_barrier();
   return emu_from<T>(r);
 }
 template <typename T>
 static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
   emu::require_full(mask);
-  emu::Warp& w = *emu::warp;
-  w.vals[emu::lane] = emu_bits(v);
-  w.bar.arrive_and_wait();
-  const unsigned long long r = (unsigned)emu::lane >= delta ? w.vals[emu::lane - delta] : emu_bits(v);
-  w.bar.arrive_and_wait();
+  emu::Warp& w = *emu::W;
+  const int lane = emu::self()->lane;
+  w.vals[lane] = emu_bits(v);
+  emu::warp_barrier();
+  const unsigned long long r = (unsigned)lane >= delta ? w.vals[lane - delta] : emu_bits(v);
+  emu::warp_barrier();
   return emu_from<T>(r);
 }
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
   emu::require_full(mask);
-  emu::Warp& w = *emu::warp;
-  w.vals[emu::lane] = pred ? 1ull : 0ull;
-  w.bar.arrive_and_wait();
+  emu::Warp& w = *emu::W;
+  w.vals[emu::self()->lane] = pred ? 1ull : 0ull;
+  emu::warp_barrier();
   unsigned r = 0;
   for (int i = 0; i < 32; ++i) r |= (unsigned)(w.vals[i] & 1ull) << i;
-  w.bar.arrive_and_wait();
+  emu::warp_barrier();
   return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
