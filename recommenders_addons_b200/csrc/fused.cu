@@ -507,7 +507,7 @@ apply_staged_kernel(TableView t, const long long* __restrict__ keys, const float
                     OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
                     unsigned lpr_shift, int use_tma) {
   constexpr int NS = OPT == 0 ? 3 : 4;  // streams per row: grad, param, slot1 (, slot2)
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  DET_DYN_SHARED(dyn_smem);
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
   __shared__ __align__(8) unsigned long long s_bar[kStages];
   __shared__ unsigned s_new, s_used;
@@ -771,13 +771,13 @@ det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t
   unique_ws_layout(n, (unsigned char*)workspace, &w);
   const size_t nblocks = (n + kScanBlock - 1) / kScanBlock;
   const int g256 = (int)((n + 255) / 256);
-  unique_init_kernel<<<(int)((w.hcap + 1023) / 1024 < 4096 ? (w.hcap + 1023) / 1024 : 4096), 1024, 0, s>>>(w);
-  unique_insert_kernel<<<g256, 256, 0, s>>>(w, (const long long*)ids, n);
-  unique_flag_kernel<<<g256, 256, 0, s>>>(w, n);
-  scan_block_sums_kernel<<<(int)nblocks, kScanBlock, 0, s>>>(w.flags, n, w.block_sums);
-  scan_sums_kernel<<<1, kScanBlock, 0, s>>>(w.block_sums, nblocks, (long long*)n_unique_dev);
-  unique_rank_kernel<<<(int)nblocks, kScanBlock, 0, s>>>(w, (const long long*)ids, n, (long long*)unique_out);
-  unique_idx_kernel<<<g256, 256, 0, s>>>(w, n, idx_out);
+  DET_LAUNCH(unique_init_kernel, (int)((w.hcap + 1023) / 1024 < 4096 ? (w.hcap + 1023) / 1024 : 4096), 1024, 0, s, w);
+  DET_LAUNCH(unique_insert_kernel, g256, 256, 0, s, w, (const long long*)ids, n);
+  DET_LAUNCH(unique_flag_kernel, g256, 256, 0, s, w, n);
+  DET_LAUNCH(scan_block_sums_kernel, (int)nblocks, kScanBlock, 0, s, w.flags, n, w.block_sums);
+  DET_LAUNCH(scan_sums_kernel, 1, kScanBlock, 0, s, w.block_sums, nblocks, (long long*)n_unique_dev);
+  DET_LAUNCH(unique_rank_kernel, (int)nblocks, kScanBlock, 0, s, w, (const long long*)ids, n, (long long*)unique_out);
+  DET_LAUNCH(unique_idx_kernel, g256, 256, 0, s, w, n, idx_out);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
 }
@@ -804,10 +804,9 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
     seg_start = (long long*)sc;
     slots = (long long*)((unsigned char*)sc + seg_bytes);
   }
-  segment_offsets_kernel<<<(int)((nnz + 1 + 255) / 256), 256, 0, s>>>(segment_ids, nnz, batch, seg_start, t->view.st);
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st);
   if (nnz)
-    resolve_slots_kernel<<<grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF,
-                           0, s>>>(t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0);
+    DET_LAUNCH(resolve_slots_kernel, grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF, 0, s, t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0);
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out) & 15u) == 0);
   unsigned vpr, lpr, sh;
@@ -818,15 +817,15 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
-      segment_sum_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
     else
-      segment_sum_kernel<1><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
   } else if ((vpr + lpr - 1) / lpr <= (unsigned)kMaxVecPerLane) {
     const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
     if (vec4)
-      segment_sum_wide_kernel<4><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+      DET_LAUNCH(segment_sum_wide_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
     else
-      segment_sum_wide_kernel<1><<<grid, kThreadsF, 0, s>>>(t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+      DET_LAUNCH(segment_sum_wide_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
   } else {
     rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse: dim too large for the fused kernel");
   }
@@ -863,11 +862,11 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
     if (opt == 0) {
       CUDA_TRY(cudaFuncSetAttribute(apply_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_staged_kernel<0>, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
-      apply_staged_kernel<0><<<grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
+      DET_LAUNCH(apply_staged_kernel<0>, grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s, v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
     } else {
       CUDA_TRY(cudaFuncSetAttribute(apply_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_staged_kernel<1>, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
-      apply_staged_kernel<1><<<grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
+      DET_LAUNCH(apply_staged_kernel<1>, grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s, v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
     }
     CUDA_TRY(cudaGetLastError());
     note_mutation(t, n, s);
@@ -877,8 +876,9 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
 #define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
   {                                                                                                           \
     const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(apply_kernel<VF_, OPT_, RU_>, kThreadsF)); \
-    apply_kernel<VF_, OPT_, RU_><<<grid, kThreadsF, 0, s>>>(v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, \
-                                                            (((uintptr_t)keys & 15u) == 0) ? 1 : 0);                 \
+    const auto kern = apply_kernel<VF_, OPT_, RU_>;                                                           \
+    DET_LAUNCH(kern, grid, kThreadsF, 0, s, v, k, grads, n, h, init_param, full_init, vpr, lpr, sh,                   \
+                                    (((uintptr_t)keys & 15u) == 0) ? 1 : 0);                                  \
   }
   if (opt == 0) {
     if (vec4) { if (ru == 2) DET_LAUNCH_APPLY(4, 0, 2) else DET_LAUNCH_APPLY(4, 0, 1) }
@@ -930,9 +930,9 @@ det_status det_partition(const int64_t* keys, size_t n, int num_shards, int gpu_
   if (workspace_bytes < det_partition_workspace_bytes(n, num_shards)) return fail(DET_INVALID_ARGUMENT, "det_partition: workspace too small");
   const size_t nblocks = (n + kPartBlock - 1) / kPartBlock;
   unsigned* hist = (unsigned*)workspace;
-  partition_hist_kernel<<<(int)nblocks, kPartBlock, 0, s>>>((const long long*)keys, n, num_shards, gpu_mode, hist, nblocks);
-  partition_scan_kernel<<<1, kScanBlock, 0, s>>>(hist, nblocks, num_shards, (long long*)counts_out);
-  partition_write_kernel<<<(int)nblocks, kPartBlock, 0, s>>>((const long long*)keys, n, num_shards, gpu_mode, hist, nblocks,
+  DET_LAUNCH(partition_hist_kernel, (int)nblocks, kPartBlock, 0, s, (const long long*)keys, n, num_shards, gpu_mode, hist, nblocks);
+  DET_LAUNCH(partition_scan_kernel, 1, kScanBlock, 0, s, hist, nblocks, num_shards, (long long*)counts_out);
+  DET_LAUNCH(partition_write_kernel, (int)nblocks, kPartBlock, 0, s, (const long long*)keys, n, num_shards, gpu_mode, hist, nblocks,
                                                             (long long*)keys_out, perm_out);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
@@ -950,9 +950,13 @@ static det_status permute_rows(const void* in, const int32_t* perm, size_t n, si
   const int grid = grid_for(n, kThreadsF, sms, 8);
   const unsigned char* i = (const unsigned char*)in;
   unsigned char* o = (unsigned char*)out;
-#define LAUNCH(V)                                                                              \
-  if (scatter) permute_rows_kernel<V, true><<<grid, kThreadsF, 0, s>>>(i, perm, n, o, g);      \
-  else permute_rows_kernel<V, false><<<grid, kThreadsF, 0, s>>>(i, perm, n, o, g);
+#define LAUNCH(V)                                                        \
+  {                                                                      \
+    const auto ks = permute_rows_kernel<V, true>;                        \
+    const auto kg = permute_rows_kernel<V, false>;                       \
+    if (scatter) DET_LAUNCH(ks, grid, kThreadsF, 0, s, i, perm, n, o, g);        \
+    else DET_LAUNCH(kg, grid, kThreadsF, 0, s, i, perm, n, o, g);                \
+  }
   switch (vec) {
     case 16: LAUNCH(16) break;
     case 8: LAUNCH(8) break;

@@ -20,8 +20,10 @@
 #ifdef DET_EMU
 #define DET_LAUNCH(kernel, grid, block, smem, stream, ...) \
   ::emu::launch((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
+#define DET_DYN_SHARED(name) static __attribute__((aligned(16))) unsigned char name[96 * 1024]
 #else
 #define DET_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DET_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
 namespace det {

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <barrier>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -51,6 +52,7 @@ struct alignas(8) int2 {
 struct alignas(16) float4 {
   float x, y, z, w;
 };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 namespace emu {
 // One OS thread per WARP; its 32 lanes are fibers (ucontext) scheduled round-robin by that thread.  A lane that
@@ -296,6 +298,17 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
   return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline unsigned __match_any_sync(unsigned mask, int v) {
+  emu::require_full(mask);
+  emu::Warp& w = *emu::W;
+  w.vals[emu::self()->lane] = emu_bits(v);
+  emu::warp_barrier();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i)
+    if (!w.f[i].done && w.vals[i] == emu_bits(v)) r |= 1u << i;
+  emu::warp_barrier();
+  return r;
+}
 
 // ---- atomics / intrinsics ---------------------------------------------------------------------------------------
 static inline unsigned long long atomicCAS(unsigned long long* a, unsigned long long cmp, unsigned long long val) {
@@ -312,6 +325,12 @@ static inline unsigned long long atomicAdd(unsigned long long* a, unsigned long 
 }
 static inline unsigned long long atomicMin(unsigned long long* a, unsigned long long v) {
   unsigned long long cur = __atomic_load_n(a, __ATOMIC_SEQ_CST);
+  while (v < cur && !__atomic_compare_exchange_n(a, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return cur;
+}
+static inline unsigned atomicMin(unsigned* a, unsigned v) {
+  unsigned cur = __atomic_load_n(a, __ATOMIC_SEQ_CST);
   while (v < cur && !__atomic_compare_exchange_n(a, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
   }
   return cur;

@@ -13,6 +13,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
 enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 struct cudaDeviceProp {
   int multiProcessorCount = 1;
   char name[64] = "simt-emulator";
@@ -58,6 +59,10 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   return cudaSuccess;
 }
 static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+  *v = 1;
+  return cudaSuccess;
+}
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
   *e = malloc(1);
   return cudaSuccess;

@@ -384,3 +384,73 @@ def test_steady_state_churn_lru():
   assert st["evict_events"] >= 2 and st["used_slots"] == st["size"]
   assert t.find(np.arange(nxt - 150, nxt))[1].all() and not t.find(np.arange(150))[1].any()
   t.close()
+
+
+# ---- (3) random op streams on tiny tables: every bucket overflows, chains wrap around, tombstones everywhere ----------
+from hypothesis import HealthCheck, given, settings, strategies as hst  # noqa: E402
+
+_OPS = hst.lists(hst.tuples(hst.sampled_from(["ins", "ins", "rem", "acc", "find"]),
+                            hst.lists(hst.integers(-40, 160), min_size=1, max_size=70, unique=True)),
+                 min_size=1, max_size=14)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(hst.sampled_from([16, 24, 64]), hst.sampled_from([0.0, 0.9]), _OPS)
+def test_random_op_streams_against_a_dict(init, lf, ops):
+  t = Table(dim=4, init=init, lf=lf)
+  ref = {}
+  try:
+    for op, ks in ops:
+      keys = np.array(ks, dtype=np.int64)
+      if op == "ins":
+        vals = (keys[:, None] * 3 + np.arange(4)[None, :] + len(ref)).astype(np.float32)
+        t.insert(keys, vals)
+        for k, v in zip(ks, vals):
+          ref[k] = v.copy()
+      elif op == "rem":
+        t.remove(keys)
+        for k in ks:
+          ref.pop(k, None)
+      elif op == "acc":
+        ex = np.array([k in ref for k in ks])
+        vod = np.ones((len(ks), 4), dtype=np.float32)
+        t.accum(keys, vod, ex)
+        for k, e in zip(ks, ex):
+          ref[k] = ref[k] + 1 if e else np.ones(4, dtype=np.float32)
+      out, ex = t.find(keys)
+      for i, k in enumerate(ks):
+        assert bool(ex[i]) == (k in ref)
+        if k in ref:
+          assert np.array_equal(out[i], ref[k])
+      assert t.size() == len(ref)
+    ks, vs = t.export()
+    assert sorted(ks.tolist()) == sorted(ref)
+    st = t.stats()
+    assert st["error_flags"] == 0 and st["used_slots"] >= st["size"]
+  finally:
+    t.close()
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(hst.sampled_from([0, 1, 4]), hst.lists(hst.lists(hst.integers(0, 300), min_size=1, max_size=90, unique=True),
+                                              min_size=2, max_size=10))
+def test_random_scored_streams_keep_the_bounded_table_consistent(strategy, batches):
+  cap = 128
+  t = Table(dim=4, init=cap, max_capacity=cap, strategy=strategy, gen_scores_fn=lambda k: (np.asarray(k) * 37) % 101)
+  last = {}
+  try:
+    for ks in batches:
+      keys = np.array(ks, dtype=np.int64)
+      vals = (keys[:, None] + np.arange(4)[None, :] + len(last)).astype(np.float32)
+      t.insert(keys, vals)
+      for k, v in zip(ks, vals):
+        last[k] = v.copy()
+      assert t.size() <= cap
+      t.check()
+    ks, vs = t.export()
+    for k, v in zip(ks.tolist(), vs):
+      assert np.array_equal(v, last[k])                      # a resident key always holds the row last written
+    st = t.stats()
+    assert st["used_slots"] == st["size"] and st["error_flags"] == 0
+  finally:
+    t.close()
