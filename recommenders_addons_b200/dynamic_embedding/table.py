@@ -23,6 +23,11 @@ _TORCH_TO_NAME = {
 VALID_VALUE_DTYPES = tuple(_TORCH_TO_NAME.keys())
 
 
+# Device types a table may be created on.  The product knows CUDA only; the test suite's SIMT emulator
+# (tests/emu/backend.py) adds "cpu" together with a libdetable built against the emulator.
+_DEVICE_TYPES = ("cuda",)
+
+
 def _stream_ptr(device):
   return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -92,10 +97,10 @@ class CuckooHashTable(object):
     if device is None:
       device = torch.device("cuda", torch.cuda.current_device())
     self._device = torch.device(device)
-    if self._device.type != "cuda":
+    if self._device.type not in _DEVICE_TYPES:
       raise RuntimeError("recommenders_addons_b200 tables live in GPU HBM; device=%s is not a CUDA device "
                          "(there is no CPU fallback)" % (device,))
-    if self._device.index is None:
+    if self._device.type == "cuda" and self._device.index is None:
       self._device = torch.device("cuda", torch.cuda.current_device())
     self._key_dtype = key_dtype
     self._value_dtype = value_dtype
@@ -109,7 +114,7 @@ class CuckooHashTable(object):
     cfg = _lib.DetConfig()
     cfg.value_dtype = _lib.DTYPE_CODES[_TORCH_TO_NAME[value_dtype]]
     cfg.dim = self._dim
-    cfg.device = self._device.index
+    cfg.device = self._device.index or 0
     cfg.num_slot_planes = self._num_slot_planes
     cfg.init_capacity = self._init_size
     cfg.max_capacity = int(max_capacity)

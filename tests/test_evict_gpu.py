@@ -20,6 +20,8 @@ pytestmark = [
 ]
 
 DIM = 8
+DEV = "cuda"   # tests/test_mirror_emu.py re-runs these bodies over the emulated library with DEV = "cpu"
+CHURN = (1 << 15, 120, 1500)   # steady-state test: (capacity, steps, new keys per step); smaller on the emulator
 
 
 def _de():
@@ -30,7 +32,7 @@ def _de():
 def make_table(strategy, name, capacity=1024, init_capacity=None, step_per_epoch=0, gen_scores_fn=None,
                value_dtype=torch.int32, dim=DIM, num_slot_planes=0):
   de = _de()
-  return de.get_variable(name, key_dtype=torch.int64, value_dtype=value_dtype, initializer=0, dim=dim,
+  return de.get_variable(name, key_dtype=torch.int64, value_dtype=value_dtype, initializer=0, dim=dim, devices=[DEV],
                          init_size=capacity, num_slot_planes=num_slot_planes,
                          kv_creator=de.HkvHashTableCreator(config=de.HkvHashTableConfig(
                              init_capacity=init_capacity or capacity, max_capacity=capacity,
@@ -39,11 +41,11 @@ def make_table(strategy, name, capacity=1024, init_capacity=None, step_per_epoch
 
 
 def K(a):
-  return torch.as_tensor(np.asarray(a, dtype=np.int64), device="cuda")
+  return torch.as_tensor(np.asarray(a, dtype=np.int64), device=DEV)
 
 
 def V(vals, dtype=torch.int32, dim=DIM):
-  return torch.as_tensor(np.repeat(np.asarray(vals).reshape(-1, 1), dim, axis=1), device="cuda").to(dtype)
+  return torch.as_tensor(np.repeat(np.asarray(vals).reshape(-1, 1), dim, axis=1), device=DEV).to(dtype)
 
 
 def gen_scores_fn(keys):
@@ -189,7 +191,7 @@ def test_explicit_evict_takes_the_lowest_scores_and_survivors_keep_their_rows():
   t = make_table(de.HkvEvictStrategy.CUSTOMIZED, "ev_explicit", capacity=1 << 17, gen_scores_fn=lambda k: (k * 7919) % 1000003,
                  value_dtype=torch.float32, dim=16)
   keys = rng.choice(1 << 40, size=n, replace=False).astype(np.int64)
-  vals = torch.as_tensor(rng.standard_normal((n, 16)).astype(np.float32), device="cuda")
+  vals = torch.as_tensor(rng.standard_normal((n, 16)).astype(np.float32), device=DEV)
   t.upsert(K(keys), vals)
   scores = (keys * 7919) % 1000003
   assert len(np.unique(scores)) > 0.9 * n
@@ -205,9 +207,9 @@ def test_explicit_evict_takes_the_lowest_scores_and_survivors_keep_their_rows():
     assert not ex[scores < kth].any()
     assert ex[scores > kth].all()
     assert (~ex).sum() == k_ev
-    assert torch.equal(out[torch.as_tensor(ex, device="cuda")], vals[torch.as_tensor(ex, device="cuda")])
+    assert torch.equal(out[torch.as_tensor(ex, device=DEV)], vals[torch.as_tensor(ex, device=DEV)])
     keep = ex
-    keys, scores, vals = keys[keep], scores[keep], vals[torch.as_tensor(keep, device="cuda")]
+    keys, scores, vals = keys[keep], scores[keep], vals[torch.as_tensor(keep, device=DEV)]
     check_table(t)
   assert tab.stats()["evict_events"] == 3 and tab.stats()["evicted_keys"] == 1 + 777 + 20000
 
@@ -231,25 +233,25 @@ def test_accum_and_fused_optimizer_refresh_scores_and_remove_clears_them():
   t = make_table(de.HkvEvictStrategy.LFU, "ev_touch", capacity=4096, value_dtype=torch.float32, dim=8, num_slot_planes=1)
   tab = t.tables[0]
   keys = K(np.arange(100))
-  t.upsert(keys, torch.ones(100, 8, device="cuda"))
+  t.upsert(keys, torch.ones(100, 8, device=DEV))
   assert (export_ks(t)[1] == 1).all()
   # accum on resident keys (exists = True) and on new keys (exists = False)
   ks2 = K(np.arange(50, 150))
-  exists = torch.as_tensor(np.arange(50, 150) < 100, device="cuda")
-  tab.accum(ks2, torch.ones(100, 8, device="cuda"), exists)
+  exists = torch.as_tensor(np.arange(50, 150) < 100, device=DEV)
+  tab.accum(ks2, torch.ones(100, 8, device=DEV), exists)
   ek, es = export_ks(t)
   sc = dict(zip(ek.tolist(), es.tolist()))
   assert all(sc[k] == 1 for k in range(50)) and all(sc[k] == 2 for k in range(50, 100))
   assert all(sc[k] == 1 for k in range(100, 150))
   # one fused Adagrad step touches its keys (the optimizer's update_op is an upsert in the reference)
   opt = de.FusedAdagrad(learning_rate=0.1)
-  opt.apply_gradients([(torch.ones(10, 8, device="cuda"), (t, K(np.arange(10))))])
+  opt.apply_gradients([(torch.ones(10, 8, device=DEV), (t, K(np.arange(10))))])
   ek, es = export_ks(t)
   sc = dict(zip(ek.tolist(), es.tolist()))
   assert all(sc[k] == 2 for k in range(10)) and all(sc[k] == 1 for k in range(10, 50))
   # removed keys leave score 0 behind: a re-inserted key starts counting from scratch
   t.remove(K(np.arange(50, 100)))
-  t.upsert(K(np.arange(50, 100)), torch.ones(50, 8, device="cuda"))
+  t.upsert(K(np.arange(50, 100)), torch.ones(50, 8, device=DEV))
   ek, es = export_ks(t)
   sc = dict(zip(ek.tolist(), es.tolist()))
   assert all(sc[k] == 1 for k in range(50, 100))
@@ -260,19 +262,19 @@ def test_steady_state_churn_keeps_the_table_consistent():
   """many steps at the limit: mixed resident / new keys, LRU; content is checked against the rows last written"""
   de = _de()
   rng = np.random.default_rng(11)
-  cap = 1 << 15
+  cap, steps, per = CHURN
   t = make_table(de.HkvEvictStrategy.LRU, "ev_churn", capacity=cap, value_dtype=torch.float32, dim=16)
   written = {}
   nxt = 0
-  for step in range(120):
-    new = np.arange(nxt, nxt + 1500)
-    nxt += 1500
+  for step in range(steps):
+    new = np.arange(nxt, nxt + per)
+    nxt += per
     ek = t.export()[0].cpu().numpy()
-    ek = ek[ek >= 1500]   # the keys of step 0 are never written again: they must be the first to go
-    old = rng.choice(ek, size=min(len(ek), 1500), replace=False) if len(ek) else np.empty(0, dtype=np.int64)
+    ek = ek[ek >= per]   # the keys of step 0 are never written again: they must be the first to go
+    old = rng.choice(ek, size=min(len(ek), per), replace=False) if len(ek) else np.empty(0, dtype=np.int64)
     ks = np.concatenate([new, old]).astype(np.int64)
     vals = rng.standard_normal((len(ks), 16)).astype(np.float32)
-    t.upsert(K(ks), torch.as_tensor(vals, device="cuda"))
+    t.upsert(K(ks), torch.as_tensor(vals, device=DEV))
     for k, v in zip(ks.tolist(), vals):
       written[k] = v
   check_table(t)
@@ -284,7 +286,7 @@ def test_steady_state_churn_keeps_the_table_consistent():
   st = t.tables[0].stats()
   assert st["evict_events"] >= 1
   # the newest keys are resident, the oldest are gone
-  _, ex = t.lookup(K(np.arange(nxt - 1500, nxt)), return_exists=True)
+  _, ex = t.lookup(K(np.arange(nxt - per, nxt)), return_exists=True)
   assert bool(ex.all())
-  _, ex = t.lookup(K(np.arange(0, 1500)), return_exists=True)
+  _, ex = t.lookup(K(np.arange(0, per)), return_exists=True)
   assert not bool(ex.any())

@@ -1,0 +1,62 @@
+"""The Python mirror (de.get_variable / de.HkvHashTable / de.Variable / fused optimizers / restrict policies) over the
+EMULATED libdetable with CPU tensors (tests/emu/backend.py): the bodies of the GPU suites that have not run on real
+hardware yet (tests/test_evict_gpu.py, tests/test_restrict_gpu.py) are executed here as they are, so their Python glue
+and the C ABI underneath have been exercised end to end before the first GPU run."""
+import time
+
+import pytest
+
+from tests import test_evict_gpu as EG
+from tests import test_restrict_gpu as RG
+from tests.emu import backend
+
+
+@pytest.fixture(autouse=True)
+def _emu(monkeypatch):
+  with backend.installed():
+    monkeypatch.setattr(EG, "DEV", "cpu")
+    monkeypatch.setattr(RG, "DEV", "cpu")
+    monkeypatch.setattr(RG.time, "sleep", lambda s: _advance(monkeypatch, s))
+    yield
+
+
+_OFFSET = [0.0]
+_REAL_TIME = time.time
+
+
+def _advance(monkeypatch, s):
+  """the timestamp policy has one-second resolution: advance its clock instead of sleeping"""
+  from recommenders_addons_b200.dynamic_embedding import restrict_policies as rp
+  _OFFSET[0] += s
+  monkeypatch.setattr(rp.time, "time", lambda: _REAL_TIME() + _OFFSET[0])
+
+
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3, 4])
+def test_evict_strategy_basic_and_export_scores(strategy):
+  EG.test_evict_strategy_basic_and_export_scores(strategy)
+
+
+@pytest.mark.parametrize("name", [
+    "test_evict_strategy_lfu", "test_evict_strategy_epoch_lfu", "test_evict_strategy_lru", "test_evict_strategy_epoch_lru",
+    "test_evict_strategy_custom", "test_scores_follow_their_keys_through_growth",
+    "test_accum_and_fused_optimizer_refresh_scores_and_remove_clears_them",
+])
+def test_evict_suite_body(name):
+  getattr(EG, name)()
+
+
+def test_explicit_evict(monkeypatch):
+  EG.test_explicit_evict_takes_the_lowest_scores_and_survivors_keep_their_rows()
+
+
+@pytest.mark.parametrize("policy_name,first,second,overdue,updated", [
+    ("TimestampRestrictPolicy", range(6), range(4, 9), range(4), range(4, 9)),
+    ("FrequencyRestrictPolicy", range(6), range(4, 9), [0, 1, 2, 3, 6, 7, 8], [4, 5]),
+])
+def test_restrict_policies_with_fused_adagrad(policy_name, first, second, overdue, updated):
+  RG.test_apply_restriction_with_fused_adagrad(policy_name, first, second, overdue, updated)
+
+
+def test_steady_state_churn(monkeypatch):
+  monkeypatch.setattr(EG, "CHURN", (1 << 11, 40, 150))
+  EG.test_steady_state_churn_keeps_the_table_consistent()

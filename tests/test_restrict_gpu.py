@@ -16,8 +16,11 @@ pytestmark = [
 ]
 
 
+DEV = "cuda"   # tests/test_mirror_emu.py re-runs this body over the emulated library with DEV = "cpu"
+
+
 def K(a):
-  return torch.as_tensor(np.asarray(list(a), dtype=np.int64), device="cuda")
+  return torch.as_tensor(np.asarray(list(a), dtype=np.int64), device=DEV)
 
 
 def status_by_key(policy):
@@ -39,7 +42,7 @@ def _train(de, var, opt, ids):
 def test_apply_restriction_with_fused_adagrad(policy_name, first, second, overdue, updated):
   from recommenders_addons_b200 import dynamic_embedding as de
   var = de.get_variable("sp_var_gpu_" + policy_name, key_dtype=torch.int64, value_dtype=torch.float32, initializer=-0.1,
-                        dim=2, num_slot_planes=1, restrict_policy=getattr(de, policy_name))
+                        dim=2, num_slot_planes=1, devices=[DEV], restrict_policy=getattr(de, policy_name))
   opt = de.DynamicEmbeddingOptimizer(de.FusedAdagrad(learning_rate=0.1))
   _train(de, var, opt, K(first))
   if policy_name.startswith("Timestamp"):
