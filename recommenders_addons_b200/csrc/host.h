@@ -20,9 +20,13 @@
 #ifdef DET_EMU
 #define DET_LAUNCH(kernel, grid, block, smem, stream, ...) \
   ::emu::launch((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
+#define DET_LAUNCH_SPIN(kernel, grid, block, smem, stream, ...) \
+  ::emu::launch_unlocked((unsigned)(grid), (unsigned)(block), [&] { kernel(__VA_ARGS__); })
 #define DET_DYN_SHARED(name) static __attribute__((aligned(16))) unsigned char name[96 * 1024]
 #else
 #define DET_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// a kernel that waits for kernels of OTHER processes (the peer flag barrier): same launch on the GPU
+#define DET_LAUNCH_SPIN(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define DET_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 

@@ -183,6 +183,24 @@ peer_route_kernel(InboxView ib, int world, int gpu_mode, const long long* __rest
   }
 }
 
+// system-scope release store / acquire load of one flag word in (peer-mapped) memory
+__device__ __forceinline__ void st_release_sys(unsigned long long* dst, unsigned long long v) {
+#ifdef DET_EMU
+  __atomic_store_n(dst, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* src) {
+#ifdef DET_EMU
+  return __atomic_load_n(src, __ATOMIC_ACQUIRE);
+#else
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+  return v;
+#endif
+}
+
 __global__ void peer_publish_counts_kernel(InboxView ib, int world, int rank, unsigned long long* cursor) {
   const int o = threadIdx.x;
   if (o < world) {
@@ -190,7 +208,7 @@ __global__ void peer_publish_counts_kernel(InboxView ib, int world, int rank, un
     unsigned long long c = cursor[o];
     if (c > ib.cap) c = ib.cap;
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(ib.base[o]) + rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(c) : "memory");
+    st_release_sys(dst, c);
     cursor[o] = 0;
   }
 }
@@ -206,12 +224,11 @@ __global__ void peer_barrier_kernel(BarPtrs bp, int rank, int world, unsigned lo
   if (p < world) {
     __threadfence_system();
     unsigned long long* dst = bp.peer[p] + rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    st_release_sys(dst, epoch);
     const unsigned long long* src = bp.peer[rank] + p;
     const long long t0 = clock64();
     while (true) {
-      unsigned long long v;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+      const unsigned long long v = ld_acquire_sys(src);
       if (v >= epoch) break;
       if (clock64() - t0 > timeout_cycles) {
         atomicOr(&st->error, kErrBarrierTimeout);
@@ -471,14 +488,14 @@ det_status det_peer_route(det_peer_group* g, const int64_t* keys, const void* ro
     const unsigned char* r = (const unsigned char*)rows;
     DevState* st = g->local->view.st;
     switch (vec) {
-      case 16: peer_route_kernel<16><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
-      case 8: peer_route_kernel<8><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
-      case 4: peer_route_kernel<4><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
-      case 2: peer_route_kernel<2><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
-      default: peer_route_kernel<1><<<grid, kThreadsP, 0, s>>>(ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 16: DET_LAUNCH(peer_route_kernel<16>, grid, kThreadsP, 0, s, ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 8: DET_LAUNCH(peer_route_kernel<8>, grid, kThreadsP, 0, s, ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 4: DET_LAUNCH(peer_route_kernel<4>, grid, kThreadsP, 0, s, ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      case 2: DET_LAUNCH(peer_route_kernel<2>, grid, kThreadsP, 0, s, ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
+      default: DET_LAUNCH(peer_route_kernel<1>, grid, kThreadsP, 0, s, ib, g->pv.world, g->pv.gpu_mode, k, r, n, geo, g->cursor, st); break;
     }
   }
-  peer_publish_counts_kernel<<<1, 32, 0, s>>>(ib, g->pv.world, g->pv.rank, g->cursor);
+  DET_LAUNCH(peer_publish_counts_kernel, 1, 32, 0, s, ib, g->pv.world, g->pv.rank, g->cursor);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
 }
@@ -528,11 +545,11 @@ det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const
   unsigned char* o = (unsigned char*)values_out;
   const long long* k = (const long long*)keys;
   switch (vec) {
-    case 16: peer_find_kernel<16><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
-    case 8: peer_find_kernel<8><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
-    case 4: peer_find_kernel<4><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
-    case 2: peer_find_kernel<2><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
-    default: peer_find_kernel<1><<<grid, kThreadsP, 0, s>>>(g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 16: DET_LAUNCH(peer_find_kernel<16>, grid, kThreadsP, 0, s, g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 8: DET_LAUNCH(peer_find_kernel<8>, grid, kThreadsP, 0, s, g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 4: DET_LAUNCH(peer_find_kernel<4>, grid, kThreadsP, 0, s, g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    case 2: DET_LAUNCH(peer_find_kernel<2>, grid, kThreadsP, 0, s, g->pv, k, n, d, full_size_default, o, exists, geo); break;
+    default: DET_LAUNCH(peer_find_kernel<1>, grid, kThreadsP, 0, s, g->pv, k, n, d, full_size_default, o, exists, geo); break;
   }
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
@@ -552,11 +569,11 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
   const long long* k = (const long long*)keys;
   const int np = g->n_slot_planes;
   switch (vec) {
-    case 16: peer_insert_kernel<16><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
-    case 8: peer_insert_kernel<8><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
-    case 4: peer_insert_kernel<4><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
-    case 2: peer_insert_kernel<2><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
-    default: peer_insert_kernel<1><<<grid, kThreadsP, 0, s>>>(g->pv, k, v, n, geo, np); break;
+    case 16: DET_LAUNCH(peer_insert_kernel<16>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
+    case 8: DET_LAUNCH(peer_insert_kernel<8>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
+    case 4: DET_LAUNCH(peer_insert_kernel<4>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
+    case 2: DET_LAUNCH(peer_insert_kernel<2>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
+    default: DET_LAUNCH(peer_insert_kernel<1>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
   }
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
@@ -568,7 +585,7 @@ det_status det_peer_barrier(det_peer_group* g, det_stream_t stream) {
   det::DevGuard _dg(g->device);
   g->epoch += 1;
   // ~20 s at 2 GHz: a peer that never arrives must not hang the GPU
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(g->bar, g->pv.rank, g->pv.world, g->epoch, g->local->view.st,
+  DET_LAUNCH_SPIN(peer_barrier_kernel, 1, 32, 0, (cudaStream_t)stream, g->bar, g->pv.rank, g->pv.world, g->epoch, g->local->view.st,
                                                          40000000000LL);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;

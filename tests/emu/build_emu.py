@@ -27,15 +27,14 @@ def build():
 
 CSRC = os.path.join(ROOT, "recommenders_addons_b200", "csrc")
 LIB_OUT = os.path.join(HERE, "_build", "libdetable_emu.so")
-LIB_SRCS = [os.path.join(CSRC, "table.cu"), os.path.join(CSRC, "fused.cu"), os.path.join(CSRC, "evict.cu"),
-            os.path.join(HERE, "detable_emu_stubs.cc")]
+LIB_SRCS = [os.path.join(CSRC, f) for f in ("table.cu", "fused.cu", "evict.cu", "host_api.cu", "sharded.cu")]
 LIB_DEPS = LIB_SRCS + [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_runtime_emu.h"),
                        os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "host.h"),
                        os.path.join(CSRC, "evict_kernels.cuh"), os.path.join(ROOT, "include", "detable.h")]
 
 
 def build_lib():
-  """the engine's own table.cu + fused.cu + evict.cu (host code AND kernels) compiled by g++ against the emulator: the real C ABI
+  """ALL of the engine's translation units (host code AND kernels) compiled by g++ against the emulator: the real C ABI
   (det_table_create, det_find, det_insert, det_insert_scored, ...) runs on the CPU"""
   if os.path.exists(LIB_OUT) and all(os.path.getmtime(LIB_OUT) >= os.path.getmtime(d) for d in LIB_DEPS):
     return LIB_OUT

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -184,8 +185,16 @@ static void run_warp(Warp* w, emu_dim3 bi, emu_dim3 bd, emu_dim3 gd) {
 
 // run `fn` as a grid of `grid` blocks of `block` threads (a last partial warp must not use warp collectives that
 // name absent lanes, as on the GPU)
+// `__shared__` variables are plain statics, so two kernels must never run at the same time: launches from different
+// host threads ("ranks" of an emulated multi-rank group) are serialised.  The one kernel that WAITS for other ranks'
+// kernels (the peer flag barrier; it uses no shared memory) is launched with launch_unlocked.
+inline std::mutex& launch_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
 template <typename F>
-void launch(unsigned grid, unsigned block, F fn) {
+void launch_unlocked(unsigned grid, unsigned block, F fn) {
   if (block == 0 || grid == 0) abort();
   const unsigned n_warps = (block + 31) / 32;
   std::vector<std::unique_ptr<Warp>> warps;
@@ -226,6 +235,12 @@ void launch(unsigned grid, unsigned block, F fn) {
   for (auto& w : warps)
     for (int l = 0; l < 32; ++l) free(w->f[l].stack);
 }
+
+template <typename F>
+void launch(unsigned grid, unsigned block, F fn) {
+  std::lock_guard<std::mutex> lk(launch_mutex());
+  launch_unlocked(grid, block, fn);
+}
 }  // namespace emu
 
 #define threadIdx (::emu::self()->tid)
@@ -239,6 +254,12 @@ static inline void __syncwarp(unsigned mask = 0xffffffffu) {
   emu::warp_barrier();
 }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+// a spinning lane must let the other lanes of its warp (and other warps / "ranks") run
+static inline long long clock64() {
+  emu::yield_lane();
+  return (long long)emu::now_ns();
+}
 
 template <typename T>
 static inline unsigned long long emu_bits(T v) {
@@ -323,6 +344,8 @@ static inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __A
 static inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) {
   return __atomic_fetch_add(a, v, __ATOMIC_SEQ_CST);
 }
+static inline unsigned long long atomicAdd_system(unsigned long long* a, unsigned long long v) { return atomicAdd(a, v); }
+static inline unsigned atomicAdd_system(unsigned* a, unsigned v) { return atomicAdd(a, v); }
 static inline unsigned long long atomicMin(unsigned long long* a, unsigned long long v) {
   unsigned long long cur = __atomic_load_n(a, __ATOMIC_SEQ_CST);
   while (v < cur && !__atomic_compare_exchange_n(a, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {

@@ -7,7 +7,8 @@
 
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
-enum cudaError_t { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600, cudaErrorUnknown = 999 };
+enum cudaError_t { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600,
+                   cudaErrorPeerAccessAlreadyEnabled = 704, cudaErrorUnknown = 999 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2,
                       cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
@@ -74,6 +75,45 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
   free(e);
   return cudaSuccess;
 }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+  *s = malloc(1);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  free(s);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes {
+  cudaMemoryType type;
+};
+// every buffer is host memory here; report it as pinned so that the asynchronous host entry points can be exercised
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) {
+  a->type = cudaMemoryTypeHost;
+  return cudaSuccess;
+}
+// CUDA IPC: all "ranks" of an emulated group live in one process, the handle simply carries the pointer
+struct cudaIpcMemHandle_t {
+  char reserved[64];
+};
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  memset(h, 0, sizeof(*h));
+  memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  memcpy(p, h.reserved, sizeof(*p));
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
+  *can = 1;
+  return cudaSuccess;
+}
+
 template <typename K>
 static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* nb, K, int, size_t) {
   *nb = 2;

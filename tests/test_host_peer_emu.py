@@ -1,0 +1,241 @@
+"""host_api.cu and sharded.cu on the SIMT emulator through the real C ABI:
+(1) host-buffer entry points (chunked pipelines) and the `-keys` / `-values` file format of det_save / det_load
+    (reference: core/kernels/cuckoo_hashtable_op.cc:310-504: raw little-endian int64 keys, raw rows);
+(2) the one-sided sharded table: shards faked on one device (the reference's own test trick) and a REAL multi-rank
+    group -- every rank a Python thread with its own table and peer group, peers mapped through the (emulated) CUDA-IPC
+    handles -- with the flag barrier, det_peer_find / det_peer_insert against default_partition_fn, and the
+    route -> barrier -> inbox exchange of the backward path.
+The same code runs on 2-8 B200s in tests/test_peer_gpu.py / tests/test_multigpu_gpu.py; here it is a CPU regression net."""
+import ctypes
+import os
+import threading
+
+import numpy as np
+import pytest
+
+os.environ.setdefault("DET_HOST_CHUNK_MB", "1")     # several pipeline chunks at test sizes (read once by the library)
+
+from oracle import oracle as O  # noqa: E402
+from recommenders_addons_b200 import _lib as real  # noqa: E402
+from tests.test_detable_emu import L, P, Table, ck  # noqa: E402
+
+_EXTRA = ["det_find_host", "det_insert_host", "det_find_host_async", "det_insert_host_async", "det_host_sync", "det_save",
+          "det_load", "det_peer_handle_bytes", "det_peer_export", "det_peer_group_create", "det_peer_group_destroy",
+          "det_peer_find", "det_peer_insert", "det_peer_barrier", "det_peer_inbox_bytes", "det_peer_inbox_attach",
+          "det_peer_route", "det_peer_inbox_counts", "det_peer_inbox_gather", "det_table_region_bytes",
+          "det_table_create_in_region", "det_peer_group_create_regions"]
+
+
+def X():
+  l = L()
+  if not getattr(l, "_extra_ready", False):
+    for name in _EXTRA:
+      res, args = real.SIGNATURES[name]
+      fn = getattr(l, name)
+      fn.restype, fn.argtypes = res, args
+    l._extra_ready = True
+  return l
+
+
+# ---- (1) host buffers and files -------------------------------------------------------------------------------------
+def test_host_buffer_entry_points_and_async_pipeline():
+  rng = np.random.default_rng(0)
+  dim, n = 64, 11000                                  # 1 MiB chunks of 256 B rows: 3 chunks per call
+  t = Table(dim=dim, init=1 << 15)
+  keys = rng.choice(1 << 40, size=n, replace=False).astype(np.int64)
+  vals = rng.standard_normal((n, dim)).astype(np.float32)
+  ck(X().det_insert_host(t.h, P(keys), P(vals), n))
+  assert t.size() == n
+  q = np.concatenate([keys[::2], np.arange(5, dtype=np.int64) - 100])
+  default = rng.standard_normal((len(q), dim)).astype(np.float32)
+  out = np.empty((len(q), dim), dtype=np.float32)
+  ex = np.empty(len(q), dtype=np.uint8)
+  ck(X().det_find_host(t.h, P(q), len(q), P(default), 1, P(out), P(ex)))
+  assert ex[:-5].all() and not ex[-5:].any()
+  np.testing.assert_array_equal(out[:-5], vals[::2])
+  np.testing.assert_array_equal(out[-5:], default[-5:])
+  # asynchronous pair: a lookup and a write-back in flight together, then one sync
+  keys2 = rng.choice(1 << 40, size=4000, replace=False).astype(np.int64) + (1 << 41)
+  vals2 = rng.standard_normal((4000, dim)).astype(np.float32)
+  out2 = np.empty((n, dim), dtype=np.float32)
+  ex2 = np.empty(n, dtype=np.uint8)
+  zero = np.zeros(dim, dtype=np.float32)
+  ck(X().det_find_host_async(t.h, P(keys), n, P(zero), 0, P(out2), P(ex2)))
+  ck(X().det_insert_host_async(t.h, P(keys2), P(vals2), 4000))
+  ck(X().det_host_sync(t.h))
+  assert ex2.all()
+  np.testing.assert_array_equal(out2, vals)
+  assert t.size() == n + 4000
+  t.close()
+
+
+@pytest.mark.parametrize("dtype,dim", [(np.float32, 16), (np.int64, 3), (np.int8, 5)])
+def test_save_load_file_format(tmp_path, dtype, dim):
+  rng = np.random.default_rng(1)
+  t = Table(dim=dim, dtype=dtype, init=64)
+  keys = rng.choice(1 << 40, size=3000, replace=False).astype(np.int64)
+  vals = (rng.integers(-100, 100, size=(3000, dim))).astype(dtype)
+  t.insert(keys, vals)
+  prefix = str(tmp_path / "tbl_mht_1of1")
+  ck(X().det_save(t.h, prefix.encode(), 700))               # buffer of 700 keys: several file chunks
+  fk = np.fromfile(prefix + "-keys", dtype="<i8")
+  fv = np.fromfile(prefix + "-values", dtype=np.dtype(dtype).newbyteorder("<")).reshape(-1, dim)
+  assert len(fk) == 3000 and fv.shape == (3000, dim)
+  o = np.argsort(keys)
+  of = np.argsort(fk)
+  np.testing.assert_array_equal(fk[of], keys[o])
+  np.testing.assert_array_equal(fv[of], vals[o])
+  # a file pair written the way the reference writes it loads into a fresh table (load = clear + insert)
+  k2 = rng.choice(1 << 40, size=1200, replace=False).astype(np.int64)
+  v2 = rng.integers(-100, 100, size=(1200, dim)).astype(dtype)
+  prefix2 = str(tmp_path / "other")
+  k2.astype("<i8").tofile(prefix2 + "-keys")
+  v2.tofile(prefix2 + "-values")
+  t2 = Table(dim=dim, dtype=dtype, init=64)
+  t2.insert(np.array([1, 2, 3], dtype=np.int64), np.zeros((3, dim), dtype=dtype))
+  ck(X().det_load(t2.h, prefix2.encode(), 500))
+  assert t2.size() == 1200
+  out, ex = t2.find(k2)
+  assert ex.all()
+  np.testing.assert_array_equal(out, v2)
+  assert X().det_load(t2.h, str(tmp_path / "missing").encode(), 500) == 7     # DET_IO_ERROR
+  t.close()
+  t2.close()
+
+
+# ---- (2) the one-sided sharded table ------------------------------------------------------------------------------
+class PeerGroup(object):
+
+  def __init__(self, tables, handles, world, rank, gpu_mode=True):
+    arr = (ctypes.c_void_p * world)(*[(t.h if t is not None else None) for t in tables])
+    self.g = ctypes.c_void_p()
+    self._keep = handles
+    ck(X().det_peer_group_create(ctypes.byref(self.g), arr, handles, world, rank, 1 if gpu_mode else 0))
+    self.world, self.rank = world, rank
+
+  def find(self, keys, dim, default=None):
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    default = np.zeros(dim, dtype=np.float32) if default is None else default
+    out = np.empty((len(keys), dim), dtype=np.float32)
+    ex = np.empty(len(keys), dtype=np.uint8)
+    ck(X().det_peer_find(self.g, P(keys), len(keys), P(default), 0, P(out), P(ex), None))
+    return out, ex.astype(bool)
+
+  def insert(self, keys, vals):
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float32)
+    ck(X().det_peer_insert(self.g, P(keys), P(vals), len(keys), None))
+
+  def barrier(self):
+    ck(X().det_peer_barrier(self.g, None))
+
+  def close(self):
+    if self.g:
+      X().det_peer_group_destroy(self.g)
+      self.g = None
+
+
+@pytest.mark.parametrize("world,gpu_mode", [(2, True), (3, False)])
+def test_fake_shards_on_one_device(world, gpu_mode):
+  """dynamic_embedding_ops_test.py:324-440: shards faked on one device; every key lands on owner(key)"""
+  rng = np.random.default_rng(world)
+  dim = 8
+  tables = [Table(dim=dim, init=4096, max_capacity=4096) for _ in range(world)]
+  g = PeerGroup(tables, None, world, 0, gpu_mode)
+  keys = rng.integers(-2**62, 2**62, size=1500, dtype=np.int64)
+  keys = np.unique(keys)
+  vals = rng.standard_normal((len(keys), dim)).astype(np.float32)
+  g.insert(keys, vals)
+  owner = O.default_partition_fn(keys, world, gpu_mode)
+  for s in range(world):
+    assert tables[s].size() == int((owner == s).sum())
+    out, ex = tables[s].find(keys[owner == s])
+    assert ex.all()
+    np.testing.assert_array_equal(out, vals[owner == s])
+  q = np.concatenate([keys[::3], np.array([12345, -7], dtype=np.int64)])
+  out, ex = g.find(q, dim, default=np.full(dim, 0.5, np.float32))
+  assert ex[:-2].all() and not ex[-2:].any()
+  np.testing.assert_array_equal(out[:-2], vals[::3])
+  assert (out[-2:] == 0.5).all()
+  g.close()
+  for t in tables:
+    t.close()
+
+
+def test_multi_rank_group_threads_as_ranks():
+  """3 ranks (threads), each with its own shard and peer group; peers are mapped through exported handles.
+  forward: everybody inserts its batch, barrier, everybody looks up everybody's keys;
+  backward: route (key, row) pairs to their owners, barrier, owners drain their inbox."""
+  world, dim, per = 3, 4, 400
+  rng = np.random.default_rng(5)
+  all_keys = rng.choice(1 << 40, size=world * per, replace=False).astype(np.int64)
+  all_vals = rng.standard_normal((world * per, dim)).astype(np.float32)
+  owner = O.default_partition_fn(all_keys, world, True)
+  tables = [Table(dim=dim, init=4096, max_capacity=4096) for _ in range(world)]
+  hb = X().det_peer_handle_bytes()
+  blob = (ctypes.c_ubyte * (hb * world))()
+  for r in range(world):
+    ck(X().det_peer_export(tables[r].h, ctypes.c_void_p(ctypes.addressof(blob) + r * hb)))
+  rb = dim * 4
+  nbytes = X().det_peer_inbox_bytes(world, 1024, rb)
+  raw = [np.zeros(nbytes + 256, dtype=np.uint8) for _ in range(world)]
+  boxes = [b[(-b.ctypes.data) % 256:][:nbytes] for b in raw]         # 256 B aligned views (zeroed by their owner)
+  results, errors = {}, []
+  start = threading.Barrier(world)
+
+  def rank_main(r):
+    try:
+      tl = [None] * world
+      tl[r] = tables[r]
+      g = PeerGroup(tl, ctypes.cast(blob, ctypes.c_void_p), world, r)
+      ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boxes])
+      ck(X().det_peer_inbox_attach(g.g, ptrs, 1024, rb))
+      start.wait()
+      mine = slice(r * per, (r + 1) * per)
+      g.insert(all_keys[mine], all_vals[mine])          # writes land on their owners, over "NVLink"
+      g.barrier()                                       # all ranks wrote -> all ranks may read
+      out, ex = g.find(all_keys, dim)
+      g.barrier()
+      # backward: my batch's "gradients" travel to the owners
+      keys = np.ascontiguousarray(all_keys[mine])
+      rows = np.ascontiguousarray(all_vals[mine] * 2)
+      ck(X().det_peer_route(g.g, P(keys), P(rows), per, None))
+      g.barrier()
+      counts = (ctypes.c_int64 * world)()
+      ck(X().det_peer_inbox_counts(g.g, r, counts, None))
+      total = int(sum(counts))
+      rk = np.empty(total, dtype=np.int64)
+      rr = np.empty((total, dim), dtype=np.float32)
+      ck(X().det_peer_inbox_gather(g.g, r, counts, P(rk), P(rr), None))
+      g.barrier()
+      results[r] = (out, ex, rk, rr, list(counts))
+      g.close()
+    except Exception as e:  # pragma: no cover
+      errors.append((r, repr(e)))
+      try:
+        start.abort()
+      except Exception:
+        pass
+
+  th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+  for x in th:
+    x.start()
+  for x in th:
+    x.join(timeout=300)
+  assert not errors, errors
+  assert len(results) == world
+  for r in range(world):
+    out, ex, rk, rr, counts = results[r]
+    assert ex.all()
+    np.testing.assert_array_equal(out, all_vals)                        # every rank sees every key
+    assert tables[r].size() == int((owner == r).sum())
+    exp = owner == r
+    assert len(rk) == int(exp.sum())
+    assert counts == [int((owner[s * per:(s + 1) * per] == r).sum()) for s in range(world)]
+    o1, o2 = np.argsort(rk), np.argsort(all_keys[exp])
+    np.testing.assert_array_equal(rk[o1], all_keys[exp][o2])
+    np.testing.assert_array_equal(rr[o1], (all_vals[exp] * 2)[o2])
+  for t in tables:
+    st = t.stats()
+    assert st["error_flags"] == 0
+    t.close()
