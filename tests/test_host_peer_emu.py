@@ -239,3 +239,40 @@ def test_multi_rank_group_threads_as_ranks():
     st = t.stats()
     assert st["error_flags"] == 0
     t.close()
+
+
+def test_bounded_table_reserve_clear_import_and_load(tmp_path):
+  """the remaining entry points on a table with an eviction strategy: det_reserve carries the scores, det_clear /
+  det_import reset them, det_load / det_insert_host go chunk by chunk through the evicting insert"""
+  rng = np.random.default_rng(2)
+  dim = 64
+  t = Table(dim=dim, init=256, max_capacity=1 << 13, strategy=1)                      # LFU
+  keys = np.arange(100, dtype=np.int64)
+  t.insert(keys, np.ones((100, dim), dtype=np.float32))
+  t.insert(keys[:50], np.ones((50, dim), dtype=np.float32))
+  ck(L().det_reserve(t.h, 4000, None))
+  assert t.stats()["rehash_count"] >= 1
+  sc = t.scores_of(keys)
+  assert (sc[:50] == 2).all() and (sc[50:] == 1).all()
+  t.clear()
+  assert t.size() == 0 and (t.scores_of(keys) == 0).all()
+  t.insert(keys, np.ones((100, dim), dtype=np.float32))
+  assert (t.scores_of(keys) == 1).all()
+  k2 = np.arange(1000, 1040, dtype=np.int64)
+  ck(L().det_import(t.h, P(k2), P(np.full((40, dim), 3, dtype=np.float32)), 40, None))
+  assert t.size() == 40 and (t.scores_of(k2) == 1).all() and (t.scores_of(keys) == 0).all()
+  # more keys than the table may hold, from host buffers / from files: the bound holds, the newest rows are right
+  big = rng.choice(1 << 40, size=9000, replace=False).astype(np.int64)
+  bv = rng.standard_normal((9000, dim)).astype(np.float32)
+  ck(X().det_insert_host(t.h, P(big), P(bv), 9000))
+  assert t.size() <= 1 << 13 and t.stats()["evict_events"] >= 1
+  out, ex = t.find(big[-1000:])
+  assert ex.all()
+  np.testing.assert_array_equal(out, bv[-1000:])
+  prefix = str(tmp_path / "bounded")
+  big.astype("<i8").tofile(prefix + "-keys")
+  bv.tofile(prefix + "-values")
+  ck(X().det_load(t.h, prefix.encode(), 3000))
+  assert 0 < t.size() <= 1 << 13
+  t.check()
+  t.close()
