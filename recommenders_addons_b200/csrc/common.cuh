@@ -488,14 +488,45 @@ __device__ __forceinline__ void warp_move_rows(const RowGeom& g, const unsigned 
 }
 
 #ifdef DET_EMU
-// The emulator has no TMA / mbarrier unit: KeyTiles runs its plain-load tile schedule (tma = false) and the
-// asynchronous 16 B copies complete immediately.
-static inline void mbar_init(unsigned long long*, unsigned) { abort(); }
-static inline void mbar_fence_init() { abort(); }
-static inline void mbar_arrive_expect_tx(unsigned long long*, unsigned) { abort(); }
-static inline void mbar_arrive(unsigned long long*) { abort(); }
-static inline void mbar_wait(unsigned long long*, unsigned) { abort(); }
-static inline void bulk_g2s(void*, const void*, unsigned, unsigned long long*) { abort(); }
+// Emulated mbarrier + bulk copy (tests/emu/): the 64-bit barrier word holds {phase : 32, pending arrivals : 8,
+// pending transaction bytes : 24}; a phase completes when both pending counts reach zero, exactly the contract the
+// KeyTiles schedule relies on (one arrival per phase, expect_tx bytes delivered by ONE bulk copy).  The copy itself is
+// a memcpy that completes at once; asynchronous 16 B copies (cp.async) likewise.
+static inline void emu_mbar_update(unsigned long long* bar, int d_arrive, long long d_tx) {
+  unsigned long long w = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+  unsigned long long phase = w & 0xffffffffull;
+  long long arrivals = (long long)((w >> 32) & 0xffull) + d_arrive;
+  long long tx = (long long)(w >> 40) + d_tx;
+  if (arrivals <= 0 && tx <= 0) {   // phase complete: next phase expects one arrival again
+    ++phase;
+    arrivals = 1;
+    tx = 0;
+  }
+  __atomic_store_n(bar, (phase & 0xffffffffull) | ((unsigned long long)arrivals << 32) | ((unsigned long long)tx << 40),
+                   __ATOMIC_RELEASE);
+}
+static inline void mbar_init(unsigned long long* bar, unsigned count) {
+  __atomic_store_n(bar, (unsigned long long)count << 32, __ATOMIC_RELEASE);
+}
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  // the arrival is recorded together with the bytes the bulk copy (issued next by the same thread) will deliver
+  unsigned long long w = __atomic_load_n(bar, __ATOMIC_ACQUIRE);
+  const unsigned long long arrivals = ((w >> 32) & 0xffull) - 1;
+  w = (w & 0xffffffffull) | (arrivals << 32) | ((unsigned long long)bytes << 40);
+  __atomic_store_n(bar, w, __ATOMIC_RELEASE);
+}
+static inline void mbar_arrive(unsigned long long* bar) { emu_mbar_update(bar, -1, 0); }
+static inline bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  return ((unsigned)(__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull)) != (parity & 1u);
+}
+static inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) emu::yield_lane();
+}
+static inline void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  memcpy(smem_dst, gsrc, bytes);
+  emu_mbar_update(bar, 0, -(long long)bytes);
+}
 static inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
 static inline void cp_async_commit() {}
 template <int N>
@@ -590,9 +621,6 @@ struct KeyTiles {
     tile = blockIdx.x;
     it = 0;
     tma = use_tma;
-#ifdef DET_EMU
-    tma = false;
-#endif
     if (tma) {
       if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);

@@ -454,3 +454,24 @@ def test_random_scored_streams_keep_the_bounded_table_consistent(strategy, batch
     assert st["used_slots"] == st["size"] and st["error_flags"] == 0
   finally:
     t.close()
+
+
+def test_tma_tile_schedule_and_its_unaligned_fallback():
+  """find / insert stage their key tiles by TMA bulk copies (emulated mbarrier + bulk copy) when the key array is 16 B
+  aligned, and fall back to plain loads when it is not: same results, ragged tile tails included"""
+  rng = np.random.default_rng(4)
+  t = Table(dim=4, init=1 << 13)
+  buf = rng.choice(1 << 40, size=2600, replace=False).astype(np.int64)
+  assert buf.ctypes.data % 16 == 0
+  for off, n in ((0, 2599), (1, 2598), (0, 257), (1, 255), (0, 1), (1, 1)):     # aligned / unaligned, odd tails
+    keys = buf[off:off + n]
+    assert (keys.ctypes.data % 16 == 0) == (off == 0)
+    vals = rng.standard_normal((n, 4)).astype(np.float32)
+    ck(L().det_insert(t.h, P(keys), P(vals), n, None))
+    out = np.empty((n, 4), dtype=np.float32)
+    ex = np.empty(n, dtype=np.uint8)
+    ck(L().det_find(t.h, P(keys), n, P(np.zeros(4, dtype=np.float32)), 0, P(out), P(ex), None))
+    assert ex.all()
+    np.testing.assert_array_equal(out, vals)
+  t.check()
+  t.close()
