@@ -15,7 +15,8 @@ class Embedding(torch.nn.Module):
 
   def __init__(self, embedding_size, key_dtype=torch.int64, value_dtype=torch.float32, combiner="sum", initializer=None,
                devices=None, name="DynamicEmbeddingLayer", with_unique=True, trainable=True, bp_v2=False,
-               init_capacity=0, partitioner=default_partition_fn, kv_creator=None, max_norm=None, num_slot_planes=2):
+               init_capacity=0, partitioner=default_partition_fn, kv_creator=None, max_norm=None, num_slot_planes=2,
+               restrict_policy=None):
     super().__init__()
     if combiner not in ("sum", "mean", "sqrtn"):
       raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
@@ -25,7 +26,7 @@ class Embedding(torch.nn.Module):
     self.max_norm = max_norm
     self.params = Variable(key_dtype=key_dtype, value_dtype=value_dtype, dim=self.embedding_size, devices=devices,
                            partitioner=partitioner, name=name, initializer=initializer, trainable=trainable,
-                           init_size=init_capacity, kv_creator=kv_creator, bp_v2=bp_v2,
+                           init_size=init_capacity, kv_creator=kv_creator, bp_v2=bp_v2, restrict_policy=restrict_policy,
                            num_slot_planes=num_slot_planes if value_dtype == torch.float32 else 0)
     self._wrappers = []
 
@@ -55,6 +56,43 @@ class SquashedEmbedding(Embedding):
     if self.combiner == "mean":
       return emb.mean(dim=1)
     return emb.sum(dim=1) / (emb.shape[1] ** 0.5)
+
+
+BasicEmbedding = Embedding  # embedding.py:340-343
+
+
+class FieldWiseEmbedding(Embedding):
+  """embedding.py:365-515: every feature id belongs to one of `nslots` fields (`slot_map_fn`, element-wise); the rows
+  of the ids of a sample that fall into the same field are combined: ids [batch, n] -> [batch, nslots, embedding_size]
+  (fields without ids give zeros, like the reference's sparse_segment_* with num_segments)."""
+
+  def __init__(self, embedding_size, nslots, slot_map_fn=None, name="SlotDynamicEmbeddingLayer", **kwargs):
+    if not callable(slot_map_fn):
+      raise ValueError("slot_map_fn is not callable.")
+    try:
+      nslots = int(nslots)
+    except Exception:
+      raise TypeError("nslots should be convertible to int, but get {}".format(type(nslots)))
+    super().__init__(embedding_size, name=name, **kwargs)
+    self.slot_map_fn = slot_map_fn
+    self.nslots = nslots
+
+  def forward(self, ids):
+    if ids.dim() > 2:
+      raise NotImplementedError("Input dimension higher than 2 is not implemented yet.")
+    if ids.dim() == 1:
+      ids = ids.reshape(1, -1)
+    batch = ids.shape[0]
+    rows = super().forward(ids.reshape(-1))                                     # [batch * n, dim]
+    slots = self.slot_map_fn(ids).to(torch.int64)
+    seg = (slots + torch.arange(batch, device=ids.device, dtype=torch.int64).reshape(batch, 1) * self.nslots).reshape(-1)
+    out = torch.zeros((batch * self.nslots, self.embedding_size), dtype=rows.dtype, device=rows.device)
+    out = out.index_add(0, seg, rows)
+    if self.combiner != "sum":
+      cnt = torch.zeros(batch * self.nslots, dtype=rows.dtype, device=rows.device).index_add(
+          0, seg, torch.ones_like(seg, dtype=rows.dtype)).clamp_(min=1).reshape(-1, 1)
+      out = out / (cnt if self.combiner == "mean" else cnt.sqrt())
+    return out.reshape(batch, self.nslots, self.embedding_size)
 
 
 class AllToAllEmbedding(torch.nn.Module):

@@ -60,3 +60,30 @@ def test_restrict_policies_with_fused_adagrad(policy_name, first, second, overdu
 def test_steady_state_churn(monkeypatch):
   monkeypatch.setattr(EG, "CHURN", (1 << 11, 40, 150))
   EG.test_steady_state_churn_keeps_the_table_consistent()
+
+
+def test_field_wise_embedding_docstring_example():
+  """keras/layers/embedding.py:365-395 (the docstring example), forward + one training step, on the emulated library"""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  nslots = 3
+  layer = de.layers.FieldWiseEmbedding(2, nslots, slot_map_fn=lambda ids: ids % nslots, initializer=0.0, devices=["cpu"],
+                                       name="fieldwise", num_slot_planes=1)
+  ids = torch.tensor([[23, 12, 0], [9, 13, 10]], dtype=torch.int64)
+  assert torch.equal(layer(ids), torch.zeros(2, 3, 2))
+  layer.params.upsert(torch.arange(100, dtype=torch.int64), torch.ones(100, 2))
+  layer.train()
+  out = layer(ids)
+  exp = torch.tensor([[[2., 2.], [0., 0.], [1., 1.]], [[1., 1.], [2., 2.], [0., 0.]]])
+  assert torch.equal(out, exp)
+  out.sum().backward()
+  layer.apply_gradients(de.FusedAdagrad(0.5, initial_accumulator_value=1.0))
+  got = layer.params.lookup(torch.tensor([23, 12, 1], dtype=torch.int64))
+  step = 0.5 * 1.0 / (1.0 + 1.0) ** 0.5                    # a += g*g; p -= lr*g/sqrt(a) with g = 1
+  assert torch.allclose(got, torch.tensor([[1 - step] * 2, [1 - step] * 2, [1.0, 1.0]]))
+  mean = de.layers.FieldWiseEmbedding(2, nslots, slot_map_fn=lambda i: i % nslots, combiner="mean", initializer=1.0,
+                                      devices=["cpu"], name="fieldwise-mean")
+  assert torch.equal(mean(ids), torch.tensor([[[1., 1.], [0., 0.], [1., 1.]], [[1., 1.], [1., 1.], [0., 0.]]]))
+  with pytest.raises(ValueError):
+    de.layers.FieldWiseEmbedding(2, 3, slot_map_fn=None, devices=["cpu"], name="bad")
+  assert de.layers.BasicEmbedding is de.layers.Embedding
