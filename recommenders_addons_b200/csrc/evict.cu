@@ -150,6 +150,42 @@ bool evict_at_max(const det_table* t) {
   return t->view.nb >= max_nb;
 }
 
+// Repair rounds (evict_kernels.cuh) until a round moves nothing and frees nothing.  Ends with the counters of the
+// event in ev->h_dev.
+static det_status repair_rounds(det_table* t, cudaStream_t s) {
+  EvictState* ev = t->ev;
+  const TableView v = t->view;
+  const size_t cap = v.capacity();
+  const int vec = pick_vec(t->row_bytes, nullptr, nullptr, nullptr);
+  const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
+  const RowGeom gs = make_geom((unsigned)t->cfg.dim * 4u, 4);
+  const int np = t->cfg.num_slot_planes;
+  const int rgrid = grid_for(cap, kThreadsE, t->sm_count, 8);
+  for (int round = 0; round < 256; ++round) {
+    CUDA_TRY(cudaMemsetAsync(&ev->dev->n_moved, 0, 2 * sizeof(unsigned long long), s));  // n_moved, n_erased
+    dispatch_vec_e(vec, [&](auto V) -> det_status {
+      DET_LAUNCH(repair_move_kernel<decltype(V)::value>, rgrid, kThreadsE, 0, s, v, ev->scores, g, gs, np, ev->dev);
+      return DET_OK;
+    });
+    DET_LAUNCH(repair_sweep_kernel, rgrid, kThreadsE, 0, s, v, ev->scores, ev->dev);
+    CUDA_TRY(cudaGetLastError());
+    det_status st = read_dev(t, s);
+    if (st != DET_OK) return st;
+    if (ev->h_dev->n_moved == 0 && ev->h_dev->n_erased == 0) break;
+  }
+  return DET_OK;
+}
+
+// det_remove leaves tombstones in full buckets; on a table that cannot be rehashed into bigger planes they are purged
+// in place: every tombstone becomes EMPTY, then the repair rounds re-seat the keys whose chains that cut.
+static det_status purge_tombstones(det_table* t, cudaStream_t s) {
+  EvictState* ev = t->ev;
+  DET_LAUNCH(purge_tombs_kernel, grid_for(t->view.capacity(), kThreadsE * 4, t->sm_count, 8), kThreadsE, 0, s, t->view,
+             ev->dev);
+  CUDA_TRY(cudaGetLastError());
+  return repair_rounds(t, s);
+}
+
 // The eviction event: remove the k lowest-scored keys (all of them when fewer are resident).  Caller holds t->mu.
 det_status evict_lowest(det_table* t, uint64_t k, cudaStream_t s) {
   EvictState* ev = t->ev;
@@ -175,24 +211,8 @@ det_status evict_lowest(det_table* t, uint64_t k, cudaStream_t s) {
   }
   DET_LAUNCH(evict_apply_kernel, grid, kThreadsE, 0, s, v, ev->scores, ev->dev);
   CUDA_TRY(cudaGetLastError());
-  // repair rounds
-  const int vec = pick_vec(t->row_bytes, nullptr, nullptr, nullptr);
-  const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
-  const RowGeom gs = make_geom((unsigned)t->cfg.dim * 4u, 4);
-  const int np = t->cfg.num_slot_planes;
-  for (int round = 0; round < 256; ++round) {
-    CUDA_TRY(cudaMemsetAsync(&ev->dev->n_moved, 0, 2 * sizeof(unsigned long long), s));  // n_moved, n_erased
-    const int rgrid = grid_for(cap, kThreadsE, t->sm_count, 8);
-    dispatch_vec_e(vec, [&](auto V) -> det_status {
-      DET_LAUNCH(repair_move_kernel<decltype(V)::value>, rgrid, kThreadsE, 0, s, v, ev->scores, g, gs, np, ev->dev);
-      return DET_OK;
-    });
-    DET_LAUNCH(repair_sweep_kernel, rgrid, kThreadsE, 0, s, v, ev->scores, ev->dev);
-    CUDA_TRY(cudaGetLastError());
-    st = read_dev(t, s);
-    if (st != DET_OK) return st;
-    if (ev->h_dev->n_moved == 0 && ev->h_dev->n_erased == 0) break;
-  }
+  st = repair_rounds(t, s);
+  if (st != DET_OK) return st;
   ev->n_events++;
   ev->n_evicted += ev->h_dev->n_evicted;
   return DET_OK;
@@ -251,6 +271,17 @@ det_status evict_room(det_table* t, const long long* keys, size_t n, cudaStream_
   }
   const uint64_t special = ds.special[0] + ds.special[1];
   const uint64_t live = ds.size - special;
+  if (ds.used > live) {   // tombstones of user removes: purge them in place before any key is evicted for room
+    st = purge_tombstones(t, s);
+    if (st != DET_OK) return st;
+    st = read_state_e(t, s, &ds);
+    if (st != DET_OK) return st;
+    t->last_used_snap = ds.used;
+    if (ds.used + n_adm <= limit) {
+      t->used_ub = ds.used + n_adm;
+      return DET_OK;
+    }
+  }
   const uint64_t need = ds.used + n_adm - limit;
   uint64_t slab = limit / 32;
   if (slab < 1) slab = 1;

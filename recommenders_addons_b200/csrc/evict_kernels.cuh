@@ -424,6 +424,29 @@ repair_sweep_kernel(TableView t, unsigned long long* __restrict__ sc, EvictDev* 
   }
 }
 
+// Tombstones left by det_remove go back to EMPTY in place; the chains this cuts are mended by the repair rounds
+// (the same machinery as after an eviction), so a bounded table never needs a second set of planes to purge them.
+__global__ void __launch_bounds__(kThreadsE)
+purge_tombs_kernel(TableView t, EvictDev* d) {
+  __shared__ unsigned s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const size_t cap = t.capacity();
+  unsigned cnt = 0;
+  for (size_t s = (size_t)blockIdx.x * kThreadsE + threadIdx.x; s < cap; s += (size_t)gridDim.x * kThreadsE) {
+    if (t.keys[s] == kTombKey) {
+      t.keys[s] = kEmptyKey;
+      ++cnt;
+    }
+  }
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) {
+    atomicAdd(&t.st->used, (unsigned long long)(-(long long)s_cnt));
+    atomicAdd(&d->n_erased, (unsigned long long)s_cnt);
+  }
+}
+
 // growth: scores follow their keys into the new planes
 __global__ void __launch_bounds__(kThreadsE)
 carry_scores_kernel(TableView src, const unsigned long long* __restrict__ old_sc, TableView dst,

@@ -153,6 +153,14 @@ class EvictModel(LayoutModel):
       assert rounds < 64
     self.max_repair_rounds = max(getattr(self, "max_repair_rounds", 0), rounds)
 
+  def purge_tombstones(self):
+    """every TOMBSTONE becomes EMPTY, then the repair rounds re-seat the keys whose chains that cut"""
+    for s in range(self.nb * BUCKET):
+      if self.keys[s] == TOMB:
+        self.keys[s] = EMPTY
+        self.used -= 1
+    self.repair()
+
   def evict_lowest(self, k):
     live = len(self._live_slots())
     k = min(k, live)
@@ -197,6 +205,8 @@ class EvictModel(LayoutModel):
       for i in missing:
         admit[i] = self.new_score(0, ps[i]) >= smin
         n_adm += admit[i]
+    if self.used > self.size - sum(self.special):
+      self.purge_tombstones()          # tombstones of user removes go first (in place), before any key is evicted
     if not self._make_room(n_adm):
       raise RuntimeError("table full")
     self.used_ub = self.used + n_adm

@@ -475,3 +475,32 @@ def test_tma_tile_schedule_and_its_unaligned_fallback():
     np.testing.assert_array_equal(out, vals)
   t.check()
   t.close()
+
+
+def test_bounded_table_purges_tombstones_in_place_before_evicting():
+  """insert / remove churn on a table at max_capacity: det_remove leaves tombstones in full buckets; they are purged in
+  place (TOMBSTONE -> EMPTY + repair rounds) when room is needed, and no resident key is evicted for them"""
+  cap = 256
+  t = Table(dim=4, init=cap, max_capacity=cap, strategy=0)
+  keep = np.arange(10_000, 10_060, dtype=np.int64)
+  kv = np.arange(60 * 4, dtype=np.float32).reshape(60, 4)
+  t.insert(keep, kv)
+  nxt = 0
+  tombs = []
+  for step in range(25):
+    ks = np.arange(nxt, nxt + 140, dtype=np.int64)
+    nxt += 140
+    t.insert(ks, np.full((140, 4), step, dtype=np.float32))
+    t.remove(ks)
+    assert t.size() == 60
+    st = t.stats()
+    tombs.append(st["used_slots"] - st["size"])
+  assert max(tombs) > 20                       # removes did leave tombstones behind ...
+  assert min(tombs[5:]) < max(tombs) // 2      # ... and purges brought their number down again
+  st = t.stats()
+  assert st["evict_events"] == 0 and st["evicted_keys"] == 0 and st["error_flags"] == 0
+  out, ex = t.find(keep)
+  assert ex.all()
+  np.testing.assert_array_equal(out, kv)
+  t.check()
+  t.close()
