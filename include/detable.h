@@ -75,6 +75,11 @@ typedef struct det_config {
   uint64_t max_capacity;    /* keys; 0 -> grow without bound (cuckoo semantics); else DET_TABLE_FULL beyond it */
   float max_load_factor;    /* 0 -> 0.75 (0.875 with an eviction strategy) */
   uint32_t flags;           /* bits 0..3: eviction strategy + 1 (DET_FLAGS_EVICT), 0 = none; other bits reserved, 0 */
+  uint64_t max_hbm_for_vectors; /* ABI >= 3.  Bytes of HBM the VALUE rows may take (attr `max_hbm_for_vectors`,
+                             * ops/hkv_hashtable_ops.cc:318-331 -> HashTableOptions, lookup_table_op_hkv.h:443-448);
+                             * 0 = all rows in HBM.  Rows beyond the budget live in pinned HOST memory that the
+                             * same kernels reach over PCIe (one virtual range); keys, scores and
+                             * optimizer slot planes always stay in HBM.  Ignored by tables in a caller's region. */
 } det_config;
 
 /* Eviction strategies of the HKV table (python/ops/hkv_hashtable_ops.py HkvEvictStrategy; kernels/lookup_impl/
@@ -293,6 +298,8 @@ typedef struct det_stats {
   uint32_t evict_events;  /* eviction events so far (ABI >= 2) */
   uint32_t reserved;
   uint64_t evicted_keys;  /* keys evicted so far */
+  uint64_t host_bytes;    /* ABI >= 3: bytes of the value plane that live in host memory (max_hbm_for_vectors);
+                           * hbm_bytes excludes them */
 } det_stats;
 det_status det_get_stats(det_table* t, det_stats* out_host, det_stream_t stream);
 

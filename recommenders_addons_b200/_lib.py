@@ -10,6 +10,7 @@ _sz = ctypes.c_size_t
 _i = ctypes.c_int
 
 DET_OK = 0
+ABI_VERSION = 3  # det_abi_version() of the library these mirrors describe (checked at load)
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 # HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
@@ -24,14 +25,14 @@ class DetConfig(ctypes.Structure):
   _fields_ = [("value_dtype", ctypes.c_int32), ("dim", ctypes.c_int32), ("device", ctypes.c_int32),
               ("num_slot_planes", ctypes.c_int32), ("init_capacity", ctypes.c_uint64),
               ("max_capacity", ctypes.c_uint64), ("max_load_factor", ctypes.c_float),
-              ("flags", ctypes.c_uint32)]
+              ("flags", ctypes.c_uint32), ("max_hbm_for_vectors", ctypes.c_uint64)]
 
 
 class DetStats(ctypes.Structure):
   _fields_ = [("size", ctypes.c_int64), ("used_slots", ctypes.c_int64), ("capacity", ctypes.c_uint64),
               ("buckets", ctypes.c_uint64), ("hbm_bytes", ctypes.c_uint64), ("error_flags", ctypes.c_uint32),
               ("rehash_count", ctypes.c_uint32), ("evict_events", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
-              ("evicted_keys", ctypes.c_uint64)]
+              ("evicted_keys", ctypes.c_uint64), ("host_bytes", ctypes.c_uint64)]
 
 
 # name -> (restype, argtypes); must list EVERY function include/detable.h declares
@@ -114,6 +115,9 @@ def lib():
       fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
       fn.restype = res
       fn.argtypes = args
+    if l.det_abi_version() != ABI_VERSION:
+      raise RuntimeError("libdetable.so at %s has ABI version %d, this package expects %d: rebuild it "
+                         "(python -m recommenders_addons_b200.build)" % (path, l.det_abi_version(), ABI_VERSION))
     _LIB = l
   return _LIB
 

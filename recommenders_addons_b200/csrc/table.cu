@@ -638,6 +638,41 @@ __global__ void rehash_fix_state_kernel(DevState* st) {
 // ================================================================================================
 // Host side
 // ================================================================================================
+// Value plane of a table with an HBM budget (det_config.max_hbm_for_vectors; HKV's "hybrid" mode,
+// lookup_table_op_hkv.h:443-448): ONE virtual range whose first `hbm` bytes are resident in HBM and whose tail is
+// host memory the GPU maps and reaches over PCIe (unified memory pinned in place by its preferred location: the
+// head is prefetched to the device, the tail is populated on the host and mapped into the GPU's page tables, so no
+// kernel ever faults or migrates a page).  Row s lives at the same address rule as in a pure-HBM table, hence every
+// kernel of the engine runs unchanged; rows of slots >= hbm / row_bytes simply cost a PCIe transaction.
+static size_t spill_head_bytes(const det_table* t, size_t val_bytes) {
+  const uint64_t budget = t->cfg.max_hbm_for_vectors;
+  if (budget == 0 || t->external || val_bytes <= budget) return val_bytes;
+  return (size_t)(budget & ~(uint64_t)((2u << 20) - 1));  // whole 2 MiB pages
+}
+static cudaError_t alloc_value_plane(const det_table* t, void** out, size_t val_bytes) {
+  const size_t head = spill_head_bytes(t, val_bytes);
+  if (head == val_bytes) return cudaMalloc(out, val_bytes);
+  void* p = nullptr;
+  cudaError_t e = cudaMallocManaged(&p, val_bytes, cudaMemAttachGlobal);
+  if (e != cudaSuccess) return e;
+  unsigned char* b = (unsigned char*)p;
+  const int dev = t->cfg.device;
+  if (head) {
+    e = cudaMemAdvise(b, head, cudaMemAdviseSetPreferredLocation, dev);
+    if (e == cudaSuccess) e = cudaMemPrefetchAsync(b, head, dev, 0);
+  }
+  if (e == cudaSuccess) e = cudaMemAdvise(b + head, val_bytes - head, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId);
+  if (e == cudaSuccess) e = cudaMemAdvise(b + head, val_bytes - head, cudaMemAdviseSetAccessedBy, dev);
+  if (e == cudaSuccess) e = cudaMemPrefetchAsync(b + head, val_bytes - head, cudaCpuDeviceId, 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return e;
+  }
+  *out = p;
+  return cudaSuccess;
+}
+
 static det_status alloc_planes(det_table* t, uint64_t nb, TableView* v, void** raw) {
   const size_t cap = nb * kBucket;
   const size_t key_bytes = cap * sizeof(long long);
@@ -645,16 +680,19 @@ static det_status alloc_planes(det_table* t, uint64_t nb, TableView* v, void** r
   const size_t slot_bytes = (cap + 2) * (size_t)t->cfg.dim * 4u;
   for (int i = 0; i < 1 + kMaxPlanes; ++i) raw[i] = nullptr;
   cudaError_t e = cudaMalloc(&raw[0], key_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&raw[1], val_bytes);
+  if (e == cudaSuccess) e = alloc_value_plane(t, &raw[1], val_bytes);
   for (int p = 1; p <= t->cfg.num_slot_planes && e == cudaSuccess; ++p) e = cudaMalloc(&raw[1 + p], slot_bytes);
   if (e != cudaSuccess) {
     for (int i = 0; i < 1 + kMaxPlanes; ++i)
       if (raw[i]) cudaFree(raw[i]);
     cudaGetLastError();
+    const size_t head = spill_head_bytes(t, val_bytes);
     return fail(DET_OUT_OF_MEMORY,
                 "detable: cannot allocate " +
-                    std::to_string((key_bytes + val_bytes + slot_bytes * t->cfg.num_slot_planes) >> 20) +
-                    " MiB of HBM for the table; choose a smaller init/max capacity");
+                    std::to_string((key_bytes + head + slot_bytes * t->cfg.num_slot_planes) >> 20) + " MiB of HBM" +
+                    (head != val_bytes ? " + " + std::to_string((val_bytes - head) >> 20) + " MiB of host memory" : std::string()) +
+                    " for the table (" + cudaGetErrorString(e) + "); choose a smaller init/max capacity" +
+                    (t->cfg.max_hbm_for_vectors ? " or adjust max_hbm_for_vectors" : ""));
   }
   v->keys = (long long*)raw[0];
   for (int p = 0; p < kMaxPlanes; ++p) v->planes[p] = (unsigned char*)raw[1 + p];
@@ -665,9 +703,12 @@ static det_status alloc_planes(det_table* t, uint64_t nb, TableView* v, void** r
   return DET_OK;
 }
 
-static size_t planes_bytes(const det_table* t, uint64_t nb) {
+static size_t planes_bytes(const det_table* t, uint64_t nb, size_t* host_bytes) {
   const size_t cap = nb * kBucket;
-  return cap * 8 + (cap + 2) * t->row_bytes + (size_t)t->cfg.num_slot_planes * (cap + 2) * t->cfg.dim * 4u;
+  const size_t val_bytes = (cap + 2) * t->row_bytes;
+  const size_t head = spill_head_bytes(t, val_bytes);
+  if (host_bytes) *host_bytes = val_bytes - head;
+  return cap * 8 + head + (size_t)t->cfg.num_slot_planes * (cap + 2) * t->cfg.dim * 4u;
 }
 
 det_status table_clear_async(det_table* t, cudaStream_t s) {
@@ -897,7 +938,7 @@ using namespace det;
 
 extern "C" {
 
-int det_abi_version(void) { return 2; }
+int det_abi_version(void) { return 3; }
 
 const char* det_build_info(void) {
   return "detable sm_100a; nvcc " __DATE__ " " __TIME__ "; 8-slot buckets; 4-lane subgroup probing";
@@ -973,17 +1014,17 @@ static det_status create_common(det_table** out, const det_config* cfg, void* re
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->snap_ev, cudaEventDisableTiming);
   if (e == cudaSuccess && region == nullptr) e = cudaMalloc((void**)&t->view.st, sizeof(DevState));
   if (e != cudaSuccess) {
-    delete t;
+    cudaGetLastError();
+    det_table_destroy(t);  // frees whatever was created so far
     return fail(DET_OUT_OF_MEMORY, std::string("det_table_create: ") + cudaGetErrorString(e));
   }
   det_status st = DET_OK;
   if (region == nullptr) {
     st = alloc_planes(t, nb, &t->view, t->raw);
     if (st != DET_OK) {
-      cudaFree(t->view.st);
-      cudaFreeHost(t->h_state);
-      delete t;
-      return st;
+      const std::string msg = g_last_error;
+      det_table_destroy(t);
+      return fail(st, msg);
     }
   } else {
     RegionLayout L;
@@ -991,8 +1032,9 @@ static det_status create_common(det_table** out, const det_config* cfg, void* re
     c2.init_capacity = init;
     region_layout(c2, &L);
     if (((uintptr_t)region & 255u) != 0 || region_bytes < L.bytes) {
-      cudaFreeHost(t->h_state);
-      delete t;
+      t->external = true;  // nothing of the caller's region is ours to free
+      t->view.st = nullptr;
+      det_table_destroy(t);
       return fail(DET_INVALID_ARGUMENT, "det_table_create_in_region: region must be 256 B aligned and hold " +
                                             std::to_string(L.bytes) + " bytes");
     }
@@ -1294,7 +1336,9 @@ det_status det_get_stats(det_table* t, det_stats* out, det_stream_t stream) {
   out->used_slots = (int64_t)ds.used;
   out->capacity = t->view.capacity();
   out->buckets = t->view.nb;
-  out->hbm_bytes = planes_bytes(t, t->view.nb);
+  size_t host_bytes = 0;
+  out->hbm_bytes = planes_bytes(t, t->view.nb, &host_bytes);
+  out->host_bytes = host_bytes;
   out->error_flags = ds.error;
   out->rehash_count = t->rehash_count;
   out->reserved = 0;

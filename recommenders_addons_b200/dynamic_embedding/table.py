@@ -70,9 +70,12 @@ class HkvHashTableConfig(object):
 
   evict_strategy=None (the default HERE; the reference defaults to LRU): the table grows without bound and never
   evicts.  With a strategy the table is bounded by max_capacity slots and evicts its lowest-scored keys
-  (csrc/evict.cu)."""
+  (csrc/evict.cu).
+  max_hbm_for_values=None (the default HERE; the reference defaults to 1 GiB): every value row lives in HBM (a B200
+  has 180 GB).  A byte count gives the reference's hybrid mode: value rows beyond the budget live in pinned host
+  memory the kernels reach over PCIe (det_config.max_hbm_for_vectors)."""
 
-  def __init__(self, init_capacity=1024 * 1024, max_capacity=1024 * 1024, max_hbm_for_values=1024 * 1024 * 1024,
+  def __init__(self, init_capacity=1024 * 1024, max_capacity=1024 * 1024, max_hbm_for_values=None,
                evict_strategy=None, step_per_epoch=0, gen_scores_fn=None, reserved_key_start_bit=0):
     self.init_capacity = init_capacity
     self.max_capacity = max_capacity
@@ -89,7 +92,7 @@ class CuckooHashTable(object):
 
   def __init__(self, key_dtype, value_dtype, default_value, name="CuckooHashTable", checkpoint=True, init_size=0,
                config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0, max_capacity=0,
-               max_load_factor=0.0, region=None, evict_strategy=None):
+               max_load_factor=0.0, region=None, evict_strategy=None, max_hbm_for_values=None):
     if key_dtype != torch.int64:
       raise TypeError("key dtype %s is not supported on GPU: keys must be int64" % (key_dtype,))
     if value_dtype not in _TORCH_TO_NAME:
@@ -120,6 +123,9 @@ class CuckooHashTable(object):
     cfg.max_capacity = int(max_capacity)
     cfg.max_load_factor = float(max_load_factor)
     cfg.flags = 0 if evict_strategy is None else _lib.flags_evict(int(evict_strategy))
+    if max_hbm_for_values is not None and int(max_hbm_for_values) < 0:
+      raise ValueError("params max_hbm_for_vectors less than 0")  # hkv_hashtable_op_gpu.cu.cc:87-89
+    cfg.max_hbm_for_vectors = 0 if max_hbm_for_values is None else max(int(max_hbm_for_values), 1)
     self._evict_strategy = evict_strategy
     self._lib = _lib.lib()
     h = ctypes.c_void_p()
@@ -337,7 +343,7 @@ class HkvHashTable(CuckooHashTable):
     super().__init__(key_dtype, value_dtype, default_value, name=name, checkpoint=checkpoint, init_size=init, config=cfg,
                      device=device, num_slot_planes=num_slot_planes,
                      max_capacity=int(cfg.max_capacity) if strategy is not None else 0, max_load_factor=0.0,
-                     evict_strategy=strategy)
+                     evict_strategy=strategy, max_hbm_for_values=getattr(cfg, "max_hbm_for_values", None))
     self._step_per_epoch = int(cfg.step_per_epoch or 0)
     self._gen_scores_fn = cfg.gen_scores_fn
     self._curr_epoch, self._curr_step = 0, 1

@@ -29,6 +29,12 @@ static inline cudaError_t cudaFree(void* p) {
   return cudaSuccess;
 }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+// unified memory (value plane with an HBM budget): one host allocation, placement advice is a no-op
+enum { cudaMemAttachGlobal = 1, cudaCpuDeviceId = -1 };
+enum cudaMemoryAdvise { cudaMemAdviseSetPreferredLocation = 3, cudaMemAdviseSetAccessedBy = 5 };
+static inline cudaError_t cudaMallocManaged(void** p, size_t n, unsigned = cudaMemAttachGlobal) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaMemAdvise(const void*, size_t, cudaMemoryAdvise, int) { return cudaSuccess; }
+static inline cudaError_t cudaMemPrefetchAsync(const void*, size_t, int, cudaStream_t = 0) { return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 static inline cudaError_t cudaMemset(void* p, int v, size_t n) {
   memset(p, v, n);

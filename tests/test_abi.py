@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
   assert set(names) == set(_lib.SIGNATURES.keys()), set(names) ^ set(_lib.SIGNATURES.keys())
   for n in names:
     assert getattr(lib, n) is not None
-  assert lib.det_abi_version() == 2
+  assert lib.det_abi_version() == _lib.ABI_VERSION == 3
   assert b"sm_100a" in lib.det_build_info()
 
 
@@ -81,9 +81,9 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
 #include <stddef.h>
 #include "%s"
 int main(void) {
-  printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(det_config), offsetof(det_config, init_capacity),
+  printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(det_config), offsetof(det_config, init_capacity),
          offsetof(det_config, max_load_factor), sizeof(det_stats), offsetof(det_stats, hbm_bytes),
-         offsetof(det_stats, rehash_count));
+         offsetof(det_stats, rehash_count), offsetof(det_config, max_hbm_for_vectors), offsetof(det_stats, host_bytes));
   return 0;
 }
 ''' % HEADER)
@@ -93,7 +93,8 @@ int main(void) {
   out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()
   got = [int(x) for x in out]
   exp = [ctypes.sizeof(_lib.DetConfig), _lib.DetConfig.init_capacity.offset, _lib.DetConfig.max_load_factor.offset,
-         ctypes.sizeof(_lib.DetStats), _lib.DetStats.hbm_bytes.offset, _lib.DetStats.rehash_count.offset]
+         ctypes.sizeof(_lib.DetStats), _lib.DetStats.hbm_bytes.offset, _lib.DetStats.rehash_count.offset,
+         _lib.DetConfig.max_hbm_for_vectors.offset, _lib.DetStats.host_bytes.offset]
   assert got == exp, (got, exp)
 
 
@@ -125,4 +126,4 @@ def test_scored_entry_points_reject_bad_arguments_without_gpu():
   assert lib.det_evict(None, 1, None, None) == 1
   assert b"null table" in lib.det_last_error()
   assert _lib.flags_evict(_lib.EVICT_STRATEGIES["LRU"]) == 1 and _lib.flags_evict(-1) == 0
-  assert ctypes.sizeof(_lib.DetStats) == 64
+  assert ctypes.sizeof(_lib.DetStats) == 72

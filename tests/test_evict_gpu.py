@@ -36,7 +36,7 @@ def make_table(strategy, name, capacity=1024, init_capacity=None, step_per_epoch
                          init_size=capacity, num_slot_planes=num_slot_planes,
                          kv_creator=de.HkvHashTableCreator(config=de.HkvHashTableConfig(
                              init_capacity=init_capacity or capacity, max_capacity=capacity,
-                             max_hbm_for_values=capacity * 64, evict_strategy=strategy, step_per_epoch=step_per_epoch,
+                             evict_strategy=strategy, step_per_epoch=step_per_epoch,
                              gen_scores_fn=gen_scores_fn)))
 
 

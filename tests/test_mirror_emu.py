@@ -8,6 +8,7 @@ import pytest
 
 from tests import test_evict_gpu as EG
 from tests import test_restrict_gpu as RG
+from tests import test_spill_gpu as SG
 from tests.emu import backend
 
 
@@ -16,6 +17,9 @@ def _emu(monkeypatch):
   with backend.installed():
     monkeypatch.setattr(EG, "DEV", "cpu")
     monkeypatch.setattr(RG, "DEV", "cpu")
+    monkeypatch.setattr(SG, "DEV", "cpu")
+    monkeypatch.setattr(SG, "REACH", 1 << 14)
+    monkeypatch.setattr(SG, "SPLIT", (1 << 15, 64))
     monkeypatch.setattr(RG.time, "sleep", lambda s: _advance(monkeypatch, s))
     yield
 
@@ -87,3 +91,10 @@ def test_field_wise_embedding_docstring_example():
   with pytest.raises(ValueError):
     de.layers.FieldWiseEmbedding(2, 3, slot_map_fn=None, devices=["cpu"], name="bad")
   assert de.layers.BasicEmbedding is de.layers.Embedding
+
+
+@pytest.mark.parametrize("name", ["test_reach_max_hbm", "test_split_value_plane_all_ops_against_a_dict",
+                                  "test_growth_across_the_budget_and_negative_budget"])
+def test_spill_suite_body(name):
+  """max_hbm_for_vectors: option plumbing, split accounting and every op on a table created with a budget"""
+  getattr(SG, name)()
