@@ -234,3 +234,39 @@ if _HAVE_HYP:
       np.testing.assert_array_equal(ka, kb)
       np.testing.assert_array_equal(va, vb)
     r.close(), p.close()
+
+
+def test_optimizer_rules_against_an_independent_implementation():
+  """The absolute Adagrad / Adam numbers are unpinned by the reference tree (the rules are stock TensorFlow kernels,
+  SURVEY 8c): besides restating TF's documented rules, check the restatement against an implementation written by
+  someone else -- torch.optim -- over 10 steps, at the reference twin-model tests' fp32 tolerance (1e-6,
+  dynamic_embedding_optimizer_test.py:387-440).  Adagrad: the same rule (eps placed like Keras').  Adam: torch adds
+  epsilon after the bias correction of v, TF before it -- the same update when eps_torch = eps_tf / sqrt(1 - b2^t),
+  which is set per step below."""
+  import torch
+  rng = np.random.default_rng(11)
+  n, dim, lr = 64, 16, 0.05
+  p0 = rng.normal(0, 0.01, (n, dim)).astype(np.float32)
+  grads = rng.normal(0, 1e-2, (10, n, dim)).astype(np.float32)
+  for eps in (0.0, 1e-7):
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adagrad([tp], lr=lr, initial_accumulator_value=0.1, eps=eps)
+    p, a = p0.copy(), np.full((n, dim), 0.1, np.float32)
+    for g in grads:
+      tp.grad = torch.from_numpy(g.copy())
+      opt.step()
+      p, a = O.adagrad_dense(p, a, g, lr, eps)
+    np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(a, opt.state[tp]["sum"].numpy(), rtol=1e-6, atol=1e-6)
+  b1, b2, eps = 0.9, 0.999, 1e-8
+  tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+  opt = torch.optim.Adam([tp], lr=lr, betas=(b1, b2), eps=eps)
+  p, m, v = p0.copy(), np.zeros((n, dim), np.float32), np.zeros((n, dim), np.float32)
+  for t, g in enumerate(grads, 1):
+    tp.grad = torch.from_numpy(g.copy())
+    opt.param_groups[0]["eps"] = eps / float(np.sqrt(1.0 - b2 ** t))
+    opt.step()
+    p, m, v = O.adam_dense(p, m, v, g, O.adam_scalars(lr, b1, b2, t), b1, b2, eps)
+  np.testing.assert_allclose(m, opt.state[tp]["exp_avg"].numpy(), rtol=1e-6, atol=1e-7)
+  np.testing.assert_allclose(v, opt.state[tp]["exp_avg_sq"].numpy(), rtol=1e-6, atol=1e-9)
+  np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-5, atol=1e-6)
