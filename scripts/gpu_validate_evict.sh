@@ -2,12 +2,12 @@
 # First GPU action of round 2: run the capacity-management (csrc/evict.cu) and restrict-policy tests, which were
 # written after round 1's GPU budget was spent and are skipped without DET_TEST_UNVALIDATED=1.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_validate_evict.sh'
-# Outputs land in gpurun_out/evict_*.log.  When they are green: drop the skipif gates in tests/test_evict_gpu.py
-# and tests/test_restrict_gpu.py, and record the run under profiles/.
+# Outputs land in gpurun_out/evict_*.log.  When they are green: drop the skipif gates in tests/test_evict_gpu.py,
+# tests/test_restrict_gpu.py and tests/test_spill_gpu.py, and record the run under profiles/.
 set -u
 mkdir -p gpurun_out
 export DET_TEST_UNVALIDATED=1
-timeout 900 python -m pytest tests/test_evict_gpu.py tests/test_restrict_gpu.py -q -m gpu 2>&1 | tee gpurun_out/evict_tests.log | tail -40
+timeout 900 python -m pytest tests/test_evict_gpu.py tests/test_restrict_gpu.py tests/test_spill_gpu.py -q -m gpu 2>&1 | tee gpurun_out/evict_tests.log | tail -40
 # memory checker over the small cases (every kernel of evict.cu runs at least once)
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_evict_gpu.py -q -m gpu \
   -k "basic or lfu or custom or growth or touch" > gpurun_out/evict_memcheck.log 2>&1
@@ -19,3 +19,8 @@ timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pyte
 echo "racecheck exit: $?" | tee -a gpurun_out/evict_tests.log
 # the validated suite must be untouched by the new translation unit
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee -a gpurun_out/evict_tests.log
+# cost of the unvalidated features once they are green (short runs)
+timeout 600 python scripts/evict_microbench.py --capacity 20000000 --steps 100 > gpurun_out/evict_microbench.jsonl 2> gpurun_out/evict_microbench.err
+echo "evict microbench exit: $?"; tail -n 3 gpurun_out/evict_microbench.jsonl
+timeout 600 python scripts/spill_microbench.py > gpurun_out/spill_microbench.jsonl 2> gpurun_out/spill_microbench.err
+echo "spill microbench exit: $?"; cat gpurun_out/spill_microbench.jsonl
