@@ -2,18 +2,22 @@
 (/root/reference/tensorflow_recommenders_addons/dynamic_embedding/__init__.py:17-53)."""
 from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreator, HkvEvictStrategy, HkvHashTable,
                     HkvHashTableConfig, HkvHashTableCreator, KVCreator)
-from .variable import (Variable, default_partition_fn, embedding_lookup, embedding_lookup_unique,
-                       get_variable, unique)
+from .variable import (ModelMode, TrainableWrapper, Variable, default_partition_fn, embedding_lookup,
+                       embedding_lookup_unique, enable_inference_mode, enable_train_mode, get_model_mode, get_variable,
+                       trainable_wrapper_filter, unique)
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
-from .optimizer import DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam
+from .optimizer import ComposedOptimizer, DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam
 from .restrict_policies import FrequencyRestrictPolicy, RestrictPolicy, TimestampRestrictPolicy
 from .sharded import PeerShardedVariable, ShardedVariable
 from . import layers
+from . import shadow_ops
 
 __all__ = [
     "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvEvictStrategy", "HkvHashTable", "HkvHashTableConfig",
     "HkvHashTableCreator", "KVCreator", "Variable", "default_partition_fn", "embedding_lookup",
     "embedding_lookup_unique", "get_variable", "unique", "SparseIds", "embedding_lookup_sparse",
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
-    "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy",
+    "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy", "TrainableWrapper", "ModelMode",
+    "enable_inference_mode", "enable_train_mode", "get_model_mode", "trainable_wrapper_filter", "shadow_ops",
+    "ComposedOptimizer",
 ]

@@ -7,6 +7,8 @@ table passes plus dense passes.  Here ONE kernel per step does find-or-insert + 
 (det_apply_adagrad / det_apply_adam); slots live in planes co-indexed with the value rows instead of in
 separate `<var>/<opt>/<slot>` tables (exportable as such through `Variable.tables[i].export(plane=k)`).
 """
+import inspect
+
 import numpy as np
 import torch
 
@@ -111,16 +113,135 @@ class FusedAdam(_FusedBase):
                                          self.beta_2, self.epsilon, _ptr(init), full, _stream_ptr(table.device)))
 
 
-def DynamicEmbeddingOptimizer(self, bp_v2=False, synchronous=False, **kwargs):
+class ComposedOptimizer(object):
+  """ANY torch.optim optimizer on dynamic-embedding rows, the way the reference patches a stock optimizer
+  (dynamic_embedding_optimizer.py:137-204 `apply_grad_to_update_var`, :870-958 `create_slots`): per step and per
+  TrainableWrapper, find the param rows and the rows of every slot (one slot Variable per optimizer state tensor,
+  named `<var>/<Optimizer>/<slot>` like the reference's slot tables), run the stock dense rule on the [U, dim] scratch,
+  write param and slots back (`TrainableWrapper.update_op`, embedding_weights.py:434-444).  Table passes per step:
+  (1 + slots) finds + (1 + slots) upserts, all through the validated table kernels; Adagrad / Adam have the fused
+  single-kernel path (FusedAdagrad / FusedAdam), which DynamicEmbeddingOptimizer picks by default.
+
+  A key without slot state starts from the state a fresh torch optimizer gives a new parameter (zeros; Adagrad's
+  `sum` from initial_accumulator_value) -- the reference's slot initializers.  State that is not per row (`step`,
+  NAdam's `mu_product`) is carried per variable by this object, like TF's `iterations`."""
+
+  def __init__(self, optimizer, bp_v2=False):
+    if not isinstance(optimizer, torch.optim.Optimizer):
+      raise TypeError("ComposedOptimizer wraps a torch.optim.Optimizer instance")
+    self._cls = type(optimizer)
+    # hyper-parameters of the wrapped instance; a param group may carry derived entries the constructor does not take
+    accepted = set(inspect.signature(self._cls.__init__).parameters)
+    self._defaults = {k: v for k, v in optimizer.param_groups[0].items() if k != "params" and k in accepted}
+    self.bp_v2 = bp_v2
+    self.iterations = 0
+    self._slots = {}       # (variable name) -> {state key: slot Variable}
+    self._slot_init = None  # state key -> initial value (float), discovered once
+    self._scalar_keys = []
+    self._globals = {}     # (variable name) -> state entries that are not per row
+
+  def _discover_slots(self, dim):
+    """state tensors a parameter row carries: construct the optimizer on a dummy row (state created eagerly, e.g.
+    Adagrad's `sum`, gives the initial value), take one zero-gradient step (lazily created state: initial 0)"""
+    p = torch.nn.Parameter(torch.zeros(2, dim + 1))   # a shape no scalar state can be mistaken for
+    opt = self._cls([p], **self._defaults)
+    eager = {k: float(v.reshape(-1)[0]) for k, v in opt.state.get(p, {}).items()
+             if torch.is_tensor(v) and v.shape == p.shape}
+    p.grad = torch.zeros_like(p)
+    opt.step()
+    init = {}
+    for k, v in opt.state[p].items():
+      if torch.is_tensor(v) and v.shape == p.shape:
+        init[k] = eager.get(k, 0.0)
+    self._scalar_keys = sorted(k for k in opt.state[p] if k not in init)   # step counters and other global state
+    return init
+
+  def slot_names(self, dim=1):
+    if self._slot_init is None:
+      self._slot_init = self._discover_slots(dim)
+    return sorted(self._slot_init)
+
+  def get_slot(self, params, name):
+    """the slot Variable of `params` (dynamic_embedding_optimizer.py:870-958)"""
+    return self._slots[params.name][name]
+
+  def _slots_of(self, params):
+    if self._slot_init is None:
+      self._slot_init = self._discover_slots(params.dim)
+    if params.name not in self._slots:
+      made = {}
+      for k, init in self._slot_init.items():
+        made[k] = Variable(key_dtype=params.key_dtype, value_dtype=params.value_dtype, dim=params.dim,
+                           devices=[str(d) for d in params.devices], partitioner=params.partition_fn,
+                           name="%s/%s/%s" % (params.name, self._cls.__name__, k), initializer=init, trainable=False,
+                           init_size=params.init_size, kv_creator=params.kv_creator)
+      self._slots[params.name] = made
+    return self._slots[params.name]
+
+  @staticmethod
+  def _materialize(opt, p):
+    """torch's INITIAL state of `p` without taking a step (most optimizers create it lazily inside step()): their
+    `_init_group(group, params_with_grad, grads, *state lists)` does exactly that.  Best effort (private API)."""
+    try:
+      n_lists = len(inspect.signature(opt._init_group).parameters) - 1
+      opt._init_group(opt.param_groups[0], *[[] for _ in range(n_lists)])
+    except Exception:  # pylint: disable=broad-except
+      pass
+    return opt.state.get(p, {})
+
+  def apply_gradients(self, grads_and_vars):
+    """grads_and_vars: iterable of (grad [n, dim], TrainableWrapper) or (grad, (Variable, unique ids))."""
+    self.iterations += 1
+    for grad, var in grads_and_vars:
+      tw = var if isinstance(var, TrainableWrapper) else TrainableWrapper(var[0], var[1])
+      params = tw.params
+      if not isinstance(params, Variable):
+        raise TypeError("params should be a Variable instance.")
+      flat = tw.ids.reshape(-1)
+      if tw.values is None or (tw._old_values is None and params.bp_v2):
+        tw.prefetch_values()
+      p = torch.nn.Parameter(tw.values.detach().clone().reshape(-1, params.dim))
+      p.grad = grad.reshape(-1, params.dim).to(p.dtype)
+      opt = self._cls([p], **self._defaults)
+      slots = self._slots_of(params)
+      # state that is not per row (step counters, NAdam's mu_product ...) is carried by this object, per variable
+      carried = self._globals.get(params.name)
+      if carried is None:
+        carried = {k: v for k, v in self._materialize(opt, p).items() if k not in slots}
+      inject = bool(carried) or not self._scalar_keys
+      if inject:   # (else: first step of an optimizer whose initial scalars are unknown -> torch's fresh state,
+        #             identical to the slot tables' initial values)
+        state = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in carried.items()}
+        for k, sv in slots.items():
+          state[k] = sv.lookup(flat).reshape(-1, params.dim).clone()
+        opt.state[p] = state
+      opt.step()
+      after = opt.state[p]
+      self._globals[params.name] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in after.items()
+                                    if k not in slots}
+      tw.values = p.detach()
+      tw.update_op()
+      for k, sv in slots.items():
+        if torch.is_tensor(after.get(k)):
+          sv.upsert(flat, after[k])
+
+
+def DynamicEmbeddingOptimizer(self, bp_v2=False, synchronous=False, fused=True, **kwargs):
   """de.DynamicEmbeddingOptimizer(optimizer): make an optimizer able to train dynamic embeddings
-  (dynamic_embedding_optimizer.py:103).  Accepts a FusedAdagrad/FusedAdam (returned unchanged) or a
-  torch.optim.Adagrad / Adam instance, whose hyper-parameters are carried over to the fused kernels."""
-  if isinstance(self, _FusedBase):
+  (dynamic_embedding_optimizer.py:103).  Accepts a FusedAdagrad/FusedAdam (returned unchanged) or any
+  torch.optim.Optimizer instance: Adagrad / Adam are carried over to the fused single-kernel path (fused=True, the
+  default); every other optimizer -- or fused=False -- gets the reference's composed find -> dense rule -> upsert
+  path (ComposedOptimizer)."""
+  if isinstance(self, (_FusedBase, ComposedOptimizer)):
     return self
-  if isinstance(self, torch.optim.Adagrad):
+  if fused and type(self) is torch.optim.Adagrad:
     g = self.param_groups[0]
-    return FusedAdagrad(g["lr"], g.get("initial_accumulator_value", 0.0), g.get("eps", 1e-10))
-  if isinstance(self, torch.optim.Adam):
+    if not (g.get("lr_decay", 0) or g.get("weight_decay", 0) or g.get("maximize", False)):
+      return FusedAdagrad(g["lr"], g.get("initial_accumulator_value", 0.0), g.get("eps", 1e-10))
+  if fused and type(self) is torch.optim.Adam:
     g = self.param_groups[0]
-    return FusedAdam(g["lr"], g["betas"][0], g["betas"][1], g["eps"])
-  raise TypeError("DynamicEmbeddingOptimizer supports Adagrad and Adam on the hot path (SURVEY.md 2, #13)")
+    if not (g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False)):
+      return FusedAdam(g["lr"], g["betas"][0], g["betas"][1], g["eps"])
+  if isinstance(self, torch.optim.Optimizer):
+    return ComposedOptimizer(self, bp_v2=bp_v2)
+  raise TypeError("DynamicEmbeddingOptimizer needs a torch.optim.Optimizer, de.FusedAdagrad or de.FusedAdam")

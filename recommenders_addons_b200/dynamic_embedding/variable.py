@@ -320,15 +320,88 @@ class Variable(object):
     return embedding_lookup(self, ids, name=name, max_norm=max_norm, return_trainable=return_trainable)
 
 
+class ModelMode(object):
+  """The global train / inference switch (python/ops/embedding_weights.py:98-120).  In INFERENCE mode a lookup builds
+  no trainable scratch and `TrainableWrapper.update_op` writes nothing back: the table is read-only."""
+  TRAIN = "train"
+  INFERENCE = "inference"
+  CURRENT_SETTING = TRAIN
+
+
+def get_model_mode():
+  """dynamic_embedding_ops.py:441-447"""
+  return ModelMode.CURRENT_SETTING
+
+
+def enable_train_mode():
+  """dynamic_embedding_ops.py:450-453"""
+  ModelMode.CURRENT_SETTING = ModelMode.TRAIN
+
+
+def enable_inference_mode():
+  """dynamic_embedding_ops.py:456-459"""
+  ModelMode.CURRENT_SETTING = ModelMode.INFERENCE
+
+
 class TrainableWrapper(object):
   """Dense scratch view of the rows of `params` selected by `ids` (python/ops/embedding_weights.py:123-170):
-  filled from the table before each read; the optimizer writes the update back to the table."""
+  filled from the table before each read (`prefetch_values`); after the optimizer stepped the scratch, `update_op`
+  writes it back to the table (upsert, or accum of the difference with bp_v2; :434-444)."""
 
-  def __init__(self, params, ids, values, exists=None):
+  def __init__(self, params, ids, values=None, exists=None, max_norm=None, model_mode=None):
     self.params = params
     self.ids = ids
     self.values = values  # [n, dim] leaf tensor, requires_grad for trainable params
     self.exists = exists
+    self.max_norm = max_norm
+    self.model_mode = model_mode if model_mode else ModelMode.CURRENT_SETTING
+    self._old_values = None
+
+  def transform(self, result):
+    """embedding_weights.py:172-174: max_norm clipping of what was read"""
+    return _clip(result, self.max_norm)
+
+  def prefetch_values(self, update=False):
+    """table -> dense scratch (:163-170); keeps `exists` for the bp_v2 write-back"""
+    flat = self.ids.reshape(-1)
+    if self.params.bp_v2:
+      vals, self.exists = self.params.lookup(flat, return_exists=True)
+    else:
+      vals = self.params.lookup(flat)
+    vals = vals.reshape(-1, self.params.dim)
+    self._old_values = vals
+    trainable = (self.model_mode == ModelMode.TRAIN and self.params.trainable and vals.dtype.is_floating_point)
+    self.values = vals.detach().clone().requires_grad_(True) if trainable else vals.detach()
+    return self.transform(self.values)
+
+  def read_value(self, do_prefetch=True):
+    """:479-495"""
+    if do_prefetch or self.values is None:
+      return self.prefetch_values()
+    return self.transform(self.values)
+
+  def update_op(self, v0=None):
+    """dense scratch -> table (:434-444): upsert, or accum(old, new, exists) with bp_v2; the restrict policy sees
+    the updated ids.  Nothing is written in inference mode."""
+    if self.model_mode != ModelMode.TRAIN:
+      return
+    flat = self.ids.reshape(-1)
+    new = self.values.detach()
+    if self.params.bp_v2:
+      old = v0 if v0 is not None else self._old_values
+      self.params.accum(flat, old, new, self.exists)
+    else:
+      self.params.upsert(flat, new)
+    if self.params.restrict_policy is not None:
+      self.params.restrict_policy.apply_update(flat)
+
+  def size(self):
+    return self.params.size()
+
+
+def trainable_wrapper_filter(variables):
+  """dynamic_embedding_ops.py trainable_wrapper_filter: the TrainableWrapper objects among `variables`"""
+  return [v for v in variables if isinstance(v, TrainableWrapper)]
 
 
 def _clip(values, max_norm):
@@ -355,8 +428,11 @@ def embedding_lookup(params, ids, partition_strategy=None, name=None, validate_i
   vals = vals.reshape(-1, params.dim)
   tw = None
   if return_trainable:
-    vals = vals.detach().requires_grad_(params.trainable and vals.dtype.is_floating_point)
-    tw = TrainableWrapper(params, flat, vals, exists)
+    trainable = params.trainable and vals.dtype.is_floating_point and ModelMode.CURRENT_SETTING == ModelMode.TRAIN
+    old = vals
+    vals = vals.detach().requires_grad_(trainable)
+    tw = TrainableWrapper(params, flat, vals, exists, max_norm=max_norm)
+    tw._old_values = old.detach().clone() if params.bp_v2 else None  # the optimizer steps `vals` in place
   out = _clip(vals, max_norm).reshape(tuple(ids.shape) + (params.dim,))
   return (out, tw) if return_trainable else out
 

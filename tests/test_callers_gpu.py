@@ -1,0 +1,201 @@
+"""Callers either side of the fused kernels, composed from the validated table ops (SURVEY 8a rows a13 / a15 / a16's
+single-GPU part): `TrainableWrapper` (prefetch -> dense scratch -> update_op, with and without bp_v2), `ModelMode`,
+`shadow_ops.ShadowVariable`, and `DynamicEmbeddingOptimizer` over ANY stock optimizer (ComposedOptimizer: one slot
+Variable per optimizer state, find -> dense rule -> upsert) -- tested the way the reference tests its optimizer patch:
+a twin model on a plain dense parameter trained with the unpatched optimizer, 10 steps, compared at fp32 tolerance
+(kernel_tests/dynamic_embedding_optimizer_test.py:349-440, swept over the optimizer list of :112-278).
+
+STATUS: written after round 1's GPU budget was spent; the bodies run over the emulated library with CPU tensors
+(tests/test_mirror_emu.py); on a GPU they run with DET_TEST_UNVALIDATED=1 (tests/test_zz_unvalidated_gpu.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("DET_TEST_UNVALIDATED") != "1",
+                       reason="caller-side mirrors not yet run on a B200 (set DET_TEST_UNVALIDATED=1)"),
+]
+
+DEV = "cuda"   # tests/test_mirror_emu.py re-runs these bodies over the emulated library with DEV = "cpu"
+V, DIM, STEPS = 48, 6, 10
+
+OPTIMIZERS = {
+    "sgd": lambda p: torch.optim.SGD(p, lr=0.1),
+    "momentum": lambda p: torch.optim.SGD(p, lr=0.1, momentum=0.9),
+    "nesterov": lambda p: torch.optim.SGD(p, lr=0.1, momentum=0.9, nesterov=True),
+    "rmsprop": lambda p: torch.optim.RMSprop(p, lr=0.01),
+    "rmsprop_centered_momentum": lambda p: torch.optim.RMSprop(p, lr=0.01, centered=True, momentum=0.5),
+    "adagrad": lambda p: torch.optim.Adagrad(p, lr=0.1, initial_accumulator_value=0.1),
+    "adadelta": lambda p: torch.optim.Adadelta(p, lr=1.0),
+    "adam": lambda p: torch.optim.Adam(p, lr=0.01),
+    "adam_amsgrad": lambda p: torch.optim.Adam(p, lr=0.01, amsgrad=True),
+    "adamw": lambda p: torch.optim.AdamW(p, lr=0.01, weight_decay=0.01),
+    "adamax": lambda p: torch.optim.Adamax(p, lr=0.01),
+    "nadam": lambda p: torch.optim.NAdam(p, lr=0.01),
+}
+
+
+def _de():
+  from recommenders_addons_b200 import dynamic_embedding as de
+  return de
+
+
+def _ids_stream(rng):
+  """every step looks ALL rows up (some twice): a dense optimizer then touches exactly the rows the sparse one does"""
+  out = []
+  for _ in range(STEPS):
+    ids = np.concatenate([rng.permutation(V), rng.integers(0, V, 16)]).astype(np.int64)
+    out.append(ids.reshape(4, -1))
+  return out
+
+
+def _train_twin(make_opt, stream, weights, init):
+  dense = torch.nn.Parameter(torch.full((V, DIM), init, device=DEV))
+  opt = make_opt([dense])
+  for ids, w in zip(stream, weights):
+    opt.zero_grad()
+    emb = dense[torch.as_tensor(ids, device=DEV)]
+    (emb * w).sum().backward()
+    opt.step()
+  return dense.detach()
+
+
+@pytest.mark.parametrize("name", sorted(OPTIMIZERS))
+def test_composed_optimizer_matches_dense_twin(name):
+  de = _de()
+  rng = np.random.default_rng(3)
+  stream = _ids_stream(rng)
+  weights = [torch.as_tensor(rng.normal(0, 1, s.shape + (DIM,)).astype(np.float32), device=DEV) for s in stream]
+  twin = _train_twin(OPTIMIZERS[name], stream, weights, 0.25)
+  var = de.get_variable("twin-" + name, dim=DIM, initializer=0.25, devices=[DEV])
+  opt = de.DynamicEmbeddingOptimizer(OPTIMIZERS[name]([torch.nn.Parameter(torch.zeros(1))]), fused=False)
+  assert isinstance(opt, de.ComposedOptimizer)
+  for ids, w in zip(stream, weights):
+    emb, tw = de.embedding_lookup_unique(var, torch.as_tensor(ids, device=DEV), return_trainable=True)
+    (emb * w).sum().backward()
+    opt.apply_gradients([(tw.values.grad, tw)])
+  got = var.lookup(torch.arange(V, device=DEV))
+  assert int(var.size()) == V
+  np.testing.assert_allclose(got.cpu().numpy(), twin.cpu().numpy(), rtol=2e-6, atol=2e-6)
+  for slot in opt.slot_names():
+    assert int(opt.get_slot(var, slot).size()) == V      # one slot table per optimizer state, like create_slots
+
+
+@pytest.mark.parametrize("kind", ["adagrad", "adam"])
+def test_composed_and_fused_paths_agree(kind):
+  """the fused single-kernel step (TF rule) and the composed path over torch's rule, same stream: 1e-6 -- Adagrad is
+  the same rule; for Adam torch applies epsilon after the bias correction (tests/test_oracle.py), hence eps = 0"""
+  de = _de()
+  rng = np.random.default_rng(5)
+  stream = _ids_stream(rng)
+  weights = [torch.as_tensor(rng.normal(0, 1, s.shape + (DIM,)).astype(np.float32), device=DEV) for s in stream]
+  if kind == "adagrad":
+    fused, stock = de.FusedAdagrad(0.1, 0.1, 1e-10), torch.optim.Adagrad([torch.nn.Parameter(torch.zeros(1))], lr=0.1,
+                                                                         initial_accumulator_value=0.1)
+  else:
+    fused, stock = de.FusedAdam(0.01, 0.9, 0.999, 0.0), torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=0.01,
+                                                                         eps=0.0)
+  assert type(de.DynamicEmbeddingOptimizer(stock)).__name__ == type(fused).__name__   # the default: the fused path
+  res = []
+  for tag, opt in (("f", fused), ("c", de.DynamicEmbeddingOptimizer(stock, fused=False))):
+    var = de.get_variable("agree-%s-%s" % (kind, tag), dim=DIM, initializer=0.25, devices=[DEV], num_slot_planes=2)
+    for ids, w in zip(stream, weights):
+      emb, tw = de.embedding_lookup_unique(var, torch.as_tensor(ids, device=DEV), return_trainable=True)
+      (emb * w).sum().backward()
+      opt.apply_gradients([(tw.values.grad, tw)])
+    res.append(var.lookup(torch.arange(V, device=DEV)).cpu().numpy())
+  np.testing.assert_allclose(res[0], res[1], rtol=1e-5, atol=1e-6)
+
+
+def test_untouched_rows_and_slot_tables_stay_sparse():
+  de = _de()
+  var = de.get_variable("sparse-touch", dim=DIM, initializer=1.0, devices=[DEV])
+  var.upsert(torch.arange(100, device=DEV), torch.ones(100, DIM, device=DEV))
+  opt = de.DynamicEmbeddingOptimizer(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.5, momentum=0.9))
+  ids = torch.tensor([3, 7, 7, 200], device=DEV)
+  for _ in range(2):
+    emb, tw = de.embedding_lookup_unique(var, ids, return_trainable=True)
+    emb.sum().backward()
+    opt.apply_gradients([(tw.values.grad, tw)])
+  got = var.lookup(torch.tensor([3, 7, 200, 5], device=DEV)).cpu()
+  # momentum SGD, lr .5: grads 1 / 2 / 1 per step (id 7 appears twice); buf1 = g, buf2 = .9 g + g
+  exp = lambda g: 1.0 - 0.5 * g - 0.5 * (0.9 * g + g)   # noqa: E731
+  assert torch.allclose(got, torch.tensor([[exp(1.0)] * DIM, [exp(2.0)] * DIM, [exp(1.0)] * DIM, [1.0] * DIM]))
+  assert int(var.size()) == 101                                        # id 200 was created by its first update
+  assert int(opt.get_slot(var, "momentum_buffer").size()) == 3         # only the touched keys carry slot state
+
+
+def test_model_mode_and_trainable_wrapper_filter():
+  de = _de()
+  var = de.get_variable("modes", dim=DIM, initializer=2.0, devices=[DEV])
+  ids = torch.tensor([[1, 2], [2, 9]], device=DEV)
+  assert de.get_model_mode() == de.ModelMode.TRAIN
+  try:
+    de.enable_inference_mode()
+    assert de.get_model_mode() == "inference"
+    emb, tw = de.embedding_lookup(var, ids, return_trainable=True)
+    assert emb.shape == (2, 2, DIM) and not emb.requires_grad and not tw.values.requires_grad
+    tw.values = tw.values + 1.0
+    tw.update_op()                                   # read-only in inference mode
+    assert int(var.size()) == 0
+    sh = de.shadow_ops.ShadowVariable(var, name="modes-shadow")
+    out = de.shadow_ops.embedding_lookup(sh, ids)
+    assert out.shape == (2, 2, DIM) and not out.requires_grad and sh.ids.numel() == 0
+  finally:
+    de.enable_train_mode()
+  emb, tw = de.embedding_lookup(var, ids, return_trainable=True)
+  assert tw.values.requires_grad and tw.model_mode == "train"
+  assert de.trainable_wrapper_filter([tw, var, 3, sh]) == [tw, sh]
+
+
+@pytest.mark.parametrize("bp_v2", [False, True])
+def test_trainable_wrapper_prefetch_and_update_op(bp_v2):
+  """embedding_weights.py:163-170 / :434-444: prefetch -> step the scratch -> update_op; with bp_v2 the write-back is
+  accum(old, new, exists): new keys are inserted with their value, resident keys get the DIFFERENCE added"""
+  de = _de()
+  var = de.get_variable("tw-%d" % bp_v2, dim=DIM, initializer=0.5, devices=[DEV], bp_v2=bp_v2)
+  var.upsert(torch.tensor([1, 2], device=DEV), torch.tensor([[1.0] * DIM, [2.0] * DIM], device=DEV))
+  tw = de.TrainableWrapper(var, torch.tensor([2, 1, 40], device=DEV))
+  vals = tw.prefetch_values()
+  assert torch.equal(vals.cpu(), torch.tensor([[2.0] * DIM, [1.0] * DIM, [0.5] * DIM]))
+  if bp_v2:
+    assert tw.exists.cpu().tolist() == [True, True, False]
+    var.upsert(torch.tensor([1], device=DEV), torch.full((1, DIM), 10.0, device=DEV))   # a concurrent writer
+  vals.sum().backward()
+  with torch.no_grad():
+    tw.values -= 0.25 * tw.values.grad
+  tw.update_op()
+  got = var.lookup(torch.tensor([1, 2, 40], device=DEV)).cpu()
+  row1 = 10.0 - 0.25 if bp_v2 else 0.75            # bp_v2 adds the delta to whatever is in the table NOW
+  assert torch.allclose(got, torch.tensor([[row1] * DIM, [1.75] * DIM, [0.25] * DIM]))
+  assert int(tw.size()) == 3
+
+
+def test_shadow_variable_training_matches_dense_twin():
+  """shadow_embedding_ops.py:242-350 + keras/layers/embedding.py:287-330: the layer's path -- shadow lookup (unique),
+  loss, gradient of the shadow's scratch, optimizer, write-back"""
+  de = _de()
+  rng = np.random.default_rng(9)
+  stream = _ids_stream(rng)
+  weights = [torch.as_tensor(rng.normal(0, 1, s.shape + (DIM,)).astype(np.float32), device=DEV) for s in stream]
+  make = OPTIMIZERS["rmsprop"]
+  twin = _train_twin(make, stream, weights, 0.25)
+  var = de.get_variable("shadow-twin", dim=DIM, initializer=0.25, devices=[DEV])
+  shadow = de.shadow_ops.ShadowVariable(var, name="shadow-twin/shadow")
+  assert var._trainable_store["shadow-twin/shadow"] is shadow
+  opt = de.DynamicEmbeddingOptimizer(make([torch.nn.Parameter(torch.zeros(1))]))
+  for ids, w in zip(stream, weights):
+    ids = torch.as_tensor(ids, device=DEV)
+    emb = de.shadow_ops.embedding_lookup_unique(shadow, ids, DIM, with_unique=True)
+    assert emb.shape == tuple(ids.shape) + (DIM,) and shadow.ids.numel() == V
+    (emb * w).sum().backward()
+    opt.apply_gradients([(shadow.values.grad, shadow)])
+  got = var.lookup(torch.arange(V, device=DEV))
+  np.testing.assert_allclose(got.cpu().numpy(), twin.cpu().numpy(), rtol=2e-6, atol=2e-6)
+  with pytest.raises(ValueError):
+    de.shadow_ops.embedding_lookup(shadow, torch.tensor([1], dtype=torch.int32, device=DEV))
+  with pytest.raises(TypeError):
+    de.shadow_ops.ShadowVariable(object())

@@ -6,6 +6,7 @@ import time
 
 import pytest
 
+from tests import test_callers_gpu as CG
 from tests import test_evict_gpu as EG
 from tests import test_restrict_gpu as RG
 from tests import test_spill_gpu as SG
@@ -18,6 +19,7 @@ def _emu(monkeypatch):
     monkeypatch.setattr(EG, "DEV", "cpu")
     monkeypatch.setattr(RG, "DEV", "cpu")
     monkeypatch.setattr(SG, "DEV", "cpu")
+    monkeypatch.setattr(CG, "DEV", "cpu")
     monkeypatch.setattr(SG, "REACH", 1 << 14)
     monkeypatch.setattr(SG, "SPLIT", (1 << 15, 64))
     monkeypatch.setattr(RG.time, "sleep", lambda s: _advance(monkeypatch, s))
@@ -98,3 +100,25 @@ def test_field_wise_embedding_docstring_example():
 def test_spill_suite_body(name):
   """max_hbm_for_vectors: option plumbing, split accounting and every op on a table created with a budget"""
   getattr(SG, name)()
+
+
+@pytest.mark.parametrize("name", sorted(CG.OPTIMIZERS))
+def test_composed_optimizer_matches_dense_twin(name):
+  CG.test_composed_optimizer_matches_dense_twin(name)
+
+
+@pytest.mark.parametrize("kind", ["adagrad", "adam"])
+def test_composed_and_fused_paths_agree(kind):
+  CG.test_composed_and_fused_paths_agree(kind)
+
+
+@pytest.mark.parametrize("name", ["test_untouched_rows_and_slot_tables_stay_sparse",
+                                  "test_model_mode_and_trainable_wrapper_filter",
+                                  "test_shadow_variable_training_matches_dense_twin"])
+def test_callers_suite_body(name):
+  getattr(CG, name)()
+
+
+@pytest.mark.parametrize("bp_v2", [False, True])
+def test_trainable_wrapper_prefetch_and_update_op(bp_v2):
+  CG.test_trainable_wrapper_prefetch_and_update_op(bp_v2)

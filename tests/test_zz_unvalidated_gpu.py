@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 def test_unvalidated_suites_in_a_subprocess():
   env = dict(os.environ, DET_TEST_UNVALIDATED="1")
   r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_evict_gpu.py", "tests/test_restrict_gpu.py",
-                      "tests/test_spill_gpu.py", "-q", "-m",
+                      "tests/test_spill_gpu.py", "tests/test_callers_gpu.py", "-q", "-m",
                       "gpu", "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=900, capture_output=True, text=True)
   print(r.stdout[-6000:])
   print(r.stderr[-2000:])
