@@ -153,6 +153,13 @@ det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream);
 det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
                       int64_t* n_out_host, det_stream_t stream);
 
+/* The same export restricted to the window [first, first + max_n) of the table order: *n_out_host = rows written
+ * (0 once `first` is past the end).  HKV's `dump(keys, values, offset, search_length, counter)` /
+ * `export_batch` (lookup_table_op_hkv.h:550-594) -- lets a caller stream a table larger than its scratch memory
+ * (det_save does).  The table must not be mutated between the windows of one pass.  ABI >= 3. */
+det_status det_export_window(det_table* t, int plane, uint64_t first, int64_t* keys_out, void* values_out,
+                             size_t max_n, int64_t* n_out_host, det_stream_t stream);
+
 /* ImportValues = clear + insert (cuckoo_hashtable_op.cc:288-291). */
 det_status det_import(det_table* t, const int64_t* keys, const void* values, size_t n,
                       det_stream_t stream);
@@ -283,8 +290,11 @@ det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* co
 /* ---- file-system format of SaveToFileSystem / LoadFromFileSystem
  * (cuckoo_hashtable_op.cc:310-504): raw little-endian `<prefix>-keys` (int64[n]) and
  * `<prefix>-values` (V[n*dim]).  HOST paths; synchronous. ---- */
-det_status det_save(det_table* t, const char* prefix, size_t buffer_keys);
-det_status det_load(det_table* t, const char* prefix, size_t buffer_keys);
+/* attrs of the ops: buffer_size (keys per chunk; memory use is bounded by it), append_to_file, and -- for
+ * load_entire_dir (cuckoo_hashtable_op.cc:477-498) -- clear_first = 0 to add one more `<name>_mht_*` file to a table
+ * that was cleared by the first call. */
+det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int append_to_file);
+det_status det_load(det_table* t, const char* prefix, size_t buffer_keys, int clear_first);
 
 /* introspection for tests / benches (HOST outs; synchronises) */
 typedef struct det_stats {

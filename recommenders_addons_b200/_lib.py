@@ -51,6 +51,7 @@ SIGNATURES = {
     "det_capacity": (_i, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "det_reserve": (_i, [_vp, ctypes.c_uint64, _vp]),
     "det_export": (_i, [_vp, _i, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_int64), _vp]),
+    "det_export_window": (_i, [_vp, _i, ctypes.c_uint64, _vp, _vp, _sz, ctypes.POINTER(ctypes.c_int64), _vp]),
     "det_import": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_unique_workspace_bytes": (_sz, [_sz]),
     "det_unique": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -82,8 +83,8 @@ SIGNATURES = {
     "det_peer_route": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_peer_inbox_counts": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp]),
     "det_peer_inbox_gather": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp]),
-    "det_save": (_i, [_vp, ctypes.c_char_p, _sz]),
-    "det_load": (_i, [_vp, ctypes.c_char_p, _sz]),
+    "det_save": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
+    "det_load": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
     "det_get_stats": (_i, [_vp, ctypes.POINTER(DetStats), _vp]),
     "det_insert_scored": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "det_accum_scored": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -284,54 +284,59 @@ det_status det_host_sync(det_table* t) {
   return DET_OK;
 }
 
-det_status det_save(det_table* t, const char* prefix, size_t buffer_keys) {
+// SaveToFileSystem (cuckoo_hashtable_op.cc:310-391; GPU: dump_to_file, lookup_table_op_hkv.h:602-652): the table is
+// exported window by window (det_export_window: `buffer_keys` keys at a time, table order) into a bounded device
+// buffer, copied to a bounded host buffer and appended to `<prefix>-keys` / `<prefix>-values`; memory use does not
+// depend on the table size.  Without append_to_file the files are written under a temporary name and renamed.
+det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int append_to_file) {
   if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_save: null argument");
   det::DevGuard _dg(t->cfg.device);
-  int64_t n = 0;
-  det_status st = det_size(t, &n, nullptr);
-  if (st != DET_OK) return st;
-  (void)buffer_keys;
+  if (buffer_keys == 0) buffer_keys = 1u << 20;
   const size_t rb = t->row_bytes;
   long long* dk = nullptr;
   unsigned char* dv = nullptr;
-  const size_t cnt = n > 0 ? (size_t)n : 1;
-  CUDA_TRY(cudaMalloc((void**)&dk, cnt * 8));
-  cudaError_t e = cudaMalloc((void**)&dv, cnt * rb);
+  CUDA_TRY(cudaMalloc((void**)&dk, buffer_keys * 8));
+  cudaError_t e = cudaMalloc((void**)&dv, buffer_keys * rb);
   if (e != cudaSuccess) {
     cudaFree(dk);
     cudaGetLastError();
-    return fail(DET_OUT_OF_MEMORY, "det_save: no HBM for the export buffer");
+    return fail(DET_OUT_OF_MEMORY, "det_save: no HBM for the export buffer; use a smaller buffer_size");
   }
-  int64_t got = 0;
-  st = det_export(t, 0, (int64_t*)dk, dv, (size_t)n, &got, nullptr);
-  std::vector<long long> hk((size_t)got);
-  std::vector<unsigned char> hv((size_t)got * rb);
-  if (st == DET_OK && got > 0) {
+  const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
+  const std::string kt = append_to_file ? kf : kf + ".tmp", vt = append_to_file ? vf : vf + ".tmp";
+  FILE* fk = fopen(kt.c_str(), append_to_file ? "ab" : "wb");
+  FILE* fv = fopen(vt.c_str(), append_to_file ? "ab" : "wb");
+  bool ok = fk && fv;
+  det_status st = DET_OK;
+  std::vector<long long> hk(buffer_keys);
+  std::vector<unsigned char> hv(buffer_keys * rb);
+  for (uint64_t first = 0; ok && st == DET_OK;) {
+    int64_t got = 0;
+    st = det_export_window(t, 0, first, (int64_t*)dk, dv, buffer_keys, &got, nullptr);
+    if (st != DET_OK || got <= 0) break;
     if (cudaMemcpy(hk.data(), dk, (size_t)got * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(hv.data(), dv, (size_t)got * rb, cudaMemcpyDeviceToHost) != cudaSuccess)
+        cudaMemcpy(hv.data(), dv, (size_t)got * rb, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cudaGetLastError();
       st = fail(DET_CUDA_ERROR, "det_save: D2H copy failed");
+      break;
+    }
+    ok = fwrite(hk.data(), 8, (size_t)got, fk) == (size_t)got && fwrite(hv.data(), rb, (size_t)got, fv) == (size_t)got;
+    first += (uint64_t)got;
+    if ((size_t)got < buffer_keys) break;
   }
   cudaFree(dk);
   cudaFree(dv);
-  if (st != DET_OK) return st;
-  // tmp + rename like the reference (cuckoo_hashtable_op.cc:310-391)
-  const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
-  const std::string kt = kf + ".tmp", vt = vf + ".tmp";
-  FILE* fk = fopen(kt.c_str(), "wb");
-  FILE* fv = fopen(vt.c_str(), "wb");
-  bool ok = fk && fv;
-  if (ok && got > 0) {
-    ok = fwrite(hk.data(), 8, (size_t)got, fk) == (size_t)got &&
-         fwrite(hv.data(), rb, (size_t)got, fv) == (size_t)got;
-  }
   if (fk) ok = (fclose(fk) == 0) && ok;
   if (fv) ok = (fclose(fv) == 0) && ok;
-  if (ok) ok = rename(kt.c_str(), kf.c_str()) == 0 && rename(vt.c_str(), vf.c_str()) == 0;
+  if (st != DET_OK) return st;
+  if (ok && !append_to_file) ok = rename(kt.c_str(), kf.c_str()) == 0 && rename(vt.c_str(), vf.c_str()) == 0;
   if (!ok) return fail(DET_IO_ERROR, "det_save: cannot write " + kf + " / " + vf);
   return DET_OK;
 }
 
-det_status det_load(det_table* t, const char* prefix, size_t buffer_keys) {
+// LoadFromFileSystem (cuckoo_hashtable_op.cc:393-504): clear_first != 0 = the op on ONE file (clear + insert all);
+// load_entire_dir = clear once, then one call per `<name>_mht_*` file with clear_first == 0.
+det_status det_load(det_table* t, const char* prefix, size_t buffer_keys, int clear_first) {
   if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_load: null argument");
   det::DevGuard _dg(t->cfg.device);
   const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
@@ -347,10 +352,11 @@ det_status det_load(det_table* t, const char* prefix, size_t buffer_keys) {
   std::vector<long long> hk(buffer_keys);
   std::vector<unsigned char> hv(buffer_keys * rb);
   det_status st = DET_OK;
-  // LoadFromFileSystem without load_entire_dir = clear + insert all (cuckoo_hashtable_op.cc:393-465)
-  st = det_clear(t, nullptr);
-  // the chunked inserts below run on the table's internal (non-blocking) streams: the clear must be complete
-  if (st == DET_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_load: clear failed");
+  if (clear_first) {
+    st = det_clear(t, nullptr);
+    // the chunked inserts below run on the table's internal (non-blocking) streams: the clear must be complete
+    if (st == DET_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_load: clear failed");
+  }
   while (st == DET_OK) {
     const size_t m = fread(hk.data(), 8, buffer_keys, fk);
     if (m == 0) break;

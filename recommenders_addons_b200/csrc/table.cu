@@ -527,12 +527,17 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 export_write_kernel(TableView t, int plane, unsigned plane_row_bytes,
                     const unsigned long long* __restrict__ tile_offsets, size_t n_tiles,
-                    long long* __restrict__ keys_out, unsigned char* __restrict__ vals_out, size_t max_n,
-                    RowGeom g) {
+                    long long* __restrict__ keys_out, unsigned char* __restrict__ vals_out, size_t first,
+                    size_t max_n, RowGeom g) {
   __shared__ unsigned s_warp_cnt[kWarpsPerBlock];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const size_t cap = t.capacity();
+  const unsigned long long win_end = (unsigned long long)first + max_n;
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // tiles whose keys all fall outside the window are skipped (block-uniform): a windowed export costs O(window)
+    const unsigned long long t_lo = tile_offsets[tile];
+    const unsigned long long t_hi = tile + 1 < n_tiles ? tile_offsets[tile + 1] : t.st->scratch[0];
+    if (t_hi <= first || t_lo >= win_end) continue;
     // each warp owns a contiguous 256-slot strip of the tile -> output order = slot order
     const size_t strip = tile * kExportTile + (size_t)w * (kExportTile / kWarpsPerBlock);
     long long k[kExportTile / kThreads];
@@ -545,7 +550,7 @@ export_write_kernel(TableView t, int plane, unsigned plane_row_bytes,
     }
     if (lane == 0) s_warp_cnt[w] = cnt;
     __syncthreads();
-    unsigned long long off = tile_offsets[tile];
+    unsigned long long off = t_lo;
     for (int ww = 0; ww < w; ++ww) off += s_warp_cnt[ww];
     __syncthreads();
 #pragma unroll
@@ -553,17 +558,19 @@ export_write_kernel(TableView t, int plane, unsigned plane_row_bytes,
       const size_t s = strip + (size_t)q * 32 + lane;
       const bool lv = live_key(k[q]);
       const unsigned b = __ballot_sync(kFull, lv);
+      // position of this key in table order; only the window [first, first + max_n) is written, at o - first
       const unsigned long long o = off + __popc(b & ((1u << lane) - 1u));
       const unsigned char* src = nullptr;
       unsigned char* dst = nullptr;
-      if (lv && o < max_n) {
-        if (keys_out) keys_out[o] = k[q];
+      const bool in_win = lv && o >= first && o - first < max_n;
+      if (in_win) {
+        if (keys_out) keys_out[o - first] = k[q];
         if (vals_out) {
           src = t.planes[plane] + s * plane_row_bytes;
-          dst = vals_out + o * plane_row_bytes;
+          dst = vals_out + (o - first) * plane_row_bytes;
         }
       }
-      if (b && vals_out) warp_move_rows<VEC>(g, src, dst, lane);
+      if (vals_out && __any_sync(kFull, in_win)) warp_move_rows<VEC>(g, src, dst, lane);
       off += __popc(b);
     }
   }
@@ -571,24 +578,25 @@ export_write_kernel(TableView t, int plane, unsigned plane_row_bytes,
 
 // the two special keys are appended after the regular ones
 __global__ void export_special_kernel(TableView t, int plane, unsigned plane_row_bytes,
-                                      long long* keys_out, unsigned char* vals_out, size_t max_n) {
+                                      long long* keys_out, unsigned char* vals_out, size_t first, size_t max_n) {
   unsigned long long o = t.st->scratch[0];
   const size_t cap = t.capacity();
   for (int idx = 0; idx < 2; ++idx) {
     if (t.st->special[idx]) {
-      if (o < max_n) {
-        if (threadIdx.x == 0 && keys_out) keys_out[o] = idx ? kTombKey : kEmptyKey;
+      if (o >= first && o - first < max_n) {
+        if (threadIdx.x == 0 && keys_out) keys_out[o - first] = idx ? kTombKey : kEmptyKey;
         if (vals_out) {
           const unsigned char* src = t.planes[plane] + (cap + idx) * plane_row_bytes;
           for (unsigned c = threadIdx.x; c < plane_row_bytes; c += blockDim.x)
-            vals_out[o * plane_row_bytes + c] = src[c];
+            vals_out[(o - first) * plane_row_bytes + c] = src[c];
         }
       }
       ++o;
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) t.st->scratch[1] = o < max_n ? o : max_n;  // rows written
+  // rows written = size of the intersection of [first, first + max_n) and [0, o)
+  if (threadIdx.x == 0) t.st->scratch[1] = o <= first ? 0 : (o - first < max_n ? o - first : max_n);
 }
 
 // exported optimizer-slot rows that were never initialised read as the slot initializer value
@@ -1277,8 +1285,8 @@ det_status det_reserve(det_table* t, uint64_t total_keys, det_stream_t stream) {
   return DET_OK;
 }
 
-det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
-                      int64_t* n_out_host, det_stream_t stream) {
+det_status det_export_window(det_table* t, int plane, uint64_t first, int64_t* keys_out, void* values_out,
+                             size_t max_n, int64_t* n_out_host, det_stream_t stream) {
   if (!t || !n_out_host) return fail(DET_INVALID_ARGUMENT, "det_export: null argument");
   std::lock_guard<std::mutex> _lk(t->mu);
   if (plane < 0 || plane > t->cfg.num_slot_planes) return fail(DET_INVALID_ARGUMENT, "det_export: bad plane");
@@ -1305,10 +1313,10 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
   const RowGeom g = make_geom(prb, vec);
   dispatch_vec(vec, [&](auto V) -> det_status {
     DET_LAUNCH(export_write_kernel<decltype(V)::value>, grid, kThreads, 0, s, 
-        v, plane, prb, offs, n_tiles, (long long*)keys_out, (unsigned char*)values_out, max_n, g);
+        v, plane, prb, offs, n_tiles, (long long*)keys_out, (unsigned char*)values_out, (size_t)first, max_n, g);
     return DET_OK;
   });
-  DET_LAUNCH(export_special_kernel, 1, 128, 0, s, v, plane, prb, (long long*)keys_out, (unsigned char*)values_out, max_n);
+  DET_LAUNCH(export_special_kernel, 1, 128, 0, s, v, plane, prb, (long long*)keys_out, (unsigned char*)values_out, (size_t)first, max_n);
   if (plane > 0 && values_out)
     DET_LAUNCH(export_fix_slot_rows_kernel, grid_for(max_n, 8, t->sm_count, 8), kThreads, 0, s, 
         (float*)values_out, &v.st->scratch[1], (unsigned)t->cfg.dim, t->slot_init[plane]);
@@ -1318,6 +1326,11 @@ det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_o
   if (st != DET_OK) return st;
   *n_out_host = (int64_t)ds.scratch[1];
   return DET_OK;
+}
+
+det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
+                      int64_t* n_out_host, det_stream_t stream) {
+  return det_export_window(t, plane, 0, keys_out, values_out, max_n, n_out_host, stream);
 }
 
 det_status det_import(det_table* t, const int64_t* keys, const void* values, size_t n, det_stream_t stream) {

@@ -8,6 +8,7 @@ failures (the reference raises tf.errors.* through OP_REQUIRES_OK).
 """
 import ctypes
 import enum
+import glob
 import os
 
 import torch
@@ -303,15 +304,30 @@ class CuckooHashTable(object):
     dirpath = os.environ.get(dirpath_env) or dirpath
     os.makedirs(dirpath, exist_ok=True)
     prefix = os.path.join(dirpath, file_name if file_name else self._name)
-    torch.cuda.current_stream(self._device).synchronize()
-    _lib.check(self._lib.det_save(self._h, prefix.encode(), int(buffer_size)))
+    if self._device.type == "cuda":
+      torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_save(self._h, prefix.encode(), int(buffer_size), 1 if append_to_file else 0))
 
   def load_from_file_system(self, dirpath, file_name=None, dirpath_env="TFRA_SAVED_KV", load_entire_dir=False,
                             buffer_size=4194304, name=None):
+    """LoadFromFileSystem (cuckoo_hashtable_op.cc:393-504): clear, then insert the file pair -- or, with
+    load_entire_dir, every `<name up to _mht_>*` pair of the directory (:477-498)."""
     dirpath = os.environ.get(dirpath_env) or dirpath
-    prefix = os.path.join(dirpath, file_name if file_name else self._name)
-    torch.cuda.current_stream(self._device).synchronize()
-    _lib.check(self._lib.det_load(self._h, prefix.encode(), int(buffer_size)))
+    file_name = file_name if file_name else self._name
+    prefixes = [os.path.join(dirpath, file_name)]
+    if load_entire_dir:
+      sep = "_mht_"
+      pos = file_name.rfind(sep)
+      stem = file_name[:pos + len(sep)] if pos >= 0 else file_name
+      found = sorted({f[:f.rfind("-")] for f in glob.glob(os.path.join(dirpath, glob.escape(stem) + "*"))
+                      if f.endswith("-keys") or f.endswith("-values")})
+      prefixes = found
+      if not prefixes:
+        raise _lib.DetError(7, "load_from_file_system: no file matches %s*" % os.path.join(dirpath, stem))
+    if self._device.type == "cuda":
+      torch.cuda.current_stream(self._device).synchronize()
+    for i, prefix in enumerate(prefixes):
+      _lib.check(self._lib.det_load(self._h, prefix.encode(), int(buffer_size), 1 if i == 0 else 0))
 
   def close(self):
     if getattr(self, "_h", None) is not None and self._h:

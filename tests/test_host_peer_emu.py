@@ -20,7 +20,7 @@ from recommenders_addons_b200 import _lib as real  # noqa: E402
 from tests.test_detable_emu import L, P, Table, ck  # noqa: E402
 
 _EXTRA = ["det_find_host", "det_insert_host", "det_find_host_async", "det_insert_host_async", "det_host_sync", "det_save",
-          "det_load", "det_peer_handle_bytes", "det_peer_export", "det_peer_group_create", "det_peer_group_destroy",
+          "det_load", "det_export_window", "det_peer_handle_bytes", "det_peer_export", "det_peer_group_create", "det_peer_group_destroy",
           "det_peer_find", "det_peer_insert", "det_peer_barrier", "det_peer_inbox_bytes", "det_peer_inbox_attach",
           "det_peer_route", "det_peer_inbox_counts", "det_peer_inbox_gather", "det_table_region_bytes",
           "det_table_create_in_region", "det_peer_group_create_regions"]
@@ -77,7 +77,7 @@ def test_save_load_file_format(tmp_path, dtype, dim):
   vals = (rng.integers(-100, 100, size=(3000, dim))).astype(dtype)
   t.insert(keys, vals)
   prefix = str(tmp_path / "tbl_mht_1of1")
-  ck(X().det_save(t.h, prefix.encode(), 700))               # buffer of 700 keys: several file chunks
+  ck(X().det_save(t.h, prefix.encode(), 700, 0))            # buffer of 700 keys: several export windows
   fk = np.fromfile(prefix + "-keys", dtype="<i8")
   fv = np.fromfile(prefix + "-values", dtype=np.dtype(dtype).newbyteorder("<")).reshape(-1, dim)
   assert len(fk) == 3000 and fv.shape == (3000, dim)
@@ -93,12 +93,32 @@ def test_save_load_file_format(tmp_path, dtype, dim):
   v2.tofile(prefix2 + "-values")
   t2 = Table(dim=dim, dtype=dtype, init=64)
   t2.insert(np.array([1, 2, 3], dtype=np.int64), np.zeros((3, dim), dtype=dtype))
-  ck(X().det_load(t2.h, prefix2.encode(), 500))
+  ck(X().det_load(t2.h, prefix2.encode(), 500, 1))
   assert t2.size() == 1200
   out, ex = t2.find(k2)
   assert ex.all()
   np.testing.assert_array_equal(out, v2)
-  assert X().det_load(t2.h, str(tmp_path / "missing").encode(), 500) == 7     # DET_IO_ERROR
+  assert X().det_load(t2.h, str(tmp_path / "missing").encode(), 500, 1) == 7     # DET_IO_ERROR
+  # load_entire_dir: the second file of a set is ADDED (clear_first = 0); append_to_file appends to a file pair
+  ck(X().det_load(t2.h, prefix.encode(), 800, 0))
+  assert t2.size() == 1200 + 3000
+  ck(X().det_save(t2.h, prefix2.encode(), 512, 1))
+  assert len(np.fromfile(prefix2 + "-keys", dtype="<i8")) == 1200 + 4200
+  assert np.fromfile(prefix2 + "-values", dtype=dtype).size == (1200 + 4200) * dim
+  # windows of the export: disjoint, in table order, together the whole table
+  whole_k, whole_v = t.export()
+  got_k, first = [], 0
+  while True:
+    kb, vb = np.empty(450, np.int64), np.empty((450, dim), dtype)
+    n = ctypes.c_int64(0)
+    ck(X().det_export_window(t.h, 0, first, P(kb), P(vb), 450, ctypes.byref(n), None))
+    if n.value == 0:
+      break
+    np.testing.assert_array_equal(kb[:n.value], whole_k[first:first + n.value])
+    np.testing.assert_array_equal(vb[:n.value], whole_v[first:first + n.value])
+    got_k.append(kb[:n.value].copy())
+    first += n.value
+  assert first == 3000 and len(np.unique(np.concatenate(got_k))) == 3000
   t.close()
   t2.close()
 
@@ -272,7 +292,7 @@ def test_bounded_table_reserve_clear_import_and_load(tmp_path):
   prefix = str(tmp_path / "bounded")
   big.astype("<i8").tofile(prefix + "-keys")
   bv.tofile(prefix + "-values")
-  ck(X().det_load(t.h, prefix.encode(), 3000))
+  ck(X().det_load(t.h, prefix.encode(), 3000, 1))
   assert 0 < t.size() <= 1 << 13
   t.check()
   t.close()

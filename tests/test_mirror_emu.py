@@ -2,6 +2,7 @@
 EMULATED libdetable with CPU tensors (tests/emu/backend.py): the bodies of the GPU suites that have not run on real
 hardware yet (tests/test_evict_gpu.py, tests/test_restrict_gpu.py) are executed here as they are, so their Python glue
 and the C ABI underneath have been exercised end to end before the first GPU run."""
+import os
 import time
 
 import pytest
@@ -122,3 +123,31 @@ def test_callers_suite_body(name):
 @pytest.mark.parametrize("bp_v2", [False, True])
 def test_trainable_wrapper_prefetch_and_update_op(bp_v2):
   CG.test_trainable_wrapper_prefetch_and_update_op(bp_v2)
+
+
+def test_table_file_ops_append_and_load_entire_dir(tmp_path):
+  """attrs of TFRA>...SaveToFileSystem / LoadFromFileSystem (cuckoo_hashtable_ops.cc:257-291): append_to_file,
+  load_entire_dir (every `<name>_mht_*` pair of the directory, cuckoo_hashtable_op.cc:477-498), buffer_size"""
+  import numpy as np
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  d = str(tmp_path)
+  mk = lambda name: de.CuckooHashTable(torch.int64, torch.float32, torch.zeros(4), name=name, device="cpu")  # noqa: E731
+  k1, k2 = torch.arange(0, 700), torch.arange(1000, 1500)
+  v1, v2 = torch.arange(700.).reshape(-1, 1).repeat(1, 4), -torch.arange(500.).reshape(-1, 1).repeat(1, 4)
+  a, b, c = mk("a"), mk("b"), mk("c")
+  a.insert(k1, v1)
+  b.insert(k2, v2)
+  a.save_to_file_system(d, file_name="emb_mht_1of2", buffer_size=256)
+  b.save_to_file_system(d, file_name="emb_mht_2of2", buffer_size=256)
+  c.insert(torch.tensor([77777]), torch.ones(1, 4))
+  c.load_from_file_system(d, file_name="emb_mht_1of2", load_entire_dir=True, buffer_size=300)
+  assert int(c.size()) == 1200                                 # cleared once, both shards loaded
+  got, ex = c.lookup(torch.cat([k1, k2]), return_exists=True)
+  assert bool(ex.all()) and torch.equal(got, torch.cat([v1, v2]))
+  c.load_from_file_system(d, file_name="emb_mht_2of2")        # one file: clear + insert
+  assert int(c.size()) == 500
+  b.save_to_file_system(d, file_name="emb_mht_1of2", append_to_file=True)
+  assert len(np.fromfile(os.path.join(d, "emb_mht_1of2-keys"), dtype="<i8")) == 1200
+  with pytest.raises(Exception):
+    c.load_from_file_system(d, file_name="nothing_mht_1of1", load_entire_dir=True)
