@@ -1,0 +1,155 @@
+// det_fused_ops.cc -- the two op chains of the hot path that collapse into ONE kernel each, as TF custom ops next to
+// the table ops (same resource handle): what `embedding_lookup_sparse` (python/ops/dynamic_embedding_ops.py:219-291:
+// unique -> lookup -> gather -> *weights -> segment_sum -> divide, 5 ops) and `DynamicEmbeddingOptimizer`
+// (python/ops/dynamic_embedding_optimizer.py:161-204: find param + find slots -> dense rule -> upsert param + slots)
+// call when the table is a DetHashTableOfTensorsGpu.  Registered like the table ops
+// (core/ops/hkv_hashtable_ops.cc:134-339, PREFIX_OP_NAME = "TFRA>", core/utils/utils.h:28-33).
+// Compiled in this repo only against the TF stand-in of tests/tf_mock/ (tests/test_tf_shim.py).
+#include "det_hashtable_of_tensors_gpu.h"
+#include "tensorflow/core/framework/op.h"
+
+namespace tensorflow {
+namespace recommenders_addons {
+namespace lookup {
+namespace det_shim {
+
+REGISTER_OP("TFRA>DetLookupSparse")
+    .Input("table_handle: resource")
+    .Input("ids: int64")           // [nnz] SparseTensor.values
+    .Input("segment_ids: int32")   // [nnz] SparseTensor.indices[:, 0], ascending
+    .Input("weights: float")       // [nnz] or [0] = all ones
+    .Input("default_row: float")   // [dim]
+    .Output("output: float")       // [batch, dim]
+    .Attr("batch: int >= 0")
+    .Attr("combiner: {'sum', 'mean', 'sqrtn'} = 'mean'");
+
+REGISTER_OP("TFRA>DetApplyAdagrad")
+    .Input("table_handle: resource")
+    .Input("keys: int64")          // [n] unique
+    .Input("grads: float")         // [n, dim]
+    .Input("lr: float")
+    .Input("init_param: float")    // [dim] or [n, dim]: the rows a key that is not in the table starts from
+    .Attr("epsilon: float = 0.0")  // 0: tf.compat.v1.train.AdagradOptimizer, 1e-7: Keras
+    .Attr("initial_accumulator_value: float = 0.1");
+
+REGISTER_OP("TFRA>DetApplyAdam")
+    .Input("table_handle: resource")
+    .Input("keys: int64")
+    .Input("grads: float")
+    .Input("alpha: float")         // lr * sqrt(1 - beta2^t) / (1 - beta1^t), computed by the Python optimizer
+    .Input("init_param: float")
+    .Attr("beta1: float = 0.9")
+    .Attr("beta2: float = 0.999")
+    .Attr("epsilon: float = 1e-8");
+
+using Table = DetHashTableOfTensorsGpu<int64, float>;
+
+static det_stream_t StreamOf(OpKernelContext* ctx) { return (det_stream_t)ctx->eigen_device<GPUDevice>().stream(); }
+
+class DetLookupSparseOp : public OpKernel {
+ public:
+  explicit DetLookupSparseOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("batch", &batch_));
+    string combiner;
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("combiner", &combiner));
+    combiner_ = combiner == "sum" ? DET_COMBINER_SUM : combiner == "mean" ? DET_COMBINER_MEAN : DET_COMBINER_SQRTN;
+    OP_REQUIRES(ctx, combiner == "sum" || combiner == "mean" || combiner == "sqrtn",
+                errors::InvalidArgument("combiner must be one of 'mean', 'sqrtn' or 'sum'"));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    tensorflow::lookup::LookupInterface* table = nullptr;
+    OP_REQUIRES_OK(ctx, GetLookupTable("table_handle", ctx, &table));
+    core::ScopedUnref unref_me(table);
+    Table* t = static_cast<Table*>(table);
+    const Tensor& ids = ctx->input(1);
+    const Tensor& seg = ctx->input(2);
+    const Tensor& w = ctx->input(3);
+    const Tensor& def = ctx->input(4);
+    const int64 dim = t->value_shape().dim_size(0);
+    OP_REQUIRES(ctx, seg.NumElements() == ids.NumElements(), errors::InvalidArgument("ids and segment_ids differ in length"));
+    OP_REQUIRES(ctx, w.NumElements() == 0 || w.NumElements() == ids.NumElements(),
+                errors::InvalidArgument("weights must be empty or have one entry per id"));
+    OP_REQUIRES(ctx, def.NumElements() == dim, errors::InvalidArgument("default_row must have shape [dim]"));
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output("output", TensorShape({batch_, dim}), &out));
+    OP_REQUIRES_OK(ctx, ToStatus(det_lookup_sparse(
+                            t->handle(), reinterpret_cast<const int64_t*>(ids.flat<int64>().data()),
+                            seg.flat<int32>().data(), w.NumElements() ? w.flat<float>().data() : nullptr,
+                            static_cast<size_t>(ids.NumElements()), static_cast<size_t>(batch_), combiner_,
+                            def.flat<float>().data(), out->flat<float>().data(), StreamOf(ctx))));
+  }
+
+ private:
+  int64 batch_ = 0;
+  int combiner_ = DET_COMBINER_MEAN;
+};
+
+class DetApplyAdagradOp : public OpKernel {
+ public:
+  explicit DetApplyAdagradOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("epsilon", &epsilon_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("initial_accumulator_value", &init_accum_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    tensorflow::lookup::LookupInterface* table = nullptr;
+    OP_REQUIRES_OK(ctx, GetLookupTable("table_handle", ctx, &table));
+    core::ScopedUnref unref_me(table);
+    Table* t = static_cast<Table*>(table);
+    const Tensor& keys = ctx->input(1);
+    const Tensor& grads = ctx->input(2);
+    const Tensor& lr = ctx->input(3);
+    const Tensor& init = ctx->input(4);
+    const int64 n = keys.NumElements(), dim = t->value_shape().dim_size(0);
+    OP_REQUIRES(ctx, grads.NumElements() == n * dim, errors::InvalidArgument("grads must have shape [n, dim]"));
+    OP_REQUIRES(ctx, init.NumElements() == dim || init.NumElements() == n * dim,
+                errors::InvalidArgument("init_param must have shape [dim] or [n, dim]"));
+    OP_REQUIRES_OK(ctx, ToStatus(det_apply_adagrad(
+                            t->handle(), reinterpret_cast<const int64_t*>(keys.flat<int64>().data()),
+                            grads.flat<float>().data(), static_cast<size_t>(n), lr.scalar<float>()(), epsilon_,
+                            init.flat<float>().data(), init.NumElements() == dim ? 0 : 1,
+                            init_accum_, StreamOf(ctx))));
+  }
+
+ private:
+  float epsilon_ = 0.f, init_accum_ = 0.1f;
+};
+
+class DetApplyAdamOp : public OpKernel {
+ public:
+  explicit DetApplyAdamOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("beta1", &beta1_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("beta2", &beta2_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("epsilon", &epsilon_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    tensorflow::lookup::LookupInterface* table = nullptr;
+    OP_REQUIRES_OK(ctx, GetLookupTable("table_handle", ctx, &table));
+    core::ScopedUnref unref_me(table);
+    Table* t = static_cast<Table*>(table);
+    const Tensor& keys = ctx->input(1);
+    const Tensor& grads = ctx->input(2);
+    const Tensor& alpha = ctx->input(3);
+    const Tensor& init = ctx->input(4);
+    const int64 n = keys.NumElements(), dim = t->value_shape().dim_size(0);
+    OP_REQUIRES(ctx, grads.NumElements() == n * dim, errors::InvalidArgument("grads must have shape [n, dim]"));
+    OP_REQUIRES(ctx, init.NumElements() == dim || init.NumElements() == n * dim,
+                errors::InvalidArgument("init_param must have shape [dim] or [n, dim]"));
+    OP_REQUIRES_OK(ctx, ToStatus(det_apply_adam(
+                            t->handle(), reinterpret_cast<const int64_t*>(keys.flat<int64>().data()),
+                            grads.flat<float>().data(), static_cast<size_t>(n), alpha.scalar<float>()(), beta1_,
+                            beta2_, epsilon_, init.flat<float>().data(), init.NumElements() == dim ? 0 : 1,
+                            StreamOf(ctx))));
+  }
+
+ private:
+  float beta1_ = 0.9f, beta2_ = 0.999f, epsilon_ = 1e-8f;
+};
+
+REGISTER_KERNEL_BUILDER(Name("TFRA>DetLookupSparse").Device(DEVICE_GPU), DetLookupSparseOp);
+REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdagrad").Device(DEVICE_GPU).HostMemory("lr"), DetApplyAdagradOp);
+REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdam").Device(DEVICE_GPU).HostMemory("alpha"), DetApplyAdamOp);
+
+}  // namespace det_shim
+}  // namespace lookup
+}  // namespace recommenders_addons
+}  // namespace tensorflow
