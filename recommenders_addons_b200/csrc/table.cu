@@ -532,7 +532,8 @@ export_write_kernel(TableView t, int plane, unsigned plane_row_bytes,
   __shared__ unsigned s_warp_cnt[kWarpsPerBlock];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const size_t cap = t.capacity();
-  const unsigned long long win_end = (unsigned long long)first + max_n;
+  const unsigned long long win_end =
+      (unsigned long long)max_n > ~0ull - (unsigned long long)first ? ~0ull : (unsigned long long)first + max_n;
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // tiles whose keys all fall outside the window are skipped (block-uniform): a windowed export costs O(window)
     const unsigned long long t_lo = tile_offsets[tile];
