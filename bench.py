@@ -12,8 +12,9 @@ inputs resident in HBM.  `e2e` = the same step through the host-buffer entry poi
 
 N>1 (launched by torchrun, one rank per GPU): the table is key-hash sharded (owner = (key & 0x7fffffff) % N,
 the reference's default_partition_fn); every rank keeps a 100M-key shard (weak scaling) and drives batches of
-keys owned by ANY rank: partition -> NCCL all-to-all of keys -> local find -> all-to-all of rows back, and
-keys+rows to their owners -> local insert.
+keys owned by ANY rank.  --exchange peer (default): ONE kernel per call probes the owner's shard over NVLink peer
+memory (det_peer_find / det_peer_insert).  --exchange nccl (the baseline): partition -> NCCL all-to-all of keys ->
+local find -> all-to-all of rows back, and keys+rows to their owners -> local insert.
 
 --impl reference : the reference's own CPU cuckoo path (oracle/_ref = its vendored libcuckoo compiled from
 /root/reference, else the C port) on the host cores, same metric, bounded sample.

@@ -56,6 +56,9 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
     raise TypeError("sp_weights must be either None or SparseTensor")
   if not isinstance(params, Variable):
     raise TypeError("params should be a Variable instance.")
+  if params.key_dtype != sp_ids.values.dtype:   # raised by the inner embedding_lookup, dynamic_embedding_variable.py:1409-1412
+    raise TypeError("params.key_dtype should be same with sp_ids.dtype: {} vs. {}".format(params.key_dtype,
+                                                                                           sp_ids.values.dtype))
   segment_ids = sp_ids.indices[:, 0].to(torch.int32)
   ids = sp_ids.values
   batch = sp_ids.dense_shape[0]
@@ -81,6 +84,19 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
     touched[seg64] = True
     out = torch.where(touched[:, None], out / den[:, None], out)
   return (out, tw) if return_trainable else out
+
+
+def verify_embedding_param_weights(embedding_weights, sparse_ids, sparse_weights=None):
+  """EmbeddingWeights.verify_embedding_param_weights (python/ops/embedding_weights.py:78-95)"""
+  if embedding_weights is None:
+    raise ValueError("Missing embedding_weights %s." % embedding_weights)
+  if embedding_weights.key_dtype != sparse_ids.values.dtype:
+    raise TypeError("embedding_weights.key_dtype should be same with sparse_ids.dtype: {} vs. {}".format(
+        embedding_weights.key_dtype, sparse_ids.values.dtype))
+  weights_dtype = sparse_weights.values.dtype if sparse_weights is not None else None
+  if weights_dtype and embedding_weights.value_dtype != weights_dtype:
+    raise TypeError("embedding_weights.value_dtype should be same with sparse_weights.dtype: {} vs. {}".format(
+        embedding_weights.value_dtype, weights_dtype))
 
 
 def _safe_preprocess(sparse_ids, sparse_weights, combiner, default_id):
@@ -134,6 +150,7 @@ def safe_embedding_lookup_sparse(embedding_weights, sparse_ids, sparse_weights=N
                                  max_norm=None, return_trainable=False):
   """dynamic_embedding_ops.py:296-438: flatten leading dims, prune weights <= 0 (unless combiner is "sum"),
   give empty rows `default_id` (or a zero vector when default_id is None), then embedding_lookup_sparse."""
+  verify_embedding_param_weights(embedding_weights, sparse_ids, sparse_weights)
   sp2, sw2, empty_rows, shape = _safe_preprocess(sparse_ids, sparse_weights, combiner, default_id)
   r = embedding_lookup_sparse(embedding_weights, sp2, sw2, combiner=combiner, max_norm=max_norm,
                               return_trainable=return_trainable)
