@@ -66,6 +66,13 @@ class HkvEvictStrategy(enum.IntEnum):
   CUSTOMIZED = 4
 
 
+class SignatureMismatchError(TypeError, ValueError):
+  """keys / values of the wrong dtype.  The reference surfaces this as ValueError from `convert_to_tensor` in the
+  Python wrappers (kernel_tests/dynamic_embedding_variable_test.py:1746-1788 asserts ValueError) and as
+  InvalidArgument "Signature mismatch" from `ctx->MatchSignature` in the kernels (cuckoo_hashtable_op.cc:601-604);
+  code written against either convention catches this class."""
+
+
 class HkvHashTableConfig(object):
   """python/ops/dynamic_embedding_creator.py:149-170 (capacity attributes of the HKV ops).
 
@@ -175,14 +182,15 @@ class CuckooHashTable(object):
     if not torch.is_tensor(keys):
       keys = torch.as_tensor(keys, dtype=self._key_dtype)
     if keys.dtype != self._key_dtype:
-      raise TypeError("Signature mismatch. Keys must be dtype %s, got %s." % (self._key_dtype, keys.dtype))
+      raise SignatureMismatchError("Signature mismatch. Keys must be dtype %s, got %s." % (self._key_dtype, keys.dtype))
     return keys.to(self._device).contiguous()
 
   def _check_values(self, values, n, what="Values"):
     if not torch.is_tensor(values):
       values = torch.as_tensor(values, dtype=self._value_dtype)
     if values.dtype != self._value_dtype:
-      raise TypeError("Signature mismatch. %s must be dtype %s, got %s." % (what, self._value_dtype, values.dtype))
+      raise SignatureMismatchError("Signature mismatch. %s must be dtype %s, got %s." %
+                                   (what, self._value_dtype, values.dtype))
     values = values.to(self._device).contiguous()
     if values.numel() != n * self._dim:
       # CheckKeyAndValueTensorsForInsert (cuckoo_hashtable_op.cc:671)

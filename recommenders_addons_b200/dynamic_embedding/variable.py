@@ -168,7 +168,10 @@ class Variable(object):
     return grouped, perm, bounds
 
   def upsert(self, keys, values, name=None):
-    """Insert or update `keys` with `values` (:772-804)."""
+    """Insert or update `keys` with `values` (:772-804).  `values` has the shape of `keys` + [dim]
+    (CheckKeyAndValueTensorsForInsert, cuckoo_hashtable_op.cc:671: "Expected shape ... for value")."""
+    if torch.is_tensor(keys) and torch.is_tensor(values) and tuple(values.shape) != tuple(keys.shape) + (self.dim,):
+      raise ValueError("Expected shape %s for value, got %s" % (list(keys.shape) + [self.dim], list(values.shape)))
     values = values.reshape(-1, self.dim)
     grouped, perm, bounds = self._partition(keys)
     vals = values if perm is None else gather_rows(values, perm)
