@@ -108,6 +108,11 @@ def test_composed_optimizer_matches_dense_twin(name):
   CG.test_composed_optimizer_matches_dense_twin(name)
 
 
+@pytest.mark.parametrize("name", ["momentum", "rmsprop", "adam", "adagrad"])
+def test_composed_optimizer_bp_v2_matches_dense_twin(name):
+  CG.test_composed_optimizer_bp_v2_matches_dense_twin(name)
+
+
 @pytest.mark.parametrize("kind", ["adagrad", "adam"])
 def test_composed_and_fused_paths_agree(kind):
   CG.test_composed_and_fused_paths_agree(kind)
