@@ -419,6 +419,10 @@ def _clip(values, max_norm):
 def embedding_lookup(params, ids, partition_strategy=None, name=None, validate_indices=None, max_norm=None,
                      return_trainable=False):
   """de.embedding_lookup (:1362-1530).  `ids` may have any shape; the result is ids.shape + [dim]."""
+  if isinstance(params, (list, tuple)) and len(params) > 1:   # :1403-1406
+    raise ValueError("Only one params is allowed.")
+  if isinstance(params, (list, tuple)):
+    params = params[0]
   if not isinstance(params, Variable):
     raise TypeError("params should be a Variable instance.")
   if params.key_dtype != ids.dtype:

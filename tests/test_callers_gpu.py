@@ -155,6 +155,18 @@ def test_model_mode_and_trainable_wrapper_filter():
     assert out.shape == (2, 2, DIM) and not out.requires_grad and sh.ids.numel() == 0
   finally:
     de.enable_train_mode()
+  # test_inference_numberic_correctness (dynamic_embedding_optimizer_test.py:1506-1562): the same prediction in both
+  # modes; a one-element list of params is accepted, more is an error (dynamic_embedding_variable.py:1403-1406)
+  var.upsert(torch.arange(20, device=DEV), torch.rand(20, DIM, device=DEV))
+  preds = []
+  for fn in (de.enable_train_mode, de.enable_inference_mode):
+    fn()
+    test_var, _ = de.embedding_lookup([var], torch.tensor([0, 1, 2, 3, 4], device=DEV), return_trainable=True)
+    preds.append((test_var.detach() + 1) * 1.0)
+  de.enable_train_mode()
+  assert torch.equal(preds[0], preds[1])
+  with pytest.raises(ValueError):
+    de.embedding_lookup([var, var], ids)
   emb, tw = de.embedding_lookup(var, ids, return_trainable=True)
   assert tw.values.requires_grad and tw.model_mode == "train"
   assert de.trainable_wrapper_filter([tw, var, 3, sh]) == [tw, sh]
