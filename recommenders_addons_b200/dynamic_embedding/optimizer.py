@@ -176,7 +176,17 @@ class ComposedOptimizer(object):
                            name="%s/%s/%s" % (params.name, self._cls.__name__, k), initializer=init, trainable=False,
                            init_size=params.init_size, kv_creator=params.kv_creator)
       self._slots[params.name] = made
+      # create_slots (dynamic_embedding_optimizer.py:870-958): a restrict policy shrinks the slot tables with the variable
+      if getattr(params, "restrict_policy", None) is not None:
+        params.restrict_policy._track_params_from_optimizer_slots(list(made.values()))
     return self._slots[params.name]
+
+  def get_slot_names(self):
+    return self.slot_names()
+
+  def slot_variables(self, params):
+    """every slot Variable this optimizer keeps for `params` (empty before the first step)"""
+    return [v for _, v in sorted(self._slots.get(params.name, {}).items())]
 
   @staticmethod
   def _materialize(opt, p):

@@ -23,10 +23,7 @@ class ShadowVariable(TrainableWrapper):
                      model_mode=kwargs.get("model_mode", None))
     self.name = name
     self.trainable = trainable
-    store = getattr(params, "_trainable_store", None)
-    if store is None:
-      store = params._trainable_store = {}
-    store[name] = self                          # :163
+    params.trainable_store[name] = self         # :163
 
   def prefetch_values(self, update=False):
     out = super().prefetch_values(update=update)

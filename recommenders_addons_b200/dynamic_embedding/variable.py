@@ -322,6 +322,28 @@ class Variable(object):
   def embedding_lookup(self, ids, name=None, max_norm=None, return_trainable=False):
     return embedding_lookup(self, ids, name=name, max_norm=max_norm, return_trainable=return_trainable)
 
+  @property
+  def trainable_store(self):
+    """name -> ShadowVariable registered on this variable (:1260-1262)"""
+    if not hasattr(self, "_trainable_store"):
+      self._trainable_store = {}
+    return self._trainable_store
+
+  def get_trainable_by_name(self, name):
+    """:1188-1224"""
+    if not isinstance(name, str):
+      raise TypeError("name should be a string")
+    return self.trainable_store.get(name, None)
+
+  def get_slot_variables(self, optimizer):
+    """:1155-1186: the slot Variables `optimizer` keeps for this variable.  The fused optimizers keep their slots in
+    planes of this variable's own tables (exported with `tables[i].export(plane=k)`): they have no slot Variables."""
+    if hasattr(optimizer, "slot_variables"):
+      return optimizer.slot_variables(self)
+    if hasattr(optimizer, "apply_gradients"):
+      return []
+    raise TypeError("Expect an optimizer, but get {}".format(type(optimizer)))
+
 
 class ModelMode(object):
   """The global train / inference switch (python/ops/embedding_weights.py:98-120).  In INFERENCE mode a lookup builds

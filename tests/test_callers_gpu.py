@@ -137,6 +137,30 @@ def test_untouched_rows_and_slot_tables_stay_sparse():
   assert int(opt.get_slot(var, "momentum_buffer").size()) == 3         # only the touched keys carry slot state
 
 
+def test_get_slot_variables_and_restrict_policy_tracks_them():
+  """kernel_tests/dynamic_embedding_variable_test.py:1959-2002 (get_slot_variables) + create_slots' hand-over of the
+  slot variables to the restrict policy (dynamic_embedding_optimizer.py:870-958): restricting the variable shrinks its
+  slot tables too"""
+  de = _de()
+  var = de.get_variable("trl4397", dim=DIM, initializer=0.0, devices=[DEV], restrict_policy=de.TimestampRestrictPolicy)
+  opt = de.DynamicEmbeddingOptimizer(torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=0.1), fused=False)
+  assert var.get_slot_variables(opt) == [] and var.get_slot_variables(de.FusedAdam(0.1)) == []
+  with pytest.raises(TypeError):
+    var.get_slot_variables(object())
+  ids = torch.arange(1, 9, device=DEV)
+  emb, tw = de.embedding_lookup(var, ids, return_trainable=True)
+  emb.sum().backward()
+  opt.apply_gradients([(tw.values.grad, tw)])
+  names = [v.name for v in var.get_slot_variables(opt)]
+  assert names == ["trl4397/Adam/exp_avg", "trl4397/Adam/exp_avg_sq"] and opt.get_slot_names() == ["exp_avg", "exp_avg_sq"]
+  assert [int(v.size()) for v in var.get_slot_variables(opt)] == [8, 8] and int(var.restrict_policy.status.size()) == 8
+  assert [id(p) for p in var.restrict_policy.params_in_slots] == [id(v) for v in var.get_slot_variables(opt)]
+  var.restrict(3)
+  assert int(var.size()) == 3 and [int(v.size()) for v in var.get_slot_variables(opt)] == [3, 3]
+  sh = de.shadow_ops.ShadowVariable(var, name="user_embedding")
+  assert var.get_trainable_by_name("user_embedding") is sh and var.get_trainable_by_name("nope") is None
+
+
 def test_model_mode_and_trainable_wrapper_filter():
   de = _de()
   var = de.get_variable("modes", dim=DIM, initializer=2.0, devices=[DEV])
