@@ -7,14 +7,14 @@
 set -u
 mkdir -p gpurun_out
 export DET_TEST_UNVALIDATED=1
-timeout 900 python -m pytest tests/test_evict_gpu.py tests/test_restrict_gpu.py tests/test_spill_gpu.py -q -m gpu 2>&1 | tee gpurun_out/evict_tests.log | tail -40
+timeout 900 python -m pytest tests/test_evict_gpu.py tests/test_restrict_gpu.py tests/test_spill_gpu.py tests/test_callers_gpu.py -q -m gpu 2>&1 | tee gpurun_out/evict_tests.log | tail -40
 # memory checker over the small cases (every kernel of evict.cu runs at least once)
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_evict_gpu.py -q -m gpu \
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_evict_gpu.py -q -m gpu \
   -k "basic or lfu or custom or growth or touch" > gpurun_out/evict_memcheck.log 2>&1
 echo "memcheck exit: $?" | tee -a gpurun_out/evict_tests.log
 tail -5 gpurun_out/evict_memcheck.log
 # racecheck on shared-memory histograms / counters
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_evict_gpu.py -q -m gpu \
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_evict_gpu.py -q -m gpu \
   -k "explicit" > gpurun_out/evict_racecheck.log 2>&1
 echo "racecheck exit: $?" | tee -a gpurun_out/evict_tests.log
 # the validated suite must be untouched by the new translation unit
