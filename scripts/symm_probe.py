@@ -3,7 +3,6 @@
 table planes, and how fast is RANDOM 256 B row access to a peer's buffer through such a mapping?"""
 import json
 import os
-import sys
 import time
 
 import torch

@@ -3,7 +3,6 @@ det_lookup_sparse and the fused Adagrad / Adam steps, compared BIT-EXACTLY with 
 oracle/oracle.py -- the same checks tests/test_fused_gpu.py makes on the B200, at sizes the emulator runs in seconds.
 (The emulated build uses the plain-load tile schedule where the GPU build stages key tiles by TMA; the arithmetic,
 the probe / claim protocol and the host code are the same source.)"""
-import ctypes
 
 import numpy as np
 import pytest
