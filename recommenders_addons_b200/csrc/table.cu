@@ -6,6 +6,11 @@
 
 namespace det {
 
+#ifdef DET_EMU
+extern "C" {
+unsigned long long g_det_emu_stat[2] = {0, 0};
+}
+#endif
 thread_local std::string g_last_error;
 
 det_status fail(det_status code, const std::string& msg) {
@@ -124,12 +129,12 @@ struct SlotInit {
 };
 
 // K2: Insert (insert_or_assign).
-template <int VEC>
+template <int VEC, bool BATCH>
 __device__ __forceinline__ void insert_step(const TableView& t, long long key, size_t i, bool valid,
                                             const unsigned char* __restrict__ values, const RowGeom& g,
                                             const SlotInit& si, int lane, unsigned* s_new, unsigned* s_used) {
   bool is_new, from_empty;
-  const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
+  const long long slot = warp_find_or_claim_v<BATCH>(t, key, valid, valid, lane, is_new, from_empty);
   const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
   if (lane == 0 && bn) {
     atomicAdd(s_new, __popc(bn));
@@ -150,7 +155,7 @@ __device__ __forceinline__ void insert_step(const TableView& t, long long key, s
       *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * t.dim * 4u) = kSlotUninit;
 }
 
-template <int VEC>
+template <int VEC, bool BATCH = false>
 __global__ void __launch_bounds__(kThreads)
 insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
               size_t n, RowGeom g, SlotInit si) {
@@ -167,7 +172,7 @@ insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned ch
     const size_t i = base + lane;
     const bool valid = i < n;
     const long long key = valid ? __ldg(keys + i) : 0;
-    insert_step<VEC>(t, key, i, valid, values, g, si, lane, &s_new, &s_used);
+    insert_step<VEC, BATCH>(t, key, i, valid, values, g, si, lane, &s_new, &s_used);
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_new) {
@@ -176,7 +181,7 @@ insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned ch
   }
 }
 
-template <int VEC>
+template <int VEC, bool BATCH = false>
 __global__ void __launch_bounds__(kThreads)
 insert_kernel_tma(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
                   size_t n, RowGeom g, SlotInit si) {
@@ -194,7 +199,7 @@ insert_kernel_tma(TableView t, const long long* __restrict__ keys, const unsigne
     size_t i;
     bool valid;
     const long long key = kt.key(i, valid);
-    insert_step<VEC>(t, key, i, valid, values, g, si, lane, &s_new, &s_used);
+    insert_step<VEC, BATCH>(t, key, i, valid, values, g, si, lane, &s_new, &s_used);
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_new) {
@@ -948,6 +953,9 @@ using namespace det;
 extern "C" {
 
 int det_abi_version(void) { return 3; }
+#ifdef DET_EMU
+unsigned long long det_emu_stat(int which) { return which >= 0 && which < 2 ? det::g_det_emu_stat[which] : 0; }
+#endif
 
 const char* det_build_info(void) {
   return "detable sm_100a; nvcc " __DATE__ " " __TIME__ "; 8-slot buckets; 4-lane subgroup probing";
@@ -1165,13 +1173,14 @@ det_status insert_impl(det_table* t, const int64_t* keys, const void* values, si
   const bool tma = variant == 1 && (((uintptr_t)keys & 15u) == 0);
   return dispatch_vec(vec, [&](auto V) -> det_status {
     constexpr int VV = decltype(V)::value;
-    if (tma) {
-      const int grid = grid_for(n, kTileKeys, t->sm_count, occupancy_of(insert_kernel_tma<VV>, kThreads));
-      DET_LAUNCH(insert_kernel_tma<VV>, grid, kThreads, 0, s, v, (const long long*)keys, (const unsigned char*)values, n, g, si);
-    } else {
-      const int grid = grid_for(n, kThreads, t->sm_count, occupancy_of(insert_kernel<VV>, kThreads));
-      DET_LAUNCH(insert_kernel<VV>, grid, kThreads, 0, s, v, (const long long*)keys, (const unsigned char*)values, n, g, si);
-    }
+    // DET_CLAIM_BATCH=1: the batched-claim probe (common.cuh), a round-2 candidate for inserts of NEW keys; the
+    // default is the validated serial claim
+    const bool batch = env_int("DET_CLAIM_BATCH", 0) != 0;
+    using KernelFn = void (*)(TableView, const long long*, const unsigned char*, size_t, RowGeom, SlotInit);
+    const KernelFn kfn = tma ? (batch ? (KernelFn)insert_kernel_tma<VV, true> : (KernelFn)insert_kernel_tma<VV, false>)
+                             : (batch ? (KernelFn)insert_kernel<VV, true> : (KernelFn)insert_kernel<VV, false>);
+    const int grid = grid_for(n, tma ? kTileKeys : kThreads, t->sm_count, occupancy_of(kfn, kThreads));
+    DET_LAUNCH(kfn, grid, kThreads, 0, s, v, (const long long*)keys, (const unsigned char*)values, n, g, si);
     CUDA_TRY(cudaGetLastError());
     if (check_room) note_mutation(t, n, s);
     return DET_OK;

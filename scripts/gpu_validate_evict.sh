@@ -24,3 +24,9 @@ timeout 600 python scripts/evict_microbench.py --capacity 20000000 --steps 100 >
 echo "evict microbench exit: $?"; tail -n 3 gpurun_out/evict_microbench.jsonl
 timeout 600 python scripts/spill_microbench.py > gpurun_out/spill_microbench.jsonl 2> gpurun_out/spill_microbench.err
 echo "spill microbench exit: $?"; cat gpurun_out/spill_microbench.jsonl
+# round-2 candidate: batched slot claims for inserts of NEW keys (DET_CLAIM_BATCH=1, common.cuh); correctness first
+# (the validated table suite under the variant), then the A/B of insert_new / insert_existing at dim 16 / 64 / 128
+DET_CLAIM_BATCH=1 timeout 900 python -m pytest tests/test_table_gpu.py tests/test_fused_gpu.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/claim_batch_tests.log
+timeout 600 python scripts/microbench.py --ops insert_new,insert_existing --resident 20000000 --tag serial > gpurun_out/claim_serial.jsonl 2> gpurun_out/claim_serial.err
+DET_CLAIM_BATCH=1 timeout 600 python scripts/microbench.py --ops insert_new,insert_existing --resident 20000000 --tag batched > gpurun_out/claim_batched.jsonl 2> gpurun_out/claim_batched.err
+echo "claim A/B:"; cat gpurun_out/claim_serial.jsonl gpurun_out/claim_batched.jsonl | cut -c1-300

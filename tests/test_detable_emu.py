@@ -504,3 +504,76 @@ def test_bounded_table_purges_tombstones_in_place_before_evicting():
   np.testing.assert_array_equal(out, kv)
   t.check()
   t.close()
+
+
+# ---- (3) the batched-claim candidate (DET_CLAIM_BATCH=1: probe all 4 rounds, then claim together; common.cuh) ----------
+@pytest.fixture
+def claim_batch(monkeypatch):
+  monkeypatch.setenv("DET_CLAIM_BATCH", "1")   # read by insert_impl at every call
+
+
+def test_batched_claim_standard_path(claim_batch):
+  """the whole standard-path scenario (growth, tombstones, both sentinel-valued keys, accum, export) with inserts going
+  through the batched-claim kernels"""
+  test_standard_path_growth_find_accum_remove_export()
+
+
+def test_batched_claim_contention_duplicates_and_crowded_buckets(claim_batch):
+  """what the batched claim changes is WHEN claims happen: (1) duplicates of a key inside one call -- in the same warp,
+  in different rounds, in different warps -- must still leave ONE copy; (2) many new keys of one call competing for the
+  free slots of the same few buckets (tiny table, load ~0.85): claims that lose their slot go through the serial
+  fallback; (3) tombstones are recycled.  Warps are OS threads here, so the CAS races are real."""
+  rng = np.random.default_rng(5)
+  # (1) heavy duplication: 4096 entries over 300 distinct keys, shuffled
+  stat = L().det_emu_stat
+  stat.restype, stat.argtypes = ctypes.c_ulonglong, [ctypes.c_int]
+  steps0, pending0 = stat(0), stat(1)
+  t = Table(dim=4, init=8192)
+  distinct = rng.choice(1 << 40, size=300, replace=False).astype(np.int64)
+  ks = rng.choice(distinct, size=4096)
+  vs = np.repeat(ks.astype(np.float32).reshape(-1, 1), 4, axis=1)     # every duplicate carries the same row
+  st = L().det_insert(t.h, P(ks), P(vs), len(ks), None)
+  assert st == 0, L().det_last_error()
+  assert t.size() == len(np.unique(ks))
+  ek, ev = t.export()
+  assert len(np.unique(ek)) == len(ek) == len(np.unique(ks))
+  out, ex = t.find(distinct)
+  present = np.isin(distinct, ks)
+  assert np.array_equal(ex, present) and np.array_equal(out[present][:, 0], distinct[present].astype(np.float32))
+  t.check()
+  t.close()
+  # (2) + (3) crowded table with churn: fill to ~0.85 with unique keys in big calls, remove a third, refill
+  t = Table(dim=2, init=2048, max_capacity=2048, lf=0.9)
+  ref = {}
+  pool = rng.choice(1 << 40, size=6000, replace=False).astype(np.int64)
+  cursor = 0
+  for rnd in range(4):
+    room = int(2048 * 0.85) - len(ref)
+    ks = pool[cursor:cursor + room]
+    cursor += room
+    vs = rng.standard_normal((len(ks), 2)).astype(np.float32)
+    t.insert(ks, vs)
+    for k, v in zip(ks.tolist(), vs):
+      ref[k] = v.copy()
+    assert t.size() == len(ref)
+    gone = rng.choice(np.array(sorted(ref), dtype=np.int64), size=len(ref) // 3, replace=False)
+    t.remove(gone)
+    for k in gone.tolist():
+      del ref[k]
+  allk = np.array(sorted(ref), dtype=np.int64)
+  out, ex = t.find(allk)
+  assert ex.all() and all(np.array_equal(o, ref[k]) for k, o in zip(allk.tolist(), out))
+  ek, _ = t.export()
+  assert sorted(ek.tolist()) == sorted(ref)
+  st = t.stats()
+  assert st["error_flags"] == 0 and st["size"] == len(ref)
+  t.close()
+  # the candidate path really ran, and so did its fallback (claims that lost their slot to another key)
+  assert stat(0) - steps0 >= 4096 // 32 and stat(1) - pending0 >= 1
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+                                                                 HealthCheck.function_scoped_fixture])
+@given(hst.sampled_from([16, 24, 64]), hst.sampled_from([0.0, 0.9]), _OPS)
+def test_batched_claim_random_op_streams(claim_batch, init, lf, ops):
+  test_random_op_streams_against_a_dict.hypothesis.inner_test(init, lf, ops)
