@@ -38,6 +38,11 @@ def needs_build():
   return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _extra_flags():
+  """DET_NVCC_EXTRA="-DDET_FIND_MINB=5 ...": extra nvcc flags for measurement builds (scripts/occupancy_sweep.sh)"""
+  return os.environ.get("DET_NVCC_EXTRA", "").split()
+
+
 def build(force=False, verbose=False):
   """Returns the path of libdetable.so, (re)building it when a source is newer.  Safe under torchrun: the build
   is serialised with a file lock, written to a temporary name and renamed, so concurrent ranks never load a
@@ -57,7 +62,7 @@ def build(force=False, verbose=False):
       if not force and not needs_build():
         return LIB  # another rank built it while we waited
       tmp = LIB + ".tmp.%d" % os.getpid()
-      cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+      cmd = [nvcc] + NVCC_FLAGS + _extra_flags() + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES]
       out = subprocess.run(cmd, capture_output=True, text=True)
       if out.returncode != 0:

@@ -65,6 +65,18 @@ int grid_for(size_t n_items, int items_per_block, int sm_count, int blocks_per_s
 // Kernels
 // ================================================================================================
 constexpr int kThreads = 256;
+// Occupancy experiments (scripts/occupancy_sweep.sh builds variants with -DDET_FIND_MINB=n / -DDET_INSERT_MINB=n: a
+// minimum of n resident CTAs per SM caps the registers of the headline kernels); undefined = the measured default.
+#ifdef DET_FIND_MINB
+#define DET_FIND_BOUNDS __launch_bounds__(kThreads, DET_FIND_MINB)
+#else
+#define DET_FIND_BOUNDS __launch_bounds__(kThreads)
+#endif
+#ifdef DET_INSERT_MINB
+#define DET_INSERT_BOUNDS __launch_bounds__(kThreads, DET_INSERT_MINB)
+#else
+#define DET_INSERT_BOUNDS __launch_bounds__(kThreads)
+#endif
 constexpr int kWarpsPerBlock = kThreads / 32;
 
 // K1: Find / FindWithExists with the default-row fill folded in (replaces HKV find +
@@ -88,7 +100,7 @@ __device__ __forceinline__ void find_step(const TableView& t, long long key, siz
 
 // variant 0: keys read with coalesced LDG, grid-stride by warp
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void DET_FIND_BOUNDS
 find_kernel(TableView t, const long long* __restrict__ keys, size_t n,
             const unsigned char* __restrict__ defaults, int full_default,
             unsigned char* __restrict__ out, unsigned char* __restrict__ exists, RowGeom g) {
@@ -106,7 +118,7 @@ find_kernel(TableView t, const long long* __restrict__ keys, size_t n,
 // variant 1 (default): persistent CTAs, key tiles staged into shared memory by TMA bulk copies
 // (cp.async.bulk + mbarrier), tile i+1 in flight while tile i is probed and gathered
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void DET_FIND_BOUNDS
 find_kernel_tma(TableView t, const long long* __restrict__ keys, size_t n,
                 const unsigned char* __restrict__ defaults, int full_default,
                 unsigned char* __restrict__ out, unsigned char* __restrict__ exists, RowGeom g) {
@@ -156,7 +168,7 @@ __device__ __forceinline__ void insert_step(const TableView& t, long long key, s
 }
 
 template <int VEC, bool BATCH = false>
-__global__ void __launch_bounds__(kThreads)
+__global__ void DET_INSERT_BOUNDS
 insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
               size_t n, RowGeom g, SlotInit si) {
   __shared__ unsigned s_new, s_used;
@@ -182,7 +194,7 @@ insert_kernel(TableView t, const long long* __restrict__ keys, const unsigned ch
 }
 
 template <int VEC, bool BATCH = false>
-__global__ void __launch_bounds__(kThreads)
+__global__ void DET_INSERT_BOUNDS
 insert_kernel_tma(TableView t, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
                   size_t n, RowGeom g, SlotInit si) {
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
