@@ -11,6 +11,8 @@ from .restrict_policies import FrequencyRestrictPolicy, RestrictPolicy, Timestam
 from .sharded import PeerShardedVariable, ShardedVariable
 from . import layers
 from . import shadow_ops
+from . import math
+from . import data_flow
 
 __all__ = [
     "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvEvictStrategy", "HkvHashTable", "HkvHashTableConfig",
@@ -19,5 +21,5 @@ __all__ = [
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
     "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy", "TrainableWrapper", "ModelMode",
     "enable_inference_mode", "enable_train_mode", "get_model_mode", "trainable_wrapper_filter", "shadow_ops",
-    "ComposedOptimizer",
+    "ComposedOptimizer", "math", "data_flow",
 ]

@@ -224,3 +224,42 @@ def test_sharded_backward_routes_and_combines_world2_gloo():
     assert p.exitcode == 0
   assert all(ok for _, ok, _ in res), res
   assert sum(n for _, _, n in res) == 40
+
+
+def test_math_and_data_flow_mirrors():
+  """de.math / de.data_flow (python/ops/math_ops.py:60-215, data_flow_ops.py:40-61): the doc examples of the TF ops
+  they stand for"""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  c = torch.tensor([[1, 2, 3, 4], [-1, -2, -3, -4], [5, 6, 7, 8]])
+  # tf.sparse.segment_sum examples
+  assert de.math.sparse_segment_sum(c, [0, 1], [0, 0]).tolist() == [[0, 0, 0, 0]]
+  assert de.math.sparse_segment_sum(c, [0, 1], [0, 1]).tolist() == [[1, 2, 3, 4], [-1, -2, -3, -4]]
+  assert de.math.sparse_segment_sum(c, [0, 1, 2], [0, 0, 1]).tolist() == [[0, 0, 0, 0], [5, 6, 7, 8]]
+  assert de.math.sparse_segment_sum(c, [0, 1], [0, 2], num_segments=4).tolist() == [[1, 2, 3, 4], [0] * 4, [-1, -2, -3, -4], [0] * 4]
+  with pytest.raises(ValueError):
+    de.math.sparse_segment_sum(c, [0, 1], [1, 0])
+  # tf.sparse.fill_empty_rows example: rows 2 and 4 of a [5, 6] input are empty
+  sp = de.SparseIds(torch.tensor([[0, 1], [0, 3], [1, 2], [1, 3], [3, 1], [3, 3]]), torch.tensor([1, 2, 3, 4, 5, 6]), (5, 6))
+  filled, was_empty = de.math.sparse_fill_empty_rows(sp, 9)
+  assert filled.indices.tolist() == [[0, 1], [0, 3], [1, 2], [1, 3], [2, 0], [3, 1], [3, 3], [4, 0]]
+  assert filled.values.tolist() == [1, 2, 3, 4, 9, 5, 6, 9] and was_empty.tolist() == [False, False, True, False, True]
+  # tf.sparse.reshape example: [2, 3, 6] -> [9, -1]
+  sp = de.SparseIds(torch.tensor([[0, 0, 0], [0, 0, 1], [0, 1, 0], [1, 0, 0], [1, 2, 3]]), torch.arange(5), (2, 3, 6))
+  r = de.math.sparse_reshape(sp, [9, -1])
+  assert r.dense_shape == (9, 4) and r.indices.tolist() == [[0, 0], [0, 1], [1, 2], [4, 2], [8, 1]]
+  with pytest.raises(ValueError):
+    de.math.sparse_reshape(sp, [7, -1])
+  # tf.dynamic_partition / tf.dynamic_stitch examples
+  parts = de.data_flow.dynamic_partition(torch.tensor([10, 20, 30, 40, 50]), torch.tensor([0, 0, 1, 1, 0]), 2)
+  assert [p.tolist() for p in parts] == [[10, 20, 50], [30, 40]]
+  idx = [torch.tensor(6), torch.tensor([4, 1]), torch.tensor([[5, 2], [0, 3]])]
+  data = [torch.tensor([61, 62]), torch.tensor([[41, 42], [11, 12]]), torch.tensor([[[51, 52], [21, 22]], [[1, 2], [31, 32]]])]
+  assert de.data_flow.dynamic_stitch(idx, data).tolist() == [[1, 2], [11, 12], [21, 22], [31, 32], [41, 42], [51, 52], [61, 62]]
+  # partition + stitch round trip = the identity (make_partition / _stitch of de.Variable)
+  x = torch.arange(12.).reshape(6, 2)
+  p = torch.tensor([2, 0, 1, 0, 2, 1])
+  pos = de.data_flow.dynamic_partition(torch.arange(6), p, 3)
+  rows = de.data_flow.dynamic_partition(x, p, 3)
+  assert torch.equal(de.data_flow.dynamic_stitch(pos, rows), x)
+  assert de.data_flow.dynamic_stitch([torch.tensor([0, 0])], [torch.tensor([1., 2.])]).tolist() == [2.0]
