@@ -5,7 +5,7 @@ of the UNIQUE rows from the table, autograd produces the gradient of that scratc
 writes the update back with the fused find-or-insert + optimizer kernel."""
 import torch
 
-from .optimizer import _FusedBase
+from .optimizer import ComposedOptimizer, _FusedBase
 from .sharded import PeerShardedVariable
 from .variable import Variable, default_partition_fn, embedding_lookup_unique, unique
 
@@ -38,7 +38,7 @@ class Embedding(torch.nn.Module):
 
   def apply_gradients(self, optimizer):
     """optimizer: de.FusedAdagrad / de.FusedAdam (or DynamicEmbeddingOptimizer(torch optimizer))."""
-    if not isinstance(optimizer, _FusedBase):
+    if not isinstance(optimizer, (_FusedBase, ComposedOptimizer)):
       raise TypeError("use de.DynamicEmbeddingOptimizer(...) / de.FusedAdagrad / de.FusedAdam")
     gv = [(tw.values.grad, tw) for tw in self._wrappers if tw.values.grad is not None]
     self._wrappers = []

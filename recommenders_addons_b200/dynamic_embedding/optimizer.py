@@ -204,36 +204,44 @@ class ComposedOptimizer(object):
     self.iterations += 1
     for grad, var in grads_and_vars:
       tw = var if isinstance(var, TrainableWrapper) else TrainableWrapper(var[0], var[1])
-      params = tw.params
-      if not isinstance(params, Variable):
-        raise TypeError("params should be a Variable instance.")
-      flat = tw.ids.reshape(-1)
-      if tw.values is None or (tw._old_values is None and params.bp_v2):
-        tw.prefetch_values()
-      p = torch.nn.Parameter(tw.values.detach().clone().reshape(-1, params.dim))
-      p.grad = grad.reshape(-1, params.dim).to(p.dtype)
-      opt = self._cls([p], **self._defaults)
-      slots = self._slots_of(params)
-      # state that is not per row (step counters, NAdam's mu_product ...) is carried by this object, per variable
-      carried = self._globals.get(params.name)
-      if carried is None:
-        carried = {k: v for k, v in self._materialize(opt, p).items() if k not in slots}
-      inject = bool(carried) or not self._scalar_keys
-      if inject:   # (else: first step of an optimizer whose initial scalars are unknown -> torch's fresh state,
-        #             identical to the slot tables' initial values)
-        state = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in carried.items()}
-        for k, sv in slots.items():
-          state[k] = sv.lookup(flat).reshape(-1, params.dim).clone()
-        opt.state[p] = state
-      opt.step()
-      after = opt.state[p]
-      self._globals[params.name] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in after.items()
-                                    if k not in slots}
-      tw.values = p.detach()
-      tw.update_op()
+      self._apply_one(tw, grad)
+
+  def apply_sparse(self, params, keys, grads):
+    """one step on the rows of `params` selected by the unique `keys` (the entry point the sharded variables call
+    on the owning rank after routing and combining the gradients; same name as the fused optimizers')"""
+    self._apply_one(TrainableWrapper(params, keys), grads)
+
+  def _apply_one(self, tw, grad):
+    params = tw.params
+    if not isinstance(params, Variable):
+      raise TypeError("params should be a Variable instance.")
+    flat = tw.ids.reshape(-1)
+    if tw.values is None or (tw._old_values is None and params.bp_v2):
+      tw.prefetch_values()
+    p = torch.nn.Parameter(tw.values.detach().clone().reshape(-1, params.dim))
+    p.grad = grad.reshape(-1, params.dim).to(p.dtype)
+    opt = self._cls([p], **self._defaults)
+    slots = self._slots_of(params)
+    # state that is not per row (step counters, NAdam's mu_product ...) is carried by this object, per variable
+    carried = self._globals.get(params.name)
+    if carried is None:
+      carried = {k: v for k, v in self._materialize(opt, p).items() if k not in slots}
+    inject = bool(carried) or not self._scalar_keys
+    if inject:   # (else: first step of an optimizer whose initial scalars are unknown -> torch's fresh state,
+      #             identical to the slot tables' initial values)
+      state = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in carried.items()}
       for k, sv in slots.items():
-        if torch.is_tensor(after.get(k)):
-          sv.upsert(flat, after[k])
+        state[k] = sv.lookup(flat).reshape(-1, params.dim).clone()
+      opt.state[p] = state
+    opt.step()
+    after = opt.state[p]
+    self._globals[params.name] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in after.items()
+                                  if k not in slots}
+    tw.values = p.detach()
+    tw.update_op()
+    for k, sv in slots.items():
+      if torch.is_tensor(after.get(k)):
+        sv.upsert(flat, after[k])
 
 
 def DynamicEmbeddingOptimizer(self, bp_v2=False, synchronous=False, fused=True, **kwargs):

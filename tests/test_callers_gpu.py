@@ -161,6 +161,21 @@ def test_get_slot_variables_and_restrict_policy_tracks_them():
   assert var.get_trainable_by_name("user_embedding") is sh and var.get_trainable_by_name("nope") is None
 
 
+def test_layers_and_apply_sparse_take_any_optimizer():
+  """de.layers.Embedding.apply_gradients with a composed optimizer; ComposedOptimizer.apply_sparse is what the sharded
+  variables call on the owning rank (same name and arguments as the fused optimizers')"""
+  de = _de()
+  layer = de.layers.Embedding(DIM, initializer=1.0, devices=[DEV], name="layer-any-opt", num_slot_planes=0)
+  opt = de.DynamicEmbeddingOptimizer(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.5))
+  layer.train()
+  layer(torch.tensor([[3, 4], [4, 5]], device=DEV)).sum().backward()
+  layer.apply_gradients(opt)
+  got = layer.params.lookup(torch.tensor([3, 4, 5, 6], device=DEV)).cpu()
+  assert torch.allclose(got[:, 0], torch.tensor([0.5, 0.0, 0.5, 1.0]))    # id 4 appears twice: gradient 2
+  opt.apply_sparse(layer.params, torch.tensor([6, 7], device=DEV), torch.ones(2, DIM, device=DEV))
+  assert torch.allclose(layer.params.lookup(torch.tensor([6, 7], device=DEV)).cpu(), torch.full((2, DIM), 0.5))
+
+
 def test_model_mode_and_trainable_wrapper_filter():
   de = _de()
   var = de.get_variable("modes", dim=DIM, initializer=2.0, devices=[DEV])

@@ -120,6 +120,7 @@ def test_composed_and_fused_paths_agree(kind):
 
 @pytest.mark.parametrize("name", ["test_untouched_rows_and_slot_tables_stay_sparse",
                                   "test_get_slot_variables_and_restrict_policy_tracks_them",
+                                  "test_layers_and_apply_sparse_take_any_optimizer",
                                   "test_model_mode_and_trainable_wrapper_filter",
                                   "test_shadow_variable_training_matches_dense_twin"])
 def test_callers_suite_body(name):
