@@ -158,3 +158,21 @@ def test_table_file_ops_append_and_load_entire_dir(tmp_path):
   assert len(np.fromfile(os.path.join(d, "emb_mht_1of2-keys"), dtype="<i8")) == 1200
   with pytest.raises(Exception):
     c.load_from_file_system(d, file_name="nothing_mht_1of1", load_entire_dir=True)
+
+
+def test_smoke_body_on_the_emulated_library():
+  """__graft_entry__.smoke() -- what the driver runs on cuda:0 at round end -- with CPU tensors over the emulated
+  library: its Python glue and every entry point it calls keep working between GPU runs"""
+  import inspect
+  import __graft_entry__ as entry
+  src = inspect.getsource(entry.smoke)
+  for cuda_only in ('assert torch.cuda.is_available(), "smoke() needs cuda:0"', "torch.cuda.set_device(0)",
+                    "torch.cuda.synchronize()"):
+    assert cuda_only in src
+    src = src.replace(cuda_only, "pass")
+  make = 'var = de.Variable(dim=dim, initializer=0.5, num_slot_planes=1, name="smoke")'
+  assert make in src
+  src = src.replace(make, make[:-1] + ', devices=["cpu"])')
+  ns = {}
+  exec(src, ns)  # pylint: disable=exec-used
+  ns["smoke"]()
