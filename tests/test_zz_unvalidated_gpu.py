@@ -20,7 +20,7 @@ def test_unvalidated_suites_in_a_subprocess():
   env = dict(os.environ, DET_TEST_UNVALIDATED="1")
   r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_evict_gpu.py", "tests/test_restrict_gpu.py",
                       "tests/test_spill_gpu.py", "tests/test_callers_gpu.py", "-q", "-m",
-                      "gpu", "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=900, capture_output=True, text=True)
+                      "gpu", "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=480, capture_output=True, text=True)
   print(r.stdout[-6000:])
   print(r.stderr[-2000:])
   assert r.returncode == 0
