@@ -292,6 +292,13 @@ det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int ap
   if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_save: null argument");
   det::DevGuard _dg(t->cfg.device);
   if (buffer_keys == 0) buffer_keys = 1u << 20;
+  {  // a table smaller than the buffer needs no more staging memory than its own size
+    int64_t n = 0;
+    det_status sst = det_size(t, &n, nullptr);
+    if (sst != DET_OK) return sst;
+    const size_t want = n > 0 ? (size_t)n : 1;
+    if (buffer_keys > want) buffer_keys = want;
+  }
   const size_t rb = t->row_bytes;
   long long* dk = nullptr;
   unsigned char* dv = nullptr;
@@ -349,6 +356,12 @@ det_status det_load(det_table* t, const char* prefix, size_t buffer_keys, int cl
   }
   const size_t rb = t->row_bytes;
   if (buffer_keys == 0) buffer_keys = 1u << 20;
+  if (fseek(fk, 0, SEEK_END) == 0) {  // a file shorter than the buffer needs no more staging memory than its own size
+    const long bytes = ftell(fk);
+    const size_t n_file = bytes > 0 ? (size_t)bytes / 8 : 0;
+    if (buffer_keys > n_file) buffer_keys = n_file ? n_file : 1;
+    rewind(fk);
+  }
   std::vector<long long> hk(buffer_keys);
   std::vector<unsigned char> hv(buffer_keys * rb);
   det_status st = DET_OK;
