@@ -259,3 +259,43 @@ def test_shadow_variable_training_matches_dense_twin():
     de.shadow_ops.embedding_lookup(shadow, torch.tensor([1], dtype=torch.int32, device=DEV))
   with pytest.raises(TypeError):
     de.shadow_ops.ShadowVariable(object())
+
+
+def test_read_only_ops_are_cuda_graph_capturable():
+  """serving: det_find / det_lookup_sparse take no host lock, allocate nothing and never synchronise, so a caller can
+  capture them in a CUDA graph (small-batch inference is launch-bound) and replay with new keys in the same buffer"""
+  if DEV != "cuda":
+    pytest.skip("CUDA graphs need a GPU")
+  de = _de()
+  from recommenders_addons_b200.dynamic_embedding.ops import lookup_sparse_fused
+  dim, n = 64, 4096
+  var = de.get_variable("graph-capture", dim=dim, initializer=0.5, devices=[DEV])
+  rng = np.random.default_rng(1)
+  keys = np.unique(rng.integers(0, 1 << 40, 3 * n))[:2 * n].astype(np.int64)
+  vals = rng.normal(0, 0.01, (len(keys), dim)).astype(np.float32)
+  var.upsert(K(keys), torch.as_tensor(vals, device=DEV))
+  table = var.tables[0]
+  static_keys = K(keys[:n]).clone()
+  seg = torch.arange(n, device=DEV, dtype=torch.int32) // 4
+  side = torch.cuda.Stream()
+  with torch.cuda.stream(side):          # warm-up: occupancy queries, scratch buffers
+    for _ in range(3):
+      table.lookup(static_keys, return_exists=True)
+      lookup_sparse_fused(var, static_keys, seg, None, n // 4, "sum")
+  torch.cuda.current_stream().wait_stream(side)
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    out, ex = table.lookup(static_keys, return_exists=True)
+    pooled = lookup_sparse_fused(var, static_keys, seg, None, n // 4, "sum")
+  for trial in range(3):
+    q = np.concatenate([keys[rng.permutation(len(keys))[:n - 100]], rng.integers(1 << 41, 1 << 42, 100)]).astype(np.int64)
+    static_keys.copy_(K(q))
+    graph.replay()
+    torch.cuda.synchronize()
+    exp, eex = table.lookup(K(q), return_exists=True)
+    assert torch.equal(out, exp) and torch.equal(ex, eex)
+    assert torch.equal(pooled, lookup_sparse_fused(var, K(q), seg, None, n // 4, "sum"))
+
+
+def K(a):
+  return torch.as_tensor(np.asarray(a, dtype=np.int64), device=DEV)
