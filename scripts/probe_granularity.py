@@ -1,0 +1,36 @@
+"""Round-2 probe: what does ONE random read of 32 / 64 / 128 / 256 contiguous bytes cost in DRAM traffic on this GPU?
+ncu showed find_kernel_tma reading ~137 B of DRAM per 64 B bucket probe (profiles/r01_find_kernel_tma_dim64.csv: 408.5 MB
+per 1,048,576 keys = 8 B key + 256 B row + ~137 B probe); if a random 64 B read really fetches 128 B, 16-slot / 128 B
+buckets cost nothing extra per probe (follow-up 1) and 4-slot / 32 B buckets would save nothing.
+Run under ncu, one launch per row size (the torch gather kernel is the measured kernel):
+  ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum,lts__t_sectors_srcunit_tex_op_read.sum \\
+      --clock-control none -k regex:index --csv --log-file gpurun_out/granularity.csv python scripts/probe_granularity.py
+Prints the row sizes in launch order; divide each launch's dram__bytes_read by N (and subtract the 8 B index read)."""
+import json
+
+import torch
+
+N = 1 << 22
+ROWS = 1 << 26  # 64M rows: 2..16 GB tables, far beyond L2
+
+
+def main():
+  dev = torch.device("cuda", 0)
+  g = torch.Generator(device=dev).manual_seed(0)
+  order = []
+  for row_bytes in (32, 64, 128, 256):
+    words = row_bytes // 8
+    table = torch.zeros((ROWS, words), dtype=torch.int64, device=dev)
+    idx = torch.randint(0, ROWS, (N,), device=dev, generator=g)
+    torch.cuda.synchronize()
+    for _ in range(2):
+      out = table.index_select(0, idx)
+    torch.cuda.synchronize()
+    order.append({"row_bytes": row_bytes, "reads": N, "launches": 2, "out_bytes": int(out.numel() * 8)})
+    del table, out
+    torch.cuda.empty_cache()
+  print(json.dumps(order))
+
+
+if __name__ == "__main__":
+  main()
