@@ -31,6 +31,6 @@ timeout 600 python scripts/microbench.py --ops insert_new,insert_existing --resi
 DET_CLAIM_BATCH=1 timeout 600 python scripts/microbench.py --ops insert_new,insert_existing --resident 20000000 --tag batched > gpurun_out/claim_batched.jsonl 2> gpurun_out/claim_batched.err
 echo "claim A/B:"; cat gpurun_out/claim_serial.jsonl gpurun_out/claim_batched.jsonl | cut -c1-300
 # how much DRAM traffic does one random 32 / 64 / 128 / 256 B read cost? (decides the bucket-width follow-up)
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k regex:index --csv \
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k "regex:[iI]ndex|gather" --csv \
   --log-file gpurun_out/granularity.csv python scripts/probe_granularity.py > gpurun_out/granularity.json 2> gpurun_out/granularity.err
-echo "granularity probe exit: $?"; grep -c index gpurun_out/granularity.csv
+echo "granularity probe exit: $?"; grep -ci "index\|gather" gpurun_out/granularity.csv

@@ -4,7 +4,7 @@ per 1,048,576 keys = 8 B key + 256 B row + ~137 B probe); if a random 64 B read 
 buckets cost nothing extra per probe (follow-up 1) and 4-slot / 32 B buckets would save nothing.
 Run under ncu, one launch per row size (the torch gather kernel is the measured kernel):
   ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum,lts__t_sectors_srcunit_tex_op_read.sum \\
-      --clock-control none -k regex:index --csv --log-file gpurun_out/granularity.csv python scripts/probe_granularity.py
+      --clock-control none -k "regex:[iI]ndex|gather" --csv --log-file gpurun_out/granularity.csv python scripts/probe_granularity.py
 Prints the row sizes in launch order; divide each launch's dram__bytes_read by N (and subtract the 8 B index read)."""
 import json
 
