@@ -202,6 +202,14 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
                              const float* weights, size_t nnz, size_t batch, int combiner,
                              const float* default_row, float* out, det_stream_t stream);
 
+/* The same with `max_norm` (embedding_lookup_sparse(..., max_norm); tf.clip_by_norm of every looked-up row BEFORE it is
+ * weighted, python/ops/embedding_weights.py:497-521): row <- row * max_norm / max(||row||_2, max_norm), folded into the
+ * gather.  max_norm == 0: no clipping (= det_lookup_sparse).  Rows of at most 32 vectors (dim <= 128 when dim % 4 == 0,
+ * else dim <= 32); DET_UNIMPLEMENTED beyond.  ABI >= 3. */
+det_status det_lookup_sparse_clip(det_table* t, const int64_t* ids, const int32_t* segment_ids,
+                                  const float* weights, size_t nnz, size_t batch, int combiner,
+                                  const float* default_row, float max_norm, float* out, det_stream_t stream);
+
 /* One DynamicEmbeddingOptimizer step on unique keys, fused (find param + find slot(s) -> dense
  * rule -> upsert param + upsert slot(s); python/ops/dynamic_embedding_optimizer.py:161-204,
  * python/ops/embedding_weights.py:434-444).  Missing keys start from init_param[dim]

@@ -21,7 +21,8 @@ REGISTER_OP("TFRA>DetLookupSparse")
     .Input("default_row: float")   // [dim]
     .Output("output: float")       // [batch, dim]
     .Attr("batch: int >= 0")
-    .Attr("combiner: {'sum', 'mean', 'sqrtn'} = 'mean'");
+    .Attr("combiner: {'sum', 'mean', 'sqrtn'} = 'mean'")
+    .Attr("max_norm: float = 0.0");  // > 0: clip every looked-up row to this l2-norm before it is weighted
 
 REGISTER_OP("TFRA>DetApplyAdagrad")
     .Input("table_handle: resource")
@@ -55,6 +56,7 @@ class DetLookupSparseOp : public OpKernel {
     combiner_ = combiner == "sum" ? DET_COMBINER_SUM : combiner == "mean" ? DET_COMBINER_MEAN : DET_COMBINER_SQRTN;
     OP_REQUIRES(ctx, combiner == "sum" || combiner == "mean" || combiner == "sqrtn",
                 errors::InvalidArgument("combiner must be one of 'mean', 'sqrtn' or 'sum'"));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("max_norm", &max_norm_));
   }
   void Compute(OpKernelContext* ctx) override {
     tensorflow::lookup::LookupInterface* table = nullptr;
@@ -72,16 +74,17 @@ class DetLookupSparseOp : public OpKernel {
     OP_REQUIRES(ctx, def.NumElements() == dim, errors::InvalidArgument("default_row must have shape [dim]"));
     Tensor* out = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output("output", TensorShape({batch_, dim}), &out));
-    OP_REQUIRES_OK(ctx, ToStatus(det_lookup_sparse(
+    OP_REQUIRES_OK(ctx, ToStatus(det_lookup_sparse_clip(
                             t->handle(), reinterpret_cast<const int64_t*>(ids.flat<int64>().data()),
                             seg.flat<int32>().data(), w.NumElements() ? w.flat<float>().data() : nullptr,
                             static_cast<size_t>(ids.NumElements()), static_cast<size_t>(batch_), combiner_,
-                            def.flat<float>().data(), out->flat<float>().data(), StreamOf(ctx))));
+                            def.flat<float>().data(), max_norm_, out->flat<float>().data(), StreamOf(ctx))));
   }
 
  private:
   int64 batch_ = 0;
   int combiner_ = DET_COMBINER_MEAN;
+  float max_norm_ = 0.f;
 };
 
 class DetApplyAdagradOp : public OpKernel {

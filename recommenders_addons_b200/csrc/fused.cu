@@ -244,12 +244,19 @@ constexpr int kSegPerGroup = 4;  // segments a lane-group works on concurrently 
 // consecutive output rows and walks their ids in lock step, so up to 4 independent row loads are in flight
 // per lane; within a segment the ids are accumulated strictly in order (mul, then add: the summation order of
 // the reference test oracle).
-template <int VF>
+// max_norm of embedding_lookup(_sparse) (tf.clip_by_norm over each looked-up row, python/ops/embedding_weights.py:497-521)
+// folded into the gather: an EMPTY trailing kernel parameter when unused, so the unclipped kernel is unchanged.
+template <bool CLIP> struct ClipArg {};
+template <> struct ClipArg<true> { float max_norm; };
+template <bool CLIP> __device__ __forceinline__ float clip_norm_of(const ClipArg<CLIP>&) { return 0.f; }
+template <> __device__ __forceinline__ float clip_norm_of<true>(const ClipArg<true>& c) { return c.max_norm; }
+
+template <int VF, bool CLIP = false>
 __global__ void __launch_bounds__(kThreadsF, 3)
 segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
                    const float* __restrict__ weights, size_t batch, int combiner,
                    const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
-                   unsigned lpr_shift) {
+                   unsigned lpr_shift, ClipArg<CLIP> clip) {
   constexpr int U = kSegPerGroup;
   const int lane = threadIdx.x & 31;
   const unsigned gl = (unsigned)lane & (lpr - 1u);
@@ -295,6 +302,19 @@ segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long 
       for (int u = 0; u < U; ++u) {
         x[u] = defv;
         if (sl[u] >= 0 && lane_on) x[u].load(table + (size_t)sl[u] * dim + (size_t)gl * VF);
+      }
+      if (CLIP) {
+        // row <- row * max_norm / max(||row||, max_norm): the squared norm is summed over the lanes of the group
+        // (lanes beyond the row hold zeros); every lane of the warp takes part in the shuffles (uniform loop)
+        const float mx = clip_norm_of(clip);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float ss = 0.f;
+          x[u].apply([&ss](float& a) { ss = ss + a * a; });
+          for (unsigned o = lpr >> 1; o > 0; o >>= 1) ss = ss + __shfl_xor_sync(kFull, ss, (int)o);
+          const float scale = mx / fmaxf(sqrtf(ss), mx);
+          x[u].apply([scale](float& a) { a = a * scale; });
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -782,10 +802,11 @@ det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t
   return DET_OK;
 }
 
-det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* segment_ids, const float* weights,
-                             size_t nnz, size_t batch, int combiner, const float* default_row, float* out,
-                             det_stream_t stream) {
+static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int32_t* segment_ids, const float* weights,
+                                     size_t nnz, size_t batch, int combiner, const float* default_row, float max_norm,
+                                     float* out, det_stream_t stream) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_lookup_sparse: null table");
+  if (!(max_norm >= 0.f)) return fail(DET_INVALID_ARGUMENT, "det_lookup_sparse: max_norm must be >= 0 (0 = no clipping)");
   std::lock_guard<std::mutex> _lk(t->mu);
   if (t->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_lookup_sparse: float32 tables only");
   if (combiner < DET_COMBINER_SUM || combiner > DET_COMBINER_SQRTN)
@@ -813,13 +834,28 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
   det_status rc = DET_OK;
   const unsigned gpw = 32u >> sh;
-  if (vpr <= lpr) {
+  if (vpr <= lpr && max_norm > 0.f) {
+    ClipArg<true> clip;
+    clip.max_norm = max_norm;
+    const auto k4 = segment_sum_kernel<4, true>;
+    const auto k1 = segment_sum_kernel<1, true>;
+    const int occ = vec4 ? occupancy_of(k4, kThreadsF) : occupancy_of(k1, kThreadsF);
+    const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
+    if (vec4)
+      DET_LAUNCH(k4, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip);
+    else
+      DET_LAUNCH(k1, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip);
+  } else if (max_norm > 0.f) {
+    rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse_clip: max_norm is fused for rows of at most 32 vectors (dim <= 128 when "
+                                 "dim % 4 == 0, else dim <= 32); use the composed path for wider rows");
+  } else if (vpr <= lpr) {
+    const ClipArg<false> noclip;
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
-      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
     else
-      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
   } else if ((vpr + lpr - 1) / lpr <= (unsigned)kMaxVecPerLane) {
     const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
     if (vec4)
@@ -831,6 +867,18 @@ det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* se
   }
   if (rc == DET_OK && cudaGetLastError() != cudaSuccess) rc = fail(DET_CUDA_ERROR, "det_lookup_sparse: launch failed");
   return rc;
+}
+
+det_status det_lookup_sparse(det_table* t, const int64_t* ids, const int32_t* segment_ids, const float* weights,
+                             size_t nnz, size_t batch, int combiner, const float* default_row, float* out,
+                             det_stream_t stream) {
+  return lookup_sparse_impl(t, ids, segment_ids, weights, nnz, batch, combiner, default_row, 0.f, out, stream);
+}
+
+det_status det_lookup_sparse_clip(det_table* t, const int64_t* ids, const int32_t* segment_ids, const float* weights,
+                                  size_t nnz, size_t batch, int combiner, const float* default_row, float max_norm,
+                                  float* out, det_stream_t stream) {
+  return lookup_sparse_impl(t, ids, segment_ids, weights, nnz, batch, combiner, default_row, max_norm, out, stream);
 }
 
 static det_status apply_common(det_table* t, const int64_t* keys, const float* grads, size_t n, OptHyper h,

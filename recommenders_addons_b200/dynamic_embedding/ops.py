@@ -21,8 +21,13 @@ def _fused_ok(params, default_rows):
   return (params.shard_num == 1 and params.value_dtype == torch.float32 and default_rows.numel() == params.dim)
 
 
-def lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner, default_row=None):
-  """K6: one kernel does find -> *weight -> per-segment sum -> normalise (det_lookup_sparse)."""
+def _clip_fusable(dim):
+  """rows the fused max_norm covers (det_lookup_sparse_clip): one vector per lane of a 32-lane group"""
+  return dim <= 128 if dim % 4 == 0 else dim <= 32
+
+
+def lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner, default_row=None, max_norm=None):
+  """K6: one kernel does find -> [clip] -> *weight -> per-segment sum -> normalise (det_lookup_sparse[_clip])."""
   table = params.tables[0]
   dev = table.device
   ids = ids.reshape(-1).to(dev).contiguous()
@@ -32,6 +37,11 @@ def lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner, defa
     default_row = table._default_value
   default_row = default_row.to(device=dev, dtype=torch.float32).contiguous()
   out = torch.empty((batch, params.dim), dtype=torch.float32, device=dev)
+  if max_norm is not None:
+    _lib.check(_lib.lib().det_lookup_sparse_clip(table.handle, _ptr(ids), _ptr(seg), _ptr(w), ids.numel(), batch,
+                                                 _lib.COMBINERS[combiner], _ptr(default_row), float(max_norm), _ptr(out),
+                                                 _stream_ptr(dev)))
+    return out
   _lib.check(_lib.lib().det_lookup_sparse(table.handle, _ptr(ids), _ptr(seg), _ptr(w), ids.numel(), batch,
                                           _lib.COMBINERS[combiner], _ptr(default_row), _ptr(out),
                                           _stream_ptr(dev)))
@@ -44,8 +54,9 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
   the dense matrix represented by sp_ids, combine (sum / mean / sqrtn) the weighted embeddings of its ids.
   Result: [dense_shape[0], dim] float32.
 
-  Forward-only calls on a single-shard fp32 variable with a constant default row run the fused kernel;
-  `return_trainable=True`, `max_norm`, sharded variables and random initializers take the composed
+  Forward-only calls on a single-shard fp32 variable with a constant default row run the fused kernel (with
+  `max_norm` folded into the gather for rows of up to 32 vectors);
+  `return_trainable=True`, sharded variables and random initializers take the composed
   path (unique -> lookup -> gather*weights -> segment sum), exactly the reference's op sequence."""
   if combiner not in ("mean", "sqrtn", "sum"):
     raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
@@ -64,8 +75,9 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
   batch = sp_ids.dense_shape[0]
   weights = None if ignore_weights else sp_weights.values
   static_default = params.initializer is None or not callable(params.initializer)
-  if not return_trainable and max_norm is None and static_default and _fused_ok(params, params.tables[0]._default_value):
-    return lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner)
+  if not return_trainable and static_default and _fused_ok(params, params.tables[0]._default_value) and \
+      (max_norm is None or (float(max_norm) > 0 and _clip_fusable(params.dim))):
+    return lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner, max_norm=max_norm)
 
   uniq, idx = unique(ids)
   r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)

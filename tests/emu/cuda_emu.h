@@ -308,6 +308,17 @@ static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
   emu::warp_barrier();
   return emu_from<T>(r);
 }
+template <typename T>
+static inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
+  emu::require_full(mask);
+  emu::Warp& w = *emu::W;
+  const int lane = emu::self()->lane;
+  w.vals[lane] = emu_bits(v);
+  emu::warp_barrier();
+  const unsigned long long r = w.vals[(lane ^ lane_mask) & 31];
+  emu::warp_barrier();
+  return emu_from<T>(r);
+}
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
   emu::require_full(mask);
   emu::Warp& w = *emu::W;

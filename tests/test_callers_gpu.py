@@ -261,6 +261,26 @@ def test_shadow_variable_training_matches_dense_twin():
     de.shadow_ops.ShadowVariable(object())
 
 
+@pytest.mark.parametrize("dim", [8, 64, 128])
+def test_lookup_sparse_max_norm_fused_vs_composed(dim):
+  """det_lookup_sparse_clip (max_norm folded into the gather) against the composed path, 1e-6"""
+  de = _de()
+  rng = np.random.default_rng(dim)
+  var = de.get_variable("mn-gpu-%d" % dim, dim=dim, initializer=0.0, devices=[DEV])
+  keys = torch.arange(5000, device=DEV)
+  rows = torch.as_tensor(rng.normal(0, 1.0 / np.sqrt(dim), (5000, dim)).astype(np.float32), device=DEV) * \
+      torch.linspace(0.2, 3, 5000, device=DEV)[:, None]
+  var.upsert(keys, rows)
+  n, batch = 40000, 6000
+  ind = torch.stack([torch.sort(torch.as_tensor(rng.integers(0, batch, n), device=DEV)).values, torch.arange(n, device=DEV)], 1)
+  sp = de.SparseIds(ind, torch.as_tensor(rng.integers(0, 6000, n), device=DEV), (batch, n))
+  sw = de.SparseIds(ind, torch.as_tensor(rng.uniform(0.5, 2, n).astype(np.float32), device=DEV), (batch, n))
+  for comb in ("sum", "mean", "sqrtn"):
+    got = de.embedding_lookup_sparse(var, sp, sw, combiner=comb, max_norm=1.0)
+    composed, _ = de.embedding_lookup_sparse(var, sp, sw, combiner=comb, max_norm=1.0, return_trainable=True)
+    np.testing.assert_allclose(got.cpu().numpy(), composed.detach().cpu().numpy(), rtol=2e-6, atol=2e-6)
+
+
 def test_read_only_ops_are_cuda_graph_capturable():
   """serving: det_find / det_lookup_sparse take no host lock, allocate nothing and never synchronise, so a caller can
   capture them in a CUDA graph (small-batch inference is launch-bound) and replay with new keys in the same buffer"""

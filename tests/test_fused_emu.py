@@ -12,7 +12,8 @@ from recommenders_addons_b200 import _lib as real
 from tests.helpers import sorted_export
 from tests.test_detable_emu import L, P, Table, ck
 
-_FUSED = ["det_unique_workspace_bytes", "det_unique", "det_lookup_sparse", "det_apply_adagrad", "det_apply_adam",
+_FUSED = ["det_unique_workspace_bytes", "det_unique", "det_lookup_sparse", "det_lookup_sparse_clip", "det_apply_adagrad",
+          "det_apply_adam",
           "det_partition_workspace_bytes", "det_partition", "det_scatter_rows", "det_gather_rows"]
 
 
@@ -99,6 +100,51 @@ def test_lookup_sparse_bit_exact_vs_oracle(combiner, use_weights, dim):
   ck(F().det_lookup_sparse(t.h, P(ids), P(seg), P(w), len(ids), batch, real.COMBINERS[combiner], P(default), P(out), None))
   exp = O.embedding_lookup_sparse(ot, ids, seg, w, batch, combiner, default=default)
   np.testing.assert_array_equal(out, exp)
+  t.close()
+
+
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+@pytest.mark.parametrize("dim", [1, 5, 16, 64, 128])
+def test_lookup_sparse_with_max_norm(combiner, dim):
+  """det_lookup_sparse_clip: tf.clip_by_norm of every looked-up row (missing ids: of the default row) BEFORE the weighted
+  combine (embedding_lookup_sparse(..., max_norm), python/ops/embedding_weights.py:497-521).  The norm is a sum of dim
+  squares (summation order differs from NumPy's): 1e-6 like the reference's max_norm tests, not bit-exact."""
+  rng = np.random.default_rng(dim + 31)
+  vocab, batch, max_norm = 600, 150, 0.35
+  t = Table(dim=dim, init=2048)
+  present = rng.choice(vocab, size=400, replace=False).astype(np.int64)
+  vals = rng.normal(0, 0.05 * 8 / np.sqrt(dim + 7), (400, dim)).astype(np.float32)   # norms on both sides of max_norm
+  t.insert(present, vals)
+  ids, seg, w = _sparse_case(rng, batch, 9, vocab)
+  default = np.full(dim, 0.9 / np.sqrt(dim), np.float32)                 # ||default|| = 0.9 > max_norm: clipped too
+  out = np.empty((batch, dim), dtype=np.float32)
+  ck(F().det_lookup_sparse_clip(t.h, P(ids), P(seg), P(w), len(ids), batch, real.COMBINERS[combiner], P(default), max_norm,
+                                P(out), None))
+
+  def clip(x):
+    n = np.sqrt((x.astype(np.float64) ** 2).sum(-1, keepdims=True))
+    return (x * (max_norm / np.maximum(n, max_norm))).astype(np.float32)
+  ot = O.PortTable(dim)
+  ot.insert(present, clip(vals))
+  exp = O.embedding_lookup_sparse(ot, ids, seg, w, batch, combiner, default=clip(default[None])[0])
+  norms = np.sqrt((vals.astype(np.float64) ** 2).sum(-1))
+  assert (norms > max_norm).any() and (norms < max_norm).any()
+  np.testing.assert_allclose(out, exp, rtol=1e-6, atol=1e-6)
+  # max_norm = 0 is the unclipped kernel, bit for bit
+  out0, ref0 = np.empty_like(out), np.empty_like(out)
+  ck(F().det_lookup_sparse_clip(t.h, P(ids), P(seg), P(w), len(ids), batch, real.COMBINERS[combiner], P(default), 0.0, P(out0), None))
+  ck(F().det_lookup_sparse(t.h, P(ids), P(seg), P(w), len(ids), batch, real.COMBINERS[combiner], P(default), P(ref0), None))
+  np.testing.assert_array_equal(out0, ref0)
+  assert F().det_lookup_sparse_clip(t.h, P(ids), P(seg), P(w), len(ids), batch, 0, P(default), -1.0, P(out), None) == 1
+  t.close()
+
+
+def test_lookup_sparse_max_norm_wide_rows_are_refused():
+  t = Table(dim=200, init=256)
+  ids, seg = np.arange(4, dtype=np.int64), np.arange(4, dtype=np.int32)
+  out = np.empty((4, 200), dtype=np.float32)
+  st = F().det_lookup_sparse_clip(t.h, P(ids), P(seg), None, 4, 4, 0, P(np.zeros(200, np.float32)), 1.0, P(out), None)
+  assert st == 5 and b"composed" in L().det_last_error()          # DET_UNIMPLEMENTED: the Python mirror composes
   t.close()
 
 

@@ -176,3 +176,7 @@ def test_smoke_body_on_the_emulated_library():
   ns = {}
   exec(src, ns)  # pylint: disable=exec-used
   ns["smoke"]()
+
+
+def test_lookup_sparse_max_norm_fused_vs_composed():
+  CG.test_lookup_sparse_max_norm_fused_vs_composed(8)

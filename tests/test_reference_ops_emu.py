@@ -278,3 +278,28 @@ def test_embedding_lookup_sparse_with_initializer():
   vals = de.embedding_lookup_sparse(var, sp, None, combiner="sum").numpy()
   assert vals.shape == (n, 8) and len(np.unique(vals[:, 0])) > n // 2
   np.testing.assert_allclose(vals.std(), 0.001, rtol=0.05)
+
+
+def test_embedding_lookup_sparse_max_norm_fused_and_composed_agree():
+  """embedding_lookup_sparse(..., max_norm): the fused kernel (rows of up to 32 vectors) and the composed path (wider
+  rows, trainable lookups) give the same result; max_norm clips every looked-up row before it is weighted"""
+  de = _de()
+  from recommenders_addons_b200.dynamic_embedding import ops
+  rng = np.random.default_rng(4)
+  for dim in (8, 200):
+    var = de.get_variable("mn-%d" % dim, dim=dim, initializer=0.0, devices=["cpu"])
+    keys = torch.arange(50)
+    rows = torch.from_numpy(rng.normal(0, 1.0 / np.sqrt(dim), (50, dim)).astype(np.float32)) * torch.linspace(0.2, 3, 50)[:, None]
+    var.upsert(keys, rows)
+    n = 120
+    ind = torch.stack([torch.sort(torch.from_numpy(rng.integers(0, 30, n))).values, torch.arange(n)], 1)
+    sp = de.SparseIds(ind, torch.from_numpy(rng.integers(0, 60, n)), (30, n))
+    sw = de.SparseIds(ind, torch.from_numpy(rng.uniform(0.5, 2, n).astype(np.float32)), (30, n))
+    assert ops._clip_fusable(dim) == (dim == 8)
+    got = de.embedding_lookup_sparse(var, sp, sw, combiner="mean", max_norm=1.0)
+    composed, _ = de.embedding_lookup_sparse(var, sp, sw, combiner="mean", max_norm=1.0, return_trainable=True)
+    _close(got, composed.detach())
+    clipped = rows * (1.0 / torch.maximum(rows.norm(dim=1, keepdim=True), torch.tensor(1.0)))
+    var2 = de.get_variable("mn-ref-%d" % dim, dim=dim, initializer=0.0, devices=["cpu"])
+    var2.upsert(keys, clipped)
+    _close(got, de.embedding_lookup_sparse(var2, sp, sw, combiner="mean"))

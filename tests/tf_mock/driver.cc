@@ -182,6 +182,7 @@ static void fused_ops() {
   NodeDef nd;
   nd.attr["batch"].i = 3;
   nd.attr["combiner"].s = "mean";
+  nd.attr["max_norm"].f = 0.f;
   OpKernelConstruction lc(nd);
   std::unique_ptr<OpKernel> look(reg.kernels["TFRA>DetLookupSparse"](&lc));
   CHECK_OK(lc.status());
