@@ -17,6 +17,8 @@
 #endif
 #include <stdint.h>
 
+#include "../../include/detable.h"  // DET_EVICT_* (score rules)
+
 namespace det {
 
 constexpr int kBucket = 8;
@@ -769,6 +771,43 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 #endif  // DET_EMU
+
+// ---- scores of a table with an eviction strategy (evict.cu; written by insert_scored_kernel, touch_kernel and the
+// fused optimizer kernels) --------------------------------------------------------------------------------------
+constexpr unsigned long long kM32 = 0xffffffffull;
+struct ScoreRule {
+  int strategy;
+  unsigned long long epoch;
+};
+
+
+__device__ __forceinline__ unsigned long long now_ns() {
+#ifdef DET_EMU
+  return emu::now_ns();
+#else
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
+
+// score of a key after an insert / assign / accumulate (HierarchicalKV v0.1.0-beta.12 rules)
+__device__ __forceinline__ unsigned long long rule_score(const ScoreRule& r, unsigned long long old, bool has,
+                                                         unsigned long long provided, unsigned long long now) {
+  switch (r.strategy) {
+    case DET_EVICT_LRU: return now;
+    case DET_EVICT_LFU: return old + (has ? provided : 1ull);
+    case DET_EVICT_EPOCHLRU: return (r.epoch << 32) | ((now >> 20) & kM32);
+    case DET_EVICT_EPOCHLFU: {
+      const unsigned long long d = has ? (provided > kM32 ? kM32 : provided) : 1ull;
+      unsigned long long f = (old & kM32) + d;
+      if (f > kM32) f = kM32;
+      return (r.epoch << 32) | f;
+    }
+    default: return has ? provided : old;  // CUSTOMIZED
+  }
+}
+
 
 constexpr int kTileKeys = 256;  // keys per CTA tile (= blockDim): 2 KB per stage
 constexpr int kStages = 2;

@@ -404,6 +404,8 @@ det_status det_evict(det_table* t, uint64_t n_evict, int64_t* n_evicted_out_host
 }  // extern "C"
 
 namespace det {
+unsigned long long* evict_scores(const det_table* t) { return t->ev->scores; }
+ScoreRule evict_rule(const det_table* t) { return rule_of(t); }
 void evict_stats(const det_table* t, uint32_t* events, uint64_t* evicted) {
   *events = t->ev ? t->ev->n_events : 0;
   *evicted = t->ev ? t->ev->n_evicted : 0;

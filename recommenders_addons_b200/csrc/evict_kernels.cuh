@@ -11,7 +11,6 @@ namespace det {
 constexpr int kThreadsE = 256;
 constexpr int kHistBits = 11;
 constexpr int kHistBins = 1 << kHistBits;
-constexpr unsigned long long kM32 = 0xffffffffull;
 
 struct EvictDev {
   unsigned long long smin, smax, n_live;        // pass 1
@@ -22,38 +21,7 @@ struct EvictDev {
   unsigned int hist[kHistBins];
 };
 
-struct ScoreRule {
-  int strategy;
-  unsigned long long epoch;
-};
-
-
-__device__ __forceinline__ unsigned long long now_ns() {
-#ifdef DET_EMU
-  return emu::now_ns();
-#else
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-#endif
-}
-
-// score of a key after an insert / assign / accumulate (HierarchicalKV v0.1.0-beta.12 rules)
-__device__ __forceinline__ unsigned long long rule_score(const ScoreRule& r, unsigned long long old, bool has,
-                                                         unsigned long long provided, unsigned long long now) {
-  switch (r.strategy) {
-    case DET_EVICT_LRU: return now;
-    case DET_EVICT_LFU: return old + (has ? provided : 1ull);
-    case DET_EVICT_EPOCHLRU: return (r.epoch << 32) | ((now >> 20) & kM32);
-    case DET_EVICT_EPOCHLFU: {
-      const unsigned long long d = has ? (provided > kM32 ? kM32 : provided) : 1ull;
-      unsigned long long f = (old & kM32) + d;
-      if (f > kM32) f = kM32;
-      return (r.epoch << 32) | f;
-    }
-    default: return has ? provided : old;  // CUSTOMIZED
-  }
-}
+// ScoreRule / rule_score / now_ns live in common.cuh (the fused optimizer kernels of fused.cu write scores too)
 
 __device__ __forceinline__ bool live_key_e(long long k) { return k != kEmptyKey && k != kTombKey; }
 

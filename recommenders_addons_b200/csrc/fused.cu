@@ -521,11 +521,27 @@ apply_kernel(TableView t, const long long* __restrict__ keys, const float* __res
 // vector per lane (vpr <= lpr, dim <= 128).  Same arithmetic, same results.
 constexpr int kStageSteps = 2;  // row-steps per batch
 
-template <int OPT>
+// Tables with an eviction strategy: the step also refreshes the score of every key it touches (HKV scores keys on
+// find_or_insert / assign).  The slot is known right after the probe, so the score write is folded in here instead of
+// a second probe pass (touch_kernel); an EMPTY trailing parameter when unused keeps the unscored kernel unchanged.
+template <bool SCORED> struct ScoreArg {};
+template <> struct ScoreArg<true> {
+  unsigned long long* sc;
+  ScoreRule rule;
+};
+template <bool SCORED>
+__device__ __forceinline__ void score_touch(const ScoreArg<SCORED>&, long long, bool, bool) {}
+template <>
+__device__ __forceinline__ void score_touch<true>(const ScoreArg<true>& sa, long long slot, bool valid, bool is_new) {
+  // a key created by this launch sits in a slot whose score is 0 (free slots always carry score 0)
+  if (valid && slot >= 0) sa.sc[slot] = rule_score(sa.rule, is_new ? 0ull : sa.sc[slot], false, 0ull, now_ns());
+}
+
+template <int OPT, bool SCORED = false>
 __global__ void __launch_bounds__(kThreadsF)
 apply_staged_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ grads, size_t n,
                     OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
-                    unsigned lpr_shift, int use_tma) {
+                    unsigned lpr_shift, int use_tma, ScoreArg<SCORED> sa) {
   constexpr int NS = OPT == 0 ? 3 : 4;  // streams per row: grad, param, slot1 (, slot2)
   DET_DYN_SHARED(dyn_smem);
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
@@ -569,6 +585,7 @@ apply_staged_kernel(TableView t, const long long* __restrict__ keys, const float
       atomicAdd(&s_new, __popc(bn));
       atomicAdd(&s_used, __popc(bu));
     }
+    score_touch<SCORED>(sa, slot, valid, is_new);
     // issue the async loads of one batch of row-steps into `stage`
     auto issue = [&](unsigned b, int stage) {
 #pragma unroll
@@ -907,19 +924,28 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
     const size_t smem = (size_t)(kThreadsF / 32) * 2 * kStageSteps * ns * 32 * 16;
     const int tma = (((uintptr_t)keys & 15u) == 0) ? 1 : 0;
     int occ = 1;
-    if (opt == 0) {
-      CUDA_TRY(cudaFuncSetAttribute(apply_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_staged_kernel<0>, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
-      DET_LAUNCH(apply_staged_kernel<0>, grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s, v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
+    const bool scored = t->ev != nullptr;
+#define DET_LAUNCH_STAGED(OPT_, SCORED_, SA_)                                                                       \
+  {                                                                                                               \
+    const auto kern = apply_staged_kernel<OPT_, SCORED_>;                                                         \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1; \
+    DET_LAUNCH(kern, grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s, v, k, grads, n, h, init_param, \
+               full_init, vpr, lpr, sh, tma, SA_);                                                                \
+  }
+    if (scored) {
+      ScoreArg<true> sa;
+      sa.sc = evict_scores(t);
+      sa.rule = evict_rule(t);
+      if (opt == 0) DET_LAUNCH_STAGED(0, true, sa) else DET_LAUNCH_STAGED(1, true, sa)
     } else {
-      CUDA_TRY(cudaFuncSetAttribute(apply_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_staged_kernel<1>, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
-      DET_LAUNCH(apply_staged_kernel<1>, grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s, v, k, grads, n, h, init_param, full_init, vpr, lpr, sh, tma);
+      const ScoreArg<false> sa;
+      if (opt == 0) DET_LAUNCH_STAGED(0, false, sa) else DET_LAUNCH_STAGED(1, false, sa)
     }
+#undef DET_LAUNCH_STAGED
     CUDA_TRY(cudaGetLastError());
     note_mutation(t, n, s);
-    if (t->ev) return evict_touch(t, k, nullptr, n, s);
-    return DET_OK;
+    return DET_OK;   // scores of a table with an eviction strategy were written by the kernel itself
   }
 #define DET_LAUNCH_APPLY(VF_, OPT_, RU_)                                                                      \
   {                                                                                                           \

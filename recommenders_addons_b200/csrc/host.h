@@ -155,4 +155,6 @@ det_status evict_touch(det_table* t, const long long* keys, const unsigned long 
 det_status evict_insert(det_table* t, const int64_t* keys, const void* values, const uint64_t* scores, size_t n,
                         cudaStream_t s);
 void evict_stats(const det_table* t, uint32_t* events, uint64_t* evicted);
+unsigned long long* evict_scores(const det_table* t);  // score plane [capacity + 2] (t->ev != nullptr)
+ScoreRule evict_rule(const det_table* t);              // strategy + current epoch
 }  // namespace det
