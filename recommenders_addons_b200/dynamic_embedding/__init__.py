@@ -1,7 +1,8 @@
 """Mirror of the reference's `tfra.dynamic_embedding` export list for the hot path
 (/root/reference/tensorflow_recommenders_addons/dynamic_embedding/__init__.py:17-53)."""
-from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreator, HkvEvictStrategy, HkvHashTable,
-                    HkvHashTableConfig, HkvHashTableCreator, KVCreator)
+from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreator, DynamicEmbeddingSaver,
+                    FileSystemSaver, FileSystemSaverConfig, HkvEvictStrategy, HkvHashTable, HkvHashTableConfig,
+                    HkvHashTableCreator, KVCreator)
 from .variable import (ModelMode, TrainableWrapper, Variable, default_partition_fn, embedding_lookup,
                        embedding_lookup_unique, enable_inference_mode, enable_train_mode, get_model_mode, get_variable,
                        trainable_wrapper_filter, unique)
@@ -21,5 +22,5 @@ __all__ = [
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
     "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy", "TrainableWrapper", "ModelMode",
     "enable_inference_mode", "enable_train_mode", "get_model_mode", "trainable_wrapper_filter", "shadow_ops",
-    "ComposedOptimizer", "math", "data_flow",
+    "ComposedOptimizer", "math", "data_flow", "FileSystemSaver", "FileSystemSaverConfig", "DynamicEmbeddingSaver",
 ]

@@ -37,12 +37,61 @@ def _ptr(t):
   return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class DynamicEmbeddingSaver(object):
+  """python/ops/dynamic_embedding_creator.py:365-390: how the tables of a variable are written / restored"""
+  _upsert_restore = True
+
+  def set_upsert_restore(self, setting):
+    self._upsert_restore = setting
+
+
+class FileSystemSaverConfig(object):
+  """python/ops/dynamic_embedding_creator.py:392-412"""
+
+  def __init__(self, proc_size=None, proc_rank=None, save_path=None, buffer_size=4096):
+    if type(proc_rank) != type(proc_size):  # noqa: E721  (the reference's check)
+      raise TypeError("proc_rank and proc_size in FileSystemSaverConfig must both be set to integer properly!")
+    self.proc_size, self.proc_rank = (1, 0) if proc_size is None or proc_rank is None else (proc_size, proc_rank)
+    self.save_path = save_path
+    self.buffer_size = buffer_size
+
+
+class FileSystemSaver(DynamicEmbeddingSaver):
+  """python/ops/dynamic_embedding_creator.py:415-560: independent raw KV files per table shard
+  (`<var>_mht_<i>of<N>_rank<r>_size<s>-keys / -values`) next to the framework's own checkpoint, re-sharded on restore
+  when the shard count or the process count changed.  The TF SaveableObject plumbing around it is out of scope here;
+  `save(variable, dirpath)` / `restore(variable, dirpath)` do what its save / restore ops do."""
+
+  def __init__(self, proc_size=None, proc_rank=None, save_path=None, buffer_size=4096):
+    self.config = FileSystemSaverConfig(proc_size=proc_size, proc_rank=proc_rank, save_path=save_path,
+                                        buffer_size=buffer_size)
+
+  def _dir(self, dirpath):
+    d = self.config.save_path if self.config.save_path else dirpath
+    if not d:
+      raise ValueError("FileSystemSaver needs a save_path (or a dirpath argument)")
+    return d
+
+  def save(self, variable, dirpath=None):
+    variable.save_to_file_system(self._dir(dirpath), proc_size=self.config.proc_size, proc_rank=self.config.proc_rank,
+                                 dirpath_env="__unset__", buffer_size=self.config.buffer_size)
+
+  def restore(self, variable, dirpath=None):
+    """clear + load every file of the directory that belongs to this process under the CURRENT topology"""
+    variable.load_from_file_system_with_restore_function(self._dir(dirpath), proc_size=self.config.proc_size,
+                                                         proc_rank=self.config.proc_rank,
+                                                         buffer_size=self.config.buffer_size)
+
+
 class KVCreator(object):
   """python/ops/dynamic_embedding_creator.py:34-78"""
 
   def __init__(self, config=None, saver=None):
     self.config = config
     self.saver = saver
+    if saver and not isinstance(saver, DynamicEmbeddingSaver):
+      raise RuntimeError("The initialization argument 'saver' for class KVCreator must be a class inheriting "
+                         "DynamicEmbeddingSaver.")
 
   def create(self, key_dtype=None, value_dtype=None, default_value=None, name=None, checkpoint=None,
              init_size=None, config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):

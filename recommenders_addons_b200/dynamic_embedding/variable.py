@@ -306,13 +306,17 @@ class Variable(object):
       raise TypeError("reshard-on-load is not implemented for %s rows" % (self.value_dtype,))
     dev = self._tables[0].device
     for kf in files:
-      keys = np.fromfile(kf, dtype=np.int64)
-      vals = np.fromfile(kf[:-len("-keys")] + "-values", dtype=np_dtype).reshape(-1, self.dim)
-      if keys.shape[0] != vals.shape[0]:
+      if os.path.getsize(kf) == 0:
+        continue
+      # memory-mapped: host memory use is bounded by buffer_size keys, whatever the size of the shard file
+      keys = np.memmap(kf, dtype=np.int64, mode="r")
+      vals = np.memmap(kf[:-len("-keys")] + "-values", dtype=np_dtype, mode="r")
+      if vals.shape[0] != keys.shape[0] * self.dim:
         raise IOError("%s: keys and values files disagree" % kf)
+      vals = vals.reshape(-1, self.dim)
       for b in range(0, keys.shape[0], int(buffer_size)):
-        k = torch.from_numpy(keys[b:b + int(buffer_size)]).to(dev)
-        v = torch.from_numpy(vals[b:b + int(buffer_size)]).to(dev)
+        k = torch.from_numpy(np.array(keys[b:b + int(buffer_size)])).to(dev)
+        v = torch.from_numpy(np.array(vals[b:b + int(buffer_size)])).to(dev)
         if proc_size > 1:
           mine = self.partition_fn(k, proc_size) == proc_rank
           k, v = k[mine], v[mine]

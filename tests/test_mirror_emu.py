@@ -180,3 +180,35 @@ def test_smoke_body_on_the_emulated_library():
 
 def test_lookup_sparse_max_norm_fused_vs_composed():
   CG.test_lookup_sparse_max_norm_fused_vs_composed(8)
+
+
+def test_file_system_saver_reshards_on_restore(tmp_path):
+  """de.FileSystemSaver (python/ops/dynamic_embedding_creator.py:415-560): 3 shards saved by one process, restored into
+  2 shards of each of 2 processes -- every key lands on the process / shard the partitioner assigns it to"""
+  import numpy as np
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  rng = np.random.default_rng(0)
+  keys = torch.from_numpy(rng.choice(1 << 40, 5000, replace=False).astype(np.int64))
+  vals = torch.from_numpy(rng.normal(size=(5000, 4)).astype(np.float32))
+  src = de.get_variable("emb/saver_var", dim=4, devices=["cpu"] * 3, kv_creator=de.CuckooHashTableCreator(
+      saver=de.FileSystemSaver()))
+  src.upsert(keys, vals)
+  de.FileSystemSaver(save_path=str(tmp_path), buffer_size=700).save(src)
+  assert len(os.listdir(tmp_path)) == 6
+  total = 0
+  for rank in range(2):
+    from recommenders_addons_b200.dynamic_embedding import variable as V
+    V._VARIABLES.pop("emb/saver_var", None)
+    dst = de.get_variable("emb/saver_var", dim=4, devices=["cpu"] * 2)
+    de.FileSystemSaver(proc_size=2, proc_rank=rank, save_path=str(tmp_path), buffer_size=512).restore(dst)
+    mine = de.default_partition_fn(keys, 2) == rank
+    assert int(dst.size()) == int(mine.sum())
+    got, ex = dst.lookup(keys[mine], return_exists=True)
+    assert bool(ex.all()) and torch.equal(got, vals[mine])
+    total += int(dst.size())
+  assert total == 5000
+  with pytest.raises(TypeError):
+    de.FileSystemSaverConfig(proc_size=2)
+  with pytest.raises(RuntimeError):
+    de.CuckooHashTableCreator(saver=object())
