@@ -207,7 +207,8 @@ def test_standard_path_growth_find_accum_remove_export():
 def test_max_capacity_without_strategy_still_reports_table_full():
   t = Table(dim=4, init=256, max_capacity=256)
   ks = np.arange(1000, dtype=np.int64)
-  st = L().det_insert(t.h, P(ks), P(np.zeros((1000, 4), dtype=np.float32)), 1000, None)
+  zeros = np.zeros((1000, 4), dtype=np.float32)   # kept alive: P() holds no reference to the array it points into
+  st = L().det_insert(t.h, P(ks), P(zeros), 1000, None)
   assert st == 4 and b"max_capacity" in L().det_last_error()       # DET_TABLE_FULL
   t.close()
 
@@ -470,7 +471,8 @@ def test_tma_tile_schedule_and_its_unaligned_fallback():
     ck(L().det_insert(t.h, P(keys), P(vals), n, None))
     out = np.empty((n, 4), dtype=np.float32)
     ex = np.empty(n, dtype=np.uint8)
-    ck(L().det_find(t.h, P(keys), n, P(np.zeros(4, dtype=np.float32)), 0, P(out), P(ex), None))
+    dflt = np.zeros(4, dtype=np.float32)
+    ck(L().det_find(t.h, P(keys), n, P(dflt), 0, P(out), P(ex), None))
     assert ex.all()
     np.testing.assert_array_equal(out, vals)
   t.check()

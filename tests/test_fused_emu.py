@@ -143,7 +143,8 @@ def test_lookup_sparse_max_norm_wide_rows_are_refused():
   t = Table(dim=200, init=256)
   ids, seg = np.arange(4, dtype=np.int64), np.arange(4, dtype=np.int32)
   out = np.empty((4, 200), dtype=np.float32)
-  st = F().det_lookup_sparse_clip(t.h, P(ids), P(seg), None, 4, 4, 0, P(np.zeros(200, np.float32)), 1.0, P(out), None)
+  dflt = np.zeros(200, np.float32)
+  st = F().det_lookup_sparse_clip(t.h, P(ids), P(seg), None, 4, 4, 0, P(dflt), 1.0, P(out), None)
   assert st == 5 and b"composed" in L().det_last_error()          # DET_UNIMPLEMENTED: the Python mirror composes
   t.close()
 

@@ -279,7 +279,8 @@ def test_bounded_table_reserve_clear_import_and_load(tmp_path):
   t.insert(keys, np.ones((100, dim), dtype=np.float32))
   assert (t.scores_of(keys) == 1).all()
   k2 = np.arange(1000, 1040, dtype=np.int64)
-  ck(L().det_import(t.h, P(k2), P(np.full((40, dim), 3, dtype=np.float32)), 40, None))
+  v2 = np.full((40, dim), 3, dtype=np.float32)     # (kept alive: P() holds no reference to the array it points into)
+  ck(L().det_import(t.h, P(k2), P(v2), 40, None))
   assert t.size() == 40 and (t.scores_of(k2) == 1).all() and (t.scores_of(keys) == 0).all()
   # more keys than the table may hold, from host buffers / from files: the bound holds, the newest rows are right
   big = rng.choice(1 << 40, size=9000, replace=False).astype(np.int64)
