@@ -20,8 +20,11 @@ struct cudaDeviceProp {
   char name[64] = "simt-emulator";
 };
 
+// cudaMalloc memory is NOT zeroed on a GPU: poison it here, so that code relying on zero-initialised device memory
+// fails in the emulator instead of working by the luck of fresh zero pages
 static inline cudaError_t cudaMalloc(void** p, size_t n) {
   *p = malloc(n ? n : 1);
+  if (*p) memset(*p, 0xCB, n ? n : 1);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 static inline cudaError_t cudaFree(void* p) {
