@@ -11,4 +11,4 @@ export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=lib
 export ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1
 export UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1
 python -m pytest tests/test_detable_emu.py tests/test_fused_emu.py tests/test_host_peer_emu.py tests/test_mirror_emu.py \
-  tests/test_reference_ops_emu.py tests/test_reference_variable_emu.py -x -q -p no:cacheprovider "$@"
+  tests/test_reference_ops_emu.py tests/test_reference_variable_emu.py tests/test_reference_hkv_emu.py -x -q -p no:cacheprovider "$@"
