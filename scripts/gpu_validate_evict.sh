@@ -34,3 +34,5 @@ echo "claim A/B:"; cat gpurun_out/claim_serial.jsonl gpurun_out/claim_batched.js
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k "regex:[iI]ndex|gather" --csv \
   --log-file gpurun_out/granularity.csv python scripts/probe_granularity.py > gpurun_out/granularity.json 2> gpurun_out/granularity.err
 echo "granularity probe exit: $?"; grep -ci "index\|gather" gpurun_out/granularity.csv
+L2_FETCH=32 timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k "regex:[iI]ndex|gather" --csv \
+  --log-file gpurun_out/granularity_l2fetch32.csv python scripts/probe_granularity.py > gpurun_out/granularity_l2fetch32.json 2>> gpurun_out/granularity.err

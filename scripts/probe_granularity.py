@@ -14,7 +14,33 @@ N = 1 << 22
 ROWS = 1 << 26  # 64M rows: 2..16 GB tables, far beyond L2
 
 
+def set_l2_fetch(nbytes):
+  """cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity = 0x05, nbytes) on the primary context (what DET_L2_FETCH does
+  at table creation); L2_FETCH=32|64|128 in the environment selects it, unset = device default"""
+  import ctypes
+  import glob
+  import os
+  cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")) + \
+      ["libcudart.so.12", "libcudart.so"]
+  for c in cands:
+    try:
+      rt = ctypes.CDLL(c)
+      break
+    except OSError:
+      continue
+  else:
+    raise RuntimeError("libcudart not found")
+  torch.zeros(1, device="cuda")  # create the primary context
+  rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(nbytes))
+  got = ctypes.c_size_t(0)
+  rt.cudaDeviceGetLimit(ctypes.byref(got), 5)
+  return rc, got.value
+
+
 def main():
+  import os
+  if os.environ.get("L2_FETCH"):
+    print(json.dumps({"l2_fetch_request": int(os.environ["L2_FETCH"]), "rc_and_value": set_l2_fetch(int(os.environ["L2_FETCH"]))}))
   dev = torch.device("cuda", 0)
   g = torch.Generator(device=dev).manual_seed(0)
   order = []
