@@ -9,7 +9,7 @@ echo "bench ref exit $?"; cut -c 1-400 gpurun_out/bench_final_ref.json
 timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 echo "bench exit $?"; cat gpurun_out/bench_final.json; tail -n 3 gpurun_out/bench_final.err
 # launch list of the SAME bench command (profiles/rNN_launches_bench_n1.csv): per-launch times under ncu are cold-cache
-# and serialised, so only each kernel's SHARE of the step is compared with the live CUDA-event split (find_ms / insert_ms)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_n1.csv \
+# and serialised (only the table kernels are listed: the prefill's inserts come first, the LAST rows are the timed steps), so only each kernel's SHARE of the step is compared with the live CUDA-event split (find_ms / insert_ms)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:find_kernel|insert_kernel" -c 600 --csv --log-file gpurun_out/launches_bench_n1.csv \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 echo "ncu launch list exit $?"; grep -c "kernel" gpurun_out/launches_bench_n1.csv
