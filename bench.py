@@ -54,6 +54,9 @@ def parse_args():
                   help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
   ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
                   help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2])")
+  ap.add_argument("--grad-reduce", default="det", choices=["det", "torch"],
+                  help="c3 / c5: per-unique gradient sum by det_segment_reduce (position order, deterministic) or by "
+                       "torch index_add (atomics); sets DET_GRAD_REDUCE for the sharded combine as well")
   ap.add_argument("--distinct-batches", type=int, default=64, help="distinct key batches cycled through")
   return ap.parse_args()
 
@@ -585,7 +588,10 @@ def c3_arm(args):
     ids = batches[i % nb]
     out = lookup_sparse_fused(var, ids, seg, None, nnz, "sum")
     uniq, idx = de.unique(ids)
-    g = torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
+    if args.grad_reduce == "det":
+      g = de.segment_reduce(gout, idx, uniq.numel())
+    else:
+      g = torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
     opt.iterations += 1
     opt.apply_sparse(var, uniq, g)
     return out
@@ -604,7 +610,7 @@ def c3_arm(args):
                     "value": nnz / ms / 1e3, "unit": "M ids/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
                     "config": {"workload": "26 features x batch 65536, dim %d, %d resident rows, Zipf(1.05) per feature; "
-                                           "includes tf.unique + torch index_add for the per-unique gradient sum" % (dim, total),
+                                           "includes tf.unique + the per-unique gradient sum (%s)" % (dim, total, "det_segment_reduce, position order" if args.grad_reduce == "det" else "torch index_add"),
                                "nnz": nnz, "unique_per_step": int(de.unique(batches[0])[0].numel())}}))
 
 
@@ -621,6 +627,7 @@ def c5_arm(args):
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+  os.environ["DET_GRAD_REDUCE"] = args.grad_reduce   # the owner-side combine of PeerShardedVariable.apply_gradients
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   dist.init_process_group("nccl", device_id=dev)
@@ -654,7 +661,10 @@ def c5_arm(args):
     emb = rows[idx.long()]                          # [ids, dim] activations handed to the dense tower
     dist.all_reduce(dense)                          # half-sync: only the dense tower is all-reduced
     gout = emb * 1e-3                               # stand-in for the tower's gradient w.r.t. the activations
-    g = torch.zeros_like(rows).index_add_(0, idx.long(), gout)
+    if args.grad_reduce == "det":
+      g = de.segment_reduce(gout, idx, uniq.numel())
+    else:
+      g = torch.zeros_like(rows).index_add_(0, idx.long(), gout)
     sv.apply_gradients(opt, uniq, g)                # backward: route -> combine -> fused Adagrad on the owner
 
   for i in range(args.warmup):
@@ -678,7 +688,7 @@ def c5_arm(args):
                       "config": {"workload": "26 features x global batch %d, dim %d, %d resident rows/GPU (2B-row key space), "
                                              "Zipf(1.05); unique -> det_peer_find -> 50 MB dense all-reduce -> det_peer_route -> "
                                              "combine -> det_apply_adagrad" % (gbatch, dim, resident),
-                                 "ids_per_rank": ids_per_rank, "unique_per_rank": int(de.unique(batches[0])[0].numel())}}))
+                                 "grad_reduce": args.grad_reduce, "ids_per_rank": ids_per_rank, "unique_per_rank": int(de.unique(batches[0])[0].numel())}}))
   dist.destroy_process_group()
 
 

@@ -191,6 +191,18 @@ det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t
                       int64_t* n_unique_dev, void* workspace, size_t workspace_bytes,
                       det_stream_t stream);
 
+/* Gradient dedupe of the sparse optimizer path: out[g, :] = sum of rows[i, :] over the positions i with idx[i] == g,
+ * added in INCREASING POSITION (the order of TF's CPU unsorted_segment_sum, which _deduplicate_indexed_slices applies
+ * before _resource_apply_sparse_duplicate_indices, python/ops/dynamic_embedding_optimizer.py:150,184; the gradient of
+ * dynamic_stitch / sparse_segment_sum, python/ops/data_flow_grad.py:65, python/ops/math_grad.py:30) -- deterministic and
+ * bit-identical to np.add.at, where atomics would make the fp32 sum depend on the schedule.  idx is what det_unique
+ * returns; indices outside [0, n_groups) are dropped; groups without rows come out as zeros.  rows fp32 [n, dim],
+ * out fp32 [n_groups, dim] (every row is written).  workspace: det_segment_reduce_workspace_bytes(n, n_groups) bytes
+ * of device scratch.  Asynchronous on `stream`, no host synchronisation.  ABI >= 4. */
+size_t det_segment_reduce_workspace_bytes(size_t n, size_t n_groups);
+det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim,
+                              float* out, void* workspace, size_t workspace_bytes, det_stream_t stream);
+
 /* embedding_lookup_sparse forward, fused (python/ops/dynamic_embedding_ops.py:219-291): a slot-resolve pass
  * (8 B per id) + ONE gather/weight/segment-sum/normalise pass -- the reference's [nnz, dim] gather, its weighted
  * copy and the segment_sum input are never materialised:

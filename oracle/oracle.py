@@ -234,6 +234,19 @@ def unique_first_occurrence(ids):
   return uniq[order], rank[inv].astype(np.int32)
 
 
+def segment_reduce(rows, idx, n_groups):
+  """Gradient dedupe: TF's _deduplicate_indexed_slices = unsorted_segment_sum(values, idx, n_unique) before
+  _resource_apply_sparse_duplicate_indices (dynamic_embedding_optimizer.py:150,184; also the gradient of
+  dynamic_stitch / sparse_segment_sum, data_flow_grad.py:65, math_grad.py:30).  The CPU kernel adds the rows of one
+  output row in increasing position, one fp32 add at a time; negative / out-of-range ids are dropped."""
+  rows = np.asarray(rows, dtype=np.float32)
+  idx = np.asarray(idx).reshape(-1).astype(np.int64)
+  out = np.zeros((n_groups, rows.shape[1]), dtype=np.float32)
+  keep = (idx >= 0) & (idx < n_groups)
+  np.add.at(out, idx[keep], rows[keep])   # unbuffered, in position order
+  return out
+
+
 def variable_accum_values(old_values, new_values, exists):
   """Variable.accum: values_or_deltas = where(exists, new - old, new) (dynamic_embedding_variable.py:826-833)."""
   old_values = np.asarray(old_values, dtype=np.float32)

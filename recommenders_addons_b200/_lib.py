@@ -10,7 +10,7 @@ _sz = ctypes.c_size_t
 _i = ctypes.c_int
 
 DET_OK = 0
-ABI_VERSION = 3  # det_abi_version() of the library these mirrors describe (checked at load)
+ABI_VERSION = 4  # det_abi_version() of the library these mirrors describe (checked at load)
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 # HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
@@ -55,6 +55,8 @@ SIGNATURES = {
     "det_import": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_unique_workspace_bytes": (_sz, [_sz]),
     "det_unique": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "det_segment_reduce_workspace_bytes": (_sz, [_sz, _sz]),
+    "det_segment_reduce": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp]),
     "det_lookup_sparse": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
     "det_lookup_sparse_clip": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp, ctypes.c_float, _vp, _vp]),
     "det_apply_adagrad": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, _vp, _i, ctypes.c_float, _vp]),

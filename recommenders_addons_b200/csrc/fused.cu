@@ -785,6 +785,305 @@ static void fgeom(unsigned dim, bool vec4, unsigned min_lpr, unsigned* vpr, unsi
   *sh = s;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K9: det_segment_reduce -- out[g] = sum of the rows whose index is g, added IN POSITION ORDER
+// ------------------------------------------------------------------------------------------------
+// The gradient dedupe of the sparse optimizer path: TF's _deduplicate_indexed_slices = unique +
+// unsorted_segment_sum(values, idx, n_unique) (python/ops/dynamic_embedding_optimizer.py:150,184 ->
+// _resource_apply_sparse_duplicate_indices; python/ops/data_flow_grad.py:65; python/ops/math_grad.py:30), whose CPU
+// kernel adds the rows of one output row in increasing position -- the order the oracle restates (np.add.at).
+// Atomics would make the fp32 sum depend on the schedule, so the rows are GROUPED first:
+//   1. stable LSD radix sort of the positions by index, 8 bits per pass over the bits of n_groups only
+//      (per pass: radix_hist -> radix_binscan -> radix_scatter; ranks inside a tile come from __match_any_sync,
+//      so equal indices keep their position order),
+//   2. group_starts: first sorted position of every group;  group_long: the groups longer than kLongGroup,
+//   3. segment_reduce_kernel: CTAs [0, n_long_ctas) take the long groups (Zipf head: thousands of rows of one key;
+//      the whole CTA stages a tile of rows in shared memory with every load in flight, then thread c adds column c
+//      in order), all other CTAs give each lane-group two short groups at a time, 4 row loads in flight per group.
+// Indices outside [0, n_groups) are dropped like unsorted_segment_sum drops negative ids.
+constexpr int kRadixBits = 8;
+constexpr int kRadixBins = 1 << kRadixBits;
+constexpr int kRadixThreads = 256;                 // == kRadixBins: thread t owns bin t
+constexpr int kRadixItems = 8;                     // items per thread
+constexpr int kRadixTile = kRadixThreads * kRadixItems;
+constexpr int kLongGroup = 64;                     // groups with more rows go to the CTA-cooperative path
+constexpr int kLongTileFloats = 8192;              // 32 KB of staged rows per CTA
+constexpr int kLongTileRows = 256;                 // staged positions per tile (<= kLongTileFloats / columns)
+constexpr int kLongCols = 1024;                    // columns staged at a time (rows wider than this: several sweeps)
+
+// key of position i in pass 0: the index itself, or n_groups ("dropped") when it lies outside [0, n_groups)
+__device__ __forceinline__ unsigned radix_key0(const int* __restrict__ idx, size_t i, unsigned n_groups) {
+  const unsigned k = (unsigned)idx[i];
+  return k < n_groups ? k : n_groups;
+}
+
+// hist[bin * nblocks + block] = items of this block's tile whose digit is `bin`
+__global__ void __launch_bounds__(kRadixThreads)
+radix_hist_kernel(const int* __restrict__ idx, const unsigned* __restrict__ keys_in, size_t n, unsigned n_groups,
+                  int shift, unsigned* __restrict__ hist, size_t nblocks) {
+  __shared__ unsigned s_h[kRadixBins];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t tile0 = (size_t)blockIdx.x * kRadixTile;
+#pragma unroll
+  for (int it = 0; it < kRadixItems; ++it) {
+    const size_t i = tile0 + (size_t)it * kRadixThreads + threadIdx.x;
+    if (i < n) {
+      const unsigned k = keys_in ? keys_in[i] : radix_key0(idx, i, n_groups);
+      atomicAdd(&s_h[(k >> shift) & (kRadixBins - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// one warp per bin: exclusive scan of the bin's per-block counts in place, bin total -> totals[bin]
+__global__ void __launch_bounds__(kRadixThreads)
+radix_binscan_kernel(unsigned* __restrict__ hist, size_t nblocks, unsigned* __restrict__ totals) {
+  const int lane = threadIdx.x & 31;
+  const unsigned bin = (unsigned)((blockIdx.x * kRadixThreads + threadIdx.x) >> 5);
+  if (bin >= (unsigned)kRadixBins) return;   // whole warps only (kRadixThreads is a multiple of 32)
+  unsigned* h = hist + (size_t)bin * nblocks;
+  unsigned carry = 0;
+  for (size_t base = 0; base < nblocks; base += 32) {
+    const size_t j = base + lane;
+    const unsigned v = j < nblocks ? h[j] : 0u;
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o) x += y;
+    }
+    if (j < nblocks) h[j] = carry + x - v;
+    carry += __shfl_sync(kFull, x, 31);
+  }
+  if (lane == 0) totals[bin] = carry;
+}
+
+// stable scatter of one tile: destination = start of the bin + start of this block inside the bin + items of the
+// same digit that precede the item inside the block
+__global__ void __launch_bounds__(kRadixThreads)
+radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ keys_in,
+                     const unsigned* __restrict__ pos_in, size_t n, unsigned n_groups, int shift,
+                     const unsigned* __restrict__ hist, size_t nblocks, const unsigned* __restrict__ totals,
+                     unsigned* __restrict__ keys_out, unsigned* __restrict__ pos_out) {
+  constexpr int kWarps = kRadixThreads / 32;
+  __shared__ unsigned s_cnt[kWarps][kRadixBins];   // per warp: items of each digit (then: exclusive over warps)
+  __shared__ unsigned s_base[kRadixBins];          // global start of the (bin, block) run
+  __shared__ unsigned s_wsum[kWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = threadIdx.x; q < kWarps * kRadixBins; q += kRadixThreads) (&s_cnt[0][0])[q] = 0;
+  // exclusive scan of the bin totals over the 256 bins (thread t = bin t)
+  const unsigned tot = totals[threadIdx.x];
+  unsigned x = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(kFull, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_wsum[w] = x;
+  __syncthreads();
+  unsigned before = 0;
+  for (int ww = 0; ww < w; ++ww) before += s_wsum[ww];
+  s_base[threadIdx.x] = before + x - tot + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  // pass A: the warp walks its 256 consecutive items 32 at a time; rank inside the warp's sub-tile
+  const size_t sub0 = (size_t)blockIdx.x * kRadixTile + (size_t)w * (kRadixTile / kWarps);
+  unsigned key[kRadixItems], rank[kRadixItems];
+#pragma unroll
+  for (int it = 0; it < kRadixItems; ++it) {
+    const size_t i = sub0 + (size_t)it * 32 + lane;
+    const bool valid = i < n;
+    key[it] = valid ? (keys_in ? keys_in[i] : radix_key0(idx, i, n_groups)) : 0u;
+    const int d = valid ? (int)((key[it] >> shift) & (kRadixBins - 1)) : -1;
+    const unsigned peers = __match_any_sync(kFull, d);
+    const unsigned old = valid ? s_cnt[w][d] : 0u;
+    rank[it] = old + (unsigned)__popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+    if (valid && (peers & ((1u << lane) - 1u)) == 0) s_cnt[w][d] = old + (unsigned)__popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // exclusive prefix over the warps, per digit (thread t = digit t)
+    unsigned run = 0;
+#pragma unroll
+    for (int ww = 0; ww < kWarps; ++ww) {
+      const unsigned c = s_cnt[ww][threadIdx.x];
+      s_cnt[ww][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kRadixItems; ++it) {
+    const size_t i = sub0 + (size_t)it * 32 + lane;
+    if (i < n) {
+      const unsigned d = (key[it] >> shift) & (kRadixBins - 1);
+      const size_t dest = (size_t)s_base[d] + s_cnt[w][d] + rank[it];
+      keys_out[dest] = key[it];
+      pos_out[dest] = pos_in ? pos_in[i] : (unsigned)i;
+    }
+  }
+}
+
+// starts[g] = first sorted position whose key is >= g (g = 0..n_groups); keys are sorted, "dropped" rows carry n_groups
+__global__ void group_starts_kernel(const unsigned* __restrict__ keys, size_t n, unsigned n_groups,
+                                    unsigned* __restrict__ starts) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n) return;
+  const long long cur = j < n ? (long long)keys[j] : (long long)n_groups;
+  const long long prev = j > 0 ? (long long)keys[j - 1] : -1;
+  for (long long g = prev + 1; g <= cur; ++g) starts[g] = (unsigned)j;
+}
+
+__global__ void group_long_kernel(const unsigned* __restrict__ starts, unsigned n_groups, unsigned* __restrict__ long_list,
+                                  unsigned* __restrict__ n_long) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  if (starts[g + 1] - starts[g] > (unsigned)kLongGroup) long_list[atomicAdd(n_long, 1u)] = (unsigned)g;
+}
+
+template <int VF>
+__global__ void __launch_bounds__(kThreadsF)
+segment_reduce_kernel(const float* __restrict__ rows, const unsigned* __restrict__ pos,
+                      const unsigned* __restrict__ starts, unsigned n_groups, unsigned dim, unsigned vpr, unsigned lpr,
+                      unsigned lpr_shift, const unsigned* __restrict__ long_list, const unsigned* __restrict__ n_long_p,
+                      int n_long_ctas, float* __restrict__ out) {
+  if ((int)blockIdx.x < n_long_ctas) {
+    // ---- long groups: one CTA per group, rows staged tile by tile, thread c adds column c in position order ----
+    __shared__ __align__(16) float s_rows[kLongTileFloats];
+    __shared__ unsigned s_pos[kLongTileRows];
+    const unsigned n_long = *n_long_p;
+    for (unsigned q = blockIdx.x; q < n_long; q += (unsigned)n_long_ctas) {
+      const unsigned g = long_list[q];
+      const unsigned st = starts[g], en = starts[g + 1];
+      for (unsigned c0 = 0; c0 < dim; c0 += kLongCols) {
+        const unsigned wcols = dim - c0 < (unsigned)kLongCols ? dim - c0 : (unsigned)kLongCols;  // multiple of VF
+        unsigned rpt = (unsigned)kLongTileFloats / wcols;
+        if (rpt > (unsigned)kLongTileRows) rpt = kLongTileRows;
+        const unsigned wv = wcols / VF;                                   // vectors per staged row
+        float acc[kLongCols / kThreadsF];
+#pragma unroll
+        for (int a = 0; a < kLongCols / kThreadsF; ++a) acc[a] = 0.f;
+        for (unsigned base = st; base < en; base += rpt) {
+          const unsigned m = en - base < rpt ? en - base : rpt;
+          for (unsigned r = threadIdx.x; r < m; r += kThreadsF) s_pos[r] = pos[base + r];
+          __syncthreads();
+          const unsigned total = m * wv;
+#pragma unroll 4
+          for (unsigned f = threadIdx.x; f < total; f += kThreadsF) {
+            const unsigned r = f / wv, cv = f - r * wv;
+            FVec<VF> x;
+            x.load(rows + (size_t)s_pos[r] * dim + c0 + (size_t)cv * VF);
+            x.store(s_rows + (size_t)r * wcols + (size_t)cv * VF);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int a = 0; a < kLongCols / kThreadsF; ++a) {
+            const unsigned c = threadIdx.x + (unsigned)a * kThreadsF;
+            if (c < wcols) {
+              float s = acc[a];
+              for (unsigned r = 0; r < m; ++r) s = s + s_rows[(size_t)r * wcols + c];
+              acc[a] = s;
+            }
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int a = 0; a < kLongCols / kThreadsF; ++a) {
+          const unsigned c = threadIdx.x + (unsigned)a * kThreadsF;
+          if (c < wcols) out[(size_t)g * dim + c0 + c] = acc[a];
+        }
+      }
+    }
+    return;
+  }
+  // ---- short groups: a lane-group walks U groups in lock step, K rows of each in flight ----
+  constexpr int U = 2, K = 4;
+  const int lane = threadIdx.x & 31;
+  const unsigned gl = (unsigned)lane & (lpr - 1u);
+  const unsigned gpw = 32u >> lpr_shift;
+  const unsigned gidx = (unsigned)lane >> lpr_shift;
+  const size_t warp0 = (((size_t)blockIdx.x - (size_t)n_long_ctas) * kThreadsF + threadIdx.x) >> 5;
+  const size_t nwarps = (((size_t)gridDim.x - (size_t)n_long_ctas) * kThreadsF) >> 5;
+  const unsigned nchunk = (vpr + lpr - 1u) / lpr;   // 1 unless the row is wider than 32 vectors
+  for (size_t sb = warp0 * gpw * U; sb < n_groups; sb += nwarps * gpw * U) {
+    const size_t g0 = sb + (size_t)gidx * U;
+    unsigned st[U], en[U];
+    bool mine[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = g0 + u < n_groups;
+      const unsigned a = ok ? starts[g0 + u] : 0u, b = ok ? starts[g0 + u + 1] : 0u;
+      mine[u] = ok && b - a <= (unsigned)kLongGroup;
+      st[u] = mine[u] ? a : 0u;
+      en[u] = mine[u] ? b : 0u;
+    }
+    for (unsigned cc = 0; cc < nchunk; ++cc) {
+      const unsigned cv = cc * lpr + gl;
+      const bool lane_on = cv < vpr;
+      FVec<VF> acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u].zero();
+      for (unsigned k = 0;; k += K) {
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) any |= st[u] + k < en[u];
+        if (!__any_sync(kFull, any)) break;
+        unsigned p[U][K];
+        FVec<VF> x[U][K];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int q = 0; q < K; ++q) p[u][q] = st[u] + k + q < en[u] ? __ldg(pos + st[u] + k + q) : 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int q = 0; q < K; ++q) {
+            x[u][q].zero();
+            if (p[u][q] != 0xffffffffu && lane_on) x[u][q].load(rows + (size_t)p[u][q] * dim + (size_t)cv * VF);
+          }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int q = 0; q < K; ++q)
+            if (p[u][q] != 0xffffffffu) acc[u].zip(x[u][q], [](float& a, float xv) { a = a + xv; });
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (mine[u] && lane_on) acc[u].store(out + (g0 + u) * dim + (size_t)cv * VF);
+    }
+  }
+}
+
+struct SegReduceWs {
+  unsigned *keys_a, *keys_b, *pos_a, *pos_b, *hist, *totals, *starts, *long_list, *n_long;
+};
+
+static size_t seg_reduce_layout(size_t n, size_t n_groups, unsigned char* base, SegReduceWs* w) {
+  const size_t nblocks = (n + kRadixTile - 1) / kRadixTile;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return (unsigned*)p;
+  };
+  unsigned* ka = take(n * 4);
+  unsigned* kb = take(n * 4);
+  unsigned* pa = take(n * 4);
+  unsigned* pb = take(n * 4);
+  unsigned* hist = take((size_t)kRadixBins * nblocks * 4);
+  unsigned* totals = take(kRadixBins * 4);
+  unsigned* starts = take((n_groups + 2) * 4);
+  unsigned* ll = take((n / kLongGroup + 2) * 4);
+  unsigned* nl = take(16);
+  if (w) {
+    w->keys_a = ka; w->keys_b = kb; w->pos_a = pa; w->pos_b = pb; w->hist = hist; w->totals = totals;
+    w->starts = starts; w->long_list = ll; w->n_long = nl;
+  }
+  return off;
+}
+
 }  // namespace det
 
 using namespace det;
@@ -1052,5 +1351,67 @@ det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, s
                            det_stream_t stream) {
   return permute_rows(rows_in, perm, n, row_bytes, rows_out, false, (cudaStream_t)stream);
 }
+
+size_t det_segment_reduce_workspace_bytes(size_t n, size_t n_groups) {
+  return seg_reduce_layout(n ? n : 1, n_groups ? n_groups : 1, nullptr, nullptr);
+}
+
+det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim, float* out,
+                              void* workspace, size_t workspace_bytes, det_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_groups == 0 || dim == 0) return DET_OK;
+  if (!out) return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: null out");
+  if (n >= 0x7fffffffull || n_groups >= 0x7fffffffull || dim >= 0x7fffffffull)
+    return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: n / n_groups / dim too large");
+  if (n == 0) {
+    CUDA_TRY(cudaMemsetAsync(out, 0, n_groups * dim * sizeof(float), s));
+    return DET_OK;
+  }
+  if (!rows || !idx || !workspace) return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: null argument");
+  if (workspace_bytes < det_segment_reduce_workspace_bytes(n, n_groups))
+    return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: workspace too small");
+  SegReduceWs w;
+  seg_reduce_layout(n, n_groups, (unsigned char*)workspace, &w);
+  const size_t nblocks = (n + kRadixTile - 1) / kRadixTile;
+  const unsigned ng = (unsigned)n_groups;
+  int bits = 0;
+  for (size_t v = n_groups; v; v >>= 1) ++bits;   // keys are 0..n_groups (n_groups = "dropped")
+  const int passes = (bits + kRadixBits - 1) / kRadixBits;
+  const unsigned *kin = nullptr, *pin = nullptr;
+  unsigned *kout = w.keys_a, *pout = w.pos_a;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * kRadixBits;
+    DET_LAUNCH(radix_hist_kernel, (int)nblocks, kRadixThreads, 0, s, idx, kin, n, ng, shift, w.hist, nblocks);
+    DET_LAUNCH(radix_binscan_kernel, kRadixBins * 32 / kRadixThreads, kRadixThreads, 0, s, w.hist, nblocks, w.totals);
+    DET_LAUNCH(radix_scatter_kernel, (int)nblocks, kRadixThreads, 0, s, idx, kin, pin, n, ng, shift, w.hist, nblocks, w.totals,
+               kout, pout);
+    kin = kout;
+    pin = pout;
+    kout = (kout == w.keys_a) ? w.keys_b : w.keys_a;
+    pout = (pout == w.pos_a) ? w.pos_b : w.pos_a;
+  }
+  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts);
+  CUDA_TRY(cudaMemsetAsync(w.n_long, 0, sizeof(unsigned), s));
+  DET_LAUNCH(group_long_kernel, (int)((n_groups + 255) / 256), 256, 0, s, w.starts, ng, w.long_list, w.n_long);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)rows | (uintptr_t)out) & 15u) == 0);
+  unsigned vpr, lpr, sh;
+  fgeom((unsigned)dim, vec4, 1, &vpr, &lpr, &sh);
+  const unsigned gpw = 32u >> sh;
+  const int n_long_ctas = sms;
+  const auto k4 = segment_reduce_kernel<4>;
+  const auto k1 = segment_reduce_kernel<1>;
+  const int occ = vec4 ? occupancy_of(k4, kThreadsF) : occupancy_of(k1, kThreadsF);
+  const int grid = n_long_ctas + grid_for(n_groups, (int)(gpw * 2 * (kThreadsF / 32)), sms, occ > 1 ? occ - 1 : 1);
+  if (vec4)
+    DET_LAUNCH(k4, grid, kThreadsF, 0, s, rows, pin, w.starts, ng, (unsigned)dim, vpr, lpr, sh, w.long_list, w.n_long, n_long_ctas, out);
+  else
+    DET_LAUNCH(k1, grid, kThreadsF, 0, s, rows, pin, w.starts, ng, (unsigned)dim, vpr, lpr, sh, w.long_list, w.n_long, n_long_ctas, out);
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
 
 }  // extern "C"

@@ -964,7 +964,7 @@ using namespace det;
 
 extern "C" {
 
-int det_abi_version(void) { return 3; }
+int det_abi_version(void) { return 4; }
 #ifdef DET_EMU
 unsigned long long det_emu_stat(int which) { return which >= 0 && which < 2 ? det::g_det_emu_stat[which] : 0; }
 #endif

@@ -5,7 +5,7 @@ from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreat
                     HkvHashTableCreator, KVCreator)
 from .variable import (ModelMode, TrainableWrapper, Variable, default_partition_fn, embedding_lookup,
                        embedding_lookup_unique, enable_inference_mode, enable_train_mode, get_model_mode, get_variable,
-                       trainable_wrapper_filter, unique)
+                       segment_reduce, trainable_wrapper_filter, unique)
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
 from .optimizer import ComposedOptimizer, DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam
 from .restrict_policies import FrequencyRestrictPolicy, RestrictPolicy, TimestampRestrictPolicy
@@ -18,7 +18,7 @@ from . import data_flow
 __all__ = [
     "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvEvictStrategy", "HkvHashTable", "HkvHashTableConfig",
     "HkvHashTableCreator", "KVCreator", "Variable", "default_partition_fn", "embedding_lookup",
-    "embedding_lookup_unique", "get_variable", "unique", "SparseIds", "embedding_lookup_sparse",
+    "embedding_lookup_unique", "get_variable", "unique", "segment_reduce", "SparseIds", "embedding_lookup_sparse",
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
     "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy", "TrainableWrapper", "ModelMode",
     "enable_inference_mode", "enable_train_mode", "get_model_mode", "trainable_wrapper_filter", "shadow_ops",

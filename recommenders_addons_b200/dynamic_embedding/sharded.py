@@ -8,7 +8,19 @@ optimizer.  Works with the `gloo` backend on CPU tensors for the exchange logic 
 import torch
 import torch.distributed as dist
 
-from .variable import Variable, gather_rows, partition, scatter_rows
+import os
+
+from .variable import Variable, gather_rows, partition, scatter_rows, segment_reduce
+
+
+def combine_rows(rows, idx, n_unique):
+  """per-unique-key sum of the gradients several ranks sent for one row (idx from `unique`).
+  DET_GRAD_REDUCE=det: det_segment_reduce -- rows added in position order, deterministic, bit-identical to the
+  sequential sum (csrc/fused.cu K9).  Default until that kernel has run on a B200 (written after round 1's GPU budget
+  was spent; emulator-tested): torch's index_add, whose atomics add in schedule order."""
+  if rows.is_cuda and os.environ.get("DET_GRAD_REDUCE", "torch") == "det":
+    return segment_reduce(rows.to(torch.float32), idx, n_unique)
+  return torch.zeros((n_unique, rows.shape[1]), dtype=rows.dtype, device=rows.device).index_add_(0, idx.long(), rows)
 
 
 def _alltoall_counts(counts, group):
@@ -79,8 +91,7 @@ class ShardedVariable(object):
       from .variable import unique
       self._unique = unique
     uniq, idx = self._unique(recv_keys)
-    gsum = torch.zeros((uniq.numel(), self.dim), dtype=recv_g.dtype, device=recv_g.device).index_add(
-        0, idx.long(), recv_g)
+    gsum = combine_rows(recv_g, idx, uniq.numel())
     optimizer.iterations += 1
     optimizer.apply_sparse(self.local, uniq, gsum)
 
@@ -280,7 +291,7 @@ class PeerShardedVariable(object):
     self.phase_barrier()  # every owner has emptied its inbox: the next route may overwrite it
     if rk.numel():
       uniq, idx = unique(rk)
-      gsum = torch.zeros((uniq.numel(), self.dim), dtype=rg.dtype, device=rg.device).index_add_(0, idx.long(), rg)
+      gsum = combine_rows(rg, idx, uniq.numel())
       optimizer.iterations += 1
       optimizer.apply_sparse(self.local, uniq, gsum)
     else:

@@ -35,6 +35,31 @@ def unique(ids):
   return uniq[:int(cnt.item())], idx
 
 
+def segment_reduce(rows, idx, n_groups):
+  """out[g] = sum of rows[i] over the positions i with idx[i] == g, added in increasing position: the gradient dedupe
+  of the sparse optimizer path (TF's _deduplicate_indexed_slices = unsorted_segment_sum(values, idx, n_unique) before
+  _resource_apply_sparse_duplicate_indices, dynamic_embedding_optimizer.py:150,184).  Deterministic (no atomics) and
+  bit-identical to the sequential CPU sum; `idx` is what `unique` returns.  rows fp32 [n, dim] -> fp32 [n_groups, dim]."""
+  if rows.dtype != torch.float32:
+    raise TypeError("segment_reduce: rows must be float32, got %s" % rows.dtype)
+  rows = rows.contiguous()
+  idx = idx.reshape(-1).to(torch.int32).contiguous()
+  n = idx.numel()
+  if rows.dim() != 2 or rows.shape[0] != n:
+    raise ValueError("segment_reduce: rows must be [n, dim] with one row per index, got %s for %d indices"
+                     % (tuple(rows.shape), n))
+  dim = rows.shape[1]
+  dev = rows.device
+  lib = _lib.lib()
+  n_groups = int(n_groups)
+  out = torch.empty((n_groups, dim), dtype=torch.float32, device=dev)
+  ws_bytes = lib.det_segment_reduce_workspace_bytes(n, n_groups)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  _lib.check(lib.det_segment_reduce(_ptr(rows), _ptr(idx), n, n_groups, dim, _ptr(out), _ptr(ws), ws_bytes,
+                                    _stream_ptr(dev)))
+  return out
+
+
 def partition(keys, shard_num, gpu_mode=True):
   """default_partition_fn + dynamic_partition in one pass: keys grouped by owner (stable), the original
   position of every grouped key, and the per-shard counts (host list)."""

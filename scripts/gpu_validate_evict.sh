@@ -7,7 +7,7 @@
 set -u
 mkdir -p gpurun_out
 export DET_TEST_UNVALIDATED=1
-timeout 900 python -m pytest tests/test_evict_gpu.py tests/test_restrict_gpu.py tests/test_spill_gpu.py tests/test_callers_gpu.py -q -m gpu 2>&1 | tee gpurun_out/evict_tests.log | tail -40
+timeout 900 python -m pytest tests/test_evict_gpu.py tests/test_restrict_gpu.py tests/test_spill_gpu.py tests/test_callers_gpu.py tests/test_segreduce_gpu.py -q -m gpu 2>&1 | tee gpurun_out/evict_tests.log | tail -40
 # memory checker over the small cases (every kernel of evict.cu runs at least once)
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_evict_gpu.py -q -m gpu \
   -k "basic or lfu or custom or growth or touch" > gpurun_out/evict_memcheck.log 2>&1
@@ -36,3 +36,7 @@ timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-co
 echo "granularity probe exit: $?"; grep -ci "index\|gather" gpurun_out/granularity.csv
 L2_FETCH=32 timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k "regex:[iI]ndex|gather" --csv \
   --log-file gpurun_out/granularity_l2fetch32.csv python scripts/probe_granularity.py > gpurun_out/granularity_l2fetch32.json 2>> gpurun_out/granularity.err
+# round-2 candidate: deterministic per-unique gradient sum (det_segment_reduce) vs torch index_add in the c3 step
+timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce det > gpurun_out/c3_det.json 2> gpurun_out/c3_det.err
+timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce torch > gpurun_out/c3_torch.json 2> gpurun_out/c3_torch.err
+echo "c3 A/B (det_segment_reduce vs index_add):"; cut -c1-260 gpurun_out/c3_det.json gpurun_out/c3_torch.json

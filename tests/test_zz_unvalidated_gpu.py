@@ -1,4 +1,5 @@
-"""Runs the GPU suites that have never executed on real hardware (tests/test_evict_gpu.py, tests/test_restrict_gpu.py, tests/test_spill_gpu.py:
+"""Runs the GPU suites that have never executed on real hardware (tests/test_evict_gpu.py, tests/test_restrict_gpu.py, tests/test_spill_gpu.py, tests/test_callers_gpu.py,
+tests/test_segreduce_gpu.py:
 written after round 1's GPU budget was spent; their code paths have run on the SIMT emulator only) in a SUBPROCESS
 with its own CUDA context and a timeout, LAST in the collection order, and reports the outcome as xpass / xfail:
 a first real-hardware data point without any way of disturbing the validated suite (`pytest -x` does not stop on
@@ -19,7 +20,7 @@ pytestmark = pytest.mark.gpu
 def test_unvalidated_suites_in_a_subprocess():
   env = dict(os.environ, DET_TEST_UNVALIDATED="1")
   r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_evict_gpu.py", "tests/test_restrict_gpu.py",
-                      "tests/test_spill_gpu.py", "tests/test_callers_gpu.py", "-q", "-m",
+                      "tests/test_spill_gpu.py", "tests/test_callers_gpu.py", "tests/test_segreduce_gpu.py", "-q", "-m",
                       "gpu", "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=480, capture_output=True, text=True)
   print(r.stdout[-6000:])
   print(r.stderr[-2000:])
