@@ -270,3 +270,18 @@ def test_optimizer_rules_against_an_independent_implementation():
   np.testing.assert_allclose(m, opt.state[tp]["exp_avg"].numpy(), rtol=1e-6, atol=1e-7)
   np.testing.assert_allclose(v, opt.state[tp]["exp_avg_sq"].numpy(), rtol=1e-6, atol=1e-9)
   np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_segment_reduce_is_the_sequential_position_order_sum():
+  """oracle.segment_reduce (np.add.at) against the literal loop of TF's CPU unsorted_segment_sum: for every position in
+  order, out[idx[i]] += rows[i], one fp32 add per element; negative / too large ids dropped"""
+  rng = np.random.default_rng(17)
+  n, g, dim = 400, 9, 5
+  rows = (rng.normal(0, 1, (n, dim)) * np.exp(rng.uniform(-8, 8, (n, 1)))).astype(np.float32)
+  idx = rng.integers(-1, g + 1, size=n).astype(np.int32)
+  exp = np.zeros((g, dim), np.float32)
+  for i in range(n):
+    if 0 <= idx[i] < g:
+      for c in range(dim):
+        exp[idx[i], c] = np.float32(exp[idx[i], c] + rows[i, c])
+  np.testing.assert_array_equal(O.segment_reduce(rows, idx, g), exp)
