@@ -69,6 +69,15 @@ class _FusedBase(object):
         self._apply_table(params, params.tables[idx], grouped[b:e].contiguous(), grads[b:e].contiguous())
 
 
+  def apply_sparse_duplicate_indices(self, params, ids, grads):
+    """one step from row gradients whose ids may repeat: gradients of the same id are summed first
+    (`_resource_apply_sparse_duplicate_indices` -> `_deduplicate_indexed_slices`, the path the reference takes for
+    IndexedSlices gradients, dynamic_embedding_optimizer.py:150,184), then the fused step runs on the unique ids"""
+    from .variable import combine_rows, unique
+    uniq, idx = unique(ids.reshape(-1))
+    self.apply_sparse(params, uniq, combine_rows(grads.reshape(-1, params.dim).to(torch.float32), idx, uniq.numel()))
+
+
 class FusedAdagrad(_FusedBase):
   """TF Adagrad on dynamic-embedding rows: accum += g*g; var -= lr*g/(sqrt(accum)+epsilon).
   epsilon=0 is tf.compat.v1.train.AdagradOptimizer, epsilon=1e-7 the Keras optimizer."""
@@ -210,6 +219,12 @@ class ComposedOptimizer(object):
     """one step on the rows of `params` selected by the unique `keys` (the entry point the sharded variables call
     on the owning rank after routing and combining the gradients; same name as the fused optimizers')"""
     self._apply_one(TrainableWrapper(params, keys), grads)
+
+  def apply_sparse_duplicate_indices(self, params, ids, grads):
+    """as the fused optimizers': gradients of repeated ids are summed (`_deduplicate_indexed_slices`), then one step"""
+    from .variable import combine_rows, unique
+    uniq, idx = unique(ids.reshape(-1))
+    self.apply_sparse(params, uniq, combine_rows(grads.reshape(-1, params.dim), idx, uniq.numel()))
 
   def _apply_one(self, tw, grad):
     params = tw.params

@@ -8,19 +8,7 @@ optimizer.  Works with the `gloo` backend on CPU tensors for the exchange logic 
 import torch
 import torch.distributed as dist
 
-import os
-
-from .variable import Variable, gather_rows, partition, scatter_rows, segment_reduce
-
-
-def combine_rows(rows, idx, n_unique):
-  """per-unique-key sum of the gradients several ranks sent for one row (idx from `unique`).
-  DET_GRAD_REDUCE=det: det_segment_reduce -- rows added in position order, deterministic, bit-identical to the
-  sequential sum (csrc/fused.cu K9).  Default until that kernel has run on a B200 (written after round 1's GPU budget
-  was spent; emulator-tested): torch's index_add, whose atomics add in schedule order."""
-  if rows.is_cuda and os.environ.get("DET_GRAD_REDUCE", "torch") == "det":
-    return segment_reduce(rows.to(torch.float32), idx, n_unique)
-  return torch.zeros((n_unique, rows.shape[1]), dtype=rows.dtype, device=rows.device).index_add_(0, idx.long(), rows)
+from .variable import Variable, combine_rows, gather_rows, partition, scatter_rows
 
 
 def _alltoall_counts(counts, group):

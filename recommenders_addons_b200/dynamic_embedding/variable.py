@@ -60,6 +60,23 @@ def segment_reduce(rows, idx, n_groups):
   return out
 
 
+def combine_rows(rows, idx, n_unique):
+  """per-unique-key sum of row gradients (idx from `unique`): the dedupe in front of the sparse optimizer step.
+  DET_GRAD_REDUCE=det: det_segment_reduce -- rows added in position order, deterministic, bit-identical to the
+  sequential sum (csrc/fused.cu K9).  Default until that kernel has run on a B200 (written after round 1's GPU budget
+  was spent; emulator-tested): torch's index_add, whose GPU atomics add in schedule order."""
+  import os
+  if os.environ.get("DET_GRAD_REDUCE", "torch") == "det" and rows.dtype == torch.float32 and \
+      rows.device.type in _segment_reduce_devices():
+    return segment_reduce(rows, idx, n_unique)
+  return torch.zeros((n_unique, rows.shape[1]), dtype=rows.dtype, device=rows.device).index_add_(0, idx.long(), rows)
+
+
+def _segment_reduce_devices():
+  from . import table
+  return table._DEVICE_TYPES   # ("cuda",): the library only ever sees device memory
+
+
 def partition(keys, shard_num, gpu_mode=True):
   """default_partition_fn + dynamic_partition in one pass: keys grouped by owner (stable), the original
   position of every grouped key, and the per-shard counts (host list)."""

@@ -140,3 +140,8 @@ def test_gpu_suite_body(emu_mirror, name):
 @pytest.mark.parametrize("n,n_groups,dim", [(1000, 37, 16), (3000, 4000, 64), (1500, 50, 260)])
 def test_gpu_suite_random_body(emu_mirror, n, n_groups, dim):
   SG.test_segment_reduce_random_bit_exact(n, n_groups, dim)
+
+
+@pytest.mark.parametrize("mode", ["det", "torch"])
+def test_gpu_suite_optimizer_duplicate_ids_body(emu_mirror, monkeypatch, mode):
+  SG.test_optimizer_step_with_duplicate_ids(monkeypatch, mode)

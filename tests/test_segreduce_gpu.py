@@ -112,3 +112,34 @@ def test_sharded_combine_with_the_deterministic_reduce(monkeypatch):
     results.append(pv.lookup(torch.as_tensor(keys, device=DEV)).cpu().numpy())
     pv.close()
   np.testing.assert_allclose(results[0], results[1], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("mode", ["det", "torch"])
+def test_optimizer_step_with_duplicate_ids(monkeypatch, mode):
+  """apply_sparse_duplicate_indices = unique + per-id gradient sum + ONE fused step (the reference's
+  _resource_apply_sparse_duplicate_indices).  With DET_GRAD_REDUCE=det every step is bit-identical to the oracle
+  (sequential sums, then the Adagrad rule); the index_add combine agrees to fp32 rounding."""
+  monkeypatch.setenv("DET_GRAD_REDUCE", mode)
+  de = _de()
+  dim = 16
+  rng = np.random.default_rng(33)
+  var = de.Variable(dim=dim, init_size=1 << 13, initializer=0.5, num_slot_planes=1, devices=[DEV], name="dup-ids-" + mode)
+  opt = de.FusedAdagrad(0.05, 0.1)
+  p, a = O.PortTable(dim), O.PortTable(dim)
+  for step in range(3):
+    ids = np.minimum(rng.zipf(1.2, size=3000), 700).astype(np.int64) * 31 - 9
+    g = rng.normal(0, 1e-2, (ids.shape[0], dim)).astype(np.float32)
+    opt.iterations += 1
+    opt.apply_sparse_duplicate_indices(var, torch.as_tensor(ids, device=DEV), torch.as_tensor(g, device=DEV))
+    eu, eidx = O.unique_first_occurrence(ids)
+    O.sparse_adagrad_step(p, a, eu, O.segment_reduce(g, eidx, eu.shape[0]), 0.05, np.full(dim, 0.5, np.float32),
+                          np.full(dim, 0.1, np.float32))
+  k, v = var.export()
+  o = torch.argsort(k)
+  ek, ev = p.export()
+  eo = np.argsort(ek)
+  np.testing.assert_array_equal(k[o].cpu().numpy(), ek[eo])
+  if mode == "det":
+    np.testing.assert_array_equal(v[o].cpu().numpy(), ev[eo])
+  else:
+    np.testing.assert_allclose(v[o].cpu().numpy(), ev[eo], rtol=1e-5, atol=1e-7)
