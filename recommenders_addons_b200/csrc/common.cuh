@@ -68,13 +68,23 @@ __device__ __forceinline__ bool is_special(long long key) { return key == kEmpty
 
 // ---- memory access flavours -----------------------------------------------------------------
 // L2-coherent 16 B load of two keys (mutating kernels: L1 may hold lines older than a peer's CAS)
+// Measurement builds may put an L2 prefetch-size qualifier on the bucket loads (-DDET_KEY_L2=64 -> ".L2::64B"): ncu shows
+// ~125 B of DRAM read per 64 B bucket probe, i.e. the L2 may be filling whole 128 B lines for these loads
+// (scripts/probe_granularity.py, scripts/keyl2_sweep.sh).  Undefined = the validated default (no qualifier).
+#define DET_STR2(x) #x
+#define DET_STR(x) DET_STR2(x)
+#ifdef DET_KEY_L2
+#define DET_KEY_L2_QUAL ".L2::" DET_STR(DET_KEY_L2) "B"
+#else
+#define DET_KEY_L2_QUAL ""
+#endif
 __device__ __forceinline__ longlong2 ld_keys_cg(const long long* p) {
   longlong2 r;
 #ifdef DET_EMU
   r.x = __atomic_load_n(p, __ATOMIC_RELAXED);
   r.y = __atomic_load_n(p + 1, __ATOMIC_RELAXED);
 #else
-  asm volatile("ld.global.cg.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  asm volatile("ld.global.cg" DET_KEY_L2_QUAL ".v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
 #endif
   return r;
 }
@@ -85,7 +95,7 @@ __device__ __forceinline__ longlong2 ld_keys_nc(const long long* p) {
   r.x = p[0];
   r.y = p[1];
 #else
-  asm volatile("ld.global.nc.v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  asm volatile("ld.global.nc" DET_KEY_L2_QUAL ".v2.s64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
 #endif
   return r;
 }

@@ -238,7 +238,15 @@ template <> struct FVec<1> {
 };
 
 constexpr int kMaxVecPerLane = 8;
-constexpr int kSegPerGroup = 4;  // segments a lane-group works on concurrently (independent load chains)
+// segments a lane-group works on concurrently (independent load chains) and the resident CTAs per SM the register
+// budget is capped for; measurement builds override them (-DDET_SEG_U=8 -DDET_SEG_MINB=2, scripts/segsum_sweep.sh)
+#ifndef DET_SEG_U
+#define DET_SEG_U 4
+#endif
+#ifndef DET_SEG_MINB
+#define DET_SEG_MINB 3
+#endif
+constexpr int kSegPerGroup = DET_SEG_U;
 
 // K6 phase B, common case (one vector per lane covers the row): each lane-group owns kSegPerGroup
 // consecutive output rows and walks their ids in lock step, so up to 4 independent row loads are in flight
@@ -252,7 +260,7 @@ template <bool CLIP> __device__ __forceinline__ float clip_norm_of(const ClipArg
 template <> __device__ __forceinline__ float clip_norm_of<true>(const ClipArg<true>& c) { return c.max_norm; }
 
 template <int VF, bool CLIP = false>
-__global__ void __launch_bounds__(kThreadsF, 3)
+__global__ void __launch_bounds__(kThreadsF, DET_SEG_MINB)
 segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
                    const float* __restrict__ weights, size_t batch, int combiner,
                    const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
