@@ -52,13 +52,18 @@ def parse_args():
   ap.add_argument("--e2e-steps", type=int, default=10)
   ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                   help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
-  ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
-                  help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2])")
+  ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                  help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2]); "
+                       "c4 = the c2 step on configs[3] (torchrun --gpus 8: 1B keys = 125M resident per GPU, dim 128); "
+                       "c5 = sharded forward+backward (configs[4], torchrun)")
   ap.add_argument("--grad-reduce", default="det", choices=["det", "torch"],
                   help="c3 / c5: per-unique gradient sum by det_segment_reduce (position order, deterministic) or by "
                        "torch index_add (atomics); sets DET_GRAD_REDUCE for the sharded combine as well")
   ap.add_argument("--distinct-batches", type=int, default=64, help="distinct key batches cycled through")
-  return ap.parse_args()
+  a = ap.parse_args()
+  if a.workload == "c4":   # BASELINE configs[3]: key-hash sharded table, 1B keys over 8 GPUs, dim 128 -- the c2 step
+    a.dim, a.resident = 128, 125_000_000
+  return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -476,13 +481,14 @@ def gpu_arm(args):
   achieved = algo_bytes / (find_ms_1 * 1e-3) / 1e9
   honest_bytes = B * (8 + 64 + 2 * dim * 4)  # key in + one 64 B bucket + row read + row written out
   line = {
-      "metric": "embedding lookup+insert M keys/s at dim64", "value": value, "unit": "M keys/s", "n_gpus": world,
+      "metric": "embedding lookup+insert M keys/s at dim%d" % dim, "value": value, "unit": "M keys/s", "n_gpus": world,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "int64 keys / f32 rows (copy; no arithmetic)",
       "data": "synthetic",
       "config": {
-          "workload": "BASELINE configs[1]: HKV-style table, %d resident keys/GPU, dim %d fp32, Zipf(%.2f) ids, "
-                      "%d unique keys/step/GPU; step = Find(batch) + Insert(batch)" % (resident, dim, ALPHA, B),
+          "workload": "BASELINE configs[%d]: HKV-style table, %d resident keys/GPU, dim %d fp32, Zipf(%.2f) ids, "
+                      "%d unique keys/step/GPU; step = Find(batch) + Insert(batch)" %
+                      (3 if args.workload == "c4" else 1, resident, dim, ALPHA, B),
           "resident_keys_per_gpu": local_size, "capacity_slots": table.capacity(), "batch": B, "dim": dim,
           "l2": "inputs larger than L2: %d distinct batches are cycled, every step touches %.0f MB of rows + %.0f MB out + "
                 "%.0f MB in of a %.1f GB table (no L2 flush; the Zipf head is hot by design)" %
