@@ -43,6 +43,16 @@ REGISTER_OP("TFRA>DetApplyAdam")
     .Attr("beta2: float = 0.999")
     .Attr("epsilon: float = 1e-8");
 
+// The gradient dedupe in front of the sparse optimizer step: unsorted_segment_sum(values, idx, num_segments) as
+// _deduplicate_indexed_slices calls it before _resource_apply_sparse_duplicate_indices
+// (python/ops/dynamic_embedding_optimizer.py:150,184), with the rows of one segment added in position order
+// (deterministic; TF's GPU kernel uses atomics).  No table involved.
+REGISTER_OP("TFRA>DetSegmentReduce")
+    .Input("rows: float")            // [n, dim]
+    .Input("idx: int32")             // [n]: the idx output of tf.unique; ids outside [0, num_segments) are dropped
+    .Input("num_segments: int32")    // scalar, host memory
+    .Output("output: float");        // [num_segments, dim]
+
 using Table = DetHashTableOfTensorsGpu<int64, float>;
 
 static det_stream_t StreamOf(OpKernelContext* ctx) { return (det_stream_t)ctx->eigen_device<GPUDevice>().stream(); }
@@ -148,7 +158,32 @@ class DetApplyAdamOp : public OpKernel {
   float beta1_ = 0.9f, beta2_ = 0.999f, epsilon_ = 1e-8f;
 };
 
+class DetSegmentReduceOp : public OpKernel {
+ public:
+  explicit DetSegmentReduceOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& rows = ctx->input(0);
+    const Tensor& idx = ctx->input(1);
+    const Tensor& ns = ctx->input(2);
+    OP_REQUIRES(ctx, rows.dims() == 2, errors::InvalidArgument("rows must have shape [n, dim]"));
+    const int64 n = rows.dim_size(0), dim = rows.dim_size(1);
+    OP_REQUIRES(ctx, idx.NumElements() == n, errors::InvalidArgument("idx must have one entry per row"));
+    const int64 groups = ns.scalar<int32>()();
+    OP_REQUIRES(ctx, groups >= 0, errors::InvalidArgument("num_segments must be >= 0"));
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output("output", TensorShape({groups, dim}), &out));
+    const size_t ws_bytes = det_segment_reduce_workspace_bytes(static_cast<size_t>(n), static_cast<size_t>(groups));
+    Tensor ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_INT8, TensorShape({static_cast<int64>(ws_bytes)}), &ws));
+    OP_REQUIRES_OK(ctx, ToStatus(det_segment_reduce(rows.flat<float>().data(), idx.flat<int32>().data(),
+                                                    static_cast<size_t>(n), static_cast<size_t>(groups),
+                                                    static_cast<size_t>(dim), out->flat<float>().data(),
+                                                    ws.flat<int8>().data(), ws_bytes, StreamOf(ctx))));
+  }
+};
+
 REGISTER_KERNEL_BUILDER(Name("TFRA>DetLookupSparse").Device(DEVICE_GPU), DetLookupSparseOp);
+REGISTER_KERNEL_BUILDER(Name("TFRA>DetSegmentReduce").Device(DEVICE_GPU).HostMemory("num_segments"), DetSegmentReduceOp);
 REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdagrad").Device(DEVICE_GPU).HostMemory("lr"), DetApplyAdagradOp);
 REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdam").Device(DEVICE_GPU).HostMemory("alpha"), DetApplyAdamOp);
 

@@ -218,6 +218,27 @@ static void fused_ops() {
   const float a2 = 0.1f + 0.3f * 0.3f, a50 = 0.1f + 0.2f * 0.2f;
   CHECK_T(got.flat<float>()(0) == 2.f - (0.5f * 0.3f) / std::sqrt(a2) && got.flat<float>()(dim) == 1.f - (0.5f * -0.2f) / std::sqrt(a50));
   CHECK_T(table.size() == 4);
+  // gradient dedupe: rows {0,2} -> segment 1, row 1 -> segment 0, row 3 dropped (idx out of range), segment 2 empty
+  {
+    CHECK_T(reg.ops.count("TFRA>DetSegmentReduce"));
+    NodeDef sd;
+    OpKernelConstruction sc(sd);
+    std::unique_ptr<OpKernel> red(reg.kernels["TFRA>DetSegmentReduce"](&sc));
+    OpKernelContext cs = Ctx(DT_FLOAT);
+    Tensor idx(DT_INT32, TensorShape({4})), ns(DT_INT32, TensorShape({}));
+    const int32 iv[4] = {1, 0, 1, 7};
+    for (int i = 0; i < 4; ++i) idx.flat<int32>()(i) = iv[i];
+    ns.scalar<int32>()() = 3;
+    cs.inputs = {Rows<float>(DT_FLOAT, {0.25f, -2.f, 1.5f, 100.f}, dim), idx, ns};
+    red->Compute(&cs);
+    CHECK_OK(cs.status());
+    const Tensor& r = cs.outputs["output"];
+    CHECK_T(r.shape() == TensorShape({3, dim}));
+    CHECK_T(r.flat<float>()(0) == -2.f && r.flat<float>()(dim) == 0.25f + 1.5f && r.flat<float>()(2 * dim + 1) == 0.f);
+    cs.inputs[1] = Tensor(DT_INT32, TensorShape({3}));
+    red->Compute(&cs);
+    CHECK_T(!cs.status().ok() && cs.status().code() == error::INVALID_ARGUMENT);
+  }
   // a bad input is an InvalidArgument on the context, not a crash
   ca.inputs[2] = Tensor(DT_FLOAT, TensorShape({3, dim}));
   ada->Compute(&ca);

@@ -107,6 +107,7 @@ class Tensor {
   const TensorShape& shape() const { return shape_; }
   int64 NumElements() const { return shape_.num_elements(); }
   int64 dim_size(int i) const { return shape_.dim_size(i); }
+  int dims() const { return shape_.dims(); }
   void* data() const { return buf_ ? (void*)buf_->data() : nullptr; }
   template <class T> FlatView<T> flat() const { return FlatView<T>{(T*)data(), NumElements()}; }
   template <class T> FlatView<T> matrix() const { return flat<T>(); }
@@ -196,6 +197,10 @@ class OpKernelContext {
     if (it == out_dtypes.end()) return errors::InvalidArgument("unknown output ", name);
     outputs[name] = Tensor(it->second, s);
     *out = &outputs[name];
+    return OkStatus();
+  }
+  Status allocate_temp(DataType dt, const TensorShape& s, Tensor* out) {
+    *out = Tensor(dt, s);
     return OkStatus();
   }
   const Tensor& input(int i) const { return inputs.at(i); }
