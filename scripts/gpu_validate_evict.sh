@@ -19,24 +19,4 @@ timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pyte
 echo "racecheck exit: $?" | tee -a gpurun_out/evict_tests.log
 # the validated suite must be untouched by the new translation unit
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee -a gpurun_out/evict_tests.log
-# cost of the unvalidated features once they are green (short runs)
-timeout 600 python scripts/evict_microbench.py --capacity 20000000 --steps 100 > gpurun_out/evict_microbench.jsonl 2> gpurun_out/evict_microbench.err
-echo "evict microbench exit: $?"; tail -n 3 gpurun_out/evict_microbench.jsonl
-timeout 600 python scripts/spill_microbench.py > gpurun_out/spill_microbench.jsonl 2> gpurun_out/spill_microbench.err
-echo "spill microbench exit: $?"; cat gpurun_out/spill_microbench.jsonl
-# round-2 candidate: batched slot claims for inserts of NEW keys (DET_CLAIM_BATCH=1, common.cuh); correctness first
-# (the validated table suite under the variant), then the A/B of insert_new / insert_existing at dim 16 / 64 / 128
-DET_CLAIM_BATCH=1 timeout 900 python -m pytest tests/test_table_gpu.py tests/test_fused_gpu.py -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/claim_batch_tests.log
-timeout 600 python scripts/microbench.py --ops insert_new,insert_existing --resident 20000000 --tag serial > gpurun_out/claim_serial.jsonl 2> gpurun_out/claim_serial.err
-DET_CLAIM_BATCH=1 timeout 600 python scripts/microbench.py --ops insert_new,insert_existing --resident 20000000 --tag batched > gpurun_out/claim_batched.jsonl 2> gpurun_out/claim_batched.err
-echo "claim A/B:"; cat gpurun_out/claim_serial.jsonl gpurun_out/claim_batched.jsonl | cut -c1-300
-# how much DRAM traffic does one random 32 / 64 / 128 / 256 B read cost? (decides the bucket-width follow-up)
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k "regex:[iI]ndex|gather" --csv \
-  --log-file gpurun_out/granularity.csv python scripts/probe_granularity.py > gpurun_out/granularity.json 2> gpurun_out/granularity.err
-echo "granularity probe exit: $?"; grep -ci "index\|gather" gpurun_out/granularity.csv
-L2_FETCH=32 timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.sum --clock-control none -k "regex:[iI]ndex|gather" --csv \
-  --log-file gpurun_out/granularity_l2fetch32.csv python scripts/probe_granularity.py > gpurun_out/granularity_l2fetch32.json 2>> gpurun_out/granularity.err
-# round-2 candidate: deterministic per-unique gradient sum (det_segment_reduce) vs torch index_add in the c3 step
-timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce det > gpurun_out/c3_det.json 2> gpurun_out/c3_det.err
-timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce torch > gpurun_out/c3_torch.json 2> gpurun_out/c3_torch.err
-echo "c3 A/B (det_segment_reduce vs index_add):"; cut -c1-260 gpurun_out/c3_det.json gpurun_out/c3_torch.json
+# the A/B experiments and microbenches that used to follow live in scripts/round2_sweeps.sh (a separate gpurun call)
