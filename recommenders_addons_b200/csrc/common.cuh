@@ -422,7 +422,7 @@ __device__ __forceinline__ long long warp_find_or_claim_t(const TabRef& my, long
 // the serial primitive, which re-probes with fresh L2-coherent loads -- rare, and exactly the validated protocol.
 #ifdef DET_EMU
 // emulator-only counters (tests/test_detable_emu.py checks that the candidate path and its fallback really ran)
-extern "C" unsigned long long g_det_emu_stat[2];   // [0] warp-steps through the batched claim, [1] ... with a pending key
+extern "C" unsigned long long g_det_emu_stat[4];   // [0] warp-steps through the batched claim, [1] ... with a pending key, [2] staged segment-sum launches
 #endif
 
 template <bool MULTI>
@@ -725,6 +725,7 @@ static inline void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, un
   emu_mbar_update(bar, 0, -(long long)bytes);
 }
 static inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+static inline void cp_async4(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 4); }
 static inline void cp_async_commit() {}
 template <int N>
 static inline void cp_async_wait() {}
@@ -773,6 +774,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // Ampere-style asynchronous 16 B copies global -> shared (SASS LDGSTS): data in flight without holding registers
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -347,6 +347,158 @@ segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long 
   }
 }
 
+// K6 phase B, staged variant (DET_SEGSUM_STAGED=1; a round-2 candidate, default off): the register-held kernel above
+// keeps kSegPerGroup 16 B loads in flight per lane and cannot go further (8 segments spill or drop to one CTA per SM,
+// scripts/segsum_sweep.sh); ncu showed it at 4.2 TB/s with nothing saturated.  Here every warp owns a CONTIGUOUS range
+// of output rows, so the ids it needs are one contiguous stretch of `slots`: the warp streams that stretch through a
+// 3-stage ring of shared memory in windows of kWinSteps row-steps with cp.async (LDGSTS: up to two windows = 4 KB per
+// warp in flight, no registers held), and sums window k while k+1 and k+2 are loading.  A segment always belongs to the
+// same lane-group (segment index mod groups per warp), which adds its rows strictly in id order and carries the partial
+// sum across windows -- the arithmetic, its order and the results are those of segment_sum_kernel.
+// Requires VF == 4 rows of one vector per lane (dim % 4 == 0, dim <= 128).
+constexpr int kWinSteps = 4;   // row-steps per window: 4 x 32 lanes x 16 B = 2 KB
+constexpr int kWinStages = 3;
+constexpr int kWinFloat4 = kWinSteps * 32;                       // float4 per stage
+constexpr int kWinStageBytes = kWinFloat4 * 16 + 32 * 4;         // rows + one weight per staged row
+constexpr int kWinWarpBytes = kWinStages * kWinStageBytes;
+
+__global__ void __launch_bounds__(kThreadsF)
+segment_sum_staged_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
+                          const float* __restrict__ weights, size_t batch, int combiner,
+                          const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
+                          unsigned lpr_shift) {
+  DET_DYN_SHARED(dyn_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned gl = (unsigned)lane & (lpr - 1u);
+  const unsigned gpw = 32u >> lpr_shift;          // lane-groups per warp = rows per row-step
+  const unsigned gidx = (unsigned)lane >> lpr_shift;
+  const unsigned gsh = 5u - lpr_shift;            // log2(gpw)
+  const unsigned wsteps = gpw * (unsigned)kWinSteps > 32u ? 32u / gpw : (unsigned)kWinSteps;
+  const unsigned W = wsteps * gpw;                // rows per window (<= 32: lane r holds the slot of row r)
+  const unsigned dim = t.dim;
+  const bool lane_on = gl < vpr;
+  const float* table = (const float*)t.planes[0];
+  unsigned char* wbase = dyn_smem + (size_t)warp * kWinWarpBytes;
+  auto s_row = [&](int stage) -> float4* { return reinterpret_cast<float4*>(wbase + (size_t)stage * kWinStageBytes); };
+  auto s_wt = [&](int stage) -> float* { return reinterpret_cast<float*>(wbase + (size_t)stage * kWinStageBytes + kWinFloat4 * 16); };
+  // this warp's contiguous range of segments [S0, S1)
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsF) >> 5;
+  const size_t spw = (batch + nwarps - 1) / nwarps;
+  const size_t S0 = ((((size_t)blockIdx.x * kThreadsF) >> 5) + (size_t)warp) * spw;
+  if (S0 >= batch) return;
+  const size_t S1 = S0 + spw < batch ? S0 + spw : batch;
+  const unsigned nseg = (unsigned)(S1 - S0);
+  const long long p_begin = seg_start[S0], p_end = seg_start[S1];
+  const unsigned npos = (unsigned)(p_end - p_begin);
+  const unsigned nwin = npos ? (npos + W - 1) / W : 1u;   // an empty range still flushes its (empty) segments
+  // segment boundaries relative to p_begin, 64 at a time: lane i of b_lo holds boundary c*32 + i, b_hi the next 32
+  auto load_bounds = [&](unsigned first) -> unsigned {
+    const unsigned i = first + (unsigned)lane;
+    return (unsigned)(seg_start[S0 + (i < nseg ? i : nseg)] - p_begin);
+  };
+  unsigned chunk = 0;
+  unsigned b_lo = load_bounds(0), b_hi = load_bounds(32);
+  auto bound = [&](unsigned i) -> unsigned {    // boundary i, chunk*32 <= i < chunk*32 + 64; warp-uniform call
+    const unsigned o = i - chunk * 32u;
+    const unsigned lo = __shfl_sync(kFull, b_lo, (int)(o & 31u)), hi = __shfl_sync(kFull, b_hi, (int)(o & 31u));
+    return o < 32u ? lo : hi;
+  };
+  // producer: the slot of row `lane` of a window, then the cp.async copies of the window
+  auto load_slot = [&](unsigned k) -> long long {
+    const unsigned r = k * W + (unsigned)lane;
+    return (k < nwin && (unsigned)lane < W && r < npos) ? __ldg(slots + p_begin + r) : -1;
+  };
+  auto issue = [&](unsigned k, long long sl_of_lane) {
+    const int stage = (int)(k % (unsigned)kWinStages);
+    const unsigned w0 = k * W;
+#pragma unroll
+    for (int stp = 0; stp < kWinSteps; ++stp) {
+      const unsigned r = (unsigned)stp * gpw + gidx;
+      const long long sl = shfl_ll(sl_of_lane, (int)r);
+      if ((unsigned)stp < wsteps && k < nwin && w0 + r < npos && lane_on)
+        cp_async16(s_row(stage) + stp * 32 + lane,
+                   sl >= 0 ? table + (size_t)sl * dim + (size_t)gl * 4 : default_row + (size_t)gl * 4);
+    }
+    if (weights && k < nwin && (unsigned)lane < W && w0 + (unsigned)lane < npos)
+      cp_async4(s_wt(stage) + lane, weights + p_begin + w0 + lane);
+    cp_async_commit();
+  };
+  long long sl_next = load_slot(0);
+  issue(0, sl_next);
+  sl_next = load_slot(1);
+  issue(1, sl_next);
+  sl_next = load_slot(2);
+  // consumer state: cs = first segment (relative) that is not finished; my group's running sums
+  unsigned cs = 0;
+  FVec<4> acc;
+  acc.zero();
+  float wsum = 0.f, wsq = 0.f;
+  for (unsigned k = 0; k < nwin; ++k) {
+    const long long sl_issue = sl_next;
+    sl_next = load_slot(k + 3);                   // in flight while this window is summed
+    issue(k + 2, sl_issue);
+    cp_async_wait<2>();
+    __syncwarp();
+    const int stage = (int)(k % (unsigned)kWinStages);
+    const unsigned w0 = k * W;
+    const unsigned w1 = w0 + W < npos ? w0 + W : npos;
+    const float4* rows = s_row(stage);
+    const float* wts = s_wt(stage);
+    unsigned done = cs;                           // segments [cs, done) are finished after this window
+    if ((cs & ~(gpw - 1u)) < chunk * 32u) {       // the unfinished segment lies before the boundaries held: step back
+      chunk = (cs & ~(gpw - 1u)) >> 5;
+      b_lo = load_bounds(chunk * 32u);
+      b_hi = load_bounds(chunk * 32u + 32u);
+    }
+    for (unsigned base = cs & ~(gpw - 1u); base < nseg; base += gpw) {
+      while (base + gpw > chunk * 32u + 63u) {    // keep boundaries base .. base + gpw inside the 64 held
+        ++chunk;
+        b_lo = b_hi;
+        b_hi = load_bounds(chunk * 32u + 32u);
+      }
+      const unsigned first_st = bound(base < cs ? cs : base);
+      if (first_st > w1) break;                   // every later segment starts after this window (uniform)
+      const unsigned seg = base + gidx;
+      const unsigned st = bound(seg < nseg ? seg : nseg), en = bound(seg + 1u < nseg ? seg + 1u : nseg);
+      if (seg >= cs && seg < nseg && st <= w1) {
+        const unsigned a = st > w0 ? st : w0, b = en < w1 ? en : w1;
+        for (unsigned p = a; p < b; ++p) {
+          const unsigned r = p - w0;
+          const float wu = weights ? wts[r] : 1.f;
+          if (lane_on) {
+            FVec<4> x;
+            x.v = rows[(r >> gsh) * 32u + ((r & (gpw - 1u)) << lpr_shift) + gl];
+            acc.zip(x, [wu](float& av, float xv) { av = av + xv * wu; });
+          }
+          wsum = wsum + wu;
+          wsq = wsq + wu * wu;
+        }
+        if (en <= w1) {                           // the segment ends inside this window: normalise, store, reset
+          if (lane_on) {
+            if (en > st && combiner != DET_COMBINER_SUM) {
+              const float div = combiner == DET_COMBINER_MEAN ? wsum : sqrtf(wsq);
+              acc.apply([div](float& av) { av = av / div; });
+            }
+            acc.store(out + (S0 + seg) * dim + (size_t)gl * 4);
+          }
+          acc.zero();
+          wsum = 0.f;
+          wsq = 0.f;
+          done = seg + 1u;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned other = __shfl_xor_sync(kFull, done, o);
+      done = other > done ? other : done;
+    }
+    cs = done;
+    __syncwarp();   // every lane is done with this stage before the next issue overwrites it
+  }
+  cp_async_wait<0>();
+}
+
 // K6 phase B, wide rows (several vectors per lane): one lane-group per output row
 template <int VF>
 __global__ void __launch_bounds__(kThreadsF)
@@ -1172,6 +1324,17 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
   } else if (max_norm > 0.f) {
     rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse_clip: max_norm is fused for rows of at most 32 vectors (dim <= 128 when "
                                  "dim % 4 == 0, else dim <= 32); use the composed path for wider rows");
+  } else if (vpr <= lpr && vec4 && env_int("DET_SEGSUM_STAGED", 0) != 0) {
+    // round-2 candidate (default off): rows staged through shared memory with cp.async, see segment_sum_staged_kernel
+    const size_t smem = (size_t)(kThreadsF / 32) * kWinWarpBytes;
+    int occ = 1;
+    CUDA_TRY(cudaFuncSetAttribute(segment_sum_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, segment_sum_staged_kernel, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int grid = grid_for(batch, kThreadsF / 32, t->sm_count, occ);
+#ifdef DET_EMU
+    __atomic_fetch_add(&g_det_emu_stat[2], 1ull, __ATOMIC_RELAXED);
+#endif
+    DET_LAUNCH(segment_sum_staged_kernel, grid, kThreadsF, smem, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
   } else if (vpr <= lpr) {
     const ClipArg<false> noclip;
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);

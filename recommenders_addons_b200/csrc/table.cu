@@ -8,7 +8,7 @@ namespace det {
 
 #ifdef DET_EMU
 extern "C" {
-unsigned long long g_det_emu_stat[2] = {0, 0};
+unsigned long long g_det_emu_stat[4] = {0, 0, 0, 0};
 }
 #endif
 thread_local std::string g_last_error;
@@ -966,7 +966,7 @@ extern "C" {
 
 int det_abi_version(void) { return 4; }
 #ifdef DET_EMU
-unsigned long long det_emu_stat(int which) { return which >= 0 && which < 2 ? det::g_det_emu_stat[which] : 0; }
+unsigned long long det_emu_stat(int which) { return which >= 0 && which < 4 ? det::g_det_emu_stat[which] : 0; }
 #endif
 
 const char* det_build_info(void) {

@@ -10,5 +10,5 @@ export DET_EMU_SANITIZE=address,undefined
 export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 export ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1
 export UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1
-python -m pytest tests/test_detable_emu.py tests/test_fused_emu.py tests/test_segreduce_emu.py tests/test_host_peer_emu.py tests/test_mirror_emu.py \
+python -m pytest tests/test_detable_emu.py tests/test_fused_emu.py tests/test_segreduce_emu.py tests/test_segsum_staged_emu.py tests/test_host_peer_emu.py tests/test_mirror_emu.py \
   tests/test_reference_ops_emu.py tests/test_reference_variable_emu.py tests/test_reference_hkv_emu.py -x -q -p no:cacheprovider "$@"

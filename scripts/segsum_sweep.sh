@@ -16,4 +16,8 @@ run default ""
 run u3_minb4 "-DDET_SEG_U=3 -DDET_SEG_MINB=4"
 run u6_minb2 "-DDET_SEG_U=6 -DDET_SEG_MINB=2"
 python -m recommenders_addons_b200.build --force > /dev/null 2>&1
+# the cp.async-staged variant (segment_sum_staged_kernel, default library): correctness on the GPU suite first, then timing
+DET_SEGSUM_STAGED=1 timeout 600 python -m pytest tests/test_fused_gpu.py -x -q -m gpu -k "sparse" 2>&1 | tail -2 | tee -a gpurun_out/segsum_sweep.log
+DET_SEGSUM_STAGED=1 timeout 600 python scripts/microbench.py --ops lookup_sparse_1id,lookup_sparse_4ids --dims 16,64,128 --resident 50000000 --tag staged >> gpurun_out/segsum_sweep.jsonl 2>> gpurun_out/segsum_sweep.err
+timeout 600 python scripts/microbench.py --ops lookup_sparse_1id,lookup_sparse_4ids --dims 16,64,128 --resident 50000000 --tag plain >> gpurun_out/segsum_sweep.jsonl 2>> gpurun_out/segsum_sweep.err
 cut -c1-260 gpurun_out/segsum_sweep.jsonl
