@@ -1,9 +1,9 @@
-"""Runs the GPU suites that have never executed on real hardware (tests/test_evict_gpu.py, tests/test_restrict_gpu.py, tests/test_spill_gpu.py, tests/test_callers_gpu.py,
-tests/test_segreduce_gpu.py:
-written after round 1's GPU budget was spent; their code paths have run on the SIMT emulator only) in a SUBPROCESS
-with its own CUDA context and a timeout, LAST in the collection order, and reports the outcome as xpass / xfail:
-a first real-hardware data point without any way of disturbing the validated suite (`pytest -x` does not stop on
-either outcome, a faulting kernel cannot poison this process's CUDA context)."""
+"""Runs the GPU suites that have never executed on real hardware (tests/test_evict_gpu.py, tests/test_restrict_gpu.py,
+tests/test_spill_gpu.py, tests/test_callers_gpu.py, tests/test_segreduce_gpu.py: written after round 1's GPU budget was
+spent; their code paths have run on the SIMT emulator only), ONE FILE PER SUBPROCESS with its own CUDA context and a
+timeout, LAST in the collection order, and reports each outcome as xpass / xfail: a first real-hardware data point per
+suite without any way of disturbing the validated suite (`pytest -x` does not stop on either outcome, a faulting kernel
+cannot poison this process's CUDA context)."""
 import os
 import subprocess
 import sys
@@ -14,14 +14,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
+SUITES = ["tests/test_evict_gpu.py", "tests/test_restrict_gpu.py", "tests/test_spill_gpu.py", "tests/test_callers_gpu.py",
+          "tests/test_segreduce_gpu.py"]
 
-@pytest.mark.xfail(strict=False, reason="capacity-management / restrict-policy GPU tests: first run on real hardware, "
-                                        "informational until they have been green once (DESIGN.md 4b)")
-def test_unvalidated_suites_in_a_subprocess():
+
+@pytest.mark.parametrize("suite", SUITES)
+@pytest.mark.xfail(strict=False, reason="first run on real hardware of a suite that has only run on the emulator; "
+                                        "informational until it has been green once (DESIGN.md 3 K9 / 4b / 4c)")
+def test_unvalidated_suite_in_a_subprocess(suite):
   env = dict(os.environ, DET_TEST_UNVALIDATED="1")
-  r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_evict_gpu.py", "tests/test_restrict_gpu.py",
-                      "tests/test_spill_gpu.py", "tests/test_callers_gpu.py", "tests/test_segreduce_gpu.py", "-q", "-m",
-                      "gpu", "-p", "no:cacheprovider"], cwd=ROOT, env=env, timeout=480, capture_output=True, text=True)
+  r = subprocess.run([sys.executable, "-m", "pytest", suite, "-q", "-m", "gpu", "-p", "no:cacheprovider"], cwd=ROOT,
+                     env=env, timeout=300, capture_output=True, text=True)
   print(r.stdout[-6000:])
   print(r.stderr[-2000:])
   assert r.returncode == 0
