@@ -1125,29 +1125,81 @@ segment_reduce_kernel(const float* __restrict__ rows, const unsigned* __restrict
         float acc[kLongCols / kThreadsF];
 #pragma unroll
         for (int a = 0; a < kLongCols / kThreadsF; ++a) acc[a] = 0.f;
-        for (unsigned base = st; base < en; base += rpt) {
-          const unsigned m = en - base < rpt ? en - base : rpt;
-          for (unsigned r = threadIdx.x; r < m; r += kThreadsF) s_pos[r] = pos[base + r];
-          __syncthreads();
-          const unsigned total = m * wv;
-#pragma unroll 4
-          for (unsigned f = threadIdx.x; f < total; f += kThreadsF) {
-            const unsigned r = f / wv, cv = f - r * wv;
-            FVec<VF> x;
-            x.load(rows + (size_t)s_pos[r] * dim + c0 + (size_t)cv * VF);
-            x.store(s_rows + (size_t)r * wcols + (size_t)cv * VF);
-          }
-          __syncthreads();
+        if (VF == 4) {
+          // double-buffered: tile j+1 is in flight (cp.async, no registers held) while tile j is summed, and the
+          // positions of tile j+2 are already being loaded; a tile is half of s_rows (<= 1024 vectors: 4 per thread)
+          constexpr unsigned kHalf = kLongTileFloats / 2;
+          const unsigned rp2 = kHalf / wcols;                               // rows per tile (>= 4)
+          const unsigned ntiles = (en - st + rp2 - 1) / rp2;
+          unsigned pp[4];
+          auto load_pos = [&](unsigned tile) {
+            const unsigned tb = st + tile * rp2;
+            const unsigned m = tile < ntiles ? (en - tb < rp2 ? en - tb : rp2) : 0u;
 #pragma unroll
-          for (int a = 0; a < kLongCols / kThreadsF; ++a) {
-            const unsigned c = threadIdx.x + (unsigned)a * kThreadsF;
-            if (c < wcols) {
-              float s = acc[a];
-              for (unsigned r = 0; r < m; ++r) s = s + s_rows[(size_t)r * wcols + c];
-              acc[a] = s;
+            for (int i = 0; i < 4; ++i) {
+              const unsigned f = threadIdx.x + (unsigned)i * kThreadsF;
+              pp[i] = f < m * wv ? __ldg(pos + tb + f / wv) : 0xffffffffu;
             }
+          };
+          auto issue = [&](unsigned tile) {
+            float* buf = s_rows + (tile & 1u) * kHalf;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const unsigned f = threadIdx.x + (unsigned)i * kThreadsF;
+              const unsigned r = f / wv, cv = f - r * wv;
+              if (pp[i] != 0xffffffffu)
+                cp_async16(buf + (size_t)r * wcols + (size_t)cv * 4, rows + (size_t)pp[i] * dim + c0 + (size_t)cv * 4);
+            }
+            cp_async_commit();
+          };
+          load_pos(0);
+          issue(0);
+          load_pos(1);
+          for (unsigned j = 0; j < ntiles; ++j) {
+            issue(j + 1);                  // an empty group past the last tile keeps the wait count uniform
+            load_pos(j + 2);
+            cp_async_wait<1>();
+            __syncthreads();
+            const unsigned tb = st + j * rp2;
+            const unsigned m = en - tb < rp2 ? en - tb : rp2;
+            const float* buf = s_rows + (j & 1u) * kHalf;
+#pragma unroll
+            for (int a = 0; a < kLongCols / kThreadsF; ++a) {
+              const unsigned c = threadIdx.x + (unsigned)a * kThreadsF;
+              if (c < wcols) {
+                float sacc = acc[a];
+                for (unsigned r = 0; r < m; ++r) sacc = sacc + buf[(size_t)r * wcols + c];
+                acc[a] = sacc;
+              }
+            }
+            __syncthreads();               // tile j's buffer is free for tile j+2
           }
-          __syncthreads();
+          cp_async_wait<0>();
+        } else {
+          for (unsigned base = st; base < en; base += rpt) {
+            const unsigned m = en - base < rpt ? en - base : rpt;
+            for (unsigned r = threadIdx.x; r < m; r += kThreadsF) s_pos[r] = pos[base + r];
+            __syncthreads();
+            const unsigned total = m * wv;
+  #pragma unroll 4
+            for (unsigned f = threadIdx.x; f < total; f += kThreadsF) {
+              const unsigned r = f / wv, cv = f - r * wv;
+              FVec<VF> x;
+              x.load(rows + (size_t)s_pos[r] * dim + c0 + (size_t)cv * VF);
+              x.store(s_rows + (size_t)r * wcols + (size_t)cv * VF);
+            }
+            __syncthreads();
+  #pragma unroll
+            for (int a = 0; a < kLongCols / kThreadsF; ++a) {
+              const unsigned c = threadIdx.x + (unsigned)a * kThreadsF;
+              if (c < wcols) {
+                float s = acc[a];
+                for (unsigned r = 0; r < m; ++r) s = s + s_rows[(size_t)r * wcols + c];
+                acc[a] = s;
+              }
+            }
+            __syncthreads();
+          }
         }
 #pragma unroll
         for (int a = 0; a < kLongCols / kThreadsF; ++a) {
