@@ -135,6 +135,19 @@ def main():
     from recommenders_addons_b200.dynamic_embedding import variable as V
     med, mn = (timeit(lambda: V.partition(u, 8, True), a.reps) if on("partition8") else (None, None))
     emit("partition8", "zipf", med, mn, Bn * 20, Bn * 28)
+    # gradient dedupe: per-unique sum of Bn row gradients whose ids follow Zipf(1.05) WITH repeats (head keys own
+    # thousands of rows): det_segment_reduce (position order, no atomics) vs torch index_add (atomics)
+    if on("segment_reduce") or on("index_add"):
+      cdf2 = B.zipf_cdf_torch(res, dev)
+      dup = B.rank_to_key_torch(torch.searchsorted(cdf2, torch.rand(Bn, dtype=torch.float64, device=dev, generator=gen)).clamp_(max=res - 1))
+      del cdf2
+      uq, ix = de.unique(dup)
+      nu = uq.numel()
+      med, mn = (timeit(lambda: de.segment_reduce(grads, ix, nu), a.reps, flush) if on("segment_reduce") else (None, None))
+      emit("segment_reduce", "zipf_dup_u%d" % nu, med, mn, Bn * row + nu * row, Bn * (row + 4 + 16 * 3) + nu * row)
+      ix64 = ix.long()
+      med, mn = (timeit(lambda: torch.zeros((nu, dim), device=dev).index_add_(0, ix64, grads), a.reps, flush) if on("index_add") else (None, None))
+      emit("index_add", "zipf_dup_u%d" % nu, med, mn, Bn * row + nu * row, Bn * (row + 8) + 2 * nu * row)
     var.tables[0].close()
     del var, t
     torch.cuda.empty_cache()

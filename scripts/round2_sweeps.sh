@@ -26,6 +26,8 @@ L2_FETCH=32 timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.su
 # round-2 candidate: deterministic per-unique gradient sum (det_segment_reduce) vs torch index_add in the c3 step
 timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce det > gpurun_out/c3_det.json 2> gpurun_out/c3_det.err
 timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce torch > gpurun_out/c3_torch.json 2> gpurun_out/c3_torch.err
+timeout 400 python scripts/microbench.py --ops segment_reduce,index_add --dims 16,64,128 --resident 20000000 > gpurun_out/segment_reduce.jsonl 2> gpurun_out/segment_reduce.err
+cut -c1-260 gpurun_out/segment_reduce.jsonl
 echo "c3 A/B (det_segment_reduce vs index_add):"; cut -c1-260 gpurun_out/c3_det.json gpurun_out/c3_torch.json
 # L2 prefetch-size qualifier on the bucket loads (the ~125 B of DRAM read per probe), register caps, segment_sum variants
 timeout 900 bash scripts/keyl2_sweep.sh 2>&1 | tail -8
