@@ -55,6 +55,24 @@ def main():
     order.append({"row_bytes": row_bytes, "reads": N, "launches": 2, "out_bytes": int(out.numel() * 8)})
     del table, out
     torch.cuda.empty_cache()
+  # second question: is part of the per-probe DRAM traffic PAGE-TABLE WALKS?  Random 64 B reads over growing footprints:
+  # a cost per read that rises with the footprint is TLB-miss traffic, not fetch granularity.  The engine touches two
+  # random pages per key (key plane + value plane of a 53 GB table); if the walks show up here, a bucket-major layout
+  # (a bucket's keys next to its rows, one page per key) is the follow-up, not a different bucket width.
+  for gib in (0.5, 4, 32, 96):
+    rows = int(gib * (1 << 30)) // 64
+    free = torch.cuda.mem_get_info()[0]
+    if rows * 64 + (2 << 30) > free:
+      continue
+    table = torch.zeros((rows, 8), dtype=torch.int64, device=dev)
+    idx = torch.randint(0, rows, (N,), device=dev, generator=g)
+    torch.cuda.synchronize()
+    for _ in range(2):
+      out = table.index_select(0, idx)
+    torch.cuda.synchronize()
+    order.append({"row_bytes": 64, "footprint_gib": gib, "reads": N, "launches": 2, "out_bytes": int(out.numel() * 8)})
+    del table, out
+    torch.cuda.empty_cache()
   print(json.dumps(order))
 
 
