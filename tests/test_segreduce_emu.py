@@ -145,3 +145,20 @@ def test_gpu_suite_random_body(emu_mirror, n, n_groups, dim):
 @pytest.mark.parametrize("mode", ["det", "torch"])
 def test_gpu_suite_optimizer_duplicate_ids_body(emu_mirror, monkeypatch, mode):
   SG.test_optimizer_step_with_duplicate_ids(monkeypatch, mode)
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(1, 2500), n_groups=st.integers(1, 70000), dim=st.sampled_from([1, 3, 4, 8, 20, 64, 130]),
+       skew=st.sampled_from([0.0, 1.1, 2.0]), seed=st.integers(0, 2**31 - 1))
+def test_property_any_shape_matches_the_sequential_sum(n, n_groups, dim, skew, seed):
+  rng = np.random.default_rng(seed)
+  if skew == 0.0:
+    idx = rng.integers(-1, n_groups + 1, size=n)
+  else:
+    idx = np.minimum(rng.zipf(skew, size=n) - 1, n_groups - 1)
+  idx = idx.astype(np.int32)
+  rows = rows_of(rng, n, dim)
+  np.testing.assert_array_equal(reduce_emu(rows, idx, n_groups), O.segment_reduce(rows, idx, n_groups))

@@ -117,3 +117,26 @@ def test_large_batch_many_warps(monkeypatch):
   ids = rng.integers(0, 900, size=seg.shape[0]).astype(np.int64)
   _both(monkeypatch, t, ot, ids, seg, None, batch, "sum")
   t.close()
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=20, deadline=None)
+@given(batch=st.integers(1, 700), maxlen=st.sampled_from([1, 3, 12, 90]), p_empty=st.sampled_from([0.0, 0.3, 0.9]),
+       dim=st.sampled_from([4, 8, 16, 64, 128]), combiner=st.sampled_from(["sum", "mean", "sqrtn"]),
+       use_w=st.booleans(), seed=st.integers(0, 2**31 - 1))
+def test_property_any_bag_structure(batch, maxlen, p_empty, dim, combiner, use_w, seed):
+  import pytest as _pytest
+  rng = np.random.default_rng(seed)
+  t, ot = _tables(rng, dim)
+  lens = rng.integers(1, maxlen + 1, size=batch) * (rng.random(batch) >= p_empty)
+  seg = np.repeat(np.arange(batch), lens).astype(np.int32)
+  ids = rng.integers(0, 900, size=seg.shape[0]).astype(np.int64)
+  w = rng.uniform(0.25, 2.0, size=seg.shape[0]).astype(np.float32) if use_w else None
+  mp = _pytest.MonkeyPatch()
+  try:
+    _both(mp, t, ot, ids, seg, w, batch, combiner)
+  finally:
+    mp.undo()
+    t.close()
