@@ -4,7 +4,7 @@ import torch
 
 from .. import _lib
 from .table import _ptr, _stream_ptr
-from .variable import Variable, embedding_lookup, unique
+from .variable import Variable, embedding_lookup, gather_unique, unique
 
 
 class SparseIds(object):
@@ -82,7 +82,7 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
   uniq, idx = unique(ids)
   r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)
   emb_u, tw = r if return_trainable else (r, None)
-  emb = emb_u.to(torch.float32)[idx.long()]
+  emb = gather_unique(emb_u.to(torch.float32), idx)
   seg64 = segment_ids.long().to(emb.device)
   w = torch.ones(ids.numel(), dtype=torch.float32, device=emb.device) if ignore_weights else \
       weights.to(device=emb.device, dtype=torch.float32)

@@ -72,6 +72,28 @@ def combine_rows(rows, idx, n_unique):
   return torch.zeros((n_unique, rows.shape[1]), dtype=rows.dtype, device=rows.device).index_add_(0, idx.long(), rows)
 
 
+class _GatherUnique(torch.autograd.Function):
+  """rows[idx] whose backward is the gradient dedupe of the reference -- the gradient of `gather(embeddings, idx)` is
+  IndexedSlices(grad, idx), which the optimizer sums per unique row (_deduplicate_indexed_slices,
+  dynamic_embedding_optimizer.py:150,184) -- computed by `combine_rows` (det_segment_reduce under DET_GRAD_REDUCE=det)."""
+
+  @staticmethod
+  def forward(ctx, rows, idx):
+    ctx.save_for_backward(idx)
+    ctx.n_unique = rows.shape[0]
+    return rows[idx.long()]
+
+  @staticmethod
+  def backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    return combine_rows(grad.reshape(idx.numel(), -1).contiguous(), idx, ctx.n_unique), None
+
+
+def gather_unique(rows, idx):
+  """rows [U, dim] -> [n, dim] by the idx of `unique`; differentiable w.r.t. rows"""
+  return _GatherUnique.apply(rows, idx)
+
+
 def _segment_reduce_devices():
   from . import table
   return table._DEVICE_TYPES   # ("cuda",): the library only ever sees device memory
@@ -519,7 +541,7 @@ def embedding_lookup_unique(params, ids, partition_strategy=None, name=None, val
   uniq, idx = unique(flat)
   r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)
   emb, tw = r if return_trainable else (r, None)
-  out = emb[idx.long()].reshape(tuple(ids.shape) + (params.dim,))
+  out = gather_unique(emb, idx).reshape(tuple(ids.shape) + (params.dim,))
   return (out, tw) if return_trainable else out
 
 

@@ -147,6 +147,11 @@ def test_gpu_suite_optimizer_duplicate_ids_body(emu_mirror, monkeypatch, mode):
   SG.test_optimizer_step_with_duplicate_ids(monkeypatch, mode)
 
 
+@pytest.mark.parametrize("mode", ["det", "torch"])
+def test_gpu_suite_lookup_unique_backward_body(emu_mirror, monkeypatch, mode):
+  SG.test_embedding_lookup_unique_backward_is_the_gradient_dedupe(monkeypatch, mode)
+
+
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 

@@ -143,3 +143,25 @@ def test_optimizer_step_with_duplicate_ids(monkeypatch, mode):
     np.testing.assert_array_equal(v[o].cpu().numpy(), ev[eo])
   else:
     np.testing.assert_allclose(v[o].cpu().numpy(), ev[eo], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("mode", ["det", "torch"])
+def test_embedding_lookup_unique_backward_is_the_gradient_dedupe(monkeypatch, mode):
+  """d(embedding_lookup_unique)/d(unique rows) = per-unique sum of the output gradients (the gradient of the reference's
+  gather, summed by _deduplicate_indexed_slices); bit-identical to the sequential sum under DET_GRAD_REDUCE=det"""
+  monkeypatch.setenv("DET_GRAD_REDUCE", mode)
+  de = _de()
+  dim = 8
+  rng = np.random.default_rng(41)
+  var = de.Variable(dim=dim, init_size=1 << 12, initializer=0.1, devices=[DEV], name="lookup-unique-bwd-" + mode)
+  ids = np.minimum(rng.zipf(1.3, size=2000), 300).astype(np.int64)
+  out, tw = de.embedding_lookup_unique(var, torch.as_tensor(ids, device=DEV), return_trainable=True)
+  gout = rng.normal(0, 1, (ids.shape[0], dim)).astype(np.float32)
+  out.backward(torch.as_tensor(gout, device=DEV))
+  eu, eidx = O.unique_first_occurrence(ids)
+  exp = O.segment_reduce(gout, eidx, eu.shape[0])
+  got = tw.values.grad.cpu().numpy()
+  if mode == "det":
+    np.testing.assert_array_equal(got, exp)
+  else:
+    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-6)
