@@ -24,7 +24,7 @@ SUITES = ["tests/test_evict_gpu.py", "tests/test_restrict_gpu.py", "tests/test_s
 def test_unvalidated_suite_in_a_subprocess(suite):
   env = dict(os.environ, DET_TEST_UNVALIDATED="1")
   r = subprocess.run([sys.executable, "-m", "pytest", suite, "-q", "-m", "gpu", "-p", "no:cacheprovider"], cwd=ROOT,
-                     env=env, timeout=300, capture_output=True, text=True)
+                     env=env, timeout=180, capture_output=True, text=True)
   print(r.stdout[-6000:])
   print(r.stderr[-2000:])
   assert r.returncode == 0
