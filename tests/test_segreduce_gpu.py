@@ -63,7 +63,7 @@ def test_segment_reduce_criteo_shaped_step():
   np.testing.assert_array_equal(got.cpu().numpy(), O.segment_reduce(g, eidx, eu.shape[0]))
   # and it is what the schedule-ordered atomics compute, up to fp32 rounding
   ref = torch.zeros_like(got).index_add_(0, idx.long(), torch.as_tensor(g, device=DEV))
-  torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6)
+  torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-3)   # sums of up to ~40 K rows in a different order
 
 
 def test_segment_reduce_is_deterministic():
