@@ -164,4 +164,4 @@ def test_embedding_lookup_unique_backward_is_the_gradient_dedupe(monkeypatch, mo
   if mode == "det":
     np.testing.assert_array_equal(got, exp)
   else:
-    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-3)   # atomics: sums of up to ~700 N(0,1) rows in any order
