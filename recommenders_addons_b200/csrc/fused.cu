@@ -1219,6 +1219,15 @@ segment_reduce_kernel(const float* __restrict__ rows, const unsigned* __restrict
   const size_t warp0 = (((size_t)blockIdx.x - (size_t)n_long_ctas) * kThreadsF + threadIdx.x) >> 5;
   const size_t nwarps = (((size_t)gridDim.x - (size_t)n_long_ctas) * kThreadsF) >> 5;
   const unsigned nchunk = (vpr + lpr - 1u) / lpr;   // 1 unless the row is wider than 32 vectors
+  // the U + 1 boundaries of the NEXT iteration's groups are loaded one iteration ahead (they head a chain of three
+  // dependent loads: boundary -> position -> row)
+  unsigned nb[U + 1];
+  auto load_bounds = [&](size_t sb_) {
+    const size_t g0_ = sb_ + (size_t)gidx * U;
+#pragma unroll
+    for (int u = 0; u <= U; ++u) nb[u] = (sb_ < n_groups && g0_ + u <= n_groups) ? __ldg(starts + g0_ + u) : 0u;
+  };
+  load_bounds(warp0 * gpw * U);
   for (size_t sb = warp0 * gpw * U; sb < n_groups; sb += nwarps * gpw * U) {
     const size_t g0 = sb + (size_t)gidx * U;
     unsigned st[U], en[U];
@@ -1226,11 +1235,12 @@ segment_reduce_kernel(const float* __restrict__ rows, const unsigned* __restrict
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const bool ok = g0 + u < n_groups;
-      const unsigned a = ok ? starts[g0 + u] : 0u, b = ok ? starts[g0 + u + 1] : 0u;
+      const unsigned a = ok ? nb[u] : 0u, b = ok ? nb[u + 1] : 0u;
       mine[u] = ok && b - a <= (unsigned)kLongGroup;
       st[u] = mine[u] ? a : 0u;
       en[u] = mine[u] ? b : 0u;
     }
+    load_bounds(sb + nwarps * gpw * U);
     for (unsigned cc = 0; cc < nchunk; ++cc) {
       const unsigned cv = cc * lpr + gl;
       const bool lane_on = cv < vpr;
