@@ -517,6 +517,17 @@ def gpu_arm(args):
                    ((world - 1) / world * B * (64 + dim * 4) / (find_ms_1 * 1e-3) / 1e9)),
       },
   }
+  if world > 1:
+    # at N > 1 the exchange is bounded by NVLink, not HBM -- (N-1)/N of a rank's bucket probes and rows
+    # cross the link (one direction for find: owner -> requester).  Peak = the measured peer copy of this pool's boxes
+    # (profiles/r01_peer_microbench_2gpu.jsonl: 735 GB/s; 770 GB/s on the 8-GPU box), nominal 900 GB/s per direction.
+    nv_bytes = (world - 1) / world * B * (64 + dim * 4)
+    nv_peak = float(os.environ.get("DET_NVLINK_PEAK_GBS", "770"))
+    line["roofline_nvlink"] = {"bound": "nvlink", "kernel": line["roofline"]["kernel"],
+                               "achieved": nv_bytes / (find_ms_1 * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
+                               "frac": nv_bytes / (find_ms_1 * 1e-3) / 1e9 / nv_peak,
+                               "bytes_per_launch": nv_bytes,
+                               "peak_source": "measured peer copy, one direction (DET_NVLINK_PEAK_GBS overrides)"}
   if e2e:
     line["e2e"] = e2e
   if no_exchange:
