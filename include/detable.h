@@ -316,6 +316,19 @@ det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* co
 det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int append_to_file);
 det_status det_load(det_table* t, const char* prefix, size_t buffer_keys, int clear_first);
 
+/* Checkpointing the state of the FUSED optimizers.  The reference keeps every optimizer slot in its own table
+ * `<var>/<opt>/<slot>` (python/ops/dynamic_embedding_optimizer.py:870-958), saved and restored like any variable;
+ * here the slots are planes of the variable's own table, so they travel as one more raw file pair per plane:
+ *   det_save_plane  = det_save of plane 1..num_slot_planes (fp32 rows; never-stepped keys carry the slot initializer),
+ *   det_load_plane  = the pair read back into the plane for the keys that are IN the table (restore the value plane
+ *                     first); keys of the file that are not in the table are skipped,
+ *   det_import_plane = the same from device buffers (keys int64 [n], rows fp32 [n, dim]), asynchronous on `stream`.
+ * ABI >= 4. */
+det_status det_import_plane(det_table* t, int plane, const int64_t* keys, const float* rows, size_t n,
+                            det_stream_t stream);
+det_status det_save_plane(det_table* t, int plane, const char* prefix, size_t buffer_keys, int append_to_file);
+det_status det_load_plane(det_table* t, int plane, const char* prefix, size_t buffer_keys);
+
 /* introspection for tests / benches (HOST outs; synchronises) */
 typedef struct det_stats {
   int64_t size;        /* live keys */

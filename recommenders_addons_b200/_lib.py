@@ -88,6 +88,9 @@ SIGNATURES = {
     "det_peer_inbox_gather": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp]),
     "det_save": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
     "det_load": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
+    "det_import_plane": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
+    "det_save_plane": (_i, [_vp, _i, ctypes.c_char_p, _sz, _i]),
+    "det_load_plane": (_i, [_vp, _i, ctypes.c_char_p, _sz]),
     "det_get_stats": (_i, [_vp, ctypes.POINTER(DetStats), _vp]),
     "det_insert_scored": (_i, [_vp, _vp, _vp, _vp, _sz, _vp]),
     "det_accum_scored": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -288,8 +288,9 @@ det_status det_host_sync(det_table* t) {
 // exported window by window (det_export_window: `buffer_keys` keys at a time, table order) into a bounded device
 // buffer, copied to a bounded host buffer and appended to `<prefix>-keys` / `<prefix>-values`; memory use does not
 // depend on the table size.  Without append_to_file the files are written under a temporary name and renamed.
-det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int append_to_file) {
+static det_status save_plane(det_table* t, int plane, const char* prefix, size_t buffer_keys, int append_to_file) {
   if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_save: null argument");
+  if (plane < 0 || plane > t->cfg.num_slot_planes) return fail(DET_INVALID_ARGUMENT, "det_save_plane: bad plane");
   det::DevGuard _dg(t->cfg.device);
   if (buffer_keys == 0) buffer_keys = 1u << 20;
   {  // a table smaller than the buffer needs no more staging memory than its own size
@@ -299,7 +300,7 @@ det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int ap
     const size_t want = n > 0 ? (size_t)n : 1;
     if (buffer_keys > want) buffer_keys = want;
   }
-  const size_t rb = t->row_bytes;
+  const size_t rb = plane == 0 ? t->row_bytes : (size_t)t->cfg.dim * 4u;   // slot planes are fp32 rows
   long long* dk = nullptr;
   unsigned char* dv = nullptr;
   CUDA_TRY(cudaMalloc((void**)&dk, buffer_keys * 8));
@@ -319,7 +320,7 @@ det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int ap
   std::vector<unsigned char> hv(buffer_keys * rb);
   for (uint64_t first = 0; ok && st == DET_OK;) {
     int64_t got = 0;
-    st = det_export_window(t, 0, first, (int64_t*)dk, dv, buffer_keys, &got, nullptr);
+    st = det_export_window(t, plane, first, (int64_t*)dk, dv, buffer_keys, &got, nullptr);
     if (st != DET_OK || got <= 0) break;
     if (cudaMemcpy(hk.data(), dk, (size_t)got * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
         cudaMemcpy(hv.data(), dv, (size_t)got * rb, cudaMemcpyDeviceToHost) != cudaSuccess) {
@@ -339,6 +340,68 @@ det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int ap
   if (ok && !append_to_file) ok = rename(kt.c_str(), kf.c_str()) == 0 && rename(vt.c_str(), vf.c_str()) == 0;
   if (!ok) return fail(DET_IO_ERROR, "det_save: cannot write " + kf + " / " + vf);
   return DET_OK;
+}
+
+det_status det_save(det_table* t, const char* prefix, size_t buffer_keys, int append_to_file) {
+  return save_plane(t, 0, prefix, buffer_keys, append_to_file);
+}
+
+det_status det_save_plane(det_table* t, int plane, const char* prefix, size_t buffer_keys, int append_to_file) {
+  if (t && plane == 0) return fail(DET_INVALID_ARGUMENT, "det_save_plane: plane 0 is det_save");
+  return save_plane(t, plane, prefix, buffer_keys, append_to_file);
+}
+
+// the slot-plane file pair of det_save_plane read back: rows of keys that are in the table (det_import_plane)
+det_status det_load_plane(det_table* t, int plane, const char* prefix, size_t buffer_keys) {
+  if (!t || !prefix) return fail(DET_INVALID_ARGUMENT, "det_load_plane: null argument");
+  if (plane < 1 || plane > t->cfg.num_slot_planes) return fail(DET_INVALID_ARGUMENT, "det_load_plane: bad plane");
+  det::DevGuard _dg(t->cfg.device);
+  const std::string kf = std::string(prefix) + "-keys", vf = std::string(prefix) + "-values";
+  FILE* fk = fopen(kf.c_str(), "rb");
+  FILE* fv = fopen(vf.c_str(), "rb");
+  if (!fk || !fv) {
+    if (fk) fclose(fk);
+    if (fv) fclose(fv);
+    return fail(DET_IO_ERROR, "det_load_plane: cannot open " + kf + " / " + vf);
+  }
+  const size_t rb = (size_t)t->cfg.dim * 4u;
+  if (buffer_keys == 0) buffer_keys = 1u << 20;
+  if (fseek(fk, 0, SEEK_END) == 0) {
+    const long bytes = ftell(fk);
+    const size_t n_file = bytes > 0 ? (size_t)bytes / 8 : 0;
+    if (buffer_keys > n_file) buffer_keys = n_file ? n_file : 1;
+    rewind(fk);
+  }
+  std::vector<long long> hk(buffer_keys);
+  std::vector<unsigned char> hv(buffer_keys * rb);
+  long long* dk = nullptr;
+  unsigned char* dv = nullptr;
+  det_status st = DET_OK;
+  if (cudaMalloc((void**)&dk, buffer_keys * 8) != cudaSuccess || cudaMalloc((void**)&dv, buffer_keys * rb) != cudaSuccess) {
+    cudaGetLastError();
+    st = fail(DET_OUT_OF_MEMORY, "det_load_plane: no HBM for the staging buffer; use a smaller buffer_size");
+  }
+  while (st == DET_OK) {
+    const size_t m = fread(hk.data(), 8, buffer_keys, fk);
+    if (m == 0) break;
+    if (fread(hv.data(), rb, m, fv) != m) {
+      st = fail(DET_IO_ERROR, "det_load_plane: " + vf + " is shorter than " + kf);
+      break;
+    }
+    if (cudaMemcpy(dk, hk.data(), m * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dv, hv.data(), m * rb, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      st = fail(DET_CUDA_ERROR, "det_load_plane: H2D copy failed");
+      break;
+    }
+    st = det_import_plane(t, plane, (const int64_t*)dk, (const float*)dv, m, nullptr);
+    if (st == DET_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) st = fail(DET_CUDA_ERROR, "det_load_plane: import failed");
+  }
+  if (dk) cudaFree(dk);
+  if (dv) cudaFree(dv);
+  fclose(fk);
+  fclose(fv);
+  return st;
 }
 
 // LoadFromFileSystem (cuckoo_hashtable_op.cc:393-504): clear_first != 0 = the op on ONE file (clear + insert all);

@@ -617,6 +617,31 @@ __global__ void export_special_kernel(TableView t, int plane, unsigned plane_row
   if (threadIdx.x == 0) t.st->scratch[1] = o <= first ? 0 : (o - first < max_n ? o - first : max_n);
 }
 
+// det_import_plane: rows of ONE optimizer slot plane written for keys that are in the table (checkpoint restore of the
+// fused optimizers' state: the reference restores each slot from its own table `<var>/<opt>/<slot>`,
+// python/ops/dynamic_embedding_optimizer.py:870-958).  Keys that are not in the table are skipped.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+set_plane_kernel(TableView t, int plane, const long long* __restrict__ keys, const unsigned char* __restrict__ rows,
+                 size_t n, RowGeom g) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreads) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const long long slot = warp_find_slots<true>(t, key, valid, lane);
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid && slot >= 0) {
+      src = rows + i * g.row_bytes;
+      dst = t.planes[plane] + (size_t)slot * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+  }
+}
+
 // exported optimizer-slot rows that were never initialised read as the slot initializer value
 __global__ void export_fix_slot_rows_kernel(float* __restrict__ vals, const unsigned long long* __restrict__ n_rows,
                                             unsigned dim, float init) {
@@ -1353,6 +1378,31 @@ det_status det_export_window(det_table* t, int plane, uint64_t first, int64_t* k
 det_status det_export(det_table* t, int plane, int64_t* keys_out, void* values_out, size_t max_n,
                       int64_t* n_out_host, det_stream_t stream) {
   return det_export_window(t, plane, 0, keys_out, values_out, max_n, n_out_host, stream);
+}
+
+det_status det_import_plane(det_table* t, int plane, const int64_t* keys, const float* rows, size_t n,
+                            det_stream_t stream) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_import_plane: null table");
+  std::lock_guard<std::mutex> _lk(t->mu);
+  if (plane < 1 || plane > t->cfg.num_slot_planes)
+    return fail(DET_INVALID_ARGUMENT, "det_import_plane: plane must be one of the table's optimizer slot planes (1.." +
+                                          std::to_string(t->cfg.num_slot_planes) + ")");
+  if (n == 0) return DET_OK;
+  if (!keys || !rows) return fail(DET_INVALID_ARGUMENT, "det_import_plane: null keys/rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  det::DevGuard _dg(t->cfg.device);
+  const size_t rb = (size_t)t->cfg.dim * 4u;
+  const int vec = pick_vec(rb, rows, nullptr, nullptr);
+  const RowGeom g = make_geom((unsigned)rb, vec);
+  const int grid = grid_for(n, kThreads, t->sm_count, 8);
+  const TableView v = t->view;
+  dispatch_vec(vec, [&](auto V) -> det_status {
+    DET_LAUNCH(set_plane_kernel<decltype(V)::value>, grid, kThreads, 0, s, v, plane, (const long long*)keys,
+               (const unsigned char*)rows, n, g);
+    return DET_OK;
+  });
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
 }
 
 det_status det_import(det_table* t, const int64_t* keys, const void* values, size_t n, det_stream_t stream) {

@@ -7,7 +7,7 @@ from .variable import (ModelMode, TrainableWrapper, Variable, default_partition_
                        embedding_lookup_unique, enable_inference_mode, enable_train_mode, get_model_mode, get_variable,
                        segment_reduce, trainable_wrapper_filter, unique)
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
-from .optimizer import ComposedOptimizer, DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam
+from .optimizer import ComposedOptimizer, DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam, SlotPlane
 from .restrict_policies import FrequencyRestrictPolicy, RestrictPolicy, TimestampRestrictPolicy
 from .sharded import PeerShardedVariable, ShardedVariable
 from . import layers
@@ -22,5 +22,5 @@ __all__ = [
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
     "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy", "TrainableWrapper", "ModelMode",
     "enable_inference_mode", "enable_train_mode", "get_model_mode", "trainable_wrapper_filter", "shadow_ops",
-    "ComposedOptimizer", "math", "data_flow", "FileSystemSaver", "FileSystemSaverConfig", "DynamicEmbeddingSaver",
+    "ComposedOptimizer", "SlotPlane", "math", "data_flow", "FileSystemSaver", "FileSystemSaverConfig", "DynamicEmbeddingSaver",
 ]

@@ -26,8 +26,69 @@ def _init_rows(params, n, device):
   return params.tables[0]._default_value.to(device).contiguous(), 0
 
 
+class SlotPlane(object):
+  """One optimizer slot of a fused optimizer: plane `plane` of the variable's own tables, presented like the slot
+  Variable the reference keeps in its own table `<var>/<opt>/<slot>` (dynamic_embedding_optimizer.py:870-958) -- enough
+  of a Variable for checkpointing (`Variable.get_slot_variables(opt)` -> save / restore like any variable) and for
+  inspection (`export`, `size`).  Restore the variable itself first: a slot row is only kept for keys of the table."""
+
+  def __init__(self, params, plane, opt_name, slot_name):
+    self.params, self.plane, self.slot_name = params, int(plane), slot_name
+    self.name = "%s/%s/%s" % (params.name, opt_name, slot_name)
+    self.dim, self.value_dtype, self.key_dtype, self.trainable = params.dim, torch.float32, params.key_dtype, False
+
+  def size(self):
+    return self.params.size()
+
+  def export(self):
+    ks, vs = zip(*[t.export(plane=self.plane) for t in self.params.tables])
+    return torch.cat(ks), torch.cat(vs)
+
+  def upsert(self, keys, values):
+    """slot rows for keys of the variable (keys the variable does not hold are skipped)"""
+    grouped, perm, bounds = self.params._partition(keys.reshape(-1))
+    values = values.reshape(-1, self.dim).to(torch.float32)
+    if perm is not None:
+      from .variable import gather_rows
+      values = gather_rows(values.contiguous(), perm)
+    for idx, (b, e) in enumerate(bounds):
+      if e > b:
+        self.params.tables[idx].import_plane(self.plane, grouped[b:e].contiguous(), values[b:e].contiguous())
+
+  def _file_name(self, idx, proc_size, proc_rank):
+    return "%s_mht_%dof%d_rank%d_size%d" % (self.name.replace("/", "_"), idx + 1, self.params.shard_num, proc_rank, proc_size)
+
+  def save_to_file_system(self, dirpath, proc_size=1, proc_rank=0, dirpath_env="TFRA_SAVED_KV", append_to_file=False,
+                          buffer_size=4194304, name=None):
+    for idx, t in enumerate(self.params.tables):
+      t.save_plane_to_file_system(self.plane, dirpath, self._file_name(idx, proc_size, proc_rank), dirpath_env=dirpath_env,
+                                  append_to_file=append_to_file, buffer_size=buffer_size)
+
+  def load_from_file_system(self, dirpath, proc_size=1, proc_rank=0, dirpath_env="TFRA_SAVED_KV", buffer_size=4194304,
+                            name=None):
+    for idx, t in enumerate(self.params.tables):
+      t.load_plane_from_file_system(self.plane, dirpath, self._file_name(idx, proc_size, proc_rank), dirpath_env=dirpath_env,
+                                    buffer_size=buffer_size)
+
+
 class _FusedBase(object):
   n_slots = 0
+  opt_name = "Fused"
+  slot_plane_names = ()
+
+  def slot_names(self, dim=1):
+    return list(self.slot_plane_names)
+
+  def get_slot_names(self):
+    return self.slot_names()
+
+  def slot_variables(self, params):
+    """the optimizer state of `params` as SlotPlane objects (what `Variable.get_slot_variables(opt)` returns)"""
+    self._check(params)
+    return [SlotPlane(params, k + 1, self.opt_name, n) for k, n in enumerate(self.slot_plane_names)]
+
+  def get_slot(self, params, name):
+    return self.slot_variables(params)[list(self.slot_plane_names).index(name)]
 
   def __init__(self):
     self.iterations = 0
@@ -82,6 +143,8 @@ class FusedAdagrad(_FusedBase):
   """TF Adagrad on dynamic-embedding rows: accum += g*g; var -= lr*g/(sqrt(accum)+epsilon).
   epsilon=0 is tf.compat.v1.train.AdagradOptimizer, epsilon=1e-7 the Keras optimizer."""
   n_slots = 1
+  opt_name = "Adagrad"
+  slot_plane_names = ("accumulator",)
 
   def __init__(self, learning_rate=0.001, initial_accumulator_value=0.1, epsilon=0.0):
     super().__init__()
@@ -101,6 +164,8 @@ class FusedAdam(_FusedBase):
   """TF Adam: m += (g-m)(1-b1); v += (g*g-v)(1-b2); var -= m*alpha/(sqrt(v)+eps) with
   alpha = lr*sqrt(1-b2^t)/(1-b1^t) (fp32, like ApplyAdam)."""
   n_slots = 2
+  opt_name = "Adam"
+  slot_plane_names = ("m", "v")
 
   def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-8):
     super().__init__()

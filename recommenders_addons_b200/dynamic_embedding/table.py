@@ -386,6 +386,31 @@ class CuckooHashTable(object):
     for i, prefix in enumerate(prefixes):
       _lib.check(self._lib.det_load(self._h, prefix.encode(), int(buffer_size), 1 if i == 0 else 0))
 
+  # -- optimizer slot planes (state of the fused optimizers): restore / checkpoint ---------------------------------
+  def import_plane(self, plane, keys, values):
+    """rows of slot plane `plane` (1..num_slot_planes) for keys that are in the table; others are skipped"""
+    keys = self._check_keys(keys).reshape(-1)
+    values = torch.as_tensor(values, dtype=torch.float32).to(self._device).contiguous()
+    if values.numel() != keys.numel() * self._dim:
+      raise ValueError("Expected shape %s for value, got %s" % ([keys.numel(), self._dim], list(values.shape)))
+    _lib.check(self._lib.det_import_plane(self._h, int(plane), _ptr(keys), _ptr(values), keys.numel(),
+                                          _stream_ptr(self._device)))
+
+  def save_plane_to_file_system(self, plane, dirpath, file_name, dirpath_env="TFRA_SAVED_KV", append_to_file=False,
+                                buffer_size=4194304):
+    dirpath = os.environ.get(dirpath_env) or dirpath
+    os.makedirs(dirpath, exist_ok=True)
+    if self._device.type == "cuda":
+      torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_save_plane(self._h, int(plane), os.path.join(dirpath, file_name).encode(), int(buffer_size),
+                                        1 if append_to_file else 0))
+
+  def load_plane_from_file_system(self, plane, dirpath, file_name, dirpath_env="TFRA_SAVED_KV", buffer_size=4194304):
+    dirpath = os.environ.get(dirpath_env) or dirpath
+    if self._device.type == "cuda":
+      torch.cuda.current_stream(self._device).synchronize()
+    _lib.check(self._lib.det_load_plane(self._h, int(plane), os.path.join(dirpath, file_name).encode(), int(buffer_size)))
+
   def close(self):
     if getattr(self, "_h", None) is not None and self._h:
       self._lib.det_table_destroy(self._h)

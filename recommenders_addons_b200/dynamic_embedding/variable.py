@@ -405,7 +405,7 @@ class Variable(object):
 
   def get_slot_variables(self, optimizer):
     """:1155-1186: the slot Variables `optimizer` keeps for this variable.  The fused optimizers keep their slots in
-    planes of this variable's own tables (exported with `tables[i].export(plane=k)`): they have no slot Variables."""
+    planes of this variable's own tables and hand out `SlotPlane` views of them (same save / restore / export calls)."""
     if hasattr(optimizer, "slot_variables"):
       return optimizer.slot_variables(self)
     if hasattr(optimizer, "apply_gradients"):

@@ -319,3 +319,54 @@ def test_read_only_ops_are_cuda_graph_capturable():
 
 def K(a):
   return torch.as_tensor(np.asarray(a, dtype=np.int64), device=DEV)
+
+
+@pytest.mark.parametrize("kind", ["adagrad", "adam"])
+def test_fused_optimizer_state_survives_a_checkpoint(kind, tmp_path):
+  """checkpoint round trip of a training run (dynamic_embedding_optimizer_test.py:1262-1470): the variable AND the
+  optimizer slots are saved (`Variable.get_slot_variables(opt)`, one raw file pair per slot like the reference's slot
+  tables), restored into a fresh variable, and training continues BIT-IDENTICALLY to the uninterrupted run"""
+  de = _de()
+  rng = np.random.default_rng(9)
+  steps = [(rng.choice(V, 12, replace=False).astype(np.int64), rng.normal(0, 1, (12, DIM)).astype(np.float32)) for _ in range(6)]
+  make = (lambda: de.FusedAdagrad(0.1, 0.1)) if kind == "adagrad" else (lambda: de.FusedAdam(0.01))
+  planes = 1 if kind == "adagrad" else 2
+
+  def run(var, opt, part):
+    for ids, g in part:
+      opt.apply_gradients([(torch.as_tensor(g, device=DEV), (var, torch.as_tensor(ids, device=DEV)))])
+
+  ref = de.get_variable("ckpt-ref-" + kind, dim=DIM, initializer=0.25, devices=[DEV], num_slot_planes=planes)
+  ropt = make()
+  run(ref, ropt, steps)
+  a = de.get_variable("ckpt-" + kind, dim=DIM, initializer=0.25, devices=[DEV], num_slot_planes=planes)
+  aopt = make()
+  run(a, aopt, steps[:3])
+  slots = a.get_slot_variables(aopt)
+  assert [s.slot_name for s in slots] == (["accumulator"] if kind == "adagrad" else ["m", "v"])
+  assert slots[0].name == "ckpt-%s/%s/%s" % (kind, "Adagrad" if kind == "adagrad" else "Adam", slots[0].slot_name)
+  a.save_to_file_system(str(tmp_path))
+  for s in slots:
+    s.save_to_file_system(str(tmp_path))
+  # a fresh process: new variable of the same name and topology, new optimizer object with the step counter restored
+  from recommenders_addons_b200.dynamic_embedding import variable as VM
+  VM._VARIABLES.pop("ckpt-" + kind)
+  b = de.get_variable("ckpt-" + kind, dim=DIM, initializer=0.25, devices=[DEV], num_slot_planes=planes)
+  bopt = make()
+  bopt.iterations = aopt.iterations
+  b.load_from_file_system(str(tmp_path))
+  for s in b.get_slot_variables(bopt):
+    s.load_from_file_system(str(tmp_path))
+  for sa, sb in zip(slots, b.get_slot_variables(bopt)):
+    ka, va = sa.export()
+    kb, vb = sb.export()
+    oa, ob = torch.argsort(ka), torch.argsort(kb)
+    assert torch.equal(ka[oa], kb[ob]) and torch.equal(va[oa], vb[ob])
+  run(b, bopt, steps[3:])
+  q = torch.arange(V, device=DEV)
+  assert torch.equal(b.lookup(q), ref.lookup(q))
+  # a slot row can also be written directly (restore from another source); keys the variable does not hold are skipped
+  sp = b.get_slot_variables(bopt)[0]
+  sp.upsert(torch.as_tensor([int(steps[0][0][0]), 10**9], device=DEV), torch.full((2, DIM), 7.0, device=DEV))
+  k, v = sp.export()
+  assert bool((v[k == int(steps[0][0][0])] == 7.0).all()) and int(b.size()) == int(k.numel())

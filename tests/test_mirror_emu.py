@@ -212,3 +212,8 @@ def test_file_system_saver_reshards_on_restore(tmp_path):
     de.FileSystemSaverConfig(proc_size=2)
   with pytest.raises(RuntimeError):
     de.CuckooHashTableCreator(saver=object())
+
+
+@pytest.mark.parametrize("kind", ["adagrad", "adam"])
+def test_fused_optimizer_state_survives_a_checkpoint(kind, tmp_path):
+  CG.test_fused_optimizer_state_survives_a_checkpoint(kind, tmp_path)
