@@ -84,7 +84,8 @@ class _FusedBase(object):
 
   def slot_variables(self, params):
     """the optimizer state of `params` as SlotPlane objects (what `Variable.get_slot_variables(opt)` returns)"""
-    self._check(params)
+    if not isinstance(params, Variable) or any(t._num_slot_planes < self.n_slots for t in params.tables):
+      return []   # a variable without slot planes cannot hold this optimizer's state
     return [SlotPlane(params, k + 1, self.opt_name, n) for k, n in enumerate(self.slot_plane_names)]
 
   def get_slot(self, params, name):
