@@ -3,7 +3,7 @@
 from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreator, DynamicEmbeddingSaver,
                     FileSystemSaver, FileSystemSaverConfig, HkvEvictStrategy, HkvHashTable, HkvHashTableConfig,
                     HkvHashTableCreator, KVCreator)
-from .variable import (ModelMode, TrainableWrapper, Variable, default_partition_fn, embedding_lookup,
+from .variable import (GraphKeys, ModelMode, TrainableWrapper, Variable, default_partition_fn, embedding_lookup,
                        embedding_lookup_unique, enable_inference_mode, enable_train_mode, get_model_mode, get_variable,
                        segment_reduce, trainable_wrapper_filter, unique)
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
@@ -14,6 +14,7 @@ from . import layers
 from . import shadow_ops
 from . import math
 from . import data_flow
+from . import keras
 
 __all__ = [
     "CuckooHashTable", "CuckooHashTableConfig", "CuckooHashTableCreator", "HkvEvictStrategy", "HkvHashTable", "HkvHashTableConfig",
@@ -22,5 +23,5 @@ __all__ = [
     "safe_embedding_lookup_sparse", "DynamicEmbeddingOptimizer", "FusedAdagrad", "FusedAdam", "ShardedVariable", "PeerShardedVariable", "layers",
     "RestrictPolicy", "TimestampRestrictPolicy", "FrequencyRestrictPolicy", "TrainableWrapper", "ModelMode",
     "enable_inference_mode", "enable_train_mode", "get_model_mode", "trainable_wrapper_filter", "shadow_ops",
-    "ComposedOptimizer", "SlotPlane", "math", "data_flow", "FileSystemSaver", "FileSystemSaverConfig", "DynamicEmbeddingSaver",
+    "ComposedOptimizer", "SlotPlane", "math", "data_flow", "keras", "GraphKeys", "FileSystemSaver", "FileSystemSaverConfig", "DynamicEmbeddingSaver",
 ]

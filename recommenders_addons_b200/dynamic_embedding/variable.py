@@ -413,6 +413,13 @@ class Variable(object):
     raise TypeError("Expect an optimizer, but get {}".format(type(optimizer)))
 
 
+class GraphKeys(object):
+  """dynamic_embedding_variable.py:453-478 (deprecated there too): names of the graph collections the reference used
+  to register Variables in; kept so that code referring to the constants keeps importing."""
+  DYNAMIC_EMBEDDING_VARIABLES = "dynamic_embedding_variables"
+  TRAINABLE_DYNAMIC_EMBEDDING_VARIABLES = "trainable_dynamic_embedding_variables"
+
+
 class ModelMode(object):
   """The global train / inference switch (python/ops/embedding_weights.py:98-120).  In INFERENCE mode a lookup builds
   no trainable scratch and `TrainableWrapper.update_op` writes nothing back: the table is read-only."""
