@@ -390,6 +390,16 @@ class Variable(object):
   def embedding_lookup(self, ids, name=None, max_norm=None, return_trainable=False):
     return embedding_lookup(self, ids, name=name, max_norm=max_norm, return_trainable=return_trainable)
 
+  def verify_embedding_weights(self, sparse_ids, sparse_weights=None):
+    """:694-696 -> EmbeddingWeights.verify_embedding_param_weights (embedding_weights.py:78-95)"""
+    from .ops import verify_embedding_param_weights
+    verify_embedding_param_weights(self, sparse_ids, sparse_weights)
+
+  @staticmethod
+  def verify_embedding_param_weights(embedding_weights, sparse_ids, sparse_weights=None):
+    from .ops import verify_embedding_param_weights
+    verify_embedding_param_weights(embedding_weights, sparse_ids, sparse_weights)
+
   @property
   def trainable_store(self):
     """name -> ShadowVariable registered on this variable (:1260-1262)"""

@@ -144,3 +144,20 @@ def test_int_float_and_random_init():
   t.upsert(T([0, 1, 2]), torch.tensor([[0.0], [1.0], [2.0]]))
   res = t.lookup(T([0, 1, 3]))
   assert res[:2].tolist() == [[0.0], [1.0]] and res[2].item() != -1.0 and 0.0 <= res[2].item() < 1.0
+
+
+def test_verify_embedding_weights_is_a_variable_method():
+  """EmbeddingWeights.verify_embedding_weights / verify_embedding_param_weights (embedding_weights.py:53, 78-95;
+  Variable's implementation dynamic_embedding_variable.py:694-696): key dtype vs ids, value dtype vs weights"""
+  from recommenders_addons_b200 import dynamic_embedding as de
+  var = _var("verify-1", value_dtype=torch.float32, initializer=0.0, dim=4)
+  ids = de.SparseIds(torch.tensor([[0, 0], [1, 0]]), T([3, 4]), (2, 1))
+  w = de.SparseIds(ids.indices, torch.tensor([1.0, 2.0]), ids.dense_shape)
+  var.verify_embedding_weights(ids, w)
+  de.Variable.verify_embedding_param_weights(var, ids)
+  with pytest.raises(TypeError, match="key_dtype should be same with sparse_ids.dtype"):
+    var.verify_embedding_weights(de.SparseIds(ids.indices, T([3, 4], I32), ids.dense_shape))
+  with pytest.raises(TypeError, match="value_dtype should be same with sparse_weights.dtype"):
+    var.verify_embedding_weights(ids, de.SparseIds(ids.indices, torch.tensor([1.0, 2.0], dtype=torch.float64), ids.dense_shape))
+  with pytest.raises(ValueError, match="Missing embedding_weights"):
+    de.Variable.verify_embedding_param_weights(None, ids)
