@@ -5,7 +5,7 @@ from .table import (CuckooHashTable, CuckooHashTableConfig, CuckooHashTableCreat
                     HkvHashTableCreator, KVCreator)
 from .variable import (GraphKeys, ModelMode, TrainableWrapper, Variable, default_partition_fn, embedding_lookup,
                        embedding_lookup_unique, enable_inference_mode, enable_train_mode, get_model_mode, get_variable,
-                       segment_reduce, trainable_wrapper_filter, unique)
+                       load_de_variable_from_file_system, make_partition, segment_reduce, trainable_wrapper_filter, unique)
 from .ops import SparseIds, embedding_lookup_sparse, safe_embedding_lookup_sparse
 from .optimizer import ComposedOptimizer, DynamicEmbeddingOptimizer, FusedAdagrad, FusedAdam, SlotPlane
 from .restrict_policies import FrequencyRestrictPolicy, RestrictPolicy, TimestampRestrictPolicy

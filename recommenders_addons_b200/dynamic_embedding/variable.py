@@ -20,6 +20,24 @@ def default_partition_fn(keys, shard_num, gpu_mode=True):
   return torch.remainder(keys, shard_num).to(torch.int32)
 
 
+def make_partition(data, partition_index, shard_num, name=None):
+  """dynamic_embedding_variable.py:131-154: (data split by partition_index, original positions of every split), or
+  ([data], None) for one shard.  `Variable` itself uses the fused stable partition (`partition` / det_partition)."""
+  if shard_num <= 1:
+    return [data], None
+  from .data_flow import dynamic_partition
+  parts = dynamic_partition(data, partition_index, shard_num)
+  idx = dynamic_partition(torch.arange(data.shape[0], device=data.device), partition_index, shard_num)
+  return parts, idx
+
+
+def load_de_variable_from_file_system(var, dirpath, proc_size=1, proc_rank=0, buffer_size=4194304):
+  """dynamic_embedding_variable.py:200-450 (reshard-on-load): every saved shard of `var`, whatever topology wrote it,
+  re-partitioned onto the current shards -- Variable.load_from_file_system_with_restore_function."""
+  return var.load_from_file_system_with_restore_function(dirpath, proc_size=proc_size, proc_rank=proc_rank,
+                                                          buffer_size=buffer_size)
+
+
 def unique(ids):
   """tf.unique on the GPU: (unique values in first-occurrence order, int32 index of each id)."""
   flat = ids.reshape(-1).contiguous()

@@ -281,3 +281,14 @@ def test_export_list_of_the_reference_is_importable():
   out_of_scope = ["RedisTable", "RedisTableConfig", "RedisTableCreator", "DistributedVariableWrapper", "DEResourceVariable",
                   "train"]
   assert [n for n in out_of_scope if hasattr(de, n)] == []
+
+
+def test_make_partition_like_the_reference():
+  """dynamic_embedding_variable.py:131-154: data and positions split by partition index, in order; one shard = as is"""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  data = torch.tensor([50, 60, 70, 80, 90])
+  parts, idx = de.make_partition(data, torch.tensor([1, 0, 1, 2, 0]), 3)
+  assert [p.tolist() for p in parts] == [[60, 90], [50, 70], [80]] and [i.tolist() for i in idx] == [[1, 4], [0, 2], [3]]
+  parts, idx = de.make_partition(data, None, 1)
+  assert parts[0] is data and idx is None
