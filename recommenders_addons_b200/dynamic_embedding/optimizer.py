@@ -34,7 +34,9 @@ class SlotPlane(object):
 
   def __init__(self, params, plane, opt_name, slot_name):
     self.params, self.plane, self.slot_name = params, int(plane), slot_name
-    self.name = "%s/%s/%s" % (params.name, opt_name, slot_name)
+    # create_slots (dynamic_embedding_optimizer.py:882-885)
+    self.name = ("%s/%s" % (params.name, slot_name)) if getattr(params, "short_file_name", False) else \
+        "%s/%s/%s" % (params.name, opt_name, slot_name)
     self.dim, self.value_dtype, self.key_dtype, self.trainable = params.dim, torch.float32, params.key_dtype, False
 
   def size(self):
@@ -248,7 +250,8 @@ class ComposedOptimizer(object):
       for k, init in self._slot_init.items():
         made[k] = Variable(key_dtype=params.key_dtype, value_dtype=params.value_dtype, dim=params.dim,
                            devices=[str(d) for d in params.devices], partitioner=params.partition_fn,
-                           name="%s/%s/%s" % (params.name, self._cls.__name__, k), initializer=init, trainable=False,
+                           name=("%s/%s" % (params.name, k)) if getattr(params, "short_file_name", False) else
+                           "%s/%s/%s" % (params.name, self._cls.__name__, k), initializer=init, trainable=False,
                            init_size=params.init_size, kv_creator=params.kv_creator)
       self._slots[params.name] = made
       # create_slots (dynamic_embedding_optimizer.py:870-958): a restrict policy shrinks the slot tables with the variable

@@ -430,8 +430,21 @@ class HkvHashTable(CuckooHashTable):
   core/kernels/lookup_impl/lookup_table_op_hkv.h:519-535)."""
 
   def __init__(self, key_dtype, value_dtype, default_value, name="HkvHashTable", checkpoint=True, init_size=0,
-               config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
-    cfg = config if config is not None else HkvHashTableConfig()
+               config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0, init_capacity=None,
+               max_capacity=None, max_hbm_for_values=None, evict_strategy=None, step_per_epoch=0, gen_scores_fn=None,
+               reserved_key_start_bit=0):
+    # hkv_hashtable_ops.py:66-136: the capacity / eviction attributes may be given directly; a config, when given,
+    # overrides every one of them
+    if config is not None:
+      cfg = config
+    else:
+      cfg = HkvHashTableConfig(max_hbm_for_values=max_hbm_for_values, evict_strategy=evict_strategy,
+                               step_per_epoch=step_per_epoch, gen_scores_fn=gen_scores_fn,
+                               reserved_key_start_bit=reserved_key_start_bit)
+      if init_capacity is not None:
+        cfg.init_capacity = init_capacity
+      if max_capacity is not None:
+        cfg.max_capacity = max_capacity
     strategy = cfg.evict_strategy
     if strategy is not None:
       strategy = HkvEvictStrategy(int(strategy))

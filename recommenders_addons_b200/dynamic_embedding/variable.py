@@ -161,8 +161,9 @@ class Variable(object):
   def __init__(self, key_dtype=torch.int64, value_dtype=torch.float32, dim=1, devices=None,
                partitioner=default_partition_fn, shared_name=None, name="DynamicEmbedding_Variable",
                initializer=None, trainable=True, checkpoint=True, init_size=0, kv_creator=None,
-               restrict_policy=None, bp_v2=False, num_slot_planes=0):
+               restrict_policy=None, bp_v2=False, num_slot_planes=0, short_file_name=False):
     self.key_dtype = key_dtype
+    self.short_file_name = bool(short_file_name)   # :553-562: slot variables are named <var>/<slot>, not <var>/<opt>/<slot>
     self.value_dtype = value_dtype
     self.dim = int(dim)
     self.bp_v2 = bp_v2
@@ -583,14 +584,15 @@ def embedding_lookup_unique(params, ids, partition_strategy=None, name=None, val
 def get_variable(name, key_dtype=torch.int64, value_dtype=torch.float32, dim=1, devices=None,
                  partitioner=default_partition_fn, shared_name="get_variable", initializer=None, trainable=True,
                  checkpoint=True, init_size=0, kv_creator=None, restrict_policy=None, bp_v2=False,
-                 num_slot_planes=0):
+                 num_slot_planes=0, short_file_name=False):
   """de.get_variable (:1265-1359): one Variable per name."""
   if name in _VARIABLES:
     raise ValueError("Variable %s has already existed." % name)
   var = Variable(key_dtype=key_dtype, value_dtype=value_dtype, dim=dim, devices=devices, partitioner=partitioner,
                  shared_name=shared_name, name=name, initializer=initializer, trainable=trainable,
                  checkpoint=checkpoint, init_size=init_size, kv_creator=kv_creator,
-                 restrict_policy=restrict_policy, bp_v2=bp_v2, num_slot_planes=num_slot_planes)
+                 restrict_policy=restrict_policy, bp_v2=bp_v2, num_slot_planes=num_slot_planes,
+                 short_file_name=short_file_name)
   _VARIABLES[name] = var
   return var
 

@@ -217,3 +217,23 @@ def test_file_system_saver_reshards_on_restore(tmp_path):
 @pytest.mark.parametrize("kind", ["adagrad", "adam"])
 def test_fused_optimizer_state_survives_a_checkpoint(kind, tmp_path):
   CG.test_fused_optimizer_state_survives_a_checkpoint(kind, tmp_path)
+
+
+def test_hkv_table_takes_the_capacity_attributes_directly_and_short_file_name_names_slots():
+  """hkv_hashtable_ops.py:66-136 (init_capacity / max_capacity / evict_strategy ... as constructor arguments, a config
+  overriding them) and `short_file_name` (dynamic_embedding_variable.py:553-562, dynamic_embedding_optimizer.py:882-885)"""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  t = de.HkvHashTable(torch.int64, torch.float32, [0.0] * 4, name="hkv-direct", init_capacity=256, max_capacity=256,
+                      evict_strategy=de.HkvEvictStrategy.LFU, device="cpu")
+  assert t.evict_strategy == de.HkvEvictStrategy.LFU and int(t.capacity()) == 256
+  t.insert(torch.arange(10), torch.ones(10, 4))
+  assert int(t.size()) == 10
+  cfg = de.HkvHashTableConfig(init_capacity=512, max_capacity=512, evict_strategy=de.HkvEvictStrategy.LRU)
+  t2 = de.HkvHashTable(torch.int64, torch.float32, [0.0] * 4, name="hkv-config-wins", init_capacity=64, max_capacity=64,
+                       evict_strategy=de.HkvEvictStrategy.LFU, config=cfg, device="cpu")
+  assert t2.evict_strategy == de.HkvEvictStrategy.LRU and int(t2.capacity()) == 512
+  var = de.get_variable("sfn", dim=4, initializer=0.0, devices=["cpu"], num_slot_planes=1, short_file_name=True)
+  assert [s.name for s in var.get_slot_variables(de.FusedAdagrad(0.1))] == ["sfn/accumulator"]
+  var2 = de.get_variable("lfn", dim=4, initializer=0.0, devices=["cpu"], num_slot_planes=1)
+  assert [s.name for s in var2.get_slot_variables(de.FusedAdagrad(0.1))] == ["lfn/Adagrad/accumulator"]
