@@ -7,7 +7,7 @@ import torch
 
 from .optimizer import ComposedOptimizer, _FusedBase
 from .sharded import PeerShardedVariable
-from .variable import Variable, default_partition_fn, embedding_lookup_unique, unique
+from .variable import Variable, default_partition_fn, embedding_lookup_unique, gather_unique, unique
 
 
 class Embedding(torch.nn.Module):
@@ -16,7 +16,7 @@ class Embedding(torch.nn.Module):
   def __init__(self, embedding_size, key_dtype=torch.int64, value_dtype=torch.float32, combiner="sum", initializer=None,
                devices=None, name="DynamicEmbeddingLayer", with_unique=True, trainable=True, bp_v2=False,
                init_capacity=0, partitioner=default_partition_fn, kv_creator=None, max_norm=None, num_slot_planes=2,
-               restrict_policy=None):
+               restrict_policy=None, short_file_name=False):
     super().__init__()
     if combiner not in ("sum", "mean", "sqrtn"):
       raise ValueError("combiner must be one of 'mean', 'sqrtn' or 'sum'")
@@ -27,8 +27,19 @@ class Embedding(torch.nn.Module):
     self.params = Variable(key_dtype=key_dtype, value_dtype=value_dtype, dim=self.embedding_size, devices=devices,
                            partitioner=partitioner, name=name, initializer=initializer, trainable=trainable,
                            init_size=init_capacity, kv_creator=kv_creator, bp_v2=bp_v2, restrict_policy=restrict_policy,
-                           num_slot_planes=num_slot_planes if value_dtype == torch.float32 else 0)
+                           num_slot_planes=num_slot_planes if value_dtype == torch.float32 else 0,
+                           short_file_name=short_file_name)
     self._wrappers = []
+
+  def call(self, ids):
+    """the Keras entry point of the reference layer (embedding.py:300-335)"""
+    return self.forward(ids)
+
+  def get_config(self):
+    """embedding.py:327-335"""
+    return {"embedding_size": self.embedding_size, "key_dtype": self.params.key_dtype, "value_dtype": self.params.value_dtype,
+            "combiner": self.combiner, "initializer": self.params.initializer, "devices": self.params.devices,
+            "name": self.params.name, "with_unique": self.with_unique}
 
   def forward(self, ids):
     out, tw = embedding_lookup_unique(self.params, ids, max_norm=self.max_norm, return_trainable=True)
@@ -100,10 +111,18 @@ class AllToAllEmbedding(torch.nn.Module):
   forward: unique -> det_peer_find -> gather; apply_gradients: per-unique gradients routed to their owners
   (det_peer_route), combined and stepped there."""
 
-  def __init__(self, embedding_size, capacity_per_shard, group=None, initializer=None, name="AllToAllEmbedding",
-               num_slot_planes=2):
+  def __init__(self, embedding_size, capacity_per_shard=None, group=None, initializer=None, name="AllToAllEmbedding",
+               num_slot_planes=2, with_unique=True, with_secondary_unique=True, mpi_size=None, batch_size=None,
+               key_dtype=torch.int64, value_dtype=torch.float32, init_capacity=0, **kwargs):
+    """The reference's arguments (embedding.py:545-563: with_unique, with_secondary_unique, mpi_size, batch_size and the
+    base layer's) are accepted; the world size comes from `group`, lookups always dedupe once (unique -> one-sided
+    find), and a published shard has a FIXED capacity: capacity_per_shard (default: init_capacity, else 1M slots)."""
     super().__init__()
+    if key_dtype != torch.int64 or value_dtype != torch.float32:
+      raise TypeError("AllToAllEmbedding: int64 keys and float32 rows")
     self.embedding_size = int(embedding_size)
+    self.with_unique, self.with_secondary_unique, self.batch_size = with_unique, with_secondary_unique, batch_size
+    capacity_per_shard = int(capacity_per_shard or init_capacity or (1 << 20))
     self.params = PeerShardedVariable.create(self.embedding_size, capacity_per_shard, group=group,
                                              initializer=initializer, num_slot_planes=num_slot_planes, name=name)
     self._pending = []
@@ -117,7 +136,7 @@ class AllToAllEmbedding(torch.nn.Module):
     rows = rows.detach().requires_grad_(self.training)
     if self.training:
       self._pending.append((uniq, rows))
-    return rows[idx.long()].reshape(tuple(ids.shape) + (self.embedding_size,))
+    return gather_unique(rows, idx).reshape(tuple(ids.shape) + (self.embedding_size,))
 
   def apply_gradients(self, optimizer, max_unique_per_rank=None):
     for uniq, rows in self._pending:
