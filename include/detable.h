@@ -203,6 +203,19 @@ size_t det_segment_reduce_workspace_bytes(size_t n, size_t n_groups);
 det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim,
                               float* out, void* workspace, size_t workspace_bytes, det_stream_t stream);
 
+/* The tail of embedding_lookup_sparse when the unique rows are a DENSE matrix (training: the TrainableWrapper's scratch,
+ * python/ops/dynamic_embedding_ops.py:247-289 -- gather(embeddings, idx) * weights -> segment_sum -> normalise; TF's
+ * sparse_segment_sum / mean / sqrt_n): out[b] = combine_{i in segment b} weights[i] * rows[row_idx[i]], the ids of a
+ * segment added in order (same arithmetic and kernels as det_lookup_sparse's second phase; the [nnz, dim] gather is
+ * never materialised).  rows fp32 [n_rows, dim]; row_idx int64 [nnz] (the idx of det_unique, widened; < 0 reads
+ * default_row [dim]); segment_ids int32 [nnz] ascending in [0, batch); weights [nnz] or NULL; out fp32 [batch, dim].
+ * Indices must lie in [.., n_rows): they are not checked.  workspace: det_sparse_segment_sum_workspace_bytes(batch).
+ * Asynchronous on `stream`.  ABI >= 4. */
+size_t det_sparse_segment_sum_workspace_bytes(size_t batch);
+det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* row_idx, const int32_t* segment_ids,
+                                  const float* weights, size_t nnz, size_t batch, int combiner, const float* default_row,
+                                  float* out, void* workspace, size_t workspace_bytes, det_stream_t stream);
+
 /* embedding_lookup_sparse forward, fused (python/ops/dynamic_embedding_ops.py:219-291): a slot-resolve pass
  * (8 B per id) + ONE gather/weight/segment-sum/normalise pass -- the reference's [nnz, dim] gather, its weighted
  * copy and the segment_sum input are never materialised:

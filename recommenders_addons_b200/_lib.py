@@ -57,6 +57,8 @@ SIGNATURES = {
     "det_unique": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
     "det_segment_reduce_workspace_bytes": (_sz, [_sz, _sz]),
     "det_segment_reduce": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _sz, _vp]),
+    "det_sparse_segment_sum_workspace_bytes": (_sz, [_sz]),
+    "det_sparse_segment_sum": (_i, [_vp, _sz, _vp, _vp, _vp, _sz, _sz, _i, _vp, _vp, _vp, _sz, _vp]),
     "det_lookup_sparse": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp, _vp, _vp]),
     "det_lookup_sparse_clip": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp, ctypes.c_float, _vp, _vp]),
     "det_apply_adagrad": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, _vp, _i, ctypes.c_float, _vp]),

@@ -1585,6 +1585,72 @@ det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, s
   return permute_rows(rows_in, perm, n, row_bytes, rows_out, false, (cudaStream_t)stream);
 }
 
+// tf.sparse.segment_{sum,mean,sqrt_n} with weights over a DENSE row matrix: the tail of embedding_lookup_sparse in
+// TRAINING, where the unique rows live in the TrainableWrapper's scratch (python/ops/dynamic_embedding_ops.py:247-289:
+// gather(embeddings, idx) * weights -> segment_sum -> / sum(w) | / sqrt(sum(w^2))).  The gather, its weighted copy and
+// the segment reduction are ONE pass of the kernels det_lookup_sparse uses for its phase B (segment_sum_kernel /
+// segment_sum_wide_kernel, or the staged variant under DET_SEGSUM_STAGED=1) over a view whose "table" is the matrix.
+size_t det_sparse_segment_sum_workspace_bytes(size_t batch) {
+  return align256((batch + 1) * sizeof(long long)) + align256(sizeof(DevState));
+}
+
+det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* row_idx, const int32_t* segment_ids,
+                                  const float* weights, size_t nnz, size_t batch, int combiner, const float* default_row,
+                                  float* out, void* workspace, size_t workspace_bytes, det_stream_t stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (batch == 0 || dim == 0) return DET_OK;
+  if (!out || !workspace || !default_row) return fail(DET_INVALID_ARGUMENT, "det_sparse_segment_sum: null out/workspace/default_row");
+  if (nnz && (!rows || !row_idx || !segment_ids)) return fail(DET_INVALID_ARGUMENT, "det_sparse_segment_sum: null argument");
+  if (combiner < DET_COMBINER_SUM || combiner > DET_COMBINER_SQRTN) return fail(DET_INVALID_ARGUMENT, "det_sparse_segment_sum: bad combiner");
+  if (workspace_bytes < det_sparse_segment_sum_workspace_bytes(batch))
+    return fail(DET_INVALID_ARGUMENT, "det_sparse_segment_sum: workspace too small");
+  if (nnz >= 0x7fffffffull || dim >= 0x7fffffffull) return fail(DET_INVALID_ARGUMENT, "det_sparse_segment_sum: nnz / dim too large");
+  long long* seg_start = (long long*)workspace;
+  DevState* st = (DevState*)((unsigned char*)workspace + align256((batch + 1) * sizeof(long long)));
+  CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(DevState), s));
+  TableView v{};
+  v.planes[0] = (unsigned char*)const_cast<float*>(rows);
+  v.dim = (unsigned)dim;
+  v.row_bytes = (unsigned)dim * 4u;
+  v.st = st;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st);
+  const long long* slots = (const long long*)row_idx;
+  const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out | (uintptr_t)rows) & 15u) == 0);
+  unsigned vpr, lpr, sh;
+  fgeom((unsigned)dim, vec4, 1, &vpr, &lpr, &sh);
+  const unsigned gpw = 32u >> sh;
+  if (vpr <= lpr && vec4 && env_int("DET_SEGSUM_STAGED", 0) != 0) {
+    const size_t smem = (size_t)(kThreadsF / 32) * kWinWarpBytes;
+    int occ = 1;
+    CUDA_TRY(cudaFuncSetAttribute(segment_sum_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, segment_sum_staged_kernel, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int grid = grid_for(batch, kThreadsF / 32, sms, occ);
+#ifdef DET_EMU
+    __atomic_fetch_add(&g_det_emu_stat[2], 1ull, __ATOMIC_RELAXED);
+#endif
+    DET_LAUNCH(segment_sum_staged_kernel, grid, kThreadsF, smem, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+  } else if (vpr <= lpr) {
+    const ClipArg<false> noclip;
+    const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
+    const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), sms, occ);
+    if (vec4)
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
+    else
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
+  } else {
+    const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), sms, 8);
+    if (vec4)
+      DET_LAUNCH(segment_sum_wide_kernel<4>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+    else
+      DET_LAUNCH(segment_sum_wide_kernel<1>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DET_OK;
+}
+
 size_t det_segment_reduce_workspace_bytes(size_t n, size_t n_groups) {
   return seg_reduce_layout(n ? n : 1, n_groups ? n_groups : 1, nullptr, nullptr);
 }

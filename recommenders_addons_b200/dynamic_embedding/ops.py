@@ -17,6 +17,11 @@ class SparseIds(object):
     self.dense_shape = tuple(int(d) for d in dense_shape)
 
 
+def _table_device_types():
+  from . import table
+  return table._DEVICE_TYPES   # ("cuda",): the library only ever sees device memory
+
+
 def _fused_ok(params, default_rows):
   return (params.shard_num == 1 and params.value_dtype == torch.float32 and default_rows.numel() == params.dim)
 
@@ -46,6 +51,53 @@ def lookup_sparse_fused(params, ids, segment_ids, weights, batch, combiner, defa
                                           _lib.COMBINERS[combiner], _ptr(default_row), _ptr(out),
                                           _stream_ptr(dev)))
   return out
+
+
+class _SparseSegmentSum(torch.autograd.Function):
+  """gather(rows, idx) * weights -> segment sum -> normalise over a DENSE [U, dim] matrix (det_sparse_segment_sum: the
+  kernels of the fused forward; the ids of a segment are added in order, so the result is deterministic and
+  bit-identical to the oracle).  Differentiable w.r.t. rows: d rows[u] = sum over the ids i of u of
+  gout[seg_i] * w_i / norm[seg_i], summed by `combine_rows` (the reference's gradient dedupe)."""
+
+  @staticmethod
+  def forward(ctx, rows, idx, seg, weights, batch, combiner):
+    dev = rows.device
+    rows_c = rows.contiguous()
+    idx64 = idx.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+    seg32 = seg.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+    w = None if weights is None else weights.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+    dim = rows_c.shape[1]
+    out = torch.empty((batch, dim), dtype=torch.float32, device=dev)
+    lib = _lib.lib()
+    ws_bytes = lib.det_sparse_segment_sum_workspace_bytes(batch)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    zero_row = torch.zeros(dim, dtype=torch.float32, device=dev)
+    _lib.check(lib.det_sparse_segment_sum(_ptr(rows_c), dim, _ptr(idx64), _ptr(seg32), _ptr(w), idx64.numel(), batch,
+                                          _lib.COMBINERS[combiner], _ptr(zero_row), _ptr(out), _ptr(ws), ws_bytes,
+                                          _stream_ptr(dev)))
+    ctx.save_for_backward(idx64, seg32, w if w is not None else torch.empty(0, device=dev))
+    ctx.meta = (rows_c.shape[0], batch, combiner, w is not None)
+    return out
+
+  @staticmethod
+  def backward(ctx, gout):
+    from .variable import combine_rows
+    idx64, seg32, w = ctx.saved_tensors
+    n_rows, batch, combiner, has_w = ctx.meta
+    seg = seg32.long()
+    coef = w if has_w else torch.ones(seg.numel(), dtype=torch.float32, device=gout.device)
+    if combiner != "sum":
+      den = torch.zeros(batch, dtype=torch.float32, device=gout.device).index_add_(0, seg, coef if combiner == "mean" else coef * coef)
+      if combiner == "sqrtn":
+        den = den.sqrt()
+      coef = coef / den[seg]
+    g_rows = gout.to(torch.float32)[seg] * coef[:, None]
+    return combine_rows(g_rows.contiguous(), idx64.to(torch.int32), n_rows), None, None, None, None, None
+
+
+def sparse_segment_sum_rows(rows, idx, segment_ids, weights, batch, combiner):
+  """[U, dim] fp32 rows, idx [nnz] into them, ascending segment_ids [nnz] -> [batch, dim]; differentiable w.r.t. rows"""
+  return _SparseSegmentSum.apply(rows, idx, segment_ids, weights, int(batch), combiner)
 
 
 def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None, name="embedding_lookup_sparse",
@@ -82,6 +134,10 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
   uniq, idx = unique(ids)
   r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)
   emb_u, tw = r if return_trainable else (r, None)
+  if emb_u.device.type in _table_device_types() and ids.numel() > 0:
+    # the dense rows of the trainable scratch go through the fused gather / weight / segment-sum kernel
+    out = sparse_segment_sum_rows(emb_u.to(torch.float32), idx, segment_ids, weights, batch, combiner)
+    return (out, tw) if return_trainable else out
   emb = gather_unique(emb_u.to(torch.float32), idx)
   seg64 = segment_ids.long().to(emb.device)
   w = torch.ones(ids.numel(), dtype=torch.float32, device=emb.device) if ignore_weights else \

@@ -303,3 +303,59 @@ def test_embedding_lookup_sparse_max_norm_fused_and_composed_agree():
     var2 = de.get_variable("mn-ref-%d" % dim, dim=dim, initializer=0.0, devices=["cpu"])
     var2.upsert(keys, clipped)
     _close(got, de.embedding_lookup_sparse(var2, sp, sw, combiner="mean"))
+
+
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+@pytest.mark.parametrize("use_w", [False, True])
+@pytest.mark.parametrize("dim", [4, 5, 64, 132])
+def test_trainable_sparse_lookup_runs_the_fused_segment_sum_and_its_backward(combiner, use_w, dim):
+  """training flavour of embedding_lookup_sparse (dynamic_embedding_ops.py:247-289; optimizer tests :747-1005): the
+  forward over the TrainableWrapper's dense rows is det_sparse_segment_sum -- BIT-identical to the sequential oracle --
+  and the gradient of the rows equals autograd through the plain torch restatement (float64) to 1e-6"""
+  from oracle import oracle as O
+  from recommenders_addons_b200.dynamic_embedding.ops import sparse_segment_sum_rows
+  rng = np.random.default_rng(dim * 3 + len(combiner) + use_w)
+  U, batch = 37, 23
+  lens = rng.integers(0, 7, size=batch)
+  seg = np.repeat(np.arange(batch), lens).astype(np.int32)
+  idx = rng.integers(0, U, size=seg.shape[0]).astype(np.int32)
+  w = rng.uniform(0.25, 2.0, size=seg.shape[0]).astype(np.float32) if use_w else None
+  rows = rng.normal(0, 0.5, (U, dim)).astype(np.float32)
+  t_rows = torch.tensor(rows, requires_grad=True)
+  out = sparse_segment_sum_rows(t_rows, torch.tensor(idx), torch.tensor(seg), None if w is None else torch.tensor(w), batch, combiner)
+  ot = O.PortTable(dim)
+  ot.insert(np.arange(U, dtype=np.int64), rows)
+  exp = O.embedding_lookup_sparse(ot, idx.astype(np.int64), seg, w, batch, combiner)
+  np.testing.assert_array_equal(out.detach().numpy(), exp)
+  gout = torch.tensor(rng.normal(0, 1, (batch, dim)).astype(np.float32))
+  out.backward(gout)
+  # reference gradient: autograd through gather * w -> index_add -> normalise, in float64
+  r64 = torch.tensor(rows, dtype=torch.float64, requires_grad=True)
+  w64 = torch.ones(seg.shape[0], dtype=torch.float64) if w is None else torch.tensor(w, dtype=torch.float64)
+  s64 = torch.tensor(seg, dtype=torch.int64)
+  o64 = torch.zeros((batch, dim), dtype=torch.float64).index_add(0, s64, r64[torch.tensor(idx, dtype=torch.int64)] * w64[:, None])
+  if combiner != "sum":
+    den = torch.zeros(batch, dtype=torch.float64).index_add(0, s64, w64 if combiner == "mean" else w64 * w64)
+    den = den.sqrt() if combiner == "sqrtn" else den
+    o64 = torch.where((den > 0)[:, None], o64 / den.clamp_min(1e-300)[:, None], o64)
+  o64.backward(gout.double())
+  np.testing.assert_allclose(t_rows.grad.numpy(), r64.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_embedding_lookup_sparse_trainable_path_end_to_end():
+  """de.embedding_lookup_sparse(..., return_trainable=True): values match the forward-only fused kernel bit for bit and
+  a gradient reaches the TrainableWrapper's rows"""
+  de = _de()
+  var = de.get_variable("sparse-train-e2e", devices=["cpu"], dim=8, initializer=0.0)
+  keys = torch.arange(0, 50)
+  g = torch.Generator().manual_seed(3)
+  var.upsert(keys, torch.randn(50, 8, generator=g))
+  ids = torch.tensor([3, 7, 3, 11, 49, 7, 7, 60])
+  indices = torch.tensor([[0, 0], [0, 1], [1, 0], [3, 0], [3, 1], [3, 2], [4, 0], [4, 1]])
+  sp = de.SparseIds(indices, ids, (5, 3))
+  spw = de.SparseIds(indices, torch.tensor([1.0, 2.0, 0.5, 1.0, 1.0, 3.0, 2.0, 1.0]), (5, 3))
+  fwd = de.embedding_lookup_sparse(var, sp, spw, combiner="mean")
+  out, tw = de.embedding_lookup_sparse(var, sp, spw, combiner="mean", return_trainable=True)
+  assert torch.equal(out.detach(), fwd)
+  out.sum().backward()
+  assert tw.values.grad is not None and tw.values.grad.shape == tw.values.shape and bool(tw.values.grad.abs().sum() > 0)
