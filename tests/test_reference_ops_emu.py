@@ -342,9 +342,10 @@ def test_trainable_sparse_lookup_runs_the_fused_segment_sum_and_its_backward(com
   np.testing.assert_allclose(t_rows.grad.numpy(), r64.grad.numpy(), rtol=1e-5, atol=1e-6)
 
 
-def test_embedding_lookup_sparse_trainable_path_end_to_end():
-  """de.embedding_lookup_sparse(..., return_trainable=True): values match the forward-only fused kernel bit for bit and
-  a gradient reaches the TrainableWrapper's rows"""
+def test_embedding_lookup_sparse_trainable_path_end_to_end(monkeypatch):
+  """de.embedding_lookup_sparse(..., return_trainable=True) with DET_SPARSE_TRAIN_FUSED=1: values match the forward-only
+  fused kernel bit for bit and a gradient reaches the TrainableWrapper's rows"""
+  monkeypatch.setenv("DET_SPARSE_TRAIN_FUSED", "1")
   de = _de()
   var = de.get_variable("sparse-train-e2e", devices=["cpu"], dim=8, initializer=0.0)
   keys = torch.arange(0, 50)

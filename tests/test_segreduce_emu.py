@@ -167,3 +167,8 @@ def test_property_any_shape_matches_the_sequential_sum(n, n_groups, dim, skew, s
   idx = idx.astype(np.int32)
   rows = rows_of(rng, n, dim)
   np.testing.assert_array_equal(reduce_emu(rows, idx, n_groups), O.segment_reduce(rows, idx, n_groups))
+
+
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+def test_gpu_suite_trainable_sparse_lookup_body(emu_mirror, monkeypatch, combiner):
+  SG.test_trainable_sparse_lookup_through_the_fused_segment_sum(monkeypatch, combiner)

@@ -165,3 +165,32 @@ def test_embedding_lookup_unique_backward_is_the_gradient_dedupe(monkeypatch, mo
     np.testing.assert_array_equal(got, exp)
   else:
     np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-3)   # atomics: sums of up to ~700 N(0,1) rows in any order
+
+
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+def test_trainable_sparse_lookup_through_the_fused_segment_sum(monkeypatch, combiner):
+  """DET_SPARSE_TRAIN_FUSED=1: embedding_lookup_sparse(return_trainable=True) sums the TrainableWrapper's rows with
+  det_sparse_segment_sum -- same values as the forward-only fused kernel, and the same parameters after one Adagrad
+  step as the torch restatement of the path (1e-6)"""
+  de = _de()
+  dim, vocab, batch = 16, 200, 64
+  rng = np.random.default_rng(50 + len(combiner))
+  res = []
+  for flag in ("1", "0"):
+    monkeypatch.setenv("DET_SPARSE_TRAIN_FUSED", flag)
+    var = de.Variable(dim=dim, init_size=1 << 12, initializer=0.0, num_slot_planes=1, devices=[DEV],
+                      name="sparse-train-%s-%s" % (combiner, flag))
+    var.upsert(torch.arange(vocab, device=DEV), torch.as_tensor(np.random.default_rng(1).normal(0, 0.1, (vocab, dim)).astype(np.float32), device=DEV))
+    r = np.random.default_rng(7)
+    ids = torch.as_tensor(r.integers(0, vocab, batch * 3), device=DEV)
+    ind = torch.stack([torch.arange(batch, device=DEV).repeat_interleave(3), torch.arange(3, device=DEV).repeat(batch)], 1)
+    w = torch.as_tensor(r.uniform(0.5, 2, batch * 3).astype(np.float32), device=DEV)
+    sp, sw = de.SparseIds(ind, ids, (batch, 3)), de.SparseIds(ind, w, (batch, 3))
+    out, tw = de.embedding_lookup_sparse(var, sp, sw, combiner=combiner, return_trainable=True)
+    if flag == "1":
+      assert torch.equal(out.detach(), de.embedding_lookup_sparse(var, sp, sw, combiner=combiner))
+    (out * out).sum().backward()
+    opt = de.FusedAdagrad(0.1, 0.1)
+    opt.apply_gradients([(tw.values.grad, tw)])
+    res.append(var.lookup(torch.arange(vocab, device=DEV)).cpu().numpy())
+  np.testing.assert_allclose(res[0], res[1], rtol=1e-5, atol=1e-6)
