@@ -73,6 +73,31 @@ class SlotPlane(object):
                                     buffer_size=buffer_size)
 
 
+  def load_from_file_system_with_restore_function(self, dirpath, buffer_size=4194304):
+    """reshard-on-load for a slot (the variable's own `load_from_file_system_with_restore_function` first): every
+    saved shard file of this slot, whatever topology wrote it, its rows routed to the shards that hold the keys now"""
+    import glob
+    import os
+    import re
+    import numpy as np
+    dirpath = os.environ.get("TFRA_SAVED_KV") or dirpath
+    base = self.name.replace("/", "_")
+    pat = re.compile(re.escape(base) + r"_mht_(\d+)of(\d+)_rank(\d+)_size(\d+)-keys$")
+    files = sorted(f for f in glob.glob(os.path.join(dirpath, glob.escape(base) + "_mht_*-keys")) if pat.search(os.path.basename(f)))
+    if not files:
+      raise FileNotFoundError("no saved shards of slot %s under %s" % (self.name, dirpath))
+    dev = self.params.tables[0].device
+    step = max(1, int(buffer_size))
+    for kf in files:
+      if os.path.getsize(kf) == 0:
+        continue
+      keys = np.memmap(kf, dtype=np.int64, mode="r")
+      vals = np.memmap(kf[:-len("-keys")] + "-values", dtype=np.float32, mode="r").reshape(-1, self.dim)
+      for b in range(0, keys.shape[0], step):
+        self.upsert(torch.from_numpy(np.array(keys[b:b + step])).to(dev),      # np.array: a writable copy of the chunk
+                    torch.from_numpy(np.array(vals[b:b + step])).to(dev))
+
+
 class _FusedBase(object):
   n_slots = 0
   opt_name = "Fused"

@@ -72,15 +72,22 @@ class FileSystemSaver(DynamicEmbeddingSaver):
       raise ValueError("FileSystemSaver needs a save_path (or a dirpath argument)")
     return d
 
-  def save(self, variable, dirpath=None):
+  def save(self, variable, dirpath=None, optimizer=None):
+    """`optimizer`: also write the optimizer's slots of `variable` (the reference checkpoints its slot Variables as
+    trackables of the optimizer; here `variable.get_slot_variables(optimizer)`)"""
     variable.save_to_file_system(self._dir(dirpath), proc_size=self.config.proc_size, proc_rank=self.config.proc_rank,
                                  dirpath_env="__unset__", buffer_size=self.config.buffer_size)
+    for slot in (variable.get_slot_variables(optimizer) if optimizer is not None else []):
+      slot.save_to_file_system(self._dir(dirpath), proc_size=self.config.proc_size, proc_rank=self.config.proc_rank,
+                               dirpath_env="__unset__", buffer_size=self.config.buffer_size)
 
-  def restore(self, variable, dirpath=None):
+  def restore(self, variable, dirpath=None, optimizer=None):
     """clear + load every file of the directory that belongs to this process under the CURRENT topology"""
     variable.load_from_file_system_with_restore_function(self._dir(dirpath), proc_size=self.config.proc_size,
                                                          proc_rank=self.config.proc_rank,
                                                          buffer_size=self.config.buffer_size)
+    for slot in (variable.get_slot_variables(optimizer) if optimizer is not None else []):
+      slot.load_from_file_system_with_restore_function(self._dir(dirpath), buffer_size=self.config.buffer_size)
 
 
 class KVCreator(object):

@@ -370,3 +370,38 @@ def test_fused_optimizer_state_survives_a_checkpoint(kind, tmp_path):
   sp.upsert(torch.as_tensor([int(steps[0][0][0]), 10**9], device=DEV), torch.full((2, DIM), 7.0, device=DEV))
   k, v = sp.export()
   assert bool((v[k == int(steps[0][0][0])] == 7.0).all()) and int(b.size()) == int(k.numel())
+
+
+def test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path):
+  """FileSystemSaver.save / restore with `optimizer=`: a 2-shard variable and its Adam slots are written shard by
+  shard, restored into a 3-shard variable (reshard-on-load for the rows AND the slots), and training continues
+  bit-identically to an uninterrupted single-shard run"""
+  de = _de()
+  rng = np.random.default_rng(19)
+  steps = [(rng.choice(V, 14, replace=False).astype(np.int64), rng.normal(0, 1, (14, DIM)).astype(np.float32)) for _ in range(6)]
+
+  def run(var, opt, part):
+    for ids, g in part:
+      opt.apply_gradients([(torch.as_tensor(g, device=DEV), (var, torch.as_tensor(ids, device=DEV)))])
+
+  ref = de.get_variable("fss-ref", dim=DIM, initializer=0.5, devices=[DEV], num_slot_planes=2)
+  ropt = de.FusedAdam(0.01)
+  run(ref, ropt, steps)
+  a = de.get_variable("fss", dim=DIM, initializer=0.5, devices=[DEV] * 2, num_slot_planes=2)
+  aopt = de.FusedAdam(0.01)
+  run(a, aopt, steps[:3])
+  saver = de.FileSystemSaver(save_path=str(tmp_path))
+  saver.save(a, optimizer=aopt)
+  import os
+  names = sorted(os.listdir(str(tmp_path)))
+  assert "fss_mht_1of2_rank0_size1-keys" in names and "fss_Adam_m_mht_2of2_rank0_size1-values" in names and len(names) == 12
+  from recommenders_addons_b200.dynamic_embedding import variable as VM
+  VM._VARIABLES.pop("fss")
+  b = de.get_variable("fss", dim=DIM, initializer=0.5, devices=[DEV] * 3, num_slot_planes=2)
+  bopt = de.FusedAdam(0.01)
+  bopt.iterations = aopt.iterations
+  saver.restore(b, optimizer=bopt)
+  assert int(b.size()) == int(a.size())
+  run(b, bopt, steps[3:])
+  q = torch.arange(V, device=DEV)
+  assert torch.equal(b.lookup(q), ref.lookup(q))

@@ -237,3 +237,7 @@ def test_hkv_table_takes_the_capacity_attributes_directly_and_short_file_name_na
   assert [s.name for s in var.get_slot_variables(de.FusedAdagrad(0.1))] == ["sfn/accumulator"]
   var2 = de.get_variable("lfn", dim=4, initializer=0.0, devices=["cpu"], num_slot_planes=1)
   assert [s.name for s in var2.get_slot_variables(de.FusedAdagrad(0.1))] == ["lfn/Adagrad/accumulator"]
+
+
+def test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path):
+  CG.test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path)
