@@ -405,3 +405,26 @@ def test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path
   run(b, bopt, steps[3:])
   q = torch.arange(V, device=DEV)
   assert torch.equal(b.lookup(q), ref.lookup(q))
+
+
+def test_restrict_shrinks_the_fused_optimizer_slots_with_the_variable():
+  """restrict_policies_test.py (`*_apply_restriction`: after the restriction the variable AND its slot tables hold the
+  reserved keys only): with the fused optimizers the slots are planes of the variable's own table, so removing a key
+  removes its optimizer state with it -- and a key that comes back starts from the slot initializer again"""
+  de = _de()
+  var = de.get_variable("restrict-fused", dim=DIM, initializer=0.0, devices=[DEV], num_slot_planes=1,
+                        restrict_policy=de.FrequencyRestrictPolicy)
+  opt = de.FusedAdagrad(0.1, 0.1)
+  ids = torch.arange(0, 12, device=DEV)
+  for rep in range(3):      # ids 0..3 are seen three times, 4..7 twice, 8..11 once
+    sel = ids[: 12 - 4 * rep]
+    opt.apply_gradients([(torch.ones(sel.numel(), DIM, device=DEV), (var, sel))])
+  slot = var.get_slot_variables(opt)[0]
+  assert int(var.size()) == 12 and int(slot.export()[0].numel()) == 12
+  var.restrict(4, trigger=4)
+  k, a = slot.export()
+  assert sorted(k.tolist()) == [0, 1, 2, 3] and int(var.size()) == 4
+  assert torch.allclose(a, torch.full_like(a, 0.1 + 3.0))                      # three steps of g = 1: a = 0.1 + 3 * 1
+  opt.apply_gradients([(torch.ones(1, DIM, device=DEV), (var, torch.tensor([9], device=DEV)))])   # key 9 returns
+  k, a = slot.export()
+  assert torch.allclose(a[k == 9], torch.full((1, DIM), 0.1 + 1.0, device=a.device))

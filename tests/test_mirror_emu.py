@@ -241,3 +241,7 @@ def test_hkv_table_takes_the_capacity_attributes_directly_and_short_file_name_na
 
 def test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path):
   CG.test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path)
+
+
+def test_restrict_shrinks_the_fused_optimizer_slots_with_the_variable():
+  CG.test_restrict_shrinks_the_fused_optimizer_slots_with_the_variable()
