@@ -42,6 +42,19 @@ class ShadowVariable(TrainableWrapper):
     """:189-195"""
     return self.read_value(do_prefetch=do_prefetch)
 
+  def verify_embedding_weights(self, sparse_ids, sparse_weights=None):
+    """:166-168"""
+    self.params.verify_embedding_weights(sparse_ids, sparse_weights)
+
+  def assign(self, value, use_locking=None, name=None, read_value=True):
+    """:198-226: a new value for the shadow's lookup buffer (one row per current id); `update_op` writes it back"""
+    value = torch.as_tensor(value, dtype=self.params.value_dtype, device=self.params.tables[0].device)
+    if value.numel() != self.ids.numel() * self.params.dim:
+      raise ValueError("assign: expected %d rows of %d elements, got %s" % (self.ids.numel(), self.params.dim, tuple(value.shape)))
+    value = value.reshape(self.ids.numel(), self.params.dim).detach().clone()
+    self.values = value.requires_grad_(True) if (self.trainable and value.is_floating_point()) else value
+    return self.values if read_value else None
+
   def _reset_ids(self, ids):
     """:231-232"""
     self.ids = ids

@@ -245,3 +245,25 @@ def test_file_system_saver_checkpoints_optimizer_state_across_a_reshard(tmp_path
 
 def test_restrict_shrinks_the_fused_optimizer_slots_with_the_variable():
   CG.test_restrict_shrinks_the_fused_optimizer_slots_with_the_variable()
+
+
+def test_shadow_variable_assign_and_verify():
+  """shadow_embedding_ops.py:166-168, :198-226 (kernel_tests/shadow_embedding_ops_test.py test_create / test_read_value):
+  assign replaces the lookup buffer of the current ids, update_op writes it back to the table"""
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  var = de.get_variable("shadow-assign", dim=3, initializer=0.0, devices=["cpu"])
+  sh = de.shadow_ops.ShadowVariable(var, name="sv-assign")
+  out = de.shadow_ops.embedding_lookup(sh, torch.tensor([5, 9]))
+  assert out.shape == (2, 3) and int(var.size()) == 0
+  got = sh.assign(torch.tensor([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]))
+  assert torch.equal(got.detach(), torch.tensor([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])) and torch.equal(sh.value().detach(), got.detach())
+  sh.update_op()
+  assert torch.equal(var.lookup(torch.tensor([9, 5])), torch.tensor([[4.0, 5.0, 6.0], [1.0, 2.0, 3.0]]))
+  import pytest as _pt
+  with _pt.raises(ValueError):
+    sh.assign(torch.zeros(3, 3))
+  ids = de.SparseIds(torch.tensor([[0, 0]]), torch.tensor([5]), (1, 1))
+  sh.verify_embedding_weights(ids)
+  with _pt.raises(TypeError):
+    sh.verify_embedding_weights(de.SparseIds(ids.indices, torch.tensor([5], dtype=torch.int32), (1, 1)))
