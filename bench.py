@@ -623,7 +623,37 @@ def c3_arm(args):
   t1.record()
   torch.cuda.synchronize()
   ms = t0.elapsed_time(t1) / args.steps
+  # where the step goes: the same step with CUDA events between its phases (outside the timed region)
+  phases = {"lookup_sparse": [], "unique": [], "grad_reduce": [], "apply_adagrad": []}
+  for i in range(5):
+    ids = batches[i % nb]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    lookup_sparse_fused(var, ids, seg, None, nnz, "sum")
+    ev[1].record()
+    uniq, idx = de.unique(ids)
+    ev[2].record()
+    g = de.segment_reduce(gout, idx, uniq.numel()) if args.grad_reduce == "det" else \
+        torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
+    ev[3].record()
+    opt.iterations += 1
+    opt.apply_sparse(var, uniq, g)
+    ev[4].record()
+    torch.cuda.synchronize()
+    for k, name in enumerate(phases):
+      phases[name].append(ev[k].elapsed_time(ev[k + 1]))
+  phases_ms = {k: float(np.median(v)) for k, v in phases.items()}
+  # algorithmic traffic of the step: forward rows + ids/segs + out, gradient rows read once + sums written,
+  # 5 x dim x 4 B per unique key for the fused Adagrad
+  n_u = int(uniq.numel())
+  step_bytes = nnz * dim * 4 + nnz * 12 + nnz * dim * 4 + (nnz + n_u) * dim * 4 + 5 * n_u * dim * 4
+  peak, peak_src = measured_peak_gbs()
   print(json.dumps({"metric": "fused embedding_lookup_sparse + Adagrad step, M ids/s (BASELINE configs[2])",
+                    "phases_ms": phases_ms,
+                    "roofline": {"bound": "hbm", "kernel": "whole step (lookup_sparse + unique + grad_reduce + apply_adagrad)",
+                                 "achieved": step_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": step_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_step": step_bytes},
                     "value": nnz / ms / 1e3, "unit": "M ids/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
                     "config": {"workload": "26 features x batch 65536, dim %d, %d resident rows, Zipf(1.05) per feature; "
