@@ -20,3 +20,6 @@ echo "racecheck exit: $?" | tee -a gpurun_out/evict_tests.log
 # the validated suite must be untouched by the new translation unit
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee -a gpurun_out/evict_tests.log
 # the A/B experiments and microbenches that used to follow live in scripts/round2_sweeps.sh (a separate gpurun call)
+# the opt-in paths of the Python mirror on the VALIDATED suites: deterministic gradient dedupe (det_segment_reduce) and
+# the trainable sparse lookup through det_sparse_segment_sum; green here -> make both the defaults (scripts/README.md)
+DET_GRAD_REDUCE=det DET_SPARSE_TRAIN_FUSED=1 timeout 900 python -m pytest tests/test_fused_gpu.py tests/test_peer_gpu.py tests/test_table_gpu.py -x -q -m gpu 2>&1 | tail -3 | tee -a gpurun_out/evict_tests.log
