@@ -1699,7 +1699,10 @@ det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, s
   unsigned vpr, lpr, sh;
   fgeom((unsigned)dim, vec4, 1, &vpr, &lpr, &sh);
   const unsigned gpw = 32u >> sh;
-  const int n_long_ctas = sms;
+  // CTAs of the launch reserved for the long groups (default one per SM); a tuning knob until the kernel has been timed
+  int n_long_ctas = env_int("DET_SEGRED_LONG_CTAS", sms);
+  if (n_long_ctas < 1) n_long_ctas = 1;
+  if (n_long_ctas > 4 * sms) n_long_ctas = 4 * sms;
   const auto k4 = segment_reduce_kernel<4>;
   const auto k1 = segment_reduce_kernel<1>;
   const int occ = vec4 ? occupancy_of(k4, kThreadsF) : occupancy_of(k1, kThreadsF);
