@@ -27,6 +27,9 @@ L2_FETCH=32 timeout 600 ncu --metrics dram__bytes_read.sum,dram__sectors_read.su
 timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce det > gpurun_out/c3_det.json 2> gpurun_out/c3_det.err
 timeout 600 python bench.py --workload c3 --steps 30 --warmup 5 --grad-reduce torch > gpurun_out/c3_torch.json 2> gpurun_out/c3_torch.err
 timeout 400 python scripts/microbench.py --ops segment_reduce,index_add --dims 16,64,128 --resident 20000000 > gpurun_out/segment_reduce.jsonl 2> gpurun_out/segment_reduce.err
+for c in 37 74 296; do
+  DET_SEGRED_LONG_CTAS=$c timeout 300 python scripts/microbench.py --ops segment_reduce --dims 64 --resident 20000000 --tag "long_ctas_$c" >> gpurun_out/segment_reduce.jsonl 2>> gpurun_out/segment_reduce.err
+done
 cut -c1-260 gpurun_out/segment_reduce.jsonl
 echo "c3 A/B (det_segment_reduce vs index_add):"; cut -c1-260 gpurun_out/c3_det.json gpurun_out/c3_torch.json
 # L2 prefetch-size qualifier on the bucket loads (the ~125 B of DRAM read per probe), register caps, segment_sum variants
