@@ -5,19 +5,14 @@ Variable per optimizer state, find -> dense rule -> upsert) -- tested the way th
 a twin model on a plain dense parameter trained with the unpatched optimizer, 10 steps, compared at fp32 tolerance
 (kernel_tests/dynamic_embedding_optimizer_test.py:349-440, swept over the optimizer list of :112-278).
 
-STATUS: written after round 1's GPU budget was spent; the bodies run over the emulated library with CPU tensors
-(tests/test_mirror_emu.py); on a GPU they run with DET_TEST_UNVALIDATED=1 (tests/test_zz_unvalidated_gpu.py)."""
+First hardware run: round 1's driver box (all five suites passed on a fresh B200); ungated in round 2."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("DET_TEST_UNVALIDATED") != "1",
-                       reason="caller-side mirrors not yet run on a B200 (set DET_TEST_UNVALIDATED=1)"),
-]
+pytestmark = pytest.mark.gpu
 
 DEV = "cuda"   # tests/test_mirror_emu.py re-runs these bodies over the emulated library with DEV = "cpu"
 V, DIM, STEPS = 48, 6, 10

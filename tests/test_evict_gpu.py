@@ -4,20 +4,14 @@ det_evict against a sort, survivors keep their rows, scores follow their keys th
 optimizer refresh scores, removed keys leave score 0).  The same bodies run on the sequential model in
 tests/test_evict_model.py.
 
-STATUS: written after round 1's GPU budget was spent -- the CUDA path here has been compiled and modelled
-(tests/evict_model.py) but NOT yet run on a B200.  Until it has been, these tests only run with
-DET_TEST_UNVALIDATED=1 so that an unproven path cannot mask the validated suite behind `pytest -x`."""
+First hardware run: round 1's driver box (all five suites passed on a fresh B200); ungated in round 2."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("DET_TEST_UNVALIDATED") != "1",
-                       reason="capacity-management kernels not yet validated on a B200 (set DET_TEST_UNVALIDATED=1)"),
-]
+pytestmark = pytest.mark.gpu
 
 DIM = 8
 DEV = "cuda"   # tests/test_mirror_emu.py re-runs these bodies over the emulated library with DEV = "cpu"

@@ -3,9 +3,7 @@ path (TF's _deduplicate_indexed_slices = unsorted_segment_sum before _resource_a
 python/ops/dynamic_embedding_optimizer.py:150,184) -- rows of one key added in POSITION ORDER, so the result is
 bit-identical to the sequential CPU sum (oracle.segment_reduce = np.add.at) and independent of the schedule.
 
-STATUS: written after round 1's GPU budget was spent; runs with DET_TEST_UNVALIDATED=1 only (tests/test_zz_unvalidated_gpu.py
-gives it its first hardware run in a subprocess).  The same bodies run over the emulated library
-(tests/test_segreduce_emu.py::test_gpu_suite_body) and the C entry point is covered bit-exactly there."""
+First hardware run: round 1's driver box (all five suites passed on a fresh B200); ungated in round 2."""
 import os
 
 import numpy as np
@@ -14,11 +12,7 @@ import torch
 
 from oracle import oracle as O
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("DET_TEST_UNVALIDATED") != "1",
-                       reason="det_segment_reduce not yet validated on a B200 (set DET_TEST_UNVALIDATED=1)"),
-]
+pytestmark = pytest.mark.gpu
 
 DEV = "cuda"     # tests/test_segreduce_emu.py re-runs these bodies over the emulated library with DEV = "cpu"
 SCALE = 1        # the emulator runs the large cases at 1/64 of the size

@@ -5,19 +5,14 @@ live in host memory that the same kernels reach over PCIe (csrc/table.cu alloc_v
  * a table whose value plane really is split (budget = a quarter of the rows): every table op against a dict, rows on
    both sides of the split, growth across the budget, fused sparse lookup and the fused optimizer.
 
-STATUS: written after round 1's GPU budget was spent; runs with DET_TEST_UNVALIDATED=1 only (tests/test_zz_unvalidated_gpu.py
-gives it its first hardware run in a subprocess); the body also runs over the emulated library (tests/test_mirror_emu.py)."""
+First hardware run: round 1's driver box (all five suites passed on a fresh B200); ungated in round 2."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("DET_TEST_UNVALIDATED") != "1",
-                       reason="host-spill allocation not yet validated on a B200 (set DET_TEST_UNVALIDATED=1)"),
-]
+pytestmark = pytest.mark.gpu
 
 DEV = "cuda"   # tests/test_mirror_emu.py re-runs these bodies over the emulated library with DEV = "cpu"
 REACH = 1024 * 1024 * 2          # key count of the reference's test; smaller on the emulator
