@@ -46,12 +46,17 @@ def parse_args():
   ap.add_argument("--resident", type=int, default=100_000_000, help="resident keys per GPU")
   ap.add_argument("--batch", type=int, default=1 << 20, help="unique keys per step per GPU")
   ap.add_argument("--dim", type=int, default=DIM)
-  ap.add_argument("--cpu-resident", type=int, default=1 << 24, help="resident keys of the CPU-baseline sample")
+  ap.add_argument("--cpu-resident", type=int, default=0,
+                  help="resident keys of the CPU arm (0 = the GPU arm's resident count when host RAM allows, else the largest power-of-two fraction that fits)")
+  ap.add_argument("--cpu-threads", type=int, default=0, help="worker threads of the CPU arm (0 = usable host cores: affinity mask capped by the cgroup quota)")
+  ap.add_argument("--no-hard-cases", action="store_true", help="N=1: skip find_hit90 / insert_new / lookup_insert_new")
+  ap.add_argument("--no-c3", action="store_true", help="N=1: skip the embedded configs[2] line (fused sparse lookup + Adagrad)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=10)
-  ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                  help="N>1: one-sided NVLink peer-memory kernels (default) or NCCL all-to-all")
+  ap.add_argument("--exchange", default="push", choices=["push", "peer", "nccl"],
+                  help="N>1: owner-side exchange with posted NVLink stores only (default, det_peer_xchg_*), one-sided "
+                       "remote-probe kernels (det_peer_find/insert), or NCCL all-to-all")
   ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                   help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2]); "
                        "c4 = the c2 step on configs[3] (torchrun --gpus 8: 1B keys = 125M resident per GPU, dim 128); "
@@ -121,6 +126,21 @@ def rank_to_key_torch(rank):
   return torch_fmix64(rank + salt) & 0x7fffffffffffffff
 
 
+def rows_of_keys_torch(keys, dim, gen):
+  """The row every copy of `keys` carries in generation `gen` (0 = prefill, 1 = written by the timed steps): a closed
+  form of the key, exact in fp32 (20-bit integers scaled by 2^-20), so that ANY rank can check ANY looked-up row."""
+  import torch
+  j = torch.arange(dim, dtype=torch.int64, device=keys.device) * 7919 + int(gen) * 104729
+  v = ((keys.reshape(-1, 1) & 0xFFFFF) + j) & 0xFFFFF
+  return v.to(torch.float32) * (1.0 / (1 << 20)) - 0.5
+
+
+def rows_of_keys_np(keys, dim, gen):
+  j = np.arange(dim, dtype=np.int64) * 7919 + int(gen) * 104729
+  v = ((keys.reshape(-1, 1) & 0xFFFFF) + j) & 0xFFFFF
+  return v.astype(np.float32) * np.float32(1.0 / (1 << 20)) - np.float32(0.5)
+
+
 def zipf_cdf_torch(vocab, device):
   import torch
   c = torch.empty(vocab, dtype=torch.float64, device=device)
@@ -150,43 +170,118 @@ def zipf_unique_batch_torch(cdf, batch, gen):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own cuckoo path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(dim, resident, batch, steps, warmup):
+def usable_host_cores():
+  """Cores this process may really use: the affinity mask, capped by the cgroup CPU quota.  os.cpu_count() ignores both;
+  a pool of that size on a lease that owns fewer cores leaves libcuckoo's spinning writers fighting for time slices
+  (round 1: the same arm gave 4.7 and 26 M keys/s on two boxes)."""
+  info = {"cpu_count": os.cpu_count() or 1}
+  try:
+    info["affinity"] = len(os.sched_getaffinity(0))
+  except AttributeError:
+    info["affinity"] = info["cpu_count"]
+  quota = None
+  try:
+    with open("/sys/fs/cgroup/cpu.max") as f:        # cgroup v2: "<quota> <period>" or "max <period>"
+      q, per = f.read().split()[:2]
+      if q != "max":
+        quota = float(q) / float(per)
+  except Exception:
+    try:
+      with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+        q, per = float(f.read()), float(g.read())
+        if q > 0:
+          quota = q / per
+    except Exception:
+      pass
+  info["cgroup_quota_cores"] = quota
+  n = info["affinity"]
+  if quota is not None:
+    n = max(1, min(n, int(quota)))
+  info["used"] = n
+  return n, info
+
+
+def cpu_resident_for(dim, want):
+  """largest resident key count <= want whose libcuckoo table (4-slot buckets of 8 + dim*4 B entries, power-of-two
+  bucket count, ~0.75 load at `want`) fits in 60 % of the available host RAM"""
+  try:
+    import psutil
+    avail = psutil.virtual_memory().available
+  except Exception:
+    avail = 32 << 30
+  r = want
+  while r > (1 << 20):
+    buckets = 1
+    while buckets * 4 < r:
+      buckets *= 2
+    if buckets * 4 * (8 + dim * 4) * 1.1 + r * 8 * 3 < 0.6 * avail:
+      break
+    r //= 2
+  return r, avail
+
+
+def cpu_arm(dim, resident, batch, steps, warmup, threads=0, want_resident=100_000_000):
+  """The reference's own CPU cuckoo path (oracle/_ref: its vendored libcuckoo behind the restated TableWrapper and
+  sharded launchers) on the usable host cores: resident table, then `warmup` + `steps` steps of Find(batch) +
+  Insert(batch) over fresh Zipf batches; median / min / max of the timed steps."""
   from oracle import oracle as O
   O.build()
-  threads = os.cpu_count() or 1
+  n_thr, cores = usable_host_cores()
+  if threads:
+    n_thr = cores["used"] = int(threads)
+  why = None
+  if not resident:
+    resident, avail = cpu_resident_for(dim, want_resident)
+    if resident < want_resident:
+      why = "host RAM: %.0f GB available, a %d-key libcuckoo table at dim %d needs ~%.0f GB" % (
+          avail / 2**30, want_resident, dim, 2**25 * 4 * (8 + dim * 4) / 2**30)
   if O.have_ref():
-    table, kind = O.RefTable(dim, resident * 2, threads=threads), "reference"
+    # init_size = resident: libcuckoo reserves the smallest power-of-two bucket count holding it (2^25 buckets x 4 slots
+    # at 100M keys, load 0.745) -- no resize during the run, same as the GPU arm's pre-sized table
+    table, kind = O.RefTable(dim, resident, threads=n_thr), "reference"
   else:
-    table, kind, threads = O.PortTable(dim, resident * 2), "port", 1
+    table, kind, n_thr = O.PortTable(dim, resident), "port", 1
   rng = np.random.default_rng(42)
   cdf = zipf_cdf_np(resident)
   fill = 1 << 20
-  fill_vals = rng.normal(0, 0.01, (fill, dim)).astype(np.float32)  # row content is irrelevant to the timing
+  t_fill = time.perf_counter()
   for b in range(0, resident, fill):
     r = np.arange(b, min(resident, b + fill), dtype=np.int64)
-    table.insert(rank_to_key_np(r), fill_vals[:r.shape[0]])
+    k = rank_to_key_np(r)
+    table.insert(k, rows_of_keys_np(k, dim, 0))
+  t_fill = time.perf_counter() - t_fill
   default = np.zeros(dim, np.float32)
-  vals = rng.normal(0, 0.01, (batch, dim)).astype(np.float32)
   out = np.zeros((batch, dim), np.float32)  # reused output buffer (TF's allocator pools outputs as well)
   times_find, times_ins = [], []
+  mism = 0
   for it in range(warmup + steps):
     keys = rank_to_key_np(zipf_unique_batch_np(cdf, batch, rng))
+    vals = rows_of_keys_np(keys, dim, 1)
     t0 = time.perf_counter()
     table.find(keys, default, out=out)
     t1 = time.perf_counter()
     table.insert(keys, vals)
     t2 = time.perf_counter()
+    if it == 0:   # same closed-form rows as the GPU arm: the CPU arm is checked too
+      e0 = rows_of_keys_np(keys[:4096], dim, 0)
+      mism = int((out[:4096] != e0).any(1).sum())
     if it >= warmup:
       times_find.append(t1 - t0)
       times_ins.append(t2 - t1)
-  tf, ti = float(np.median(times_find)), float(np.median(times_ins))
+  tot = np.asarray(times_find) + np.asarray(times_ins)
+  tf, ti, tt = float(np.median(times_find)), float(np.median(times_ins)), float(np.median(tot))
   table.close()
   return {
-      "value": batch / (tf + ti) / 1e6, "unit": "M keys/s", "cores": threads, "kind": kind,
-      "sample": "resident %d keys (of the GPU arm's %s), dim %d, batch %d unique Zipf(%.2f) keys, %d timed steps "
-                "of find+insert; find %.1f M keys/s, insert %.1f M keys/s" %
-                (resident, "100M", dim, batch, ALPHA, steps, batch / tf / 1e6, batch / ti / 1e6),
-      "ms_per_step": (tf + ti) * 1e3,
+      "value": batch / tt / 1e6, "unit": "M keys/s", "cores": n_thr, "kind": kind,
+      "sample": "resident %d keys%s, dim %d, batch %d unique Zipf(%.2f) keys, %d timed steps of find+insert after %d "
+                "warm-ups (median; fill took %.0f s)" %
+                (resident, "" if why is None else " (of the GPU arm's %d: %s)" % (want_resident, why), dim, batch, ALPHA, steps,
+                 warmup, t_fill),
+      "find_Mkeys_s": batch / tf / 1e6, "insert_Mkeys_s": batch / ti / 1e6,
+      "value_min": batch / float(tot.max()) / 1e6, "value_max": batch / float(tot.min()) / 1e6,
+      "host_cores": cores, "resident": resident, "same_resident_as_gpu_arm": resident >= want_resident,
+      "parity_mismatches_first_batch": mism,
+      "ms_per_step": tt * 1e3,
   }
 
 
@@ -267,6 +362,120 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+
+def src_sha():
+  """hash of the kernel sources a committed ncu traffic figure belongs to"""
+  import hashlib
+  h = hashlib.sha256()
+  for f in ("table.cu", "common.cuh"):
+    with open(os.path.join(ROOT, "recommenders_addons_b200", "csrc", f), "rb") as fh:
+      h.update(fh.read())
+  return h.hexdigest()[:16]
+
+
+def committed_traffic(kernel_key):
+  """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel_key` on this workload, from the ncu capture
+  committed in profiles/r02_traffic.json by scripts/ncu_traffic.py.  A capture taken from other kernel sources is STALE:
+  it is reported as null with the reason, never silently."""
+  path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+  try:
+    with open(path) as f:
+      rec = json.load(f)[kernel_key]
+  except Exception as ex:
+    return None, "no committed capture (%s)" % (ex,)
+  if rec.get("src_sha") != src_sha():
+    print("bench.py: profiles/r02_traffic.json is STALE for %s (kernel sources changed since the capture): "
+          "roofline.traffic = null; re-run scripts/ncu_traffic.py under gpurun" % kernel_key, file=sys.stderr)
+    return None, "stale capture (sources %s, capture %s)" % (src_sha(), rec.get("src_sha"))
+  return int(rec["dram_read"] + rec["dram_write"]), "profiles/r02_traffic.json (%s)" % rec.get("when", "?")
+
+
+def hard_cases(de, table, dev, dim, B, vocab, default, peak, key_batches):
+  """SURVEY 8(d)'s sweep beyond the all-hits step (N=1): Find with 10 % misses on the headline table; inserts of
+  BRAND-NEW keys at load 0.25 / 0.5 / 0.75 and a Find+Insert pair with 50 % new keys on a second, pre-sized table
+  (2^26 slots, 17 GB of rows: far beyond L2 like the headline table).  CUDA events, median of the reps, every rep a
+  different batch.  honest bytes = key + 64 B bucket + row in + row out."""
+  import torch
+  row = dim * 4
+  res = {}
+
+  def med_ms(fns):
+    ts = []
+    for fn in fns:
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      fn()
+      b.record()
+      torch.cuda.synchronize()
+      ts.append(a.elapsed_time(b))
+    return float(np.median(ts[2:] if len(ts) > 4 else ts))
+
+  def entry(ms, n, algo, honest, note):
+    return {"Mkeys_s": n / ms / 1e3, "ms": ms, "algorithmic_frac": algo / (ms * 1e-3) / 1e9 / peak,
+            "honest_frac": honest / (ms * 1e-3) / 1e9 / peak, "note": note}
+
+  gen = torch.Generator(device=dev).manual_seed(99)
+  # ---- find_hit90 -------------------------------------------------------------------------------------------
+  nm = B // 10
+  qs = []
+  for i in range(8):
+    hit = key_batches[i % len(key_batches)][:B - nm]
+    miss = rank_to_key_torch(vocab + 1000 + i * nm + torch.arange(nm, device=dev))
+    q = torch.cat([hit, miss])
+    qs.append(q[torch.randperm(B, device=dev, generator=gen)].contiguous())
+  ms = med_ms([(lambda q=q: table.lookup(q, dynamic_default_values=default)) for q in qs])
+  res["find_hit90"] = entry(ms, B, (B - nm) * row, B * (8 + 64 + row) + (B - nm) * row,
+                            "Find, 90 % resident Zipf keys + 10 % absent keys (default row written), headline table")
+  # ---- second table for the new-key cases -----------------------------------------------------------------------
+  cap = 1 << 26
+  t2 = de.CuckooHashTable(torch.int64, torch.float32, default, name="bench_new_keys", init_size=cap, max_capacity=cap,
+                          max_load_factor=0.95)
+  base = 20 * vocab
+  filled = 0
+
+  def fresh(n):
+    nonlocal filled
+    k = rank_to_key_torch(base + filled + torch.arange(n, device=dev))
+    filled += n
+    return k
+
+  def fill_to(load):
+    while filled < int(cap * load):
+      k = fresh(min(1 << 20, int(cap * load) - filled))
+      t2.insert(k, rows_of_keys_torch(k, dim, 0))
+
+  vals = rows_of_keys_torch(key_batches[0], dim, 1)
+  for load in (0.25, 0.5, 0.75):
+    fill_to(load)
+    batches = [fresh(B) for _ in range(6)]
+    ms = med_ms([(lambda k=k: t2.insert(k, vals)) for k in batches])
+    res["insert_new_load%02d" % int(load * 100)] = entry(
+        ms, B, B * row, B * (8 + 64 + 2 * row),
+        "Insert of %d BRAND-NEW keys per launch, table pre-sized (2^26 slots), load %.2f -> %.2f" % (B, load, filled / cap))
+    if load == 0.5:
+      # Find + Insert pair, 50 % of every batch brand-new, 50 % resident in this table
+      pairs = []
+      for i in range(6):
+        old = rank_to_key_torch(base + torch.randint(0, filled, (B // 2,), device=dev, generator=gen))
+        old = torch.unique(old)
+        new = fresh(B - old.numel())
+        pairs.append(torch.cat([old, new])[torch.randperm(B, device=dev, generator=gen)].contiguous())
+
+      def pair(k):
+        t2.lookup(k, dynamic_default_values=default)
+        t2.insert(k, vals)
+      ms = med_ms([(lambda k=k: pair(k)) for k in pairs])
+      res["lookup_insert_new"] = entry(
+          ms, B, B // 2 * row + B * row, B * (8 + 64 + row) + B // 2 * row + B * (8 + 64 + 2 * row),
+          "Find(batch) + Insert(batch), 50 % of the batch brand-new keys, load ~0.5; Mkeys_s counts every key once "
+          "(looked up AND upserted), like the headline value")
+  assert t2.stats()["error_flags"] == 0
+  t2.close()
+  del t2
+  torch.cuda.empty_cache()
+  return res
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -294,13 +503,16 @@ def gpu_arm(args):
   sharded, exchange = None, "none"
   if world > 1:
     exchange = args.exchange
-    if exchange == "peer":
+    if exchange in ("push", "peer"):
       try:
         # the shard lives in a symmetric-memory region that every rank maps (CUDA VMM, 2 MB pages)
         sharded = de.PeerShardedVariable.create(dim, 2 * resident, initializer=0.0, name="bench_table")
+        if exchange == "push":
+          sharded.attach_exchange(B)   # mailbox: request / insert segments per source rank + the output ring
       except Exception as ex:  # no symmetric memory in this sandbox: NCCL exchange instead, and say so
         print("symmetric-memory peer group failed (%r): falling back to NCCL all-to-all" % (ex,), file=sys.stderr)
         exchange = "nccl"
+        sharded = None
   if sharded is not None:
     var = sharded.local
   else:
@@ -310,8 +522,9 @@ def gpu_arm(args):
   if world > 1 and exchange == "nccl":
     sharded = de.ShardedVariable(var)
   is_peer = exchange == "peer"
+  is_push = exchange == "push"
   table = var.tables[0]
-  # ---- prefill this rank's shard: all ranks r of the vocabulary with owner(key(r)) == rank --------------
+  # ---- prefill this rank's shard: all ranks r of the vocabulary with owner(key(r)) == rank; row = f(key, generation 0)
   chunk = 1 << 20
   for b in range(0, vocab, chunk):
     r = torch.arange(b, min(vocab, b + chunk), dtype=torch.int64, device=dev)
@@ -319,35 +532,37 @@ def gpu_arm(args):
     if world > 1:
       k = k[de.default_partition_fn(k, world, True) == rank]
     if k.numel():
-      table.insert(k, torch.randn(k.numel(), dim, device=dev, generator=gen_v) * 0.01)
+      table.insert(k, rows_of_keys_torch(k, dim, 0))
   local_size = int(table.size())
   cdf = zipf_cdf_torch(vocab, dev)
-  n_batches = max(1, min(args.steps + args.warmup, args.distinct_batches))
+  n_batches = max(1, min(args.steps + args.warmup, args.distinct_batches if dim <= 64 else min(args.distinct_batches, 8)))
   key_batches = [rank_to_key_torch(zipf_unique_batch_torch(cdf, B, gen)) for _ in range(n_batches)]
   del cdf
-  new_vals = torch.randn(B, dim, device=dev, generator=gen_v) * 0.01
+  # the rows the timed steps write: f(key, generation 1) -- a function of the key, so any rank can check any row later
+  val_batches = [rows_of_keys_torch(k, dim, 1) for k in key_batches]
   default = torch.zeros(dim, device=dev)
-  out = torch.empty(B, dim, device=dev)
+
   def step(i, ev=None):
     k = key_batches[i % n_batches]
+    v = val_batches[i % n_batches]
     if sharded is None:
       if ev:
         ev[0].record()
       rows = table.lookup(k, dynamic_default_values=default)
       if ev:
         ev[1].record()
-      table.insert(k, new_vals)
+      table.insert(k, v)
       if ev:
         ev[2].record()
       return rows
     if ev:
       ev[0].record()
-    rows = sharded.lookup(k)
+    rows = sharded.lookup(k, copy=False) if is_push else sharded.lookup(k)
     if is_peer:
       sharded.phase_barrier()  # every rank has finished reading before any rank writes
     if ev:
       ev[1].record()
-    sharded.upsert(k, new_vals)
+    sharded.upsert(k, v)
     if is_peer:
       sharded.phase_barrier()  # every rank has finished writing before the next step reads
     if ev:
@@ -384,6 +599,46 @@ def gpu_arm(args):
   ms_per_step = total_ms / args.steps
   value = world * B / (ms_per_step * 1e-3) / 1e6
 
+  # ---- parity: a fixed sample looked up AFTER the timed region against the closed-form rows (every N) ------------
+  # (a) keys this rank wrote in its last timed step -> generation 1; (b) keys the OTHER ranks wrote in theirs ->
+  # generation 1; (c) random resident keys of any owner -> generation 0 or 1, never a mixture (a torn row);
+  # (d) keys outside the vocabulary -> the default row, exists = False.
+  ns = 16384
+  last = key_batches[(args.warmup + args.steps - 1) % n_batches]
+  qa = last[:ns].contiguous()
+  if world > 1:
+    gathered = [torch.empty_like(qa) for _ in range(world)]
+    dist.all_gather(gathered, qa)
+    qb = torch.cat([g for r_, g in enumerate(gathered) if r_ != rank])
+  else:
+    qb = key_batches[(args.warmup + max(0, args.steps - 2)) % n_batches][ns:2 * ns].contiguous()
+  gen_p = torch.Generator(device=dev).manual_seed(7 + rank)
+  qc = rank_to_key_torch(torch.randint(0, vocab, (ns,), device=dev, generator=gen_p))
+  qd = rank_to_key_torch(vocab + 17 + torch.arange(ns, device=dev) * (rank + 1))
+  q = torch.cat([qa, qb, qc, qd])
+  if sharded is None:
+    rows, ex = table.lookup(q, dynamic_default_values=default, return_exists=True)
+  elif exchange == "nccl":
+    rows, ex = sharded.lookup(q), None
+  else:
+    rows, ex = sharded.lookup(q, return_exists=True)
+  rows = rows.reshape(-1, dim)
+  e0, e1 = rows_of_keys_torch(q, dim, 0), rows_of_keys_torch(q, dim, 1)
+  is0, is1, isd = (rows == e0).all(1), (rows == e1).all(1), (rows == default).all(1)
+  na, nb_ = qa.numel(), qb.numel()
+  good = torch.cat([is1[:na + nb_], (is0 | is1)[na + nb_:na + nb_ + ns], isd[na + nb_ + ns:]])
+  if ex is not None:
+    good &= torch.cat([ex[:na + nb_ + ns], ~ex[na + nb_ + ns:]])
+  pm = torch.tensor([int((~good).sum()), q.numel()], dtype=torch.int64, device=dev)
+  if world > 1:
+    if is_peer:
+      sharded.phase_barrier()
+    dist.all_reduce(pm)
+  parity = {"checked": int(pm[1]), "mismatches": int(pm[0]),
+            "what": "after the timed region every rank looks up 16384 keys it wrote last step + 16384 per peer that the "
+                    "peers wrote (generation-1 rows), 16384 random resident keys (generation 0 or 1, never torn) and "
+                    "16384 absent keys (default row, exists false) and compares with the closed-form row of the key"}
+
   # ---- N>1: upper bound without the exchange (every rank only touches keys it owns: pure local kernels) -----
   no_exchange = None
   if world > 1:
@@ -392,6 +647,7 @@ def gpu_arm(args):
       mine = kb[de.default_partition_fn(kb, world, True) == rank]
       reps = (B + mine.numel() - 1) // max(1, mine.numel())
       own_batches.append(mine.repeat(reps)[:B].contiguous() if mine.numel() else kb)
+    own_vals = [rows_of_keys_torch(kb, dim, 1) for kb in own_batches]
     for i in range(3):
       table.lookup(own_batches[i % 8], dynamic_default_values=default)
     barrier()
@@ -400,7 +656,7 @@ def gpu_arm(args):
     a0.record()
     for i in range(n_ne):
       table.lookup(own_batches[i % 8], dynamic_default_values=default)
-      table.insert(own_batches[i % 8], new_vals)
+      table.insert(own_batches[i % 8], own_vals[i % 8])
     a1.record()
     barrier()
     tne = torch.tensor([a0.elapsed_time(a1) / n_ne], dtype=torch.float64, device=dev)
@@ -416,17 +672,17 @@ def gpu_arm(args):
     prev_aff = bind_to_gpu_numa(local_rank)
     n_e2e = max(1, min(args.e2e_steps, args.steps))
     hk = [key_batches[(args.warmup + i) % n_batches].cpu().pin_memory() for i in range(n_e2e)]
-    hv = new_vals.cpu().pin_memory()
+    hvs = [val_batches[(args.warmup + i) % n_batches].cpu().pin_memory() for i in range(n_e2e)]
     hd = default.cpu().pin_memory()
     ho = torch.empty(B, dim).pin_memory()
     if sharded is None:
       def e2e_step(i):
         table.lookup_host(hk[i], hd, ho)
-        table.insert_host(hk[i], hv)
+        table.insert_host(hk[i], hvs[i])
     else:
       def e2e_step(i):
         k = hk[i].to(dev, non_blocking=True)
-        v = hv.to(dev, non_blocking=True)
+        v = hvs[i].to(dev, non_blocking=True)
         rows = sharded.lookup(k)
         if is_peer:
           sharded.phase_barrier()
@@ -449,7 +705,7 @@ def gpu_arm(args):
            "h2d_bytes_per_step": int(B * (8 + 8 + dim * 4) + dim * 4), "d2h_bytes_per_step": int(B * dim * 4),
            "steps": n_e2e,
            "api": "CuckooHashTable.lookup_host + insert_host (det_find_host / det_insert_host), pinned host buffers"
-                  if sharded is None else ("PeerShardedVariable" if is_peer else "ShardedVariable") + ".lookup/upsert with pinned H2D/D2H copies"}
+                  if sharded is None else ("PeerShardedVariable" if (is_peer or is_push) else "ShardedVariable") + ".lookup/upsert with pinned H2D/D2H copies"}
     if sharded is None:
       # software-pipelined flavour of the SAME per-step work: the lookup of batch i+1 (D2H-heavy) is issued
       # together with the write-back of batch i (H2D-heavy) -- input prefetch, as tf.data does for the reference
@@ -460,7 +716,7 @@ def gpu_arm(args):
       t0 = time.perf_counter()
       for i in range(n_e2e):
         table.lookup_host_async(hk[(i + 1) % n_e2e], hd, ho2 if i % 2 == 0 else ho)  # D2H-heavy: rows of batch i+1
-        table.insert_host_async(hk[i], hv)                                          # H2D-heavy: write-back of batch i
+        table.insert_host_async(hk[i], hvs[i])                                      # H2D-heavy: write-back of batch i
         table.host_sync()
       dtp = time.perf_counter() - t0
       e2e["sequential_value"] = seq_value
@@ -480,6 +736,13 @@ def gpu_arm(args):
   algo_bytes = B * dim * 4  # north_star roofline: keys x dim x 4 B per lookup launch
   achieved = algo_bytes / (find_ms_1 * 1e-3) / 1e9
   honest_bytes = B * (8 + 64 + 2 * dim * 4)  # key in + one 64 B bucket + row read + row written out
+  kernels = {"none": "det::find_kernel_tma<16>",
+             "push": "det::xchg_route_kernel<false> + xchg_serve_find_kernel<16> (+ 2 flag waits)",
+             "peer": "det::peer_find_kernel<16> (+peer barrier)",
+             "nccl": "partition+all_to_all+find_kernel+all_to_all+scatter"}
+  launches = {"none": 2, "push": 8, "peer": 4, "nccl": 10}
+  traffic, traffic_src = (committed_traffic("find_kernel_tma<16>") if (world == 1 and B == (1 << 20) and dim == 64)
+                          else (None, "only captured for the N=1 headline workload"))
   line = {
       "metric": "embedding lookup+insert M keys/s at dim%d" % dim, "value": value, "unit": "M keys/s", "n_gpus": world,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -493,48 +756,73 @@ def gpu_arm(args):
           "l2": "inputs larger than L2: %d distinct batches are cycled, every step touches %.0f MB of rows + %.0f MB out + "
                 "%.0f MB in of a %.1f GB table (no L2 flush; the Zipf head is hot by design)" %
                 (n_batches, B * dim * 4 / 1e6, B * dim * 4 / 1e6, B * dim * 4 / 1e6, table.stats()["hbm_bytes"] / 1e9),
-          "parallelism": ("key-hash sharded x%d, %s" % (world, "one-sided NVLink peer-memory kernels (det_peer_find/insert), no collective"
-                                                       if is_peer else "NCCL all-to-all of keys and rows")) if world > 1 else "single GPU",
+          "parallelism": ("key-hash sharded x%d, %s" % (world, {
+              "push": "owner-side exchange: ids pushed to the owner's mailbox, local probe, rows pushed back with posted "
+                      "NVLink stores, flag words instead of barriers (det_peer_xchg_find/insert), no collective",
+              "peer": "one-sided NVLink peer-memory kernels with remote probes (det_peer_find/insert), no collective",
+              "nccl": "NCCL all-to-all of keys and rows"}[exchange])) if world > 1 else "single GPU",
       },
       "find_ms": find_ms_max, "insert_ms": ins_ms_max,
       "find_Mkeys_s": world * B / (find_ms_max * 1e-3) / 1e6, "insert_Mkeys_s": world * B / (ins_ms_max * 1e-3) / 1e6,
-      "gpu_launches": (2 if world == 1 else (4 if is_peer else 10)) * args.steps,
+      "gpu_launches": launches[exchange] * args.steps,
       "clocks": clocks,
+      "parity": parity,
       "roofline": {
-          "bound": "hbm", "kernel": ("det::find_kernel_tma<16>" if world == 1 else ("det::peer_find_kernel<16> (+peer barrier)" if is_peer else "partition+all_to_all+find_kernel+all_to_all+scatter")), "achieved": achieved, "peak": peak, "unit": "GB/s",
+          "bound": "hbm", "kernel": kernels[exchange], "achieved": achieved, "peak": peak, "unit": "GB/s",
           "frac": achieved / peak,
-          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload, from the
-          # ncu --set full capture summarised in profiles/r01_find_kernel_tma_dim64.csv (408.5 MB + 213.2 MB)
-          "traffic": 621701120 if (world == 1 and B == (1 << 20) and dim == 64) else None, "traffic_unit": "bytes per launch",
+          "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
           "peak_source": peak_src,
           "algorithmic_bytes_per_launch": algo_bytes,
+          "honest_frac": honest_bytes / (find_ms_1 * 1e-3) / 1e9 / peak,
           "note": "algorithmic = keys x dim x 4 B (north_star definition); the kernel necessarily also moves the "
                   "gathered rows out (+%d B/key) and one 64 B bucket + 8 B key per probe: honest-traffic rate %.0f GB/s "
                   "(%.2f of peak)" % (dim * 4, honest_bytes / (find_ms_1 * 1e-3) / 1e9,
-                                      honest_bytes / (find_ms_1 * 1e-3) / 1e9 / peak) +
-                  ("" if world == 1 else "; at N>1 (N-1)/N of the buckets and rows cross NVLink (measured peer copy 770 GB/s "
-                   "per direction per GPU): NVLink-side rate of this rank %.0f GB/s" %
-                   ((world - 1) / world * B * (64 + dim * 4) / (find_ms_1 * 1e-3) / 1e9)),
+                                      honest_bytes / (find_ms_1 * 1e-3) / 1e9 / peak),
       },
   }
   if world > 1:
-    # at N > 1 the exchange is bounded by NVLink, not HBM -- (N-1)/N of a rank's bucket probes and rows
-    # cross the link (one direction for find: owner -> requester).  Peak = the measured peer copy of this pool's boxes
-    # (profiles/r01_peer_microbench_2gpu.jsonl: 735 GB/s; 770 GB/s on the 8-GPU box), nominal 900 GB/s per direction.
-    nv_bytes = (world - 1) / world * B * (64 + dim * 4)
+    # at N > 1 the exchange is bounded by NVLink, not HBM.  Bytes one rank must SEND (= receive) per step:
+    # push: (N-1)/N of its requests (8 B key + 4 B position), of the rows it serves (4*D) and of its insert pairs
+    # (8 + 4*D); peer (remote probes): (N-1)/N x (64 B bucket + 4*D row) inbound per find, 64 B inbound + 4*D outbound per
+    # insert.  Peak = measured peer copy, one direction (profiles/r01_peer_microbench_2gpu.jsonl 735 GB/s, 770 GB/s on
+    # the 8-GPU box; nominal 900 GB/s).
+    f = (world - 1) / world
+    nv_bytes = f * B * ((12 + dim * 4 + 8 + dim * 4) if is_push else (64 + dim * 4 + dim * 4))
     nv_peak = float(os.environ.get("DET_NVLINK_PEAK_GBS", "770"))
-    line["roofline_nvlink"] = {"bound": "nvlink", "kernel": line["roofline"]["kernel"],
-                               "achieved": nv_bytes / (find_ms_1 * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
-                               "frac": nv_bytes / (find_ms_1 * 1e-3) / 1e9 / nv_peak,
-                               "bytes_per_launch": nv_bytes,
+    line["roofline_nvlink"] = {"bound": "nvlink", "kernel": "whole step (%s)" % exchange,
+                               "achieved": nv_bytes / (ms_per_step * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
+                               "frac": nv_bytes / (ms_per_step * 1e-3) / 1e9 / nv_peak,
+                               "bytes_per_step_per_direction": nv_bytes,
                                "peak_source": "measured peer copy, one direction (DET_NVLINK_PEAK_GBS overrides)"}
   if e2e:
+    if world == 1:
+      # the host-buffer step moves h2d + d2h bytes over one PCIe link; measured on this pool's boxes
+      # (scripts/pcie_probe.py): 55-57 GB/s per direction, 99 GB/s with both directions busy
+      pcie_peak = float(os.environ.get("DET_PCIE_BIDIR_GBS", "99"))
+      moved = e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]
+      e2e["pcie_GBs"] = moved * e2e["value"] * 1e6 / B / 1e9
+      e2e["pcie_frac"] = e2e["pcie_GBs"] / pcie_peak
+      e2e["pcie_peak_source"] = "scripts/pcie_probe.py, both directions busy (DET_PCIE_BIDIR_GBS overrides)"
     line["e2e"] = e2e
   if no_exchange:
     line["no_exchange"] = no_exchange
+  if world == 1 and not args.no_hard_cases:
+    try:
+      line["hard_cases"] = hard_cases(de, table, dev, dim, B, vocab, default, peak, key_batches)
+    except Exception as ex:
+      line["hard_cases"] = {"error": repr(ex)}
+  if world == 1 and not args.no_c3 and dim == 64:
+    # BASELINE configs[2] in the same run (the driver only records this line): free the headline table first
+    try:
+      table.close()
+      del table, var, key_batches, val_batches
+      torch.cuda.empty_cache()
+      line["c3"] = c3_measure(args, steps=min(args.steps, 50), warmup=5)
+    except Exception as ex:
+      line["c3"] = {"error": repr(ex)}
   if world == 1 and not args.no_cpu_baseline:
     try:
-      cb = cpu_arm(dim, args.cpu_resident, B, steps=7, warmup=2)
+      cb = cpu_arm(dim, args.cpu_resident, B, steps=7, warmup=3, threads=args.cpu_threads, want_resident=args.resident)
       cb.pop("ms_per_step", None)
       line["cpu_baseline"] = cb
     except Exception as ex:  # the checker is optional for the bench line; never hide the GPU number
@@ -548,17 +836,21 @@ def reference_arm(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  steps = max(1, min(args.steps, 9))
-  warm = max(1, min(args.warmup, 3))
-  cb = cpu_arm(args.dim, args.cpu_resident, args.batch, steps=steps, warmup=warm)
+  steps = max(20, min(args.steps, 40))     # >= 20 timed steps after >= 5 warm-ups, bounded so the run ends in minutes
+  warm = max(5, min(args.warmup, 10))
+  cb = cpu_arm(args.dim, args.cpu_resident, args.batch, steps=steps, warmup=warm, threads=args.cpu_threads,
+               want_resident=args.resident)
   ms = cb.pop("ms_per_step")
   line = {
-      "impl": "reference", "metric": "embedding lookup+insert M keys/s at dim64", "value": cb["value"],
+      "impl": "reference", "metric": "embedding lookup+insert M keys/s at dim%d" % args.dim, "value": cb["value"],
       "unit": "M keys/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "int64 keys / f32 rows (copy; no arithmetic)", "data": "synthetic",
       "config": {"workload": "BASELINE configs[1] on the reference's CPU cuckoo path (TableWrapperOptimized over "
-                             "libcuckoo), bounded sample: " + cb["sample"], "batch": args.batch, "dim": args.dim},
+                             "libcuckoo): " + cb["sample"], "batch": args.batch, "dim": args.dim,
+                 "resident_keys": cb["resident"], "same_resident_as_gpu_arm": cb["same_resident_as_gpu_arm"]},
+      "find_Mkeys_s": cb["find_Mkeys_s"], "insert_Mkeys_s": cb["insert_Mkeys_s"],
+      "value_min": cb["value_min"], "value_max": cb["value_max"],
       "cpu_baseline": cb,
       "e2e": {"value": cb["value"], "unit": "M keys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
@@ -567,6 +859,10 @@ def reference_arm(args):
 
 
 def c3_arm(args):
+  print(json.dumps(c3_measure(args, args.steps, args.warmup)))
+
+
+def c3_measure(args, steps, warmup):
   """Secondary workload, BASELINE configs[2]: fused embedding_lookup_sparse + Adagrad, 26 Criteo-shaped sparse
   features x batch 65536 (nnz = 1,703,936 ids/step, one id per (sample, feature)), dim 64, single GPU.
   Step = forward (det_lookup_sparse: ids -> [nnz, dim] rows, combiner sum) + tf.unique of the ids + per-unique
@@ -587,9 +883,10 @@ def c3_arm(args):
   offs = np.concatenate([[0], np.cumsum(vocab)])[:-1]
   for b in range(0, total, 1 << 20):  # resident: every (feature, rank) key
     r = torch.arange(b, min(total, b + (1 << 20)), dtype=torch.int64, device=dev)
-    table.insert(rank_to_key_torch(r), torch.randn(r.numel(), dim, device=dev, generator=gen) * 0.01)
+    k = rank_to_key_torch(r)
+    table.insert(k, rows_of_keys_torch(k, dim, 0))
   cdfs = [zipf_cdf_torch(int(v), dev) for v in vocab]
-  nb = max(1, min(args.steps + args.warmup, 16))
+  nb = max(1, min(steps + warmup, 16))
   batches = []
   for _ in range(nb):
     cols = [torch.searchsorted(c, torch.rand(batch, dtype=torch.float64, device=dev, generator=gen)).clamp_(max=c.numel() - 1) + int(o)
@@ -613,16 +910,22 @@ def c3_arm(args):
     opt.apply_sparse(var, uniq, g)
     return out
 
-  for i in range(args.warmup):
+  # parity of the fused forward before any optimizer step: one id per output row and combiner sum, so row i of the
+  # output must be the closed-form generation-0 row of ids[i], bit for bit
+  o0 = lookup_sparse_fused(var, batches[0], seg, None, nnz, "sum")
+  parity = {"checked": nnz, "mismatches": int((o0 != rows_of_keys_torch(batches[0], dim, 0)).any(1).sum()),
+            "what": "det_lookup_sparse output of the first batch vs the closed-form rows of its ids (before any update)"}
+  del o0
+  for i in range(warmup):
     step(i)
   torch.cuda.synchronize()
   t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   t0.record()
-  for i in range(args.steps):
-    step(args.warmup + i)
+  for i in range(steps):
+    step(warmup + i)
   t1.record()
   torch.cuda.synchronize()
-  ms = t0.elapsed_time(t1) / args.steps
+  ms = t0.elapsed_time(t1) / steps
   # where the step goes: the same step with CUDA events between its phases (outside the timed region)
   phases = {"lookup_sparse": [], "unique": [], "grad_reduce": [], "apply_adagrad": []}
   for i in range(5):
@@ -648,17 +951,18 @@ def c3_arm(args):
   n_u = int(uniq.numel())
   step_bytes = nnz * dim * 4 + nnz * 12 + nnz * dim * 4 + (nnz + n_u) * dim * 4 + 5 * n_u * dim * 4
   peak, peak_src = measured_peak_gbs()
-  print(json.dumps({"metric": "fused embedding_lookup_sparse + Adagrad step, M ids/s (BASELINE configs[2])",
-                    "phases_ms": phases_ms,
+  table.close()
+  return ({"metric": "fused embedding_lookup_sparse + Adagrad step, M ids/s (BASELINE configs[2])",
+                    "phases_ms": phases_ms, "parity": parity,
                     "roofline": {"bound": "hbm", "kernel": "whole step (lookup_sparse + unique + grad_reduce + apply_adagrad)",
                                  "achieved": step_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": step_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                                  "algorithmic_bytes_per_step": step_bytes},
-                    "value": nnz / ms / 1e3, "unit": "M ids/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                    "value": nnz / ms / 1e3, "unit": "M ids/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
                     "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
                     "config": {"workload": "26 features x batch 65536, dim %d, %d resident rows, Zipf(1.05) per feature; "
                                            "includes tf.unique + the per-unique gradient sum (%s)" % (dim, total, "det_segment_reduce, position order" if args.grad_reduce == "det" else "torch index_add"),
-                               "nnz": nnz, "unique_per_step": int(de.unique(batches[0])[0].numel())}}))
+                               "nnz": nnz, "unique_per_step": n_u}})
 
 
 def c5_arm(args):

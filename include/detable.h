@@ -320,6 +320,29 @@ det_status det_peer_inbox_counts(det_peer_group* g, int shard, int64_t* counts_h
 det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* counts_host, int64_t* keys_out,
                                  void* rows_out, det_stream_t stream);
 
+/* ---- owner-side exchange: the sharded Find / Insert with PUSHES only (ABI >= 5) ----
+ * Replaces HvdVariable.__alltoall_embedding_lookup__ (python/ops/shadow_embedding_ops.py:397-447: alltoall(ids) ->
+ * local lookup -> alltoall(rows) -> scatter) and the reverse path of the write-back, without a collective library and
+ * without the remote probe reads of det_peer_find / det_peer_insert: ids travel to the owner's MAILBOX with posted
+ * NVLink stores, the owner probes its own shard at HBM speed and stores every row straight into the requester's
+ * output ring at the id's position; inserts travel as (key, row) pairs and are applied by the owner locally.
+ * Ordering: per-(source, owner) flag words in the mailbox (st.release.sys / ld.acquire.sys), no rank-wide barrier.
+ * COLLECTIVE: every rank of the group issues the same sequence of det_peer_xchg_find / det_peer_xchg_insert calls on ONE
+ * stream per group (n may differ per rank, 0 allowed) -- the contract of the reference's alltoall ops.
+ * mailbox_ptrs[p] = where THIS process sees rank p's mailbox (det_peer_xchg_bytes each, zeroed by its owner before
+ * any rank attaches; ranks synchronise on the host between zeroing and the first call).  max_items bounds one call's n.
+ * det_peer_xchg_find: rows land in this rank's 2-entry output ring; *rows_view (nullable) = device pointer of the n
+ * rows, valid until the next-but-one det_peer_xchg_find; values_out (nullable) receives a copy; exists_out nullable.
+ * With full_size_default = 0 the broadcast default row must be identical on every rank (the owner writes it).
+ * A full shard is reported by DET_TABLE_FULL of a LATER call (asynchronous state snapshots), never silently. */
+size_t det_peer_xchg_bytes(int world, size_t max_items, size_t row_bytes);
+det_status det_peer_xchg_attach(det_peer_group* g, const void* const* mailbox_ptrs, size_t max_items, size_t row_bytes);
+det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
+                              int full_size_default, void* values_out, uint8_t* exists_out, void** rows_view,
+                              det_stream_t stream);
+det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
+                                det_stream_t stream);
+
 /* ---- file-system format of SaveToFileSystem / LoadFromFileSystem
  * (cuckoo_hashtable_op.cc:310-504): raw little-endian `<prefix>-keys` (int64[n]) and
  * `<prefix>-values` (V[n*dim]).  HOST paths; synchronous. ---- */

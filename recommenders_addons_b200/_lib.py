@@ -10,7 +10,7 @@ _sz = ctypes.c_size_t
 _i = ctypes.c_int
 
 DET_OK = 0
-ABI_VERSION = 4  # det_abi_version() of the library these mirrors describe (checked at load)
+ABI_VERSION = 5  # det_abi_version() of the library these mirrors describe (checked at load)
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 # HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
@@ -88,6 +88,10 @@ SIGNATURES = {
     "det_peer_route": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_peer_inbox_counts": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp]),
     "det_peer_inbox_gather": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp, _vp, _vp]),
+    "det_peer_xchg_bytes": (_sz, [_i, _sz, _sz]),
+    "det_peer_xchg_attach": (_i, [_vp, ctypes.POINTER(_vp), _sz, _sz]),
+    "det_peer_xchg_find": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, ctypes.POINTER(_vp), _vp]),
+    "det_peer_xchg_insert": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "det_save": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
     "det_load": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
     "det_import_plane": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
@@ -116,7 +120,8 @@ def lib():
   """Load libdetable.so (building it when sources are newer).  Fails loudly: there is no fallback."""
   global _LIB
   if _LIB is None:
-    path = _build.build()
+    # DET_LIB_PATH: a measurement build of the SAME sources (build.build_variant; scripts/*_sweep.sh), never a fallback
+    path = os.environ.get("DET_LIB_PATH") or _build.build()
     if not os.path.exists(path):
       raise RuntimeError("libdetable.so missing: the CUDA extension is required (no CPU fallback)")
     l = ctypes.CDLL(path)

@@ -43,12 +43,30 @@ def _extra_flags():
   return os.environ.get("DET_NVCC_EXTRA", "").split()
 
 
+def build_variant(tag, extra_flags):
+  """Measurement builds (scripts/*_sweep.sh): lib/variants/libdetable_<tag>.so with extra nvcc flags, built HERE so that
+  the GPU box spends no GPU-minutes compiling; selected at run time with DET_LIB_PATH=<path> (see _lib.lib)."""
+  nvcc = _nvcc()
+  if nvcc is None:
+    raise RuntimeError("nvcc not found")
+  vdir = os.path.join(LIB_DIR, "variants")
+  os.makedirs(vdir, exist_ok=True)
+  out_path = os.path.join(vdir, "libdetable_%s.so" % tag)
+  cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+  out = subprocess.run(cmd, capture_output=True, text=True)
+  if out.returncode != 0:
+    raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out.stdout + out.stderr)
+  return out_path
+
+
 def build(force=False, verbose=False):
   """Returns the path of libdetable.so, (re)building it when a source is newer.  Safe under torchrun: the build
   is serialised with a file lock, written to a temporary name and renamed, so concurrent ranks never load a
   half-written library."""
   if not force and not needs_build():
     return LIB
+  if os.environ.get("DET_NO_REBUILD") == "1" and os.path.exists(LIB):
+    return LIB  # measurement scripts on the GPU box: use the library that travelled with the snapshot, never compile there
   nvcc = _nvcc()
   if nvcc is None:
     if os.path.exists(LIB):
@@ -78,4 +96,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+  if "--variant" in sys.argv:   # python -m recommenders_addons_b200.build --variant <tag> <nvcc flags...>
+    k = sys.argv.index("--variant")
+    print(build_variant(sys.argv[k + 1], sys.argv[k + 2:]))
+  else:
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -239,6 +239,260 @@ __global__ void peer_barrier_kernel(BarPtrs bp, int rank, int world, unsigned lo
   }
 }
 
+
+// ---- owner-side exchange ("xchg"): the sharded Find / Insert with PUSHES only ------------------------------------
+// The one-sided kernels above (K8a/K8b) let the requester probe the owner's key plane REMOTELY: every key costs a 64 B
+// bucket read round trip over NVLink before its row can move, and rows are pulled with reads (request + response).
+// Measured at 8 GPUs (SCALE_r01.json): 0.234 scaling efficiency, ~565 GB/s per GPU of a 770 GB/s link.  Here the
+// reference's own shape (shadow_embedding_ops.py:397-447: ids travel to the owner, the owner looks up LOCALLY, rows
+// travel back) is rebuilt with posted NVLink stores only and no collective library:
+//   Find  : xchg_route_kernel<false>  partition by owner + send (key, position) into the owner's request segment   8+4 B/key
+//           xchg_serve_find_kernel    owner probes its OWN table at HBM speed and stores every row straight into the
+//                                     requester's output ring at `position` (128-bit posted stores)                4*D B/key
+//   Insert: xchg_route_kernel<true>   partition + send (key, row) into the owner's insert segment                  8+4*D B/key
+//           xchg_apply_insert_kernel  owner claims / overwrites locally (device-scope CAS, no system atomics)
+// Ordering uses per-(source, owner) FLAG WORDS in the same peer-mapped mailbox: the last CTA of a sending kernel
+// publishes {epoch, count} with st.release.sys after every CTA fenced its stores; the consumer's stream runs a one-CTA
+// xchg_wait_kernel (ld.acquire.sys spin, bounded) in front of the consuming kernel.  No rank-wide barrier: a rank only
+// ever waits for the ranks whose data it is about to read.  All ranks call det_peer_xchg_find / det_peer_xchg_insert
+// collectively and in the same order (exactly like the reference's alltoall ops).
+enum : int { kFlagReq = 0, kFlagDone = 1, kFlagIns = 2, kFlagAck = 3 };   // one 64 B line of 8 u64 each
+
+struct XchgView {
+  unsigned char* base[kMaxPeers];   // where THIS process sees rank p's mailbox
+  size_t off_req_keys, off_req_idx, off_ins_keys, off_ins_rows, off_out, off_exists;
+  size_t seg_req_keys, seg_req_idx, seg_ins_keys, seg_ins_rows, out_bytes, ex_bytes;
+  size_t cap;                       // items per (source, owner) segment and per output ring entry
+  unsigned row_bytes;
+  int world, rank, gpu_mode;
+};
+
+__device__ __forceinline__ unsigned long long* xchg_flag(const XchgView& xv, int p, int which, int idx) {
+  return reinterpret_cast<unsigned long long*>(xv.base[p] + which * 64) + idx;
+}
+
+__device__ __forceinline__ long long ld_cg_ll(const long long* p) {
+#ifdef DET_EMU
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ unsigned ld_cg_u32(const unsigned* p) {
+#ifdef DET_EMU
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+#else
+  return __ldcg(p);
+#endif
+}
+
+// wait until every rank p < world has published epoch (or a later one) in flags[p] (local memory, written by peers)
+__global__ void xchg_wait_kernel(const unsigned long long* flags, int world, unsigned long long epoch, DevState* st,
+                                 long long timeout_cycles) {
+  const int p = threadIdx.x;
+  if (p < world) {
+    const long long t0 = clock64();
+    while (true) {
+      const unsigned long long v = ld_acquire_sys(flags + p);
+      if ((v >> 32) >= epoch) break;
+      if (clock64() - t0 > timeout_cycles) {
+        atomicOr(&st->error, kErrBarrierTimeout);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+// every CTA calls this after its last remote store; returns true in ALL threads of the CTA that finished last
+__device__ __forceinline__ bool xchg_last_cta(unsigned* ticket) {
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  const bool last = s_last != 0;
+  if (last) __threadfence_system();
+  return last;
+}
+
+// partition by owner + pack + send.  WITH_ROWS = false: (key, position) requests of a Find; true: (key, row) of an Insert
+template <bool WITH_ROWS, int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigned char* __restrict__ rows, size_t n,
+                  RowGeom g, unsigned long long* cursor, unsigned* ticket, unsigned long long epoch, DevState* st) {
+  __shared__ unsigned s_cnt[kMaxPeers];
+  __shared__ unsigned long long s_base[kMaxPeers];
+  const int lane = threadIdx.x & 31;
+  const size_t n_tiles = (n + kThreadsP - 1) / kThreadsP;
+  const size_t seg_k = WITH_ROWS ? xv.seg_ins_keys : xv.seg_req_keys;
+  const size_t off_k = (WITH_ROWS ? xv.off_ins_keys : xv.off_req_keys) + (size_t)xv.rank * seg_k;
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x < kMaxPeers) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t i = tile * kThreadsP + threadIdx.x;
+    const bool valid = i < n;
+    const long long key = valid ? __ldg(keys + i) : 0;
+    const int own = valid ? peer_owner(key, xv.world, xv.gpu_mode) : 0;
+    unsigned pos = 0;
+    if (valid) pos = atomicAdd(&s_cnt[own], 1u);
+    __syncthreads();
+    if ((int)threadIdx.x < xv.world) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    __syncthreads();
+    const unsigned long long dest = s_base[own] + pos;
+    const bool ok = valid && dest < xv.cap;
+    if (valid && !ok) atomicOr(&st->error, kErrTableFull);
+    if (ok) reinterpret_cast<long long*>(xv.base[own] + off_k)[dest] = key;
+    if (WITH_ROWS) {
+      const unsigned char* src = nullptr;
+      unsigned char* dst = nullptr;
+      if (ok) {
+        src = rows + i * g.row_bytes;
+        dst = xv.base[own] + xv.off_ins_rows + (size_t)xv.rank * xv.seg_ins_rows + dest * g.row_bytes;
+      }
+      warp_move_rows<VEC>(g, src, dst, lane);
+    } else if (ok) {
+      reinterpret_cast<unsigned*>(xv.base[own] + xv.off_req_idx + (size_t)xv.rank * xv.seg_req_idx)[dest] = (unsigned)i;
+    }
+    __syncthreads();
+  }
+  if (xchg_last_cta(ticket) && (int)threadIdx.x < xv.world) {
+    const int o = threadIdx.x;
+    unsigned long long c = atomicAdd(&cursor[o], 0ull);
+    if (c > xv.cap) c = xv.cap;
+    cursor[o] = 0;
+    st_release_sys(xchg_flag(xv, o, WITH_ROWS ? kFlagIns : kFlagReq, xv.rank), (epoch << 32) | c);
+  }
+}
+
+// flat item f of the concatenated segments -> (source, index); pref[s] = items of the sources before s
+__device__ __forceinline__ int xchg_locate(const unsigned long long* pref, int world, unsigned long long f,
+                                           unsigned long long& i) {
+  int s = 0;
+#pragma unroll
+  for (int q = 1; q < kMaxPeers; ++q)
+    if (q < world && f >= pref[q]) s = q;
+  i = f - pref[s];
+  return s;
+}
+
+// owner side of Find: probe the LOCAL table for every requested key and push its row into the requester's output ring
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+xchg_serve_find_kernel(XchgView xv, TableView t, const unsigned char* __restrict__ defaults, int full_default,
+                       int want_exists, int parity, RowGeom g, unsigned* ticket, unsigned long long epoch) {
+  __shared__ unsigned long long s_pref[kMaxPeers + 1];
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int s = 0; s < xv.world; ++s) {
+      s_pref[s] = acc;
+      acc += *((volatile unsigned long long*)xchg_flag(xv, xv.rank, kFlagReq, s)) & 0xffffffffull;
+    }
+    for (int s = xv.world; s <= kMaxPeers; ++s) s_pref[s] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = s_pref[kMaxPeers];
+  const unsigned long long n_tiles = (total + kThreadsP - 1) / kThreadsP;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long f = tile * kThreadsP + threadIdx.x;
+    const bool valid = f < total;
+    unsigned long long i = 0;
+    const int s = valid ? xchg_locate(s_pref, xv.world, f, i) : 0;
+    long long key = 0;
+    unsigned idx = 0;
+    if (valid) {
+      key = ld_cg_ll(reinterpret_cast<const long long*>(xv.base[xv.rank] + xv.off_req_keys + (size_t)s * xv.seg_req_keys) + i);
+      idx = ld_cg_u32(reinterpret_cast<const unsigned*>(xv.base[xv.rank] + xv.off_req_idx + (size_t)s * xv.seg_req_idx) + i);
+    }
+    const long long slot = warp_find_slots<false>(t, key, valid, lane);
+    if (want_exists && valid) (xv.base[s] + xv.off_exists + (size_t)parity * xv.ex_bytes)[idx] = slot >= 0 ? 1 : 0;
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid) {
+      src = slot >= 0 ? t.planes[0] + (size_t)slot * g.row_bytes : (full_default ? nullptr : DET_SRC_DEFAULT);
+      dst = xv.base[s] + xv.off_out + (size_t)parity * xv.out_bytes + (size_t)idx * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane, full_default ? nullptr : defaults);
+  }
+  if (xchg_last_cta(ticket) && (int)threadIdx.x < xv.world)
+    st_release_sys(xchg_flag(xv, threadIdx.x, kFlagDone, xv.rank), epoch << 32);
+}
+
+// requester side of a Find with per-key default rows: the owner skipped the misses, fill them from `defaults`
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+xchg_fill_missing_kernel(const unsigned char* __restrict__ exists, const unsigned char* __restrict__ defaults,
+                         unsigned char* __restrict__ out, size_t n, RowGeom g) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * kThreadsP + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * kThreadsP) >> 5;
+  for (size_t base = warp0 * 32; base < n; base += nwarps * 32) {
+    const size_t i = base + lane;
+    const bool miss = i < n && exists[i] == 0;
+    warp_move_rows<VEC>(g, miss ? defaults + i * g.row_bytes : nullptr, miss ? out + i * g.row_bytes : nullptr, lane);
+  }
+}
+
+// owner side of Insert: insert_or_assign of every (key, row) pair the sources routed here, on the LOCAL table
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+xchg_apply_insert_kernel(XchgView xv, TableView t, RowGeom g, int n_slot_planes, unsigned* ticket,
+                         unsigned long long epoch) {
+  __shared__ unsigned long long s_pref[kMaxPeers + 1];
+  __shared__ unsigned s_new, s_used;
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int s = 0; s < xv.world; ++s) {
+      s_pref[s] = acc;
+      acc += *((volatile unsigned long long*)xchg_flag(xv, xv.rank, kFlagIns, s)) & 0xffffffffull;
+    }
+    for (int s = xv.world; s <= kMaxPeers; ++s) s_pref[s] = acc;
+    s_new = 0;
+    s_used = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = s_pref[kMaxPeers];
+  const unsigned long long n_tiles = (total + kThreadsP - 1) / kThreadsP;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long f = tile * kThreadsP + threadIdx.x;
+    const bool valid = f < total;
+    unsigned long long i = 0;
+    const int s = valid ? xchg_locate(s_pref, xv.world, f, i) : 0;
+    const long long key = valid ? ld_cg_ll(reinterpret_cast<const long long*>(xv.base[xv.rank] + xv.off_ins_keys + (size_t)s * xv.seg_ins_keys) + i) : 0;
+    bool is_new, from_empty;
+    const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
+    const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
+    if (lane == 0 && bn) {
+      atomicAdd(&s_new, __popc(bn));
+      atomicAdd(&s_used, __popc(bu));
+    }
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid && slot >= 0) {
+      src = xv.base[xv.rank] + xv.off_ins_rows + (size_t)s * xv.seg_ins_rows + (size_t)i * g.row_bytes;
+      dst = t.planes[0] + (size_t)slot * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+    if (is_new && slot >= 0)
+      for (int p = 1; p <= n_slot_planes; ++p)
+        *reinterpret_cast<unsigned*>(t.planes[p] + (size_t)slot * t.dim * 4u) = kSlotUninit;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_new) {
+    atomicAdd(&t.st->size, (unsigned long long)s_new);
+    atomicAdd(&t.st->used, (unsigned long long)s_used);
+  }
+  // the insert segments of this rank have been consumed: the sources may overwrite them
+  if (xchg_last_cta(ticket) && (int)threadIdx.x < xv.world)
+    st_release_sys(xchg_flag(xv, threadIdx.x, kFlagAck, xv.rank), epoch << 32);
+}
+
 }  // namespace det
 
 using namespace det;
@@ -260,6 +514,14 @@ struct det_peer_group {
   size_t inbox_cap = 0, inbox_row_bytes = 0, inbox_seg_keys = 0, inbox_seg_rows = 0;
   unsigned long long* cursor = nullptr;      // owned, [kMaxPeers]
   unsigned long long* h_counts = nullptr;    // pinned, [kMaxPeers]
+  // owner-side exchange (det_peer_xchg_*)
+  XchgView xv{};
+  bool xchg = false;
+  unsigned long long* xcursor = nullptr;     // owned: [kMaxPeers] cursors + 1 ticket word
+  unsigned long long ep_find = 0, ep_ins = 0;
+  DevState* h_snap = nullptr;                // pinned: async snapshot of the local shard's DevState
+  cudaEvent_t snap_ev = nullptr;
+  bool snap_inflight = false;
 };
 
 extern "C" {
@@ -301,6 +563,9 @@ det_status det_peer_group_destroy(det_peer_group* g) {
       if (g->opened[p][q]) cudaIpcCloseMemHandle(g->opened[p][q]);
   if (g->cursor) cudaFree(g->cursor);
   if (g->h_counts) cudaFreeHost(g->h_counts);
+  if (g->xcursor) cudaFree(g->xcursor);
+  if (g->h_snap) cudaFreeHost(g->h_snap);
+  if (g->snap_ev) cudaEventDestroy(g->snap_ev);
   delete g;
   return DET_OK;
 }
@@ -528,6 +793,225 @@ det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* co
     CUDA_TRY(cudaMemcpyAsync((unsigned char*)rows_out + off * g->inbox_row_bytes, rb, c * g->inbox_row_bytes, cudaMemcpyDeviceToDevice, s));
     off += c;
   }
+  return DET_OK;
+}
+
+
+// ---- owner-side exchange: host entry points ----------------------------------------------------------------------
+static void xchg_layout(int world, size_t cap, size_t rb, XchgView* xv) {
+  size_t off = 256;
+  xv->seg_req_keys = al256(cap * 8);
+  xv->seg_req_idx = al256(cap * 4);
+  xv->seg_ins_keys = al256(cap * 8);
+  xv->seg_ins_rows = al256(cap * rb);
+  xv->out_bytes = al256(cap * rb);
+  xv->ex_bytes = al256(cap);
+  xv->off_req_keys = off; off += (size_t)world * xv->seg_req_keys;
+  xv->off_req_idx = off;  off += (size_t)world * xv->seg_req_idx;
+  xv->off_ins_keys = off; off += (size_t)world * xv->seg_ins_keys;
+  xv->off_ins_rows = off; off += (size_t)world * xv->seg_ins_rows;
+  xv->off_out = off;      off += 2 * xv->out_bytes;
+  xv->off_exists = off;   off += 2 * xv->ex_bytes;
+  xv->cap = cap;
+  xv->row_bytes = (unsigned)rb;
+  xv->world = world;
+}
+
+size_t det_peer_xchg_bytes(int world, size_t max_items, size_t row_bytes) {
+  if (world < 1 || world > kMaxPeers || max_items == 0 || max_items > 0xffffffffull || row_bytes == 0) return 0;
+  XchgView xv;
+  xchg_layout(world, max_items, row_bytes, &xv);
+  return xv.off_exists + 2 * xv.ex_bytes;
+}
+
+// mailbox_ptrs[p] = where THIS process sees rank p's mailbox (det_peer_xchg_bytes each, zeroed by its owner BEFORE any
+// rank calls this; follow with a host barrier over the ranks).  max_items bounds the batch of one call.
+det_status det_peer_xchg_attach(det_peer_group* g, const void* const* mailbox_ptrs, size_t max_items, size_t row_bytes) {
+  if (!g || !mailbox_ptrs || max_items == 0 || max_items > 0xffffffffull) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_attach: bad argument");
+  if (row_bytes != g->row_bytes) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_attach: row_bytes differs from the shards' row size");
+  det::DevGuard _dg(g->device);
+  xchg_layout(g->pv.world, max_items, row_bytes, &g->xv);
+  g->xv.rank = g->pv.rank;
+  g->xv.gpu_mode = g->pv.gpu_mode;
+  for (int p = 0; p < kMaxPeers; ++p) g->xv.base[p] = nullptr;
+  for (int p = 0; p < g->pv.world; ++p) {
+    if (!mailbox_ptrs[p] || ((uintptr_t)mailbox_ptrs[p] & 255u)) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_attach: mailbox pointers must be non-null and 256 B aligned");
+    g->xv.base[p] = (unsigned char*)mailbox_ptrs[p];
+  }
+  if (!g->xcursor) {
+    CUDA_TRY(cudaMalloc((void**)&g->xcursor, (kMaxPeers + 1) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(g->xcursor, 0, (kMaxPeers + 1) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocHost((void**)&g->h_snap, sizeof(DevState)));
+    memset(g->h_snap, 0, sizeof(DevState));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->snap_ev, cudaEventDisableTiming));
+  }
+  g->ep_find = g->ep_ins = 0;
+  g->xchg = true;
+  return DET_OK;
+}
+
+constexpr long long kXchgTimeoutCycles = 40000000000LL;  // ~20 s at 2 GHz: a peer that never arrives must not hang the GPU
+
+static void xchg_wait(det_peer_group* g, int which, unsigned long long epoch, cudaStream_t s) {
+  const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(g->xv.base[g->pv.rank] + which * 64);
+  DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, s, flags, g->pv.world, epoch, g->local->view.st, kXchgTimeoutCycles);
+}
+
+// A shard of a peer group has a FIXED capacity and is written by kernels whose key counts the owner's host never sees
+// (remote claims of det_peer_insert, the owner-side apply of det_peer_xchg_insert).  Room is therefore checked against
+// an asynchronous snapshot of the shard's own DevState: a call fails loudly with DET_TABLE_FULL once the last landed
+// snapshot shows the shard over its load limit or carrying the sticky table-full bit, instead of degrading silently.
+static det_status peer_room(det_peer_group* g, const char* who) {
+  det_table* t = g->local;
+  if (g->snap_inflight && cudaEventQuery(g->snap_ev) == cudaSuccess) {
+    g->snap_inflight = false;
+    t->used_ub = g->h_snap->used;           // remote / owner-side inserts never went through ensure_room
+    t->last_used_snap = g->h_snap->used;
+  } else {
+    cudaGetLastError();
+  }
+  if (g->h_snap) {
+    const uint64_t limit = (uint64_t)((double)t->view.capacity() * t->max_lf);
+    if ((g->h_snap->error & kErrTableFull) || g->h_snap->used > limit)
+      return fail(DET_TABLE_FULL, std::string(who) + ": the local shard is full (" + std::to_string(g->h_snap->used) + " of " +
+                                      std::to_string(t->view.capacity()) + " slots used, load limit " + std::to_string(limit) +
+                                      "; a sharded table has a fixed capacity per rank)");
+    if (g->h_snap->error & kErrBarrierTimeout)
+      return fail(DET_INTERNAL, std::string(who) + ": a peer did not arrive within the flag-wait timeout");
+  }
+  return DET_OK;
+}
+
+static void peer_snapshot(det_peer_group* g, cudaStream_t s) {
+  if (!g->h_snap || g->snap_inflight) return;
+  if (cudaMemcpyAsync(g->h_snap, g->local->view.st, sizeof(DevState), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+      cudaEventRecord(g->snap_ev, s) == cudaSuccess)
+    g->snap_inflight = true;
+  else
+    cudaGetLastError();
+}
+
+// Sharded Find through the owners.  COLLECTIVE: every rank of the group calls it (n may differ, 0 allowed), in the same
+// order as its peers.  Rows land in this rank's output ring (2 entries): *rows_view (if non-null) receives the device
+// pointer of the n rows, valid until the next-but-one det_peer_xchg_find; values_out (if non-null) additionally gets a
+// copy.  exists_out (nullable) [n].  A broadcast default row (full_size_default = 0) must be the same on every rank.
+det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
+                              int full_size_default, void* values_out, uint8_t* exists_out, void** rows_view,
+                              det_stream_t stream) {
+  if (!g || !g->xchg) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_find: no exchange mailbox attached");
+  if (n > g->xv.cap) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_find: batch larger than the mailbox (max_items)");
+  if (!defaults || (n && !keys)) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_find: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  det::DevGuard _dg(g->device);
+  det_status rs = peer_room(g, "det_peer_xchg_find");
+  if (rs != DET_OK && rs != DET_TABLE_FULL) return rs;
+  const unsigned long long ep = ++g->ep_find;
+  const int parity = (int)(ep & 1ull);
+  const XchgView& xv = g->xv;
+  unsigned char* out = xv.base[xv.rank] + xv.off_out + (size_t)parity * xv.out_bytes;
+  unsigned char* ex = xv.base[xv.rank] + xv.off_exists + (size_t)parity * xv.ex_bytes;
+  const int want_exists = (exists_out != nullptr || full_size_default) ? 1 : 0;
+  // serve: table row or the broadcast default row -> the requester's ring (256 B aligned); fill: per-key defaults -> ring
+  const int v = pick_vec(g->row_bytes, full_size_default ? nullptr : defaults, nullptr, nullptr);
+  const RowGeom geo = make_geom((unsigned)g->row_bytes, v);
+  unsigned* ticket = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
+  DevState* st = g->local->view.st;
+  const long long* k = (const long long*)keys;
+  {
+    const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+    DET_LAUNCH((xchg_route_kernel<false, 16>), grid, kThreadsP, 0, s, xv, k, (const unsigned char*)nullptr, n, geo, g->xcursor, ticket, ep, st);
+  }
+  xchg_wait(g, kFlagReq, ep, s);
+  {
+    const unsigned char* d = (const unsigned char*)defaults;
+    const TableView tv = g->local->view;
+    switch (v) {
+#define DET_XSERVE(VV)                                                                                                   \
+  case VV: {                                                                                                              \
+    const int grid = g->sm_count * occupancy_of(xchg_serve_find_kernel<VV>, kThreadsP);                                   \
+    DET_LAUNCH(xchg_serve_find_kernel<VV>, grid, kThreadsP, 0, s, xv, tv, d, full_size_default, want_exists, parity, geo, ticket, ep); \
+  } break;
+      DET_XSERVE(16) DET_XSERVE(8) DET_XSERVE(4) DET_XSERVE(2)
+      default: {
+        const int grid = g->sm_count * occupancy_of(xchg_serve_find_kernel<1>, kThreadsP);
+        DET_LAUNCH(xchg_serve_find_kernel<1>, grid, kThreadsP, 0, s, xv, tv, d, full_size_default, want_exists, parity, geo, ticket, ep);
+      } break;
+#undef DET_XSERVE
+    }
+  }
+  xchg_wait(g, kFlagDone, ep, s);
+  if (full_size_default && n) {
+    const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+    const unsigned char* d = (const unsigned char*)defaults;
+    const int vf = pick_vec(g->row_bytes, defaults, nullptr, nullptr);
+    const RowGeom gf = make_geom((unsigned)g->row_bytes, vf);
+    switch (vf) {
+      case 16: DET_LAUNCH(xchg_fill_missing_kernel<16>, grid, kThreadsP, 0, s, ex, d, out, n, gf); break;
+      case 8: DET_LAUNCH(xchg_fill_missing_kernel<8>, grid, kThreadsP, 0, s, ex, d, out, n, gf); break;
+      case 4: DET_LAUNCH(xchg_fill_missing_kernel<4>, grid, kThreadsP, 0, s, ex, d, out, n, gf); break;
+      case 2: DET_LAUNCH(xchg_fill_missing_kernel<2>, grid, kThreadsP, 0, s, ex, d, out, n, gf); break;
+      default: DET_LAUNCH(xchg_fill_missing_kernel<1>, grid, kThreadsP, 0, s, ex, d, out, n, gf); break;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (values_out && n) CUDA_TRY(cudaMemcpyAsync(values_out, out, n * g->row_bytes, cudaMemcpyDeviceToDevice, s));
+  if (exists_out && n) CUDA_TRY(cudaMemcpyAsync(exists_out, ex, n, cudaMemcpyDeviceToDevice, s));
+  if (rows_view) *rows_view = out;
+  return DET_OK;
+}
+
+// Sharded Insert (insert_or_assign) through the owners.  COLLECTIVE like det_peer_xchg_find.
+det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
+                                det_stream_t stream) {
+  if (!g || !g->xchg) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: no exchange mailbox attached");
+  if (n > g->xv.cap) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: batch larger than the mailbox (max_items)");
+  if (n && (!keys || !values)) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  det::DevGuard _dg(g->device);
+  det_status rs = peer_room(g, "det_peer_xchg_insert");
+  if (rs != DET_OK) return rs;
+  std::lock_guard<std::mutex> _lk(g->local->mu);
+  const unsigned long long ep = ++g->ep_ins;
+  const XchgView& xv = g->xv;
+  const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
+  const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
+  unsigned* ticket = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
+  DevState* st = g->local->view.st;
+  const long long* k = (const long long*)keys;
+  const unsigned char* r = (const unsigned char*)values;
+  if (ep > 1) xchg_wait(g, kFlagAck, ep - 1, s);   // every owner has consumed what this rank sent last time
+  {
+    const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+    switch (vec) {
+      case 16: DET_LAUNCH((xchg_route_kernel<true, 16>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
+      case 8: DET_LAUNCH((xchg_route_kernel<true, 8>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
+      case 4: DET_LAUNCH((xchg_route_kernel<true, 4>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
+      case 2: DET_LAUNCH((xchg_route_kernel<true, 2>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
+      default: DET_LAUNCH((xchg_route_kernel<true, 1>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
+    }
+  }
+  xchg_wait(g, kFlagIns, ep, s);
+  {
+    const int avec = pick_vec(g->row_bytes, nullptr, nullptr, nullptr);
+    const RowGeom ageo = make_geom((unsigned)g->row_bytes, avec);
+    const TableView tv = g->local->view;
+    const int np = g->n_slot_planes;
+    switch (avec) {
+#define DET_XAPPLY(VV)                                                                                        \
+  case VV: {                                                                                                   \
+    const int grid = g->sm_count * occupancy_of(xchg_apply_insert_kernel<VV>, kThreadsP);                      \
+    DET_LAUNCH(xchg_apply_insert_kernel<VV>, grid, kThreadsP, 0, s, xv, tv, ageo, np, ticket, ep);             \
+  } break;
+      DET_XAPPLY(16) DET_XAPPLY(8) DET_XAPPLY(4) DET_XAPPLY(2)
+      default: {
+        const int grid = g->sm_count * occupancy_of(xchg_apply_insert_kernel<1>, kThreadsP);
+        DET_LAUNCH(xchg_apply_insert_kernel<1>, grid, kThreadsP, 0, s, xv, tv, ageo, np, ticket, ep);
+      } break;
+#undef DET_XAPPLY
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  peer_snapshot(g, s);
   return DET_OK;
 }
 

@@ -989,7 +989,7 @@ using namespace det;
 
 extern "C" {
 
-int det_abi_version(void) { return 4; }
+int det_abi_version(void) { return 5; }
 #ifdef DET_EMU
 unsigned long long det_emu_stat(int which) { return which >= 0 && which < 4 ? det::g_det_emu_stat[which] : 0; }
 #endif

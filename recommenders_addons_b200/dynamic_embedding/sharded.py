@@ -197,12 +197,62 @@ class PeerShardedVariable(object):
     import ctypes
     return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-  def lookup(self, keys, return_exists=False, default=None):
+  # ---- owner-side exchange (det_peer_xchg_*): ids travel to the owner, the owner probes locally and pushes rows ----
+  def attach_exchange(self, max_items, mailbox_ptrs=None, keepalive=None):
+    """Collective.  Gives every rank a MAILBOX all peers map (request / insert segments per source rank, a 2-entry
+    output ring, flag words); afterwards lookup() / upsert() run through the owners with posted NVLink stores only
+    (HvdVariable.__alltoall_embedding_lookup__, shadow_embedding_ops.py:397-447, without a collective library).
+    Every rank must then issue the same sequence of lookup / upsert calls (n may differ), as with the reference's
+    alltoall ops.  `mailbox_ptrs` (tests): explicit pointers instead of a symmetric-memory allocation."""
+    import ctypes
+    rb = self.dim * torch.empty(0, dtype=self.value_dtype).element_size()
+    nbytes = int(self._lib.det_peer_xchg_bytes(self.world, int(max_items), rb))
+    if nbytes == 0:
+      raise ValueError("attach_exchange: bad max_items / world")
+    if mailbox_ptrs is not None:
+      ptrs, self._xbox = [int(p) for p in mailbox_ptrs], keepalive
+    elif self.backing == "symmetric-memory":
+      import torch.distributed._symmetric_memory as symm_mem
+      box = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+      box.zero_()
+      hdl = symm_mem.rendezvous(box, self._group if self._group is not None else dist.group.WORLD)
+      ptrs = [int(p) for p in hdl.buffer_ptrs]
+      self._xbox = (box, hdl)
+      torch.cuda.synchronize(self.device)
+      dist.barrier(group=self._group)   # every mailbox is zeroed before any rank may write into it
+    else:
+      raise RuntimeError("the exchange mailbox needs the symmetric-memory backing (PeerShardedVariable.create)")
+    arr = (ctypes.c_void_p * self.world)(*ptrs)
+    self._libmod.check(self._lib.det_peer_xchg_attach(self._g, arr, int(max_items), rb))
+    self._xchg_items = int(max_items)
+    self._xchg = True
+
+  def _ring_view(self, ptr, n):
+    """torch view of n rows of the output ring (lives inside the mailbox allocation)"""
+    box = self._xbox[0]
+    es = torch.empty(0, dtype=self.value_dtype).element_size()
+    off = int(ptr) - box.data_ptr()
+    return box[off:off + n * self.dim * es].view(self.value_dtype).reshape(n, self.dim)
+
+  def lookup(self, keys, return_exists=False, default=None, copy=True):
     import ctypes
     flat = keys.reshape(-1).contiguous()
     n = flat.numel()
     d = self._default if default is None else default.contiguous()
     full = 1 if (n > 0 and d.numel() == n * self.dim) else 0
+    if getattr(self, "_xchg", False):
+      # copy=False: the rows are a VIEW of the output ring, valid until the next-but-one lookup (no extra HBM pass)
+      p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+      zero_copy = (not copy) and isinstance(self._xbox, tuple) and torch.is_tensor(self._xbox[0])
+      out = None if zero_copy else torch.empty((n, self.dim), dtype=self.value_dtype, device=self.device)
+      ex = torch.empty(n, dtype=torch.bool, device=self.device) if return_exists else None
+      view = ctypes.c_void_p()
+      self._libmod.check(self._lib.det_peer_xchg_find(self._g, p(flat), n, p(d), full, p(out), p(ex),
+                                                      ctypes.byref(view), self._sp()))
+      if zero_copy:
+        out = self._ring_view(view.value, n)
+      out = out.reshape(tuple(keys.shape) + (self.dim,))
+      return (out, ex.reshape(keys.shape)) if return_exists else out
     out = torch.empty((n, self.dim), dtype=self.value_dtype, device=self.device)
     ex = torch.empty(n, dtype=torch.bool, device=self.device) if return_exists else None
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -215,9 +265,16 @@ class PeerShardedVariable(object):
     flat = keys.reshape(-1).contiguous()
     vals = values.reshape(-1, self.dim).contiguous()
     p = lambda t: ctypes.c_void_p(t.data_ptr())
+    if getattr(self, "_xchg", False):
+      self._libmod.check(self._lib.det_peer_xchg_insert(self._g, p(flat), p(vals), flat.numel(), self._sp()))
+      return
     self._libmod.check(self._lib.det_peer_insert(self._g, p(flat), p(vals), flat.numel(), self._sp()))
 
   def phase_barrier(self):
+    """Separates a phase in which ranks read from one in which they write (one-sided kernels).  With the owner-side
+    exchange attached it is a no-op: every shard is read and written by its OWNER's kernels only, in stream order."""
+    if getattr(self, "_xchg", False):
+      return
     self._libmod.check(self._lib.det_peer_barrier(self._g, self._sp()))
 
   # ---- one-sided all-to-all-v: (key, row) pairs travel to the owner's inbox (backward path) ---------------

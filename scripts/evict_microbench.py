@@ -11,7 +11,11 @@ import time
 import numpy as np
 import torch
 
-from recommenders_addons_b200 import dynamic_embedding as de
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from recommenders_addons_b200 import dynamic_embedding as de  # noqa: E402
 
 
 def ev_time(fn, reps=5):

@@ -10,7 +10,11 @@ import json
 import numpy as np
 import torch
 
-from recommenders_addons_b200 import dynamic_embedding as de
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from recommenders_addons_b200 import dynamic_embedding as de  # noqa: E402
 
 
 def ev_time(fn, reps=7):

@@ -24,6 +24,10 @@ def test_reference_arm_prints_contract_line():
     assert k in d, k
   assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
   assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+  assert d["steps"] >= 20 and d["warmup"] >= 5                       # enough timed steps for a stable median
+  cores = d["cpu_baseline"]["host_cores"]
+  assert d["cpu_baseline"]["cores"] == cores["used"] <= cores["affinity"]   # never more workers than usable cores
+  assert d["cpu_baseline"]["parity_mismatches_first_batch"] == 0
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():
@@ -42,6 +46,10 @@ def test_zipf_key_stream_helpers():
   kt = B.rank_to_key_torch(torch.from_numpy(r)).numpy()
   np.testing.assert_array_equal(kn, kt)              # both arms draw the same key for the same rank
   assert (kn >= 0).all() and np.unique(kn).shape[0] == 1000
+  # the closed-form rows both arms (and the in-bench parity check) use: exact in fp32, torch == numpy
+  for gen in (0, 1):
+    np.testing.assert_array_equal(B.rows_of_keys_np(kn, 16, gen), B.rows_of_keys_torch(torch.from_numpy(kn), 16, gen).numpy())
+  assert not np.array_equal(B.rows_of_keys_np(kn, 16, 0), B.rows_of_keys_np(kn, 16, 1))
   cdf = B.zipf_cdf_np(10000)
   b = B.zipf_unique_batch_np(cdf, 2000, np.random.default_rng(0))
   assert b.shape[0] == 2000 and np.unique(b).shape[0] == 2000 and b.max() < 10000

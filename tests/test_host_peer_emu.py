@@ -23,7 +23,8 @@ _EXTRA = ["det_find_host", "det_insert_host", "det_find_host_async", "det_insert
           "det_load", "det_export_window", "det_peer_handle_bytes", "det_peer_export", "det_peer_group_create", "det_peer_group_destroy",
           "det_peer_find", "det_peer_insert", "det_peer_barrier", "det_peer_inbox_bytes", "det_peer_inbox_attach",
           "det_peer_route", "det_peer_inbox_counts", "det_peer_inbox_gather", "det_table_region_bytes",
-          "det_table_create_in_region", "det_peer_group_create_regions"]
+          "det_table_create_in_region", "det_peer_group_create_regions", "det_peer_xchg_bytes", "det_peer_xchg_attach",
+          "det_peer_xchg_find", "det_peer_xchg_insert"]
 
 
 def X():
@@ -259,6 +260,112 @@ def test_multi_rank_group_threads_as_ranks():
     st = t.stats()
     assert st["error_flags"] == 0
     t.close()
+
+
+@pytest.mark.parametrize("world,dim", [(2, 4), (3, 16)])
+def test_owner_side_exchange_threads_as_ranks(world, dim):
+  """det_peer_xchg_find / det_peer_xchg_insert (the push-only sharded path): every rank a thread with its own shard,
+  group and mailbox.  Several rounds of insert -> lookup with changing values, misses with a broadcast default and with
+  per-key defaults, exists masks, ranks with DIFFERENT batch sizes (one of them empty), no barrier call anywhere:
+  the flag words alone order owner-side reads and writes.  Every lookup must see exactly the dict model."""
+  per, rounds, cap = 300, 4, 512
+  rng = np.random.default_rng(11 + world)
+  pool = rng.choice(1 << 40, size=world * per, replace=False).astype(np.int64)
+  owner = O.default_partition_fn(pool, world, True)
+  tables = [Table(dim=dim, init=4096, max_capacity=4096) for _ in range(world)]
+  hb = X().det_peer_handle_bytes()
+  blob = (ctypes.c_ubyte * (hb * world))()
+  for r in range(world):
+    ck(X().det_peer_export(tables[r].h, ctypes.c_void_p(ctypes.addressof(blob) + r * hb)))
+  rb = dim * 4
+  nbytes = X().det_peer_xchg_bytes(world, cap, rb)
+  assert nbytes > 0 and X().det_peer_xchg_bytes(9, cap, rb) == 0
+  raw = [np.zeros(nbytes + 256, dtype=np.uint8) for _ in range(world)]
+  boxes = [b[(-b.ctypes.data) % 256:][:nbytes] for b in raw]
+  # the schedule, known to every rank: round -> per rank (keys inserted, values) ; model applied in rank order is NOT
+  # needed because a key is written by exactly one rank per round
+  sched = []
+  for t in range(rounds):
+    perm = rng.permutation(world * per)
+    parts = np.array_split(perm[: world * per - 50 * t], world)          # differing sizes per rank and round
+    if t == 1:
+      parts[0] = parts[0][:0]                                             # rank 0 sends nothing in round 1
+    vals = [rng.standard_normal((len(q), dim)).astype(np.float32) for q in parts]
+    sched.append((parts, vals))
+  errors, results = [], {}
+  start = threading.Barrier(world)
+
+  def rank_main(r):
+    try:
+      tl = [None] * world
+      tl[r] = tables[r]
+      g = PeerGroup(tl, ctypes.cast(blob, ctypes.c_void_p), world, r)
+      ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boxes])
+      ck(X().det_peer_xchg_attach(g.g, ptrs, cap, rb))
+      assert X().det_peer_xchg_attach(g.g, ptrs, cap, rb + 4) != 0       # row size must match the shards
+      start.wait()
+      model, got = {}, []
+      for t in range(rounds):
+        parts, vals = sched[t]
+        keys = np.ascontiguousarray(pool[parts[r]])
+        v = np.ascontiguousarray(vals[r])
+        ck(X().det_peer_xchg_insert(g.g, P(keys) if len(keys) else None, P(v) if len(keys) else None, len(keys), None))
+        for q in range(world):                                           # what the whole job wrote this round
+          for k, row in zip(pool[parts[q]].tolist(), vals[q]):
+            model[k] = row
+        # lookup: a rank-specific sample of everything + two keys nobody owns
+        m = 200 + 37 * r if not (t == 2 and r == world - 1) else 0      # one rank looks up nothing in round 2
+        q = np.concatenate([rng_r[r].choice(pool, size=m, replace=False), np.array([-5 - r, 1 << 50], np.int64)]) if m else np.zeros(0, np.int64)
+        n = len(q)
+        out = np.full((max(n, 1), dim), np.nan, np.float32)
+        ex = np.zeros(max(n, 1), np.uint8)
+        view = ctypes.c_void_p()
+        if t % 2 == 0:
+          d = np.full(dim, 0.25, np.float32)                              # broadcast default (same on every rank)
+          ck(X().det_peer_xchg_find(g.g, P(q) if n else None, n, P(d), 0, P(out), P(ex), ctypes.byref(view), None))
+          exp_miss = lambda j: d
+        else:
+          d = rng_r[r].standard_normal((max(n, 1), dim)).astype(np.float32)   # per-key defaults (full size)
+          ck(X().det_peer_xchg_find(g.g, P(q) if n else None, n, P(d), 1, P(out), P(ex), ctypes.byref(view), None))
+          exp_miss = lambda j: d[j]
+        for j in range(n):
+          k = int(q[j])
+          if k in model:
+            assert ex[j] == 1
+            np.testing.assert_array_equal(out[j], model[k])
+          else:
+            assert ex[j] == 0
+            np.testing.assert_array_equal(out[j], exp_miss(j))
+        if n:   # the zero-copy ring view holds the same rows
+          ring = np.ctypeslib.as_array(ctypes.cast(view.value, ctypes.POINTER(ctypes.c_float)), shape=(n, dim))
+          np.testing.assert_array_equal(ring, out[:n])
+        got.append(n)
+      results[r] = got
+      g.close()
+    except BaseException as e:  # pragma: no cover
+      import traceback
+      errors.append((r, traceback.format_exc()))
+      try:
+        start.abort()
+      except Exception:
+        pass
+
+  rng_r = [np.random.default_rng(100 + r) for r in range(world)]
+  th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+  for x in th:
+    x.start()
+  for x in th:
+    x.join(timeout=600)
+  assert not errors, errors
+  assert len(results) == world
+  written = set()
+  for parts, _ in sched:
+    for q in parts:
+      written.update(pool[q].tolist())
+  for r in range(world):
+    assert tables[r].size() == sum(1 for k in written if O.default_partition_fn(np.array([k]), world, True)[0] == r)
+    assert tables[r].stats()["error_flags"] == 0
+    tables[r].close()
 
 
 def test_bounded_table_reserve_clear_import_and_load(tmp_path):

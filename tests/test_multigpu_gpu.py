@@ -23,10 +23,12 @@ def _worker(rank, world, port, q):
   ok = True
   msg = ""
   try:
-    for mode in ("nccl", "peer", "symm"):
-      if mode == "symm":  # shard inside a torch symmetric-memory region (CUDA VMM): the production path
-        sv = de.PeerShardedVariable.create(dim, 1 << 18, initializer=-1.0, name="mg-symm-%d" % rank)
+    for mode in ("nccl", "peer", "symm", "push"):
+      if mode in ("symm", "push"):  # shard inside a torch symmetric-memory region (CUDA VMM): the production path
+        sv = de.PeerShardedVariable.create(dim, 1 << 18, initializer=-1.0, name="mg-%s-%d" % (mode, rank))
         var = sv.local
+        if mode == "push":          # owner-side exchange: ids to the owner, local probe, rows pushed back; no barriers
+          sv.attach_exchange(1 << 16)
       else:
         var = de.Variable(dim=dim, init_size=1 << 18, initializer=-1.0, name="mg-%s-%d" % (mode, rank))
         sv = de.ShardedVariable(var) if mode == "nccl" else de.PeerShardedVariable(var)
@@ -95,6 +97,36 @@ def _worker(rank, world, port, q):
         dist.barrier()
         if not np.allclose(got3, expect, rtol=1e-6, atol=1e-8):
           ok, msg = False, "layer backward: %r vs %r" % (got3[0, 0], expect)
+      if mode == "push":
+        # several rounds of rewrite -> read with NO barrier in between: the flag words alone must order every owner's
+        # reads after the writes of the same round (the horovod_sync_train_test shape: values change every step)
+        model = dict(zip(allkeys.tolist(), allvals))
+        for rnd in range(1, 4):
+          sub = allkeys[mine][rnd::5]
+          newv = (allvals[mine][rnd::5] + np.float32(rnd)).astype(np.float32)
+          sv.upsert(torch.from_numpy(np.ascontiguousarray(sub)).to(dev), torch.from_numpy(np.ascontiguousarray(newv)).to(dev))
+          for r2 in range(world):   # what EVERY rank wrote this round
+            k2 = allkeys[slice(r2, None, world)][rnd::5]
+            v2 = (allvals[slice(r2, None, world)][rnd::5] + np.float32(rnd)).astype(np.float32)
+            model.update(zip(k2.tolist(), v2))
+          qk = np.concatenate([allkeys[rnd::7], np.array([5 * 10**6 + rank, -5 * 10**6 - rank], np.int64)])
+          got_r, got_e = sv.lookup(torch.from_numpy(qk).to(dev), return_exists=True)
+          exp_r = np.stack([model.get(int(k), np.full(dim, -1, np.float32)) for k in qk])
+          exp_e = np.array([int(k) in model for k in qk])
+          if not (np.array_equal(got_r.cpu().numpy(), exp_r) and np.array_equal(got_e.cpu().numpy(), exp_e)):
+            ok, msg = False, "push mode: round %d lookup differs from the model" % rnd
+          # per-key default rows (full-size default) for the misses
+          fd = torch.from_numpy(np.random.default_rng(rnd).normal(0, 1, (len(qk), dim)).astype(np.float32)).to(dev)
+          got_f = sv.lookup(torch.from_numpy(qk).to(dev), default=fd).cpu().numpy()
+          exp_f = np.where(exp_e[:, None], exp_r, fd.cpu().numpy())
+          if not np.array_equal(got_f, exp_f):
+            ok, msg = False, "push mode: full-size defaults in round %d" % rnd
+          # zero-copy ring view == copied rows
+          v1 = sv.lookup(torch.from_numpy(qk).to(dev), copy=False)
+          if not np.array_equal(v1.cpu().numpy(), exp_r):
+            ok, msg = False, "push mode: ring view in round %d" % rnd
+        torch.cuda.synchronize()
+        dist.barrier()
       if var.tables[0].stats()["error_flags"] != 0:
         ok, msg = False, "error flags in mode %s" % mode
   except Exception as e:  # noqa: BLE001
