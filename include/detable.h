@@ -23,6 +23,18 @@
  *   - keys inside ONE mutating call must be unique (same contract as the reference's GPU
  *     table, python/ops/dynamic_embedding_variable.py:1377-1378).  Duplicates are memory-safe:
  *     the key is stored once; insert keeps one of the rows per 16-byte chunk, accum adds all.
+ *   - concurrency (the reference serialises every op on one table with a reader/writer mutex,
+ *     kernels/hkv_hashtable_op_gpu.cu.cc:201,258; here calls are stream-ordered instead):
+ *       * calls on ONE stream see each other's effects in issue order;
+ *       * read-only calls (det_find, det_find_scores, det_lookup_sparse, det_peer_find) may run
+ *         concurrently on any streams / host threads, also while another host thread grows the
+ *         table (det_find holds a shared host lock against the plane swap);
+ *       * a read-only call and a mutating call that overlap in time on DIFFERENT streams (e.g.
+ *         det_find_host_async + det_insert_host_async) are only defined for DISJOINT key sets:
+ *         a row being rewritten may be read torn (16-byte chunks of the old and new row), keys
+ *         are never torn and no other key is affected;
+ *       * two mutating calls on one table must be stream-ordered (host bookkeeping is
+ *         serialised by a per-table mutex, device work is not).
  */
 #ifndef DETABLE_H_
 #define DETABLE_H_
@@ -72,7 +84,8 @@ typedef struct det_config {
   int32_t device;           /* CUDA device ordinal */
   int32_t num_slot_planes;  /* 0..3 optimizer slot planes co-indexed with the value rows (fp32 only) */
   uint64_t init_capacity;   /* keys; 0 -> 8192 (TF_HASHTABLE_INIT_SIZE default, cuckoo_hashtable_op.cc:199-205) */
-  uint64_t max_capacity;    /* keys; 0 -> grow without bound (cuckoo semantics); else DET_TABLE_FULL beyond it */
+  uint64_t max_capacity;    /* SLOTS (HKV's max_capacity); 0 -> grow without bound (cuckoo semantics); else the table
+                             * holds at most max_load_factor * max_capacity keys and answers DET_TABLE_FULL beyond */
   float max_load_factor;    /* 0 -> 0.75 (0.875 with an eviction strategy) */
   uint32_t flags;           /* bits 0..3: eviction strategy + 1 (DET_FLAGS_EVICT), 0 = none; other bits reserved, 0 */
   uint64_t max_hbm_for_vectors; /* ABI >= 3.  Bytes of HBM the VALUE rows may take (attr `max_hbm_for_vectors`,

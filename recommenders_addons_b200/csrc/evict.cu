@@ -115,11 +115,18 @@ det_status evict_on_rehash(det_table* t, const TableView& ov, const TableView& n
   const size_t ocap = ov.capacity(), ncap = nv.capacity();
   unsigned long long* ns = nullptr;
   CUDA_TRY(cudaMalloc((void**)&ns, (ncap + 2) * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemsetAsync(ns, 0, (ncap + 2) * sizeof(unsigned long long), s));
-  DET_LAUNCH(carry_scores_kernel, grid_for(ocap, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, ov, ev->scores, nv, ns);
-  CUDA_TRY(cudaMemcpyAsync(ns + ncap, ev->scores + ocap, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s));
+  cudaError_t ce = cudaMemsetAsync(ns, 0, (ncap + 2) * sizeof(unsigned long long), s);
+  if (ce == cudaSuccess) {
+    DET_LAUNCH(carry_scores_kernel, grid_for(ocap, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, ov, ev->scores, nv, ns);
+    ce = cudaMemcpyAsync(ns + ncap, ev->scores + ocap, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s);
+  }
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (ce != cudaSuccess) {   // keep the old score plane, give the new one back
+    cudaGetLastError();
+    cudaFree(ns);
+    return fail(DET_CUDA_ERROR, std::string("evict_on_rehash: ") + cudaGetErrorString(ce));
+  }
   cudaFree(ev->scores);
   ev->scores = ns;
   return DET_OK;
@@ -171,9 +178,11 @@ static det_status repair_rounds(det_table* t, cudaStream_t s) {
     CUDA_TRY(cudaGetLastError());
     det_status st = read_dev(t, s);
     if (st != DET_OK) return st;
-    if (ev->h_dev->n_moved == 0 && ev->h_dev->n_erased == 0) break;
+    if (ev->h_dev->n_moved == 0 && ev->h_dev->n_erased == 0) return DET_OK;
   }
-  return DET_OK;
+  // the fixed point was not reached: live keys may sit behind EMPTY buckets or as stale duplicates, and size / used
+  // would no longer describe what lookups see -- never report that as success
+  return fail(DET_INTERNAL, "detable: the eviction repair did not converge within 256 rounds (table state is inconsistent)");
 }
 
 // det_remove leaves tombstones in full buckets; on a table that cannot be rehashed into bigger planes they are purged
@@ -368,6 +377,7 @@ det_status det_find_scores(det_table* t, const int64_t* keys, size_t n, uint64_t
   if (!keys || !scores_out) return fail(DET_INVALID_ARGUMENT, "det_find_scores: null argument");
   det::DevGuard _dg(t->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
+  std::shared_lock<std::shared_mutex> _vl(t->view_mu);
   DET_LAUNCH(scores_of_keys_kernel, grid_for(n, kThreadsE, t->sm_count, 8), kThreadsE, 0, s, 
       t->view, (const long long*)keys, n, t->ev->scores, (unsigned long long*)scores_out, 0);
   CUDA_TRY(cudaGetLastError());

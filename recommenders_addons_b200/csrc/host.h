@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <type_traits>
 
@@ -103,6 +104,11 @@ struct det_table {
   // host-side bookkeeping of mutating / scratch-using entry points (the reference takes a mutex for mutators and a
   // shared lock for readers, hkv_hashtable_op_gpu.cu.cc:201-364; det_find needs no host lock)
   std::mutex mu;
+  // Readers that take no `mu` (det_find, det_find_scores: no bookkeeping, CUDA-graph capturable) hold this SHARED while
+  // they copy `view` and enqueue their kernel; rehash_to holds it EXCLUSIVELY around "device-wide sync, free the old
+  // planes, swap view".  A find launched from another host thread therefore either completed before the old planes
+  // are freed or already sees the new ones (the reference: tf_shared_lock for readers, hkv_hashtable_op_gpu.cu.cc:201).
+  std::shared_mutex view_mu;
   det_config cfg;
   size_t row_bytes = 0;
   float max_lf = 0.75f;

@@ -841,9 +841,6 @@ det_status det_peer_xchg_attach(det_peer_group* g, const void* const* mailbox_pt
   if (!g->xcursor) {
     CUDA_TRY(cudaMalloc((void**)&g->xcursor, (kMaxPeers + 1) * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(g->xcursor, 0, (kMaxPeers + 1) * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMallocHost((void**)&g->h_snap, sizeof(DevState)));
-    memset(g->h_snap, 0, sizeof(DevState));
-    CUDA_TRY(cudaEventCreateWithFlags(&g->snap_ev, cudaEventDisableTiming));
   }
   g->ep_find = g->ep_ins = 0;
   g->xchg = true;
@@ -863,6 +860,11 @@ static void xchg_wait(det_peer_group* g, int which, unsigned long long epoch, cu
 // snapshot shows the shard over its load limit or carrying the sticky table-full bit, instead of degrading silently.
 static det_status peer_room(det_peer_group* g, const char* who) {
   det_table* t = g->local;
+  if (!g->h_snap) {   // first mutating call of a group without an exchange mailbox
+    CUDA_TRY(cudaMallocHost((void**)&g->h_snap, sizeof(DevState)));
+    memset(g->h_snap, 0, sizeof(DevState));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->snap_ev, cudaEventDisableTiming));
+  }
   if (g->snap_inflight && cudaEventQuery(g->snap_ev) == cudaSuccess) {
     g->snap_inflight = false;
     t->used_ub = g->h_snap->used;           // remote / owner-side inserts never went through ensure_room
@@ -1046,6 +1048,12 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_peer_insert: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   det::DevGuard _dg(g->device);
+  // remote claims never pass through the owner's ensure_room: the shard's own state snapshot is the room check
+  // (a full shard fails the NEXT call loudly instead of dropping keys behind a sticky bit nobody reads)
+  {
+    det_status rs = peer_room(g, "det_peer_insert");
+    if (rs != DET_OK) return rs;
+  }
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
   const int grid = grid_for(n, kThreadsP, g->sm_count, occupancy_of(peer_insert_kernel<16>, kThreadsP));
@@ -1060,6 +1068,7 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
     default: DET_LAUNCH(peer_insert_kernel<1>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
   }
   CUDA_TRY(cudaGetLastError());
+  peer_snapshot(g, s);
   return DET_OK;
 }
 

@@ -808,20 +808,37 @@ det_status rehash_to(det_table* t, uint64_t new_nb, cudaStream_t s) {
     DET_LAUNCH(rehash_kernel<decltype(V)::value>, grid, kThreads, 0, s, ov, nv, g, gs, np);
     return DET_OK;
   });
+  // an error from here on must not leak the new planes (the table keeps its old ones and stays usable)
+  auto drop_new = [&](det_status code) {
+    cudaDeviceSynchronize();  // the rehash kernel may still be writing the new planes
+    cudaGetLastError();
+    for (int i = 0; i < 1 + kMaxPlanes; ++i)
+      if (raw[i]) cudaFree(raw[i]);
+    return code;
+  };
   // special rows
   for (int p = 0; p <= np; ++p) {
     const size_t rb = p == 0 ? t->row_bytes : (size_t)t->cfg.dim * 4u;
-    CUDA_TRY(cudaMemcpyAsync(nv.planes[p] + ncap * rb, ov.planes[p] + ov.capacity() * rb, 2 * rb,
-                             cudaMemcpyDeviceToDevice, s));
+    const cudaError_t ce = cudaMemcpyAsync(nv.planes[p] + ncap * rb, ov.planes[p] + ov.capacity() * rb, 2 * rb,
+                                           cudaMemcpyDeviceToDevice, s);
+    if (ce != cudaSuccess) return drop_new(fail(DET_CUDA_ERROR, std::string("rehash: ") + cudaGetErrorString(ce)));
   }
   DET_LAUNCH(rehash_fix_state_kernel, 1, 1, 0, s, t->view.st);
-  CUDA_TRY(cudaGetLastError());
+  {
+    const cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return drop_new(fail(DET_CUDA_ERROR, std::string("rehash: ") + cudaGetErrorString(ce)));
+  }
+  // the old planes (and the old score plane) are freed below: nothing on ANY stream may still be reading them (async
+  // host pipelines), and no lock-free reader may be between "copied the old view" and "enqueued its kernel" (view_mu)
+  std::unique_lock<std::shared_mutex> _vl(t->view_mu);
+  {
+    const cudaError_t ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return drop_new(fail(DET_CUDA_ERROR, std::string("rehash: ") + cudaGetErrorString(ce)));
+  }
   if (t->ev) {  // scores follow their keys into the new planes
     st = evict_on_rehash(t, ov, nv, s);
-    if (st != DET_OK) return st;
+    if (st != DET_OK) return drop_new(st);
   }
-  // the old planes are freed below: nothing on ANY stream may still be reading them (async host pipelines)
-  CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 1 + kMaxPlanes; ++i)
     if (t->raw[i]) cudaFree(t->raw[i]);
   for (int i = 0; i < 1 + kMaxPlanes; ++i) t->raw[i] = raw[i];
@@ -1162,6 +1179,7 @@ det_status det_find(det_table* t, const int64_t* keys, size_t n, const void* def
   det::DevGuard _dg(t->cfg.device);
   const int vec = pick_vec(t->row_bytes, defaults, values_out, nullptr);
   const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
+  std::shared_lock<std::shared_mutex> _vl(t->view_mu);   // vs a concurrent growth on another host thread (host.h)
   const TableView v = t->view;
   // variant 1 (default): persistent CTAs + TMA-staged key tiles; needs 16 B aligned keys.  DET_FIND_VARIANT=0
   // selects the plain grid-stride kernel.

@@ -139,12 +139,25 @@ class AllToAllEmbedding(torch.nn.Module):
     return gather_unique(rows, idx).reshape(tuple(ids.shape) + (self.embedding_size,))
 
   def apply_gradients(self, optimizer, max_unique_per_rank=None):
+    """COLLECTIVE: every rank calls it once per forward, whatever happened to its own gradients.  The inbox capacity is
+    agreed by all ranks (an all-reduce MAX of the largest per-rank unique count, unless `max_unique_per_rank` is given
+    identically everywhere): attach_inbox is itself collective and the inbox segment offsets depend on the capacity,
+    so a rank-local decision could hang the job or misplace remote writes.  A rank whose rows received no gradient
+    routes zeros instead of skipping the exchange."""
+    import torch.distributed as dist
     for uniq, rows in self._pending:
-      if rows.grad is None:
-        continue
-      need = int(max_unique_per_rank or uniq.numel())
+      grad = rows.grad if rows.grad is not None else torch.zeros_like(rows)
+      if max_unique_per_rank is not None:
+        need = int(max_unique_per_rank)
+      else:
+        t = torch.tensor([uniq.numel()], dtype=torch.int64, device=uniq.device)
+        if dist.is_available() and dist.is_initialized() and self.params.world > 1:
+          dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.params._group)
+        need = int(t.item())
+      if uniq.numel() > need:
+        raise ValueError("AllToAllEmbedding.apply_gradients: %d unique ids exceed max_unique_per_rank=%d" % (uniq.numel(), need))
       if need > self._inbox_items:
-        self.params.attach_inbox(max(need, 2 * self._inbox_items))  # collective
-        self._inbox_items = max(need, 2 * self._inbox_items)
-      self.params.apply_gradients(optimizer, uniq, rows.grad)
+        self._inbox_items = max(need, 2 * self._inbox_items)   # same value on every rank: a function of agreed numbers
+        self.params.attach_inbox(self._inbox_items)            # collective
+      self.params.apply_gradients(optimizer, uniq, grad)
     self._pending = []

@@ -155,7 +155,8 @@ class _FusedBase(object):
       grads = gather_rows(grads, perm)
     for idx, (b, e) in enumerate(bounds):
       if e > b:
-        self._apply_table(params, params.tables[idx], grouped[b:e].contiguous(), grads[b:e].contiguous())
+        t = params.tables[idx]   # raw pointers cross the C ABI: keys and gradients must live on the shard's own GPU
+        self._apply_table(params, t, grouped[b:e].to(t.device).contiguous(), grads[b:e].to(t.device).contiguous())
 
 
   def apply_sparse_duplicate_indices(self, params, ids, grads):

@@ -306,11 +306,14 @@ class Variable(object):
       part = grouped[b:e]
       dyn = self._create_default_values_by_initializer(e - b, self._tables[idx].device) if e > b else None
       r = self._tables[idx].lookup(part, dynamic_default_values=dyn, return_exists=return_exists)
+      # shards on different GPUs answer on their own device: gather every shard's rows on ONE device (the first
+      # shard's, where `perm` lives) before they are concatenated and stitched back into request order
+      out_dev = self._tables[0].device
       if return_exists:
-        vals.append(r[0])
-        exs.append(r[1])
+        vals.append(r[0].to(out_dev))
+        exs.append(r[1].to(out_dev))
       else:
-        vals.append(r)
+        vals.append(r.to(out_dev))
     values = vals[0] if len(vals) == 1 else torch.cat(vals, 0)
     if perm is not None:
       values = scatter_rows(values, perm)
