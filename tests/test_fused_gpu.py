@@ -97,6 +97,64 @@ def test_lookup_sparse_bit_exact_vs_oracle(combiner, use_weights, dim):
   assert tw.ids.numel() == np.unique(ids).shape[0]
 
 
+def test_lookup_sparse_c3_sized_bit_exact():
+  """BASELINE configs[2] size: 26 features x batch 65536 = 1,703,936 ids, dim 64, Zipf-skewed with repeats, ~10 % of
+  the ids absent -> det_lookup_sparse must equal the oracle BIT FOR BIT in both shapes the workload comes in:
+  (A) one output row per (sample, feature) (bench.py --workload c3), (B) the 26 ids of a sample combined into one row
+  (weighted mean).  The oracle's per-id Python loop is vectorised over ROWS here (26 sequential fp32 mul+add passes in
+  id order, the same operations in the same order); that vectorisation is itself pinned against
+  oracle.embedding_lookup_sparse on a prefix."""
+  torch = _torch()
+  from recommenders_addons_b200 import dynamic_embedding as de
+  from recommenders_addons_b200.dynamic_embedding.ops import lookup_sparse_fused
+  rng = np.random.default_rng(2026)
+  dim, nfeat, batch = 64, 26, 65536
+  nnz = nfeat * batch
+  vocab = np.maximum(1000, np.exp(rng.uniform(np.log(1e3), np.log(3e5), nfeat))).astype(np.int64)
+  offs = np.concatenate([[0], np.cumsum(vocab)])[:-1]
+  cols = []
+  for f in range(nfeat):   # Zipf(1.05) over the feature's vocabulary, one id per (sample, feature)
+    w = np.arange(1, vocab[f] + 1, dtype=np.float64) ** -1.05
+    cdf = np.cumsum(w) / w.sum()
+    cols.append(np.minimum(np.searchsorted(cdf, rng.random(batch)), vocab[f] - 1) + offs[f])
+  ranks = np.stack(cols, 1).reshape(-1).astype(np.int64)                 # row-major (sample, feature)
+  ids = (ranks * np.int64(2654435761) + 12345) ^ (ranks << 20)            # scrambled int64 keys, injective
+  uniq = np.unique(ids)
+  present = uniq[rng.random(uniq.shape[0]) < 0.9]
+  vals = rng.normal(0, 0.05, (present.shape[0], dim)).astype(np.float32)
+  var = de.Variable(dim=dim, initializer=0.125, init_size=4 * present.shape[0], name="sp-c3")
+  dev = var.tables[0].device
+  var.upsert(torch.from_numpy(present).to(dev), torch.from_numpy(vals).to(dev))
+  ot = O.PortTable(dim)
+  ot.insert(present, vals)
+  default = np.full(dim, 0.125, np.float32)
+  u, inv = O.unique_first_occurrence(ids)
+  emb = ot.find(u, default)[inv]                                          # [nnz, dim] rows in id order
+  t_ids = torch.from_numpy(ids).to(dev)
+  # (A) one id per output row, combiner sum: the output is the gathered rows themselves (0 + row * 1)
+  seg_a = torch.arange(nnz, dtype=torch.int32, device=dev)
+  got_a = lookup_sparse_fused(var, t_ids, seg_a, None, nnz, "sum")
+  exp_a = (np.zeros_like(emb) + emb * np.float32(1)).astype(np.float32)
+  assert torch.equal(got_a.cpu(), torch.from_numpy(exp_a))
+  del got_a
+  # (B) 26 ids per row, weighted mean
+  wts = rng.uniform(0.25, 2.0, nnz).astype(np.float32)
+  seg_b = (np.arange(nnz) // nfeat).astype(np.int32)
+  got_b = lookup_sparse_fused(var, t_ids, torch.from_numpy(seg_b).to(dev), torch.from_numpy(wts).to(dev), batch, "mean")
+  e3, w3 = emb.reshape(batch, nfeat, dim), wts.reshape(batch, nfeat)
+  out = np.zeros((batch, dim), np.float32)
+  wsum = np.zeros(batch, np.float32)
+  for j in range(nfeat):
+    out = out + e3[:, j] * w3[:, j, None]
+    wsum = wsum + w3[:, j]
+  exp_b = (out / wsum[:, None]).astype(np.float32)
+  np.testing.assert_array_equal(got_b.cpu().numpy(), exp_b)
+  # the vectorised oracle == the per-id loop of oracle.embedding_lookup_sparse on a prefix of 1500 rows
+  m = 1500 * nfeat
+  ref = O.embedding_lookup_sparse(ot, ids[:m], seg_b[:m], wts[:m], 1500, "mean", default=default)
+  np.testing.assert_array_equal(exp_b[:1500], ref)
+
+
 def test_lookup_sparse_reference_test_vectors():
   """EmbeddingLookupSparseTest grouping (dynamic_embedding_ops_test.py:875-969), rtol=atol=1e-6 against the
   reference test's own NumPy formulation."""
