@@ -701,7 +701,8 @@ template <int OPT, bool SCORED = false>
 __global__ void __launch_bounds__(kThreadsF)
 apply_staged_kernel(TableView t, const long long* __restrict__ keys, const float* __restrict__ grads, size_t n,
                     OptHyper h, const float* __restrict__ init_param, int full_init, unsigned vpr, unsigned lpr,
-                    unsigned lpr_shift, int use_tma, ScoreArg<SCORED> sa) {
+                    unsigned lpr_shift, int use_tma, ScoreArg<SCORED> sa, const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;        // key count produced on the device (det_apply_*_dup); the grid covers the bound
   constexpr int NS = OPT == 0 ? 3 : 4;  // streams per row: grad, param, slot1 (, slot2)
   DET_DYN_SHARED(dyn_smem);
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
@@ -968,6 +969,8 @@ constexpr int kRadixThreads = 256;                 // == kRadixBins: thread t ow
 constexpr int kRadixItems = 8;                     // items per thread
 constexpr int kRadixTile = kRadixThreads * kRadixItems;
 constexpr int kLongGroup = 64;                     // groups with more rows go to the CTA-cooperative path
+constexpr int kHugeGroup = 1024;                   // ... and beyond this a group is split into 16-column slices (one work item each)
+constexpr int kSliceCols = 16;                     // 64 B of every row: still two full 32 B sectors per access
 constexpr int kLongTileFloats = 8192;              // 32 KB of staged rows per CTA
 constexpr int kLongTileRows = 256;                 // staged positions per tile (<= kLongTileFloats / columns)
 constexpr int kLongCols = 1024;                    // columns staged at a time (rows wider than this: several sweeps)
@@ -1087,8 +1090,10 @@ radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ k
 }
 
 // starts[g] = first sorted position whose key is >= g (g = 0..n_groups); keys are sorted, "dropped" rows carry n_groups
+// `ngd` (nullable): the group count lives on the device (det_apply_*_dup: n_unique of det_unique, never read by the host)
 __global__ void group_starts_kernel(const unsigned* __restrict__ keys, size_t n, unsigned n_groups,
-                                    unsigned* __restrict__ starts) {
+                                    unsigned* __restrict__ starts, const long long* __restrict__ ngd) {
+  if (ngd) n_groups = (unsigned)*ngd;
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j > n) return;
   const long long cur = j < n ? (long long)keys[j] : (long long)n_groups;
@@ -1096,29 +1101,58 @@ __global__ void group_starts_kernel(const unsigned* __restrict__ keys, size_t n,
   for (long long g = prev + 1; g <= cur; ++g) starts[g] = (unsigned)j;
 }
 
-__global__ void group_long_kernel(const unsigned* __restrict__ starts, unsigned n_groups, unsigned* __restrict__ long_list,
-                                  unsigned* __restrict__ n_long) {
+// work lists of the CTA-cooperative path: ctr[0] = long groups (kLongGroup < rows), ctr[1] = huge groups (> kHugeGroup rows
+// of sliceable rows), ctr[2] = the work queue's cursor
+__global__ void group_long_kernel(const unsigned* __restrict__ starts, unsigned n_groups, int sliceable,
+                                  unsigned* __restrict__ long_list, unsigned* __restrict__ huge_list,
+                                  unsigned* __restrict__ ctr, const long long* __restrict__ ngd) {
+  if (ngd) n_groups = (unsigned)*ngd;
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  if (starts[g + 1] - starts[g] > (unsigned)kLongGroup) long_list[atomicAdd(n_long, 1u)] = (unsigned)g;
+  const unsigned len = starts[g + 1] - starts[g];
+  if (sliceable && len > (unsigned)kHugeGroup) huge_list[atomicAdd(&ctr[1], 1u)] = (unsigned)g;
+  else if (len > (unsigned)kLongGroup) long_list[atomicAdd(&ctr[0], 1u)] = (unsigned)g;
 }
 
 template <int VF>
 __global__ void __launch_bounds__(kThreadsF)
 segment_reduce_kernel(const float* __restrict__ rows, const unsigned* __restrict__ pos,
                       const unsigned* __restrict__ starts, unsigned n_groups, unsigned dim, unsigned vpr, unsigned lpr,
-                      unsigned lpr_shift, const unsigned* __restrict__ long_list, const unsigned* __restrict__ n_long_p,
-                      int n_long_ctas, float* __restrict__ out) {
+                      unsigned lpr_shift, const unsigned* __restrict__ long_list, const unsigned* __restrict__ huge_list,
+                      unsigned* __restrict__ ctr, int n_long_ctas, float* __restrict__ out,
+                      const long long* __restrict__ ngd) {
+  if (ngd) n_groups = (unsigned)*ngd;
   if ((int)blockIdx.x < n_long_ctas) {
-    // ---- long groups: one CTA per group, rows staged tile by tile, thread c adds column c in position order ----
+    // ---- long groups: a CTA per work item, rows staged tile by tile, thread c adds column c in position order ----
+    // Work items come from a queue (atomic cursor), the HUGE groups first: the Zipf head owns thousands of rows of
+    // one key, and a sum in position order is a serial chain per column (>= rows x 4 cycles), so the longest group is
+    // the critical path of the launch.  A huge group is therefore cut into 16-column slices, one work item each: every
+    // slice streams 256 rows per staged tile instead of 64 and the slices of one group run on different SMs.
     __shared__ __align__(16) float s_rows[kLongTileFloats];
     __shared__ unsigned s_pos[kLongTileRows];
-    const unsigned n_long = *n_long_p;
-    for (unsigned q = blockIdx.x; q < n_long; q += (unsigned)n_long_ctas) {
-      const unsigned g = long_list[q];
+    __shared__ unsigned s_q;
+    const unsigned n_long = ctr[0], n_huge = ctr[1];
+    const unsigned slices = dim / (unsigned)kSliceCols;          // only used when huge groups exist (sliceable rows)
+    const unsigned n_huge_items = n_huge * slices;
+    while (true) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_q = atomicAdd(&ctr[2], 1u);
+      __syncthreads();
+      const unsigned q = s_q;
+      if (q >= n_huge_items + n_long) break;
+      unsigned g, c_lo, c_hi;
+      if (q < n_huge_items) {
+        g = huge_list[q / slices];
+        c_lo = (q % slices) * (unsigned)kSliceCols;
+        c_hi = c_lo + (unsigned)kSliceCols;
+      } else {
+        g = long_list[q - n_huge_items];
+        c_lo = 0;
+        c_hi = dim;
+      }
       const unsigned st = starts[g], en = starts[g + 1];
-      for (unsigned c0 = 0; c0 < dim; c0 += kLongCols) {
-        const unsigned wcols = dim - c0 < (unsigned)kLongCols ? dim - c0 : (unsigned)kLongCols;  // multiple of VF
+      for (unsigned c0 = c_lo; c0 < c_hi; c0 += kLongCols) {
+        const unsigned wcols = c_hi - c0 < (unsigned)kLongCols ? c_hi - c0 : (unsigned)kLongCols;  // multiple of VF
         unsigned rpt = (unsigned)kLongTileFloats / wcols;
         if (rpt > (unsigned)kLongTileRows) rpt = kLongTileRows;
         const unsigned wv = wcols / VF;                                   // vectors per staged row
@@ -1279,7 +1313,7 @@ segment_reduce_kernel(const float* __restrict__ rows, const unsigned* __restrict
 }
 
 struct SegReduceWs {
-  unsigned *keys_a, *keys_b, *pos_a, *pos_b, *hist, *totals, *starts, *long_list, *n_long;
+  unsigned *keys_a, *keys_b, *pos_a, *pos_b, *hist, *totals, *starts, *long_list, *huge_list, *n_long;
 };
 
 static size_t seg_reduce_layout(size_t n, size_t n_groups, unsigned char* base, SegReduceWs* w) {
@@ -1298,10 +1332,11 @@ static size_t seg_reduce_layout(size_t n, size_t n_groups, unsigned char* base, 
   unsigned* totals = take(kRadixBins * 4);
   unsigned* starts = take((n_groups + 2) * 4);
   unsigned* ll = take((n / kLongGroup + 2) * 4);
+  unsigned* hl = take((n / kHugeGroup + 2) * 4);
   unsigned* nl = take(16);
   if (w) {
     w->keys_a = ka; w->keys_b = kb; w->pos_a = pa; w->pos_b = pb; w->hist = hist; w->totals = totals;
-    w->starts = starts; w->long_list = ll; w->n_long = nl;
+    w->starts = starts; w->long_list = ll; w->huge_list = hl; w->n_long = nl;
   }
   return off;
 }
@@ -1430,8 +1465,11 @@ det_status det_lookup_sparse_clip(det_table* t, const int64_t* ids, const int32_
   return lookup_sparse_impl(t, ids, segment_ids, weights, nnz, batch, combiner, default_row, max_norm, out, stream);
 }
 
+// n_dev (nullable): the key count lives on the device (det_apply_*_dup); n is then its upper bound -- room is reserved
+// for n NEW keys (the unique keys themselves are not read by the host path) and only the staged kernels support it
 static det_status apply_common(det_table* t, const int64_t* keys, const float* grads, size_t n, OptHyper h,
-                               const float* init_param, int full_init, int opt, cudaStream_t s) {
+                               const float* init_param, int full_init, int opt, cudaStream_t s,
+                               const long long* n_dev = nullptr) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_apply: null table");
   std::lock_guard<std::mutex> _lk(t->mu);
   if (t->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_apply: float32 tables only");
@@ -1440,17 +1478,19 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
   if (n == 0) return DET_OK;
   if (!keys || !grads || !init_param) return fail(DET_INVALID_ARGUMENT, "det_apply: null argument");
   det::DevGuard _dg(t->cfg.device);
-  det_status st = ensure_room(t, (const long long*)keys, n, s);
-  if (st != DET_OK) return st;
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)grads | (uintptr_t)init_param) & 15u) == 0);
   unsigned vpr, lpr, sh;
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
+  if (n_dev && !(vec4 && vpr <= lpr))
+    return fail(DET_UNIMPLEMENTED, "det_apply_*_dup: rows of up to 32 aligned 16-byte vectors only (use unique + segment_reduce + apply)");
+  det_status st = ensure_room(t, n_dev ? nullptr : (const long long*)keys, n, s);
+  if (st != DET_OK) return st;
   static const int ru = env_int("DET_APPLY_RU", 1);  // measured on B200: one row-step per iteration wins (more resident CTAs)
   static const int staged = env_int("DET_APPLY_STAGED", 1);  // measured: +12..18 % over the register-held variant
   const TableView v = t->view;
   const long long* k = (const long long*)keys;
-  if (staged && vec4 && vpr <= lpr) {
+  if ((staged || n_dev) && vec4 && vpr <= lpr) {
     // cp.async-staged variant: 2 stages x kStageSteps x streams x 512 B per warp of dynamic shared memory
     const int ns = opt == 0 ? 3 : 4;
     const size_t smem = (size_t)(kThreadsF / 32) * 2 * kStageSteps * ns * 32 * 16;
@@ -1463,7 +1503,7 @@ static det_status apply_common(det_table* t, const int64_t* keys, const float* g
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreadsF, smem) != cudaSuccess || occ < 1) occ = 1; \
     DET_LAUNCH(kern, grid_for(n, kTileKeys, t->sm_count, occ), kThreadsF, smem, s, v, k, grads, n, h, init_param, \
-               full_init, vpr, lpr, sh, tma, SA_);                                                                \
+               full_init, vpr, lpr, sh, tma, SA_, n_dev);                                                         \
   }
     if (scored) {
       ScoreArg<true> sa;
@@ -1655,15 +1695,15 @@ size_t det_segment_reduce_workspace_bytes(size_t n, size_t n_groups) {
   return seg_reduce_layout(n ? n : 1, n_groups ? n_groups : 1, nullptr, nullptr);
 }
 
-det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim, float* out,
-                              void* workspace, size_t workspace_bytes, det_stream_t stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+// n_groups bounds the group count (sizes, pass count, grids); with `ngd` the real count is read on the device
+static det_status seg_reduce_run(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim, float* out,
+                                 void* workspace, size_t workspace_bytes, const long long* ngd, cudaStream_t s) {
   if (n_groups == 0 || dim == 0) return DET_OK;
   if (!out) return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: null out");
   if (n >= 0x7fffffffull || n_groups >= 0x7fffffffull || dim >= 0x7fffffffull)
     return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: n / n_groups / dim too large");
   if (n == 0) {
-    CUDA_TRY(cudaMemsetAsync(out, 0, n_groups * dim * sizeof(float), s));
+    if (!ngd) CUDA_TRY(cudaMemsetAsync(out, 0, n_groups * dim * sizeof(float), s));
     return DET_OK;
   }
   if (!rows || !idx || !workspace) return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: null argument");
@@ -1689,31 +1729,122 @@ det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, s
     kout = (kout == w.keys_a) ? w.keys_b : w.keys_a;
     pout = (pout == w.pos_a) ? w.pos_b : w.pos_a;
   }
-  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts);
-  CUDA_TRY(cudaMemsetAsync(w.n_long, 0, sizeof(unsigned), s));
-  DET_LAUNCH(group_long_kernel, (int)((n_groups + 255) / 256), 256, 0, s, w.starts, ng, w.long_list, w.n_long);
+  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts, ngd);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)rows | (uintptr_t)out) & 15u) == 0);
+  // rows that can be cut into 16-column slices (the double-buffered cp.async staging moves 16 B vectors)
+  const int sliceable = (vec4 && dim % kSliceCols == 0 && dim > (size_t)kSliceCols) ? 1 : 0;
+  CUDA_TRY(cudaMemsetAsync(w.n_long, 0, 4 * sizeof(unsigned), s));   // long count, huge count, queue cursor
+  DET_LAUNCH(group_long_kernel, (int)((n_groups + 255) / 256), 256, 0, s, w.starts, ng, sliceable, w.long_list, w.huge_list,
+             w.n_long, ngd);
   unsigned vpr, lpr, sh;
   fgeom((unsigned)dim, vec4, 1, &vpr, &lpr, &sh);
   const unsigned gpw = 32u >> sh;
   // CTAs of the launch reserved for the long groups (default one per SM); a tuning knob until the kernel has been timed
-  int n_long_ctas = env_int("DET_SEGRED_LONG_CTAS", sms);
+  int n_long_ctas = env_int("DET_SEGRED_LONG_CTAS", 2 * sms);
   if (n_long_ctas < 1) n_long_ctas = 1;
   if (n_long_ctas > 4 * sms) n_long_ctas = 4 * sms;
   const auto k4 = segment_reduce_kernel<4>;
   const auto k1 = segment_reduce_kernel<1>;
   const int occ = vec4 ? occupancy_of(k4, kThreadsF) : occupancy_of(k1, kThreadsF);
-  const int grid = n_long_ctas + grid_for(n_groups, (int)(gpw * 2 * (kThreadsF / 32)), sms, occ > 1 ? occ - 1 : 1);
+  // one resident wave: the long-path CTAs (blockIdx < n_long_ctas) plus the short-group CTAs that still fit beside them
+  const int long_per_sm = (n_long_ctas + sms - 1) / sms;
+  const int grid = n_long_ctas + grid_for(n_groups, (int)(gpw * 2 * (kThreadsF / 32)), sms, occ > long_per_sm ? occ - long_per_sm : 1);
   if (vec4)
-    DET_LAUNCH(k4, grid, kThreadsF, 0, s, rows, pin, w.starts, ng, (unsigned)dim, vpr, lpr, sh, w.long_list, w.n_long, n_long_ctas, out);
+    DET_LAUNCH(k4, grid, kThreadsF, 0, s, rows, pin, w.starts, ng, (unsigned)dim, vpr, lpr, sh, w.long_list, w.huge_list, w.n_long, n_long_ctas, out, ngd);
   else
-    DET_LAUNCH(k1, grid, kThreadsF, 0, s, rows, pin, w.starts, ng, (unsigned)dim, vpr, lpr, sh, w.long_list, w.n_long, n_long_ctas, out);
+    DET_LAUNCH(k1, grid, kThreadsF, 0, s, rows, pin, w.starts, ng, (unsigned)dim, vpr, lpr, sh, w.long_list, w.huge_list, w.n_long, n_long_ctas, out, ngd);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
 }
 
+
+det_status det_segment_reduce(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim, float* out,
+                              void* workspace, size_t workspace_bytes, det_stream_t stream) {
+  return seg_reduce_run(rows, idx, n, n_groups, dim, out, workspace, workspace_bytes, nullptr, (cudaStream_t)stream);
+}
+
+// ---- sparse apply_gradients with REPEATED ids, one call, no host synchronisation -----------------------------------
+// The reference's optimizer patch handles IndexedSlices gradients with `_resource_apply_sparse_duplicate_indices`:
+// unique(ids) -> unsorted_segment_sum(grads, idx, n_unique) -> find / dense rule / upsert per unique id
+// (python/ops/dynamic_embedding_optimizer.py:150,184 + :161-204).  Here: det_unique -> det_segment_reduce (position
+// order) -> the fused find-or-insert optimizer kernel, chained on the caller's stream with the unique count staying on
+// the DEVICE (kernels read it from memory; grids and buffers are sized for the bound n), so a training step has no
+// cudaStreamSynchronize and no `.item()`.  New keys start from the broadcast `init_param` row (a per-key initializer
+// needs the unique ids on the host side first: use det_unique + det_segment_reduce + det_apply_*).
+struct DupWs {
+  long long* uniq;
+  int* idx;
+  long long* cnt;
+  unsigned char* uws;
+  size_t uws_bytes;
+  float* gsum;
+  unsigned char* sws;
+  size_t sws_bytes;
+};
+static size_t dup_layout(size_t n, size_t dim, unsigned char* base, DupWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  const size_t ub = unique_ws_layout(n, nullptr, nullptr), sb = seg_reduce_layout(n, n, nullptr, nullptr);
+  unsigned char* uniq = take(n * 8);
+  unsigned char* idx = take(n * 4);
+  unsigned char* cnt = take(16);
+  unsigned char* uws = take(ub);
+  unsigned char* gsum = take(n * dim * 4);
+  unsigned char* sws = take(sb);
+  if (w) {
+    w->uniq = (long long*)uniq; w->idx = (int*)idx; w->cnt = (long long*)cnt; w->uws = uws; w->uws_bytes = ub;
+    w->gsum = (float*)gsum; w->sws = sws; w->sws_bytes = sb;
+  }
+  return off;
+}
+
+size_t det_apply_dup_workspace_bytes(size_t n, size_t dim) { return dup_layout(n ? n : 1, dim ? dim : 1, nullptr, nullptr); }
+
+static det_status apply_dup(det_table* t, const int64_t* ids, const float* grads, size_t n, OptHyper h,
+                            const float* init_param, int opt, void* workspace, size_t workspace_bytes,
+                            int64_t* n_unique_dev_out, cudaStream_t s) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: null table");
+  if (n == 0) return DET_OK;
+  if (!ids || !grads || !init_param || !workspace) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: null argument");
+  if (n >= 0x7fffffffull) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: n too large");
+  const size_t dim = (size_t)t->cfg.dim;
+  if (workspace_bytes < det_apply_dup_workspace_bytes(n, dim)) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: workspace too small");
+  if (((uintptr_t)workspace & 255u) != 0) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: workspace must be 256 B aligned");
+  det::DevGuard _dg(t->cfg.device);
+  DupWs w;
+  dup_layout(n, dim, (unsigned char*)workspace, &w);
+  det_status st = det_unique(ids, n, (int64_t*)w.uniq, w.idx, (int64_t*)w.cnt, w.uws, w.uws_bytes, (det_stream_t)s);
+  if (st != DET_OK) return st;
+  st = seg_reduce_run(grads, w.idx, n, n, dim, w.gsum, w.sws, w.sws_bytes, w.cnt, s);
+  if (st != DET_OK) return st;
+  st = apply_common(t, (const int64_t*)w.uniq, w.gsum, n, h, init_param, 0, opt, s, w.cnt);
+  if (st != DET_OK) return st;
+  if (n_unique_dev_out) CUDA_TRY(cudaMemcpyAsync(n_unique_dev_out, w.cnt, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  return DET_OK;
+}
+
+det_status det_apply_adagrad_dup(det_table* t, const int64_t* ids, const float* grads, size_t n, float lr, float epsilon,
+                                 const float* init_param, float init_accum, void* workspace, size_t workspace_bytes,
+                                 int64_t* n_unique_dev_out, det_stream_t stream) {
+  OptHyper h;
+  h.lr = lr; h.eps = epsilon; h.beta1 = 0.f; h.beta2 = 0.f; h.init_slot = init_accum;
+  if (t) t->slot_init[1] = init_accum;
+  return apply_dup(t, ids, grads, n, h, init_param, 0, workspace, workspace_bytes, n_unique_dev_out, (cudaStream_t)stream);
+}
+
+det_status det_apply_adam_dup(det_table* t, const int64_t* ids, const float* grads, size_t n, float alpha, float beta1,
+                              float beta2, float epsilon, const float* init_param, void* workspace, size_t workspace_bytes,
+                              int64_t* n_unique_dev_out, det_stream_t stream) {
+  OptHyper h;
+  h.lr = alpha; h.eps = epsilon; h.beta1 = beta1; h.beta2 = beta2; h.init_slot = 0.f;
+  return apply_dup(t, ids, grads, n, h, init_param, 1, workspace, workspace_bytes, n_unique_dev_out, (cudaStream_t)stream);
+}
 
 }  // extern "C"

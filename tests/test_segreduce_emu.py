@@ -47,6 +47,24 @@ def test_random_groups_bit_exact(n, n_groups, dim):
   np.testing.assert_array_equal(reduce_emu(rows, idx, n_groups), O.segment_reduce(rows, idx, n_groups))
 
 
+@pytest.mark.parametrize("dim,n_huge", [(64, 2), (32, 1), (128, 1), (48, 1), (16, 1), (36, 1)])
+def test_huge_groups_are_cut_into_column_slices(dim, n_huge):
+  """groups of more than 1024 rows (the Zipf head of a 26 x 65536 batch owns thousands of rows of one key): with rows of
+  a multiple of 16 columns every such group becomes dim/16 work items of 16 columns each, pulled from the work queue
+  before the ordinary long groups; dims that cannot be sliced (16 itself, 36) keep the whole-row path.  Sums stay in
+  position order: bit-identical to the sequential oracle, every output row written."""
+  rng = np.random.default_rng(dim * 7 + n_huge)
+  n_groups = 60
+  parts = [np.full(1100 + 700 * h, 3 + 17 * h) for h in range(n_huge)]        # the huge groups
+  parts += [np.full(200, 11), np.full(90, 40)]                                # ordinary long groups
+  parts += [rng.integers(0, n_groups, size=900)]                              # short groups and a few empty ones
+  idx = np.concatenate(parts).astype(np.int32)
+  rng.shuffle(idx)
+  rows = rows_of(rng, idx.shape[0], dim)
+  got = reduce_emu(rows, idx, n_groups)
+  np.testing.assert_array_equal(got, O.segment_reduce(rows, idx, n_groups))
+
+
 @pytest.mark.parametrize("dim", [64, 7, 36])
 def test_zipf_head_takes_the_long_group_path(dim):
   rng = np.random.default_rng(dim)
