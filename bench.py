@@ -898,16 +898,20 @@ def c3_measure(args, steps, warmup):
   gout = torch.randn(nnz, dim, device=dev, generator=gen) * 0.01  # upstream gradient of every (sample, feature) row
   opt = de.FusedAdagrad(0.01, 0.1)
 
+  def backward(ids):
+    opt.iterations += 1
+    if args.grad_reduce == "det":
+      # ONE C call: unique -> position-order gradient sum -> fused find-or-insert Adagrad, count stays on the device
+      opt.apply_sparse_duplicate_indices(var, ids, gout)
+    else:   # A/B: eager composition with torch index_add (atomics) and a host-side unique count
+      uniq, idx = de.unique(ids)
+      g = torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
+      opt.apply_sparse(var, uniq, g)
+
   def step(i):
     ids = batches[i % nb]
     out = lookup_sparse_fused(var, ids, seg, None, nnz, "sum")
-    uniq, idx = de.unique(ids)
-    if args.grad_reduce == "det":
-      g = de.segment_reduce(gout, idx, uniq.numel())
-    else:
-      g = torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
-    opt.iterations += 1
-    opt.apply_sparse(var, uniq, g)
+    backward(ids)
     return out
 
   # parity of the fused forward before any optimizer step: one id per output row and combiner sum, so row i of the
@@ -927,25 +931,35 @@ def c3_measure(args, steps, warmup):
   torch.cuda.synchronize()
   ms = t0.elapsed_time(t1) / steps
   # where the step goes: the same step with CUDA events between its phases (outside the timed region)
-  phases = {"lookup_sparse": [], "unique": [], "grad_reduce": [], "apply_adagrad": []}
+  phases = {"lookup_sparse": [], "backward_unique_gradsum_apply": []}
   for i in range(5):
     ids = batches[i % nb]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     lookup_sparse_fused(var, ids, seg, None, nnz, "sum")
     ev[1].record()
-    uniq, idx = de.unique(ids)
+    backward(ids)
     ev[2].record()
-    g = de.segment_reduce(gout, idx, uniq.numel()) if args.grad_reduce == "det" else \
-        torch.zeros((uniq.numel(), dim), device=dev).index_add_(0, idx.long(), gout)
-    ev[3].record()
-    opt.iterations += 1
-    opt.apply_sparse(var, uniq, g)
-    ev[4].record()
     torch.cuda.synchronize()
     for k, name in enumerate(phases):
       phases[name].append(ev[k].elapsed_time(ev[k + 1]))
   phases_ms = {k: float(np.median(v)) for k, v in phases.items()}
+  # host synchronisations inside a step: torch raises on any synchronising call in this mode (.item(), blocking copies)
+  host_syncs = None
+  try:
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+      for i in range(3):
+        step(i)
+      host_syncs = 0
+    except RuntimeError as ex:
+      host_syncs = "at least one (%s)" % str(ex).splitlines()[0][:120]
+    finally:
+      torch.cuda.set_sync_debug_mode("default")
+  except Exception:
+    pass
+  torch.cuda.synchronize()
+  uniq = de.unique(batches[0])[0]
   # algorithmic traffic of the step: forward rows + ids/segs + out, gradient rows read once + sums written,
   # 5 x dim x 4 B per unique key for the fused Adagrad
   n_u = int(uniq.numel())
@@ -953,7 +967,7 @@ def c3_measure(args, steps, warmup):
   peak, peak_src = measured_peak_gbs()
   table.close()
   return ({"metric": "fused embedding_lookup_sparse + Adagrad step, M ids/s (BASELINE configs[2])",
-                    "phases_ms": phases_ms, "parity": parity,
+                    "phases_ms": phases_ms, "parity": parity, "host_syncs_per_step": host_syncs,
                     "roofline": {"bound": "hbm", "kernel": "whole step (lookup_sparse + unique + grad_reduce + apply_adagrad)",
                                  "achieved": step_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": step_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
@@ -961,7 +975,7 @@ def c3_measure(args, steps, warmup):
                     "value": nnz / ms / 1e3, "unit": "M ids/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
                     "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
                     "config": {"workload": "26 features x batch 65536, dim %d, %d resident rows, Zipf(1.05) per feature; "
-                                           "includes tf.unique + the per-unique gradient sum (%s)" % (dim, total, "det_segment_reduce, position order" if args.grad_reduce == "det" else "torch index_add"),
+                                           "includes tf.unique + the per-unique gradient sum (%s)" % (dim, total, "one det_apply_adagrad_dup call: det_unique + det_segment_reduce in position order + fused Adagrad, device-side count" if args.grad_reduce == "det" else "torch index_add, host-side unique count"),
                                "nnz": nnz, "unique_per_step": n_u}})
 
 

@@ -277,6 +277,23 @@ det_status det_find_host_async(det_table* t, const int64_t* keys_host, size_t n,
 det_status det_insert_host_async(det_table* t, const int64_t* keys_host, const void* values_host, size_t n);
 det_status det_host_sync(det_table* t);
 
+/* Sparse apply_gradients with REPEATED ids in ONE call and without host synchronisation (ABI >= 6): what the reference's
+ * optimizer patch does for IndexedSlices gradients -- unique(ids) -> unsorted_segment_sum(grads, idx, n_unique) ->
+ * find / dense rule / upsert per unique id (python/ops/dynamic_embedding_optimizer.py:150,184 and :161-204) -- as
+ * det_unique -> det_segment_reduce (rows of one id added in position order, bit-identical to the sequential sum) ->
+ * the fused find-or-insert optimizer kernel, chained on `stream` with the unique count staying ON THE DEVICE.
+ * ids int64[n] (repeats allowed), grads f32[n, dim]; new keys start from the broadcast row init_param[dim].
+ * workspace: det_apply_dup_workspace_bytes(n, dim) bytes of device memory, 256 B aligned, stream-ordered scratch.
+ * n_unique_dev_out (nullable): device int64 that receives the number of distinct ids.
+ * DET_UNIMPLEMENTED for rows that are not 16-byte vectors (use det_unique + det_segment_reduce + det_apply_*). */
+size_t det_apply_dup_workspace_bytes(size_t n, size_t dim);
+det_status det_apply_adagrad_dup(det_table* t, const int64_t* ids, const float* grads, size_t n, float lr, float epsilon,
+                                 const float* init_param, float init_accum, void* workspace, size_t workspace_bytes,
+                                 int64_t* n_unique_dev_out, det_stream_t stream);
+det_status det_apply_adam_dup(det_table* t, const int64_t* ids, const float* grads, size_t n, float alpha, float beta1,
+                              float beta2, float epsilon, const float* init_param, void* workspace,
+                              size_t workspace_bytes, int64_t* n_unique_dev_out, det_stream_t stream);
+
 /* ---- key-hash sharding across GPUs (python/ops/dynamic_embedding_variable.py:165-197 default_partition_fn,
  * python/ops/shadow_embedding_ops.py:397-447 alltoall exchange) ----
  * Partition n keys into num_shards contiguous groups by owner = (key & 0x7fffffff) % S (gpu_mode)

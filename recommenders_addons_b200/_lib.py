@@ -10,7 +10,7 @@ _sz = ctypes.c_size_t
 _i = ctypes.c_int
 
 DET_OK = 0
-ABI_VERSION = 5  # det_abi_version() of the library these mirrors describe (checked at load)
+ABI_VERSION = 6  # det_abi_version() of the library these mirrors describe (checked at load)
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 # HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
@@ -64,6 +64,10 @@ SIGNATURES = {
     "det_apply_adagrad": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, _vp, _i, ctypes.c_float, _vp]),
     "det_apply_adam": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                             _vp, _i, _vp]),
+    "det_apply_dup_workspace_bytes": (_sz, [_sz, _sz]),
+    "det_apply_adagrad_dup": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, _vp, ctypes.c_float, _vp, _sz, _vp, _vp]),
+    "det_apply_adam_dup": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp,
+                                _sz, _vp, _vp]),
     "det_find_host": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "det_insert_host": (_i, [_vp, _vp, _vp, _sz]),
     "det_find_host_async": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),

@@ -11,6 +11,7 @@
 //
 // Phases (all ranks reading / all ranks writing) are separated by det_peer_barrier, a flag barrier over the same
 // peer memory, which gives the ordering the reference gets from its collectives.
+#include <stdio.h>
 #include <string.h>
 
 #include "host.h"
@@ -522,7 +523,17 @@ struct det_peer_group {
   DevState* h_snap = nullptr;                // pinned: async snapshot of the local shard's DevState
   cudaEvent_t snap_ev = nullptr;
   bool snap_inflight = false;
+  // DET_XCHG_TIMING=1: CUDA events between the kernels of a call, accumulated and printed when the group is destroyed
+  bool timing = false;
+  cudaEvent_t tev[2][6] = {};                // [find | insert][boundary]
+  bool tev_pending[2] = {false, false};
+  double tacc[2][5] = {};
+  unsigned long long tcalls[2] = {0, 0};
 };
+extern "C" {
+static void xchg_time_collect(det_peer_group* g, int which, int n_iv);
+}
+
 
 extern "C" {
 
@@ -563,6 +574,19 @@ det_status det_peer_group_destroy(det_peer_group* g) {
       if (g->opened[p][q]) cudaIpcCloseMemHandle(g->opened[p][q]);
   if (g->cursor) cudaFree(g->cursor);
   if (g->h_counts) cudaFreeHost(g->h_counts);
+  if (g->timing) {
+    xchg_time_collect(g, 0, 4);
+    xchg_time_collect(g, 1, 5);
+    const double cf = g->tcalls[0] ? (double)g->tcalls[0] : 1.0, ci = g->tcalls[1] ? (double)g->tcalls[1] : 1.0;
+    fprintf(stderr, "[det xchg timing rank %d] find x%llu: route %.1f us, wait_req %.1f, serve %.1f, wait_done %.1f | "
+                    "insert x%llu: wait_ack %.1f us, route %.1f, wait_ins %.1f, apply %.1f, snapshot %.1f\n", g->pv.rank,
+            g->tcalls[0], g->tacc[0][0] / cf * 1e3, g->tacc[0][1] / cf * 1e3, g->tacc[0][2] / cf * 1e3, g->tacc[0][3] / cf * 1e3,
+            g->tcalls[1], g->tacc[1][0] / ci * 1e3, g->tacc[1][1] / ci * 1e3, g->tacc[1][2] / ci * 1e3, g->tacc[1][3] / ci * 1e3,
+            g->tacc[1][4] / ci * 1e3);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 6; ++b)
+        if (g->tev[a][b]) cudaEventDestroy(g->tev[a][b]);
+  }
   if (g->xcursor) cudaFree(g->xcursor);
   if (g->h_snap) cudaFreeHost(g->h_snap);
   if (g->snap_ev) cudaEventDestroy(g->snap_ev);
@@ -844,6 +868,7 @@ det_status det_peer_xchg_attach(det_peer_group* g, const void* const* mailbox_pt
   }
   g->ep_find = g->ep_ins = 0;
   g->xchg = true;
+  g->timing = env_int("DET_XCHG_TIMING", 0) != 0;
   return DET_OK;
 }
 
@@ -893,6 +918,22 @@ static void peer_snapshot(det_peer_group* g, cudaStream_t s) {
     cudaGetLastError();
 }
 
+static void xchg_time_collect(det_peer_group* g, int which, int n_iv) {
+  if (!g->timing || !g->tev_pending[which]) return;
+  if (cudaEventSynchronize(g->tev[which][n_iv]) != cudaSuccess) { cudaGetLastError(); return; }
+  for (int i = 0; i < n_iv; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g->tev[which][i], g->tev[which][i + 1]) == cudaSuccess) g->tacc[which][i] += ms;
+  }
+  g->tcalls[which]++;
+  g->tev_pending[which] = false;
+}
+static void xchg_mark(det_peer_group* g, int which, int i, cudaStream_t s) {
+  if (!g->timing) return;
+  if (!g->tev[which][i]) cudaEventCreate(&g->tev[which][i]);
+  cudaEventRecord(g->tev[which][i], s);
+}
+
 // Sharded Find through the owners.  COLLECTIVE: every rank of the group calls it (n may differ, 0 allowed), in the same
 // order as its peers.  Rows land in this rank's output ring (2 entries): *rows_view (if non-null) receives the device
 // pointer of the n rows, valid until the next-but-one det_peer_xchg_find; values_out (if non-null) additionally gets a
@@ -907,6 +948,7 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
   det::DevGuard _dg(g->device);
   det_status rs = peer_room(g, "det_peer_xchg_find");
   if (rs != DET_OK && rs != DET_TABLE_FULL) return rs;
+  xchg_time_collect(g, 0, 4);
   const unsigned long long ep = ++g->ep_find;
   const int parity = (int)(ep & 1ull);
   const XchgView& xv = g->xv;
@@ -919,11 +961,14 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
   unsigned* ticket = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
   DevState* st = g->local->view.st;
   const long long* k = (const long long*)keys;
+  xchg_mark(g, 0, 0, s);
   {
     const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
     DET_LAUNCH((xchg_route_kernel<false, 16>), grid, kThreadsP, 0, s, xv, k, (const unsigned char*)nullptr, n, geo, g->xcursor, ticket, ep, st);
   }
+  xchg_mark(g, 0, 1, s);
   xchg_wait(g, kFlagReq, ep, s);
+  xchg_mark(g, 0, 2, s);
   {
     const unsigned char* d = (const unsigned char*)defaults;
     const TableView tv = g->local->view;
@@ -941,7 +986,10 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
 #undef DET_XSERVE
     }
   }
+  xchg_mark(g, 0, 3, s);
   xchg_wait(g, kFlagDone, ep, s);
+  xchg_mark(g, 0, 4, s);
+  g->tev_pending[0] = g->timing;
   if (full_size_default && n) {
     const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
     const unsigned char* d = (const unsigned char*)defaults;
@@ -973,6 +1021,7 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
   det_status rs = peer_room(g, "det_peer_xchg_insert");
   if (rs != DET_OK) return rs;
   std::lock_guard<std::mutex> _lk(g->local->mu);
+  xchg_time_collect(g, 1, 5);
   const unsigned long long ep = ++g->ep_ins;
   const XchgView& xv = g->xv;
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
@@ -981,7 +1030,9 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
   DevState* st = g->local->view.st;
   const long long* k = (const long long*)keys;
   const unsigned char* r = (const unsigned char*)values;
+  xchg_mark(g, 1, 0, s);
   if (ep > 1) xchg_wait(g, kFlagAck, ep - 1, s);   // every owner has consumed what this rank sent last time
+  xchg_mark(g, 1, 1, s);
   {
     const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
     switch (vec) {
@@ -992,7 +1043,9 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
       default: DET_LAUNCH((xchg_route_kernel<true, 1>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
     }
   }
+  xchg_mark(g, 1, 2, s);
   xchg_wait(g, kFlagIns, ep, s);
+  xchg_mark(g, 1, 3, s);
   {
     const int avec = pick_vec(g->row_bytes, nullptr, nullptr, nullptr);
     const RowGeom ageo = make_geom((unsigned)g->row_bytes, avec);
@@ -1013,7 +1066,10 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
     }
   }
   CUDA_TRY(cudaGetLastError());
+  xchg_mark(g, 1, 4, s);
   peer_snapshot(g, s);
+  xchg_mark(g, 1, 5, s);
+  g->tev_pending[1] = g->timing;
   return DET_OK;
 }
 

@@ -135,10 +135,10 @@ def embedding_lookup_sparse(params, sp_ids, sp_weights, partition_strategy=None,
   r = embedding_lookup(params, uniq, max_norm=max_norm, return_trainable=return_trainable)
   emb_u, tw = r if return_trainable else (r, None)
   import os
-  if os.environ.get("DET_SPARSE_TRAIN_FUSED", "0") == "1" and emb_u.device.type in _table_device_types() and ids.numel() > 0:
-    # the dense rows of the trainable scratch go through the fused gather / weight / segment-sum kernel
-    # (det_sparse_segment_sum; written after round 1's GPU budget was spent, emulator-tested: opt-in until it has run
-    # on a B200, the torch restatement below stays the default)
+  if os.environ.get("DET_SPARSE_TRAIN_FUSED", "1") == "1" and emb_u.device.type in _table_device_types() and ids.numel() > 0:
+    # DEFAULT: the dense rows of the trainable scratch go through the fused gather / weight / segment-sum kernel
+    # (det_sparse_segment_sum; validated on B200 in round 2, bit-identical to the oracle; its backward is the
+    # position-order gradient dedupe).  DET_SPARSE_TRAIN_FUSED=0 selects the eager torch restatement below.
     out = sparse_segment_sum_rows(emb_u.to(torch.float32), idx, segment_ids, weights, batch, combiner)
     return (out, tw) if return_trainable else out
   emb = gather_unique(emb_u.to(torch.float32), idx)

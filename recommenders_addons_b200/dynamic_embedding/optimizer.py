@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib
 from .table import _ptr, _stream_ptr
-from .variable import TrainableWrapper, Variable
+from .variable import TrainableWrapper, Variable, _segment_reduce_devices
 
 
 def _init_rows(params, n, device):
@@ -162,10 +162,33 @@ class _FusedBase(object):
   def apply_sparse_duplicate_indices(self, params, ids, grads):
     """one step from row gradients whose ids may repeat: gradients of the same id are summed first
     (`_resource_apply_sparse_duplicate_indices` -> `_deduplicate_indexed_slices`, the path the reference takes for
-    IndexedSlices gradients, dynamic_embedding_optimizer.py:150,184), then the fused step runs on the unique ids"""
+    IndexedSlices gradients, dynamic_embedding_optimizer.py:150,184), then the fused step runs on the unique ids.
+    Single-shard fp32 variables with a static initializer take ONE C call (det_apply_*_dup): unique -> position-order
+    gradient sum -> fused find-or-insert step, the unique count never leaves the device (no host synchronisation)."""
+    ids = ids.reshape(-1)
+    grads = grads.reshape(-1, params.dim).to(torch.float32).contiguous()
+    t = params.tables[0]
+    import os
+    if (len(params.tables) == 1 and not callable(params.initializer) and params.dim % 4 == 0 and params.dim <= 128
+        and ids.numel() > 0 and t.device.type in _segment_reduce_devices()
+        and os.environ.get("DET_GRAD_REDUCE", "det") == "det"):
+      ids = ids.to(t.device).contiguous()
+      grads = grads.to(t.device)
+      n = ids.numel()
+      lib = _lib.lib()
+      need = int(lib.det_apply_dup_workspace_bytes(n, params.dim))
+      ws = getattr(self, "_dup_ws", None)
+      if ws is None or ws.numel() < need or ws.device != t.device:
+        # reused across steps (stream-ordered scratch): no allocation on the hot path after the first step
+        raw = torch.empty(need + need // 8 + 256, dtype=torch.uint8, device=t.device)
+        off = (-raw.data_ptr()) % 256          # the C ABI wants a 256 B aligned workspace (CUDA allocations already are)
+        ws = self._dup_ws = raw[off:off + need + need // 8]
+      init = t._default_value.to(t.device).contiguous()
+      self._apply_table_dup(t, ids, grads, n, init, ws)
+      return
     from .variable import combine_rows, unique
-    uniq, idx = unique(ids.reshape(-1))
-    self.apply_sparse(params, uniq, combine_rows(grads.reshape(-1, params.dim).to(torch.float32), idx, uniq.numel()))
+    uniq, idx = unique(ids)
+    self.apply_sparse(params, uniq, combine_rows(grads, idx, uniq.numel()))
 
 
 class FusedAdagrad(_FusedBase):
@@ -187,6 +210,12 @@ class FusedAdagrad(_FusedBase):
     _lib.check(_lib.lib().det_apply_adagrad(table.handle, _ptr(keys), _ptr(grads), n, self.learning_rate,
                                             self.epsilon, _ptr(init), full, self.initial_accumulator_value,
                                             _stream_ptr(table.device)))
+
+
+  def _apply_table_dup(self, table, ids, grads, n, init, ws):
+    _lib.check(_lib.lib().det_apply_adagrad_dup(table.handle, _ptr(ids), _ptr(grads), n, self.learning_rate, self.epsilon,
+                                                _ptr(init), self.initial_accumulator_value, _ptr(ws), ws.numel(), None,
+                                                _stream_ptr(table.device)))
 
 
 class FusedAdam(_FusedBase):
@@ -214,6 +243,12 @@ class FusedAdam(_FusedBase):
     init, full = _init_rows(params, n, table.device)
     _lib.check(_lib.lib().det_apply_adam(table.handle, _ptr(keys), _ptr(grads), n, self.alpha(), self.beta_1,
                                          self.beta_2, self.epsilon, _ptr(init), full, _stream_ptr(table.device)))
+
+
+  def _apply_table_dup(self, table, ids, grads, n, init, ws):
+    _lib.check(_lib.lib().det_apply_adam_dup(table.handle, _ptr(ids), _ptr(grads), n, self.alpha(), self.beta_1, self.beta_2,
+                                             self.epsilon, _ptr(init), _ptr(ws), ws.numel(), None,
+                                             _stream_ptr(table.device)))
 
 
 class ComposedOptimizer(object):

@@ -38,8 +38,10 @@ def load_de_variable_from_file_system(var, dirpath, proc_size=1, proc_rank=0, bu
                                                           buffer_size=buffer_size)
 
 
-def unique(ids):
-  """tf.unique on the GPU: (unique values in first-occurrence order, int32 index of each id)."""
+def unique(ids, return_count_tensor=False):
+  """tf.unique on the GPU: (unique values in first-occurrence order, int32 index of each id).
+  return_count_tensor=True: no host synchronisation -- returns (unique values PADDED to len(ids), idx, device int64
+  count); only the first `count` entries are meaningful (callers that stay on the device, e.g. det_apply_*_dup)."""
   flat = ids.reshape(-1).contiguous()
   n = flat.numel()
   dev = flat.device
@@ -50,6 +52,8 @@ def unique(ids):
   ws_bytes = lib.det_unique_workspace_bytes(n)
   ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
   _lib.check(lib.det_unique(_ptr(flat), n, _ptr(uniq), _ptr(idx), _ptr(cnt), _ptr(ws), ws_bytes, _stream_ptr(dev)))
+  if return_count_tensor:
+    return uniq, idx, cnt
   return uniq[:int(cnt.item())], idx
 
 
@@ -80,11 +84,12 @@ def segment_reduce(rows, idx, n_groups):
 
 def combine_rows(rows, idx, n_unique):
   """per-unique-key sum of row gradients (idx from `unique`): the dedupe in front of the sparse optimizer step.
-  DET_GRAD_REDUCE=det: det_segment_reduce -- rows added in position order, deterministic, bit-identical to the
-  sequential sum (csrc/fused.cu K9).  Default until that kernel has run on a B200 (written after round 1's GPU budget
-  was spent; emulator-tested): torch's index_add, whose GPU atomics add in schedule order."""
+  Default (DET_GRAD_REDUCE=det): det_segment_reduce -- rows added in position order, deterministic, bit-identical to
+  the sequential sum (csrc/fused.cu K9; validated on B200 in round 2: the c3 step's gradient sum takes 0.42 ms against
+  0.83 ms of index_add, profiles/r02_bench_c3_{det,torch}.json).  DET_GRAD_REDUCE=torch: torch's index_add, whose GPU
+  atomics add in schedule order."""
   import os
-  if os.environ.get("DET_GRAD_REDUCE", "torch") == "det" and rows.dtype == torch.float32 and \
+  if os.environ.get("DET_GRAD_REDUCE", "det") == "det" and rows.dtype == torch.float32 and \
       rows.device.type in _segment_reduce_devices():
     return segment_reduce(rows, idx, n_unique)
   return torch.zeros((n_unique, rows.shape[1]), dtype=rows.dtype, device=rows.device).index_add_(0, idx.long(), rows)

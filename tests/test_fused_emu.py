@@ -12,7 +12,8 @@ from recommenders_addons_b200 import _lib as real
 from tests.helpers import sorted_export
 from tests.test_detable_emu import L, P, Table, ck
 
-_FUSED = ["det_unique_workspace_bytes", "det_unique", "det_lookup_sparse", "det_lookup_sparse_clip", "det_apply_adagrad",
+_FUSED = ["det_apply_dup_workspace_bytes", "det_apply_adagrad_dup", "det_apply_adam_dup",
+          "det_unique_workspace_bytes", "det_unique", "det_lookup_sparse", "det_lookup_sparse_clip", "det_apply_adagrad",
           "det_apply_adam",
           "det_partition_workspace_bytes", "det_partition", "det_scatter_rows", "det_gather_rows"]
 
@@ -196,6 +197,57 @@ def test_fused_adam_twin(dim):
     np.testing.assert_array_equal(k, ek)
     np.testing.assert_array_equal(val, ev)
   t.close()
+
+
+@pytest.mark.parametrize("dim,opt", [(64, "adagrad"), (16, "adagrad"), (32, "adam")])
+def test_apply_with_repeated_ids_in_one_call(dim, opt):
+  """det_apply_*_dup: ids WITH repeats (Zipf head: one id owns a group of > 1024 rows, the column-sliced path) and their
+  row gradients in ONE call -- unique + position-order sum + fused step chained on the device, the unique count never
+  read by the host.  Twin: oracle unique_first_occurrence -> segment_reduce -> sparse_*_step; params and slots bit-exact
+  over several steps, the table growing underneath; the device count is returned too."""
+  rng = np.random.default_rng(dim * 3 + len(opt))
+  planes = 1 if opt == "adagrad" else 2
+  t = Table(dim=dim, init=256, slot_planes=planes)
+  tabs = [O.PortTable(dim) for _ in range(1 + planes)]
+  ip = np.full(dim, 0.05, np.float32)
+  ia = np.full(dim, 0.1, np.float32)
+  z = np.zeros(dim, np.float32)
+  n = 2600
+  wsb = F().det_apply_dup_workspace_bytes(n, dim)
+  raw = np.zeros(wsb + 256, np.uint8)
+  ws = raw[(-raw.ctypes.data) % 256:][:wsb]
+  cnt = np.zeros(1, np.int64)
+  for step in range(1, 4):
+    ids = np.concatenate([np.full(1200, 7), rng.integers(0, 40, 600), rng.integers(0, 5000, n - 1800)]).astype(np.int64)
+    rng.shuffle(ids)
+    g = (rng.normal(0, 1e-2, (n, dim)) * np.exp(rng.uniform(-4, 4, (n, 1)))).astype(np.float32)
+    uniq, idx = O.unique_first_occurrence(ids)
+    gs = O.segment_reduce(g, idx, len(uniq))
+    if opt == "adagrad":
+      O.sparse_adagrad_step(tabs[0], tabs[1], uniq, gs, 0.1, ip, ia, 0.0)
+      ck(F().det_apply_adagrad_dup(t.h, P(ids), P(g), n, 0.1, 0.0, P(ip), 0.1, P(ws), wsb, P(cnt), None))
+    else:
+      alpha = O.adam_scalars(0.01, 0.9, 0.999, step)
+      O.sparse_adam_step(tabs[0], tabs[1], tabs[2], uniq, gs, alpha, 0.9, 0.999, 1e-8, ip)
+      ck(F().det_apply_adam_dup(t.h, P(ids), P(g), n, float(alpha), 0.9, 0.999, 1e-8, P(ip), P(ws), wsb, P(cnt), None))
+    assert cnt[0] == len(uniq)
+  assert t.size() == tabs[0].size()
+  for plane, ot in enumerate(tabs):
+    k, v = _export_sorted(t, plane)
+    ek, ev = sorted_export(ot)
+    np.testing.assert_array_equal(k, ek)
+    np.testing.assert_array_equal(v, ev)
+  # argument checks: workspace too small / misaligned, odd rows are refused with DET_UNIMPLEMENTED (5)
+  assert F().det_apply_adagrad_dup(t.h, P(ids), P(g), n, 0.1, 0.0, P(ip), 0.1, P(ws), wsb - 1024, None, None) == 1
+  t.close()
+  t3 = Table(dim=3, init=256, slot_planes=2)
+  g3 = np.zeros((8, 3), np.float32)
+  i3 = np.arange(8, dtype=np.int64)
+  w3b = F().det_apply_dup_workspace_bytes(8, 3)
+  raw3 = np.zeros(w3b + 256, np.uint8)
+  w3 = raw3[(-raw3.ctypes.data) % 256:][:w3b]
+  assert F().det_apply_adagrad_dup(t3.h, P(i3), P(g3), 8, 0.1, 0.0, P(np.zeros(3, np.float32)), 0.1, P(w3), w3b, None, None) == 5
+  t3.close()
 
 
 def test_slot_state_of_keys_created_by_insert():
