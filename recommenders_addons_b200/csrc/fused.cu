@@ -185,11 +185,14 @@ static size_t unique_ws_layout(size_t n, unsigned char* base, UniqueWs* w) {
 // K6: fused embedding_lookup_sparse
 // ------------------------------------------------------------------------------------------------
 // seg_start[b] = first position i with segment_ids[i] >= b ; seg_start[batch] = nnz
+// not_identity (nullable, zeroed by the caller): set when some id i does not belong to row i -- with nnz == batch a zero
+// afterwards means "exactly one id per output row", the Criteo shape, which the find-shaped kernel below serves
 __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, size_t batch,
-                                       long long* __restrict__ seg_start, DevState* st) {
+                                       long long* __restrict__ seg_start, DevState* st, unsigned* not_identity) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nnz) return;
   const long long cur = i < nnz ? (long long)seg[i] : (long long)batch;
+  if (not_identity && i < nnz && cur != (long long)i) *not_identity = 1u;
   const long long prev = i > 0 ? (long long)seg[i - 1] : -1;
   if (cur < prev || cur < 0 || cur > (long long)batch || (i < nnz && cur >= (long long)batch)) {
     atomicOr(&st->error, kErrBadSegment);
@@ -202,7 +205,8 @@ __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, 
 // det_find; only 8 B per id leave the kernel (the [nnz, dim] gather of the reference is never materialised)
 __global__ void __launch_bounds__(kThreadsF)
 resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz, long long* __restrict__ slots,
-                     int use_tma) {
+                     int use_tma, const unsigned* __restrict__ run_if_set) {
+  if (run_if_set && *run_if_set == 0u) return;   // the one-id-per-row kernel has served this call
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
   __shared__ __align__(8) unsigned long long s_bar[kStages];
   const int lane = threadIdx.x & 31;
@@ -214,6 +218,35 @@ resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz,
     const long long key = kt.key(i, valid);
     const long long slot = warp_find_slots<false>(t, key, valid, lane);
     if (valid) slots[i] = slot;
+  }
+}
+
+// K6, one id per output row and no weights (every combiner then returns the row itself: 0 + row * 1, / 1): the call IS a
+// Find into the dense output, so it runs as one -- 32 rows per warp-step, 4 row loads in flight per lane, no slot
+// scratch and no per-row segment bookkeeping.  Launched on spec next to the general kernels: `not_identity` (written by
+// segment_offsets_kernel earlier on the stream) decides on the device which of the two does the work.
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsF)
+lookup_identity_kernel(TableView t, const long long* __restrict__ ids, size_t n, const unsigned char* __restrict__ default_row,
+                       unsigned char* __restrict__ out, RowGeom g, int use_tma, const unsigned* __restrict__ not_identity) {
+  if (*not_identity != 0u) return;
+  __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
+  __shared__ __align__(8) unsigned long long s_bar[kStages];
+  const int lane = threadIdx.x & 31;
+  KeyTiles kt;
+  kt.init(s_keys, s_bar, ids, n, use_tma != 0);
+  for (; kt.valid(); kt.next()) {
+    size_t i;
+    bool valid;
+    const long long key = kt.key(i, valid);
+    const long long slot = warp_find_slots<false>(t, key, valid, lane);
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid) {
+      src = slot >= 0 ? t.planes[0] + (size_t)slot * g.row_bytes : DET_SRC_DEFAULT;
+      dst = out + i * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane, default_row);
   }
 }
 
@@ -264,7 +297,8 @@ __global__ void __launch_bounds__(kThreadsF, DET_SEG_MINB)
 segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
                    const float* __restrict__ weights, size_t batch, int combiner,
                    const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
-                   unsigned lpr_shift, ClipArg<CLIP> clip) {
+                   unsigned lpr_shift, ClipArg<CLIP> clip, const unsigned* __restrict__ run_if_set) {
+  if (run_if_set && *run_if_set == 0u) return;   // the one-id-per-row kernel has served this call
   constexpr int U = kSegPerGroup;
   const int lane = threadIdx.x & 31;
   const unsigned gl = (unsigned)lane & (lpr - 1u);
@@ -1390,21 +1424,50 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
   det::DevGuard _dg(t->cfg.device);
   long long* seg_start = nullptr;
   long long* slots = nullptr;
+  unsigned* not_identity = nullptr;
   {
     void* sc = nullptr;
     const size_t seg_bytes = ((batch + 1) * sizeof(long long) + 255) & ~(size_t)255;
-    det_status sst = table_scratch(t, seg_bytes + (nnz ? nnz : 1) * sizeof(long long), &sc);
+    det_status sst = table_scratch(t, 256 + seg_bytes + (nnz ? nnz : 1) * sizeof(long long), &sc);
     if (sst != DET_OK) return sst;
-    seg_start = (long long*)sc;
-    slots = (long long*)((unsigned char*)sc + seg_bytes);
+    not_identity = (unsigned*)sc;
+    seg_start = (long long*)((unsigned char*)sc + 256);
+    slots = (long long*)((unsigned char*)sc + 256 + seg_bytes);
   }
-  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st);
-  if (nnz)
-    DET_LAUNCH(resolve_slots_kernel, grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF, 0, s, t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0);
   const unsigned dim = (unsigned)t->cfg.dim;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out) & 15u) == 0);
   unsigned vpr, lpr, sh;
   fgeom(dim, vec4, 1, &vpr, &lpr, &sh);
+  // One id per output row and no weights (the Criteo shape: 26 features x batch, one id each): the op is a Find into the
+  // dense output.  Whether the segment ids really are 0..nnz-1 is only known on the DEVICE (segment_offsets_kernel
+  // computes it): the find-shaped kernel and the general pair are both launched, the flag lets exactly one of them work.
+  const int ivec = pick_vec(t->row_bytes, default_row, out, nullptr);
+  const bool try_identity = nnz == batch && nnz > 0 && weights == nullptr && !(max_norm > 0.f) && vpr <= lpr && ivec >= 4 &&
+                            env_int("DET_SEGSUM_STAGED", 0) == 0 && env_int("DET_SPARSE_IDENTITY", 1) != 0;
+  const unsigned* gate = try_identity ? not_identity : nullptr;
+  if (try_identity) CUDA_TRY(cudaMemsetAsync(not_identity, 0, sizeof(unsigned), s));
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st,
+             try_identity ? not_identity : (unsigned*)nullptr);
+  if (try_identity) {
+    const int vec = ivec;
+    const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
+    const int tma = (((uintptr_t)ids & 15u) == 0) ? 1 : 0;
+    const long long* k = (const long long*)ids;
+    const unsigned char* d = (const unsigned char*)default_row;
+    unsigned char* o = (unsigned char*)out;
+#define DET_IDENT(VV)                                                                                              \
+  case VV: {                                                                                                        \
+    const int grid = grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(lookup_identity_kernel<VV>, kThreadsF));   \
+    DET_LAUNCH(lookup_identity_kernel<VV>, grid, kThreadsF, 0, s, t->view, k, nnz, d, o, g, tma, gate);             \
+  } break;
+    switch (vec) {
+      DET_IDENT(16) DET_IDENT(8) DET_IDENT(4)
+      default: break;
+    }
+#undef DET_IDENT
+  }
+  if (nnz)
+    DET_LAUNCH(resolve_slots_kernel, grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF, 0, s, t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0, gate);
   det_status rc = DET_OK;
   const unsigned gpw = 32u >> sh;
   if (vpr <= lpr && max_norm > 0.f) {
@@ -1415,9 +1478,9 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
     const int occ = vec4 ? occupancy_of(k4, kThreadsF) : occupancy_of(k1, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
-      DET_LAUNCH(k4, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip);
+      DET_LAUNCH(k4, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip, (const unsigned*)nullptr);
     else
-      DET_LAUNCH(k1, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip);
+      DET_LAUNCH(k1, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip, (const unsigned*)nullptr);
   } else if (max_norm > 0.f) {
     rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse_clip: max_norm is fused for rows of at most 32 vectors (dim <= 128 when "
                                  "dim % 4 == 0, else dim <= 32); use the composed path for wider rows");
@@ -1437,9 +1500,9 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
-      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, gate);
     else
-      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, gate);
   } else if ((vpr + lpr - 1) / lpr <= (unsigned)kMaxVecPerLane) {
     const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
     if (vec4)
@@ -1656,7 +1719,7 @@ det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st);
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st, (unsigned*)nullptr);
   const long long* slots = (const long long*)row_idx;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out | (uintptr_t)rows) & 15u) == 0);
   unsigned vpr, lpr, sh;
@@ -1677,9 +1740,9 @@ det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* 
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), sms, occ);
     if (vec4)
-      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, (const unsigned*)nullptr);
     else
-      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip);
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, (const unsigned*)nullptr);
   } else {
     const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), sms, 8);
     if (vec4)

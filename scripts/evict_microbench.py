@@ -38,6 +38,9 @@ def main():
   ap.add_argument("--batch", type=int, default=1 << 20)
   ap.add_argument("--new-frac", type=float, default=0.1)
   ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--fill-frac", type=float, default=0.87, help="resident keys / capacity before the measurements (the soft "
+                  "limit of a table with an eviction strategy is 0.875: just below it, so that the steady state evicts)")
+  ap.add_argument("--only-events", action="store_true", help="stop after the explicit eviction events (ncu launch lists)")
   a = ap.parse_args()
   dev = torch.device("cuda", 0)
   g = torch.Generator(device=dev)
@@ -59,7 +62,7 @@ def main():
     print(json.dumps({"what": "insert below the limit", "path": name, "ms": ms, "keys_per_s": a.batch / ms * 1e3}))
   del plain
   # (2) explicit events
-  fill = int(a.capacity * 0.8)
+  fill = int(a.capacity * a.fill_frac)
   done = a.batch
   while done < fill:
     k = torch.randint(0, 1 << 62, (a.batch,), device=dev, generator=g)
@@ -72,6 +75,8 @@ def main():
     torch.cuda.synchronize()
     print(json.dumps({"what": "explicit eviction event", "k": k_ev, "evicted": got, "ms": (time.perf_counter() - t0) * 1e3,
                       "resident": int(lru.size())}))
+  if a.only_events:
+    return
   # (3) steady state at the limit
   n_new = int(a.batch * a.new_frac)
   resident = lru.export()[0]

@@ -105,6 +105,37 @@ def test_lookup_sparse_bit_exact_vs_oracle(combiner, use_weights, dim):
 
 
 @pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
+@pytest.mark.parametrize("dim", [1, 6, 16, 64, 200])
+@pytest.mark.parametrize("shape", ["identity", "same_count_not_identity", "identity_with_weights"])
+def test_lookup_sparse_one_id_per_row(combiner, dim, shape):
+  """nnz == batch: the library launches the find-shaped kernel AND the general pair and lets a device flag (are the
+  segment ids 0..nnz-1?) pick the one that works.  identity: one id per row (the Criteo shape) -> rows / default rows,
+  whatever the combiner; same_count_not_identity: nnz == batch but two ids share a row and one row is empty -> the
+  general kernels must do the work; with weights the fast path is never tried.  All bit-exact vs the oracle."""
+  rng = np.random.default_rng(dim * 5 + len(shape))
+  vocab, batch = 500, 333
+  t = Table(dim=dim, init=2048)
+  present = rng.choice(vocab, size=350, replace=False).astype(np.int64)
+  vals = rng.normal(0, 0.05, (350, dim)).astype(np.float32)
+  t.insert(present, vals)
+  ot = O.PortTable(dim)
+  ot.insert(present, vals)
+  ids = rng.integers(0, vocab, size=batch).astype(np.int64)           # repeats and ~30 % missing ids
+  seg = np.arange(batch, dtype=np.int32)
+  w = None
+  if shape == "same_count_not_identity":
+    seg[100] = 99                                                      # rows 99 (two ids) and 100 (none)
+  if shape == "identity_with_weights":
+    w = rng.uniform(0.25, 2.0, size=batch).astype(np.float32)
+  default = np.full(dim, 0.25, np.float32)
+  out = np.full((batch, dim), np.nan, dtype=np.float32)
+  ck(F().det_lookup_sparse(t.h, P(ids), P(seg), P(w), batch, batch, real.COMBINERS[combiner], P(default), P(out), None))
+  exp = O.embedding_lookup_sparse(ot, ids, seg, w, batch, combiner, default=default)
+  np.testing.assert_array_equal(out, exp)
+  t.close()
+
+
+@pytest.mark.parametrize("combiner", ["sum", "mean", "sqrtn"])
 @pytest.mark.parametrize("dim", [1, 5, 16, 64, 128])
 def test_lookup_sparse_with_max_norm(combiner, dim):
   """det_lookup_sparse_clip: tf.clip_by_norm of every looked-up row (missing ids: of the default row) BEFORE the weighted
