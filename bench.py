@@ -525,14 +525,22 @@ def gpu_arm(args):
   is_push = exchange == "push"
   table = var.tables[0]
   # ---- prefill this rank's shard: all ranks r of the vocabulary with owner(key(r)) == rank; row = f(key, generation 0)
-  chunk = 1 << 20
-  for b in range(0, vocab, chunk):
-    r = torch.arange(b, min(vocab, b + chunk), dtype=torch.int64, device=dev)
-    k = rank_to_key_torch(r)
-    if world > 1:
-      k = k[de.default_partition_fn(k, world, True) == rank]
-    if k.numel():
+  chunk = min(1 << 20, B)
+  if sharded is None:
+    for b in range(0, vocab, chunk):
+      k = rank_to_key_torch(torch.arange(b, min(vocab, b + chunk), dtype=torch.int64, device=dev))
       table.insert(k, rows_of_keys_torch(k, dim, 0))
+  else:
+    # every rank generates 1/N of the vocabulary (ranks [rank*resident, (rank+1)*resident)) and writes it THROUGH the
+    # sharded table: the keys travel to their owners over the same exchange the timed steps use (N times less work per
+    # rank than filtering the whole vocabulary, and the exchange has moved `resident` keys per rank before it is timed)
+    for b in range(rank * resident, (rank + 1) * resident, chunk):
+      k = rank_to_key_torch(torch.arange(b, min((rank + 1) * resident, b + chunk), dtype=torch.int64, device=dev))
+      sharded.upsert(k, rows_of_keys_torch(k, dim, 0))
+    if is_peer:
+      sharded.phase_barrier()
+    torch.cuda.synchronize()
+    dist.barrier()
   local_size = int(table.size())
   cdf = zipf_cdf_torch(vocab, dev)
   n_batches = max(1, min(args.steps + args.warmup, args.distinct_batches if dim <= 64 else min(args.distinct_batches, 8)))

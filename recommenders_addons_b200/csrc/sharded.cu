@@ -257,7 +257,10 @@ __global__ void peer_barrier_kernel(BarPtrs bp, int rank, int world, unsigned lo
 // xchg_wait_kernel (ld.acquire.sys spin, bounded) in front of the consuming kernel.  No rank-wide barrier: a rank only
 // ever waits for the ranks whose data it is about to read.  All ranks call det_peer_xchg_find / det_peer_xchg_insert
 // collectively and in the same order (exactly like the reference's alltoall ops).
-enum : int { kFlagReq = 0, kFlagDone = 1, kFlagIns = 2, kFlagAck = 3 };   // one 64 B line of 8 u64 each
+enum : int { kFlagReq = 0, kFlagDone = 1, kFlagIns = 2, kFlagAck = 3, kFlagIns1 = 4 };   // one 64 B line of 8 u64 each
+constexpr size_t kXchgHeader = 512;   // flag lines (5 x 64 B) live in front of the segments
+// Insert epochs alternate between TWO sets of (segments, count flags): a source may already be routing epoch e+1 into
+// set (e+1)&1 while the owner still applies epoch e from set e&1 -- the chunk pipeline of det_peer_xchg_insert.
 
 struct XchgView {
   unsigned char* base[kMaxPeers];   // where THIS process sees rank p's mailbox
@@ -330,8 +333,10 @@ xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigne
   __shared__ unsigned long long s_base[kMaxPeers];
   const int lane = threadIdx.x & 31;
   const size_t n_tiles = (n + kThreadsP - 1) / kThreadsP;
+  const size_t par = WITH_ROWS ? (size_t)(epoch & 1ull) : 0;          // insert epochs alternate between two segment sets
   const size_t seg_k = WITH_ROWS ? xv.seg_ins_keys : xv.seg_req_keys;
-  const size_t off_k = (WITH_ROWS ? xv.off_ins_keys : xv.off_req_keys) + (size_t)xv.rank * seg_k;
+  const size_t off_k = (WITH_ROWS ? xv.off_ins_keys + par * (size_t)xv.world * seg_k : xv.off_req_keys) + (size_t)xv.rank * seg_k;
+  const size_t off_r = xv.off_ins_rows + (par * (size_t)xv.world + (size_t)xv.rank) * xv.seg_ins_rows;
   for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     if (threadIdx.x < kMaxPeers) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -353,7 +358,7 @@ xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigne
       unsigned char* dst = nullptr;
       if (ok) {
         src = rows + i * g.row_bytes;
-        dst = xv.base[own] + xv.off_ins_rows + (size_t)xv.rank * xv.seg_ins_rows + dest * g.row_bytes;
+        dst = xv.base[own] + off_r + dest * g.row_bytes;
       }
       warp_move_rows<VEC>(g, src, dst, lane);
     } else if (ok) {
@@ -366,7 +371,7 @@ xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigne
     unsigned long long c = atomicAdd(&cursor[o], 0ull);
     if (c > xv.cap) c = xv.cap;
     cursor[o] = 0;
-    st_release_sys(xchg_flag(xv, o, WITH_ROWS ? kFlagIns : kFlagReq, xv.rank), (epoch << 32) | c);
+    st_release_sys(xchg_flag(xv, o, WITH_ROWS ? (par ? kFlagIns1 : kFlagIns) : kFlagReq, xv.rank), (epoch << 32) | c);
   }
 }
 
@@ -446,11 +451,12 @@ xchg_apply_insert_kernel(XchgView xv, TableView t, RowGeom g, int n_slot_planes,
                          unsigned long long epoch) {
   __shared__ unsigned long long s_pref[kMaxPeers + 1];
   __shared__ unsigned s_new, s_used;
+  const size_t par = (size_t)(epoch & 1ull);
   if (threadIdx.x == 0) {
     unsigned long long acc = 0;
     for (int s = 0; s < xv.world; ++s) {
       s_pref[s] = acc;
-      acc += *((volatile unsigned long long*)xchg_flag(xv, xv.rank, kFlagIns, s)) & 0xffffffffull;
+      acc += *((volatile unsigned long long*)xchg_flag(xv, xv.rank, par ? kFlagIns1 : kFlagIns, s)) & 0xffffffffull;
     }
     for (int s = xv.world; s <= kMaxPeers; ++s) s_pref[s] = acc;
     s_new = 0;
@@ -465,7 +471,7 @@ xchg_apply_insert_kernel(XchgView xv, TableView t, RowGeom g, int n_slot_planes,
     const bool valid = f < total;
     unsigned long long i = 0;
     const int s = valid ? xchg_locate(s_pref, xv.world, f, i) : 0;
-    const long long key = valid ? ld_cg_ll(reinterpret_cast<const long long*>(xv.base[xv.rank] + xv.off_ins_keys + (size_t)s * xv.seg_ins_keys) + i) : 0;
+    const long long key = valid ? ld_cg_ll(reinterpret_cast<const long long*>(xv.base[xv.rank] + xv.off_ins_keys + (par * (size_t)xv.world + (size_t)s) * xv.seg_ins_keys) + i) : 0;
     bool is_new, from_empty;
     const long long slot = warp_find_or_claim(t, key, valid, valid, lane, is_new, from_empty);
     const unsigned bn = __ballot_sync(kFull, is_new), bu = __ballot_sync(kFull, from_empty);
@@ -476,7 +482,7 @@ xchg_apply_insert_kernel(XchgView xv, TableView t, RowGeom g, int n_slot_planes,
     const unsigned char* src = nullptr;
     unsigned char* dst = nullptr;
     if (valid && slot >= 0) {
-      src = xv.base[xv.rank] + xv.off_ins_rows + (size_t)s * xv.seg_ins_rows + (size_t)i * g.row_bytes;
+      src = xv.base[xv.rank] + xv.off_ins_rows + (par * (size_t)xv.world + (size_t)s) * xv.seg_ins_rows + (size_t)i * g.row_bytes;
       dst = t.planes[0] + (size_t)slot * g.row_bytes;
     }
     warp_move_rows<VEC>(g, src, dst, lane);
@@ -518,7 +524,10 @@ struct det_peer_group {
   // owner-side exchange (det_peer_xchg_*)
   XchgView xv{};
   bool xchg = false;
-  unsigned long long* xcursor = nullptr;     // owned: [kMaxPeers] cursors + 1 ticket word
+  unsigned long long* xcursor = nullptr;     // owned: [kMaxPeers] cursors + 2 ticket words (senders / owner-side kernels)
+  cudaStream_t s_route = nullptr, s_apply = nullptr;   // chunk pipeline of det_peer_xchg_insert
+  cudaEvent_t ev_in = nullptr, ev_route = nullptr, ev_apply = nullptr;
+  int chunks = 1;
   unsigned long long ep_find = 0, ep_ins = 0;
   DevState* h_snap = nullptr;                // pinned: async snapshot of the local shard's DevState
   cudaEvent_t snap_ev = nullptr;
@@ -576,18 +585,22 @@ det_status det_peer_group_destroy(det_peer_group* g) {
   if (g->h_counts) cudaFreeHost(g->h_counts);
   if (g->timing) {
     xchg_time_collect(g, 0, 4);
-    xchg_time_collect(g, 1, 5);
+    xchg_time_collect(g, 1, 1);
     const double cf = g->tcalls[0] ? (double)g->tcalls[0] : 1.0, ci = g->tcalls[1] ? (double)g->tcalls[1] : 1.0;
     fprintf(stderr, "[det xchg timing rank %d] find x%llu: route %.1f us, wait_req %.1f, serve %.1f, wait_done %.1f | "
-                    "insert x%llu: wait_ack %.1f us, route %.1f, wait_ins %.1f, apply %.1f, snapshot %.1f\n", g->pv.rank,
+                    "insert x%llu (%d chunks, pipelined): %.1f us\n", g->pv.rank,
             g->tcalls[0], g->tacc[0][0] / cf * 1e3, g->tacc[0][1] / cf * 1e3, g->tacc[0][2] / cf * 1e3, g->tacc[0][3] / cf * 1e3,
-            g->tcalls[1], g->tacc[1][0] / ci * 1e3, g->tacc[1][1] / ci * 1e3, g->tacc[1][2] / ci * 1e3, g->tacc[1][3] / ci * 1e3,
-            g->tacc[1][4] / ci * 1e3);
+            g->tcalls[1], g->chunks, g->tacc[1][0] / ci * 1e3);
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 6; ++b)
         if (g->tev[a][b]) cudaEventDestroy(g->tev[a][b]);
   }
   if (g->xcursor) cudaFree(g->xcursor);
+  if (g->s_route) cudaStreamDestroy(g->s_route);
+  if (g->s_apply) cudaStreamDestroy(g->s_apply);
+  if (g->ev_in) cudaEventDestroy(g->ev_in);
+  if (g->ev_route) cudaEventDestroy(g->ev_route);
+  if (g->ev_apply) cudaEventDestroy(g->ev_apply);
   if (g->h_snap) cudaFreeHost(g->h_snap);
   if (g->snap_ev) cudaEventDestroy(g->snap_ev);
   delete g;
@@ -823,7 +836,7 @@ det_status det_peer_inbox_gather(det_peer_group* g, int shard, const int64_t* co
 
 // ---- owner-side exchange: host entry points ----------------------------------------------------------------------
 static void xchg_layout(int world, size_t cap, size_t rb, XchgView* xv) {
-  size_t off = 256;
+  size_t off = kXchgHeader;
   xv->seg_req_keys = al256(cap * 8);
   xv->seg_req_idx = al256(cap * 4);
   xv->seg_ins_keys = al256(cap * 8);
@@ -832,8 +845,8 @@ static void xchg_layout(int world, size_t cap, size_t rb, XchgView* xv) {
   xv->ex_bytes = al256(cap);
   xv->off_req_keys = off; off += (size_t)world * xv->seg_req_keys;
   xv->off_req_idx = off;  off += (size_t)world * xv->seg_req_idx;
-  xv->off_ins_keys = off; off += (size_t)world * xv->seg_ins_keys;
-  xv->off_ins_rows = off; off += (size_t)world * xv->seg_ins_rows;
+  xv->off_ins_keys = off; off += 2 * (size_t)world * xv->seg_ins_keys;   // two sets (epoch parity)
+  xv->off_ins_rows = off; off += 2 * (size_t)world * xv->seg_ins_rows;
   xv->off_out = off;      off += 2 * xv->out_bytes;
   xv->off_exists = off;   off += 2 * xv->ex_bytes;
   xv->cap = cap;
@@ -863,9 +876,18 @@ det_status det_peer_xchg_attach(det_peer_group* g, const void* const* mailbox_pt
     g->xv.base[p] = (unsigned char*)mailbox_ptrs[p];
   }
   if (!g->xcursor) {
-    CUDA_TRY(cudaMalloc((void**)&g->xcursor, (kMaxPeers + 1) * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(g->xcursor, 0, (kMaxPeers + 1) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc((void**)&g->xcursor, (kMaxPeers + 2) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(g->xcursor, 0, (kMaxPeers + 2) * sizeof(unsigned long long)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->s_route, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->s_apply, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->ev_route, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->ev_apply, cudaEventDisableTiming));
   }
+  // chunks of one det_peer_xchg_insert call (every chunk is a collective epoch: the SAME value on every rank)
+  g->chunks = env_int("DET_XCHG_CHUNKS", 4);
+  if (g->chunks < 1) g->chunks = 1;
+  if (g->chunks > 16) g->chunks = 16;
   g->ep_find = g->ep_ins = 0;
   g->xchg = true;
   g->timing = env_int("DET_XCHG_TIMING", 0) != 0;
@@ -976,12 +998,12 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
 #define DET_XSERVE(VV)                                                                                                   \
   case VV: {                                                                                                              \
     const int grid = g->sm_count * occupancy_of(xchg_serve_find_kernel<VV>, kThreadsP);                                   \
-    DET_LAUNCH(xchg_serve_find_kernel<VV>, grid, kThreadsP, 0, s, xv, tv, d, full_size_default, want_exists, parity, geo, ticket, ep); \
+    DET_LAUNCH(xchg_serve_find_kernel<VV>, grid, kThreadsP, 0, s, xv, tv, d, full_size_default, want_exists, parity, geo, ticket + 2, ep); \
   } break;
       DET_XSERVE(16) DET_XSERVE(8) DET_XSERVE(4) DET_XSERVE(2)
       default: {
         const int grid = g->sm_count * occupancy_of(xchg_serve_find_kernel<1>, kThreadsP);
-        DET_LAUNCH(xchg_serve_find_kernel<1>, grid, kThreadsP, 0, s, xv, tv, d, full_size_default, want_exists, parity, geo, ticket, ep);
+        DET_LAUNCH(xchg_serve_find_kernel<1>, grid, kThreadsP, 0, s, xv, tv, d, full_size_default, want_exists, parity, geo, ticket + 2, ep);
       } break;
 #undef DET_XSERVE
     }
@@ -1011,6 +1033,11 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
 }
 
 // Sharded Insert (insert_or_assign) through the owners.  COLLECTIVE like det_peer_xchg_find.
+// The batch is cut into `chunks` pieces (DET_XCHG_CHUNKS, default 4, the same on every rank) and PIPELINED over two
+// internal streams: while the owner-side kernel applies the pairs of chunk c to the local shard (HBM-bound, no NVLink
+// traffic), the sender kernel already routes chunk c+1 to its owners (NVLink-bound, little SM time).  Every chunk is an
+// epoch of the flag protocol; epochs alternate between two sets of inbox segments, so a sender only ever waits for
+// the owners to have consumed the epoch before the previous one.  The caller's stream is fenced on both sides by events.
 det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
                                 det_stream_t stream) {
   if (!g || !g->xchg) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: no exchange mailbox attached");
@@ -1021,55 +1048,82 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
   det_status rs = peer_room(g, "det_peer_xchg_insert");
   if (rs != DET_OK) return rs;
   std::lock_guard<std::mutex> _lk(g->local->mu);
-  xchg_time_collect(g, 1, 5);
-  const unsigned long long ep = ++g->ep_ins;
+  xchg_time_collect(g, 1, 1);
+  xchg_mark(g, 1, 0, s);
   const XchgView& xv = g->xv;
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
-  unsigned* ticket = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
+  const int avec = pick_vec(g->row_bytes, nullptr, nullptr, nullptr);
+  const RowGeom ageo = make_geom((unsigned)g->row_bytes, avec);
+  unsigned* ticket_r = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
+  unsigned* ticket_a = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers + 1);
   DevState* st = g->local->view.st;
-  const long long* k = (const long long*)keys;
-  const unsigned char* r = (const unsigned char*)values;
-  xchg_mark(g, 1, 0, s);
-  if (ep > 1) xchg_wait(g, kFlagAck, ep - 1, s);   // every owner has consumed what this rank sent last time
-  xchg_mark(g, 1, 1, s);
-  {
-    const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
-    switch (vec) {
-      case 16: DET_LAUNCH((xchg_route_kernel<true, 16>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
-      case 8: DET_LAUNCH((xchg_route_kernel<true, 8>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
-      case 4: DET_LAUNCH((xchg_route_kernel<true, 4>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
-      case 2: DET_LAUNCH((xchg_route_kernel<true, 2>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
-      default: DET_LAUNCH((xchg_route_kernel<true, 1>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket, ep, st); break;
-    }
+  const TableView tv = g->local->view;
+  const int np = g->n_slot_planes;
+  const int C = g->chunks;
+  const bool piped = C > 1;
+  cudaStream_t sr = piped ? g->s_route : s, sa = piped ? g->s_apply : s;
+  if (piped) {
+    CUDA_TRY(cudaEventRecord(g->ev_in, s));
+    CUDA_TRY(cudaStreamWaitEvent(sr, g->ev_in, 0));
+    CUDA_TRY(cudaStreamWaitEvent(sa, g->ev_in, 0));
   }
-  xchg_mark(g, 1, 2, s);
-  xchg_wait(g, kFlagIns, ep, s);
-  xchg_mark(g, 1, 3, s);
-  {
-    const int avec = pick_vec(g->row_bytes, nullptr, nullptr, nullptr);
-    const RowGeom ageo = make_geom((unsigned)g->row_bytes, avec);
-    const TableView tv = g->local->view;
-    const int np = g->n_slot_planes;
+  // per-chunk key ranges: multiples of 256 keys so that every chunk's rows stay 16 B aligned like the batch
+  const size_t per = ((n + (size_t)C - 1) / (size_t)C + 255) & ~(size_t)255;
+  // two kernels share the SMs: neither grid may take every resident slot (registers) of an SM
+  const int route_cap = piped ? 2 : 4;
+  for (int c = 0; c < C; ++c) {
+    const size_t b = (size_t)c * per < n ? (size_t)c * per : n;
+    const size_t e = b + per < n ? b + per : n;
+    const size_t m = e - b;
+    const long long* k = (const long long*)keys + b;
+    const unsigned char* r = (const unsigned char*)values + b * g->row_bytes;
+    const unsigned long long ep = ++g->ep_ins;
+    // sender side: the owners have consumed the segment set this epoch is about to overwrite (epoch ep - 2)
+    if (ep > 2) {
+      const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + kFlagAck * 64);
+      DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, sr, flags, xv.world, ep - 2, st, kXchgTimeoutCycles);
+    }
+    {
+      const int grid = grid_for(m, kThreadsP, g->sm_count, route_cap);
+      switch (vec) {
+        case 16: DET_LAUNCH((xchg_route_kernel<true, 16>), grid, kThreadsP, 0, sr, xv, k, r, m, geo, g->xcursor, ticket_r, ep, st); break;
+        case 8: DET_LAUNCH((xchg_route_kernel<true, 8>), grid, kThreadsP, 0, sr, xv, k, r, m, geo, g->xcursor, ticket_r, ep, st); break;
+        case 4: DET_LAUNCH((xchg_route_kernel<true, 4>), grid, kThreadsP, 0, sr, xv, k, r, m, geo, g->xcursor, ticket_r, ep, st); break;
+        case 2: DET_LAUNCH((xchg_route_kernel<true, 2>), grid, kThreadsP, 0, sr, xv, k, r, m, geo, g->xcursor, ticket_r, ep, st); break;
+        default: DET_LAUNCH((xchg_route_kernel<true, 1>), grid, kThreadsP, 0, sr, xv, k, r, m, geo, g->xcursor, ticket_r, ep, st); break;
+      }
+    }
+    // owner side: every source has published its count of this epoch
+    {
+      const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + ((ep & 1ull) ? kFlagIns1 : kFlagIns) * 64);
+      DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, sa, flags, xv.world, ep, st, kXchgTimeoutCycles);
+    }
     switch (avec) {
 #define DET_XAPPLY(VV)                                                                                        \
   case VV: {                                                                                                   \
-    const int grid = g->sm_count * occupancy_of(xchg_apply_insert_kernel<VV>, kThreadsP);                      \
-    DET_LAUNCH(xchg_apply_insert_kernel<VV>, grid, kThreadsP, 0, s, xv, tv, ageo, np, ticket, ep);             \
+    int occ = occupancy_of(xchg_apply_insert_kernel<VV>, kThreadsP);                                           \
+    if (piped && occ > 2) occ = occ - 1;   /* leave room for the sender kernel of the next chunk */            \
+    DET_LAUNCH(xchg_apply_insert_kernel<VV>, g->sm_count * occ, kThreadsP, 0, sa, xv, tv, ageo, np, ticket_a, ep); \
   } break;
       DET_XAPPLY(16) DET_XAPPLY(8) DET_XAPPLY(4) DET_XAPPLY(2)
       default: {
-        const int grid = g->sm_count * occupancy_of(xchg_apply_insert_kernel<1>, kThreadsP);
-        DET_LAUNCH(xchg_apply_insert_kernel<1>, grid, kThreadsP, 0, s, xv, tv, ageo, np, ticket, ep);
+        const int occ = occupancy_of(xchg_apply_insert_kernel<1>, kThreadsP);
+        DET_LAUNCH(xchg_apply_insert_kernel<1>, g->sm_count * occ, kThreadsP, 0, sa, xv, tv, ageo, np, ticket_a, ep);
       } break;
 #undef DET_XAPPLY
     }
   }
   CUDA_TRY(cudaGetLastError());
-  xchg_mark(g, 1, 4, s);
-  peer_snapshot(g, s);
-  xchg_mark(g, 1, 5, s);
+  if (piped) {
+    CUDA_TRY(cudaEventRecord(g->ev_route, sr));
+    CUDA_TRY(cudaEventRecord(g->ev_apply, sa));
+    CUDA_TRY(cudaStreamWaitEvent(s, g->ev_route, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s, g->ev_apply, 0));
+  }
+  xchg_mark(g, 1, 1, s);
   g->tev_pending[1] = g->timing;
+  peer_snapshot(g, s);
   return DET_OK;
 }
 
