@@ -885,7 +885,9 @@ det_status det_peer_xchg_attach(det_peer_group* g, const void* const* mailbox_pt
     CUDA_TRY(cudaEventCreateWithFlags(&g->ev_apply, cudaEventDisableTiming));
   }
   // chunks of one det_peer_xchg_insert call (every chunk is a collective epoch: the SAME value on every rank)
-  g->chunks = env_int("DET_XCHG_CHUNKS", 4);
+  // (measured at N=2, profiles/r02_xchg_chunks_n2.txt: 4 chunks 433 us per insert vs 374 us unchunked -- four extra
+  // rounds of flag waits cost more than the overlap returns, so the default is ONE chunk; the pipeline stays selectable)
+  g->chunks = env_int("DET_XCHG_CHUNKS", 1);
   if (g->chunks < 1) g->chunks = 1;
   if (g->chunks > 16) g->chunks = 16;
   g->ep_find = g->ep_ins = 0;
@@ -1033,7 +1035,7 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
 }
 
 // Sharded Insert (insert_or_assign) through the owners.  COLLECTIVE like det_peer_xchg_find.
-// The batch is cut into `chunks` pieces (DET_XCHG_CHUNKS, default 4, the same on every rank) and PIPELINED over two
+// The batch can be cut into `chunks` pieces (DET_XCHG_CHUNKS, default 1 = off, the same on every rank) and PIPELINED over two
 // internal streams: while the owner-side kernel applies the pairs of chunk c to the local shard (HBM-bound, no NVLink
 // traffic), the sender kernel already routes chunk c+1 to its owners (NVLink-bound, little SM time).  Every chunk is an
 // epoch of the flag protocol; epochs alternate between two sets of inbox segments, so a sender only ever waits for
