@@ -48,7 +48,9 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
 }
 
 __global__ void __launch_bounds__(kScanBlock)
-scan_block_sums_kernel(const unsigned* __restrict__ flags, size_t n, unsigned* __restrict__ block_sums) {
+scan_block_sums_kernel(const unsigned* __restrict__ flags, size_t n, unsigned* __restrict__ block_sums,
+                       const long long* __restrict__ n_dev = nullptr) {
+  if (n_dev) n = (size_t)*n_dev;   // item count produced on the device; the grid covers its bound
   __shared__ unsigned s_warp[33];
   const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
   unsigned total;
@@ -104,7 +106,9 @@ __global__ void unique_init_kernel(UniqueWs w) {
   if (blockIdx.x == 0 && threadIdx.x < 2) w.special[threadIdx.x] = 0xffffffffu;
 }
 
-__global__ void unique_insert_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n) {
+__global__ void unique_insert_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n,
+                                     const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long key = ids[i];
@@ -126,7 +130,8 @@ __global__ void unique_insert_kernel(UniqueWs w, const long long* __restrict__ i
   }
 }
 
-__global__ void unique_flag_kernel(UniqueWs w, size_t n) {
+__global__ void unique_flag_kernel(UniqueWs w, size_t n, const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned s = w.myslot[i];
@@ -136,7 +141,9 @@ __global__ void unique_flag_kernel(UniqueWs w, size_t n) {
 
 // first occurrences: rank = exclusive scan; write unique_out[rank], remember rank in the hash slot
 __global__ void __launch_bounds__(kScanBlock)
-unique_rank_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n, long long* __restrict__ unique_out) {
+unique_rank_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n, long long* __restrict__ unique_out,
+                   const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
   __shared__ unsigned s_warp[33];
   const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
   const unsigned f = i < n ? w.flags[i] : 0u;
@@ -150,7 +157,8 @@ unique_rank_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n, long
   }
 }
 
-__global__ void unique_idx_kernel(UniqueWs w, size_t n, int* __restrict__ idx_out) {
+__global__ void unique_idx_kernel(UniqueWs w, size_t n, int* __restrict__ idx_out, const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned s = w.myslot[i];
@@ -997,9 +1005,11 @@ static void fgeom(unsigned dim, bool vec4, unsigned min_lpr, unsigned* vpr, unsi
 //      the whole CTA stages a tile of rows in shared memory with every load in flight, then thread c adds column c
 //      in order), all other CTAs give each lane-group two short groups at a time, 4 row loads in flight per group.
 // Indices outside [0, n_groups) are dropped like unsorted_segment_sum drops negative ids.
-constexpr int kRadixBits = 8;
+constexpr int kRadixBits = 11;                     // 2 passes sort 22 bits: every batch below 4M groups (3 passes of 8 bits
+                                                   // cost 160 us of the c3 step, profiles/r02_c3_launch_list_before.csv)
 constexpr int kRadixBins = 1 << kRadixBits;
-constexpr int kRadixThreads = 256;                 // == kRadixBins: thread t owns bin t
+constexpr int kRadixThreads = 256;
+constexpr int kRadixBpt = kRadixBins / kRadixThreads;   // bins per thread: thread t owns bins [t * kRadixBpt, (t + 1) * kRadixBpt)
 constexpr int kRadixItems = 8;                     // items per thread
 constexpr int kRadixTile = kRadixThreads * kRadixItems;
 constexpr int kLongGroup = 64;                     // groups with more rows go to the CTA-cooperative path
@@ -1018,9 +1028,11 @@ __device__ __forceinline__ unsigned radix_key0(const int* __restrict__ idx, size
 // hist[bin * nblocks + block] = items of this block's tile whose digit is `bin`
 __global__ void __launch_bounds__(kRadixThreads)
 radix_hist_kernel(const int* __restrict__ idx, const unsigned* __restrict__ keys_in, size_t n, unsigned n_groups,
-                  int shift, unsigned* __restrict__ hist, size_t nblocks) {
+                  int shift, unsigned* __restrict__ hist, size_t nblocks, const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
   __shared__ unsigned s_h[kRadixBins];
-  s_h[threadIdx.x] = 0;
+#pragma unroll
+  for (int q = 0; q < kRadixBpt; ++q) s_h[threadIdx.x + q * kRadixThreads] = 0;
   __syncthreads();
   const size_t tile0 = (size_t)blockIdx.x * kRadixTile;
 #pragma unroll
@@ -1032,7 +1044,11 @@ radix_hist_kernel(const int* __restrict__ idx, const unsigned* __restrict__ keys
     }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+#pragma unroll
+  for (int q = 0; q < kRadixBpt; ++q) {
+    const unsigned bin = threadIdx.x + q * kRadixThreads;
+    hist[(size_t)bin * nblocks + blockIdx.x] = s_h[bin];
+  }
 }
 
 // one warp per bin: exclusive scan of the bin's per-block counts in place, bin total -> totals[bin]
@@ -1064,16 +1080,23 @@ __global__ void __launch_bounds__(kRadixThreads)
 radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ keys_in,
                      const unsigned* __restrict__ pos_in, size_t n, unsigned n_groups, int shift,
                      const unsigned* __restrict__ hist, size_t nblocks, const unsigned* __restrict__ totals,
-                     unsigned* __restrict__ keys_out, unsigned* __restrict__ pos_out) {
+                     unsigned* __restrict__ keys_out, unsigned* __restrict__ pos_out, const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
   constexpr int kWarps = kRadixThreads / 32;
-  __shared__ unsigned s_cnt[kWarps][kRadixBins];   // per warp: items of each digit (then: exclusive over warps)
+  // per warp: items of each digit (then: exclusive over warps); a warp's sub-tile has 256 items, 16 bits are enough
+  __shared__ unsigned short s_cnt[kWarps][kRadixBins];
   __shared__ unsigned s_base[kRadixBins];          // global start of the (bin, block) run
   __shared__ unsigned s_wsum[kWarps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int q = threadIdx.x; q < kWarps * kRadixBins; q += kRadixThreads) (&s_cnt[0][0])[q] = 0;
-  // exclusive scan of the bin totals over the 256 bins (thread t = bin t)
-  const unsigned tot = totals[threadIdx.x];
-  unsigned x = tot;
+  // exclusive scan of the bin totals over all bins: thread t owns kRadixBpt consecutive bins
+  unsigned tot[kRadixBpt], mine = 0;
+#pragma unroll
+  for (int q = 0; q < kRadixBpt; ++q) {
+    tot[q] = totals[threadIdx.x * kRadixBpt + q];
+    mine += tot[q];
+  }
+  unsigned x = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned y = __shfl_up_sync(kFull, x, o);
@@ -1083,7 +1106,15 @@ radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ k
   __syncthreads();
   unsigned before = 0;
   for (int ww = 0; ww < w; ++ww) before += s_wsum[ww];
-  s_base[threadIdx.x] = before + x - tot + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  {
+    unsigned run = before + x - mine;              // items in the bins before this thread's first bin
+#pragma unroll
+    for (int q = 0; q < kRadixBpt; ++q) {
+      const unsigned bin = threadIdx.x * kRadixBpt + q;
+      s_base[bin] = run + hist[(size_t)bin * nblocks + blockIdx.x];
+      run += tot[q];
+    }
+  }
   // pass A: the warp walks its 256 consecutive items 32 at a time; rank inside the warp's sub-tile
   const size_t sub0 = (size_t)blockIdx.x * kRadixTile + (size_t)w * (kRadixTile / kWarps);
   unsigned key[kRadixItems], rank[kRadixItems];
@@ -1094,20 +1125,24 @@ radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ k
     key[it] = valid ? (keys_in ? keys_in[i] : radix_key0(idx, i, n_groups)) : 0u;
     const int d = valid ? (int)((key[it] >> shift) & (kRadixBins - 1)) : -1;
     const unsigned peers = __match_any_sync(kFull, d);
-    const unsigned old = valid ? s_cnt[w][d] : 0u;
+    const unsigned old = valid ? (unsigned)s_cnt[w][d] : 0u;
     rank[it] = old + (unsigned)__popc(peers & ((1u << lane) - 1u));
     __syncwarp();
-    if (valid && (peers & ((1u << lane) - 1u)) == 0) s_cnt[w][d] = old + (unsigned)__popc(peers);
+    if (valid && (peers & ((1u << lane) - 1u)) == 0) s_cnt[w][d] = (unsigned short)(old + (unsigned)__popc(peers));
     __syncwarp();
   }
   __syncthreads();
-  {  // exclusive prefix over the warps, per digit (thread t = digit t)
-    unsigned run = 0;
+  {  // exclusive prefix over the warps, per digit (thread t owns digits t, t + 256, ...)
 #pragma unroll
-    for (int ww = 0; ww < kWarps; ++ww) {
-      const unsigned c = s_cnt[ww][threadIdx.x];
-      s_cnt[ww][threadIdx.x] = run;
-      run += c;
+    for (int q = 0; q < kRadixBpt; ++q) {
+      const unsigned dgt = threadIdx.x + q * kRadixThreads;
+      unsigned run = 0;
+#pragma unroll
+      for (int ww = 0; ww < kWarps; ++ww) {
+        const unsigned c = s_cnt[ww][dgt];
+        s_cnt[ww][dgt] = (unsigned short)run;
+        run += c;
+      }
     }
   }
   __syncthreads();
@@ -1126,8 +1161,10 @@ radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ k
 // starts[g] = first sorted position whose key is >= g (g = 0..n_groups); keys are sorted, "dropped" rows carry n_groups
 // `ngd` (nullable): the group count lives on the device (det_apply_*_dup: n_unique of det_unique, never read by the host)
 __global__ void group_starts_kernel(const unsigned* __restrict__ keys, size_t n, unsigned n_groups,
-                                    unsigned* __restrict__ starts, const long long* __restrict__ ngd) {
+                                    unsigned* __restrict__ starts, const long long* __restrict__ ngd,
+                                    const long long* __restrict__ n_dev) {
   if (ngd) n_groups = (unsigned)*ngd;
+  if (n_dev) n = (size_t)*n_dev;
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j > n) return;
   const long long cur = j < n ? (long long)keys[j] : (long long)n_groups;
@@ -1383,9 +1420,9 @@ extern "C" {
 
 size_t det_unique_workspace_bytes(size_t n) { return unique_ws_layout(n ? n : 1, nullptr, nullptr); }
 
-det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t* idx_out, int64_t* n_unique_dev,
-                      void* workspace, size_t workspace_bytes, det_stream_t stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+// n bounds the id count (sizes, grids); with `n_dev` the real count is read on the device by every kernel
+static det_status unique_run(const int64_t* ids, size_t n, int64_t* unique_out, int32_t* idx_out, int64_t* n_unique_dev,
+                             void* workspace, size_t workspace_bytes, const long long* n_dev, cudaStream_t s) {
   if (!n_unique_dev) return fail(DET_INVALID_ARGUMENT, "det_unique: null n_unique");
   if (n == 0) {
     CUDA_TRY(cudaMemsetAsync(n_unique_dev, 0, sizeof(int64_t), s));
@@ -1399,14 +1436,19 @@ det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t
   const size_t nblocks = (n + kScanBlock - 1) / kScanBlock;
   const int g256 = (int)((n + 255) / 256);
   DET_LAUNCH(unique_init_kernel, (int)((w.hcap + 1023) / 1024 < 4096 ? (w.hcap + 1023) / 1024 : 4096), 1024, 0, s, w);
-  DET_LAUNCH(unique_insert_kernel, g256, 256, 0, s, w, (const long long*)ids, n);
-  DET_LAUNCH(unique_flag_kernel, g256, 256, 0, s, w, n);
-  DET_LAUNCH(scan_block_sums_kernel, (int)nblocks, kScanBlock, 0, s, w.flags, n, w.block_sums);
+  DET_LAUNCH(unique_insert_kernel, g256, 256, 0, s, w, (const long long*)ids, n, n_dev);
+  DET_LAUNCH(unique_flag_kernel, g256, 256, 0, s, w, n, n_dev);
+  DET_LAUNCH(scan_block_sums_kernel, (int)nblocks, kScanBlock, 0, s, w.flags, n, w.block_sums, n_dev);
   DET_LAUNCH(scan_sums_kernel, 1, kScanBlock, 0, s, w.block_sums, nblocks, (long long*)n_unique_dev);
-  DET_LAUNCH(unique_rank_kernel, (int)nblocks, kScanBlock, 0, s, w, (const long long*)ids, n, (long long*)unique_out);
-  DET_LAUNCH(unique_idx_kernel, g256, 256, 0, s, w, n, idx_out);
+  DET_LAUNCH(unique_rank_kernel, (int)nblocks, kScanBlock, 0, s, w, (const long long*)ids, n, (long long*)unique_out, n_dev);
+  DET_LAUNCH(unique_idx_kernel, g256, 256, 0, s, w, n, idx_out, n_dev);
   CUDA_TRY(cudaGetLastError());
   return DET_OK;
+}
+
+det_status det_unique(const int64_t* ids, size_t n, int64_t* unique_out, int32_t* idx_out, int64_t* n_unique_dev,
+                      void* workspace, size_t workspace_bytes, det_stream_t stream) {
+  return unique_run(ids, n, unique_out, idx_out, n_unique_dev, workspace, workspace_bytes, nullptr, (cudaStream_t)stream);
 }
 
 static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int32_t* segment_ids, const float* weights,
@@ -1760,7 +1802,8 @@ size_t det_segment_reduce_workspace_bytes(size_t n, size_t n_groups) {
 
 // n_groups bounds the group count (sizes, pass count, grids); with `ngd` the real count is read on the device
 static det_status seg_reduce_run(const float* rows, const int32_t* idx, size_t n, size_t n_groups, size_t dim, float* out,
-                                 void* workspace, size_t workspace_bytes, const long long* ngd, cudaStream_t s) {
+                                 void* workspace, size_t workspace_bytes, const long long* ngd, cudaStream_t s,
+                                 const long long* n_dev = nullptr) {
   if (n_groups == 0 || dim == 0) return DET_OK;
   if (!out) return fail(DET_INVALID_ARGUMENT, "det_segment_reduce: null out");
   if (n >= 0x7fffffffull || n_groups >= 0x7fffffffull || dim >= 0x7fffffffull)
@@ -1783,16 +1826,16 @@ static det_status seg_reduce_run(const float* rows, const int32_t* idx, size_t n
   unsigned *kout = w.keys_a, *pout = w.pos_a;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = pass * kRadixBits;
-    DET_LAUNCH(radix_hist_kernel, (int)nblocks, kRadixThreads, 0, s, idx, kin, n, ng, shift, w.hist, nblocks);
+    DET_LAUNCH(radix_hist_kernel, (int)nblocks, kRadixThreads, 0, s, idx, kin, n, ng, shift, w.hist, nblocks, n_dev);
     DET_LAUNCH(radix_binscan_kernel, kRadixBins * 32 / kRadixThreads, kRadixThreads, 0, s, w.hist, nblocks, w.totals);
     DET_LAUNCH(radix_scatter_kernel, (int)nblocks, kRadixThreads, 0, s, idx, kin, pin, n, ng, shift, w.hist, nblocks, w.totals,
-               kout, pout);
+               kout, pout, n_dev);
     kin = kout;
     pin = pout;
     kout = (kout == w.keys_a) ? w.keys_b : w.keys_a;
     pout = (pout == w.pos_a) ? w.pos_b : w.pos_a;
   }
-  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts, ngd);
+  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts, ngd, n_dev);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1872,7 +1915,7 @@ size_t det_apply_dup_workspace_bytes(size_t n, size_t dim) { return dup_layout(n
 
 static det_status apply_dup(det_table* t, const int64_t* ids, const float* grads, size_t n, OptHyper h,
                             const float* init_param, int opt, void* workspace, size_t workspace_bytes,
-                            int64_t* n_unique_dev_out, cudaStream_t s) {
+                            int64_t* n_unique_dev_out, cudaStream_t s, const long long* n_items_dev = nullptr) {
   if (!t) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: null table");
   if (n == 0) return DET_OK;
   if (!ids || !grads || !init_param || !workspace) return fail(DET_INVALID_ARGUMENT, "det_apply_dup: null argument");
@@ -1883,9 +1926,10 @@ static det_status apply_dup(det_table* t, const int64_t* ids, const float* grads
   det::DevGuard _dg(t->cfg.device);
   DupWs w;
   dup_layout(n, dim, (unsigned char*)workspace, &w);
-  det_status st = det_unique(ids, n, (int64_t*)w.uniq, w.idx, (int64_t*)w.cnt, w.uws, w.uws_bytes, (det_stream_t)s);
+  // n_items_dev: the id count itself lives on the device (owner side of the sharded backward); n is its bound
+  det_status st = unique_run(ids, n, (int64_t*)w.uniq, w.idx, (int64_t*)w.cnt, w.uws, w.uws_bytes, n_items_dev, s);
   if (st != DET_OK) return st;
-  st = seg_reduce_run(grads, w.idx, n, n, dim, w.gsum, w.sws, w.sws_bytes, w.cnt, s);
+  st = seg_reduce_run(grads, w.idx, n, n, dim, w.gsum, w.sws, w.sws_bytes, w.cnt, s, n_items_dev);
   if (st != DET_OK) return st;
   st = apply_common(t, (const int64_t*)w.uniq, w.gsum, n, h, init_param, 0, opt, s, w.cnt);
   if (st != DET_OK) return st;
@@ -1911,3 +1955,18 @@ det_status det_apply_adam_dup(det_table* t, const int64_t* ids, const float* gra
 }
 
 }  // extern "C"
+
+namespace det {
+// owner side of the sharded backward (sharded.cu): ids / grads were compacted out of the inbox segments by a kernel,
+// their count lives in *n_items_dev; opt 0 = Adagrad (lr, eps, init_slot), 1 = Adam (lr = alpha, eps, beta1, beta2)
+det_status apply_dup_on_device_count(det_table* t, const int64_t* ids, const float* grads, size_t n_bound,
+                                     const long long* n_items_dev, int opt, float lr, float eps, float beta1, float beta2,
+                                     float init_slot, const float* init_param, void* workspace, size_t workspace_bytes,
+                                     cudaStream_t s) {
+  OptHyper h;
+  h.lr = lr; h.eps = eps; h.beta1 = beta1; h.beta2 = beta2; h.init_slot = init_slot;
+  if (t && opt == 0) t->slot_init[1] = init_slot;
+  return apply_dup(t, ids, grads, n_bound, h, init_param, opt, workspace, workspace_bytes, nullptr, s, n_items_dev);
+}
+}  // namespace det
+

@@ -500,6 +500,48 @@ xchg_apply_insert_kernel(XchgView xv, TableView t, RowGeom g, int n_slot_planes,
     st_release_sys(xchg_flag(xv, threadIdx.x, kFlagAck, xv.rank), epoch << 32);
 }
 
+
+// owner side of the sharded BACKWARD: the (key, gradient row) pairs every source routed here are concatenated in
+// source-rank order into contiguous buffers and their number is left ON THE DEVICE (*n_out) -- the input of
+// det::apply_dup_on_device_count (unique -> position-order sum -> fused optimizer step).  The last CTA publishes the
+// ack: the segments are free for the sources' next epoch.
+template <int VEC>
+__global__ void __launch_bounds__(kThreadsP)
+xchg_compact_kernel(XchgView xv, long long* __restrict__ keys_out, unsigned char* __restrict__ rows_out, RowGeom g,
+                    long long* __restrict__ n_out, unsigned* ticket, unsigned long long epoch) {
+  __shared__ unsigned long long s_pref[kMaxPeers + 1];
+  const size_t par = (size_t)(epoch & 1ull);
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int s = 0; s < xv.world; ++s) {
+      s_pref[s] = acc;
+      acc += *((volatile unsigned long long*)xchg_flag(xv, xv.rank, par ? kFlagIns1 : kFlagIns, s)) & 0xffffffffull;
+    }
+    for (int s = xv.world; s <= kMaxPeers; ++s) s_pref[s] = acc;
+    if (blockIdx.x == 0) *n_out = (long long)acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = s_pref[kMaxPeers];
+  const unsigned long long n_tiles = (total + kThreadsP - 1) / kThreadsP;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long f = tile * kThreadsP + threadIdx.x;
+    const bool valid = f < total;
+    unsigned long long i = 0;
+    const int s = valid ? xchg_locate(s_pref, xv.world, f, i) : 0;
+    const unsigned char* src = nullptr;
+    unsigned char* dst = nullptr;
+    if (valid) {
+      keys_out[f] = ld_cg_ll(reinterpret_cast<const long long*>(xv.base[xv.rank] + xv.off_ins_keys + (par * (size_t)xv.world + (size_t)s) * xv.seg_ins_keys) + i);
+      src = xv.base[xv.rank] + xv.off_ins_rows + (par * (size_t)xv.world + (size_t)s) * xv.seg_ins_rows + (size_t)i * g.row_bytes;
+      dst = rows_out + (size_t)f * g.row_bytes;
+    }
+    warp_move_rows<VEC>(g, src, dst, lane);
+  }
+  if (xchg_last_cta(ticket) && (int)threadIdx.x < xv.world)
+    st_release_sys(xchg_flag(xv, threadIdx.x, kFlagAck, xv.rank), epoch << 32);
+}
+
 }  // namespace det
 
 using namespace det;
@@ -1127,6 +1169,110 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
   g->tev_pending[1] = g->timing;
   peer_snapshot(g, s);
   return DET_OK;
+}
+
+// Sharded sparse optimizer step (the backward of the sharded lookup; reference: the gradient of
+// HvdVariable.__alltoall_embedding_lookup__ + DynamicEmbeddingOptimizer, python/ops/shadow_embedding_ops.py:397-447,
+// python/ops/dynamic_embedding_optimizer.py:150-204 -- half-sync: sparse rows are never all-reduced, :580-595).
+// COLLECTIVE.  Every rank routes its (unique id, row gradient) pairs to the owners like det_peer_xchg_insert; the owner
+// compacts what arrived, sums the gradients several ranks sent for one id (position order: source rank, then the
+// sender's order) and runs the fused find-or-insert optimizer step on its shard.  Every count stays on the device:
+// no cudaStreamSynchronize, no host round trip for split sizes (the reference negotiates them on the host).
+// workspace: det_peer_xchg_apply_workspace_bytes(g) bytes of device memory, 256 B aligned.
+static size_t xchg_apply_layout(const det_peer_group* g, size_t* off_rows, size_t* off_n, size_t* off_dup, size_t* dup_bytes) {
+  const size_t bound = (size_t)g->pv.world * g->xv.cap;
+  const size_t dim = g->row_bytes / 4;
+  size_t off = 0;
+  off += al256(bound * 8);
+  if (off_rows) *off_rows = off;
+  off += al256(bound * g->row_bytes);
+  if (off_n) *off_n = off;
+  off += 256;
+  if (off_dup) *off_dup = off;
+  const size_t db = det_apply_dup_workspace_bytes(bound, dim);
+  if (dup_bytes) *dup_bytes = db;
+  return off + db;
+}
+
+size_t det_peer_xchg_apply_workspace_bytes(det_peer_group* g) {
+  if (!g || !g->xchg) return 0;
+  return xchg_apply_layout(g, nullptr, nullptr, nullptr, nullptr);
+}
+
+static det_status xchg_apply(det_peer_group* g, const int64_t* keys, const float* grads, size_t n, int opt, float lr,
+                             float eps, float beta1, float beta2, float init_slot, const float* init_param,
+                             void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (!g || !g->xchg) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_apply: no exchange mailbox attached");
+  if (g->local->cfg.value_dtype != DET_FLOAT32) return fail(DET_UNIMPLEMENTED, "det_peer_xchg_apply: float32 tables only");
+  if (n > g->xv.cap) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_apply: batch larger than the mailbox (max_items)");
+  if (!init_param || !workspace || (n && (!keys || !grads))) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_apply: null argument");
+  if (((uintptr_t)workspace & 255u) != 0) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_apply: workspace must be 256 B aligned");
+  size_t off_rows, off_n, off_dup, dup_bytes;
+  if (workspace_bytes < xchg_apply_layout(g, &off_rows, &off_n, &off_dup, &dup_bytes))
+    return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_apply: workspace too small");
+  det::DevGuard _dg(g->device);
+  det_status rs = peer_room(g, "det_peer_xchg_apply");
+  if (rs != DET_OK) return rs;
+  const XchgView& xv = g->xv;
+  const unsigned long long ep = ++g->ep_ins;
+  unsigned* ticket_r = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
+  unsigned* ticket_a = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers + 1);
+  DevState* st = g->local->view.st;
+  const int vec = pick_vec(g->row_bytes, grads, nullptr, nullptr);
+  const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
+  if (ep > 2) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + kFlagAck * 64);
+    DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, s, flags, xv.world, ep - 2, st, kXchgTimeoutCycles);
+  }
+  {
+    const int grid = grid_for(n, kThreadsP, g->sm_count, 4);
+    const long long* k = (const long long*)keys;
+    const unsigned char* r = (const unsigned char*)grads;
+    switch (vec) {
+      case 16: DET_LAUNCH((xchg_route_kernel<true, 16>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket_r, ep, st); break;
+      case 8: DET_LAUNCH((xchg_route_kernel<true, 8>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket_r, ep, st); break;
+      default: DET_LAUNCH((xchg_route_kernel<true, 4>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket_r, ep, st); break;
+    }
+  }
+  {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + ((ep & 1ull) ? kFlagIns1 : kFlagIns) * 64);
+    DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, s, flags, xv.world, ep, st, kXchgTimeoutCycles);
+  }
+  unsigned char* ws = (unsigned char*)workspace;
+  long long* ckeys = (long long*)ws;
+  unsigned char* crows = ws + off_rows;
+  long long* n_dev = (long long*)(ws + off_n);
+  {
+    const int cvec = pick_vec(g->row_bytes, nullptr, nullptr, nullptr);
+    const RowGeom cgeo = make_geom((unsigned)g->row_bytes, cvec);
+    const int grid = g->sm_count * 4;
+    switch (cvec) {
+      case 16: DET_LAUNCH(xchg_compact_kernel<16>, grid, kThreadsP, 0, s, xv, ckeys, crows, cgeo, n_dev, ticket_a, ep); break;
+      case 8: DET_LAUNCH(xchg_compact_kernel<8>, grid, kThreadsP, 0, s, xv, ckeys, crows, cgeo, n_dev, ticket_a, ep); break;
+      default: DET_LAUNCH(xchg_compact_kernel<4>, grid, kThreadsP, 0, s, xv, ckeys, crows, cgeo, n_dev, ticket_a, ep); break;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  const size_t bound = (size_t)g->pv.world * g->xv.cap;
+  det_status rc = det::apply_dup_on_device_count(g->local, (const int64_t*)ckeys, (const float*)crows, bound, n_dev, opt, lr, eps,
+                                                 beta1, beta2, init_slot, init_param, ws + off_dup, dup_bytes, s);
+  if (rc != DET_OK) return rc;
+  peer_snapshot(g, s);
+  return DET_OK;
+}
+
+det_status det_peer_xchg_apply_adagrad(det_peer_group* g, const int64_t* keys, const float* grads, size_t n, float lr,
+                                       float epsilon, const float* init_param, float init_accum, void* workspace,
+                                       size_t workspace_bytes, det_stream_t stream) {
+  return xchg_apply(g, keys, grads, n, 0, lr, epsilon, 0.f, 0.f, init_accum, init_param, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+
+det_status det_peer_xchg_apply_adam(det_peer_group* g, const int64_t* keys, const float* grads, size_t n, float alpha,
+                                    float beta1, float beta2, float epsilon, const float* init_param, void* workspace,
+                                    size_t workspace_bytes, det_stream_t stream) {
+  return xchg_apply(g, keys, grads, n, 1, alpha, epsilon, beta1, beta2, 0.f, init_param, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,

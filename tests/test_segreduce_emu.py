@@ -39,7 +39,8 @@ def rows_of(rng, n, dim):
 
 
 @pytest.mark.parametrize("n,n_groups,dim", [(1, 1, 4), (37, 5, 64), (3000, 200, 64), (3000, 700, 16), (5000, 70000, 8),
-                                            (2500, 300, 128), (4099, 257, 12)])
+                                            (2500, 300, 128), (4099, 257, 12), (3000, 2047, 4), (3000, 2048, 4),
+                                            (2000, (1 << 22) + 5, 4)])   # 1 / 2 / 3 passes of 11-bit digits
 def test_random_groups_bit_exact(n, n_groups, dim):
   rng = np.random.default_rng(n * 31 + dim)
   rows = rows_of(rng, n, dim)
