@@ -54,9 +54,10 @@ def parse_args():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--e2e-steps", type=int, default=10)
-  ap.add_argument("--exchange", default="push", choices=["push", "peer", "nccl"],
-                  help="N>1: owner-side exchange with posted NVLink stores only (default, det_peer_xchg_*), one-sided "
-                       "remote-probe kernels (det_peer_find/insert), or NCCL all-to-all")
+  ap.add_argument("--exchange", default="hybrid", choices=["hybrid", "push", "peer", "nccl"],
+                  help="N>1: hybrid (default) = lookups through the owners with posted NVLink stores only (det_peer_xchg_find) + "
+                       "one-sided inserts (det_peer_insert); push = owner-side exchange both ways (det_peer_xchg_*); peer = the "
+                       "one-sided remote-probe kernels both ways (det_peer_find/insert); nccl = NCCL all-to-all")
   ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                   help="c2 = headline lookup+insert (BASELINE configs[1]); c3 = fused embedding_lookup_sparse + Adagrad (configs[2]); "
                        "c4 = the c2 step on configs[3] (torchrun --gpus 8: 1B keys = 125M resident per GPU, dim 128); "
@@ -503,12 +504,13 @@ def gpu_arm(args):
   sharded, exchange = None, "none"
   if world > 1:
     exchange = args.exchange
-    if exchange in ("push", "peer"):
+    if exchange in ("hybrid", "push", "peer"):
       try:
         # the shard lives in a symmetric-memory region that every rank maps (CUDA VMM, 2 MB pages)
         sharded = de.PeerShardedVariable.create(dim, 2 * resident, initializer=0.0, name="bench_table")
-        if exchange == "push":
-          sharded.attach_exchange(B)   # mailbox: request / insert segments per source rank + the output ring
+        if exchange in ("push", "hybrid"):
+          # mailbox: request / insert segments per source rank + the output ring
+          sharded.attach_exchange(B, insert="push" if exchange == "push" else "pull")
       except Exception as ex:  # no symmetric memory in this sandbox: NCCL exchange instead, and say so
         print("symmetric-memory peer group failed (%r): falling back to NCCL all-to-all" % (ex,), file=sys.stderr)
         exchange = "nccl"
@@ -521,8 +523,8 @@ def gpu_arm(args):
                                                                                max_capacity=2 * resident)))
   if world > 1 and exchange == "nccl":
     sharded = de.ShardedVariable(var)
-  is_peer = exchange == "peer"
-  is_push = exchange == "push"
+  is_peer = exchange in ("peer", "hybrid")     # one-sided remote writes: reads and writes need phase barriers
+  is_push = exchange in ("push", "hybrid")     # lookups through the owners, rows land in the output ring
   table = var.tables[0]
   # ---- prefill this rank's shard: all ranks r of the vocabulary with owner(key(r)) == rank; row = f(key, generation 0)
   chunk = min(1 << 20, B)
@@ -713,7 +715,7 @@ def gpu_arm(args):
            "h2d_bytes_per_step": int(B * (8 + 8 + dim * 4) + dim * 4), "d2h_bytes_per_step": int(B * dim * 4),
            "steps": n_e2e,
            "api": "CuckooHashTable.lookup_host + insert_host (det_find_host / det_insert_host), pinned host buffers"
-                  if sharded is None else ("PeerShardedVariable" if (is_peer or is_push) else "ShardedVariable") + ".lookup/upsert with pinned H2D/D2H copies"}
+                  if sharded is None else ("PeerShardedVariable" if exchange != "nccl" else "ShardedVariable") + ".lookup/upsert with pinned H2D/D2H copies"}
     if sharded is None:
       # software-pipelined flavour of the SAME per-step work: the lookup of batch i+1 (D2H-heavy) is issued
       # together with the write-back of batch i (H2D-heavy) -- input prefetch, as tf.data does for the reference
@@ -745,10 +747,11 @@ def gpu_arm(args):
   achieved = algo_bytes / (find_ms_1 * 1e-3) / 1e9
   honest_bytes = B * (8 + 64 + 2 * dim * 4)  # key in + one 64 B bucket + row read + row written out
   kernels = {"none": "det::find_kernel_tma<16>",
+             "hybrid": "det::xchg_route_kernel<false> + xchg_serve_find_kernel<16> (+ 2 flag waits, + peer barrier)",
              "push": "det::xchg_route_kernel<false> + xchg_serve_find_kernel<16> (+ 2 flag waits)",
              "peer": "det::peer_find_kernel<16> (+peer barrier)",
              "nccl": "partition+all_to_all+find_kernel+all_to_all+scatter"}
-  launches = {"none": 2, "push": 8, "peer": 4, "nccl": 10}
+  launches = {"none": 2, "hybrid": 7, "push": 8, "peer": 4, "nccl": 10}
   traffic, traffic_src = (committed_traffic("find_kernel_tma<16>") if (world == 1 and B == (1 << 20) and dim == 64)
                           else (None, "only captured for the N=1 headline workload"))
   line = {
@@ -765,6 +768,9 @@ def gpu_arm(args):
                 "%.0f MB in of a %.1f GB table (no L2 flush; the Zipf head is hot by design)" %
                 (n_batches, B * dim * 4 / 1e6, B * dim * 4 / 1e6, B * dim * 4 / 1e6, table.stats()["hbm_bytes"] / 1e9),
           "parallelism": ("key-hash sharded x%d, %s" % (world, {
+              "hybrid": "lookups: ids pushed to the owner's mailbox, local probe, rows pushed back with posted NVLink stores "
+                        "(det_peer_xchg_find); inserts: one-sided kernel, remote probe + posted row store (det_peer_insert); flag "
+                        "barrier between the read and the write phase; no collective",
               "push": "owner-side exchange: ids pushed to the owner's mailbox, local probe, rows pushed back with posted "
                       "NVLink stores, flag words instead of barriers (det_peer_xchg_find/insert), no collective",
               "peer": "one-sided NVLink peer-memory kernels with remote probes (det_peer_find/insert), no collective",
@@ -795,7 +801,8 @@ def gpu_arm(args):
     # insert.  Peak = measured peer copy, one direction (profiles/r01_peer_microbench_2gpu.jsonl 735 GB/s, 770 GB/s on
     # the 8-GPU box; nominal 900 GB/s).
     f = (world - 1) / world
-    nv_bytes = f * B * ((12 + dim * 4 + 8 + dim * 4) if is_push else (64 + dim * 4 + dim * 4))
+    nv_bytes = f * B * {"push": 12 + dim * 4 + 8 + dim * 4, "hybrid": 12 + dim * 4 + dim * 4, "peer": 64 + dim * 4 + dim * 4,
+                        "nccl": 8 + dim * 4 + 8 + dim * 4}[exchange]
     nv_peak = float(os.environ.get("DET_NVLINK_PEAK_GBS", "770"))
     line["roofline_nvlink"] = {"bound": "nvlink", "kernel": "whole step (%s)" % exchange,
                                "achieved": nv_bytes / (ms_per_step * 1e-3) / 1e9, "peak": nv_peak, "unit": "GB/s",
@@ -1021,7 +1028,11 @@ def c5_arm(args):
   dist.barrier()
   cdf = zipf_cdf_torch(vocab, dev)
   ids_per_rank = gbatch // world * nfeat
-  sv.attach_inbox(ids_per_rank)
+  owner_side = args.exchange in ("push", "hybrid")
+  if owner_side:   # forward and backward through the owners: no inbox round trip, every count stays on the device
+    sv.attach_exchange(ids_per_rank)
+  else:            # round-1 path: remote-probe lookup, inbox + host-side split counts
+    sv.attach_inbox(ids_per_rank)
   nb = max(1, min(args.steps + args.warmup, 16))
   batches = [rank_to_key_torch(torch.searchsorted(cdf, torch.rand(ids_per_rank, dtype=torch.float64, device=dev, generator=gen))
                                .clamp_(max=vocab - 1)) for _ in range(nb)]
@@ -1032,7 +1043,7 @@ def c5_arm(args):
   def step(i):
     ids = batches[i % nb]
     uniq, idx = de.unique(ids)
-    rows = sv.lookup(uniq)                          # forward: one-sided sharded lookup of the unique ids
+    rows = sv.lookup(uniq)                          # forward: sharded lookup of the unique ids
     sv.phase_barrier()
     emb = rows[idx.long()]                          # [ids, dim] activations handed to the dense tower
     dist.all_reduce(dense)                          # half-sync: only the dense tower is all-reduced
@@ -1062,8 +1073,9 @@ def c5_arm(args):
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()),
                       "higher_is_better": True, "scaling": "strong", "data": "synthetic",
                       "config": {"workload": "26 features x global batch %d, dim %d, %d resident rows/GPU (2B-row key space), "
-                                             "Zipf(1.05); unique -> det_peer_find -> 50 MB dense all-reduce -> det_peer_route -> "
-                                             "combine -> det_apply_adagrad" % (gbatch, dim, resident),
+                                             "Zipf(1.05); unique -> sharded lookup -> 50 MB dense all-reduce -> sharded optimizer step (%s)" %
+                                             (gbatch, dim, resident, "det_peer_xchg_find + det_peer_xchg_apply_adagrad: owner-side, counts on the device"
+                                              if owner_side else "det_peer_find + det_peer_route / inbox / host counts / det_apply_adagrad"),
                                  "grad_reduce": args.grad_reduce, "ids_per_rank": ids_per_rank, "unique_per_rank": int(de.unique(batches[0])[0].numel())}}))
   dist.destroy_process_group()
 

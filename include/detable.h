@@ -373,6 +373,22 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
 det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
                                 det_stream_t stream);
 
+/* Sharded sparse optimizer step through the owners (ABI >= 7): the backward of the sharded lookup -- the gradient of
+ * HvdVariable.__alltoall_embedding_lookup__ followed by the optimizer patch (python/ops/shadow_embedding_ops.py:397-447,
+ * python/ops/dynamic_embedding_optimizer.py:150-204; half-sync: sparse rows are never all-reduced, :580-595).
+ * COLLECTIVE like det_peer_xchg_insert.  Every rank routes its (unique id, row gradient) pairs to the owners; the owner
+ * compacts what arrived, sums the gradients several ranks sent for one id (position order: source rank, then the
+ * sender's order) and runs the fused find-or-insert optimizer step on its shard (det_apply_*_dup on the device-side
+ * count).  No cudaStreamSynchronize and no host round trip for split sizes (the reference negotiates them on the host,
+ * shadow_embedding_ops.py:414-421).  workspace: det_peer_xchg_apply_workspace_bytes(g) bytes, 256 B aligned. */
+size_t det_peer_xchg_apply_workspace_bytes(det_peer_group* g);
+det_status det_peer_xchg_apply_adagrad(det_peer_group* g, const int64_t* keys, const float* grads, size_t n, float lr,
+                                       float epsilon, const float* init_param, float init_accum, void* workspace,
+                                       size_t workspace_bytes, det_stream_t stream);
+det_status det_peer_xchg_apply_adam(det_peer_group* g, const int64_t* keys, const float* grads, size_t n, float alpha,
+                                    float beta1, float beta2, float epsilon, const float* init_param, void* workspace,
+                                    size_t workspace_bytes, det_stream_t stream);
+
 /* ---- file-system format of SaveToFileSystem / LoadFromFileSystem
  * (cuckoo_hashtable_op.cc:310-504): raw little-endian `<prefix>-keys` (int64[n]) and
  * `<prefix>-values` (V[n*dim]).  HOST paths; synchronous. ---- */

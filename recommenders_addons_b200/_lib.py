@@ -10,7 +10,7 @@ _sz = ctypes.c_size_t
 _i = ctypes.c_int
 
 DET_OK = 0
-ABI_VERSION = 6  # det_abi_version() of the library these mirrors describe (checked at load)
+ABI_VERSION = 7  # det_abi_version() of the library these mirrors describe (checked at load)
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 # HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
@@ -96,6 +96,10 @@ SIGNATURES = {
     "det_peer_xchg_attach": (_i, [_vp, ctypes.POINTER(_vp), _sz, _sz]),
     "det_peer_xchg_find": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp, ctypes.POINTER(_vp), _vp]),
     "det_peer_xchg_insert": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "det_peer_xchg_apply_workspace_bytes": (_sz, [_vp]),
+    "det_peer_xchg_apply_adagrad": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, _vp, ctypes.c_float, _vp, _sz, _vp]),
+    "det_peer_xchg_apply_adam": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp,
+                                      _vp, _sz, _vp]),
     "det_save": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
     "det_load": (_i, [_vp, ctypes.c_char_p, _sz, _i]),
     "det_import_plane": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),

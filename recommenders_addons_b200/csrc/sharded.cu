@@ -386,35 +386,42 @@ __device__ __forceinline__ int xchg_locate(const unsigned long long* pref, int w
   return s;
 }
 
-// owner side of Find: probe the LOCAL table for every requested key and push its row into the requester's output ring
+// owner side of Find: probe the LOCAL table for every requested key and push its row into the requester's output ring.
+// Tiles are dealt ROUND-ROBIN over the sources, starting at a different source on every rank: at any moment the CTAs
+// of one owner write to all requesters and the owners do not gang up on one requester.  (Walking the sources one after
+// the other made every owner serve source 0 first, then source 1, ...: 7 senders into ONE inbound link while the other
+// seven idled -- measured at N=8: serve 400-760 us instead of ~330, profiles/r02_xchg_phase_timing_n8_before_interleave.txt.)
 template <int VEC>
 __global__ void __launch_bounds__(kThreadsP)
 xchg_serve_find_kernel(XchgView xv, TableView t, const unsigned char* __restrict__ defaults, int full_default,
                        int want_exists, int parity, RowGeom g, unsigned* ticket, unsigned long long epoch) {
-  __shared__ unsigned long long s_pref[kMaxPeers + 1];
+  __shared__ unsigned s_cnt[kMaxPeers];
+  __shared__ unsigned s_max_tiles;
   if (threadIdx.x == 0) {
-    unsigned long long acc = 0;
+    unsigned mx = 0;
     for (int s = 0; s < xv.world; ++s) {
-      s_pref[s] = acc;
-      acc += *((volatile unsigned long long*)xchg_flag(xv, xv.rank, kFlagReq, s)) & 0xffffffffull;
+      const unsigned c = (unsigned)(*((volatile unsigned long long*)xchg_flag(xv, xv.rank, kFlagReq, s)) & 0xffffffffull);
+      s_cnt[s] = c;
+      const unsigned tl = (c + kThreadsP - 1) / kThreadsP;
+      mx = tl > mx ? tl : mx;
     }
-    for (int s = xv.world; s <= kMaxPeers; ++s) s_pref[s] = acc;
+    s_max_tiles = mx;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const unsigned long long total = s_pref[kMaxPeers];
-  const unsigned long long n_tiles = (total + kThreadsP - 1) / kThreadsP;
-  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const unsigned long long f = tile * kThreadsP + threadIdx.x;
-    const bool valid = f < total;
-    unsigned long long i = 0;
-    const int s = valid ? xchg_locate(s_pref, xv.world, f, i) : 0;
+  const unsigned W = (unsigned)xv.world;
+  const unsigned long long n_tiles = (unsigned long long)s_max_tiles * W;   // tile q: source (q + rank) % W, its tile q / W
+  for (unsigned long long q = blockIdx.x; q < n_tiles; q += gridDim.x) {
+    const int s = (int)((q + (unsigned)xv.rank) % W);
+    const unsigned long long i = (q / W) * kThreadsP + threadIdx.x;
+    const bool valid = i < s_cnt[s];
     long long key = 0;
     unsigned idx = 0;
     if (valid) {
       key = ld_cg_ll(reinterpret_cast<const long long*>(xv.base[xv.rank] + xv.off_req_keys + (size_t)s * xv.seg_req_keys) + i);
       idx = ld_cg_u32(reinterpret_cast<const unsigned*>(xv.base[xv.rank] + xv.off_req_idx + (size_t)s * xv.seg_req_idx) + i);
     }
+    if ((q / W) * kThreadsP >= s_cnt[s]) continue;   // the whole tile lies beyond this source's requests (uniform per CTA)
     const long long slot = warp_find_slots<false>(t, key, valid, lane);
     if (want_exists && valid) (xv.base[s] + xv.off_exists + (size_t)parity * xv.ex_bytes)[idx] = slot >= 0 ? 1 : 0;
     const unsigned char* src = nullptr;

@@ -198,7 +198,7 @@ class PeerShardedVariable(object):
     return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
   # ---- owner-side exchange (det_peer_xchg_*): ids travel to the owner, the owner probes locally and pushes rows ----
-  def attach_exchange(self, max_items, mailbox_ptrs=None, keepalive=None):
+  def attach_exchange(self, max_items, mailbox_ptrs=None, keepalive=None, insert="push"):
     """Collective.  Gives every rank a MAILBOX all peers map (request / insert segments per source rank, a 2-entry
     output ring, flag words); afterwards lookup() / upsert() run through the owners with posted NVLink stores only
     (HvdVariable.__alltoall_embedding_lookup__, shadow_embedding_ops.py:397-447, without a collective library).
@@ -226,6 +226,12 @@ class PeerShardedVariable(object):
     self._libmod.check(self._lib.det_peer_xchg_attach(self._g, arr, int(max_items), rb))
     self._xchg_items = int(max_items)
     self._xchg = True
+    # insert="pull" (the HYBRID exchange): lookups go through the owners (pushes only), upserts keep the one-sided kernel
+    # that probes the owner's key plane remotely and posts the row -- the faster of the two at every measured N
+    # (profiles/r02_bench_n{2,8}_*.json).  Reads and remote writes then need phase_barrier() between them again.
+    if insert not in ("push", "pull"):
+      raise ValueError("attach_exchange: insert must be 'push' or 'pull'")
+    self._xchg_insert = insert == "push"
 
   def _ring_view(self, ptr, n):
     """torch view of n rows of the output ring (lives inside the mailbox allocation)"""
@@ -265,7 +271,7 @@ class PeerShardedVariable(object):
     flat = keys.reshape(-1).contiguous()
     vals = values.reshape(-1, self.dim).contiguous()
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    if getattr(self, "_xchg", False):
+    if getattr(self, "_xchg", False) and self._xchg_insert:
       self._libmod.check(self._lib.det_peer_xchg_insert(self._g, p(flat), p(vals), flat.numel(), self._sp()))
       return
     self._libmod.check(self._lib.det_peer_insert(self._g, p(flat), p(vals), flat.numel(), self._sp()))
@@ -273,7 +279,7 @@ class PeerShardedVariable(object):
   def phase_barrier(self):
     """Separates a phase in which ranks read from one in which they write (one-sided kernels).  With the owner-side
     exchange attached it is a no-op: every shard is read and written by its OWNER's kernels only, in stream order."""
-    if getattr(self, "_xchg", False):
+    if getattr(self, "_xchg", False) and self._xchg_insert:
       return
     self._libmod.check(self._lib.det_peer_barrier(self._g, self._sp()))
 
@@ -329,6 +335,8 @@ class PeerShardedVariable(object):
     """Backward of the sharded lookup: route the row-gradients to their owners over NVLink, combine the gradients
     that several ranks sent for the same key, then run the fused optimizer on the local shard (half-sync: sparse
     rows are never all-reduced, dynamic_embedding_optimizer.py:580-595)."""
+    if getattr(self, "_xchg", False) and self._xchg_insert and self.value_dtype == torch.float32:
+      return self._apply_gradients_xchg(optimizer, keys, grads)
     from .variable import unique
     self.route(keys, grads)
     self.phase_barrier()
@@ -341,6 +349,33 @@ class PeerShardedVariable(object):
       optimizer.apply_sparse(self.local, uniq, gsum)
     else:
       optimizer.iterations += 1
+
+  def _apply_gradients_xchg(self, optimizer, keys, grads):
+    """owner-side step in ONE collective C call (det_peer_xchg_apply_*): route -> compact -> unique -> position-order
+    gradient sum -> fused optimizer, every count on the device (no host synchronisation, no inbox round trip)"""
+    import ctypes
+    from .optimizer import FusedAdagrad, FusedAdam
+    flat = keys.reshape(-1).contiguous()
+    g = grads.reshape(-1, self.dim).to(torch.float32).contiguous()
+    need = int(self._lib.det_peer_xchg_apply_workspace_bytes(self._g))
+    ws = getattr(self, "_xapply_ws", None)
+    if ws is None or ws.numel() < need:
+      raw = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+      off = (-raw.data_ptr()) % 256
+      ws = self._xapply_ws = raw[off:off + need]
+    init = self._default.to(self.device).contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t.numel() else None
+    optimizer.iterations += 1
+    if isinstance(optimizer, FusedAdagrad):
+      self._libmod.check(self._lib.det_peer_xchg_apply_adagrad(self._g, p(flat), p(g), flat.numel(), optimizer.learning_rate,
+                                                               optimizer.epsilon, p(init), optimizer.initial_accumulator_value,
+                                                               p(ws), ws.numel(), self._sp()))
+    elif isinstance(optimizer, FusedAdam):
+      self._libmod.check(self._lib.det_peer_xchg_apply_adam(self._g, p(flat), p(g), flat.numel(), optimizer.alpha(),
+                                                            optimizer.beta_1, optimizer.beta_2, optimizer.epsilon, p(init),
+                                                            p(ws), ws.numel(), self._sp()))
+    else:
+      raise TypeError("PeerShardedVariable.apply_gradients: de.FusedAdagrad / de.FusedAdam")
 
   def size(self):
     if self._group is None and self.world > 1 and all(t is not None for t in self._tables):

@@ -24,7 +24,8 @@ _EXTRA = ["det_find_host", "det_insert_host", "det_find_host_async", "det_insert
           "det_peer_find", "det_peer_insert", "det_peer_barrier", "det_peer_inbox_bytes", "det_peer_inbox_attach",
           "det_peer_route", "det_peer_inbox_counts", "det_peer_inbox_gather", "det_table_region_bytes",
           "det_table_create_in_region", "det_peer_group_create_regions", "det_peer_xchg_bytes", "det_peer_xchg_attach",
-          "det_peer_xchg_find", "det_peer_xchg_insert"]
+          "det_peer_xchg_find", "det_peer_xchg_insert", "det_peer_xchg_apply_workspace_bytes", "det_peer_xchg_apply_adagrad",
+          "det_peer_xchg_apply_adam"]
 
 
 def X():
@@ -366,6 +367,101 @@ def test_owner_side_exchange_threads_as_ranks(world, dim):
     assert tables[r].size() == sum(1 for k in written if O.default_partition_fn(np.array([k]), world, True)[0] == r)
     assert tables[r].stats()["error_flags"] == 0
     tables[r].close()
+
+
+@pytest.mark.parametrize("opt", ["adagrad", "adam"])
+def test_owner_side_sharded_optimizer_step(opt):
+  """det_peer_xchg_apply_*: the backward of the sharded lookup.  3 ranks (threads); every rank sends gradients for ids of
+  ALL owners, the SAME ids from several ranks (summed on the owner in source-rank order), fresh ids every step; counts
+  never leave the "device".  Twin per owner: oracle tables stepped with unique -> segment_reduce -> sparse_*_step over
+  the pairs in (source rank, sender order); params and slot planes of every shard bit-exact after 3 steps."""
+  world, dim, per, cap, steps = 3, 16, 260, 512, 3
+  planes = 1 if opt == "adagrad" else 2
+  rng = np.random.default_rng(77 + planes)
+  pool = rng.choice(1 << 40, size=900, replace=False).astype(np.int64)
+  owner_of = lambda k: O.default_partition_fn(k, world, True)
+  tables = [Table(dim=dim, init=4096, max_capacity=4096, slot_planes=planes) for _ in range(world)]
+  hb = X().det_peer_handle_bytes()
+  blob = (ctypes.c_ubyte * (hb * world))()
+  for r in range(world):
+    ck(X().det_peer_export(tables[r].h, ctypes.c_void_p(ctypes.addressof(blob) + r * hb)))
+  rb = dim * 4
+  nbytes = X().det_peer_xchg_bytes(world, cap, rb)
+  raw = [np.zeros(nbytes + 256, dtype=np.uint8) for _ in range(world)]
+  boxes = [b[(-b.ctypes.data) % 256:][:nbytes] for b in raw]
+  sched = [[(np.ascontiguousarray(rng.choice(pool, size=per - 40 * r, replace=False)),
+             rng.normal(0, 1e-2, (per - 40 * r, dim)).astype(np.float32)) for r in range(world)] for _ in range(steps)]
+  ip, ia = np.full(dim, 0.05, np.float32), np.full(dim, 0.1, np.float32)
+  errors = []
+  start = threading.Barrier(world)
+
+  def rank_main(r):
+    try:
+      tl = [None] * world
+      tl[r] = tables[r]
+      g = PeerGroup(tl, ctypes.cast(blob, ctypes.c_void_p), world, r)
+      ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boxes])
+      ck(X().det_peer_xchg_attach(g.g, ptrs, cap, rb))
+      wsb = X().det_peer_xchg_apply_workspace_bytes(g.g)
+      assert wsb > 0
+      wraw = np.zeros(wsb + 256, np.uint8)
+      ws = wraw[(-wraw.ctypes.data) % 256:][:wsb]
+      start.wait()
+      for t in range(steps):
+        k, gr = sched[t][r]
+        if opt == "adagrad":
+          ck(X().det_peer_xchg_apply_adagrad(g.g, P(k), P(gr), len(k), 0.1, 0.0, P(ip), 0.1, P(ws), wsb, None))
+        else:
+          alpha = float(O.adam_scalars(0.01, 0.9, 0.999, t + 1))
+          ck(X().det_peer_xchg_apply_adam(g.g, P(k), P(gr), len(k), alpha, 0.9, 0.999, 1e-8, P(ip), P(ws), wsb, None))
+      # a lookup through the owners sees every owner's updated rows
+      q = np.ascontiguousarray(pool[::5])
+      out = np.empty((len(q), dim), np.float32)
+      ck(X().det_peer_xchg_find(g.g, P(q), len(q), P(ip), 0, P(out), None, None, None))
+      got[r] = (q, out)
+      g.close()
+    except BaseException:  # pragma: no cover
+      import traceback
+      errors.append((r, traceback.format_exc()))
+      try:
+        start.abort()
+      except Exception:
+        pass
+
+  got = {}
+  th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+  for x in th:
+    x.start()
+  for x in th:
+    x.join(timeout=600)
+  assert not errors, errors
+  from tests.test_fused_emu import _export_sorted, sorted_export
+  model = {}
+  for o in range(world):
+    tabs = [O.PortTable(dim) for _ in range(1 + planes)]
+    for t in range(steps):
+      ks = np.concatenate([sched[t][s][0][owner_of(sched[t][s][0]) == o] for s in range(world)])
+      gs = np.concatenate([sched[t][s][1][owner_of(sched[t][s][0]) == o] for s in range(world)])
+      u, idx = O.unique_first_occurrence(ks)
+      gsum = O.segment_reduce(gs, idx, len(u))
+      if opt == "adagrad":
+        O.sparse_adagrad_step(tabs[0], tabs[1], u, gsum, 0.1, ip, ia, 0.0)
+      else:
+        O.sparse_adam_step(tabs[0], tabs[1], tabs[2], u, gsum, O.adam_scalars(0.01, 0.9, 0.999, t + 1), 0.9, 0.999, 1e-8, ip)
+    for plane, ot in enumerate(tabs):
+      k, v = _export_sorted(tables[o], plane)
+      ek, ev = sorted_export(ot)
+      np.testing.assert_array_equal(k, ek)
+      np.testing.assert_array_equal(v, ev)
+    ek, ev = tabs[0].export()
+    model.update(zip(ek.tolist(), ev))
+  for r in range(world):
+    q, out = got[r]
+    exp = np.stack([model.get(int(k), ip) for k in q])
+    np.testing.assert_array_equal(out, exp)
+  for t in tables:
+    assert t.stats()["error_flags"] == 0
+    t.close()
 
 
 def test_bounded_table_reserve_clear_import_and_load(tmp_path):

@@ -23,12 +23,14 @@ def _worker(rank, world, port, q):
   ok = True
   msg = ""
   try:
-    for mode in ("nccl", "peer", "symm", "push"):
-      if mode in ("symm", "push"):  # shard inside a torch symmetric-memory region (CUDA VMM): the production path
+    for mode in ("nccl", "peer", "symm", "push", "hybrid"):
+      if mode in ("symm", "push", "hybrid"):  # shard inside a torch symmetric-memory region (CUDA VMM): the production path
         sv = de.PeerShardedVariable.create(dim, 1 << 18, initializer=-1.0, name="mg-%s-%d" % (mode, rank))
         var = sv.local
         if mode == "push":          # owner-side exchange: ids to the owner, local probe, rows pushed back; no barriers
           sv.attach_exchange(1 << 16)
+        if mode == "hybrid":        # lookups through the owners, one-sided inserts, flag barrier between the phases
+          sv.attach_exchange(1 << 16, insert="pull")
       else:
         var = de.Variable(dim=dim, init_size=1 << 18, initializer=-1.0, name="mg-%s-%d" % (mode, rank))
         sv = de.ShardedVariable(var) if mode == "nccl" else de.PeerShardedVariable(var)
@@ -125,6 +127,27 @@ def _worker(rank, world, port, q):
           v1 = sv.lookup(torch.from_numpy(qk).to(dev), copy=False)
           if not np.array_equal(v1.cpu().numpy(), exp_r):
             ok, msg = False, "push mode: ring view in round %d" % rnd
+        torch.cuda.synchronize()
+        dist.barrier()
+        # the sharded optimizer step through the owners (det_peer_xchg_apply_adagrad): the SAME keys from every rank
+        var3 = de.PeerShardedVariable.create(dim, 1 << 18, initializer=0.0, num_slot_planes=1, name="mg-xopt-%d" % rank)
+        var3.attach_exchange(1 << 16)
+        opt3 = de.FusedAdagrad(0.1, 0.1)
+        gk3 = allkeys[:20000]
+        gg3 = np.full((gk3.shape[0], dim), 0.01 * (rank + 1), np.float32)
+        for _ in range(2):
+          var3.apply_gradients(opt3, torch.from_numpy(gk3).to(dev), torch.from_numpy(gg3).to(dev))
+        got3 = var3.lookup(torch.from_numpy(gk3).to(dev)).cpu().numpy()
+        f32 = np.float32
+        gsum3 = f32(0)
+        for r3 in range(world):                      # summed on the owner in source-rank order
+          gsum3 = f32(gsum3 + f32(0.01 * (r3 + 1)))
+        acc3, p3 = f32(0.1), f32(0)
+        for _ in range(2):
+          acc3 = f32(acc3 + f32(gsum3 * gsum3))
+          p3 = f32(p3 - f32(f32(f32(0.1) * gsum3) / f32(np.sqrt(acc3))))
+        if not np.array_equal(got3, np.full_like(got3, p3)):
+          ok, msg = False, "owner-side sharded adagrad: %r vs %r" % (got3[0, 0], p3)
         torch.cuda.synchronize()
         dist.barrier()
       if var.tables[0].stats()["error_flags"] != 0:
