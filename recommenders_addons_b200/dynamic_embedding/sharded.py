@@ -139,7 +139,71 @@ class PeerShardedVariable(object):
     self._tables = [None] * self.world
     self._tables[self.rank] = var.tables[0]
     self.backing = "symmetric-memory"
+    self._create_args = dict(dim=dim, group=group, value_dtype=value_dtype, initializer=initializer,
+                             num_slot_planes=num_slot_planes, name=name, gpu_mode=gpu_mode)
+    self.capacity = int(capacity)
     return self
+
+  # ---- lifecycle of a sharded table: a shard has a FIXED capacity (its planes are mapped by every peer) ------------
+  def load(self):
+    """COLLECTIVE.  Highest load (live keys / slots) over all shards, agreed by every rank."""
+    t = torch.tensor([float(self.local.size()) / float(self.capacity)], dtype=torch.float64, device=self.device)
+    if self.world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._group)
+    return float(t.item())
+
+  def grow(self, new_capacity, window=1 << 22):
+    """COLLECTIVE.  The reference's cuckoo shards double under the hood (cuckoohash_map.hh:1774+); a shard that peers have
+    mapped cannot: every rank builds a NEW symmetric region of `new_capacity` slots, re-rendezvouses, streams its own shard
+    across in bounded windows (rows and optimizer slot planes), and swaps the peer group, mailbox and inbox over.  Keys
+    keep their owner, so no row crosses NVLink.  Call it between steps (maybe_grow does, on an agreed load)."""
+    if self.backing != "symmetric-memory":
+      raise RuntimeError("grow needs the symmetric-memory backing (PeerShardedVariable.create)")
+    new_capacity = int(new_capacity)
+    if new_capacity <= self.capacity:
+      raise ValueError("grow: new_capacity must exceed the current %d slots" % self.capacity)
+    torch.cuda.synchronize(self.device)
+    dist.barrier(group=self._group)                       # nobody is still reading or writing the old shards
+    fresh = PeerShardedVariable.create(capacity=new_capacity, **self._create_args)
+    told, tnew = self.local.tables[0], fresh.local.tables[0]
+    planes = int(self._create_args["num_slot_planes"])
+    first = 0
+    while True:
+      k, v = told.export_window(first, window)
+      if k.numel() == 0:
+        break
+      tnew.insert(k, v)
+      for pl in range(1, planes + 1):
+        k2, sv_ = told.export_window(first, window, plane=pl)
+        tnew.import_plane(pl, k2, sv_)
+      first += k.numel()
+    torch.cuda.synchronize(self.device)
+    xitems = getattr(self, "_xchg_items", 0) if getattr(self, "_xchg", False) else 0
+    xins = "push" if getattr(self, "_xchg_insert", True) else "pull"
+    inbox_items = getattr(self, "_inbox_items", 0)
+    self.close()                                          # old group; the old region dies with its last reference
+    old_table = told
+    for attr in ("local", "_g", "_symm", "_tables", "capacity", "_default"):
+      setattr(self, attr, getattr(fresh, attr))
+    fresh._g = None                                       # ownership moved
+    self._xchg = False
+    for attr in ("_xbox", "_inbox", "_xapply_ws"):
+      if hasattr(self, attr):
+        delattr(self, attr)
+    old_table.close()
+    if xitems:
+      self.attach_exchange(xitems, insert=xins)
+    if inbox_items:
+      self.attach_inbox(inbox_items)
+    dist.barrier(group=self._group)
+
+  def maybe_grow(self, threshold=0.6, factor=2.0):
+    """COLLECTIVE.  Grows every shard by `factor` once the fullest shard has passed `threshold` (the decision is an
+    all-reduce MAX, so all ranks take it together).  Returns True when it grew."""
+    if self.load() > threshold:
+      self.grow(int(self.capacity * factor))
+      return True
+    return False
 
   def _init_common(self, local_variable, group, gpu_mode):
     from .. import _lib

@@ -331,6 +331,18 @@ class CuckooHashTable(object):
                                     _stream_ptr(self._device)))
     return keys[:got.value], values[:got.value]
 
+  def export_window(self, first, max_keys, plane=0):
+    """(keys, values) of at most `max_keys` live keys starting at live key number `first` of the table order: bounded-
+    memory streaming of a table (det_export_window; what det_save uses).  The table must not be mutated between the
+    windows of one pass.  An empty result marks the end."""
+    vdtype = self._value_dtype if plane == 0 else torch.float32
+    keys = torch.empty(int(max_keys), dtype=torch.int64, device=self._device)
+    values = torch.empty((int(max_keys), self._dim), dtype=vdtype, device=self._device)
+    got = ctypes.c_int64(0)
+    _lib.check(self._lib.det_export_window(self._h, int(plane), int(first), _ptr(keys), _ptr(values), int(max_keys),
+                                           ctypes.byref(got), _stream_ptr(self._device)))
+    return keys[:got.value], values[:got.value]
+
   def import_(self, keys, values):
     """ImportValues = clear + insert (cuckoo_hashtable_op.cc:288-291)."""
     keys = self._check_keys(keys).reshape(-1)

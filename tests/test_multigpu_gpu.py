@@ -150,6 +150,24 @@ def _worker(rank, world, port, q):
           ok, msg = False, "owner-side sharded adagrad: %r vs %r" % (got3[0, 0], p3)
         torch.cuda.synchronize()
         dist.barrier()
+        # coordinated growth: every rank re-creates its shard in a bigger symmetric region and streams its rows AND its
+        # optimizer slots across; lookups, sizes and the next optimizer step must not notice
+        size_before = int(var3.local.size())
+        if var3.maybe_grow(threshold=0.99):
+          ok, msg = False, "maybe_grow grew a table at load %.3f" % var3.load()
+        var3.grow(1 << 19)
+        if var3.capacity != 1 << 19 or int(var3.local.size()) != size_before:
+          ok, msg = False, "grow: capacity %d size %d (was %d)" % (var3.capacity, int(var3.local.size()), size_before)
+        if not np.array_equal(var3.lookup(torch.from_numpy(gk3).to(dev)).cpu().numpy(), got3):
+          ok, msg = False, "grow: rows changed"
+        var3.apply_gradients(opt3, torch.from_numpy(gk3).to(dev), torch.from_numpy(gg3).to(dev))   # accumulators survived
+        acc3 = f32(acc3 + f32(gsum3 * gsum3))
+        p3 = f32(p3 - f32(f32(f32(0.1) * gsum3) / f32(np.sqrt(acc3))))
+        got4 = var3.lookup(torch.from_numpy(gk3).to(dev)).cpu().numpy()
+        if not np.array_equal(got4, np.full_like(got4, p3)):
+          ok, msg = False, "step after grow: %r vs %r" % (got4[0, 0], p3)
+        torch.cuda.synchronize()
+        dist.barrier()
       if var.tables[0].stats()["error_flags"] != 0:
         ok, msg = False, "error flags in mode %s" % mode
   except Exception as e:  # noqa: BLE001
