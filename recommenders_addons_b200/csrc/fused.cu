@@ -1005,8 +1005,13 @@ static void fgeom(unsigned dim, bool vec4, unsigned min_lpr, unsigned* vpr, unsi
 //      the whole CTA stages a tile of rows in shared memory with every load in flight, then thread c adds column c
 //      in order), all other CTAs give each lane-group two short groups at a time, 4 row loads in flight per group.
 // Indices outside [0, n_groups) are dropped like unsorted_segment_sum drops negative ids.
-constexpr int kRadixBits = 11;                     // 2 passes sort 22 bits: every batch below 4M groups (3 passes of 8 bits
-                                                   // cost 160 us of the c3 step, profiles/r02_c3_launch_list_before.csv)
+// 8-bit digits, measured: the c3 sort (1.7M items, 19 significant bits) takes 3 x (9 + 10 + 35) us = 162 us; with 11-bit
+// digits (-DDET_RADIX_BITS=11: 2 passes) 2 x (19 + 10 + 60) = 178 us -- the 2048-bin scatter pays for its shared-memory
+// counters (profiles/r02_c3_launch_list_{before,after}.csv).  The kernels below are written for any width <= 11.
+#ifndef DET_RADIX_BITS
+#define DET_RADIX_BITS 8
+#endif
+constexpr int kRadixBits = DET_RADIX_BITS;
 constexpr int kRadixBins = 1 << kRadixBits;
 constexpr int kRadixThreads = 256;
 constexpr int kRadixBpt = kRadixBins / kRadixThreads;   // bins per thread: thread t owns bins [t * kRadixBpt, (t + 1) * kRadixBpt)
