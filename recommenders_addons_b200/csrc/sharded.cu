@@ -332,10 +332,17 @@ template <bool WITH_ROWS, int VEC>
 __global__ void __launch_bounds__(kThreadsP)
 xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigned char* __restrict__ rows, size_t n,
                   RowGeom g, unsigned long long* cursor, unsigned* ticket, unsigned long long epoch, DevState* st) {
+  constexpr int kTileI = kThreadsP * kRouteKpt;
   __shared__ unsigned s_cnt[kMaxPeers];
+  __shared__ unsigned s_off[kMaxPeers + 1];          // start of every owner's run inside the staged tile
   __shared__ unsigned long long s_base[kMaxPeers];
+  // the tile's keys and positions grouped by owner: the remote stores of one owner's run are CONTIGUOUS (a warp writes
+  // 256 B of keys with one instruction instead of eight 32 B pieces -- 2M tiny NVLink packets per 1M keys otherwise,
+  // 73 us of the N=8 find, profiles/r02_xchg_phase_timing_n8_after_interleave.txt)
+  __shared__ long long s_key[kTileI];
+  __shared__ unsigned s_idx[kTileI];
   const int lane = threadIdx.x & 31;
-  constexpr size_t kTile = (size_t)kThreadsP * kRouteKpt;
+  constexpr size_t kTile = (size_t)kTileI;
   const size_t n_tiles = (n + kTile - 1) / kTile;
   const size_t par = WITH_ROWS ? (size_t)(epoch & 1ull) : 0;          // insert epochs alternate between two segment sets
   const size_t seg_k = WITH_ROWS ? xv.seg_ins_keys : xv.seg_req_keys;
@@ -358,6 +365,14 @@ xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigne
     }
     __syncthreads();
     if ((int)threadIdx.x < xv.world) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0) {
+      unsigned acc = 0;
+      for (int o = 0; o < kMaxPeers; ++o) {
+        s_off[o] = acc;
+        acc += o < xv.world ? s_cnt[o] : 0u;
+      }
+      s_off[kMaxPeers] = acc;
+    }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < kRouteKpt; ++q) {
@@ -365,7 +380,11 @@ xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigne
       const unsigned long long dest = s_base[own[q]] + pos[q];
       const bool ok = valid[q] && dest < xv.cap;
       if (valid[q] && !ok) atomicOr(&st->error, kErrTableFull);
-      if (ok) reinterpret_cast<long long*>(xv.base[own[q]] + off_k)[dest] = key[q];
+      if (valid[q]) {
+        const unsigned e = s_off[own[q]] + pos[q];
+        s_key[e] = key[q];
+        s_idx[e] = (unsigned)(i - tile * kTile);       // position inside the tile (the global one is rebuilt below)
+      }
       if (WITH_ROWS) {
         const unsigned char* src = nullptr;
         unsigned char* dst = nullptr;
@@ -374,8 +393,27 @@ xchg_route_kernel(XchgView xv, const long long* __restrict__ keys, const unsigne
           dst = xv.base[own[q]] + off_r + dest * g.row_bytes;
         }
         warp_move_rows<VEC>(g, src, dst, lane);
-      } else if (ok) {
-        reinterpret_cast<unsigned*>(xv.base[own[q]] + xv.off_req_idx + (size_t)xv.rank * xv.seg_req_idx)[dest] = (unsigned)i;
+      }
+    }
+    __syncthreads();
+    // write-out: entry e of the staged tile belongs to the owner whose run contains it; consecutive threads write
+    // consecutive remote addresses
+    const unsigned total = s_off[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kRouteKpt; ++q) {
+      const unsigned e = (unsigned)q * kThreadsP + threadIdx.x;
+      if (e < total) {
+        int o = 0;
+#pragma unroll
+        for (int c = 1; c < kMaxPeers; ++c)
+          if (c < xv.world && e >= s_off[c]) o = c;
+        const unsigned long long dest = s_base[o] + (e - s_off[o]);
+        if (dest < xv.cap) {
+          reinterpret_cast<long long*>(xv.base[o] + off_k)[dest] = s_key[e];
+          if (!WITH_ROWS)
+            reinterpret_cast<unsigned*>(xv.base[o] + xv.off_req_idx + (size_t)xv.rank * xv.seg_req_idx)[dest] =
+                (unsigned)(tile * kTile) + s_idx[e];
+        }
       }
     }
     __syncthreads();
