@@ -730,10 +730,37 @@ def gpu_arm(args):
         table.host_sync()
       dtp = time.perf_counter() - t0
       e2e["sequential_value"] = seq_value
-      e2e["value"] = B * n_e2e / dtp / 1e6
+      e2e["drained_every_step_value"] = B * n_e2e / dtp / 1e6
+      e2e["value"] = e2e["drained_every_step_value"]
       e2e["api"] = ("CuckooHashTable.lookup_host_async(batch i+1) + insert_host_async(batch i) + host_sync per step "
                     "(det_insert_host_async / det_find_host_async, pinned host buffers, both PCIe directions busy); "
                     "sequential_value = lookup_host then insert_host of the same batch, back to back")
+      # Same per-step work, but a step only waits for what it CONSUMES: the looked-up rows of batch i+1
+      # (det_host_sync_pipe(0)); the write-back of batch i keeps draining while step i+1's copies start, everything has
+      # landed before the clock stops (final host_sync).  Every step still uploads its keys / rows and downloads its
+      # rows inside the timed region; no step boundary drains the link.
+      try:
+        table.host_sync()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+          table.lookup_host_async(hk[(i + 1) % n_e2e], hd, ho2 if i % 2 == 0 else ho)
+          table.insert_host_async(hk[i], hvs[i])
+          table.host_sync("lookup")
+        table.host_sync()
+        dtq = time.perf_counter() - t0
+        chk = ho2 if (n_e2e - 1) % 2 == 0 else ho                   # rows of the last prefetched batch, on the host
+        kq = hk[n_e2e % n_e2e]
+        okq = bool(torch.equal(chk[:4096], rows_of_keys_torch(kq[:4096], dim, 1)))
+        if okq and B * n_e2e / dtq / 1e6 > e2e["value"]:
+          e2e["value"] = B * n_e2e / dtq / 1e6
+          e2e["api"] = ("CuckooHashTable.lookup_host_async(batch i+1) + insert_host_async(batch i) per step, the step waits "
+                        "for its looked-up rows only (host_sync('lookup') = det_host_sync_pipe(0)) while the write-back "
+                        "drains behind; final host_sync inside the timed region; pinned host buffers, both PCIe directions "
+                        "busy across steps.  drained_every_step_value = full host_sync per step; sequential_value = "
+                        "lookup_host then insert_host of the same batch, back to back")
+        e2e["prefetch_rows_checked"] = {"checked": 4096, "ok": okq}
+      except Exception as ex:   # never lose the line over the optional flavour
+        e2e["pipelined_error"] = repr(ex)
 
   if not args.no_e2e and prev_aff is not None:
     os.sched_setaffinity(0, prev_aff)  # the CPU baseline below must see every host core again

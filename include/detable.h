@@ -276,6 +276,11 @@ det_status det_find_host_async(det_table* t, const int64_t* keys_host, size_t n,
                                int full_size_default, void* values_out_host, uint8_t* exists_host);
 det_status det_insert_host_async(det_table* t, const int64_t* keys_host, const void* values_host, size_t n);
 det_status det_host_sync(det_table* t);
+/* ABI >= 8.  which = 0: everything det_find_host_async has enqueued is on the host; 1: everything det_insert_host_async
+ * has enqueued has been applied; -1: both (= det_host_sync).  A loop that prefetches the rows of step i+1 and writes
+ * step i back waits with which = 0: the write-back keeps draining while the next step's copies start, so both PCIe
+ * directions stay busy across step boundaries. */
+det_status det_host_sync_pipe(det_table* t, int which);
 
 /* Sparse apply_gradients with REPEATED ids in ONE call and without host synchronisation (ABI >= 6): what the reference's
  * optimizer patch does for IndexedSlices gradients -- unique(ids) -> unsorted_segment_sum(grads, idx, n_unique) ->

@@ -10,7 +10,7 @@ _sz = ctypes.c_size_t
 _i = ctypes.c_int
 
 DET_OK = 0
-ABI_VERSION = 7  # det_abi_version() of the library these mirrors describe (checked at load)
+ABI_VERSION = 8  # det_abi_version() of the library these mirrors describe (checked at load)
 DTYPE_CODES = {"float32": 0, "float16": 1, "bfloat16": 2, "int32": 3, "int64": 4, "int8": 5, "float64": 6}
 COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 # HkvEvictStrategy (python/ops/hkv_hashtable_ops.py); det_config.flags low nibble = strategy + 1
@@ -73,6 +73,7 @@ SIGNATURES = {
     "det_find_host_async": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "det_insert_host_async": (_i, [_vp, _vp, _vp, _sz]),
     "det_host_sync": (_i, [_vp]),
+    "det_host_sync_pipe": (_i, [_vp, _i]),
     "det_partition_workspace_bytes": (_sz, [_sz, _i]),
     "det_partition": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "det_scatter_rows": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),

@@ -284,6 +284,21 @@ det_status det_host_sync(det_table* t) {
   return DET_OK;
 }
 
+// which = 0: everything det_find_host_async has enqueued is on the host (the rows a consumer waits for); 1: everything
+// det_insert_host_async has enqueued has been applied; -1: both (= det_host_sync).  Lets a training loop wait for the
+// prefetched rows of step i+1 while the write-back of step i is still draining into the table: the two PCIe directions
+// then stay busy across steps instead of draining at every step boundary.
+det_status det_host_sync_pipe(det_table* t, int which) {
+  if (!t) return fail(DET_INVALID_ARGUMENT, "det_host_sync_pipe: null table");
+  if (which < -1 || which > 1) return fail(DET_INVALID_ARGUMENT, "det_host_sync_pipe: which must be -1, 0 or 1");
+  if (which < 0) return det_host_sync(t);
+  det::DevGuard _dg(t->cfg.device);
+  HostPipe* p = which == 0 ? t->pipe : t->pipe2;
+  if (p)
+    for (int i = 0; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamSynchronize(p->streams[i]));
+  return DET_OK;
+}
+
 // SaveToFileSystem (cuckoo_hashtable_op.cc:310-391; GPU: dump_to_file, lookup_table_op_hkv.h:602-652): the table is
 // exported window by window (det_export_window: `buffer_keys` keys at a time, table order) into a bounded device
 // buffer, copied to a bounded host buffer and appended to `<prefix>-keys` / `<prefix>-values`; memory use does not

@@ -1006,7 +1006,7 @@ using namespace det;
 
 extern "C" {
 
-int det_abi_version(void) { return 7; }
+int det_abi_version(void) { return 8; }
 #ifdef DET_EMU
 unsigned long long det_emu_stat(int which) { return which >= 0 && which < 4 ? det::g_det_emu_stat[which] : 0; }
 #endif

@@ -371,8 +371,13 @@ class CuckooHashTable(object):
   def insert_host_async(self, keys_host, values_host):
     _lib.check(self._lib.det_insert_host_async(self._h, _ptr(keys_host), _ptr(values_host), keys_host.numel()))
 
-  def host_sync(self):
-    _lib.check(self._lib.det_host_sync(self._h))
+  def host_sync(self, which=None):
+    """which=None: every enqueued host-buffer op has finished; "lookup": the rows of every lookup_host_async are on the
+    host (the write-backs may still be draining); "insert": every insert_host_async has been applied."""
+    if which is None:
+      _lib.check(self._lib.det_host_sync(self._h))
+    else:
+      _lib.check(self._lib.det_host_sync_pipe(self._h, {"lookup": 0, "insert": 1}[which]))
 
   # file-system format (cuckoo_hashtable_ops.py:425-523)
   def save_to_file_system(self, dirpath, file_name=None, dirpath_env="TFRA_SAVED_KV", append_to_file=False,

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
   assert set(names) == set(_lib.SIGNATURES.keys()), set(names) ^ set(_lib.SIGNATURES.keys())
   for n in names:
     assert getattr(lib, n) is not None
-  assert lib.det_abi_version() == _lib.ABI_VERSION == 7
+  assert lib.det_abi_version() == _lib.ABI_VERSION == 8
   assert b"sm_100a" in lib.det_build_info()
 
 

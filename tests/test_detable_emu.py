@@ -161,7 +161,7 @@ def rows(vals, dim=8, dtype=np.int32):
 
 # ---- (1) the standard path ---------------------------------------------------------------------------------------
 def test_standard_path_growth_find_accum_remove_export():
-  assert L().det_abi_version() == 7
+  assert L().det_abi_version() == 8
   rng = np.random.default_rng(0)
   t = Table(dim=8, init=64)
   ref = {}

@@ -19,7 +19,7 @@ from oracle import oracle as O  # noqa: E402
 from recommenders_addons_b200 import _lib as real  # noqa: E402
 from tests.test_detable_emu import L, P, Table, ck  # noqa: E402
 
-_EXTRA = ["det_find_host", "det_insert_host", "det_find_host_async", "det_insert_host_async", "det_host_sync", "det_save",
+_EXTRA = ["det_find_host", "det_insert_host", "det_find_host_async", "det_insert_host_async", "det_host_sync", "det_host_sync_pipe", "det_save",
           "det_load", "det_export_window", "det_peer_handle_bytes", "det_peer_export", "det_peer_group_create", "det_peer_group_destroy",
           "det_peer_find", "det_peer_insert", "det_peer_barrier", "det_peer_inbox_bytes", "det_peer_inbox_attach",
           "det_peer_route", "det_peer_inbox_counts", "det_peer_inbox_gather", "det_table_region_bytes",
@@ -68,6 +68,17 @@ def test_host_buffer_entry_points_and_async_pipeline():
   assert ex2.all()
   np.testing.assert_array_equal(out2, vals)
   assert t.size() == n + 4000
+  # waiting for one pipeline only: the looked-up rows are on the host after sync_pipe(0), the write-back after (1)
+  keys3 = keys2 + 7
+  out3 = np.full((4000, dim), np.nan, dtype=np.float32)
+  ck(X().det_find_host_async(t.h, P(keys2), 4000, P(zero), 0, P(out3), None))
+  ck(X().det_insert_host_async(t.h, P(keys3), P(vals2), 4000))
+  ck(X().det_host_sync_pipe(t.h, 0))
+  np.testing.assert_array_equal(out3, vals2)
+  ck(X().det_host_sync_pipe(t.h, 1))
+  assert t.size() == n + 8000
+  ck(X().det_host_sync_pipe(t.h, -1))
+  assert X().det_host_sync_pipe(t.h, 2) == 1 and X().det_host_sync_pipe(None, 0) == 1
   t.close()
 
 

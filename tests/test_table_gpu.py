@@ -298,7 +298,22 @@ def test_export_import_and_file_round_trip(tmp_path):
   ob = torch.argsort(kb)
   np.testing.assert_array_equal(kb[ob].cpu().numpy(), np.sort(k))
   np.testing.assert_array_equal(vb[ob].cpu().numpy(), v[np.argsort(k)])
-  # files written by the reference engine load into ours (same raw format)
+  # A file pair laid out the way the reference's SaveToFileSystem writes it (cuckoo_hashtable_op.cc:310-392: the
+  # table's dump -- here the REFERENCE ENGINE's own iteration order, from the oracle -- as raw little-endian int64 keys
+  # and raw rows) loads into our table: same content, whatever the order.
+  ref = O.best_table(dim)
+  ref.insert(k, v)
+  rk, rv = ref.export()
+  rk.astype("<i8").tofile(str(tmp_path / "refckpt-keys"))
+  rv.astype("<f4").tofile(str(tmp_path / "refckpt-values"))
+  d = de.CuckooHashTable(torch.int64, torch.float32, [0.0] * dim, name="td")
+  d.load_from_file_system(str(tmp_path), file_name="refckpt", dirpath_env="__unset__")
+  assert int(d.size()) == n
+  kd, vd = d.export()
+  od = torch.argsort(kd)
+  np.testing.assert_array_equal(kd[od].cpu().numpy(), np.sort(k))
+  np.testing.assert_array_equal(vd[od].cpu().numpy(), v[np.argsort(k)])
+  # import / export of 168 keys (cuckoo_hashtable_ops_test.py:76-99)
   c = de.CuckooHashTable(torch.int64, torch.float32, [0.0] * dim, name="tc")
   c.import_(torch.from_numpy(k[:168]), torch.from_numpy(v[:168]))  # :76-99 import/export of 168 keys
   kc, vc = c.export()
