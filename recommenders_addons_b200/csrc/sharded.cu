@@ -83,8 +83,10 @@ peer_find_kernel(PeerViews pv, const long long* __restrict__ keys, size_t n,
 }
 
 // K8b: sharded Insert -- find-or-claim in the owner's key plane (system-scope CAS), row stored to the owner's HBM
-template <int VEC>
-__global__ void __launch_bounds__(kThreadsP)
+// MINB: resident CTAs per SM the register budget is capped for (1 = uncapped: 83 registers, 3 CTAs/SM; 4 caps at 64
+// registers -- more remote probes in flight per SM; DET_PEER_MINB selects, A/B in profiles/)
+template <int VEC, int MINB = 1>
+__global__ void __launch_bounds__(kThreadsP, MINB)
 peer_insert_kernel(PeerViews pv, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
                    size_t n, RowGeom g, int n_slot_planes) {
   __shared__ unsigned s_new[kMaxPeers], s_used[kMaxPeers];
@@ -1373,10 +1375,19 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
   }
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
-  const int grid = grid_for(n, kThreadsP, g->sm_count, occupancy_of(peer_insert_kernel<16>, kThreadsP));
+  static const int minb = env_int("DET_PEER_MINB", 1);
   const unsigned char* v = (const unsigned char*)values;
   const long long* k = (const long long*)keys;
   const int np = g->n_slot_planes;
+  if (vec == 16 && minb >= 4) {
+    const auto kern = peer_insert_kernel<16, 4>;
+    const int grid4 = grid_for(n, kThreadsP, g->sm_count, occupancy_of(kern, kThreadsP));
+    DET_LAUNCH(kern, grid4, kThreadsP, 0, s, g->pv, k, v, n, geo, np);
+    CUDA_TRY(cudaGetLastError());
+    peer_snapshot(g, s);
+    return DET_OK;
+  }
+  const int grid = grid_for(n, kThreadsP, g->sm_count, occupancy_of(peer_insert_kernel<16>, kThreadsP));
   switch (vec) {
     case 16: DET_LAUNCH(peer_insert_kernel<16>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
     case 8: DET_LAUNCH(peer_insert_kernel<8>, grid, kThreadsP, 0, s, g->pv, k, v, n, geo, np); break;
