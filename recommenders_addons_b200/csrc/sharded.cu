@@ -83,8 +83,8 @@ peer_find_kernel(PeerViews pv, const long long* __restrict__ keys, size_t n,
 }
 
 // K8b: sharded Insert -- find-or-claim in the owner's key plane (system-scope CAS), row stored to the owner's HBM
-// MINB: resident CTAs per SM the register budget is capped for (1 = uncapped: 83 registers, 3 CTAs/SM; 4 caps at 64
-// registers -- more remote probes in flight per SM; DET_PEER_MINB selects, A/B in profiles/)
+// MINB: resident CTAs per SM the register budget is capped for (1 = uncapped: 83 registers, 3 CTAs/SM; 4 = the default:
+// 64 registers -- more remote probes in flight per SM; DET_PEER_MINB selects)
 template <int VEC, int MINB = 1>
 __global__ void __launch_bounds__(kThreadsP, MINB)
 peer_insert_kernel(PeerViews pv, const long long* __restrict__ keys, const unsigned char* __restrict__ values,
@@ -1375,7 +1375,8 @@ det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* v
   }
   const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
   const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
-  static const int minb = env_int("DET_PEER_MINB", 1);
+  // measured at N=2 (profiles/r02_bench_n2_hybrid_minb{1,4}_call11.json): 0.282 vs 0.291 ms per insert with the cap
+  static const int minb = env_int("DET_PEER_MINB", 4);
   const unsigned char* v = (const unsigned char*)values;
   const long long* k = (const long long*)keys;
   const int np = g->n_slot_planes;
