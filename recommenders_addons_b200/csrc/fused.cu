@@ -139,6 +139,24 @@ __global__ void unique_flag_kernel(UniqueWs w, size_t n, const long long* __rest
   w.flags[i] = (first == (unsigned)i) ? 1u : 0u;
 }
 
+// unique_flag_kernel + scan_block_sums_kernel in one pass: flag of every position and the flag count of its block
+__global__ void __launch_bounds__(kScanBlock)
+unique_flag_sums_kernel(UniqueWs w, size_t n, const long long* __restrict__ n_dev) {
+  if (n_dev) n = (size_t)*n_dev;
+  __shared__ unsigned s_warp[33];
+  const size_t i = (size_t)blockIdx.x * kScanBlock + threadIdx.x;
+  unsigned f = 0u;
+  if (i < n) {
+    const unsigned s = w.myslot[i];
+    const unsigned first = (s == 0xffffffffu) ? w.special[0] : w.hmin[s];
+    f = (first == (unsigned)i) ? 1u : 0u;
+    w.flags[i] = f;
+  }
+  unsigned total;
+  block_exclusive_scan(f, s_warp, total);
+  if (threadIdx.x == 0) w.block_sums[blockIdx.x] = total;
+}
+
 // first occurrences: rank = exclusive scan; write unique_out[rank], remember rank in the hash slot
 __global__ void __launch_bounds__(kScanBlock)
 unique_rank_kernel(UniqueWs w, const long long* __restrict__ ids, size_t n, long long* __restrict__ unique_out,
@@ -193,14 +211,14 @@ static size_t unique_ws_layout(size_t n, unsigned char* base, UniqueWs* w) {
 // K6: fused embedding_lookup_sparse
 // ------------------------------------------------------------------------------------------------
 // seg_start[b] = first position i with segment_ids[i] >= b ; seg_start[batch] = nnz
-// not_identity (nullable, zeroed by the caller): set when some id i does not belong to row i -- with nnz == batch a zero
-// afterwards means "exactly one id per output row", the Criteo shape, which the find-shaped kernel below serves
+// run_if_set (nullable): the flag lookup_identity_kernel leaves behind -- zero means "exactly one id per output row was
+// verified and served", the Criteo shape; the general kernels then have nothing to do
 __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, size_t batch,
-                                       long long* __restrict__ seg_start, DevState* st, unsigned* not_identity) {
+                                       long long* __restrict__ seg_start, DevState* st, const unsigned* run_if_set) {
+  if (run_if_set && *run_if_set == 0u) return;   // one id per row, verified by lookup_identity_kernel: nothing to do
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nnz) return;
   const long long cur = i < nnz ? (long long)seg[i] : (long long)batch;
-  if (not_identity && i < nnz && cur != (long long)i) *not_identity = 1u;
   const long long prev = i > 0 ? (long long)seg[i - 1] : -1;
   if (cur < prev || cur < 0 || cur > (long long)batch || (i < nnz && cur >= (long long)batch)) {
     atomicOr(&st->error, kErrBadSegment);
@@ -231,13 +249,14 @@ resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz,
 
 // K6, one id per output row and no weights (every combiner then returns the row itself: 0 + row * 1, / 1): the call IS a
 // Find into the dense output, so it runs as one -- 32 rows per warp-step, 4 row loads in flight per lane, no slot
-// scratch and no per-row segment bookkeeping.  Launched on spec next to the general kernels: `not_identity` (written by
-// segment_offsets_kernel earlier on the stream) decides on the device which of the two does the work.
+// scratch and no per-row segment bookkeeping.  Launched on spec IN FRONT of the general kernels (nnz == batch, no weights):
+// it checks segment_ids[i] == i for the ids it serves and raises `not_identity` otherwise; the general kernels
+// (segment_offsets, resolve_slots, segment_sum) run only when the flag is set and then rewrite every output row.
 template <int VEC>
 __global__ void __launch_bounds__(kThreadsF)
-lookup_identity_kernel(TableView t, const long long* __restrict__ ids, size_t n, const unsigned char* __restrict__ default_row,
-                       unsigned char* __restrict__ out, RowGeom g, int use_tma, const unsigned* __restrict__ not_identity) {
-  if (*not_identity != 0u) return;
+lookup_identity_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ seg, size_t n,
+                       const unsigned char* __restrict__ default_row, unsigned char* __restrict__ out, RowGeom g, int use_tma,
+                       unsigned* __restrict__ not_identity) {
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
   __shared__ __align__(8) unsigned long long s_bar[kStages];
   const int lane = threadIdx.x & 31;
@@ -247,6 +266,8 @@ lookup_identity_kernel(TableView t, const long long* __restrict__ ids, size_t n,
     size_t i;
     bool valid;
     const long long key = kt.key(i, valid);
+    const bool off_row = valid && __ldg(seg + i) != (int)i;        // this id does not belong to output row i
+    if (__any_sync(kFull, off_row) && lane == 0) *not_identity = 1u;
     const long long slot = warp_find_slots<false>(t, key, valid, lane);
     const unsigned char* src = nullptr;
     unsigned char* dst = nullptr;
@@ -1442,8 +1463,7 @@ static det_status unique_run(const int64_t* ids, size_t n, int64_t* unique_out, 
   const int g256 = (int)((n + 255) / 256);
   DET_LAUNCH(unique_init_kernel, (int)((w.hcap + 1023) / 1024 < 4096 ? (w.hcap + 1023) / 1024 : 4096), 1024, 0, s, w);
   DET_LAUNCH(unique_insert_kernel, g256, 256, 0, s, w, (const long long*)ids, n, n_dev);
-  DET_LAUNCH(unique_flag_kernel, g256, 256, 0, s, w, n, n_dev);
-  DET_LAUNCH(scan_block_sums_kernel, (int)nblocks, kScanBlock, 0, s, w.flags, n, w.block_sums, n_dev);
+  DET_LAUNCH(unique_flag_sums_kernel, (int)nblocks, kScanBlock, 0, s, w, n, n_dev);
   DET_LAUNCH(scan_sums_kernel, 1, kScanBlock, 0, s, w.block_sums, nblocks, (long long*)n_unique_dev);
   DET_LAUNCH(unique_rank_kernel, (int)nblocks, kScanBlock, 0, s, w, (const long long*)ids, n, (long long*)unique_out, n_dev);
   DET_LAUNCH(unique_idx_kernel, g256, 256, 0, s, w, n, idx_out, n_dev);
@@ -1492,10 +1512,8 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
   const bool try_identity = nnz == batch && nnz > 0 && weights == nullptr && !(max_norm > 0.f) && vpr <= lpr && ivec >= 4 &&
                             env_int("DET_SEGSUM_STAGED", 0) == 0 && env_int("DET_SPARSE_IDENTITY", 1) != 0;
   const unsigned* gate = try_identity ? not_identity : nullptr;
-  if (try_identity) CUDA_TRY(cudaMemsetAsync(not_identity, 0, sizeof(unsigned), s));
-  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st,
-             try_identity ? not_identity : (unsigned*)nullptr);
   if (try_identity) {
+    CUDA_TRY(cudaMemsetAsync(not_identity, 0, sizeof(unsigned), s));
     const int vec = ivec;
     const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
     const int tma = (((uintptr_t)ids & 15u) == 0) ? 1 : 0;
@@ -1505,7 +1523,7 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
 #define DET_IDENT(VV)                                                                                              \
   case VV: {                                                                                                        \
     const int grid = grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(lookup_identity_kernel<VV>, kThreadsF));   \
-    DET_LAUNCH(lookup_identity_kernel<VV>, grid, kThreadsF, 0, s, t->view, k, nnz, d, o, g, tma, gate);             \
+    DET_LAUNCH(lookup_identity_kernel<VV>, grid, kThreadsF, 0, s, t->view, k, segment_ids, nnz, d, o, g, tma, not_identity); \
   } break;
     switch (vec) {
       DET_IDENT(16) DET_IDENT(8) DET_IDENT(4)
@@ -1513,6 +1531,7 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
     }
 #undef DET_IDENT
   }
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st, gate);
   if (nnz)
     DET_LAUNCH(resolve_slots_kernel, grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF, 0, s, t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0, gate);
   det_status rc = DET_OK;
@@ -1766,7 +1785,7 @@ det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st, (unsigned*)nullptr);
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st, (const unsigned*)nullptr);
   const long long* slots = (const long long*)row_idx;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out | (uintptr_t)rows) & 15u) == 0);
   unsigned vpr, lpr, sh;
