@@ -64,6 +64,81 @@ def fuzz_staged_segment_sum(cases):
   return bad
 
 
+def fuzz_lookup_one_id_per_row(cases):
+  """round 2: det_lookup_sparse with nnz == batch (identity / almost identity / weights): the device picks the find-shaped
+  kernel or the general pair; always bit-exact vs the oracle"""
+  from tests.test_fused_emu import F, P, Table, ck, real
+  rng0 = np.random.default_rng(4242)
+  bad = 0
+  for it in range(cases):
+    seed = int(rng0.integers(0, 2**31))
+    rng = np.random.default_rng(seed)
+    dim = int(rng.choice([1, 3, 4, 8, 16, 36, 64, 128, 200]))
+    batch = int(rng.integers(1, 1200))
+    t = Table(dim=dim, init=4096)
+    present = rng.choice(3000, size=1500, replace=False).astype(np.int64)
+    vals = rng.normal(0, 0.05, (1500, dim)).astype(np.float32)
+    t.insert(present, vals)
+    ot = O.PortTable(dim)
+    ot.insert(present, vals)
+    ids = rng.integers(0, 3000, size=batch).astype(np.int64)
+    seg = np.arange(batch, dtype=np.int32)
+    shape = int(rng.integers(0, 4))
+    if shape == 1 and batch > 3:           # same count, not identity: one row gets two ids, its neighbour none
+      j = int(rng.integers(1, batch))
+      seg[j] = seg[j - 1]
+    w = rng.uniform(0.25, 2.0, size=batch).astype(np.float32) if shape == 2 else None
+    combiner = str(rng.choice(["sum", "mean", "sqrtn"]))
+    default = np.full(dim, 0.25, np.float32)
+    out = np.full((batch, dim), np.nan, dtype=np.float32)
+    ck(F().det_lookup_sparse(t.h, P(ids), P(seg), P(w), batch, batch, real.COMBINERS[combiner], P(default), P(out), None))
+    exp = O.embedding_lookup_sparse(ot, ids, seg, w, batch, combiner, default=default)
+    if not np.array_equal(out, exp):
+      bad += 1
+      print("MISMATCH one-id-per-row lookup", seed, dim, batch, shape, combiner)
+    t.close()
+  print("det_lookup_sparse (nnz == batch):", cases, "cases, mismatches:", bad)
+  return bad
+
+
+def fuzz_apply_dup(cases):
+  """round 2: det_apply_adagrad_dup (unique -> position-order sum -> fused step, device-side count) vs the oracle chain"""
+  from tests.test_fused_emu import F, P, Table, ck, _export_sorted, sorted_export
+  rng0 = np.random.default_rng(9191)
+  bad = 0
+  for it in range(cases):
+    seed = int(rng0.integers(0, 2**31))
+    rng = np.random.default_rng(seed)
+    dim = int(rng.choice([4, 8, 16, 32, 64, 128]))
+    n = int(rng.integers(1, 4000))
+    vocab = int(rng.choice([3, 50, 700, 100000]))
+    t = Table(dim=dim, init=256, slot_planes=1)
+    p, a = O.PortTable(dim), O.PortTable(dim)
+    ip, ia = np.full(dim, 0.05, np.float32), np.full(dim, 0.1, np.float32)
+    wsb = F().det_apply_dup_workspace_bytes(n, dim)
+    raw = np.zeros(wsb + 256, np.uint8)
+    ws = raw[(-raw.ctypes.data) % 256:][:wsb]
+    ok = True
+    for step in range(2):
+      ids = (np.minimum(rng.zipf(1.2, size=n), vocab) if rng.integers(0, 2) else rng.integers(0, vocab, size=n)).astype(np.int64)
+      g = (rng.normal(0, 1e-2, (n, dim)) * np.exp(rng.uniform(-3, 3, (n, 1)))).astype(np.float32)
+      u, idx = O.unique_first_occurrence(ids)
+      O.sparse_adagrad_step(p, a, u, O.segment_reduce(g, idx, len(u)), 0.1, ip, ia, 0.0)
+      ck(F().det_apply_adagrad_dup(t.h, P(ids), P(g), n, 0.1, 0.0, P(ip), 0.1, P(ws), wsb, None, None))
+    for plane, ot in ((0, p), (1, a)):
+      k, v = _export_sorted(t, plane)
+      ek, ev = sorted_export(ot)
+      ok = ok and np.array_equal(k, ek) and np.array_equal(v, ev)
+    if not ok:
+      bad += 1
+      print("MISMATCH det_apply_adagrad_dup", seed, dim, n, vocab)
+    t.close()
+  print("det_apply_adagrad_dup:", cases, "cases, mismatches:", bad)
+  return bad
+
+
 if __name__ == "__main__":
   n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-  sys.exit(1 if fuzz_segment_reduce(n) + fuzz_staged_segment_sum(max(1, n * 5 // 8)) else 0)
+  sys.exit(1 if fuzz_segment_reduce(n) + fuzz_staged_segment_sum(max(1, n * 5 // 8)) + fuzz_lookup_one_id_per_row(max(1, n // 2)) +
+           fuzz_apply_dup(max(1, n // 4)) else 0)
+
