@@ -214,8 +214,9 @@ static size_t unique_ws_layout(size_t n, unsigned char* base, UniqueWs* w) {
 // run_if_set (nullable): the flag lookup_identity_kernel leaves behind -- zero means "exactly one id per output row was
 // verified and served", the Criteo shape; the general kernels then have nothing to do
 __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, size_t batch,
-                                       long long* __restrict__ seg_start, DevState* st, const unsigned* run_if_set) {
-  if (run_if_set && *run_if_set == 0u) return;   // one id per row, verified by lookup_identity_kernel: nothing to do
+                                       long long* __restrict__ seg_start, DevState* st, const unsigned* run_if_set,
+                                       unsigned epoch) {
+  if (run_if_set && *run_if_set != epoch) return;   // one id per row, verified by lookup_identity_kernel: nothing to do
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nnz) return;
   const long long cur = i < nnz ? (long long)seg[i] : (long long)batch;
@@ -231,8 +232,8 @@ __global__ void segment_offsets_kernel(const int* __restrict__ seg, size_t nnz, 
 // det_find; only 8 B per id leave the kernel (the [nnz, dim] gather of the reference is never materialised)
 __global__ void __launch_bounds__(kThreadsF)
 resolve_slots_kernel(TableView t, const long long* __restrict__ ids, size_t nnz, long long* __restrict__ slots,
-                     int use_tma, const unsigned* __restrict__ run_if_set) {
-  if (run_if_set && *run_if_set == 0u) return;   // the one-id-per-row kernel has served this call
+                     int use_tma, const unsigned* __restrict__ run_if_set, unsigned epoch) {
+  if (run_if_set && *run_if_set != epoch) return;   // the one-id-per-row kernel has served this call
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
   __shared__ __align__(8) unsigned long long s_bar[kStages];
   const int lane = threadIdx.x & 31;
@@ -256,7 +257,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreadsF)
 lookup_identity_kernel(TableView t, const long long* __restrict__ ids, const int* __restrict__ seg, size_t n,
                        const unsigned char* __restrict__ default_row, unsigned char* __restrict__ out, RowGeom g, int use_tma,
-                       unsigned* __restrict__ not_identity) {
+                       unsigned* __restrict__ not_identity, unsigned epoch) {
   __shared__ __align__(128) long long s_keys[kStages][kTileKeys];
   __shared__ __align__(8) unsigned long long s_bar[kStages];
   const int lane = threadIdx.x & 31;
@@ -267,7 +268,7 @@ lookup_identity_kernel(TableView t, const long long* __restrict__ ids, const int
     bool valid;
     const long long key = kt.key(i, valid);
     const bool off_row = valid && __ldg(seg + i) != (int)i;        // this id does not belong to output row i
-    if (__any_sync(kFull, off_row) && lane == 0) *not_identity = 1u;
+    if (__any_sync(kFull, off_row) && lane == 0) *not_identity = epoch;   // "raised in THIS call": the flag is never reset
     const long long slot = warp_find_slots<false>(t, key, valid, lane);
     const unsigned char* src = nullptr;
     unsigned char* dst = nullptr;
@@ -326,8 +327,8 @@ __global__ void __launch_bounds__(kThreadsF, DET_SEG_MINB)
 segment_sum_kernel(TableView t, const long long* __restrict__ slots, const long long* __restrict__ seg_start,
                    const float* __restrict__ weights, size_t batch, int combiner,
                    const float* __restrict__ default_row, float* __restrict__ out, unsigned vpr, unsigned lpr,
-                   unsigned lpr_shift, ClipArg<CLIP> clip, const unsigned* __restrict__ run_if_set) {
-  if (run_if_set && *run_if_set == 0u) return;   // the one-id-per-row kernel has served this call
+                   unsigned lpr_shift, ClipArg<CLIP> clip, const unsigned* __restrict__ run_if_set, unsigned epoch) {
+  if (run_if_set && *run_if_set != epoch) return;   // the one-id-per-row kernel has served this call
   constexpr int U = kSegPerGroup;
   const int lane = threadIdx.x & 31;
   const unsigned gl = (unsigned)lane & (lpr - 1u);
@@ -1188,9 +1189,10 @@ radix_scatter_kernel(const int* __restrict__ idx, const unsigned* __restrict__ k
 // `ngd` (nullable): the group count lives on the device (det_apply_*_dup: n_unique of det_unique, never read by the host)
 __global__ void group_starts_kernel(const unsigned* __restrict__ keys, size_t n, unsigned n_groups,
                                     unsigned* __restrict__ starts, const long long* __restrict__ ngd,
-                                    const long long* __restrict__ n_dev) {
+                                    const long long* __restrict__ n_dev, unsigned* __restrict__ ctr) {
   if (ngd) n_groups = (unsigned)*ngd;
   if (n_dev) n = (size_t)*n_dev;
+  if (blockIdx.x == 0 && threadIdx.x < 4) ctr[threadIdx.x] = 0u;   // work-list counters of the next two kernels (no memset launch)
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j > n) return;
   const long long cur = j < n ? (long long)keys[j] : (long long)n_groups;
@@ -1512,8 +1514,16 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
   const bool try_identity = nnz == batch && nnz > 0 && weights == nullptr && !(max_norm > 0.f) && vpr <= lpr && ivec >= 4 &&
                             env_int("DET_SEGSUM_STAGED", 0) == 0 && env_int("DET_SPARSE_IDENTITY", 1) != 0;
   const unsigned* gate = try_identity ? not_identity : nullptr;
+  // the flag word is compared with a per-table call counter instead of being reset by a memset launch per call
+  unsigned epoch = 0;
   if (try_identity) {
-    CUDA_TRY(cudaMemsetAsync(not_identity, 0, sizeof(unsigned), s));
+    if (t->sparse_flag != (void*)not_identity) {     // scratch (re)allocated: unknown content, clear it once
+      CUDA_TRY(cudaMemsetAsync(not_identity, 0, sizeof(unsigned), s));
+      t->sparse_flag = (void*)not_identity;
+      t->sparse_epoch = 0;
+    }
+    epoch = ++t->sparse_epoch;
+    if (epoch == 0) epoch = ++t->sparse_epoch;
     const int vec = ivec;
     const RowGeom g = make_geom((unsigned)t->row_bytes, vec);
     const int tma = (((uintptr_t)ids & 15u) == 0) ? 1 : 0;
@@ -1523,7 +1533,7 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
 #define DET_IDENT(VV)                                                                                              \
   case VV: {                                                                                                        \
     const int grid = grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(lookup_identity_kernel<VV>, kThreadsF));   \
-    DET_LAUNCH(lookup_identity_kernel<VV>, grid, kThreadsF, 0, s, t->view, k, segment_ids, nnz, d, o, g, tma, not_identity); \
+    DET_LAUNCH(lookup_identity_kernel<VV>, grid, kThreadsF, 0, s, t->view, k, segment_ids, nnz, d, o, g, tma, not_identity, epoch); \
   } break;
     switch (vec) {
       DET_IDENT(16) DET_IDENT(8) DET_IDENT(4)
@@ -1531,9 +1541,9 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
     }
 #undef DET_IDENT
   }
-  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st, gate);
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, t->view.st, gate, epoch);
   if (nnz)
-    DET_LAUNCH(resolve_slots_kernel, grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF, 0, s, t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0, gate);
+    DET_LAUNCH(resolve_slots_kernel, grid_for(nnz, kTileKeys, t->sm_count, occupancy_of(resolve_slots_kernel, kThreadsF)), kThreadsF, 0, s, t->view, (const long long*)ids, nnz, slots, (((uintptr_t)ids & 15u) == 0) ? 1 : 0, gate, epoch);
   det_status rc = DET_OK;
   const unsigned gpw = 32u >> sh;
   if (vpr <= lpr && max_norm > 0.f) {
@@ -1544,9 +1554,9 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
     const int occ = vec4 ? occupancy_of(k4, kThreadsF) : occupancy_of(k1, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
-      DET_LAUNCH(k4, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip, (const unsigned*)nullptr);
+      DET_LAUNCH(k4, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip, (const unsigned*)nullptr, 0u);
     else
-      DET_LAUNCH(k1, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip, (const unsigned*)nullptr);
+      DET_LAUNCH(k1, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, clip, (const unsigned*)nullptr, 0u);
   } else if (max_norm > 0.f) {
     rc = fail(DET_UNIMPLEMENTED, "det_lookup_sparse_clip: max_norm is fused for rows of at most 32 vectors (dim <= 128 when "
                                  "dim % 4 == 0, else dim <= 32); use the composed path for wider rows");
@@ -1566,9 +1576,9 @@ static det_status lookup_sparse_impl(det_table* t, const int64_t* ids, const int
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), t->sm_count, occ);
     if (vec4)
-      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, gate);
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, gate, epoch);
     else
-      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, gate);
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, t->view, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, gate, epoch);
   } else if ((vpr + lpr - 1) / lpr <= (unsigned)kMaxVecPerLane) {
     const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), t->sm_count, 8);
     if (vec4)
@@ -1785,7 +1795,7 @@ det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st, (const unsigned*)nullptr);
+  DET_LAUNCH(segment_offsets_kernel, (int)((nnz + 1 + 255) / 256), 256, 0, s, segment_ids, nnz, batch, seg_start, st, (const unsigned*)nullptr, 0u);
   const long long* slots = (const long long*)row_idx;
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)default_row | (uintptr_t)out | (uintptr_t)rows) & 15u) == 0);
   unsigned vpr, lpr, sh;
@@ -1806,9 +1816,9 @@ det_status det_sparse_segment_sum(const float* rows, size_t dim, const int64_t* 
     const int occ = vec4 ? occupancy_of(segment_sum_kernel<4>, kThreadsF) : occupancy_of(segment_sum_kernel<1>, kThreadsF);
     const int grid = grid_for(batch, (int)(gpw * kSegPerGroup * (kThreadsF / 32)), sms, occ);
     if (vec4)
-      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, (const unsigned*)nullptr);
+      DET_LAUNCH(segment_sum_kernel<4>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, (const unsigned*)nullptr, 0u);
     else
-      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, (const unsigned*)nullptr);
+      DET_LAUNCH(segment_sum_kernel<1>, grid, kThreadsF, 0, s, v, slots, seg_start, weights, batch, combiner, default_row, out, vpr, lpr, sh, noclip, (const unsigned*)nullptr, 0u);
   } else {
     const int grid = grid_for(batch, (int)(gpw * (kThreadsF / 32)), sms, 8);
     if (vec4)
@@ -1859,14 +1869,13 @@ static det_status seg_reduce_run(const float* rows, const int32_t* idx, size_t n
     kout = (kout == w.keys_a) ? w.keys_b : w.keys_a;
     pout = (pout == w.pos_a) ? w.pos_b : w.pos_a;
   }
-  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts, ngd, n_dev);
+  DET_LAUNCH(group_starts_kernel, (int)((n + 1 + 255) / 256), 256, 0, s, kin, n, ng, w.starts, ngd, n_dev, w.n_long);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool vec4 = (dim % 4 == 0) && ((((uintptr_t)rows | (uintptr_t)out) & 15u) == 0);
   // rows that can be cut into 16-column slices (the double-buffered cp.async staging moves 16 B vectors)
   const int sliceable = (vec4 && dim % kSliceCols == 0 && dim > (size_t)kSliceCols) ? 1 : 0;
-  CUDA_TRY(cudaMemsetAsync(w.n_long, 0, 4 * sizeof(unsigned), s));   // long count, huge count, queue cursor
   DET_LAUNCH(group_long_kernel, (int)((n_groups + 255) / 256), 256, 0, s, w.starts, ng, sliceable, w.long_list, w.huge_list,
              w.n_long, ngd);
   unsigned vpr, lpr, sh;

@@ -131,6 +131,8 @@ struct det_table {
   unsigned long long* peer_bar = nullptr;  // arrival flags of the NVLink peer barrier (sharded.cu)
   det::EvictState* ev = nullptr;     // non-null: the table has an eviction strategy (evict.cu)
   uint64_t last_used_snap = 0;       // last exact value of DevState::used the host has seen (snapshot or sync read)
+  void* sparse_flag = nullptr;       // det_lookup_sparse: where the one-id-per-row flag word lives (scratch may move)
+  unsigned sparse_epoch = 0;         // ... and the call counter it is compared with
 };
 
 namespace det {
