@@ -864,7 +864,7 @@ def gpu_arm(args):
       line["c3"] = {"error": repr(ex)}
   if world == 1 and not args.no_cpu_baseline:
     try:
-      cb = cpu_arm(dim, args.cpu_resident, B, steps=7, warmup=3, threads=args.cpu_threads, want_resident=args.resident)
+      cb = cpu_arm(dim, args.cpu_resident, B, steps=15, warmup=3, threads=args.cpu_threads, want_resident=args.resident)
       cb.pop("ms_per_step", None)
       line["cpu_baseline"] = cb
     except Exception as ex:  # the checker is optional for the bench line; never hide the GPU number
