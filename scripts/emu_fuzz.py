@@ -137,8 +137,134 @@ def fuzz_apply_dup(cases):
   return bad
 
 
+def fuzz_owner_side_exchange(cases):
+  """round 2: det_peer_xchg_find / _insert / _apply_adagrad with threads as ranks: random world (2..4), random batch sizes
+  per rank and call (incl. 0), random interleaving of lookups, inserts and sharded optimizer steps -- the SAME sequence on
+  every rank, as the collective contract demands -- against a dict model; shard sizes and error flags at the end."""
+  import ctypes
+  import threading
+  from tests.test_host_peer_emu import X, P, PeerGroup, Table, ck
+  rng0 = np.random.default_rng(31337)
+  bad = 0
+  for it in range(cases):
+    seed = int(rng0.integers(0, 2**31))
+    rng = np.random.default_rng(seed)
+    world = int(rng.integers(2, 5))
+    dim = int(rng.choice([4, 16, 64]))
+    cap = 384
+    n_ops = int(rng.integers(3, 8))
+    pool = rng.choice(1 << 40, size=1500, replace=False).astype(np.int64)
+    tables = [Table(dim=dim, init=8192, max_capacity=8192, slot_planes=1) for _ in range(world)]
+    hb = X().det_peer_handle_bytes()
+    blob = (ctypes.c_ubyte * (hb * world))()
+    for r in range(world):
+      ck(X().det_peer_export(tables[r].h, ctypes.c_void_p(ctypes.addressof(blob) + r * hb)))
+    rb = dim * 4
+    nbytes = X().det_peer_xchg_bytes(world, cap, rb)
+    raw = [np.zeros(nbytes + 256, dtype=np.uint8) for _ in range(world)]
+    boxes = [b[(-b.ctypes.data) % 256:][:nbytes] for b in raw]
+    ip = np.full(dim, 0.05, np.float32)
+    # the schedule (known to all ranks): op kind + per-rank inputs
+    sched = []
+    for _ in range(n_ops):
+      kind = str(rng.choice(["insert", "find", "apply"]))
+      per = []
+      for r in range(world):
+        m = int(rng.integers(0, cap + 1)) if rng.random() > 0.15 else 0
+        if kind == "insert":   # a key is written by at most one rank per op (the contract of unique keys per call + no races)
+          ks = pool[r::world]
+          k = np.ascontiguousarray(rng.choice(ks, size=min(m, len(ks)), replace=False))
+          per.append((k, rng.standard_normal((len(k), dim)).astype(np.float32)))
+        elif kind == "find":
+          k = np.ascontiguousarray(np.concatenate([rng.choice(pool, size=m, replace=False), np.array([-7 - r], np.int64)])) if m else np.zeros(0, np.int64)
+          per.append((k, None))
+        else:
+          k = np.ascontiguousarray(rng.choice(pool, size=m, replace=False))
+          per.append((k, rng.normal(0, 1e-2, (m, dim)).astype(np.float32)))
+      sched.append((kind, per))
+    # sequential model: params + accumulators per key
+    owner = O.default_partition_fn(pool, world, True)
+    errors, finds = [], {}
+    start = threading.Barrier(world)
+
+    def rank_main(r):
+      try:
+        tl = [None] * world
+        tl[r] = tables[r]
+        g = PeerGroup(tl, ctypes.cast(blob, ctypes.c_void_p), world, r)
+        ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boxes])
+        ck(X().det_peer_xchg_attach(g.g, ptrs, cap, rb))
+        wsb = X().det_peer_xchg_apply_workspace_bytes(g.g)
+        wraw = np.zeros(wsb + 256, np.uint8)
+        ws = wraw[(-wraw.ctypes.data) % 256:][:wsb]
+        start.wait()
+        for t, (kind, per) in enumerate(sched):
+          k, v = per[r]
+          n = len(k)
+          if kind == "insert":
+            ck(X().det_peer_xchg_insert(g.g, P(k) if n else None, P(v) if n else None, n, None))
+          elif kind == "find":
+            out = np.full((max(n, 1), dim), np.nan, np.float32)
+            ex = np.zeros(max(n, 1), np.uint8)
+            ck(X().det_peer_xchg_find(g.g, P(k) if n else None, n, P(ip), 0, P(out), P(ex), None, None))
+            finds[(t, r)] = (out[:n].copy(), ex[:n].copy())
+          else:
+            ck(X().det_peer_xchg_apply_adagrad(g.g, P(k) if n else None, P(v) if n else None, n, 0.1, 0.0, P(ip), 0.1, P(ws), wsb, None))
+        g.close()
+      except BaseException:
+        import traceback
+        errors.append((r, traceback.format_exc()))
+        try:
+          start.abort()
+        except Exception:
+          pass
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for x in th:
+      x.start()
+    for x in th:
+      x.join(timeout=600)
+    ok = not errors
+    if ok:
+      par, acc = {}, {}
+      f32 = np.float32
+      for t, (kind, per) in enumerate(sched):
+        if kind == "insert":
+          for r in range(world):
+            for kk, row in zip(per[r][0].tolist(), per[r][1]):
+              par[kk] = row.copy()        # insert leaves the optimizer slot of an existing key alone, a new key has none
+        elif kind == "find":
+          for r in range(world):
+            out, ex = finds[(t, r)]
+            for j, kk in enumerate(per[r][0].tolist()):
+              exp = par.get(kk)
+              if (exp is None) != (ex[j] == 0) or not np.array_equal(out[j], ip if exp is None else exp):
+                ok = False
+        else:
+          gsum = {}
+          for r in range(world):           # summed on the owner in source-rank order
+            for kk, row in zip(per[r][0].tolist(), per[r][1]):
+              gsum[kk] = row.copy() if kk not in gsum else (gsum[kk] + row).astype(f32)
+          for kk, gg in gsum.items():
+            p0 = par.get(kk, ip).astype(f32)
+            a0 = acc.get(kk, np.full(dim, 0.1, f32))
+            a1 = (a0 + gg * gg).astype(f32)
+            par[kk] = (p0 - (f32(0.1) * gg) / np.sqrt(a1)).astype(f32)
+            acc[kk] = a1
+      for o in range(world):
+        mine = {kk for kk in par if O.default_partition_fn(np.array([kk]), world, True)[0] == o}
+        ok = ok and tables[o].size() == len(mine) and tables[o].stats()["error_flags"] == 0
+    if not ok:
+      bad += 1
+      print("MISMATCH owner-side exchange", seed, world, dim, [k for k, _ in sched], errors[:1])
+    for t in tables:
+      t.close()
+  print("det_peer_xchg_* (threads as ranks):", cases, "cases, mismatches:", bad)
+  return bad
+
+
 if __name__ == "__main__":
   n = int(sys.argv[1]) if len(sys.argv) > 1 else 400
   sys.exit(1 if fuzz_segment_reduce(n) + fuzz_staged_segment_sum(max(1, n * 5 // 8)) + fuzz_lookup_one_id_per_row(max(1, n // 2)) +
-           fuzz_apply_dup(max(1, n // 4)) else 0)
+           fuzz_apply_dup(max(1, n // 4)) + fuzz_owner_side_exchange(max(1, n // 10)) else 0)
 
