@@ -647,12 +647,25 @@ static void xchg_time_collect(det_peer_group* g, int which, int n_iv);
 }
 
 
+// A shard that peers write one-sidedly must not have an eviction strategy: a remote claim would bypass the owner's score
+// plane and its eviction at max_capacity (evict.cu).  Sharded tables WITH eviction run on the collective exchange
+// (ShardedVariable: keys travel to the owner, which calls its own det_insert / det_apply_* with eviction).
+static det_status peer_reject_evicting(const det_table* t, const char* who) {
+  if (t && t->ev) {
+    std::string m = std::string(who) + ": a table with an eviction strategy cannot be published to peers "
+                    "(use the collective exchange, ShardedVariable, for sharded tables with eviction)";
+    return fail(DET_INVALID_ARGUMENT, m.c_str());
+  }
+  return DET_OK;
+}
+
 extern "C" {
 
 size_t det_peer_handle_bytes(void) { return sizeof(PeerBlob); }
 
 det_status det_peer_export(det_table* t, void* blob_out) {
   if (!t || !blob_out) return fail(DET_INVALID_ARGUMENT, "det_peer_export: null argument");
+  if (det_status e = peer_reject_evicting(t, "det_peer_export")) return e;
   det::DevGuard _dg(t->cfg.device);
   PeerBlob b;
   memset(&b, 0, sizeof(b));
@@ -717,6 +730,8 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
     return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: world must be in [1,8] and rank in [0,world)");
   det_table* local = tables[rank];
   if (!local) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: tables[rank] must be the local shard");
+  for (int p = 0; p < world; ++p)
+    if (det_status e = peer_reject_evicting(tables[p], "det_peer_group_create")) return e;
   det::DevGuard _dg(local->cfg.device);
   det_peer_group* g = new det_peer_group();
   memset(g->opened, 0, sizeof(g->opened));
@@ -804,6 +819,7 @@ det_status det_peer_group_create_regions(det_peer_group** out, det_table* local,
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
     return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: world must be in [1,8] and rank in [0,world)");
   if (!local->external) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: the local shard must live in a region");
+  if (det_status e = peer_reject_evicting(local, "det_peer_group_create_regions")) return e;
   det::DevGuard _dg(local->cfg.device);
   det_peer_group* g = new det_peer_group();
   memset(g->opened, 0, sizeof(g->opened));

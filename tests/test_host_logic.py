@@ -226,6 +226,95 @@ def test_sharded_backward_routes_and_combines_world2_gloo():
   assert sum(n for _, _, n in res) == 40
 
 
+def _score_of(keys):
+  return keys * 3 + 11          # CUSTOMIZED: one distinct score per key, so which keys an event evicts is fully determined
+
+
+def _worker_evict(rank, world, port, q):
+  """sharded table WITH eviction = the collective exchange over a local shard that has an eviction strategy (the reference:
+  every Horovod rank owns one HkvHashTable, shadow_embedding_ops.py:397-447 over hkv_hashtable_ops.py).  The local shard
+  is the real engine on the emulator; its twin is a second, unsharded table fed with exactly what the owner receives."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from tests.emu import backend
+  with backend.installed():
+    from recommenders_addons_b200 import dynamic_embedding as de
+    from recommenders_addons_b200.dynamic_embedding.sharded import ShardedVariable
+    dim, cap = 4, 512
+
+    def shard(name):
+      cfg = de.HkvHashTableConfig(init_capacity=cap, max_capacity=cap, evict_strategy=de.HkvEvictStrategy.CUSTOMIZED,
+                                  gen_scores_fn=_score_of)
+      return de.get_variable(name, key_dtype=torch.int64, value_dtype=torch.float32, devices=["cpu"], initializer=0.0,
+                             dim=dim, init_size=cap, kv_creator=de.HkvHashTableCreator(config=cfg))
+
+    local, twin = shard("evict_shard_%d" % rank), shard("evict_twin_%d" % rank)
+    sv = ShardedVariable(local, partition_impl=_cpu_partition(world),
+                         gather_impl=lambda rows, perm: rows[perm.long()],
+                         scatter_impl=lambda rows, perm: torch.empty_like(rows).index_copy_(0, perm.long(), rows),
+                         unique_impl=_cpu_unique)
+    streams = []
+    for step in range(6):                                   # 6 x 2 x 300 distinct keys >> 2 x 512 slots
+      per_rank = [torch.arange(300, dtype=torch.int64) * 2 + r + 600 * step for r in range(world)]
+      streams.append(per_rank)
+    for per_rank in streams:
+      keys = per_rank[rank]
+      sv.upsert(keys, keys.float().reshape(-1, 1).repeat(1, dim))
+      # what this owner received, in source-rank order (exchange_keys concatenates by source)
+      got = torch.cat([k[torch.from_numpy(O.default_partition_fn(k.numpy(), world, True)).long() == rank] for k in per_rank])
+      twin.upsert(got, got.float().reshape(-1, 1).repeat(1, dim))
+    dist.barrier()
+    n_local = int(local.size())
+    lk, lv = local.export()
+    tk, _ = twin.export()
+    ok = n_local <= cap and sorted(lk.tolist()) == sorted(tk.tolist())
+    ok = ok and bool((lv[:, 0] == lk.float()).all())                      # rows of the survivors are intact
+    ok = ok and bool((torch.from_numpy(O.default_partition_fn(lk.numpy(), world, True)) == rank).all())
+    # the survivors are the highest-scored keys this owner ever received
+    seen = torch.cat([k for per_rank in streams for k in per_rank])
+    mine = seen[torch.from_numpy(O.default_partition_fn(seen.numpy(), world, True)).long() == rank]
+    ok = ok and sorted(lk.tolist()) == sorted(mine.tolist())[-n_local:]
+    ok = ok and local.tables[0].stats()["evict_events"] > 0
+    # a lookup through the exchange: survivors come back with their rows, evicted keys with the default (0)
+    probe = torch.cat([seen[-50:], seen[:50]])
+    rows = sv.lookup(probe)
+    total = int(sv.size())
+    alive = torch.isin(probe, torch.cat([lk, torch.tensor(q_peer(rank, world, lk), dtype=torch.int64)]))
+    ok = ok and bool((rows[alive][:, 0] == probe[alive].float()).all()) and bool((rows[~alive] == 0).all())
+    q.put((rank, ok, n_local, total))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def q_peer(rank, world, my_keys):
+  """keys alive on the OTHER rank, exchanged with an all-gather of padded key lists"""
+  n = torch.tensor([len(my_keys)])
+  sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+  dist.all_gather(sizes, n)
+  m = int(max(int(s) for s in sizes))
+  pad = torch.full((m,), -1, dtype=torch.int64)
+  pad[:len(my_keys)] = my_keys
+  bufs = [torch.empty(m, dtype=torch.int64) for _ in range(world)]
+  dist.all_gather(bufs, pad)
+  return [k for r in range(world) if r != rank for k in bufs[r][:int(sizes[r])].tolist()]
+
+
+def test_sharded_table_with_eviction_world2_gloo():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 30100 + (os.getpid() % 150)
+  procs = [ctx.Process(target=_worker_evict, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=600) for _ in range(2)]
+  for p in procs:
+    p.join(timeout=120)
+    assert p.exitcode == 0
+  assert all(r[1] for r in res), res
+  assert all(r[2] <= 512 for r in res) and res[0][3] == res[1][3] == sum(r[2] for r in res)
+
+
 def test_math_and_data_flow_mirrors():
   """de.math / de.data_flow (python/ops/math_ops.py:60-215, data_flow_ops.py:40-61): the doc examples of the TF ops
   they stand for"""

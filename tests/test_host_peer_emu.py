@@ -511,3 +511,17 @@ def test_bounded_table_reserve_clear_import_and_load(tmp_path):
   assert 0 < t.size() <= 1 << 13
   t.check()
   t.close()
+
+
+def test_peer_publish_rejects_a_table_with_an_eviction_strategy():
+  """a remote one-sided claim would bypass the owner's score plane and its eviction at max_capacity: publishing such a
+  shard fails loudly (sharded tables with eviction run on the collective exchange, tests/test_host_logic.py)."""
+  t = Table(dim=4, init=1024, max_capacity=1024, strategy=0)        # LRU
+  blob = (ctypes.c_ubyte * X().det_peer_handle_bytes())()
+  assert X().det_peer_export(t.h, blob) == 1                        # DET_INVALID_ARGUMENT
+  assert b"eviction strategy" in L().det_last_error()
+  tl = (ctypes.c_void_p * 1)(t.h)
+  g = ctypes.c_void_p()
+  assert X().det_peer_group_create(ctypes.byref(g), tl, None, 1, 0, 1) == 1
+  assert b"eviction strategy" in L().det_last_error()
+  t.close()
