@@ -34,6 +34,21 @@ def exchange_rows(rows, in_splits, out_splits, group=None):
   return out
 
 
+def agree_on(value, group=None, device=None, what="value"):
+  """COLLECTIVE.  Every rank must pass the same integer (mailbox / inbox capacities fix the segment offsets peers write
+  to, so a rank-local choice would misplace remote stores): MAX(v) == -MAX(-v) over the group, else ValueError on
+  every rank."""
+  value = int(value)
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return value
+  t = torch.tensor([value, -value], dtype=torch.int64, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+  hi, lo = int(t[0].item()), -int(t[1].item())
+  if hi != lo:
+    raise ValueError("%s differs between ranks (min %d, max %d, this rank %d): it must be agreed" % (what, lo, hi, value))
+  return value
+
+
 class ShardedVariable(object):
   """One shard of a key-hash-sharded variable per rank; lookups / updates take keys owned by ANY rank."""
 
@@ -277,6 +292,7 @@ class PeerShardedVariable(object):
       ptrs, self._xbox = [int(p) for p in mailbox_ptrs], keepalive
     elif self.backing == "symmetric-memory":
       import torch.distributed._symmetric_memory as symm_mem
+      agree_on(max_items, self._group, self.device, "attach_exchange: max_items")
       box = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
       box.zero_()
       hdl = symm_mem.rendezvous(box, self._group if self._group is not None else dist.group.WORLD)
@@ -355,6 +371,7 @@ class PeerShardedVariable(object):
     nbytes = int(self._lib.det_peer_inbox_bytes(self.world, int(max_items), rb))
     if self.backing == "symmetric-memory":
       import torch.distributed._symmetric_memory as symm_mem
+      agree_on(max_items, self._group, self.device, "attach_inbox: max_items")
       box = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
       box.zero_()
       hdl = symm_mem.rendezvous(box, self._group if self._group is not None else dist.group.WORLD)

@@ -226,6 +226,37 @@ def test_sharded_backward_routes_and_combines_world2_gloo():
   assert sum(n for _, _, n in res) == 40
 
 
+def _worker_agree(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from recommenders_addons_b200.dynamic_embedding.sharded import agree_on
+  ok = agree_on(4096, what="max_items") == 4096
+  try:
+    agree_on(4096 + rank, what="max_items")           # a rank-local choice: refused on EVERY rank
+    ok = False
+  except ValueError as e:
+    ok = ok and "min 4096, max 4097" in str(e)
+  q.put((rank, ok))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_mailbox_capacity_must_be_agreed_world2_gloo():
+  """attach_exchange / attach_inbox fix the segment offsets peers store to: every rank must pass the same capacity"""
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 30400 + (os.getpid() % 150)
+  procs = [ctx.Process(target=_worker_agree, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=120) for _ in range(2)]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert all(ok for _, ok in res), res
+
+
 def _score_of(keys):
   return keys * 3 + 11          # CUSTOMIZED: one distinct score per key, so which keys an event evicts is fully determined
 
