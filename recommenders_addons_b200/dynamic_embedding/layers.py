@@ -6,7 +6,7 @@ writes the update back with the fused find-or-insert + optimizer kernel."""
 import torch
 
 from .optimizer import ComposedOptimizer, _FusedBase
-from .sharded import PeerShardedVariable
+from .sharded import PeerShardedVariable, ShardedVariable
 from .variable import Variable, default_partition_fn, embedding_lookup_unique, gather_unique, unique
 
 
@@ -109,11 +109,16 @@ class FieldWiseEmbedding(Embedding):
 class AllToAllEmbedding(torch.nn.Module):
   """HvdAllToAllEmbedding (embedding.py:545-595) over the one-sided sharded table: ids owned by ANY rank.
   forward: unique -> det_peer_find -> gather; apply_gradients: per-unique gradients routed to their owners
-  (det_peer_route), combined and stepped there."""
+  (det_peer_route), combined and stepped there.
+
+  With a `kv_creator` whose config has an eviction strategy (the reference's HkvHashTableCreator) every rank owns an
+  ordinary, evicting HkvHashTable and the layer runs on the COLLECTIVE exchange (ShardedVariable: all-to-all of ids,
+  owner-side find / fused step, all-to-all of rows back) -- a shard peers write one-sidedly cannot evict."""
 
   def __init__(self, embedding_size, capacity_per_shard=None, group=None, initializer=None, name="AllToAllEmbedding",
                num_slot_planes=2, with_unique=True, with_secondary_unique=True, mpi_size=None, batch_size=None,
-               key_dtype=torch.int64, value_dtype=torch.float32, init_capacity=0, **kwargs):
+               key_dtype=torch.int64, value_dtype=torch.float32, init_capacity=0, kv_creator=None, devices=None,
+               exchange_impls=None, **kwargs):
     """The reference's arguments (embedding.py:545-563: with_unique, with_secondary_unique, mpi_size, batch_size and the
     base layer's) are accepted; the world size comes from `group`, lookups always dedupe once (unique -> one-sided
     find), and a published shard has a FIXED capacity: capacity_per_shard (default: init_capacity, else 1M slots)."""
@@ -123,8 +128,21 @@ class AllToAllEmbedding(torch.nn.Module):
     self.embedding_size = int(embedding_size)
     self.with_unique, self.with_secondary_unique, self.batch_size = with_unique, with_secondary_unique, batch_size
     capacity_per_shard = int(capacity_per_shard or init_capacity or (1 << 20))
-    self.params = PeerShardedVariable.create(self.embedding_size, capacity_per_shard, group=group,
-                                             initializer=initializer, num_slot_planes=num_slot_planes, name=name)
+    evicting = getattr(getattr(kv_creator, "config", None), "evict_strategy", None) is not None
+    self.collective = kv_creator is not None
+    if self.collective:
+      # `exchange_impls` (tests): partition_impl / gather_impl / scatter_impl / unique_impl of ShardedVariable
+      local = Variable(key_dtype=key_dtype, value_dtype=value_dtype, dim=self.embedding_size, devices=devices, name=name,
+                       initializer=initializer, init_size=capacity_per_shard, kv_creator=kv_creator,
+                       num_slot_planes=num_slot_planes)
+      if len(local.tables) != 1:
+        raise ValueError("AllToAllEmbedding: one local shard per rank (devices must name one device)")
+      self.params = ShardedVariable(local, group, **(exchange_impls or {}))
+      self.evicting = evicting
+    else:
+      self.evicting = False
+      self.params = PeerShardedVariable.create(self.embedding_size, capacity_per_shard, group=group,
+                                               initializer=initializer, num_slot_planes=num_slot_planes, name=name)
     self._pending = []
     self._inbox_items = 0
 
@@ -132,7 +150,8 @@ class AllToAllEmbedding(torch.nn.Module):
     flat = ids.reshape(-1)
     uniq, idx = unique(flat)
     rows = self.params.lookup(uniq).reshape(-1, self.embedding_size)
-    self.params.phase_barrier()
+    if not self.collective:
+      self.params.phase_barrier()
     rows = rows.detach().requires_grad_(self.training)
     if self.training:
       self._pending.append((uniq, rows))
@@ -145,6 +164,11 @@ class AllToAllEmbedding(torch.nn.Module):
     so a rank-local decision could hang the job or misplace remote writes.  A rank whose rows received no gradient
     routes zeros instead of skipping the exchange."""
     import torch.distributed as dist
+    if self.collective:           # the all-to-all sizes itself; a rank without gradients still takes part, with zeros
+      for uniq, rows in self._pending:
+        self.params.apply_gradients(optimizer, uniq, rows.grad if rows.grad is not None else torch.zeros_like(rows))
+      self._pending = []
+      return
     for uniq, rows in self._pending:
       grad = rows.grad if rows.grad is not None else torch.zeros_like(rows)
       if max_unique_per_rank is not None:

@@ -346,6 +346,87 @@ def test_sharded_table_with_eviction_world2_gloo():
   assert all(r[2] <= 512 for r in res) and res[0][3] == res[1][3] == sum(r[2] for r in res)
 
 
+def _worker_a2a_layer(rank, world, port, q):
+  """de.layers.AllToAllEmbedding with the reference's HkvHashTableCreator (an eviction strategy): the collective exchange
+  over one evicting HkvHashTable per rank (HvdAllToAllEmbedding over hkv tables, embedding.py:545-595)."""
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  import numpy as np
+  from tests.emu import backend
+  with backend.installed():
+    from recommenders_addons_b200 import dynamic_embedding as de
+    dim, cap, lr = 4, 512, 0.5
+    impls = dict(partition_impl=_cpu_partition(world), gather_impl=lambda rows, perm: rows[perm.long()],
+                 scatter_impl=lambda rows, perm: torch.empty_like(rows).index_copy_(0, perm.long(), rows),
+                 unique_impl=_cpu_unique)
+    cfg = de.HkvHashTableConfig(init_capacity=cap, max_capacity=cap, evict_strategy=de.HkvEvictStrategy.LFU)
+    layer = de.layers.AllToAllEmbedding(dim, cap, initializer=0.5, name="a2a_evict_%d" % rank, num_slot_planes=1,
+                                        kv_creator=de.HkvHashTableCreator(config=cfg), devices=["cpu"], exchange_impls=impls)
+    assert layer.collective and layer.evicting
+    opt = de.FusedAdagrad(lr, 0.1)
+    # phase 1 (no eviction yet): both ranks train overlapping ids; a sequential twin keeps params and accumulators
+    par, acc = {}, {}
+    f32 = np.float32
+    ok = True
+    for step in range(3):
+      ids_of = [torch.tensor([[1, 2, 3, 2], [7, 1, 9 + r, 40 + step]], dtype=torch.int64) for r in range(world)]
+      wts_of = [torch.tensor([[1., 2., -1., 4.], [2., 1., 1., -2.]]) * (r + 1) for r in range(world)]
+      out = layer(ids_of[rank])
+      exp = torch.tensor([[par.get(int(k), np.full(dim, 0.5, f32)) for k in row] for row in ids_of[rank].tolist()])
+      ok = ok and bool(torch.equal(out.detach(), exp))
+      (out * wts_of[rank].unsqueeze(-1)).sum().backward()
+      layer.apply_gradients(opt)
+      gsum = {}
+      for r in range(world):                       # the owner adds the ranks' per-unique gradients in source order
+        per = {}
+        for k, w in zip(ids_of[r].reshape(-1).tolist(), wts_of[r].reshape(-1).tolist()):
+          per[k] = f32(per.get(k, f32(0)) + f32(w))
+        for k, g in per.items():
+          gsum[k] = f32(gsum.get(k, f32(0)) + g)
+      for k, g in gsum.items():
+        gv = np.full(dim, g, f32)
+        a1 = (acc.get(k, np.full(dim, 0.1, f32)) + gv * gv).astype(f32)
+        par[k] = (par.get(k, np.full(dim, 0.5, f32)) - (f32(lr) * gv) / np.sqrt(a1)).astype(f32)
+        acc[k] = a1
+    probe = torch.tensor(sorted(par), dtype=torch.int64)
+    layer.eval()
+    got = layer(probe)
+    ok = ok and bool(torch.equal(got, torch.tensor(np.stack([par[int(k)] for k in probe.tolist()]))))
+    # phase 2: far more ids than 2 x 512 slots; the ids of phase 1 keep being trained (LFU keeps them)
+    layer.train()
+    hot = probe
+    for step in range(8):
+      cold = torch.arange(200, dtype=torch.int64) * world + rank + 1000 + 400 * step
+      out = layer(torch.cat([hot, cold]))
+      out.sum().backward()
+      layer.apply_gradients(opt)
+    local = layer.params.local
+    n_local = int(local.size())
+    ok = ok and n_local <= cap and local.tables[0].stats()["evict_events"] > 0
+    lk, _ = local.export()
+    mine_hot = hot[torch.from_numpy(O.default_partition_fn(hot.numpy(), world, True)).long() == rank]
+    ok = ok and bool(torch.isin(mine_hot, lk).all())
+    q.put((rank, ok, n_local, int(layer.params.size())))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_alltoall_embedding_with_an_evicting_kv_creator_world2_gloo():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 30700 + (os.getpid() % 150)
+  procs = [ctx.Process(target=_worker_a2a_layer, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=600) for _ in range(2)]
+  for p in procs:
+    p.join(timeout=120)
+    assert p.exitcode == 0
+  assert all(r[1] for r in res), res
+  assert res[0][3] == res[1][3] == sum(r[2] for r in res)
+
+
 def test_math_and_data_flow_mirrors():
   """de.math / de.data_flow (python/ops/math_ops.py:60-215, data_flow_ops.py:40-61): the doc examples of the TF ops
   they stand for"""
