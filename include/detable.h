@@ -117,7 +117,8 @@ enum {
 det_status det_table_create(det_table** out, const det_config* cfg);
 det_status det_table_destroy(det_table* t);
 /* A table inside caller-provided device memory (fixed capacity = cfg->init_capacity slots, never grows, memory not
- * freed by destroy): lets the planes live in memory that peers map, see det_peer_group_create_regions. */
+ * freed by destroy): lets the planes live in memory that peers map, see det_peer_group_create_regions.  With
+ * DET_FLAGS_EVICT in cfg->flags the table evicts in place at that capacity (the score plane is the library's own). */
 size_t det_table_region_bytes(const det_config* cfg);
 det_status det_table_create_in_region(det_table** out, const det_config* cfg, void* region, size_t region_bytes);
 const char* det_last_error(void);
@@ -324,7 +325,12 @@ det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, s
  * key plane and moves the row over NVLink, no collective.  A published table cannot grow.
  * tables[p] non-NULL = shard p lives in this process (its own rank, or several shards faked on one GPU like the
  * reference's tests, kernel_tests/dynamic_embedding_ops_test.py:329); NULL = map it from handles[p].
- * det_peer_barrier: flag barrier over peer memory separating the "all ranks read" / "all ranks write" phases. */
+ * det_peer_barrier: flag barrier over peer memory separating the "all ranks read" / "all ranks write" phases.
+ * Shards with an eviction strategy (DET_FLAGS_EVICT) are served by their OWNERS only: det_peer_find, det_peer_insert and
+ * det_peer_xchg_insert return DET_INVALID_ARGUMENT / DET_UNIMPLEMENTED for such a group; lookups go through
+ * det_peer_xchg_find and new keys enter through det_peer_xchg_apply_* (or det_peer_route + inbox + the owner's own
+ * det_apply_* / det_insert_scored), whose find-or-insert makes room by evicting and writes the scores
+ * (the reference: one HkvHashTable per Horovod rank behind HvdAllToAllEmbedding, keras/layers/embedding.py:545-595). */
 typedef struct det_peer_group det_peer_group;
 size_t det_peer_handle_bytes(void);
 det_status det_peer_export(det_table* t, void* handle_out_host);

@@ -78,8 +78,8 @@ static det_status dispatch_vec_e(int vec, F&& f) {
 det_status evict_attach(det_table* t, int strategy) {
   if (strategy < DET_EVICT_LRU || strategy > DET_EVICT_CUSTOMIZED)
     return fail(DET_INVALID_ARGUMENT, "det_table_create: unknown eviction strategy in cfg.flags");
-  if (t->external)
-    return fail(DET_UNIMPLEMENTED, "det_table_create_in_region: eviction strategies are not available for tables in a caller-provided region");
+  // a table in a caller-provided region (a shard of a peer group) sits at its maximum from the start: every event works
+  // in place (evict_lowest + repair rounds), the score plane is the owner's own allocation
   EvictState* ev = new EvictState();
   ev->strategy = strategy;
   const size_t n = t->view.capacity() + 2;

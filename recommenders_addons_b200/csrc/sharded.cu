@@ -647,15 +647,16 @@ static void xchg_time_collect(det_peer_group* g, int which, int n_iv);
 }
 
 
-// A shard that peers write one-sidedly must not have an eviction strategy: a remote claim would bypass the owner's score
-// plane and its eviction at max_capacity (evict.cu).  Sharded tables WITH eviction run on the collective exchange
-// (ShardedVariable: keys travel to the owner, which calls its own det_insert / det_apply_* with eviction).
-static det_status peer_reject_evicting(const det_table* t, const char* who) {
-  if (t && t->ev) {
-    std::string m = std::string(who) + ": a table with an eviction strategy cannot be published to peers "
-                    "(use the collective exchange, ShardedVariable, for sharded tables with eviction)";
-    return fail(DET_INVALID_ARGUMENT, m.c_str());
-  }
+// A shard with an eviction strategy is read and written by its OWNER's kernels only: a remote claim would bypass the
+// owner's score plane and its eviction at max_capacity, a remote probe could run into an eviction event (evict.cu moves
+// keys in place).  Such a group therefore runs on the owner-side exchange -- det_peer_xchg_find for lookups,
+// det_peer_xchg_apply_* (or route -> inbox -> the owner's own det_apply_*) for the training step, whose find-or-insert
+// makes room through evict_room and writes scores inside apply_staged_kernel<OPT, SCORED> -- and the one-sided entry
+// points refuse it loudly.  (Collective alternative: ShardedVariable over one ordinary evicting table per rank.)
+static det_status peer_reject_evicting(const det_peer_group* g, const char* who) {
+  if (g && g->local && g->local->ev)
+    return fail(DET_INVALID_ARGUMENT, std::string(who) + ": the shards have an eviction strategy; they are served by their "
+                                      "owners only (det_peer_xchg_find / det_peer_xchg_apply_*, or route + inbox)");
   return DET_OK;
 }
 
@@ -665,7 +666,6 @@ size_t det_peer_handle_bytes(void) { return sizeof(PeerBlob); }
 
 det_status det_peer_export(det_table* t, void* blob_out) {
   if (!t || !blob_out) return fail(DET_INVALID_ARGUMENT, "det_peer_export: null argument");
-  if (det_status e = peer_reject_evicting(t, "det_peer_export")) return e;
   det::DevGuard _dg(t->cfg.device);
   PeerBlob b;
   memset(&b, 0, sizeof(b));
@@ -730,8 +730,6 @@ det_status det_peer_group_create(det_peer_group** out, det_table* const* tables,
     return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: world must be in [1,8] and rank in [0,world)");
   det_table* local = tables[rank];
   if (!local) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create: tables[rank] must be the local shard");
-  for (int p = 0; p < world; ++p)
-    if (det_status e = peer_reject_evicting(tables[p], "det_peer_group_create")) return e;
   det::DevGuard _dg(local->cfg.device);
   det_peer_group* g = new det_peer_group();
   memset(g->opened, 0, sizeof(g->opened));
@@ -819,7 +817,6 @@ det_status det_peer_group_create_regions(det_peer_group** out, det_table* local,
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
     return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: world must be in [1,8] and rank in [0,world)");
   if (!local->external) return fail(DET_INVALID_ARGUMENT, "det_peer_group_create_regions: the local shard must live in a region");
-  if (det_status e = peer_reject_evicting(local, "det_peer_group_create_regions")) return e;
   det::DevGuard _dg(local->cfg.device);
   det_peer_group* g = new det_peer_group();
   memset(g->opened, 0, sizeof(g->opened));
@@ -1035,14 +1032,17 @@ static det_status peer_room(det_peer_group* g, const char* who) {
   }
   if (g->snap_inflight && cudaEventQuery(g->snap_ev) == cudaSuccess) {
     g->snap_inflight = false;
-    t->used_ub = g->h_snap->used;           // remote / owner-side inserts never went through ensure_room
-    t->last_used_snap = g->h_snap->used;
+    if (!t->ev) {                           // an evicting shard is written by its owner's host calls only: evict_room
+      t->used_ub = g->h_snap->used;         // keeps the bound.  Otherwise: remote / owner-side inserts never went
+      t->last_used_snap = g->h_snap->used;  // through ensure_room, the snapshot is the bound
+    }
   } else {
     cudaGetLastError();
   }
   if (g->h_snap) {
     const uint64_t limit = (uint64_t)((double)t->view.capacity() * t->max_lf);
-    if ((g->h_snap->error & kErrTableFull) || g->h_snap->used > limit)
+    // (an evicting shard may sit between its soft limit and the hard bound of evict_room: only the sticky bit counts)
+    if ((g->h_snap->error & kErrTableFull) || (!t->ev && g->h_snap->used > limit))
       return fail(DET_TABLE_FULL, std::string(who) + ": the local shard is full (" + std::to_string(g->h_snap->used) + " of " +
                                       std::to_string(t->view.capacity()) + " slots used, load limit " + std::to_string(limit) +
                                       "; a sharded table has a fixed capacity per rank)");
@@ -1164,6 +1164,9 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
   if (!g || !g->xchg) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: no exchange mailbox attached");
   if (n > g->xv.cap) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: batch larger than the mailbox (max_items)");
   if (n && (!keys || !values)) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: null argument");
+  if (g->local->ev)   // the owner-side insert kernel neither scores nor makes room; the training step (xchg_apply) does
+    return fail(DET_UNIMPLEMENTED, "det_peer_xchg_insert: shards with an eviction strategy take new keys through "
+                                   "det_peer_xchg_apply_* (or the owner's own det_insert_scored)");
   cudaStream_t s = (cudaStream_t)stream;
   det::DevGuard _dg(g->device);
   det_status rs = peer_room(g, "det_peer_xchg_insert");
@@ -1355,6 +1358,7 @@ det_status det_peer_xchg_apply_adam(det_peer_group* g, const int64_t* keys, cons
 det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const void* defaults,
                          int full_size_default, void* values_out, uint8_t* exists, det_stream_t stream) {
   if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_find: null group");
+  if (det_status e = peer_reject_evicting(g, "det_peer_find")) return e;
   if (n == 0) return DET_OK;
   if (!keys || !values_out || !defaults) return fail(DET_INVALID_ARGUMENT, "det_peer_find: null argument");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1379,6 +1383,7 @@ det_status det_peer_find(det_peer_group* g, const int64_t* keys, size_t n, const
 det_status det_peer_insert(det_peer_group* g, const int64_t* keys, const void* values, size_t n,
                            det_stream_t stream) {
   if (!g) return fail(DET_INVALID_ARGUMENT, "det_peer_insert: null group");
+  if (det_status e = peer_reject_evicting(g, "det_peer_insert")) return e;
   if (n == 0) return DET_OK;
   if (!keys || !values) return fail(DET_INVALID_ARGUMENT, "det_peer_insert: null argument");
   cudaStream_t s = (cudaStream_t)stream;

@@ -118,7 +118,7 @@ class AllToAllEmbedding(torch.nn.Module):
   def __init__(self, embedding_size, capacity_per_shard=None, group=None, initializer=None, name="AllToAllEmbedding",
                num_slot_planes=2, with_unique=True, with_secondary_unique=True, mpi_size=None, batch_size=None,
                key_dtype=torch.int64, value_dtype=torch.float32, init_capacity=0, kv_creator=None, devices=None,
-               exchange_impls=None, **kwargs):
+               exchange_impls=None, evict_strategy=None, max_ids_per_rank=None, **kwargs):
     """The reference's arguments (embedding.py:545-563: with_unique, with_secondary_unique, mpi_size, batch_size and the
     base layer's) are accepted; the world size comes from `group`, lookups always dedupe once (unique -> one-sided
     find), and a published shard has a FIXED capacity: capacity_per_shard (default: init_capacity, else 1M slots)."""
@@ -140,9 +140,16 @@ class AllToAllEmbedding(torch.nn.Module):
       self.params = ShardedVariable(local, group, **(exchange_impls or {}))
       self.evicting = evicting
     else:
-      self.evicting = False
+      # evict_strategy without a kv_creator: fixed-capacity shards that evict, served by their owners over the owner-side
+      # exchange (max_ids_per_rank = the mailbox capacity: the most unique ids one rank sends in one call)
+      self.evicting = evict_strategy is not None
       self.params = PeerShardedVariable.create(self.embedding_size, capacity_per_shard, group=group,
-                                               initializer=initializer, num_slot_planes=num_slot_planes, name=name)
+                                               initializer=initializer, num_slot_planes=num_slot_planes, name=name,
+                                               evict_strategy=evict_strategy)
+      if self.evicting:
+        if not max_ids_per_rank:
+          raise ValueError("AllToAllEmbedding(evict_strategy=...): max_ids_per_rank (the exchange mailbox capacity) is required")
+        self.params.attach_exchange(int(max_ids_per_rank), insert="push")
     self._pending = []
     self._inbox_items = 0
 
@@ -165,6 +172,11 @@ class AllToAllEmbedding(torch.nn.Module):
     routes zeros instead of skipping the exchange."""
     import torch.distributed as dist
     if self.collective:           # the all-to-all sizes itself; a rank without gradients still takes part, with zeros
+      for uniq, rows in self._pending:
+        self.params.apply_gradients(optimizer, uniq, rows.grad if rows.grad is not None else torch.zeros_like(rows))
+      self._pending = []
+      return
+    if getattr(self.params, "_xchg", False) and self.params._xchg_insert:   # owner-side exchange: no inbox to size
       for uniq, rows in self._pending:
         self.params.apply_gradients(optimizer, uniq, rows.grad if rows.grad is not None else torch.zeros_like(rows))
       self._pending = []

@@ -117,10 +117,16 @@ class PeerShardedVariable(object):
 
   @classmethod
   def create(cls, dim, capacity, group=None, value_dtype=torch.float32, initializer=None, num_slot_planes=0,
-             name="PeerShardedVariable", gpu_mode=True):
+             name="PeerShardedVariable", gpu_mode=True, evict_strategy=None):
     """Preferred constructor: the local shard (fixed `capacity` slots) is built inside a torch symmetric-memory
     region (CUDA VMM, mapped by every rank with 2 MB pages); peers are addressed through the rendezvous
-    handle's buffer pointers.  Collective over `group`."""
+    handle's buffer pointers.  Collective over `group`.
+
+    evict_strategy (de.HkvEvictStrategy): every shard keeps a score plane and evicts its lowest-scored keys at
+    `capacity` instead of failing with DET_TABLE_FULL.  Such shards are served by their owners only: call
+    attach_exchange() (insert="push"); lookup() and apply_gradients() then run as det_peer_xchg_find /
+    det_peer_xchg_apply_* -- the step's find-or-insert makes room (evict_room) and writes the scores; upsert() through
+    the exchange and the one-sided kernels are refused by the library."""
     import torch.distributed._symmetric_memory as symm_mem
     from .table import CuckooHashTable
     from .variable import Variable
@@ -137,7 +143,8 @@ class PeerShardedVariable(object):
       def create(self, key_dtype=None, value_dtype=None, default_value=None, name=None, checkpoint=None,
                  init_size=None, config=None, device=None, shard_saveable_object_fn=None, num_slot_planes=0):
         return CuckooHashTable(key_dtype, value_dtype, default_value, name=name, init_size=capacity, device=device,
-                               num_slot_planes=num_slot_planes, region=region)
+                               num_slot_planes=num_slot_planes, region=region, evict_strategy=evict_strategy,
+                               max_capacity=capacity if evict_strategy is not None else 0)
 
     creator = _RegionCreator()
     var = Variable(dim=dim, value_dtype=value_dtype, init_size=capacity, initializer=initializer, name=name,
@@ -155,7 +162,8 @@ class PeerShardedVariable(object):
     self._tables[self.rank] = var.tables[0]
     self.backing = "symmetric-memory"
     self._create_args = dict(dim=dim, group=group, value_dtype=value_dtype, initializer=initializer,
-                             num_slot_planes=num_slot_planes, name=name, gpu_mode=gpu_mode)
+                             num_slot_planes=num_slot_planes, name=name, gpu_mode=gpu_mode, evict_strategy=evict_strategy)
+    self.evict_strategy = evict_strategy
     self.capacity = int(capacity)
     return self
 
@@ -174,6 +182,8 @@ class PeerShardedVariable(object):
     keep their owner, so no row crosses NVLink.  Call it between steps (maybe_grow does, on an agreed load)."""
     if self.backing != "symmetric-memory":
       raise RuntimeError("grow needs the symmetric-memory backing (PeerShardedVariable.create)")
+    if getattr(self, "evict_strategy", None) is not None:
+      raise RuntimeError("grow: shards with an eviction strategy stay at their capacity and evict")
     new_capacity = int(new_capacity)
     if new_capacity <= self.capacity:
       raise ValueError("grow: new_capacity must exceed the current %d slots" % self.capacity)
@@ -215,6 +225,8 @@ class PeerShardedVariable(object):
   def maybe_grow(self, threshold=0.6, factor=2.0):
     """COLLECTIVE.  Grows every shard by `factor` once the fullest shard has passed `threshold` (the decision is an
     all-reduce MAX, so all ranks take it together).  Returns True when it grew."""
+    if getattr(self, "evict_strategy", None) is not None:
+      return False                                   # shards with an eviction strategy evict instead
     if self.load() > threshold:
       self.grow(int(self.capacity * factor))
       return True

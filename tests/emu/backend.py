@@ -6,7 +6,7 @@ import contextlib
 import ctypes
 
 from recommenders_addons_b200 import _lib
-from recommenders_addons_b200.dynamic_embedding import ops, optimizer, table, variable
+from recommenders_addons_b200.dynamic_embedding import ops, optimizer, sharded, table, variable
 from tests.emu import build_emu
 
 _EMU = None
@@ -28,6 +28,8 @@ def emu_cdll():
 def installed():
   saved = (_lib._LIB, table._DEVICE_TYPES, table._stream_ptr, variable._stream_ptr, optimizer._stream_ptr,
            ops._stream_ptr)
+  saved_sp = sharded.PeerShardedVariable._sp
+  sharded.PeerShardedVariable._sp = lambda self: None
   _lib._LIB = emu_cdll()
   table._DEVICE_TYPES = ("cuda", "cpu")
   no_stream = lambda device: None  # noqa: E731  (the emulated runtime is synchronous)
@@ -37,5 +39,6 @@ def installed():
     yield
   finally:
     variable._reset_variables()
+    sharded.PeerShardedVariable._sp = saved_sp
     (_lib._LIB, table._DEVICE_TYPES, table._stream_ptr, variable._stream_ptr, optimizer._stream_ptr,
      ops._stream_ptr) = saved

@@ -513,15 +513,177 @@ def test_bounded_table_reserve_clear_import_and_load(tmp_path):
   t.close()
 
 
-def test_peer_publish_rejects_a_table_with_an_eviction_strategy():
-  """a remote one-sided claim would bypass the owner's score plane and its eviction at max_capacity: publishing such a
-  shard fails loudly (sharded tables with eviction run on the collective exchange, tests/test_host_logic.py)."""
+def test_one_sided_entry_points_refuse_shards_with_an_eviction_strategy():
+  """a remote claim would bypass the owner's score plane and its eviction at max_capacity, a remote probe could run into
+  an eviction event: such shards are served by their owners only (the next test); the one-sided calls fail loudly."""
   t = Table(dim=4, init=1024, max_capacity=1024, strategy=0)        # LRU
-  blob = (ctypes.c_ubyte * X().det_peer_handle_bytes())()
-  assert X().det_peer_export(t.h, blob) == 1                        # DET_INVALID_ARGUMENT
+  g = PeerGroup([t], None, 1, 0)
+  k, v = np.arange(4, dtype=np.int64), np.zeros((4, 4), np.float32)
+  out, ex = np.empty((4, 4), np.float32), np.empty(4, np.uint8)
+  assert X().det_peer_find(g.g, P(k), 4, P(v[0]), 0, P(out), P(ex), None) == 1      # DET_INVALID_ARGUMENT
   assert b"eviction strategy" in L().det_last_error()
-  tl = (ctypes.c_void_p * 1)(t.h)
-  g = ctypes.c_void_p()
-  assert X().det_peer_group_create(ctypes.byref(g), tl, None, 1, 0, 1) == 1
-  assert b"eviction strategy" in L().det_last_error()
+  assert X().det_peer_insert(g.g, P(k), P(v), 4, None) == 1
+  rb = 16
+  nbytes = X().det_peer_xchg_bytes(1, 64, rb)
+  raw = np.zeros(nbytes + 256, dtype=np.uint8)
+  box = raw[(-raw.ctypes.data) % 256:][:nbytes]
+  ck(X().det_peer_xchg_attach(g.g, (ctypes.c_void_p * 1)(box.ctypes.data), 64, rb))
+  assert X().det_peer_xchg_insert(g.g, P(k), P(v), 4, None) == 5                   # DET_UNIMPLEMENTED
+  assert b"det_peer_xchg_apply" in L().det_last_error()
+  g.close()
   t.close()
+
+
+class RegionTable(Table):
+  """a table whose planes live in a caller-provided region (det_table_create_in_region): what PeerShardedVariable.create
+  builds inside a symmetric-memory allocation"""
+
+  def __init__(self, dim, slots, slot_planes=0, strategy=None):
+    cfg = real.DetConfig()
+    cfg.value_dtype = real.DTYPE_CODES["float32"]
+    cfg.dim, cfg.device, cfg.num_slot_planes = dim, 0, slot_planes
+    cfg.init_capacity, cfg.max_capacity, cfg.max_load_factor = slots, slots, 0.0
+    cfg.flags = 0 if strategy is None else real.flags_evict(strategy)
+    nbytes = X().det_table_region_bytes(ctypes.byref(cfg))
+    self._raw = np.zeros(nbytes + 256, dtype=np.uint8)
+    self.region = self._raw[(-self._raw.ctypes.data) % 256:][:nbytes]
+    self.h = ctypes.c_void_p()
+    ck(X().det_table_create_in_region(ctypes.byref(self.h), ctypes.byref(cfg), self.region.ctypes.data, nbytes))
+    self.dim, self.dtype, self.strategy = dim, np.dtype(np.float32), strategy
+    self.step_per_epoch, self.gen_scores_fn, self.curr_epoch, self.curr_step = 0, None, 0, 1
+
+
+def test_table_in_a_region_evicts_in_place():
+  """eviction needs no second set of planes, so a fixed-capacity table in a caller-provided region may have a strategy"""
+  rng = np.random.default_rng(9)
+  t = RegionTable(dim=4, slots=1024, strategy=1)                 # LFU
+  keys = rng.choice(1 << 40, size=3000, replace=False).astype(np.int64)
+  hot = keys[:100]
+  for b in range(0, 3000, 150):
+    k = np.concatenate([hot, keys[b:b + 150]]) if b else keys[:150]
+    k = np.unique(k)
+    t.insert(k, np.repeat(k.astype(np.float32)[:, None] % 1000, 4, axis=1))
+  st = t.stats()
+  assert st["evict_events"] > 0 and st["error_flags"] == 0 and st["capacity"] == 1024
+  t.check()
+  ks, vs = t.export()
+  assert np.isin(hot, ks).all() and len(ks) <= int(1024 * 0.95)
+  np.testing.assert_array_equal(vs[:, 0], ks.astype(np.float32) % 1000)
+  t.close()
+
+
+@pytest.mark.parametrize("strategy,backing", [(1, "ipc"), (0, "ipc"), (1, "regions")])          # LFU, LRU
+def test_owner_side_training_on_shards_that_evict(strategy, backing):
+  """Sharded table WITH eviction on the owner-side exchange: 3 ranks (threads), every shard a fixed 1024 slots with an
+  eviction strategy; 80 training steps (det_peer_xchg_apply_adagrad) send 30 HOT ids from every rank every step plus
+  fresh cold ids -- ~3x more distinct ids than the shards hold.  Every shard stays under its hard bound, evicts (events
+  counted), keeps no duplicate and no error flag; the hot ids are never evicted (highest count / most recent) and their
+  params and accumulators equal a sequential model bit for bit; every cold id that is still there carries exactly its
+  one step from the initial row."""
+  world, dim, cap, steps, slots = 3, 16, 64, 80, 1024
+  rng = np.random.default_rng(400 + strategy)
+  owner_of = lambda k: O.default_partition_fn(k, world, True)
+  hot = rng.choice(1 << 40, size=30, replace=False).astype(np.int64)
+  cold_pool = (rng.choice(1 << 40, size=world * steps * (cap - 30), replace=False).astype(np.int64) | (1 << 41))
+  if backing == "regions":
+    tables = [RegionTable(dim, slots, slot_planes=1, strategy=strategy) for _ in range(world)]
+  else:
+    tables = [Table(dim=dim, init=slots, max_capacity=slots, slot_planes=1, strategy=strategy) for _ in range(world)]
+    hb = X().det_peer_handle_bytes()
+    blob = (ctypes.c_ubyte * (hb * world))()
+    for r in range(world):
+      ck(X().det_peer_export(tables[r].h, ctypes.c_void_p(ctypes.addressof(blob) + r * hb)))
+  rb = dim * 4
+  nbytes = X().det_peer_xchg_bytes(world, cap, rb)
+  raw = [np.zeros(nbytes + 256, dtype=np.uint8) for _ in range(world)]
+  boxes = [b[(-b.ctypes.data) % 256:][:nbytes] for b in raw]
+  sched, c = [], 0
+  for t in range(steps):
+    per = []
+    for r in range(world):
+      n_cold = int(rng.integers(0, cap - 30 + 1))
+      k = np.ascontiguousarray(np.concatenate([hot, cold_pool[c:c + n_cold]]))
+      c += n_cold
+      if t % 7 == r:                                  # now and then a rank has nothing to send
+        k = np.zeros(0, np.int64)
+      per.append((k, rng.normal(0, 1e-2, (len(k), dim)).astype(np.float32)))
+    sched.append(per)
+  ip = np.full(dim, 0.05, np.float32)
+  errors, got = [], {}
+  start = threading.Barrier(world)
+
+  def rank_main(r):
+    try:
+      if backing == "regions":
+        g = PeerGroup.__new__(PeerGroup)
+        g.g, g.world, g.rank = ctypes.c_void_p(), world, r
+        rp = (ctypes.c_void_p * world)(*[t.region.ctypes.data for t in tables])
+        ck(X().det_peer_group_create_regions(ctypes.byref(g.g), tables[r].h, rp, world, r, 1))
+      else:
+        tl = [None] * world
+        tl[r] = tables[r]
+        g = PeerGroup(tl, ctypes.cast(blob, ctypes.c_void_p), world, r)
+      ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boxes])
+      ck(X().det_peer_xchg_attach(g.g, ptrs, cap, rb))
+      wsb = X().det_peer_xchg_apply_workspace_bytes(g.g)
+      wraw = np.zeros(wsb + 256, np.uint8)
+      ws = wraw[(-wraw.ctypes.data) % 256:][:wsb]
+      start.wait()
+      for t in range(steps):
+        k, gr = sched[t][r]
+        n = len(k)
+        ck(X().det_peer_xchg_apply_adagrad(g.g, P(k) if n else None, P(gr) if n else None, n, 0.1, 0.0, P(ip), 0.1, P(ws), wsb, None))
+      q = np.ascontiguousarray(np.concatenate([hot, cold_pool[:c:11]]))
+      out = np.empty((len(q), dim), np.float32)
+      ex = np.empty(len(q), np.uint8)
+      for b in range(0, len(q), cap):                 # the same number of collective calls on every rank
+        qb, ob, eb = q[b:b + cap], out[b:b + cap], ex[b:b + cap]
+        ck(X().det_peer_xchg_find(g.g, P(qb), len(qb), P(ip), 0, P(ob), P(eb), None, None))
+      got[r] = (q, out, ex.astype(bool))
+      g.close()
+    except BaseException:  # pragma: no cover
+      import traceback
+      errors.append((r, traceback.format_exc()))
+      try:
+        start.abort()
+      except Exception:
+        pass
+
+  th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+  for x in th:
+    x.start()
+  for x in th:
+    x.join(timeout=1200)
+  assert not errors, errors
+  f32 = np.float32
+  par, acc, cold_row = {}, {}, {}
+  for t in range(steps):
+    gsum = {}
+    for r in range(world):                          # summed on the owner in source-rank order
+      for kk, row in zip(sched[t][r][0].tolist(), sched[t][r][1]):
+        gsum[kk] = row.copy() if kk not in gsum else (gsum[kk] + row).astype(f32)
+    for kk, gg in gsum.items():
+      a1 = (acc.get(kk, np.full(dim, 0.1, f32)) + gg * gg).astype(f32)
+      par[kk] = (par.get(kk, ip) - (f32(0.1) * gg) / np.sqrt(a1)).astype(f32)
+      acc[kk] = a1
+  hot_set = set(hot.tolist())
+  total_seen = len(par)
+  total_live = 0
+  for o in range(world):
+    st = tables[o].stats()
+    assert st["error_flags"] == 0 and st["evict_events"] > 0, st
+    tables[o].check()
+    ks, vs = tables[o].export()
+    assert len(ks) <= int(slots * 0.95)
+    total_live += len(ks)
+    assert (owner_of(ks) == o).all()
+    mine_hot = hot[owner_of(hot) == o]
+    assert np.isin(mine_hot, ks).all()              # never evicted
+    for kk, row in zip(ks.tolist(), vs):
+      np.testing.assert_array_equal(row, par[kk])   # hot: the whole history; cold: its single step
+  assert total_seen - total_live > 1000              # ~1200 ids a shard saw beyond its soft limit are gone
+  for r in range(world):
+    q, out, ex = got[r]
+    assert ex[:len(hot)].all() and not ex.all()
+    for j, kk in enumerate(q.tolist()):
+      np.testing.assert_array_equal(out[j], par[kk] if ex[j] else ip)

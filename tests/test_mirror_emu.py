@@ -267,3 +267,46 @@ def test_shadow_variable_assign_and_verify():
   sh.verify_embedding_weights(ids)
   with _pt.raises(TypeError):
     sh.verify_embedding_weights(de.SparseIds(ids.indices, torch.tensor([5], dtype=torch.int32), (1, 1)))
+
+
+
+def test_peer_sharded_variable_with_an_eviction_strategy_python_path():
+  """the Python glue of the sharded-table-with-eviction path (scripts/gpu_sharded_evict.py runs the same flow on a GPU):
+  one fake shard with an LFU strategy behind PeerShardedVariable + the owner-side exchange; apply_gradients goes through
+  det_peer_xchg_apply_adagrad, lookups through det_peer_xchg_find, the one-sided calls are refused."""
+  import numpy as np
+  import torch
+  from recommenders_addons_b200 import dynamic_embedding as de
+  from recommenders_addons_b200._lib import DetError
+  dim, slots, cap, steps = 8, 1024, 128, 30
+  cfg = de.HkvHashTableConfig(init_capacity=slots, max_capacity=slots, evict_strategy=de.HkvEvictStrategy.LFU)
+  var = de.Variable(dim=dim, init_size=slots, initializer=0.05, num_slot_planes=1, name="emu-shard-evict", devices=["cpu"],
+                    kv_creator=de.HkvHashTableCreator(config=cfg))
+  pv = de.PeerShardedVariable(fake_shards=[var])
+  with pytest.raises(DetError, match="eviction strategy"):
+    pv.lookup(torch.arange(4))
+  nbytes = int(pv._lib.det_peer_xchg_bytes(1, cap, dim * 4))
+  raw = torch.zeros(nbytes + 256, dtype=torch.uint8)
+  off = (-raw.data_ptr()) % 256
+  pv.attach_exchange(cap, mailbox_ptrs=[raw.data_ptr() + off], keepalive=raw, insert="push")
+  with pytest.raises(DetError, match="det_peer_xchg_apply"):
+    pv.upsert(torch.arange(4), torch.zeros(4, dim))
+  opt = de.FusedAdagrad(0.1, 0.1)
+  rng = np.random.default_rng(2)
+  hot = torch.from_numpy(rng.choice(1 << 40, size=20, replace=False).astype(np.int64))
+  f32 = np.float32
+  par = {int(k): np.full(dim, 0.05, f32) for k in hot}
+  acc = {int(k): np.full(dim, 0.1, f32) for k in hot}
+  for t in range(steps):
+    cold = torch.from_numpy((rng.choice(1 << 40, size=cap - 20, replace=False).astype(np.int64) | (1 << 41)) + t * (1 << 42))
+    g = torch.from_numpy(rng.normal(0, 1e-2, (cap, dim)).astype(f32))
+    pv.apply_gradients(opt, torch.cat([hot, cold]), g)
+    for k, gg in zip(hot.tolist(), g[:20].numpy()):
+      acc[k] = (acc[k] + gg * gg).astype(f32)
+      par[k] = (par[k] - (f32(0.1) * gg) / np.sqrt(acc[k])).astype(f32)
+  rows, ex = pv.lookup(hot, return_exists=True)
+  assert bool(ex.all()) and np.array_equal(rows.numpy(), np.stack([par[int(k)] for k in hot]))
+  st = var.tables[0].stats()
+  assert st["evict_events"] > 0 and st["error_flags"] == 0 and int(var.size()) <= int(slots * 0.95)
+  pv.close()
+
