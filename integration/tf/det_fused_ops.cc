@@ -43,6 +43,28 @@ REGISTER_OP("TFRA>DetApplyAdam")
     .Attr("beta2: float = 0.999")
     .Attr("epsilon: float = 1e-8");
 
+// `_resource_apply_sparse_duplicate_indices` (python/ops/dynamic_embedding_optimizer.py:150,184 + :161-204) in ONE op:
+// ids WITH repeats and their row gradients in, unique -> position-order gradient sum -> fused find-or-insert step on the
+// device, the unique count never visiting the host (det_apply_*_dup).  Rows must be 16-byte vectors (dim % 4 == 0).
+REGISTER_OP("TFRA>DetApplyAdagradDuplicateIndices")
+    .Input("table_handle: resource")
+    .Input("ids: int64")           // [n], repeats allowed (IndexedSlices.indices)
+    .Input("grads: float")         // [n, dim]     (IndexedSlices.values)
+    .Input("lr: float")
+    .Input("init_param: float")    // [dim]
+    .Attr("epsilon: float = 0.0")
+    .Attr("initial_accumulator_value: float = 0.1");
+
+REGISTER_OP("TFRA>DetApplyAdamDuplicateIndices")
+    .Input("table_handle: resource")
+    .Input("ids: int64")
+    .Input("grads: float")
+    .Input("alpha: float")
+    .Input("init_param: float")    // [dim]
+    .Attr("beta1: float = 0.9")
+    .Attr("beta2: float = 0.999")
+    .Attr("epsilon: float = 1e-8");
+
 // The gradient dedupe in front of the sparse optimizer step: unsorted_segment_sum(values, idx, num_segments) as
 // _deduplicate_indexed_slices calls it before _resource_apply_sparse_duplicate_indices
 // (python/ops/dynamic_embedding_optimizer.py:150,184), with the rows of one segment added in position order
@@ -158,6 +180,55 @@ class DetApplyAdamOp : public OpKernel {
   float beta1_ = 0.9f, beta2_ = 0.999f, epsilon_ = 1e-8f;
 };
 
+// OPT 0 = Adagrad (input 3 = lr), 1 = Adam (input 3 = alpha)
+template <int OPT>
+class DetApplyDuplicateIndicesOp : public OpKernel {
+ public:
+  explicit DetApplyDuplicateIndicesOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("epsilon", &epsilon_));
+    if (OPT == 0) {
+      OP_REQUIRES_OK(ctx, ctx->GetAttr("initial_accumulator_value", &init_accum_));
+    } else {
+      OP_REQUIRES_OK(ctx, ctx->GetAttr("beta1", &beta1_));
+      OP_REQUIRES_OK(ctx, ctx->GetAttr("beta2", &beta2_));
+    }
+  }
+  void Compute(OpKernelContext* ctx) override {
+    tensorflow::lookup::LookupInterface* table = nullptr;
+    OP_REQUIRES_OK(ctx, GetLookupTable("table_handle", ctx, &table));
+    core::ScopedUnref unref_me(table);
+    Table* t = static_cast<Table*>(table);
+    const Tensor& ids = ctx->input(1);
+    const Tensor& grads = ctx->input(2);
+    const Tensor& step = ctx->input(3);
+    const Tensor& init = ctx->input(4);
+    const int64 n = ids.NumElements(), dim = t->value_shape().dim_size(0);
+    OP_REQUIRES(ctx, grads.NumElements() == n * dim, errors::InvalidArgument("grads must have shape [n, dim]"));
+    OP_REQUIRES(ctx, init.NumElements() == dim, errors::InvalidArgument("init_param must have shape [dim]"));
+    if (n == 0) return;
+    // stream-ordered scratch from TF's allocator, aligned up to the 256 B the library asks for
+    const size_t ws_bytes = det_apply_dup_workspace_bytes(static_cast<size_t>(n), static_cast<size_t>(dim));
+    Tensor ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_INT8, TensorShape({static_cast<int64>(ws_bytes + 256)}), &ws));
+    int8* raw = ws.flat<int8>().data();
+    void* aligned = raw + ((256 - (reinterpret_cast<uintptr_t>(raw) & 255u)) & 255u);
+    const int64_t* k = reinterpret_cast<const int64_t*>(ids.flat<int64>().data());
+    const float* g = grads.flat<float>().data();
+    if (OPT == 0) {
+      OP_REQUIRES_OK(ctx, ToStatus(det_apply_adagrad_dup(t->handle(), k, g, static_cast<size_t>(n), step.scalar<float>()(),
+                                                         epsilon_, init.flat<float>().data(), init_accum_, aligned,
+                                                         ws_bytes, nullptr, StreamOf(ctx))));
+    } else {
+      OP_REQUIRES_OK(ctx, ToStatus(det_apply_adam_dup(t->handle(), k, g, static_cast<size_t>(n), step.scalar<float>()(),
+                                                      beta1_, beta2_, epsilon_, init.flat<float>().data(), aligned,
+                                                      ws_bytes, nullptr, StreamOf(ctx))));
+    }
+  }
+
+ private:
+  float epsilon_ = 0.f, init_accum_ = 0.1f, beta1_ = 0.9f, beta2_ = 0.999f;
+};
+
 class DetSegmentReduceOp : public OpKernel {
  public:
   explicit DetSegmentReduceOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
@@ -186,6 +257,10 @@ REGISTER_KERNEL_BUILDER(Name("TFRA>DetLookupSparse").Device(DEVICE_GPU), DetLook
 REGISTER_KERNEL_BUILDER(Name("TFRA>DetSegmentReduce").Device(DEVICE_GPU).HostMemory("num_segments"), DetSegmentReduceOp);
 REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdagrad").Device(DEVICE_GPU).HostMemory("lr"), DetApplyAdagradOp);
 REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdam").Device(DEVICE_GPU).HostMemory("alpha"), DetApplyAdamOp);
+REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdagradDuplicateIndices").Device(DEVICE_GPU).HostMemory("lr"),
+                        DetApplyDuplicateIndicesOp<0>);
+REGISTER_KERNEL_BUILDER(Name("TFRA>DetApplyAdamDuplicateIndices").Device(DEVICE_GPU).HostMemory("alpha"),
+                        DetApplyDuplicateIndicesOp<1>);
 
 }  // namespace det_shim
 }  // namespace lookup

@@ -239,6 +239,50 @@ static void fused_ops() {
     red->Compute(&cs);
     CHECK_T(!cs.status().ok() && cs.status().code() == error::INVALID_ARGUMENT);
   }
+  // _resource_apply_sparse_duplicate_indices in one op: ids {2, 60, 2, 2, 60} with repeats; id 2 receives
+  // ((0.5 + 0.25) + 0.125) in position order, id 60 is new and starts from init_param
+  {
+    CHECK_T(reg.ops.count("TFRA>DetApplyAdagradDuplicateIndices") && reg.ops.count("TFRA>DetApplyAdamDuplicateIndices"));
+    Tensor before(DT_FLOAT, TensorShape({1, dim}));
+    CHECK_OK(table.Find(&c, I64({2}), &before, d0));
+    const float p2 = before.flat<float>()(0);
+    OpKernelConstruction dc(ad);
+    std::unique_ptr<OpKernel> dup(reg.kernels["TFRA>DetApplyAdagradDuplicateIndices"](&dc));
+    CHECK_OK(dc.status());
+    OpKernelContext cd = Ctx(DT_FLOAT);
+    cd.table = &table;
+    cd.inputs = {Tensor(), I64({2, 60, 2, 2, 60}), Rows<float>(DT_FLOAT, {0.5f, 1.f, 0.25f, 0.125f, -0.5f}, dim), lr, init};
+    dup->Compute(&cd);
+    CHECK_OK(cd.status());
+    Tensor g2(DT_FLOAT, TensorShape({2, dim}));
+    CHECK_OK(table.Find(&c, I64({2, 60}), &g2, d0));
+    const float s2 = (0.5f + 0.25f) + 0.125f, s60 = 1.f + -0.5f;
+    const float b2 = a2 + s2 * s2, b60 = 0.1f + s60 * s60;     // id 2 already carries the accumulator of the step above
+    CHECK_T(g2.flat<float>()(0) == p2 - (0.5f * s2) / std::sqrt(b2) && g2.flat<float>()(dim) == 1.f - (0.5f * s60) / std::sqrt(b60));
+    CHECK_T(table.size() == 5);
+    cd.inputs[4] = Tensor(DT_FLOAT, TensorShape({2, dim}));      // a full-size init_param is not part of this op
+    dup->Compute(&cd);
+    CHECK_T(!cd.status().ok() && cd.status().code() == error::INVALID_ARGUMENT);
+    // Adam flavour: m = (1-b1) g, v = (1-b2) g^2, p -= alpha * m / (sqrt(v) + eps) on a new id
+    NodeDef am;
+    am.attr["beta1"].f = 0.9f;
+    am.attr["beta2"].f = 0.999f;
+    am.attr["epsilon"].f = 1e-8f;
+    OpKernelConstruction mc(am);
+    std::unique_ptr<OpKernel> dupm(reg.kernels["TFRA>DetApplyAdamDuplicateIndices"](&mc));
+    CHECK_OK(mc.status());
+    OpKernelContext cm = Ctx(DT_FLOAT);
+    cm.table = &table;
+    Tensor alpha(DT_FLOAT, TensorShape({}));
+    alpha.scalar<float>()() = 0.01f;
+    cm.inputs = {Tensor(), I64({70, 70}), Rows<float>(DT_FLOAT, {0.25f, 0.25f}, dim), alpha, init};
+    dupm->Compute(&cm);
+    CHECK_OK(cm.status());
+    Tensor g3(DT_FLOAT, TensorShape({1, dim}));
+    CHECK_OK(table.Find(&c, I64({70}), &g3, d0));
+    const float gs = 0.25f + 0.25f, m = (1.f - 0.9f) * gs, v = (1.f - 0.999f) * gs * gs;
+    CHECK_T(std::fabs(g3.flat<float>()(0) - (1.f - 0.01f * m / (std::sqrt(v) + 1e-8f))) < 1e-6f);
+  }
   // a bad input is an InvalidArgument on the context, not a crash
   ca.inputs[2] = Tensor(DT_FLOAT, TensorShape({3, dim}));
   ada->Compute(&ca);
