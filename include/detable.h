@@ -326,10 +326,12 @@ det_status det_gather_rows(const void* rows_in, const int32_t* perm, size_t n, s
  * tables[p] non-NULL = shard p lives in this process (its own rank, or several shards faked on one GPU like the
  * reference's tests, kernel_tests/dynamic_embedding_ops_test.py:329); NULL = map it from handles[p].
  * det_peer_barrier: flag barrier over peer memory separating the "all ranks read" / "all ranks write" phases.
- * Shards with an eviction strategy (DET_FLAGS_EVICT) are served by their OWNERS only: det_peer_find, det_peer_insert and
- * det_peer_xchg_insert return DET_INVALID_ARGUMENT / DET_UNIMPLEMENTED for such a group; lookups go through
- * det_peer_xchg_find and new keys enter through det_peer_xchg_apply_* (or det_peer_route + inbox + the owner's own
- * det_apply_* / det_insert_scored), whose find-or-insert makes room by evicting and writes the scores
+ * Shards with an eviction strategy (DET_FLAGS_EVICT) are served by their OWNERS only: the one-sided det_peer_find and
+ * det_peer_insert return DET_INVALID_ARGUMENT for such a group.  Lookups go through det_peer_xchg_find; new keys enter
+ * through det_peer_xchg_apply_* (find-or-insert inside the fused step: room by eviction, scores written by the kernel,
+ * no host synchronisation below the load limit) or det_peer_xchg_insert (the owner compacts what arrived and runs its
+ * own scored insert: ONE host synchronisation per call; DET_UNIMPLEMENTED for the CUSTOMIZED strategy, which needs
+ * caller scores), or det_peer_route + inbox + the owner's own det_apply_* / det_insert_scored
  * (the reference: one HkvHashTable per Horovod rank behind HvdAllToAllEmbedding, keras/layers/embedding.py:545-595). */
 typedef struct det_peer_group det_peer_group;
 size_t det_peer_handle_bytes(void);

@@ -632,6 +632,8 @@ struct det_peer_group {
   cudaEvent_t ev_in = nullptr, ev_route = nullptr, ev_apply = nullptr;
   int chunks = 1;
   unsigned long long ep_find = 0, ep_ins = 0;
+  unsigned char* ins_ws = nullptr;           // owned: compacted inbound (keys, rows) of det_peer_xchg_insert on shards that evict
+  long long* h_ins_n = nullptr;              // pinned: their count
   DevState* h_snap = nullptr;                // pinned: async snapshot of the local shard's DevState
   cudaEvent_t snap_ev = nullptr;
   bool snap_inflight = false;
@@ -719,6 +721,8 @@ det_status det_peer_group_destroy(det_peer_group* g) {
   if (g->ev_apply) cudaEventDestroy(g->ev_apply);
   if (g->h_snap) cudaFreeHost(g->h_snap);
   if (g->snap_ev) cudaEventDestroy(g->snap_ev);
+  if (g->ins_ws) cudaFree(g->ins_ws);
+  if (g->h_ins_n) cudaFreeHost(g->h_ins_n);
   delete g;
   return DET_OK;
 }
@@ -1153,6 +1157,74 @@ det_status det_peer_xchg_find(det_peer_group* g, const int64_t* keys, size_t n, 
   return DET_OK;
 }
 
+// det_peer_xchg_insert on shards with an eviction strategy.  The owner-side insert kernel neither scores nor makes room,
+// so the owner COMPACTS what arrived (the kernel of the sharded optimizer step), reads the count -- one host
+// synchronisation per call, the price of evict_room's host-side decisions -- and hands the list to its own scored insert
+// (evict_insert: classify -> room by eviction -> insert_scored_kernel).  Keys several ranks sent in one call are stored
+// once; which row wins is unspecified, as for duplicates inside one det_insert.  CUSTOMIZED needs caller scores: refused.
+static det_status xchg_insert_evicting(det_peer_group* g, const int64_t* keys, const void* values, size_t n, cudaStream_t s) {
+  det_table* t = g->local;
+  if (det::evict_rule(t).strategy == DET_EVICT_CUSTOMIZED)
+    return fail(DET_UNIMPLEMENTED, "det_peer_xchg_insert: the CUSTOMIZED strategy needs scores (the owner's det_insert_scored)");
+  if (g->row_bytes % 4 != 0)
+    return fail(DET_UNIMPLEMENTED, "det_peer_xchg_insert: shards with an eviction strategy need rows of whole 4-byte words");
+  det::DevGuard _dg(g->device);
+  det_status rs = peer_room(g, "det_peer_xchg_insert");
+  if (rs != DET_OK) return rs;
+  const XchgView& xv = g->xv;
+  const size_t bound = (size_t)g->pv.world * xv.cap;
+  const size_t off_rows = al256(bound * 8), off_n = off_rows + al256(bound * g->row_bytes);
+  if (!g->ins_ws) {
+    CUDA_TRY(cudaMalloc((void**)&g->ins_ws, off_n + 256));
+    CUDA_TRY(cudaMallocHost((void**)&g->h_ins_n, sizeof(long long)));
+  }
+  const unsigned long long ep = ++g->ep_ins;
+  unsigned* ticket_r = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers);
+  unsigned* ticket_a = reinterpret_cast<unsigned*>(g->xcursor + kMaxPeers + 1);
+  DevState* st = t->view.st;
+  if (ep > 2) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + kFlagAck * 64);
+    DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, s, flags, xv.world, ep - 2, st, kXchgTimeoutCycles);
+  }
+  {
+    const int vec = pick_vec(g->row_bytes, values, nullptr, nullptr);
+    const RowGeom geo = make_geom((unsigned)g->row_bytes, vec);
+    const int grid = grid_for(n, kThreadsP * kRouteKpt, g->sm_count, 4);
+    const long long* k = (const long long*)keys;
+    const unsigned char* r = (const unsigned char*)values;
+    switch (vec) {
+      case 16: DET_LAUNCH((xchg_route_kernel<true, 16>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket_r, ep, st); break;
+      case 8: DET_LAUNCH((xchg_route_kernel<true, 8>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket_r, ep, st); break;
+      default: DET_LAUNCH((xchg_route_kernel<true, 4>), grid, kThreadsP, 0, s, xv, k, r, n, geo, g->xcursor, ticket_r, ep, st); break;
+    }
+  }
+  {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + ((ep & 1ull) ? kFlagIns1 : kFlagIns) * 64);
+    DET_LAUNCH_SPIN(xchg_wait_kernel, 1, 32, 0, s, flags, xv.world, ep, st, kXchgTimeoutCycles);
+  }
+  long long* ckeys = (long long*)g->ins_ws;
+  unsigned char* crows = g->ins_ws + off_rows;
+  long long* n_dev = (long long*)(g->ins_ws + off_n);
+  {
+    const int cvec = pick_vec(g->row_bytes, nullptr, nullptr, nullptr);
+    const RowGeom cgeo = make_geom((unsigned)g->row_bytes, cvec);
+    const int grid = g->sm_count * 4;
+    switch (cvec) {
+      case 16: DET_LAUNCH(xchg_compact_kernel<16>, grid, kThreadsP, 0, s, xv, ckeys, crows, cgeo, n_dev, ticket_a, ep); break;
+      case 8: DET_LAUNCH(xchg_compact_kernel<8>, grid, kThreadsP, 0, s, xv, ckeys, crows, cgeo, n_dev, ticket_a, ep); break;
+      default: DET_LAUNCH(xchg_compact_kernel<4>, grid, kThreadsP, 0, s, xv, ckeys, crows, cgeo, n_dev, ticket_a, ep); break;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(g->h_ins_n, n_dev, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const long long m = *g->h_ins_n;
+  if (m < 0 || (size_t)m > bound) return fail(DET_INTERNAL, "det_peer_xchg_insert: inbound count out of range");
+  if (m == 0) return DET_OK;
+  return det::evict_insert(t, (const int64_t*)ckeys, crows, nullptr, (size_t)m, s);
+}
+
+
 // Sharded Insert (insert_or_assign) through the owners.  COLLECTIVE like det_peer_xchg_find.
 // The batch can be cut into `chunks` pieces (DET_XCHG_CHUNKS, default 1 = off, the same on every rank) and PIPELINED over two
 // internal streams: while the owner-side kernel applies the pairs of chunk c to the local shard (HBM-bound, no NVLink
@@ -1164,9 +1236,7 @@ det_status det_peer_xchg_insert(det_peer_group* g, const int64_t* keys, const vo
   if (!g || !g->xchg) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: no exchange mailbox attached");
   if (n > g->xv.cap) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: batch larger than the mailbox (max_items)");
   if (n && (!keys || !values)) return fail(DET_INVALID_ARGUMENT, "det_peer_xchg_insert: null argument");
-  if (g->local->ev)   // the owner-side insert kernel neither scores nor makes room; the training step (xchg_apply) does
-    return fail(DET_UNIMPLEMENTED, "det_peer_xchg_insert: shards with an eviction strategy take new keys through "
-                                   "det_peer_xchg_apply_* (or the owner's own det_insert_scored)");
+  if (g->local->ev) return xchg_insert_evicting(g, keys, values, n, (cudaStream_t)stream);
   cudaStream_t s = (cudaStream_t)stream;
   det::DevGuard _dg(g->device);
   det_status rs = peer_room(g, "det_peer_xchg_insert");

@@ -125,8 +125,9 @@ class PeerShardedVariable(object):
     evict_strategy (de.HkvEvictStrategy): every shard keeps a score plane and evicts its lowest-scored keys at
     `capacity` instead of failing with DET_TABLE_FULL.  Such shards are served by their owners only: call
     attach_exchange() (insert="push"); lookup() and apply_gradients() then run as det_peer_xchg_find /
-    det_peer_xchg_apply_* -- the step's find-or-insert makes room (evict_room) and writes the scores; upsert() through
-    the exchange and the one-sided kernels are refused by the library."""
+    det_peer_xchg_apply_* -- the step's find-or-insert makes room (evict_room) and writes the scores -- and upsert() as
+    det_peer_xchg_insert, where the owner compacts what arrived and runs its own scored insert (one host sync per
+    call).  The one-sided kernels are refused by the library."""
     import torch.distributed._symmetric_memory as symm_mem
     from .table import CuckooHashTable
     from .variable import Variable

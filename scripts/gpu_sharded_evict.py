@@ -73,6 +73,12 @@ def main():
     for kk, gg in gs.items():
       acc[kk] = (acc[kk] + gg * gg).astype(f32)
       par[kk] = (par[kk] - (f32(0.1) * gg) / np.sqrt(acc[kk])).astype(f32)
+  # upsert through the owners (det_peer_xchg_insert on evicting shards): 8 rank-private keys per rank, read back by all
+  mine_k = torch.arange(8, dtype=torch.int64, device=dev) + 1000 * (rank + 1)
+  pv.upsert(mine_k, torch.full((8, dim), float(rank + 1), device=dev))
+  allk = torch.cat([torch.arange(8, dtype=torch.int64, device=dev) + 1000 * (r + 1) for r in range(world)])
+  up = pv.lookup(allk)
+  upsert_ok = bool((up[:, 0] == (allk // 1000).to(torch.float32)).all())
   rows, ex = pv.lookup(torch.from_numpy(hot).to(dev), return_exists=True)
   rows, ex = rows.cpu().numpy(), ex.cpu().numpy()
   exp = np.stack([par[int(kk)] for kk in hot])
@@ -81,8 +87,8 @@ def main():
   lk, _ = local.export()
   mine = bool((de.default_partition_fn(lk, world, True) == rank).all())
   ok = bool(ex.all()) and bool(np.array_equal(rows, exp)) and st["error_flags"] == 0 and st["evict_events"] > 0 and \
-      int(local.size()) <= int(slots * 0.95) and mine
-  res = {"rank": rank, "world": world, "ok": ok, "hot_found": int(ex.sum()), "hot_rows_bit_exact": bool(np.array_equal(rows, exp)),
+      int(local.size()) <= int(slots * 0.95) and mine and upsert_ok
+  res = {"rank": rank, "world": world, "ok": ok, "hot_found": int(ex.sum()), "upsert_ok": upsert_ok, "hot_rows_bit_exact": bool(np.array_equal(rows, exp)),
          "size": int(local.size()), "slots": slots, "evict_events": int(st["evict_events"]), "error_flags": int(st["error_flags"]),
          "ms_per_step": 1e3 * dt / steps}
   print(json.dumps(res), flush=True)

@@ -528,10 +528,103 @@ def test_one_sided_entry_points_refuse_shards_with_an_eviction_strategy():
   raw = np.zeros(nbytes + 256, dtype=np.uint8)
   box = raw[(-raw.ctypes.data) % 256:][:nbytes]
   ck(X().det_peer_xchg_attach(g.g, (ctypes.c_void_p * 1)(box.ctypes.data), 64, rb))
-  assert X().det_peer_xchg_insert(g.g, P(k), P(v), 4, None) == 5                   # DET_UNIMPLEMENTED
-  assert b"det_peer_xchg_apply" in L().det_last_error()
+  ck(X().det_peer_xchg_insert(g.g, P(k), P(v), 4, None))           # through the owner: compact -> the owner's scored insert
+  assert t.size() == 4
   g.close()
   t.close()
+  t = Table(dim=4, init=1024, max_capacity=1024, strategy=4, gen_scores_fn=lambda ks: ks)     # CUSTOMIZED needs scores
+  g = PeerGroup([t], None, 1, 0)
+  raw2 = np.zeros(nbytes + 256, dtype=np.uint8)
+  box2 = raw2[(-raw2.ctypes.data) % 256:][:nbytes]
+  ck(X().det_peer_xchg_attach(g.g, (ctypes.c_void_p * 1)(box2.ctypes.data), 64, rb))
+  assert X().det_peer_xchg_insert(g.g, P(k), P(v), 4, None) == 5                   # DET_UNIMPLEMENTED
+  assert b"CUSTOMIZED" in L().det_last_error()
+  g.close()
+  t.close()
+
+
+@pytest.mark.parametrize("strategy", [1, 0])          # LFU, LRU
+def test_owner_side_upsert_on_shards_that_evict(strategy):
+  """det_peer_xchg_insert on shards with an eviction strategy (3 ranks as threads, 1024 slots each): every call every
+  rank upserts the same 24 HOT keys (identical rows) plus fresh cold keys, ~3x more distinct keys than fit.  Shards stay
+  under the hard bound and evict; hot keys survive with their rows; every surviving cold key has its row; no duplicates,
+  no error flags; an empty batch on one rank is fine."""
+  world, dim, cap, steps, slots = 3, 8, 64, 70, 1024
+  rng = np.random.default_rng(900 + strategy)
+  owner_of = lambda k: O.default_partition_fn(k, world, True)
+  row_of = lambda k: np.repeat((k % 100003).astype(np.float32)[:, None], dim, axis=1)
+  hot = rng.choice(1 << 40, size=24, replace=False).astype(np.int64)
+  cold_pool = (rng.choice(1 << 40, size=world * steps * (cap - 24), replace=False).astype(np.int64) | (1 << 41))
+  tables = [Table(dim=dim, init=slots, max_capacity=slots, strategy=strategy) for _ in range(world)]
+  hb = X().det_peer_handle_bytes()
+  blob = (ctypes.c_ubyte * (hb * world))()
+  for r in range(world):
+    ck(X().det_peer_export(tables[r].h, ctypes.c_void_p(ctypes.addressof(blob) + r * hb)))
+  rb = dim * 4
+  nbytes = X().det_peer_xchg_bytes(world, cap, rb)
+  raw = [np.zeros(nbytes + 256, dtype=np.uint8) for _ in range(world)]
+  boxes = [b[(-b.ctypes.data) % 256:][:nbytes] for b in raw]
+  sched, c = [], 0
+  for t in range(steps):
+    per = []
+    for r in range(world):
+      n_cold = cap - 24
+      k = np.ascontiguousarray(np.concatenate([hot, cold_pool[c:c + n_cold]]))
+      c += n_cold
+      if t % 9 == r:
+        k = np.zeros(0, np.int64)
+      per.append((k, row_of(k)))
+    sched.append(per)
+  errors, got = [], {}
+  start = threading.Barrier(world)
+  zero = np.zeros(dim, np.float32)
+
+  def rank_main(r):
+    try:
+      tl = [None] * world
+      tl[r] = tables[r]
+      g = PeerGroup(tl, ctypes.cast(blob, ctypes.c_void_p), world, r)
+      ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boxes])
+      ck(X().det_peer_xchg_attach(g.g, ptrs, cap, rb))
+      start.wait()
+      for t in range(steps):
+        k, v = sched[t][r]
+        n = len(k)
+        ck(X().det_peer_xchg_insert(g.g, P(k) if n else None, P(v) if n else None, n, None))
+      out = np.empty((len(hot), dim), np.float32)
+      ex = np.empty(len(hot), np.uint8)
+      ck(X().det_peer_xchg_find(g.g, P(hot), len(hot), P(zero), 0, P(out), P(ex), None, None))
+      got[r] = (out, ex.astype(bool))
+      g.close()
+    except BaseException:  # pragma: no cover
+      import traceback
+      errors.append((r, traceback.format_exc()))
+      try:
+        start.abort()
+      except Exception:
+        pass
+
+  th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+  for x in th:
+    x.start()
+  for x in th:
+    x.join(timeout=1200)
+  assert not errors, errors
+  live = 0
+  for o in range(world):
+    st = tables[o].stats()
+    assert st["error_flags"] == 0 and st["evict_events"] > 0, st
+    tables[o].check()
+    ks, vs = tables[o].export()
+    live += len(ks)
+    assert len(ks) <= int(slots * 0.95) and (owner_of(ks) == o).all()
+    assert np.isin(hot[owner_of(hot) == o], ks).all()
+    np.testing.assert_array_equal(vs, row_of(ks))
+  assert c - live > 1000
+  for r in range(world):
+    out, ex = got[r]
+    assert ex.all()
+    np.testing.assert_array_equal(out, row_of(hot))
 
 
 class RegionTable(Table):

@@ -273,7 +273,8 @@ def test_shadow_variable_assign_and_verify():
 def test_peer_sharded_variable_with_an_eviction_strategy_python_path():
   """the Python glue of the sharded-table-with-eviction path (scripts/gpu_sharded_evict.py runs the same flow on a GPU):
   one fake shard with an LFU strategy behind PeerShardedVariable + the owner-side exchange; apply_gradients goes through
-  det_peer_xchg_apply_adagrad, lookups through det_peer_xchg_find, the one-sided calls are refused."""
+  det_peer_xchg_apply_adagrad, lookups through det_peer_xchg_find, upserts through the owner's scored insert; the one-sided
+  calls are refused."""
   import numpy as np
   import torch
   from recommenders_addons_b200 import dynamic_embedding as de
@@ -289,8 +290,8 @@ def test_peer_sharded_variable_with_an_eviction_strategy_python_path():
   raw = torch.zeros(nbytes + 256, dtype=torch.uint8)
   off = (-raw.data_ptr()) % 256
   pv.attach_exchange(cap, mailbox_ptrs=[raw.data_ptr() + off], keepalive=raw, insert="push")
-  with pytest.raises(DetError, match="det_peer_xchg_apply"):
-    pv.upsert(torch.arange(4), torch.zeros(4, dim))
+  pv.upsert(torch.arange(4), torch.full((4, dim), 7.0))           # through the owner: compact -> its own scored insert
+  assert bool((pv.lookup(torch.arange(4)) == 7.0).all())
   opt = de.FusedAdagrad(0.1, 0.1)
   rng = np.random.default_rng(2)
   hot = torch.from_numpy(rng.choice(1 << 40, size=20, replace=False).astype(np.int64))
