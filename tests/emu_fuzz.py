@@ -1,6 +1,6 @@
 """CPU, no GPU: randomised differential runs of the kernels written after round 1's GPU budget was spent, on the SIMT
 emulator against the oracle -- many more cases than the test suite's property tests.
-  python scripts/emu_fuzz.py [cases]      (default 400: det_segment_reduce, 250: staged segment-sum)"""
+  python tests/emu_fuzz.py [cases]      (default 400: det_segment_reduce, 250: staged segment-sum)"""
 import os
 import sys
 
